@@ -1,0 +1,345 @@
+/*
+ * ncn.h - C ABI of libncn.so: the B200-native (sm_100a) replacement for the
+ * per-step NeRF hot path of nikola3794/normal-clustering-nerf.
+ *
+ * Boundary.  The reference reaches its native code through three python
+ * extension surfaces: the `vren` pybind module (models/csrc/binding.cpp:330-350,
+ * 15 functions), tiny-cuda-nn's `Encoding`/`Network` (models/ngp_mt.py:70-155)
+ * and faiss' `Kmeans` (losses.py:86-92).  Every entry point below names the
+ * reference interface it replaces (file:line relative to the reference root).
+ *
+ * Conventions
+ *   - plain C: device pointers + sizes + a stream; no torch / C++ types.
+ *   - all pointers are DEVICE pointers unless the name ends in `_host`.
+ *   - tensors are dense row-major ("C-contiguous"), exactly the layouts the
+ *     reference's CHECK_INPUT (models/csrc/include/utils.h:4-6) enforces.
+ *   - the library owns no tensor memory: outputs and scratch are caller
+ *     allocated (sizes are given by the ncn_*_workspace_bytes helpers).
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*),
+ *     never synchronises the device, and is re-entrant per stream.
+ *   - return value: 0 = ok, <0 = argument error (NCN_E_*), >0 = cudaError_t.
+ *     ncn_error_string() renders either.
+ *   - integer / index outputs are bit-exact with the reference kernels; fp32
+ *     marching outputs are bit-exact as well (same rounding sequence, see
+ *     DESIGN.md); compositing / field outputs are within the tolerances stated
+ *     in DESIGN.md and tests/.
+ */
+#ifndef NCN_H_
+#define NCN_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NCN_VERSION 100 /* 0.1.0 */
+
+typedef void* ncn_stream_t; /* cudaStream_t */
+
+enum {
+  NCN_OK = 0,
+  NCN_E_NULL = -1,      /* a required pointer is NULL */
+  NCN_E_SIZE = -2,      /* a size / count argument is out of range */
+  NCN_E_CONFIG = -3,    /* unsupported configuration (e.g. grid_size > 1024) */
+  NCN_E_ALIGN = -4,     /* pointer alignment requirement violated */
+  NCN_E_NCCL = -5,      /* NCCL failure (see ncn_comm_last_error) */
+  NCN_E_UNSUPPORTED = -6
+};
+
+int ncn_version(void);
+const char* ncn_error_string(int code);
+/* number of SMs / compute capability of the current device (for grid sizing / checks) */
+int ncn_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ------------------------------------------------------------------------- */
+/* (1) ray / volume intersection          replaces vren.ray_aabb_intersect,  */
+/*     vren.ray_sphere_intersect  (binding.cpp:12-41, intersection.cu:25-197) */
+/* ------------------------------------------------------------------------- */
+/* rays_o, rays_d (R,3) f32; centers, half_sizes (V,3) f32;
+ * out: hit_cnt (R) i32, hits_t (R,max_hits,2) f32, hits_idx (R,max_hits) i64.
+ * Unfilled slots are -1; slots are ordered by ascending t1 exactly like the
+ * reference's torch::sort over hits_t[...,0] (-1 slots therefore sort first). */
+int ncn_ray_aabb_intersect(const float* rays_o, const float* rays_d,
+                           const float* centers, const float* half_sizes,
+                           int64_t n_rays, int64_t n_boxes, int max_hits,
+                           int32_t* hit_cnt, float* hits_t, int64_t* hits_idx,
+                           ncn_stream_t stream);
+/* radii (V) f32 */
+int ncn_ray_sphere_intersect(const float* rays_o, const float* rays_d,
+                             const float* centers, const float* radii,
+                             int64_t n_rays, int64_t n_spheres, int max_hits,
+                             int32_t* hit_cnt, float* hits_t, int64_t* hits_idx,
+                             ncn_stream_t stream);
+/* Fused fast path used by render(): one box, max_hits = 1, plus the near clamp
+ * of models/rendering.py:28 (t1 in [0,near) -> near).  hits_t (R,1,2). */
+int ncn_ray_aabb_near(const float* rays_o, const float* rays_d,
+                      const float* center, const float* half_size, float near_distance,
+                      int64_t n_rays, float* hits_t, ncn_stream_t stream);
+
+/* ------------------------------------------------------------------------- */
+/* (2) occupancy grid: Morton codes and bit packing                           */
+/*     replaces vren.morton3D / morton3D_invert / packbits                    */
+/*     (binding.cpp:44-75, raymarching.cu:35-161)                             */
+/* ------------------------------------------------------------------------- */
+int ncn_morton3d(const int32_t* coords /*(n,3)*/, int64_t n, int32_t* indices /*(n)*/,
+                 ncn_stream_t stream);
+int ncn_morton3d_invert(const int32_t* indices /*(n)*/, int64_t n, int32_t* coords /*(n,3)*/,
+                        ncn_stream_t stream);
+/* bit i of byte b = density_grid[8b+i] > threshold (LSB first); n_bytes = C*G^3/8 */
+int ncn_packbits(const float* density_grid, int64_t n_bytes, float threshold,
+                 uint8_t* density_bitfield, ncn_stream_t stream);
+/* Fused update of models/ngp_mt.py:360-367 minus the mean: grid = grid<0 ? grid :
+ * max(grid*decay, tmp).  Also accumulates sum/count of cells > 0 into
+ * stats[0] (f32 sum) / stats[1] (f32 count) which the caller zeroed. */
+int ncn_density_grid_update(float* density_grid, const float* density_tmp, int64_t n_cells,
+                            float decay, float* stats, ncn_stream_t stream);
+/* packbits with threshold = min(stats[0]/stats[1], density_threshold) read on device:
+ * removes the .item() host sync of models/ngp_mt.py:365. */
+int ncn_packbits_auto(const float* density_grid, int64_t n_bytes, const float* stats,
+                      float density_threshold, uint8_t* density_bitfield, ncn_stream_t stream);
+
+/* ------------------------------------------------------------------------- */
+/* (3) ray marching        replaces vren.raymarching_train / raymarching_test */
+/*     (binding.cpp:78-131, raymarching.cu:166-453)                           */
+/* ------------------------------------------------------------------------- */
+/* Scratch needed by ncn_march_train for n_rays rays. */
+size_t ncn_march_train_workspace_bytes(int64_t n_rays, int max_samples);
+/*
+ * Train-time march.  One DDA pass per ray (the reference does two), a
+ * scan of the per-ray counts and a coalesced warp-per-ray expansion:
+ * ray r owns rays_a row r = [r, start_idx, N_samples] with start_idx the
+ * exclusive prefix sum of N_samples in ray order - a deterministic instance of
+ * the layouts the reference's atomics can produce (raymarching.cu:237-241).
+ *
+ * hits_t (R,2) [t1,t2]; noise (R) f32 in [0,1) or NULL (=0); bitfield u8.
+ * Samples are written only while start_idx+k < capacity; counter[0] always
+ * receives the true total so the caller can detect overflow and retry with a
+ * larger arena; counter[1] = n_rays (as in the reference).
+ * out: rays_a (R,3) i64; xyzs, dirs (capacity,3) f32; deltas, ts (capacity) f32;
+ *      counter (2) i32.  Entries >= total are left untouched.
+ */
+int ncn_march_train(const float* rays_o, const float* rays_d, const float* hits_t,
+                    const uint8_t* density_bitfield, int cascades, float scale,
+                    float exp_step_factor, const float* noise, int grid_size,
+                    int max_samples, int64_t n_rays, int64_t capacity,
+                    int64_t* rays_a, float* xyzs, float* dirs, float* deltas, float* ts,
+                    int32_t* counter, void* workspace, size_t workspace_bytes,
+                    ncn_stream_t stream);
+/* The same march split at the point where the reference surface must learn the
+ * sample count on the host (custom_functions.py:91-96): _count runs the DDA and the
+ * scan (rays_a and counter are final afterwards), the caller reads counter[0],
+ * allocates exact-size arrays and calls _expand with the same workspace. */
+int ncn_march_train_count(const float* rays_o, const float* rays_d, const float* hits_t,
+                          const uint8_t* density_bitfield, int cascades, float scale,
+                          float exp_step_factor, const float* noise, int grid_size,
+                          int max_samples, int64_t n_rays, int64_t* rays_a, int32_t* counter,
+                          void* workspace, size_t workspace_bytes, ncn_stream_t stream);
+int ncn_march_train_expand(const float* rays_o, const float* rays_d, const int64_t* rays_a,
+                           float exp_step_factor, float scale, int grid_size, int max_samples,
+                           int64_t n_rays, int64_t capacity, float* xyzs, float* dirs,
+                           float* deltas, float* ts, const void* workspace,
+                           size_t workspace_bytes, ncn_stream_t stream);
+/*
+ * Test-time march: up to n_samples occupied steps per alive ray, resuming from
+ * hits_t[r][0] which is advanced in place.  Reproduces the reference's
+ * calc_dt(..., cascades) argument quirk (raymarching.cu:370,399).
+ * alive_indices (A) i64; out xyzs, dirs (A,n_samples,3), deltas, ts (A,n_samples)
+ * (padding slots are zero-filled by this call), n_eff (A) i32.
+ */
+int ncn_march_test(const float* rays_o, const float* rays_d, float* hits_t,
+                   const int64_t* alive_indices, const uint8_t* density_bitfield,
+                   int cascades, float scale, float exp_step_factor, int grid_size,
+                   int max_samples, int n_samples, int64_t n_alive,
+                   float* xyzs, float* dirs, float* deltas, float* ts, int32_t* n_eff,
+                   ncn_stream_t stream);
+
+/* ------------------------------------------------------------------------- */
+/* (4) volume compositing   replaces vren.composite_train_fw/_multi_fw,       */
+/*     composite_train_bw/_multi_bw, composite_test_fw/_multi_fw              */
+/*     (binding.cpp:134-298, volumerendering.cu:16-585)                       */
+/* ------------------------------------------------------------------------- */
+/* sigmas (N), raws (N,C), deltas, ts (N) f32, rays_a (R,3) i64.
+ * out: total_samples (R) i64, opacity, depth (R), rend (R,C), ws (N); all are
+ * fully written for the rays_a rows given (rays with 0 samples get zeros; ws
+ * beyond an early stop = 0).  `capacity` is the length of the sample arrays:
+ * a ray whose [start,start+N) range runs past it is clipped (sync-free arena
+ * mode, see ncn_march_train); pass N for exact-size arrays.  C <= 64. */
+int ncn_composite_train_fw(const float* sigmas, const float* raws, const float* deltas,
+                           const float* ts, const int64_t* rays_a, float T_threshold,
+                           int64_t n_rays, int64_t capacity, int n_channels,
+                           int64_t* total_samples, float* opacity, float* depth, float* rend,
+                           float* ws, ncn_stream_t stream);
+/* out: dL_dsigmas (N), dL_draws (N,C) fully written for the samples the rays_a rows
+ * cover.  dL_dopacity / dL_ddepth / dL_drend / dL_dws may each be NULL (= zeros). */
+int ncn_composite_train_bw(const float* dL_dopacity, const float* dL_ddepth,
+                           const float* dL_drend, const float* dL_dws,
+                           const float* sigmas, const float* raws, const float* ws,
+                           const float* deltas, const float* ts, const int64_t* rays_a,
+                           const float* opacity, const float* depth, const float* rend,
+                           float T_threshold, int64_t n_rays, int64_t capacity, int n_channels,
+                           float* dL_dsigmas, float* dL_draws, ncn_stream_t stream);
+/* sigmas, deltas, ts (A,S); raws (A,S,C); in/out alive_indices (A) i64,
+ * opacity, depth (R), rend (R,C); n_eff (A) i32.  hits_t is accepted by the
+ * reference signature but unused by its kernel (volumerendering.cu:504-550). */
+int ncn_composite_test_fw(const float* sigmas, const float* raws, const float* deltas,
+                          const float* ts, int64_t* alive_indices, float T_threshold,
+                          const int32_t* n_eff, int64_t n_alive, int n_samples, int n_channels,
+                          float* opacity, float* depth, float* rend, ncn_stream_t stream);
+
+/* ------------------------------------------------------------------------- */
+/* (5) distortion loss      replaces vren.distortion_loss_fw / _bw            */
+/*     (binding.cpp:301-327, losses.cu:7-172)                                 */
+/* ------------------------------------------------------------------------- */
+int ncn_distortion_fw(const float* ws, const float* deltas, const float* ts,
+                      const int64_t* rays_a, int64_t n_rays, int64_t n_samples,
+                      float* loss /*(R)*/, float* ws_inclusive /*(N)*/, float* wts_inclusive /*(N)*/,
+                      ncn_stream_t stream);
+int ncn_distortion_bw(const float* dL_dloss, const float* ws_inclusive, const float* wts_inclusive,
+                      const float* ws, const float* deltas, const float* ts,
+                      const int64_t* rays_a, int64_t n_rays, int64_t n_samples,
+                      float* dL_dws /*(N)*/, ncn_stream_t stream);
+
+/* segmented (CSR) row sum: replaces torch_scatter.segment_csr as used by
+ * RayMarcher.backward (models/custom_functions.py:102-112).
+ * src (N,D) f32, indptr (S+1) i64 -> out (S,D). */
+int ncn_segment_csr_sum(const float* src, const int64_t* indptr, int64_t n_segments, int dim,
+                        float* out, ncn_stream_t stream);
+
+/* ------------------------------------------------------------------------- */
+/* (6) multiresolution hash grid   replaces tcnn.Encoding (Grid/Hash/Linear)  */
+/*     call site models/ngp_mt.py:70-82; semantics: SURVEY.md Appendix B      */
+/* ------------------------------------------------------------------------- */
+#define NCN_GRID_MAX_LEVELS 32
+typedef struct ncn_grid_desc {
+  int32_t n_levels;             /* L (16)           */
+  int32_t n_features;           /* F (2; 1,2,4,8)   */
+  int32_t log2_hashmap_size;    /* log2 T (19)      */
+  int32_t base_resolution;      /* N_min (16)       */
+  float per_level_scale;        /* b                */
+  /* derived by ncn_grid_desc_init: */
+  float level_scale[NCN_GRID_MAX_LEVELS];     /* exp2f(l*log2f(b))*N_min - 1  */
+  uint32_t level_res[NCN_GRID_MAX_LEVELS];    /* ceilf(scale)+1               */
+  uint32_t level_size[NCN_GRID_MAX_LEVELS];   /* entries in the level         */
+  uint32_t level_offset[NCN_GRID_MAX_LEVELS + 1]; /* entry offset, [L] = total */
+} ncn_grid_desc;
+/* host-only helper: fill the derived fields; returns total #params = entries*F */
+int64_t ncn_grid_desc_init(ncn_grid_desc* desc);
+/* x (N,3) f32 in [0,1]; table fp16 (entries,F); out (N, L*F) fp16 (row major). */
+int ncn_grid_fwd(const ncn_grid_desc* desc_host, const float* x, const void* table_f16,
+                 int64_t n, void* out_f16, ncn_stream_t stream);
+/* dL_dy (N,L*F) fp16 -> grad_table fp32 (entries*F), ACCUMULATED (caller zeroes). */
+int ncn_grid_bwd(const ncn_grid_desc* desc_host, const float* x, const void* dL_dy_f16,
+                 int64_t n, float* grad_table_f32, float grad_scale, ncn_stream_t stream);
+/* dL_dx (N,3) f32 = d out / d x contracted with dL_dy. */
+int ncn_grid_bwd_input(const ncn_grid_desc* desc_host, const float* x, const void* table_f16,
+                       const void* dL_dy_f16, int64_t n, float* dL_dx, ncn_stream_t stream);
+/* double backward of the input gradient (tcnn bwd_bwd_input): given dL_ddLdx (N,3)
+ * accumulates into grad_table (if non-NULL) and writes dL_ddLdy (N,L*F) f16 (if non-NULL).
+ * (Linear interpolation => the second derivative wrt x itself is zero.) */
+int ncn_grid_bwd_bwd_input(const ncn_grid_desc* desc_host, const float* x, const void* table_f16,
+                           const float* dL_ddLdx, const void* dL_dy_f16, int64_t n,
+                           float* grad_table_f32, void* dL_ddLdy_f16, ncn_stream_t stream);
+
+/* ------------------------------------------------------------------------- */
+/* (7) fully fused MLPs   replaces tcnn.Network (FullyFusedMLP, width 64)     */
+/*     call sites models/ngp_mt.py:83-155                                     */
+/* ------------------------------------------------------------------------- */
+enum { NCN_ACT_NONE = 0, NCN_ACT_RELU = 1, NCN_ACT_SIGMOID = 2, NCN_ACT_EXP = 3 };
+typedef struct ncn_mlp_desc {
+  int32_t n_in;          /* logical input width (padded up to x16 with 1.0) */
+  int32_t n_out;         /* logical output width (padded up to x16)         */
+  int32_t n_hidden;      /* number of hidden layers (1 or 2..)              */
+  int32_t width;         /* 64                                              */
+  int32_t activation;    /* hidden: NCN_ACT_RELU                            */
+  int32_t out_activation;/* NCN_ACT_NONE / NCN_ACT_SIGMOID                  */
+} ncn_mlp_desc;
+int64_t ncn_mlp_n_params(const ncn_mlp_desc* d);
+size_t ncn_mlp_fwd_workspace_bytes(const ncn_mlp_desc* d, int64_t n);
+/* x (N, n_in_pad) f16, weights f16 (tcnn layout: consecutive (out,in) row-major
+ * matrices); out (N, n_out_pad) f16.  If `acts` != NULL the post-activation
+ * hidden states (n_hidden, N, width) f16 are kept for the backward pass. */
+int ncn_mlp_fwd(const ncn_mlp_desc* d, const void* x_f16, const void* w_f16, int64_t n,
+                void* out_f16, void* acts_f16, ncn_stream_t stream);
+/* dL_dout (N,n_out_pad) f16 -> grad_w f32 (ACCUMULATED), dL_dx (N,n_in_pad) f16 or NULL */
+int ncn_mlp_bwd(const ncn_mlp_desc* d, const void* x_f16, const void* w_f16,
+                const void* out_f16, const void* acts_f16, const void* dL_dout_f16, int64_t n,
+                float* grad_w_f32, void* dL_dx_f16, void* scratch, size_t scratch_bytes,
+                ncn_stream_t stream);
+
+/* ------------------------------------------------------------------------- */
+/* (8) normals from rendered depth + Manhattan clustering loss                */
+/*     replaces datasets/hypersim_src/utils.py:505-541, faiss.Kmeans          */
+/*     (losses.py:86-92) and losses.py:97-166, 441-509                        */
+/* ------------------------------------------------------------------------- */
+/* P = origin + dir*depth; n = normalize(cross(P2-P1, P3-P1)), eps 1e-12.
+ * origin/dir (R,3), depth (R), idx1/2/3 (M) i64 -> normals (M,3). */
+int ncn_normals_from_depth_fw(const float* origin, const float* dir, const float* depth,
+                              const int64_t* idx1, const int64_t* idx2, const int64_t* idx3,
+                              int64_t n_tri, float* normals, ncn_stream_t stream);
+/* dL_dnormals (M,3) -> dL_ddepth (R) ACCUMULATED via atomics (caller zeroes). */
+int ncn_normals_from_depth_bw(const float* origin, const float* dir, const float* depth,
+                              const int64_t* idx1, const int64_t* idx2, const int64_t* idx3,
+                              const float* dL_dnormals, int64_t n_tri, float* dL_ddepth,
+                              ncn_stream_t stream);
+
+typedef struct ncn_kmeans_params {
+  int32_t k;                      /* 20  (losses.py:436) */
+  int32_t niter;                  /* 20  (losses.py:437) */
+  int32_t seed;                   /* 1234 (faiss default) */
+  int32_t max_points_per_centroid;/* 256 (faiss default) */
+  int32_t spherical;              /* 1 */
+} ncn_kmeans_params;
+size_t ncn_kmeans_workspace_bytes(int64_t n_points_max, int k);
+/* Spherical k-means on the valid rows of x (M,3) (rows that are all-zero / NaN / Inf
+ * are skipped, exactly the filter of losses.py:427-430).  Single-CTA, no host sync.
+ * out: centroids (k,3) f32, assign (M) i32 (-1 for skipped rows), n_valid (1) i32. */
+int ncn_kmeans_spherical(const float* x, int64_t n_points, const ncn_kmeans_params* p,
+                         float* centroids, int32_t* assign, int32_t* n_valid,
+                         void* workspace, size_t workspace_bytes, ncn_stream_t stream);
+/* Orthogonal-triple selection + merge + opposite labelling (losses.py:97-166).
+ * labels (M) i32 in {-3..3} (0 = unused / skipped), sel (3) i32 = (c1,c2,c3). */
+int ncn_cluster_select(const float* centroids, const int32_t* assign, int64_t n_points, int k,
+                       float t_similar, int32_t* labels, int32_t* sel, ncn_stream_t stream);
+/* Loss terms of losses.py:441-478 and their gradient.
+ * out losses (3) f32 = [ort_dot, centr_dot, centr_L1] (unweighted), NaN if a cluster
+ * is empty (caller applies the reference's validity filter);
+ * stats (24) f32 scratch/outputs: per cluster count, mean, c_k. */
+int ncn_cluster_loss_fw(const float* normals, const int32_t* labels, int64_t n_points,
+                        float* losses, float* stats, ncn_stream_t stream);
+/* weights (3) f32 = dL/d[ort_dot, centr_dot, centr_L1] -> dL_dnormals (M,3) fully written */
+int ncn_cluster_loss_bw(const float* normals, const int32_t* labels, int64_t n_points,
+                        const float* stats, const float* weights_dev, float* dL_dnormals,
+                        ncn_stream_t stream);
+
+/* ------------------------------------------------------------------------- */
+/* (9) optimizer + data-parallel all-reduce  (the step either side of the path)*/
+/*     replaces apex FusedAdam (train_nerf.py:262-285) and torch DDP          */
+/*     (train_nerf.py:949-952)                                                */
+/* ------------------------------------------------------------------------- */
+/* Adam (apex FusedAdam adam_w_mode=True semantics: decoupled weight decay), fp32
+ * master params; also refreshes the fp16 copy used by the kernels and zeroes the
+ * gradient, in one pass.  grad is divided by *grad_div_dev if non-NULL
+ * (loss-scale * world-size) and the step is skipped when *skip_dev != 0. */
+int ncn_adam_step(float* param, float* grad, float* m, float* v, void* param_f16,
+                  int64_t n, float lr, float beta1, float beta2, float eps, float weight_decay,
+                  int step, const float* grad_div_dev, const int32_t* skip_dev,
+                  const float* clip_coef_dev, ncn_stream_t stream);
+/* sum of squares of grad/(div) into out[0] (ACCUMULATED), and non-finite flag into flag[0] */
+int ncn_grad_sumsq(const float* grad, int64_t n, const float* grad_div_dev,
+                   float* out, int32_t* flag, ncn_stream_t stream);
+
+typedef struct ncn_comm ncn_comm;
+/* NCCL unique id plumbing: rank 0 calls ncn_comm_unique_id (128 bytes), shares the
+ * bytes out of band (torch.distributed broadcast), every rank calls ncn_comm_init. */
+int ncn_comm_unique_id(void* id128_host);
+int ncn_comm_init(ncn_comm** comm, const void* id128_host, int world_size, int rank);
+int ncn_comm_allreduce_sum_f32(ncn_comm* comm, float* buf, int64_t n, ncn_stream_t stream);
+int ncn_comm_destroy(ncn_comm* comm);
+const char* ncn_comm_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NCN_H_ */

@@ -1,0 +1,78 @@
+"""ctypes binding of libncn.so - the C-ABI declared in include/ncn.h.
+
+There is no fallback: if the shared library is missing this module raises at import of
+the first symbol (``lib()``), and every non-zero return code becomes a RuntimeError.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libncn.so")
+_lib = None
+
+c_i64, c_i32, c_f32, c_vp, c_sz = C.c_int64, C.c_int, C.c_float, C.c_void_p, C.c_size_t
+
+# name -> (restype, argtypes); must list every function include/ncn.h declares.
+SIGNATURES = {
+    "ncn_version": (c_i32, []),
+    "ncn_error_string": (C.c_char_p, [c_i32]),
+    "ncn_device_info": (c_i32, [c_vp, c_vp, c_vp]),
+    "ncn_ray_aabb_intersect": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_i32, c_vp, c_vp, c_vp, c_vp]),
+    "ncn_ray_sphere_intersect": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_i32, c_vp, c_vp, c_vp, c_vp]),
+    "ncn_ray_aabb_near": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_f32, c_i64, c_vp, c_vp]),
+    "ncn_morton3d": (c_i32, [c_vp, c_i64, c_vp, c_vp]),
+    "ncn_morton3d_invert": (c_i32, [c_vp, c_i64, c_vp, c_vp]),
+    "ncn_packbits": (c_i32, [c_vp, c_i64, c_f32, c_vp, c_vp]),
+    "ncn_density_grid_update": (c_i32, [c_vp, c_vp, c_i64, c_f32, c_vp, c_vp]),
+    "ncn_packbits_auto": (c_i32, [c_vp, c_i64, c_vp, c_f32, c_vp, c_vp]),
+    "ncn_march_train_workspace_bytes": (c_sz, [c_i64, c_i32]),
+    "ncn_march_train": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i32, c_f32, c_f32, c_vp, c_i32, c_i32, c_i64, c_i64,
+                                c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
+    "ncn_march_train_count": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i32, c_f32, c_f32, c_vp, c_i32, c_i32, c_i64,
+                                      c_vp, c_vp, c_vp, c_sz, c_vp]),
+    "ncn_march_train_expand": (c_i32, [c_vp, c_vp, c_vp, c_f32, c_f32, c_i32, c_i32, c_i64, c_i64,
+                                       c_vp, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
+    "ncn_march_test": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_f32, c_f32, c_i32, c_i32, c_i32, c_i64,
+                               c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "ncn_composite_train_fw": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_f32, c_i64, c_i64, c_i32,
+                                       c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "ncn_composite_train_bw": (c_i32, [c_vp] * 13 + [c_f32, c_i64, c_i64, c_i32, c_vp, c_vp, c_vp]),
+    "ncn_composite_test_fw": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_f32, c_vp, c_i64, c_i32, c_i32,
+                                      c_vp, c_vp, c_vp, c_vp]),
+    "ncn_distortion_fw": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp]),
+    "ncn_distortion_bw": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_vp, c_vp]),
+    "ncn_segment_csr_sum": (c_i32, [c_vp, c_vp, c_i64, c_i32, c_vp, c_vp]),
+}
+
+
+def lib():
+    """Load libncn.so once; raise loudly if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"libncn.so not found at {LIB_PATH}: build it with "
+                "`python normal-clustering-nerf_b200/csrc/build.py` (there is no CPU / torch fallback)")
+        h = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(h, name)   # AttributeError if the .so is stale
+            fn.restype = res
+            fn.argtypes = args
+        _lib = h
+    return _lib
+
+
+def check(rc, what=""):
+    if rc != 0:
+        msg = lib().ncn_error_string(int(rc)).decode()
+        raise RuntimeError(f"{what}: {msg} (code {rc})" if what else f"{msg} (code {rc})")
+
+
+def ptr(t):
+    """Device pointer of a torch tensor (None -> NULL)."""
+    return None if t is None else t.data_ptr()
+
+
+def stream():
+    import torch
+    return torch.cuda.current_stream().cuda_stream

@@ -1,0 +1,310 @@
+// Multiresolution hash-grid encoding (tcnn "Grid"/"Hash"/"Linear", 3-D inputs).
+// Replaces tcnn.Encoding as used by models/ngp_mt.py:70-82 (semantics: SURVEY.md Appendix B;
+// tiny-cuda-nn itself is NOT in the reference tree - parity is pinned against oracle/hashgrid.py).
+//
+// Thread mapping: one thread per (sample, level) with the level index fastest, so a warp
+// covers 2 samples x 16 levels and writes 2 x 64 B = one contiguous 128 B line of the
+// (N, L*F) fp16 output; the 8 corner gathers per thread are independent 4 B (half2) loads
+// (MLP = 8) served by L1/L2 (the 21.8 MiB fp16 table at T=2^19 is L2 resident on B200).
+// Backward scatters fp32 with vector red.global.add.v2.f32 (one per corner).
+#include "ncn_common.cuh"
+#include <math.h>
+
+namespace ncn {
+
+struct GridMeta {          // per-level constants, copied to shared memory by each CTA
+  float scale[NCN_GRID_MAX_LEVELS];
+  uint32_t res[NCN_GRID_MAX_LEVELS];
+  uint32_t size[NCN_GRID_MAX_LEVELS];
+  uint32_t offset[NCN_GRID_MAX_LEVELS];
+  int32_t n_levels;
+};
+
+__device__ __forceinline__ uint32_t grid_index(uint32_t gx, uint32_t gy, uint32_t gz, uint32_t res, uint32_t size) {
+  // dense while the running stride fits in the level, else the coherent prime hash
+  uint32_t stride = 1, index = 0;
+  index += gx * stride; stride *= res;
+  if (stride <= size) { index += gy * stride; stride *= res;
+    if (stride <= size) { index += gz * stride; stride *= res; } }
+  if (size < stride) index = gx ^ (gy * 2654435761u) ^ (gz * 805459861u);
+  return index % size;
+}
+
+struct Cell8 {
+  uint32_t idx[8];
+  float w[3];       // fractional position
+};
+
+__device__ __forceinline__ void locate8(const float* __restrict__ x, int64_t n, float scale, uint32_t res, uint32_t size,
+                                        Cell8& c) {
+  uint32_t g[3];
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    const float pos = fmaf(scale, x[3 * n + d], 0.5f);
+    const float fl = floorf(pos);
+    g[d] = (uint32_t)(int)fl;
+    c.w[d] = pos - fl;
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k)
+    c.idx[k] = grid_index(g[0] + (k & 1), g[1] + ((k >> 1) & 1), g[2] + ((k >> 2) & 1), res, size);
+}
+
+__device__ __forceinline__ float corner_w(const float* w, int k) {
+  return ((k & 1) ? w[0] : 1.f - w[0]) * ((k & 2) ? w[1] : 1.f - w[1]) * ((k & 4) ? w[2] : 1.f - w[2]);
+}
+// d(corner weight)/d(w[d])
+__device__ __forceinline__ float corner_dw(const float* w, int k, int d) {
+  float r = ((k >> d) & 1) ? 1.f : -1.f;
+#pragma unroll
+  for (int e = 0; e < 3; ++e) if (e != d) r *= ((k >> e) & 1) ? w[e] : 1.f - w[e];
+  return r;
+}
+
+#define NCN_GRID_PROLOGUE                                                          \
+  __shared__ GridMeta sm;                                                          \
+  for (int i = threadIdx.x; i < (int)(sizeof(GridMeta) / 4); i += blockDim.x)     \
+    reinterpret_cast<uint32_t*>(&sm)[i] = reinterpret_cast<const uint32_t*>(&meta)[i]; \
+  __syncthreads();                                                                 \
+  const int L = sm.n_levels;                                                       \
+  const int64_t total = n * L;                                                     \
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+
+template <int F>
+__global__ void __launch_bounds__(256)
+grid_fwd_kernel(const __grid_constant__ GridMeta meta, const float* __restrict__ x, const __half* __restrict__ table,
+                int64_t n, __half* __restrict__ out) {
+  NCN_GRID_PROLOGUE
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int64_t s = i / L;
+    const int l = (int)(i - s * L);
+    Cell8 c;
+    locate8(x, s, sm.scale[l], sm.res[l], sm.size[l], c);
+    const __half* tl = table + (size_t)sm.offset[l] * F;
+    float acc[F];
+#pragma unroll
+    for (int f = 0; f < F; ++f) acc[f] = 0.f;
+    if (F == 2) {
+      __half2 v[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = __ldg(reinterpret_cast<const __half2*>(tl) + c.idx[k]);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float wk = corner_w(c.w, k);
+        const float2 f2 = __half22float2(v[k]);
+        acc[0] = fmaf(wk, f2.x, acc[0]); acc[1] = fmaf(wk, f2.y, acc[1]);
+      }
+      reinterpret_cast<__half2*>(out)[i] = __floats2half2_rn(acc[0], acc[1]);
+    } else {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float wk = corner_w(c.w, k);
+#pragma unroll
+        for (int f = 0; f < F; ++f) acc[f] = fmaf(wk, __half2float(__ldg(tl + (size_t)c.idx[k] * F + f)), acc[f]);
+      }
+#pragma unroll
+      for (int f = 0; f < F; ++f) out[i * F + f] = __float2half_rn(acc[f]);
+    }
+  }
+}
+
+template <int F>
+__global__ void __launch_bounds__(256)
+grid_bwd_kernel(const __grid_constant__ GridMeta meta, const float* __restrict__ x, const __half* __restrict__ dy,
+                int64_t n, float grad_scale, float* __restrict__ grad) {
+  NCN_GRID_PROLOGUE
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int64_t s = i / L;
+    const int l = (int)(i - s * L);
+    float g[F];
+    bool any = false;
+#pragma unroll
+    for (int f = 0; f < F; ++f) { g[f] = __half2float(dy[i * F + f]) * grad_scale; any |= (g[f] != 0.f); }
+    if (!any) continue;    // samples cut by early ray termination carry exact-zero gradients
+    Cell8 c;
+    locate8(x, s, sm.scale[l], sm.res[l], sm.size[l], c);
+    float* gl = grad + (size_t)sm.offset[l] * F;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float wk = corner_w(c.w, k);
+      if (F == 2) {
+        atomicAdd(reinterpret_cast<float2*>(gl) + c.idx[k], make_float2(wk * g[0], wk * g[1]));
+      } else {
+#pragma unroll
+        for (int f = 0; f < F; ++f) atomicAdd(gl + (size_t)c.idx[k] * F + f, wk * g[f]);
+      }
+    }
+  }
+}
+
+// dL/dx (atomically accumulated over levels into a zeroed (N,3) buffer)
+template <int F>
+__global__ void __launch_bounds__(256)
+grid_bwd_input_kernel(const __grid_constant__ GridMeta meta, const float* __restrict__ x,
+                      const __half* __restrict__ table, const __half* __restrict__ dy, int64_t n,
+                      float* __restrict__ dx) {
+  NCN_GRID_PROLOGUE
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int64_t s = i / L;
+    const int l = (int)(i - s * L);
+    Cell8 c;
+    const float scale = sm.scale[l];
+    locate8(x, s, scale, sm.res[l], sm.size[l], c);
+    const __half* tl = table + (size_t)sm.offset[l] * F;
+    float g[F];
+#pragma unroll
+    for (int f = 0; f < F; ++f) g[f] = __half2float(dy[i * F + f]);
+    float acc[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      float dot = 0.f;
+#pragma unroll
+      for (int f = 0; f < F; ++f) dot = fmaf(__half2float(__ldg(tl + (size_t)c.idx[k] * F + f)), g[f], dot);
+#pragma unroll
+      for (int d = 0; d < 3; ++d) acc[d] = fmaf(corner_dw(c.w, k, d), dot, acc[d]);
+    }
+#pragma unroll
+    for (int d = 0; d < 3; ++d) atomicAdd(dx + 3 * s + d, scale * acc[d]);
+  }
+}
+
+// double backward of the input gradient: given v = dL/d(dL/dx) (N,3)
+//   grad_table[corner] += sum_d v_d * scale * dw_corner/dw_d * dy_f
+//   dL/d(dy)_f          = sum_d v_d * scale * sum_corner dw_corner/dw_d * table[corner]_f
+template <int F>
+__global__ void __launch_bounds__(256)
+grid_bwd_bwd_input_kernel(const __grid_constant__ GridMeta meta, const float* __restrict__ x,
+                          const __half* __restrict__ table, const float* __restrict__ v,
+                          const __half* __restrict__ dy, int64_t n, float* __restrict__ grad,
+                          __half* __restrict__ ddy) {
+  NCN_GRID_PROLOGUE
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int64_t s = i / L;
+    const int l = (int)(i - s * L);
+    Cell8 c;
+    const float scale = sm.scale[l];
+    locate8(x, s, scale, sm.res[l], sm.size[l], c);
+    const float v0 = v[3 * s] * scale, v1 = v[3 * s + 1] * scale, v2 = v[3 * s + 2] * scale;
+    float g[F], o[F];
+#pragma unroll
+    for (int f = 0; f < F; ++f) { g[f] = dy ? __half2float(dy[i * F + f]) : 0.f; o[f] = 0.f; }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float coef = v0 * corner_dw(c.w, k, 0) + v1 * corner_dw(c.w, k, 1) + v2 * corner_dw(c.w, k, 2);
+#pragma unroll
+      for (int f = 0; f < F; ++f) {
+        if (grad) atomicAdd(grad + ((size_t)sm.offset[l] + c.idx[k]) * F + f, coef * g[f]);
+        if (ddy) o[f] = fmaf(coef, __half2float(__ldg(table + ((size_t)sm.offset[l] + c.idx[k]) * F + f)), o[f]);
+      }
+    }
+    if (ddy) {
+#pragma unroll
+      for (int f = 0; f < F; ++f) ddy[i * F + f] = __float2half_rn(o[f]);
+    }
+  }
+}
+
+}  // namespace ncn
+
+using namespace ncn;
+
+extern "C" int64_t ncn_grid_desc_init(ncn_grid_desc* d) {
+  if (!d || d->n_levels < 1 || d->n_levels > NCN_GRID_MAX_LEVELS) return -1;
+  if (d->n_features != 1 && d->n_features != 2 && d->n_features != 4 && d->n_features != 8) return -1;
+  if (d->log2_hashmap_size < 1 || d->log2_hashmap_size > 28 || d->base_resolution < 1) return -1;
+  const float log2b = log2f(d->per_level_scale);
+  uint32_t off = 0;
+  const uint32_t T = 1u << d->log2_hashmap_size;
+  for (int l = 0; l < d->n_levels; ++l) {
+    const float scale = exp2f((float)l * log2b) * (float)d->base_resolution - 1.0f;
+    const uint32_t res = (uint32_t)ceilf(scale) + 1u;
+    // entries of the level: res^3 rounded up to a multiple of 8, capped at T
+    const double cube = (double)res * res * res;
+    uint32_t size = cube > (double)T ? T : (uint32_t)cube;
+    size = (size + 7u) / 8u * 8u;
+    if (size > T) size = T;
+    d->level_scale[l] = scale; d->level_res[l] = res; d->level_size[l] = size; d->level_offset[l] = off;
+    off += size;
+  }
+  d->level_offset[d->n_levels] = off;
+  for (int l = d->n_levels; l < NCN_GRID_MAX_LEVELS; ++l) { d->level_scale[l] = 0; d->level_res[l] = 0; d->level_size[l] = 0; if (l > d->n_levels) d->level_offset[l] = off; }
+  return (int64_t)off * d->n_features;
+}
+
+static int to_meta(const ncn_grid_desc* d, GridMeta* m) {
+  if (!d) return NCN_E_NULL;
+  if (d->n_levels < 1 || d->n_levels > NCN_GRID_MAX_LEVELS) return NCN_E_CONFIG;
+  for (int l = 0; l < NCN_GRID_MAX_LEVELS; ++l) {
+    m->scale[l] = d->level_scale[l]; m->res[l] = d->level_res[l]; m->size[l] = d->level_size[l];
+    m->offset[l] = d->level_offset[l];
+    if (l < d->n_levels && d->level_size[l] == 0) return NCN_E_CONFIG;
+  }
+  m->n_levels = d->n_levels;
+  return NCN_OK;
+}
+
+#define NCN_GRID_DISPATCH(F, CALL)                 \
+  switch (F) {                                     \
+    case 1: { constexpr int kF = 1; CALL; } break; \
+    case 2: { constexpr int kF = 2; CALL; } break; \
+    case 4: { constexpr int kF = 4; CALL; } break; \
+    case 8: { constexpr int kF = 8; CALL; } break; \
+    default: return NCN_E_CONFIG;                  \
+  }
+
+extern "C" int ncn_grid_fwd(const ncn_grid_desc* desc, const float* x, const void* table, int64_t n, void* out,
+                            ncn_stream_t stream) {
+  GridMeta m; int rc = to_meta(desc, &m); if (rc) return rc;
+  NCN_CHECK_SIZE(n >= 0);
+  if (n == 0) return NCN_OK;
+  NCN_CHECK_PTR(x); NCN_CHECK_PTR(table); NCN_CHECK_PTR(out);
+  if (((uintptr_t)table | (uintptr_t)out) & 3) return NCN_E_ALIGN;
+  const int grid = persistent_grid(n * m.n_levels, 256, 8);
+  NCN_GRID_DISPATCH(desc->n_features, (grid_fwd_kernel<kF><<<grid, 256, 0, as_stream(stream)>>>(
+      m, x, (const __half*)table, n, (__half*)out)));
+  NCN_LAUNCH_OK();
+  return NCN_OK;
+}
+
+extern "C" int ncn_grid_bwd(const ncn_grid_desc* desc, const float* x, const void* dy, int64_t n, float* grad,
+                            float grad_scale, ncn_stream_t stream) {
+  GridMeta m; int rc = to_meta(desc, &m); if (rc) return rc;
+  NCN_CHECK_SIZE(n >= 0);
+  if (n == 0) return NCN_OK;
+  NCN_CHECK_PTR(x); NCN_CHECK_PTR(dy); NCN_CHECK_PTR(grad);
+  if ((uintptr_t)grad & 7) return NCN_E_ALIGN;
+  const int grid = persistent_grid(n * m.n_levels, 256, 8);
+  NCN_GRID_DISPATCH(desc->n_features, (grid_bwd_kernel<kF><<<grid, 256, 0, as_stream(stream)>>>(
+      m, x, (const __half*)dy, n, grad_scale, grad)));
+  NCN_LAUNCH_OK();
+  return NCN_OK;
+}
+
+extern "C" int ncn_grid_bwd_input(const ncn_grid_desc* desc, const float* x, const void* table, const void* dy,
+                                  int64_t n, float* dx, ncn_stream_t stream) {
+  GridMeta m; int rc = to_meta(desc, &m); if (rc) return rc;
+  NCN_CHECK_SIZE(n >= 0);
+  if (n == 0) return NCN_OK;
+  NCN_CHECK_PTR(x); NCN_CHECK_PTR(table); NCN_CHECK_PTR(dy); NCN_CHECK_PTR(dx);
+  NCN_CUDA(cudaMemsetAsync(dx, 0, (size_t)n * 3 * sizeof(float), as_stream(stream)));
+  const int grid = persistent_grid(n * m.n_levels, 256, 8);
+  NCN_GRID_DISPATCH(desc->n_features, (grid_bwd_input_kernel<kF><<<grid, 256, 0, as_stream(stream)>>>(
+      m, x, (const __half*)table, (const __half*)dy, n, dx)));
+  NCN_LAUNCH_OK();
+  return NCN_OK;
+}
+
+extern "C" int ncn_grid_bwd_bwd_input(const ncn_grid_desc* desc, const float* x, const void* table,
+                                      const float* dL_ddLdx, const void* dy, int64_t n, float* grad, void* ddy,
+                                      ncn_stream_t stream) {
+  GridMeta m; int rc = to_meta(desc, &m); if (rc) return rc;
+  NCN_CHECK_SIZE(n >= 0);
+  if (n == 0 || (!grad && !ddy)) return NCN_OK;
+  NCN_CHECK_PTR(x); NCN_CHECK_PTR(table); NCN_CHECK_PTR(dL_ddLdx);
+  if (grad) NCN_CHECK_PTR(dy);
+  const int grid = persistent_grid(n * m.n_levels, 256, 8);
+  NCN_GRID_DISPATCH(desc->n_features, (grid_bwd_bwd_input_kernel<kF><<<grid, 256, 0, as_stream(stream)>>>(
+      m, x, (const __half*)table, dL_ddLdx, (const __half*)dy, n, grad, (__half*)ddy)));
+  NCN_LAUNCH_OK();
+  return NCN_OK;
+}

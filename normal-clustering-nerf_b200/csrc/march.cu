@@ -1,0 +1,348 @@
+// Occupancy-grid ray marching.  Replaces raymarching.cu:166-453 of the reference
+// (vren.raymarching_train / vren.raymarching_test).
+//
+// Bit-exactness.  The DDA below reproduces the reference's fp32 rounding sequence as it
+// is actually compiled (nvcc -O2, default -fmad=true; SASS of the reference build
+// inspected, see DESIGN.md "marching arithmetic"): every operation is an explicit
+// round-to-nearest intrinsic so neither nvcc nor ptxas may re-associate or (un)fuse it:
+//   x      = fma(d, t, o)
+//   dt     = max(dt_min, min(t*exp_step_factor, dt_max)),  dt_min = sqrt3/max_samples (IEEE div),
+//            dt_max = (scale*2sqrt3)/grid_size (IEEE div)
+//   cell   = trunc(max(0, min(((fma(x, 1/mip_bound, 1))*0.5)*G, G-1)))
+//   t_face = (fma(mip_bound, fma(((cell+0.5) + 0.5*sign(d))*(1/G), 2, -1), -x)) * (1/d)
+//   skip   : t_target = t + max(0, min3(tx,ty,tz));  do t += dt(t) while (t < t_target)
+//
+// B200 design.  The reference marches every ray twice (count pass, then an atomicAdd for
+// the output slot, then a write pass) into 268 MB of zero-filled worst-case buffers.
+// Here a ray is marched ONCE: the thread records the t of each emitted sample in an
+// L2-resident scratch slab, a scan turns the per-ray counts into start offsets in RAY
+// ORDER (deterministic; one of the layouts the reference's atomics can produce), and a
+// warp-per-ray expansion writes the exact-size sample arrays with coalesced stores.
+// The DDA is an inherently serial, divergent fp32 chain (latency bound); the expansion is
+// a pure streaming pass (32 B/sample).
+#include "ncn_common.cuh"
+#include "morton.cuh"
+
+namespace ncn {
+
+struct MarchCfg {
+  int cascades, grid_size, max_samples;
+  uint32_t grid_size3;
+  float scale;             // mip_bound cap (train: scale; test: scale)
+  float exp_step_factor;
+  float dt_min, dt_max;    // calc_dt clamp bounds
+  float gs_f, gs_inv, gs_m1;
+};
+
+// calc_dt(t) - raymarching.cu:11-13 : clamp(t*f, lo, hi) = fmaxf(lo, fminf(t*f, hi))
+__device__ __forceinline__ float calc_dt(float t, const MarchCfg& c) {
+  return fmaxf(c.dt_min, fminf(__fmul_rn(t, c.exp_step_factor), c.dt_max));
+}
+
+// raymarching.cu:19-23 / 29-32
+__device__ __forceinline__ int mip_from_pos(float x, float y, float z, int cascades) {
+  const float mx = fmaxf(fabsf(x), fmaxf(fabsf(y), fabsf(z)));
+  int e; frexpf(mx, &e);
+  return min(cascades - 1, max(0, e + 1));
+}
+__device__ __forceinline__ int mip_from_dt(float dt, float gs_f, int cascades) {
+  int e; frexpf(__fmul_rn(dt, gs_f), &e);
+  return min(cascades - 1, max(0, e));
+}
+
+struct Cell { int nx, ny, nz; float mip_bound; bool occ; };
+
+__device__ __forceinline__ int cell_coord(float x, float mb_inv, const MarchCfg& c) {
+  const float v = __fmul_rn(__fmul_rn(__fmaf_rn(x, mb_inv, 1.0f), 0.5f), c.gs_f);
+  return (int)fmaxf(0.0f, fminf(v, c.gs_m1));   // clamp(v, 0, G-1) then float->int truncation
+}
+
+__device__ __forceinline__ Cell locate(float x, float y, float z, float dt, const MarchCfg& c,
+                                       const uint8_t* __restrict__ bitfield) {
+  Cell k;
+  int mip = 0;
+  if (c.cascades > 1) mip = max(mip_from_pos(x, y, z, c.cascades), mip_from_dt(dt, c.gs_f, c.cascades));
+  // scalbnf(1, mip-1): exact power of two
+  const float p2 = __int_as_float((126 + mip) << 23);
+  k.mip_bound = fminf(p2, c.scale);
+  const float mb_inv = __frcp_rn(k.mip_bound);
+  k.nx = cell_coord(x, mb_inv, c); k.ny = cell_coord(y, mb_inv, c); k.nz = cell_coord(z, mb_inv, c);
+  const uint32_t idx = (uint32_t)mip * c.grid_size3 + morton3d((uint32_t)k.nx, (uint32_t)k.ny, (uint32_t)k.nz);
+  k.occ = (__ldg(bitfield + (idx >> 3)) >> (idx & 7u)) & 1u;
+  return k;
+}
+
+__device__ __forceinline__ float face_t(int n, float sgn_half, float mip_bound, float x, float d_inv,
+                                        const MarchCfg& c) {
+  // (((n+0.5f+0.5f*sign)*grid_size_inv*2-1)*mip_bound-x)*d_inv
+  const float a = __fadd_rn(__fadd_rn((float)n, 0.5f), sgn_half);
+  const float b = __fmaf_rn(__fmul_rn(a, c.gs_inv), 2.0f, -1.0f);
+  return __fmul_rn(__fmaf_rn(mip_bound, b, -x), d_inv);
+}
+
+// advance t past the current (empty) cell in whole dt steps
+__device__ __forceinline__ float skip_cell(float t, const Cell& k, float x, float y, float z,
+                                           float sx, float sy, float sz, float ix, float iy, float iz,
+                                           const MarchCfg& c) {
+  const float tx = face_t(k.nx, sx, k.mip_bound, x, ix, c);
+  const float ty = face_t(k.ny, sy, k.mip_bound, y, iy, c);
+  const float tz = face_t(k.nz, sz, k.mip_bound, z, iz, c);
+  const float t_target = __fadd_rn(t, fmaxf(0.0f, fminf(tx, fminf(ty, tz))));
+  do { t = __fadd_rn(t, calc_dt(t, c)); } while (t < t_target);
+  return t;
+}
+
+// ---- train: pass 1 (one thread per ray): march, record sample ts, count -------------------
+__global__ void __launch_bounds__(64)
+march_train_count_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d,
+                         const float* __restrict__ hits_t, const uint8_t* __restrict__ bitfield,
+                         const float* __restrict__ noise, MarchCfg c, int64_t n_rays,
+                         int32_t* __restrict__ counts, float* __restrict__ ts_scratch) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_rays) return;
+  const float ox = rays_o[3 * r], oy = rays_o[3 * r + 1], oz = rays_o[3 * r + 2];
+  const float dx = rays_d[3 * r], dy = rays_d[3 * r + 1], dz = rays_d[3 * r + 2];
+  const float ix = __frcp_rn(dx), iy = __frcp_rn(dy), iz = __frcp_rn(dz);
+  const float sx = copysignf(0.5f, dx), sy = copysignf(0.5f, dy), sz = copysignf(0.5f, dz);
+  const float2 h = reinterpret_cast<const float2*>(hits_t)[r];
+  float t = h.x;
+  const float t2 = h.y;
+  if (t >= 0.0f && noise != nullptr) t = __fmaf_rn(calc_dt(t, c), noise[r], t);   // raymarching.cu:195-198
+  float* out = ts_scratch + r * (int64_t)c.max_samples;
+  int n = 0;
+  while (0.0f <= t && t < t2 && n < c.max_samples) {
+    const float x = __fmaf_rn(dx, t, ox), y = __fmaf_rn(dy, t, oy), z = __fmaf_rn(dz, t, oz);
+    const float dt = calc_dt(t, c);
+    const Cell k = locate(x, y, z, dt, c, bitfield);
+    if (k.occ) {
+      out[n++] = t;
+      t = __fadd_rn(t, dt);
+    } else {
+      t = skip_cell(t, k, x, y, z, sx, sy, sz, ix, iy, iz, c);
+    }
+  }
+  counts[r] = n;
+}
+
+// ---- train: pass 2 (single CTA): exclusive scan of counts -> rays_a, counter ---------------
+constexpr int kScanThreads = 1024;
+__global__ void __launch_bounds__(kScanThreads)
+march_scan_kernel(const int32_t* __restrict__ counts, int64_t n_rays, int64_t* __restrict__ rays_a,
+                  int32_t* __restrict__ counter) {
+  __shared__ int s_warp[32];
+  __shared__ int s_carry;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (threadIdx.x == 0) s_carry = 0;
+  __syncthreads();
+  for (int64_t base = 0; base < n_rays; base += kScanThreads) {
+    const int64_t r = base + threadIdx.x;
+    const int v = r < n_rays ? counts[r] : 0;
+    int incl = warp_scan_incl_i(v, lane);
+    if (lane == 31) s_warp[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+      const int w = s_warp[lane];
+      const int wi = warp_scan_incl_i(w, lane);
+      s_warp[lane] = wi - w;   // exclusive offset of each warp
+    }
+    __syncthreads();
+    const int carry = s_carry;
+    const int excl = carry + s_warp[wid] + incl - v;
+    if (r < n_rays) {
+      rays_a[3 * r + 0] = r;
+      rays_a[3 * r + 1] = excl;
+      rays_a[3 * r + 2] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x == kScanThreads - 1) s_carry = excl + v;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { counter[0] = s_carry; counter[1] = (int32_t)n_rays; }
+}
+
+// ---- train: pass 3 (one warp per ray): expand recorded ts into the sample arrays -----------
+__global__ void __launch_bounds__(256)
+march_train_expand_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d,
+                          const int64_t* __restrict__ rays_a, const float* __restrict__ ts_scratch,
+                          MarchCfg c, int64_t n_rays, int64_t capacity,
+                          float* __restrict__ xyzs, float* __restrict__ dirs,
+                          float* __restrict__ deltas, float* __restrict__ ts) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t r = warp; r < n_rays; r += n_warps) {
+    const int64_t start = rays_a[3 * r + 1];
+    const int n = (int)rays_a[3 * r + 2];
+    if (n == 0) continue;
+    const float ox = rays_o[3 * r], oy = rays_o[3 * r + 1], oz = rays_o[3 * r + 2];
+    const float dx = rays_d[3 * r], dy = rays_d[3 * r + 1], dz = rays_d[3 * r + 2];
+    const float* src = ts_scratch + r * (int64_t)c.max_samples;
+    for (int k = lane; k < n; k += 32) {
+      const int64_t s = start + k;
+      if (s >= capacity) break;
+      const float t = src[k];
+      float* p = xyzs + 3 * s;
+      p[0] = __fmaf_rn(dx, t, ox); p[1] = __fmaf_rn(dy, t, oy); p[2] = __fmaf_rn(dz, t, oz);
+      float* q = dirs + 3 * s;
+      q[0] = dx; q[1] = dy; q[2] = dz;
+      ts[s] = t;
+      deltas[s] = calc_dt(t, c);
+    }
+  }
+}
+
+// ---- test-time march (one thread per alive ray) --------------------------------------------
+__global__ void __launch_bounds__(128)
+march_test_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d,
+                  float* __restrict__ hits_t, const int64_t* __restrict__ alive,
+                  const uint8_t* __restrict__ bitfield, MarchCfg c, int n_samples, int64_t n_alive,
+                  float* __restrict__ xyzs, float* __restrict__ dirs, float* __restrict__ deltas,
+                  float* __restrict__ ts, int32_t* __restrict__ n_eff) {
+  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= n_alive) return;
+  const int64_t r = alive[n];
+  const float ox = rays_o[3 * r], oy = rays_o[3 * r + 1], oz = rays_o[3 * r + 2];
+  const float dx = rays_d[3 * r], dy = rays_d[3 * r + 1], dz = rays_d[3 * r + 2];
+  const float ix = __frcp_rn(dx), iy = __frcp_rn(dy), iz = __frcp_rn(dz);
+  const float sx = copysignf(0.5f, dx), sy = copysignf(0.5f, dy), sz = copysignf(0.5f, dz);
+  float t = hits_t[2 * r];
+  const float t2 = hits_t[2 * r + 1];
+  float* px = xyzs + n * (int64_t)n_samples * 3;
+  float* pd = dirs + n * (int64_t)n_samples * 3;
+  float* pt = ts + n * (int64_t)n_samples;
+  float* pdt = deltas + n * (int64_t)n_samples;
+  int s = 0;
+  float t_resume = t;
+  while (t < t2 && s < n_samples) {
+    const float x = __fmaf_rn(dx, t, ox), y = __fmaf_rn(dy, t, oy), z = __fmaf_rn(dz, t, oz);
+    const float dt = calc_dt(t, c);
+    const Cell k = locate(x, y, z, dt, c, bitfield);
+    if (k.occ) {
+      px[3 * s] = x; px[3 * s + 1] = y; px[3 * s + 2] = z;
+      pd[3 * s] = dx; pd[3 * s + 1] = dy; pd[3 * s + 2] = dz;
+      pt[s] = t; pdt[s] = dt;
+      t = __fadd_rn(t, dt);
+      t_resume = t;
+      ++s;
+    } else {
+      t = skip_cell(t, k, x, y, z, sx, sy, sz, ix, iy, iz, c);
+    }
+  }
+  if (s > 0) hits_t[2 * r] = t_resume;  // start of the next march (raymarching.cu:390)
+  n_eff[n] = s;
+  for (int j = s; j < n_samples; ++j) {   // padding slots read as zeros (torch::zeros in the reference)
+    px[3 * j] = 0.f; px[3 * j + 1] = 0.f; px[3 * j + 2] = 0.f;
+    pd[3 * j] = 0.f; pd[3 * j + 1] = 0.f; pd[3 * j + 2] = 0.f;
+    pt[j] = 0.f; pdt[j] = 0.f;
+  }
+}
+
+}  // namespace ncn
+
+using namespace ncn;
+
+static int make_cfg(MarchCfg* c, int cascades, float scale, float dt_scale, float exp_step_factor,
+                    int grid_size, int max_samples) {
+  if (cascades < 1 || cascades > 8) return NCN_E_CONFIG;
+  if (grid_size < 2 || grid_size > 1024) return NCN_E_CONFIG;
+  if (max_samples < 1) return NCN_E_CONFIG;
+  c->cascades = cascades; c->grid_size = grid_size; c->max_samples = max_samples;
+  c->grid_size3 = (uint32_t)grid_size * grid_size * grid_size;
+  c->scale = scale; c->exp_step_factor = exp_step_factor;
+  // host IEEE single division == div.rn.f32
+  c->dt_min = 1.73205080757f / (float)max_samples;
+  volatile float two_sqrt3_scale = dt_scale * 3.4641015529632568359f;   // (SQRT3*2 folded)*scale
+  c->dt_max = two_sqrt3_scale / (float)grid_size;
+  c->gs_f = (float)grid_size; c->gs_inv = 1.0f / (float)grid_size; c->gs_m1 = (float)grid_size - 1.0f;
+  return NCN_OK;
+}
+
+static inline size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+
+extern "C" size_t ncn_march_train_workspace_bytes(int64_t n_rays, int max_samples) {
+  if (n_rays < 0 || max_samples < 1) return 0;
+  return align256((size_t)n_rays * sizeof(int32_t)) + align256((size_t)n_rays * (size_t)max_samples * sizeof(float));
+}
+
+extern "C" int ncn_march_train_count(const float* rays_o, const float* rays_d, const float* hits_t,
+                                     const uint8_t* density_bitfield, int cascades, float scale,
+                                     float exp_step_factor, const float* noise, int grid_size, int max_samples,
+                                     int64_t n_rays, int64_t* rays_a, int32_t* counter, void* workspace,
+                                     size_t workspace_bytes, ncn_stream_t stream) {
+  MarchCfg c;
+  int rc = make_cfg(&c, cascades, scale, scale, exp_step_factor, grid_size, max_samples);
+  if (rc) return rc;
+  NCN_CHECK_SIZE(n_rays >= 0 && n_rays < (int64_t)1 << 31);
+  NCN_CHECK_PTR(counter);
+  if (n_rays > 0) {
+    NCN_CHECK_PTR(rays_o); NCN_CHECK_PTR(rays_d); NCN_CHECK_PTR(hits_t); NCN_CHECK_PTR(density_bitfield);
+    NCN_CHECK_PTR(rays_a); NCN_CHECK_PTR(workspace);
+    if (workspace_bytes < ncn_march_train_workspace_bytes(n_rays, max_samples)) return NCN_E_SIZE;
+    if (((uintptr_t)hits_t & 7) || ((uintptr_t)workspace & 255)) return NCN_E_ALIGN;
+    int32_t* counts = (int32_t*)workspace;
+    float* ts_scratch = (float*)((char*)workspace + align256((size_t)n_rays * sizeof(int32_t)));
+    const int threads = 64;
+    march_train_count_kernel<<<(unsigned)ceil_div(n_rays, threads), threads, 0, as_stream(stream)>>>(
+        rays_o, rays_d, hits_t, density_bitfield, noise, c, n_rays, counts, ts_scratch);
+    NCN_LAUNCH_OK();
+    march_scan_kernel<<<1, kScanThreads, 0, as_stream(stream)>>>(counts, n_rays, rays_a, counter);
+  } else {
+    march_scan_kernel<<<1, kScanThreads, 0, as_stream(stream)>>>(nullptr, 0, rays_a, counter);
+  }
+  NCN_LAUNCH_OK();
+  return NCN_OK;
+}
+
+extern "C" int ncn_march_train_expand(const float* rays_o, const float* rays_d, const int64_t* rays_a,
+                                      float exp_step_factor, float scale, int grid_size, int max_samples,
+                                      int64_t n_rays, int64_t capacity, float* xyzs, float* dirs, float* deltas,
+                                      float* ts, const void* workspace, size_t workspace_bytes,
+                                      ncn_stream_t stream) {
+  MarchCfg c;
+  int rc = make_cfg(&c, 1, scale, scale, exp_step_factor, grid_size, max_samples);
+  if (rc) return rc;
+  NCN_CHECK_SIZE(n_rays >= 0 && capacity >= 0);
+  if (n_rays == 0 || capacity == 0) return NCN_OK;
+  NCN_CHECK_PTR(rays_o); NCN_CHECK_PTR(rays_d); NCN_CHECK_PTR(rays_a); NCN_CHECK_PTR(workspace);
+  NCN_CHECK_PTR(xyzs); NCN_CHECK_PTR(dirs); NCN_CHECK_PTR(deltas); NCN_CHECK_PTR(ts);
+  if (workspace_bytes < ncn_march_train_workspace_bytes(n_rays, max_samples)) return NCN_E_SIZE;
+  const float* ts_scratch = (const float*)((const char*)workspace + align256((size_t)n_rays * sizeof(int32_t)));
+  const int grid = persistent_grid(n_rays * 32, 256, 8);
+  march_train_expand_kernel<<<grid, 256, 0, as_stream(stream)>>>(rays_o, rays_d, rays_a, ts_scratch, c, n_rays,
+                                                                 capacity, xyzs, dirs, deltas, ts);
+  NCN_LAUNCH_OK();
+  return NCN_OK;
+}
+
+extern "C" int ncn_march_train(const float* rays_o, const float* rays_d, const float* hits_t,
+                               const uint8_t* density_bitfield, int cascades, float scale, float exp_step_factor,
+                               const float* noise, int grid_size, int max_samples, int64_t n_rays, int64_t capacity,
+                               int64_t* rays_a, float* xyzs, float* dirs, float* deltas, float* ts,
+                               int32_t* counter, void* workspace, size_t workspace_bytes, ncn_stream_t stream) {
+  int rc = ncn_march_train_count(rays_o, rays_d, hits_t, density_bitfield, cascades, scale, exp_step_factor, noise,
+                                 grid_size, max_samples, n_rays, rays_a, counter, workspace, workspace_bytes, stream);
+  if (rc) return rc;
+  return ncn_march_train_expand(rays_o, rays_d, rays_a, exp_step_factor, scale, grid_size, max_samples, n_rays,
+                                capacity, xyzs, dirs, deltas, ts, workspace, workspace_bytes, stream);
+}
+
+extern "C" int ncn_march_test(const float* rays_o, const float* rays_d, float* hits_t,
+                              const int64_t* alive_indices, const uint8_t* density_bitfield, int cascades,
+                              float scale, float exp_step_factor, int grid_size, int max_samples, int n_samples,
+                              int64_t n_alive, float* xyzs, float* dirs, float* deltas, float* ts, int32_t* n_eff,
+                              ncn_stream_t stream) {
+  MarchCfg c;
+  // the reference passes `cascades` where calc_dt expects `scale` (raymarching.cu:370,399)
+  int rc = make_cfg(&c, cascades, scale, (float)cascades, exp_step_factor, grid_size, max_samples);
+  if (rc) return rc;
+  NCN_CHECK_SIZE(n_alive >= 0 && n_samples >= 1);
+  if (n_alive == 0) return NCN_OK;
+  NCN_CHECK_PTR(rays_o); NCN_CHECK_PTR(rays_d); NCN_CHECK_PTR(hits_t); NCN_CHECK_PTR(alive_indices);
+  NCN_CHECK_PTR(density_bitfield); NCN_CHECK_PTR(xyzs); NCN_CHECK_PTR(dirs); NCN_CHECK_PTR(deltas);
+  NCN_CHECK_PTR(ts); NCN_CHECK_PTR(n_eff);
+  const int threads = 128;
+  march_test_kernel<<<(unsigned)ceil_div(n_alive, threads), threads, 0, as_stream(stream)>>>(
+      rays_o, rays_d, hits_t, alive_indices, density_bitfield, c, n_samples, n_alive, xyzs, dirs, deltas, ts, n_eff);
+  NCN_LAUNCH_OK();
+  return NCN_OK;
+}

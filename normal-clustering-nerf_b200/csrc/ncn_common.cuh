@@ -1,0 +1,62 @@
+// Shared helpers for libncn.so (sm_100a).  Compiled with -fmad=false: every fused
+// multiply-add in this library is written out (__fmaf_rn / fmaf) so the fp32
+// rounding sequence of the bit-exact kernels is fixed in the source, not chosen
+// by the compiler.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+#include "../../include/ncn.h"
+
+#define NCN_CHECK_PTR(p) do { if ((p) == nullptr) return NCN_E_NULL; } while (0)
+#define NCN_CHECK_SIZE(c) do { if (!(c)) return NCN_E_SIZE; } while (0)
+#define NCN_LAUNCH_OK() do { cudaError_t e__ = cudaGetLastError(); if (e__ != cudaSuccess) return (int)e__; } while (0)
+#define NCN_CUDA(x) do { cudaError_t e__ = (x); if (e__ != cudaSuccess) return (int)e__; } while (0)
+
+namespace ncn {
+
+constexpr int kWarp = 32;
+constexpr float kSqrt3 = 1.73205080757f;  // raymarching.cu:4
+
+static inline cudaStream_t as_stream(ncn_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+
+// SM count of the current device, cached per device.
+int sm_count();
+
+static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// grid for a grid-stride kernel: enough CTAs for `n` items but at most `waves`
+// resident waves of the 148-SM part (blocks_per_sm resident CTAs each).
+static inline int persistent_grid(int64_t n, int threads, int blocks_per_sm) {
+  int64_t need = ceil_div(n > 0 ? n : 1, threads);
+  int64_t cap = (int64_t)sm_count() * blocks_per_sm;
+  return (int)(need < cap ? need : cap);
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ int warp_sum_i(int v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+// inclusive warp prefix sum
+__device__ __forceinline__ int warp_scan_incl_i(int v, int lane) {
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int t = __shfl_up_sync(0xffffffffu, v, o);
+    if (lane >= o) v += t;
+  }
+  return v;
+}
+
+__device__ __forceinline__ float clampf(float v, float lo, float hi) { return fminf(fmaxf(v, lo), hi); }
+
+// streaming (read-once) loads / (write-once) stores
+__device__ __forceinline__ float ld_stream(const float* p) { return __ldcs(p); }
+__device__ __forceinline__ void st_stream(float* p, float v) { __stcs(p, v); }
+
+}  // namespace ncn
