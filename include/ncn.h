@@ -256,17 +256,20 @@ typedef struct ncn_mlp_desc {
   int32_t out_activation;/* NCN_ACT_NONE / NCN_ACT_SIGMOID                  */
 } ncn_mlp_desc;
 int64_t ncn_mlp_n_params(const ncn_mlp_desc* d);
-size_t ncn_mlp_fwd_workspace_bytes(const ncn_mlp_desc* d, int64_t n);
+size_t ncn_mlp_bwd_workspace_bytes(const ncn_mlp_desc* d, int64_t n);
 /* x (N, n_in_pad) f16, weights f16 (tcnn layout: consecutive (out,in) row-major
- * matrices); out (N, n_out_pad) f16.  If `acts` != NULL the post-activation
- * hidden states (n_hidden, N, width) f16 are kept for the backward pass. */
+ * matrices: (64,in_pad), (n_hidden-1) x (64,64), (out_pad,64)); out (N, n_out_pad) f16.
+ * If `acts` != NULL the post-activation hidden states (n_hidden, N, 64) f16 are kept
+ * for the backward pass.  Padded dims are multiples of 16 and <= 64. */
 int ncn_mlp_fwd(const ncn_mlp_desc* d, const void* x_f16, const void* w_f16, int64_t n,
                 void* out_f16, void* acts_f16, ncn_stream_t stream);
-/* dL_dout (N,n_out_pad) f16 -> grad_w f32 (ACCUMULATED), dL_dx (N,n_in_pad) f16 or NULL */
+/* dL_dout (N,n_out_pad) f16 -> grad_w f32 += grad_scale * dL/dW (ACCUMULATED; may be
+ * NULL), dL_dx (N,n_in_pad) f16 or NULL (in the units of dL_dout, not scaled).
+ * scratch: ncn_mlp_bwd_workspace_bytes(d, n) bytes, 16 B aligned. */
 int ncn_mlp_bwd(const ncn_mlp_desc* d, const void* x_f16, const void* w_f16,
                 const void* out_f16, const void* acts_f16, const void* dL_dout_f16, int64_t n,
-                float* grad_w_f32, void* dL_dx_f16, void* scratch, size_t scratch_bytes,
-                ncn_stream_t stream);
+                float* grad_w_f32, void* dL_dx_f16, float grad_scale, void* scratch,
+                size_t scratch_bytes, ncn_stream_t stream);
 
 /* ------------------------------------------------------------------------- */
 /* (8) normals from rendered depth + Manhattan clustering loss                */

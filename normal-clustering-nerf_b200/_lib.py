@@ -76,3 +76,35 @@ def ptr(t):
 def stream():
     import torch
     return torch.cuda.current_stream().cuda_stream
+
+
+# ----------------------------------------------------------------------------- structs (include/ncn.h)
+NCN_GRID_MAX_LEVELS = 32
+
+
+class GridDesc(C.Structure):
+    _fields_ = [("n_levels", C.c_int32), ("n_features", C.c_int32), ("log2_hashmap_size", C.c_int32),
+                ("base_resolution", C.c_int32), ("per_level_scale", C.c_float),
+                ("level_scale", C.c_float * NCN_GRID_MAX_LEVELS), ("level_res", C.c_uint32 * NCN_GRID_MAX_LEVELS),
+                ("level_size", C.c_uint32 * NCN_GRID_MAX_LEVELS),
+                ("level_offset", C.c_uint32 * (NCN_GRID_MAX_LEVELS + 1))]
+
+
+class MlpDesc(C.Structure):
+    _fields_ = [("n_in", C.c_int32), ("n_out", C.c_int32), ("n_hidden", C.c_int32), ("width", C.c_int32),
+                ("activation", C.c_int32), ("out_activation", C.c_int32)]
+
+
+ACT = {"None": 0, "ReLU": 1, "Sigmoid": 2, "Exponential": 3}
+
+SIGNATURES.update({
+    "ncn_grid_desc_init": (c_i64, [C.POINTER(GridDesc)]),
+    "ncn_grid_fwd": (c_i32, [C.POINTER(GridDesc), c_vp, c_vp, c_i64, c_vp, c_vp]),
+    "ncn_grid_bwd": (c_i32, [C.POINTER(GridDesc), c_vp, c_vp, c_i64, c_vp, c_f32, c_vp]),
+    "ncn_grid_bwd_input": (c_i32, [C.POINTER(GridDesc), c_vp, c_vp, c_vp, c_i64, c_vp, c_vp]),
+    "ncn_grid_bwd_bwd_input": (c_i32, [C.POINTER(GridDesc), c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp]),
+    "ncn_mlp_n_params": (c_i64, [C.POINTER(MlpDesc)]),
+    "ncn_mlp_bwd_workspace_bytes": (c_sz, [C.POINTER(MlpDesc), c_i64]),
+    "ncn_mlp_fwd": (c_i32, [C.POINTER(MlpDesc), c_vp, c_vp, c_i64, c_vp, c_vp, c_vp]),
+    "ncn_mlp_bwd": (c_i32, [C.POINTER(MlpDesc), c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_f32, c_vp, c_sz, c_vp]),
+})

@@ -212,11 +212,15 @@ extern "C" int64_t ncn_grid_desc_init(ncn_grid_desc* d) {
   if (!d || d->n_levels < 1 || d->n_levels > NCN_GRID_MAX_LEVELS) return -1;
   if (d->n_features != 1 && d->n_features != 2 && d->n_features != 4 && d->n_features != 8) return -1;
   if (d->log2_hashmap_size < 1 || d->log2_hashmap_size > 28 || d->base_resolution < 1) return -1;
-  const float log2b = log2f(d->per_level_scale);
+  // tcnn evaluates log2f / exp2f in fp32; libm implementations may differ in the last ulp between
+  // hosts, so both are evaluated in double and rounded once (== the correctly rounded fp32 result).
+  const float log2b = (float)log2((double)d->per_level_scale);
   uint32_t off = 0;
   const uint32_t T = 1u << d->log2_hashmap_size;
   for (int l = 0; l < d->n_levels; ++l) {
-    const float scale = exp2f((float)l * log2b) * (float)d->base_resolution - 1.0f;
+    const float p2 = (float)exp2((double)((float)l * log2b));
+    volatile float scaled = p2 * (float)d->base_resolution;
+    const float scale = scaled - 1.0f;
     const uint32_t res = (uint32_t)ceilf(scale) + 1u;
     // entries of the level: res^3 rounded up to a multiple of 8, capped at T
     const double cube = (double)res * res * res;

@@ -1,0 +1,132 @@
+"""GPU parity of the tcnn drop-ins (hash-grid Encoding, fused MLP Network) against the torch
+restatements in oracle/ (tcnn itself is absent: parity unpinned, see oracle/hashgrid.py).
+
+Tolerances: features / MLP outputs are fp16 -> |err| <= 2e-3*scale + rtol 1e-2;
+gradients are compared with autograd through the fp32/fp64 restatement on identical fp16-rounded
+parameters, rtol 2e-2 of the gradient scale (fp16 dL/dy with loss scale 128)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+CFG = dict(otype="Grid", type="Hash", n_levels=16, n_features_per_level=2, log2_hashmap_size=19,
+           base_resolution=16, per_level_scale=float(np.exp(np.log(2048 * 0.5 / 16) / 15)), interpolation="Linear")
+
+
+def _enc(log2_T=19, std=0.05, seed=0):
+    from ncn_b200 import tinycudann as tcnn
+    cfg = dict(CFG, log2_hashmap_size=log2_T)
+    enc = tcnn.Encoding(3, cfg).cuda()
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    with torch.no_grad():
+        enc.params.copy_((torch.randn(enc.params.numel(), device="cuda", generator=g) * std).half().float())
+    return enc, cfg
+
+
+def _levels(cfg, enc=None):
+    """oracle level table; must equal the library's (ncn_grid_desc_init) bit for bit"""
+    from oracle import hashgrid
+    levels, total = hashgrid.grid_levels(cfg["n_levels"], cfg["n_features_per_level"], cfg["log2_hashmap_size"],
+                                         cfg["base_resolution"], cfg["per_level_scale"])
+    if enc is not None:
+        for a, b in zip(levels, enc.level_table()):
+            assert a["res"] == b["res"] and a["size"] == b["size"] and a["offset"] == b["offset"]
+            assert np.float32(a["scale"]) == np.float32(b["scale"]), (a, b)
+    return levels, total
+
+
+@pytest.mark.parametrize("log2_T,n", [(19, 100000), (14, 4099), (22, 65536), (19, 1)])
+def test_grid_forward(ncn, log2_T, n):
+    from oracle import hashgrid
+    enc, cfg = _enc(log2_T)
+    levels, total = _levels(cfg, enc)
+    assert total * 2 == enc.params.numel()
+    g = torch.Generator(device="cuda").manual_seed(1)
+    x = torch.rand(n, 3, device="cuda", generator=g)
+    if n > 16:
+        x[:8] = torch.tensor([[0, 0, 0], [1, 1, 1], [0, 1, 0], [1, 0, 0], [0.5, 0.5, 0.5], [1, 1, 0], [0, 0, 1], [0.25, 1, 0.75]], device="cuda")
+    out = enc(x)
+    assert out.dtype == torch.float16 and out.shape == (n, 32)
+    ref = hashgrid.forward(x, enc.params.detach().view(-1, 2), levels, out_dtype=None)
+    err = (out.float() - ref).abs()
+    assert err.max() <= 2e-3 * ref.abs().max() + 1e-2 * 0, f"max err {err.max()} vs scale {ref.abs().max()}"
+
+
+def test_grid_backward_params_and_input(ncn):
+    from oracle import hashgrid
+    enc, cfg = _enc(15)
+    levels, _ = _levels(cfg, enc)
+    g = torch.Generator(device="cuda").manual_seed(2)
+    n = 20000
+    x = torch.rand(n, 3, device="cuda", generator=g).requires_grad_(True)
+    dy = torch.randn(n, 32, device="cuda", generator=g)
+    out = enc(x)
+    (out.float() * dy).sum().backward()
+    gp, gx = enc.params.grad.clone(), x.grad.clone()
+    xr = x.detach().clone().requires_grad_(True)
+    tab = enc.params.detach().clone().view(-1, 2).requires_grad_(True)
+    ref = hashgrid.forward(xr, tab, levels, out_dtype=None)
+    (ref * dy.half().float()).sum().backward()
+    sp = tab.grad.abs().max()
+    assert (gp.view(-1, 2) - tab.grad).abs().max() <= 2e-2 * sp
+    sx = xr.grad.abs().max()
+    assert (gx - xr.grad).abs().max() <= 2e-2 * sx
+
+
+def test_grid_double_backward(ncn):
+    """d/d(dy) and d/d(params) of <dL/dx, v> (the path a density-gradient normal would use)."""
+    from oracle import hashgrid
+    enc, cfg = _enc(14, std=0.5)
+    levels, _ = _levels(cfg, enc)
+    g = torch.Generator(device="cuda").manual_seed(3)
+    n = 3000
+    x = torch.rand(n, 3, device="cuda", generator=g).requires_grad_(True)
+    proj = torch.randn(32, device="cuda", generator=g)
+    v = torch.randn(n, 3, device="cuda", generator=g)
+    out = enc(x)
+    s = (out.float() * proj).sum()
+    (dx,) = torch.autograd.grad(s, x, create_graph=True)
+    enc.params.grad = None
+    (dx * v).sum().backward()
+    gp = enc.params.grad.clone()
+    xr = x.detach().clone().requires_grad_(True)
+    tab = enc.params.detach().clone().view(-1, 2).requires_grad_(True)
+    ref = hashgrid.forward(xr, tab, levels, out_dtype=None)
+    (dxr,) = torch.autograd.grad((ref * proj).sum(), xr, create_graph=True)
+    torch.testing.assert_close(dx.detach(), dxr.detach(), rtol=2e-2, atol=2e-2 * float(dxr.abs().max()))
+    (dxr * v).sum().backward()
+    assert (gp.view(-1, 2) - tab.grad).abs().max() <= 2e-2 * tab.grad.abs().max()
+
+
+NETS = [(32, 16, 1, "None"), (19, 3, 2, "Sigmoid"), (16, 3, 2, "None"), (16, 40, 2, "None"), (1, 1, 1, "Sigmoid")]
+
+
+@pytest.mark.parametrize("n_in,n_out,n_hidden,act", NETS)
+@pytest.mark.parametrize("n", [1, 100, 16384 + 5])
+def test_mlp_forward_backward(ncn, n_in, n_out, n_hidden, act, n):
+    from ncn_b200 import tinycudann as tcnn
+    from oracle import mlp
+    net = tcnn.Network(n_in, n_out, dict(otype="FullyFusedMLP", activation="ReLU", output_activation=act,
+                                         n_neurons=64, n_hidden_layers=n_hidden)).cuda()
+    with torch.no_grad():
+        net.params.copy_(net.params.half().float())
+    g = torch.Generator(device="cuda").manual_seed(n)
+    x = (torch.randn(n, n_in, device="cuda", generator=g)).half().float().requires_grad_(True)
+    out = net(x)
+    assert out.dtype == torch.float16 and out.shape == (n, n_out)
+    ref = mlp.forward(x.detach(), net.params.detach(), n_in, n_out, n_hidden, act)
+    torch.testing.assert_close(out.float(), ref.float(), rtol=1e-2, atol=2e-3)
+    dy = torch.randn(n, n_out, device="cuda", generator=g)
+    (out.float() * dy).sum().backward()
+    gp, gx = net.params.grad.clone(), x.grad.clone()
+    xr = x.detach().clone().requires_grad_(True)
+    pr = net.params.detach().clone().requires_grad_(True)
+    # fp32 autograd through the restatement evaluated at the SAME fp16-rounded hidden states
+    refo = mlp.forward(xr, pr, n_in, n_out, n_hidden, act, emulate_half=False)
+    (refo * dy.half().float()).sum().backward()
+    # fp16 hidden states: a ReLU whose pre-activation is within fp16 rounding of 0 may gate differently
+    # than the fp32 restatement for a few rows -> bound the Frobenius error tightly, the max error loosely
+    for got, want in ((gx, xr.grad), (gp, pr.grad)):
+        assert (got - want).norm() <= 1e-2 * want.norm() + 1e-5
+        assert (got - want).abs().max() <= 8e-2 * want.abs().max() + 1e-4
