@@ -308,13 +308,25 @@ int ncn_cluster_select(const float* centroids, const int32_t* assign, int64_t n_
 /* Loss terms of losses.py:441-478 and their gradient.
  * out losses (3) f32 = [ort_dot, centr_dot, centr_L1] (unweighted), NaN if a cluster
  * is empty (caller applies the reference's validity filter);
- * stats (24) f32 scratch/outputs: per cluster count, mean, c_k. */
+ * stats (32) f32: per cluster k at [8k..8k+7] = count, c_k (3), |mean|, sum sign(n-c_k) (3);
+ * [24..26] = the three losses, [27] = 1 if all three clusters are non-empty. */
 int ncn_cluster_loss_fw(const float* normals, const int32_t* labels, int64_t n_points,
                         float* losses, float* stats, ncn_stream_t stream);
 /* weights (3) f32 = dL/d[ort_dot, centr_dot, centr_L1] -> dL_dnormals (M,3) fully written */
 int ncn_cluster_loss_bw(const float* normals, const int32_t* labels, int64_t n_points,
                         const float* stats, const float* weights_dev, float* dL_dnormals,
                         ncn_stream_t stream);
+
+/* Photometric terms fused with the background composite (rendering.py:231-241,
+ * losses.py:347-361): rgb = rend[:, :3] + bg*(1-opacity); sums[0] += sum((rgb-target)^2),
+ * sums[1] += sum(-(o+1e-10)log(o+1e-10)) (caller zeroes sums; means = /3R and /R).
+ * Writes (not accumulates) dL_drend (R,C) and dL_dopacity (R) of
+ *   grad_scale * ( mean((rgb-target)^2) + opacity_w * mean(entropy) );  either may be NULL.
+ * bg_rgb_host: 3 floats on the HOST.  rgb_out (R,3) may be NULL. */
+int ncn_photometric_loss(const float* rend, const float* opacity, const float* target_rgb,
+                         int64_t n_rays, int n_channels, const float* bg_rgb_host,
+                         float opacity_w, float grad_scale, float* rgb_out, float* sums,
+                         float* dL_drend, float* dL_dopacity, ncn_stream_t stream);
 
 /* ------------------------------------------------------------------------- */
 /* (9) optimizer + data-parallel all-reduce  (the step either side of the path)*/
@@ -332,6 +344,8 @@ int ncn_adam_step(float* param, float* grad, float* m, float* v, void* param_f16
 /* sum of squares of grad/(div) into out[0] (ACCUMULATED), and non-finite flag into flag[0] */
 int ncn_grad_sumsq(const float* grad, int64_t n, const float* grad_div_dev,
                    float* out, int32_t* flag, ncn_stream_t stream);
+/* coef[0] = min(1, max_norm / (sqrt(sumsq[0]) + 1e-6))  (torch clip_grad_norm_), on device */
+int ncn_clip_coef(const float* sumsq_dev, float max_norm, float* coef_dev, ncn_stream_t stream);
 
 typedef struct ncn_comm ncn_comm;
 /* NCCL unique id plumbing: rank 0 calls ncn_comm_unique_id (128 bytes), shares the

@@ -108,3 +108,28 @@ SIGNATURES.update({
     "ncn_mlp_fwd": (c_i32, [C.POINTER(MlpDesc), c_vp, c_vp, c_i64, c_vp, c_vp, c_vp]),
     "ncn_mlp_bwd": (c_i32, [C.POINTER(MlpDesc), c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_f32, c_vp, c_sz, c_vp]),
 })
+
+
+class KmeansParams(C.Structure):
+    _fields_ = [("k", C.c_int32), ("niter", C.c_int32), ("seed", C.c_int32),
+                ("max_points_per_centroid", C.c_int32), ("spherical", C.c_int32)]
+
+
+SIGNATURES.update({
+    "ncn_normals_from_depth_fw": (c_i32, [c_vp] * 6 + [c_i64, c_vp, c_vp]),
+    "ncn_normals_from_depth_bw": (c_i32, [c_vp] * 7 + [c_i64, c_vp, c_vp]),
+    "ncn_kmeans_workspace_bytes": (c_sz, [c_i64, c_i32]),
+    "ncn_kmeans_spherical": (c_i32, [c_vp, c_i64, C.POINTER(KmeansParams), c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
+    "ncn_cluster_select": (c_i32, [c_vp, c_vp, c_i64, c_i32, c_f32, c_vp, c_vp, c_vp]),
+    "ncn_cluster_loss_fw": (c_i32, [c_vp, c_vp, c_i64, c_vp, c_vp, c_vp]),
+    "ncn_cluster_loss_bw": (c_i32, [c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp]),
+    "ncn_photometric_loss": (c_i32, [c_vp, c_vp, c_vp, c_i64, c_i32, C.POINTER(c_f32), c_f32, c_f32, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "ncn_adam_step": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_f32, c_f32, c_f32, c_f32, c_f32, c_i32, c_vp, c_vp, c_vp, c_vp]),
+    "ncn_grad_sumsq": (c_i32, [c_vp, c_i64, c_vp, c_vp, c_vp, c_vp]),
+    "ncn_clip_coef": (c_i32, [c_vp, c_f32, c_vp, c_vp]),
+    "ncn_comm_unique_id": (c_i32, [c_vp]),
+    "ncn_comm_init": (c_i32, [C.POINTER(c_vp), c_vp, c_i32, c_i32]),
+    "ncn_comm_allreduce_sum_f32": (c_i32, [c_vp, c_vp, c_i64, c_vp]),
+    "ncn_comm_destroy": (c_i32, [c_vp]),
+    "ncn_comm_last_error": (C.c_char_p, []),
+})

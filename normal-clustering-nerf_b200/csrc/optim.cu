@@ -1,0 +1,142 @@
+// Optimizer tail of the training step: the dense per-parameter passes that, at T=2^19,
+// move more bytes per step than all per-sample traffic.
+// Replaces apex FusedAdam (adam_w_mode, train_nerf.py:262-285: eps 1e-15, weight decay 0 for
+// the hash table / 1e-6 for the MLPs), GradScaler.unscale_, clip_grad_norm_(0.05)
+// (train_nerf.py:954-955, opt.py:159) and the per-call fp32->fp16 parameter cast of the tcnn
+// binding - fused into ONE streaming pass: read p, g, m, v (16 B) - write p, m, v, g=0, p16 (18 B).
+#include "ncn_common.cuh"
+
+namespace ncn {
+
+struct AdamArgs {
+  float lr, beta1, beta2, eps, weight_decay, bc1, bc2;
+};
+
+__device__ __forceinline__ void adam_one(float& p, float& g, float& m, float& v, const AdamArgs& a, float gmul) {
+  const float gr = g * gmul;
+  m = a.beta1 * m + (1.f - a.beta1) * gr;
+  v = a.beta2 * v + (1.f - a.beta2) * gr * gr;
+  const float denom = sqrtf(v / a.bc2) + a.eps;
+  const float upd = (m / a.bc1) / denom + a.weight_decay * p;
+  p = p - a.lr * upd;
+  g = 0.f;
+}
+
+__global__ void __launch_bounds__(256)
+adam_kernel(float* __restrict__ param, float* __restrict__ grad, float* __restrict__ m, float* __restrict__ v,
+            __half* __restrict__ p16, int64_t n, AdamArgs a, const float* __restrict__ grad_div,
+            const int32_t* __restrict__ skip, const float* __restrict__ clip_coef) {
+  const bool do_skip = skip != nullptr && *skip != 0;
+  float gmul = 1.f;
+  if (grad_div) gmul = 1.f / *grad_div;
+  if (clip_coef) gmul *= *clip_coef;
+  const int64_t n4 = n >> 2;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    float4 g = reinterpret_cast<float4*>(grad)[i];
+    if (do_skip) { reinterpret_cast<float4*>(grad)[i] = make_float4(0.f, 0.f, 0.f, 0.f); continue; }
+    float4 p = reinterpret_cast<float4*>(param)[i];
+    float4 mm = reinterpret_cast<float4*>(m)[i];
+    float4 vv = reinterpret_cast<float4*>(v)[i];
+    adam_one(p.x, g.x, mm.x, vv.x, a, gmul); adam_one(p.y, g.y, mm.y, vv.y, a, gmul);
+    adam_one(p.z, g.z, mm.z, vv.z, a, gmul); adam_one(p.w, g.w, mm.w, vv.w, a, gmul);
+    reinterpret_cast<float4*>(param)[i] = p;
+    reinterpret_cast<float4*>(m)[i] = mm;
+    reinterpret_cast<float4*>(v)[i] = vv;
+    reinterpret_cast<float4*>(grad)[i] = g;
+    if (p16) {
+      const __half2 lo = __floats2half2_rn(p.x, p.y), hi = __floats2half2_rn(p.z, p.w);
+      uint2 pk; pk.x = *reinterpret_cast<const uint32_t*>(&lo); pk.y = *reinterpret_cast<const uint32_t*>(&hi);
+      reinterpret_cast<uint2*>(p16)[i] = pk;
+    }
+  }
+  const int64_t t = (n4 << 2) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n) {
+    float g = grad[t];
+    if (!do_skip) {
+      float p = param[t], mm = m[t], vv = v[t];
+      adam_one(p, g, mm, vv, a, gmul);
+      param[t] = p; m[t] = mm; v[t] = vv;
+      if (p16) p16[t] = __float2half_rn(p);
+    }
+    grad[t] = 0.f;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+sumsq_kernel(const float* __restrict__ grad, int64_t n, const float* __restrict__ grad_div, float* __restrict__ out,
+             int32_t* __restrict__ flag) {
+  const float gmul = grad_div ? 1.f / *grad_div : 1.f;
+  float acc = 0.f;
+  bool bad = false;
+  const int64_t n4 = n >> 2;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const float4 g = reinterpret_cast<const float4*>(grad)[i];
+    const float a = g.x * gmul, b = g.y * gmul, c = g.z * gmul, d = g.w * gmul;
+    acc += a * a + b * b + c * c + d * d;
+    bad |= !(isfinite(a) && isfinite(b) && isfinite(c) && isfinite(d));
+  }
+  const int64_t t = (n4 << 2) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n) { const float a = grad[t] * gmul; acc += a * a; bad |= !isfinite(a); }
+  acc = warp_sum(acc);
+  __shared__ float s[8];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane == 0) s[wid] = acc;
+  if (bad && flag) atomicOr(flag, 1);
+  __syncthreads();
+  if (wid == 0) {
+    acc = lane < 8 ? s[lane] : 0.f;
+    acc = warp_sum(acc);
+    if (lane == 0) atomicAdd(out, acc);
+  }
+}
+
+// clip_coef = min(1, max_norm / (sqrt(sumsq) + 1e-6))  (torch.nn.utils.clip_grad_norm_)
+__global__ void clip_coef_kernel(const float* __restrict__ sumsq, float max_norm, float* __restrict__ coef) {
+  const float nrm = sqrtf(*sumsq);
+  const float c = max_norm / (nrm + 1e-6f);
+  *coef = c < 1.f ? c : 1.f;
+}
+
+}  // namespace ncn
+
+using namespace ncn;
+
+extern "C" int ncn_adam_step(float* param, float* grad, float* m, float* v, void* param_f16, int64_t n, float lr,
+                             float beta1, float beta2, float eps, float weight_decay, int step,
+                             const float* grad_div_dev, const int32_t* skip_dev, const float* clip_coef_dev,
+                             ncn_stream_t stream) {
+  NCN_CHECK_SIZE(n >= 0 && step >= 1);
+  if (n == 0) return NCN_OK;
+  NCN_CHECK_PTR(param); NCN_CHECK_PTR(grad); NCN_CHECK_PTR(m); NCN_CHECK_PTR(v);
+  if (((uintptr_t)param | (uintptr_t)grad | (uintptr_t)m | (uintptr_t)v) & 15) return NCN_E_ALIGN;
+  if ((uintptr_t)param_f16 & 7) return NCN_E_ALIGN;
+  AdamArgs a;
+  a.lr = lr; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.weight_decay = weight_decay;
+  a.bc1 = 1.0f - powf(beta1, (float)step); a.bc2 = 1.0f - powf(beta2, (float)step);
+  const int grid = persistent_grid((n + 3) / 4, 256, 8);
+  adam_kernel<<<grid, 256, 0, as_stream(stream)>>>(param, grad, m, v, (__half*)param_f16, n, a, grad_div_dev, skip_dev,
+                                                   clip_coef_dev);
+  NCN_LAUNCH_OK();
+  return NCN_OK;
+}
+
+extern "C" int ncn_grad_sumsq(const float* grad, int64_t n, const float* grad_div_dev, float* out, int32_t* flag,
+                              ncn_stream_t stream) {
+  NCN_CHECK_SIZE(n >= 0);
+  if (n == 0) return NCN_OK;
+  NCN_CHECK_PTR(grad); NCN_CHECK_PTR(out);
+  if ((uintptr_t)grad & 15) return NCN_E_ALIGN;
+  const int grid = persistent_grid((n + 3) / 4, 256, 8);
+  sumsq_kernel<<<grid, 256, 0, as_stream(stream)>>>(grad, n, grad_div_dev, out, flag);
+  NCN_LAUNCH_OK();
+  return NCN_OK;
+}
+
+extern "C" int ncn_clip_coef(const float* sumsq_dev, float max_norm, float* coef_dev, ncn_stream_t stream) {
+  NCN_CHECK_PTR(sumsq_dev); NCN_CHECK_PTR(coef_dev);
+  clip_coef_kernel<<<1, 1, 0, as_stream(stream)>>>(sumsq_dev, max_norm, coef_dev);
+  NCN_LAUNCH_OK();
+  return NCN_OK;
+}

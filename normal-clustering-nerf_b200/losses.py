@@ -1,0 +1,116 @@
+"""NeRFMTLoss - host-side mirror of the reference's losses.py::NeRFMTLoss (:169-587) for the terms on
+the hot path, with the same constructor (a hyper-parameter dict), the same ``forward(pred, target,
+**kwargs) -> dict`` surface and the same loss-dict keys, but without any host synchronisation:
+
+  reference                                              here
+  -----------------------------------------------------  ------------------------------------------------
+  norm_D_C.cpu().numpy() -> faiss k-means (CPU) -> .to()   single-CTA k-means kernel on the device
+  4x .item() in the triple selection                       selection kernel, labels stay on the device
+  boolean-mask compaction of the normals                   labels (0 = unused / invalid) - no nonzero()
+  `elif torch.isnan(loss)` per term (one sync each)        torch.where(isfinite) - no sync
+  ~60 tiny kernels for the three cluster terms             one statistics kernel + one gradient kernel
+
+Reference quirks that are reproduced: normals use ``pred['rays_o']`` which rendering.py:227 sets to the ray
+DIRECTIONS; the distortion term is evaluated on ``ts`` in place of ``ws`` (losses.py:290); clustering runs from
+step 0 even while its schedule weight is 0; an empty cluster zeroes all three cluster terms.
+"""
+import torch
+from torch import nn
+
+from . import clustering
+from . import vren
+
+
+class _Distortion(torch.autograd.Function):
+    """losses.py:16-44 (DistortionLoss)"""
+
+    @staticmethod
+    def forward(ctx, ws, deltas, ts, rays_a):
+        loss, ws_inc, wts_inc = vren.distortion_loss_fw(ws.contiguous(), deltas.contiguous(), ts.contiguous(), rays_a)
+        ctx.save_for_backward(ws_inc, wts_inc, ws, deltas, ts, rays_a)
+        return loss
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g):
+        ws_inc, wts_inc, ws, deltas, ts, rays_a = ctx.saved_tensors
+        return vren.distortion_loss_bw(g.contiguous(), ws_inc, wts_inc, ws.contiguous(), deltas.contiguous(),
+                                       ts.contiguous(), rays_a), None, None, None
+
+
+def _valid(loss):
+    """_loss_validity_filter (losses.py:246-262) without the host sync: NaN / Inf -> 0."""
+    return torch.where(torch.isfinite(loss), loss, torch.zeros_like(loss))
+
+
+def triangle_indices(n, strategy, target=None, device="cuda"):
+    """x1/x2/x3 index triplets (losses.py:294-329)."""
+    idx = torch.arange(n, device=device)
+    if strategy in ("all_images_triang", "same_image_triang"):
+        t = idx.view(-1, 3)
+        return {"x1": t[:, 0].contiguous(), "x2": t[:, 1].contiguous(), "x3": t[:, 2].contiguous()}
+    ps = int(target["patch_area"])
+    p = idx.view(-1, ps)
+    return {k: p[:, target[f"{k}_offsets_local"]].reshape(-1) for k in ("x1", "x2", "x3")}
+
+
+class NeRFMTLoss(nn.Module):
+    def __init__(self, hparams_dict):
+        super().__init__()
+        g = hparams_dict.get
+        self.opacity_w = g("loss_opacity_w", 0)
+        self.distortion_w = g("loss_distortion_w", 0)
+        self.depth_w = g("loss_depth_w", 0)
+        self.reg_depth_w = g("loss_reg_depth_w", 0)
+        self.norm_CAN_tres = g("loss_norm_can_tres", 0)
+        self.w_ort = g("loss_norm_D_C_ort_dot_w", 0)
+        self.w_dot = g("loss_norm_D_C_centr_dot_w", 0)
+        self.w_l1 = g("loss_norm_D_C_centr_L1_w", 0)
+        self.ray_sampling_strategy = g("ray_sampling_strategy", None)
+        self.random_tr_poses = g("random_tr_poses", False)
+        self.pred_norm_depth = g("pred_norm_depth", False)
+        self.can_sched_start = g("loss_norm_can_start", 0)
+        self.can_sched_end = g("loss_norm_can_end", -1)
+        self.can_grow = g("loss_norm_can_grow", 1)
+        self.kmeans_k, self.kmeans_niter = g("kmeans_k", 20), g("kmeans_niter", 20)   # losses.py:436-437 literals
+
+    def w_sched(self, w, step):
+        return max(0, min(w, (step - self.can_sched_start) * (w / self.can_grow)))   # losses.py:217
+
+    def forward(self, pred, target, **kwargs):
+        loss_d = {}
+        gt_l = target["rgb"].shape[0]
+        rgb_pred = pred["rgb"][:gt_l]
+        loss_d["rgb"] = _valid(((rgb_pred - target["rgb"]) ** 2).mean())
+        if self.opacity_w > 0:
+            o = pred["opacity"] + 1e-10
+            loss_d["opacity"] = _valid(self.opacity_w * (-o * torch.log(o)).mean())
+        if self.distortion_w > 0:
+            # the reference passes ts where ws is meant (losses.py:290) - reproduced
+            d = _Distortion.apply(pred["ts"], pred["deltas"], pred["ts"], pred["rays_a"]).mean()
+            loss_d["distortion"] = _valid(self.distortion_w * d)
+        if self.depth_w > 0 and "depth" in target:
+            dp, dt = pred["depth"][:gt_l], target["depth"]
+            m = (dt > 0).float()
+            loss_d["depth"] = _valid(self.depth_w * (((dp - dt) ** 2) * m).sum() / m.sum().clamp_min(1.0))
+
+        unsup_start = gt_l if self.random_tr_poses else 0
+        depth_u = pred["depth"][unsup_start:]
+        x123 = None
+        if self.pred_norm_depth:
+            x123 = triangle_indices(depth_u.shape[0], self.ray_sampling_strategy, target, depth_u.device)
+        step = kwargs.get("global_step", 0)
+        if self.reg_depth_w > 0 and step > self.can_sched_start and x123 is not None:
+            r = (depth_u[x123["x1"]] - depth_u[x123["x2"]]) ** 2 + (depth_u[x123["x1"]] - depth_u[x123["x3"]]) ** 2
+            loss_d["reg_depth"] = _valid(r.mean())
+        if (self.w_ort > 0 or self.w_dot > 0 or self.w_l1 > 0) and (step <= self.can_sched_end or self.can_sched_end == -1):
+            normals = clustering.normals_from_depth(pred["rays_o"][unsup_start:], pred["rays_d"][unsup_start:], depth_u, x123)
+            labels, _, _ = clustering.normals_clustering(normals, K=self.kmeans_k, niter=self.kmeans_niter,
+                                                         t_similar=1.0 - self.norm_CAN_tres)
+            terms = clustering.cluster_loss(normals, labels)
+            loss_d["norm_D_C_ort_dot"] = _valid(self.w_sched(self.w_ort, step) * terms[0])
+            loss_d["norm_D_C_centr_dot"] = _valid(self.w_sched(self.w_dot, step) * terms[1])
+            loss_d["norm_D_C_centr_L1"] = _valid(self.w_sched(self.w_l1, step) * terms[2])
+            pred["norm_depth"] = normals
+        loss_d["total"] = sum(v for v in loss_d.values())
+        return loss_d

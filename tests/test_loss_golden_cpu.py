@@ -1,0 +1,57 @@
+"""CPU: the torch restatement in oracle/cluster_loss.py against golden vectors produced by the reference's own
+losses.py (oracle/gen_golden_loss.py) - pins selection / merge / opposite labelling, the three cluster terms and
+the gradient that reaches the rendered depth."""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CASES = sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "cluster_loss_*.npz")))
+
+
+def _load(path):
+    return {k: v for k, v in np.load(path).items()}
+
+
+@pytest.mark.parametrize("path", CASES)
+def test_oracle_matches_reference_golden(path):
+    from oracle import cluster_loss as cl
+    g = _load(path)
+    rays_d = torch.from_numpy(g["rays_d"])
+    depth = torch.from_numpy(g["depth"]).requires_grad_(True)
+    x123 = {k: torch.from_numpy(g["tri"][i]) for i, k in enumerate(("x1", "x2", "x3"))}
+    normals = cl.normals_from_rays(rays_d, rays_d, depth, x123)          # rays_o := rays_d (rendering.py:227)
+    torch.testing.assert_close(normals.detach(), torch.from_numpy(g["normals"]), rtol=1e-6, atol=1e-7)
+    valid = cl.valid_rows(normals.detach())
+    assert np.array_equal(valid.numpy(), g["valid"])
+    labels_v, sel = cl.select_clusters(torch.from_numpy(g["kmeans_assign"]), torch.from_numpy(g["kmeans_centroids"]),
+                                       1.0 - 0.01)
+    assert np.array_equal(labels_v.numpy(), g["labels"])
+    torch.testing.assert_close(torch.from_numpy(g["kmeans_centroids"])[list(sel)], torch.from_numpy(g["centrs_new"]))
+    ort, dot, l1 = cl.cluster_terms(normals[valid], labels_v)
+    w = float(g["w_sched"])
+    assert abs(w * float(ort) - float(g["loss_ort"])) <= 1e-6 * max(1, abs(float(g["loss_ort"])))
+    assert abs(w * float(dot) - float(g["loss_dot"])) <= 2e-6
+    assert abs(w * float(l1) - float(g["loss_l1"])) <= 2e-6
+    (w * (ort + dot + l1)).backward()
+    torch.testing.assert_close(depth.grad, torch.from_numpy(g["grad_depth"]), rtol=1e-4, atol=1e-7)
+
+
+def test_kmeans_standin_recovers_planted_frame():
+    """oracle k-means + selection on config-1 normals recovers the planted Manhattan frame within 1 degree"""
+    from oracle import cluster_loss as cl
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("synth", os.path.join(ROOT, "normal-clustering-nerf_b200", "synth.py"))
+    synth = importlib.util.module_from_spec(spec); spec.loader.exec_module(synth)
+    x, q = synth.manhattan_normals(8192, seed=0)
+    xt = torch.from_numpy(x)
+    valid = cl.valid_rows(xt)
+    cent, assign = cl.spherical_kmeans(x[valid.numpy()], 20, 20)
+    labels, sel = cl.select_clusters(torch.from_numpy(assign), torch.from_numpy(cent), 0.99)
+    axes = cent[list(sel)]
+    cos = np.abs(axes @ q)            # each selected centroid aligns with one planted axis
+    assert (cos.max(1) > np.cos(np.deg2rad(1.5))).all(), cos
+    assert sorted(cos.argmax(1).tolist()) == [0, 1, 2]
