@@ -261,3 +261,28 @@ def test_distortion(ncn, vren_ref, scene):
     go = vren.distortion_loss_bw(dl, ours[1], ours[2], ws, deltas, ts, ra)
     gr = vren_ref.distortion_loss_bw(dl, ref[1], ref[2], ws, deltas, ts, ra)
     torch.testing.assert_close(go, gr, rtol=1e-5, atol=1e-7)
+
+
+# ------------------------------------------------------------------ committed golden vectors (reference csrc on B200)
+import glob
+import os
+
+_GOLD = sorted(glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "vren_ref_*.npz")))
+
+
+@pytest.mark.parametrize("path", _GOLD)
+def test_against_committed_golden(ncn, scene, path):
+    from ncn_b200 import vren
+    g = np.load(path)
+    t = lambda k: torch.from_numpy(g[k]).cuda()
+    _, hits, _ = vren.ray_aabb_intersect(t("rays_o"), t("rays_d"), scene["center"], scene["half_size"], 1)
+    assert _bits_equal(hits[:, 0], t("hits_raw"))
+    ra, xyzs, dirs, deltas, ts, counter = vren.raymarching_train(t("rays_o"), t("rays_d"), t("hits_t"), scene["bitfield"], 1, 0.5,
+                                                                 float(g["esf"]), t("noise"), 128, 1024)
+    assert torch.equal(ra, t("rays_a"))
+    assert _bits_equal(ts, t("ts")) and _bits_equal(deltas, t("deltas")) and _bits_equal(xyzs, t("xyzs")) and _bits_equal(dirs, t("dirs"))
+    out = vren.composite_train_multi_fw(t("sigmas"), t("raws"), deltas, ts, ra, 1e-4)
+    assert torch.equal(out[0], t("total_samples")) and _bits_equal(out[4], t("ws"))
+    for a, k in zip(out[1:4], ("opacity", "depth", "rend")):
+        torch.testing.assert_close(a, t(k), rtol=1e-5, atol=1e-6)
+    assert torch.equal(vren.morton3D(t("coords")), t("morton"))
