@@ -45,6 +45,66 @@ SIGNATURES = {
 }
 
 
+class Profiler:
+    """Optional launch counter / per-call CUDA-event timer (used by bench.py; off by default).
+    launches: number of libncn kernels launched (every C call is counted with the kernels it enqueues)."""
+    counting = False
+    timing = None          # None, or a set of call names to time ("*" = all)
+    launches = 0
+    events = []            # (name, start_event, end_event, n_items)
+    KERNELS_PER_CALL = {"ncn_march_train": 3, "ncn_march_train_count": 2, "ncn_kmeans_workspace_bytes": 0,
+                        "ncn_march_train_workspace_bytes": 0, "ncn_mlp_bwd_workspace_bytes": 0, "ncn_mlp_n_params": 0,
+                        "ncn_grid_desc_init": 0, "ncn_version": 0, "ncn_error_string": 0, "ncn_device_info": 0,
+                        "ncn_comm_unique_id": 0, "ncn_comm_init": 0, "ncn_comm_destroy": 0, "ncn_comm_last_error": 0}
+
+    @classmethod
+    def reset(cls):
+        cls.launches = 0
+        cls.events = []
+
+    @classmethod
+    def summary(cls):
+        """name -> (calls, total_ms) from the recorded events (synchronises)."""
+        import torch
+        torch.cuda.synchronize()
+        out = {}
+        for name, e0, e1 in cls.events:
+            c, t = out.get(name, (0, 0.0))
+            out[name] = (c + 1, t + e0.elapsed_time(e1))
+        return out
+
+
+class _Proxy:
+    """Attribute access returns the ctypes function, wrapped with counting / event timing when enabled."""
+
+    def __init__(self, h):
+        self._h = h
+
+    def __getattr__(self, name):
+        fn = getattr(self._h, name)
+        if not Profiler.counting and Profiler.timing is None:
+            return fn
+        k = Profiler.KERNELS_PER_CALL.get(name, 1)
+
+        def wrapped(*args):
+            import torch
+            timed = Profiler.timing is not None and ("*" in Profiler.timing or name in Profiler.timing) and k > 0
+            if timed:
+                e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+                e0.record()
+            rc = fn(*args)
+            if timed:
+                e1.record()
+                Profiler.events.append((name, e0, e1))
+            if Profiler.counting:
+                kk = k
+                if name == "ncn_mlp_bwd":      # dgrad + one wgrad per layer (when a weight gradient is requested)
+                    kk = 1 + (args[0]._obj.n_hidden + 1 if args[7] else 0)
+                Profiler.launches += kk
+            return rc
+        return wrapped
+
+
 def lib():
     """Load libncn.so once; raise loudly if it has not been built."""
     global _lib
@@ -58,7 +118,7 @@ def lib():
             fn = getattr(h, name)   # AttributeError if the .so is stale
             fn.restype = res
             fn.argtypes = args
-        _lib = h
+        _lib = _Proxy(h)
     return _lib
 
 

@@ -96,6 +96,7 @@ class TruncExp(torch.autograd.Function):
     @staticmethod
     @_fwd32
     def forward(ctx, x):
+        x = x.float()                     # fp32 also outside an autocast region (custom_fwd only casts under autocast)
         ctx.save_for_backward(x)
         return torch.exp(x)
 
