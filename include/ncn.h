@@ -226,12 +226,18 @@ typedef struct ncn_grid_desc {
 } ncn_grid_desc;
 /* host-only helper: fill the derived fields; returns total #params = entries*F */
 int64_t ncn_grid_desc_init(ncn_grid_desc* desc);
-/* x (N,3) f32 in [0,1]; table fp16 (entries,F); out (N, L*F) fp16 (row major). */
+/* x (N,3) f32 in [0,1]; table fp16 (entries,F); out (N, L*F) fp16 (row major).
+ * xform_host: NULL, or 6 HOST floats (lo[3], size[3]): the kernel encodes (x - lo) / size
+ * (the normalisation of models/ngp_mt.py:166 fused in).
+ * n_dev: NULL, or a DEVICE int32 holding the live row count (rows processed = min(n, *n_dev));
+ * lets a sync-free caller size its arrays by capacity (see ncn_march_train). */
 int ncn_grid_fwd(const ncn_grid_desc* desc_host, const float* x, const void* table_f16,
-                 int64_t n, void* out_f16, ncn_stream_t stream);
+                 int64_t n, void* out_f16, const float* xform_host, const int32_t* n_dev,
+                 ncn_stream_t stream);
 /* dL_dy (N,L*F) fp16 -> grad_table fp32 (entries*F), ACCUMULATED (caller zeroes). */
 int ncn_grid_bwd(const ncn_grid_desc* desc_host, const float* x, const void* dL_dy_f16,
-                 int64_t n, float* grad_table_f32, float grad_scale, ncn_stream_t stream);
+                 int64_t n, float* grad_table_f32, float grad_scale, const float* xform_host,
+                 const int32_t* n_dev, ncn_stream_t stream);
 /* dL_dx (N,3) f32 = d out / d x contracted with dL_dy. */
 int ncn_grid_bwd_input(const ncn_grid_desc* desc_host, const float* x, const void* table_f16,
                        const void* dL_dy_f16, int64_t n, float* dL_dx, ncn_stream_t stream);
@@ -260,16 +266,35 @@ size_t ncn_mlp_bwd_workspace_bytes(const ncn_mlp_desc* d, int64_t n);
 /* x (N, n_in_pad) f16, weights f16 (tcnn layout: consecutive (out,in) row-major
  * matrices: (64,in_pad), (n_hidden-1) x (64,64), (out_pad,64)); out (N, n_out_pad) f16.
  * If `acts` != NULL the post-activation hidden states (n_hidden, N, 64) f16 are kept
- * for the backward pass.  Padded dims are multiples of 16 and <= 64. */
+ * for the backward pass.  Padded dims are multiples of 16 and <= 64.
+ * n_dev: NULL or a DEVICE int32 live row count (rows = min(n, *n_dev)); the (n_hidden, n, 64)
+ * strides stay those of n. */
 int ncn_mlp_fwd(const ncn_mlp_desc* d, const void* x_f16, const void* w_f16, int64_t n,
-                void* out_f16, void* acts_f16, ncn_stream_t stream);
+                void* out_f16, void* acts_f16, const int32_t* n_dev, ncn_stream_t stream);
 /* dL_dout (N,n_out_pad) f16 -> grad_w f32 += grad_scale * dL/dW (ACCUMULATED; may be
  * NULL), dL_dx (N,n_in_pad) f16 or NULL (in the units of dL_dout, not scaled).
  * scratch: ncn_mlp_bwd_workspace_bytes(d, n) bytes, 16 B aligned. */
 int ncn_mlp_bwd(const ncn_mlp_desc* d, const void* x_f16, const void* w_f16,
                 const void* out_f16, const void* acts_f16, const void* dL_dout_f16, int64_t n,
                 float* grad_w_f32, void* dL_dx_f16, float grad_scale, void* scratch,
-                size_t scratch_bytes, ncn_stream_t stream);
+                size_t scratch_bytes, const int32_t* n_dev, ncn_stream_t stream);
+
+/* Elementwise glue of the NGPMT field (models/ngp_mt.py:157-229, rendering.py:203-212) between the
+ * encoder / MLP kernels; every function takes the device-side live row count n_dev (may be NULL).
+ *   prepare_rgb: x_rgb (N,32) f16 = [d/||d|| (3), h (16), 1.0 x13], sigmas (N) f32 = exp(h[:,0])
+ *   head_out   : raws[:, c_offset:c_offset+n_ch] (row stride c_total, f32) = out_f16[:, :n_ch]
+ *   head_dout  : dout_f16 (N,out_pad) = [dL_draws[:, c_offset:+n_ch] * scale, 0...]
+ *   bwd_h      : dh (N,16) f16 = dx_rgb[:, 3:19] (+ dx_a + dx_b) + e0 * dL_dsigmas * exp(clamp(h0,-15,15)) * scale */
+int ncn_field_prepare_rgb(const float* dirs, const void* h_f16, int64_t n, const int32_t* n_dev,
+                          void* x_rgb_f16, float* sigmas, ncn_stream_t stream);
+int ncn_field_head_out(const void* out_f16, int out_pad, int64_t n, const int32_t* n_dev,
+                       float* raws, int c_total, int c_offset, int n_ch, ncn_stream_t stream);
+int ncn_field_head_dout(const float* dL_draws, int c_total, int c_offset, int n_ch, float scale,
+                        int64_t n, const int32_t* n_dev, void* dout_f16, int out_pad,
+                        ncn_stream_t stream);
+int ncn_field_bwd_h(const void* dx_rgb_f16, const float* dL_dsigmas, const void* h_f16,
+                    const void* dx_a_f16, const void* dx_b_f16, float scale, int64_t n,
+                    const int32_t* n_dev, void* dh_f16, ncn_stream_t stream);
 
 /* ------------------------------------------------------------------------- */
 /* (8) normals from rendered depth + Manhattan clustering loss                */
@@ -336,11 +361,13 @@ int ncn_photometric_loss(const float* rend, const float* opacity, const float* t
 /* Adam (apex FusedAdam adam_w_mode=True semantics: decoupled weight decay), fp32
  * master params; also refreshes the fp16 copy used by the kernels and zeroes the
  * gradient, in one pass.  grad is divided by *grad_div_dev if non-NULL
- * (loss-scale * world-size) and the step is skipped when *skip_dev != 0. */
+ * (loss-scale * world-size) and the step is skipped when *skip_dev != 0.
+ * lr_bc_dev: NULL, or 3 DEVICE floats (lr, 1-beta1^t, 1-beta2^t) that override lr / step, so a
+ * captured CUDA graph can be replayed while the host advances the schedule. */
 int ncn_adam_step(float* param, float* grad, float* m, float* v, void* param_f16,
                   int64_t n, float lr, float beta1, float beta2, float eps, float weight_decay,
                   int step, const float* grad_div_dev, const int32_t* skip_dev,
-                  const float* clip_coef_dev, ncn_stream_t stream);
+                  const float* clip_coef_dev, const float* lr_bc_dev, ncn_stream_t stream);
 /* sum of squares of grad/(div) into out[0] (ACCUMULATED), and non-finite flag into flag[0] */
 int ncn_grad_sumsq(const float* grad, int64_t n, const float* grad_div_dev,
                    float* out, int32_t* flag, ncn_stream_t stream);

@@ -159,14 +159,14 @@ ACT = {"None": 0, "ReLU": 1, "Sigmoid": 2, "Exponential": 3}
 
 SIGNATURES.update({
     "ncn_grid_desc_init": (c_i64, [C.POINTER(GridDesc)]),
-    "ncn_grid_fwd": (c_i32, [C.POINTER(GridDesc), c_vp, c_vp, c_i64, c_vp, c_vp]),
-    "ncn_grid_bwd": (c_i32, [C.POINTER(GridDesc), c_vp, c_vp, c_i64, c_vp, c_f32, c_vp]),
+    "ncn_grid_fwd": (c_i32, [C.POINTER(GridDesc), c_vp, c_vp, c_i64, c_vp, C.POINTER(c_f32), c_vp, c_vp]),
+    "ncn_grid_bwd": (c_i32, [C.POINTER(GridDesc), c_vp, c_vp, c_i64, c_vp, c_f32, C.POINTER(c_f32), c_vp, c_vp]),
     "ncn_grid_bwd_input": (c_i32, [C.POINTER(GridDesc), c_vp, c_vp, c_vp, c_i64, c_vp, c_vp]),
     "ncn_grid_bwd_bwd_input": (c_i32, [C.POINTER(GridDesc), c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp]),
     "ncn_mlp_n_params": (c_i64, [C.POINTER(MlpDesc)]),
     "ncn_mlp_bwd_workspace_bytes": (c_sz, [C.POINTER(MlpDesc), c_i64]),
-    "ncn_mlp_fwd": (c_i32, [C.POINTER(MlpDesc), c_vp, c_vp, c_i64, c_vp, c_vp, c_vp]),
-    "ncn_mlp_bwd": (c_i32, [C.POINTER(MlpDesc), c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_f32, c_vp, c_sz, c_vp]),
+    "ncn_mlp_fwd": (c_i32, [C.POINTER(MlpDesc), c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp]),
+    "ncn_mlp_bwd": (c_i32, [C.POINTER(MlpDesc), c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_f32, c_vp, c_sz, c_vp, c_vp]),
 })
 
 
@@ -184,7 +184,11 @@ SIGNATURES.update({
     "ncn_cluster_loss_fw": (c_i32, [c_vp, c_vp, c_i64, c_vp, c_vp, c_vp]),
     "ncn_cluster_loss_bw": (c_i32, [c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp]),
     "ncn_photometric_loss": (c_i32, [c_vp, c_vp, c_vp, c_i64, c_i32, C.POINTER(c_f32), c_f32, c_f32, c_vp, c_vp, c_vp, c_vp, c_vp]),
-    "ncn_adam_step": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_f32, c_f32, c_f32, c_f32, c_f32, c_i32, c_vp, c_vp, c_vp, c_vp]),
+    "ncn_adam_step": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_f32, c_f32, c_f32, c_f32, c_f32, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "ncn_field_prepare_rgb": (c_i32, [c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp]),
+    "ncn_field_head_out": (c_i32, [c_vp, c_i32, c_i64, c_vp, c_vp, c_i32, c_i32, c_i32, c_vp]),
+    "ncn_field_head_dout": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_f32, c_i64, c_vp, c_vp, c_i32, c_vp]),
+    "ncn_field_bwd_h": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_f32, c_i64, c_vp, c_vp, c_vp]),
     "ncn_grad_sumsq": (c_i32, [c_vp, c_i64, c_vp, c_vp, c_vp, c_vp]),
     "ncn_clip_coef": (c_i32, [c_vp, c_f32, c_vp, c_vp]),
     "ncn_comm_unique_id": (c_i32, [c_vp]),

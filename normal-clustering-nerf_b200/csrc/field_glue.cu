@@ -1,0 +1,138 @@
+// Elementwise glue of the NGPMT field (models/ngp_mt.py:157-229) between the encoder / MLP kernels: what the
+// reference does with ~20 small torch launches per step (x normalisation is folded into the grid kernel):
+//   prepare_rgb : d/||d||, cat[d, h] (19 -> padded to 32 with ones, the tcnn Identity-encoding padding),
+//                 sigma = TruncExp(h[:,0])  (custom_functions.py:162-173)
+//   head_out    : a head's fp16 output columns -> the fp32 `raws` matrix fed to the compositor (rendering.py:203-212)
+//   head_dout   : dL/draws columns -> the head's (padded) fp16 dL/dout, times the loss scale
+//   bwd_h       : dL/dh = dL/dx_rgb[:, 3:19] (+ other heads' dL/dx) + e_0 * dL/dsigma * exp(clamp(h0,-15,15))
+// All take a device-side live row count (n_dev) so the training step never synchronises.
+#include "ncn_common.cuh"
+
+namespace ncn {
+
+__device__ __forceinline__ int64_t live_rows(int64_t n_cap, const int32_t* __restrict__ n_dev) {
+  int64_t n = n_cap;
+  if (n_dev != nullptr) { const int64_t nd = *n_dev; if (nd < n) n = nd; }
+  return n;
+}
+
+__global__ void __launch_bounds__(256)
+prepare_rgb_kernel(const float* __restrict__ dirs, const __half* __restrict__ h, int64_t n_cap,
+                   const int32_t* __restrict__ n_dev, __half* __restrict__ x_rgb, float* __restrict__ sigmas) {
+  const int64_t n = live_rows(n_cap, n_dev);
+  const int64_t total = n * 16, stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int64_t s = i >> 4;
+    const int c = (int)(i & 15);          // this thread writes columns 2c, 2c+1 of the 32-wide row
+    float v[2];
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int col = 2 * c + q;
+      if (col < 3) {
+        const float dx = dirs[3 * s], dy = dirs[3 * s + 1], dz = dirs[3 * s + 2];
+        const float nrm = sqrtf(dx * dx + dy * dy + dz * dz);
+        v[q] = dirs[3 * s + col] / nrm;
+      } else if (col < 19) {
+        v[q] = __half2float(h[s * 16 + (col - 3)]);
+      } else {
+        v[q] = 1.0f;
+      }
+    }
+    reinterpret_cast<__half2*>(x_rgb)[i] = __floats2half2_rn(v[0], v[1]);
+    if (c == 0 && sigmas) sigmas[s] = expf(__half2float(h[s * 16]));
+  }
+}
+
+__global__ void __launch_bounds__(256)
+head_out_kernel(const __half* __restrict__ out, int out_pad, int64_t n_cap, const int32_t* __restrict__ n_dev,
+                float* __restrict__ raws, int c_total, int c_offset, int n_ch) {
+  const int64_t n = live_rows(n_cap, n_dev);
+  const int64_t total = n * n_ch, stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int64_t s = i / n_ch;
+    const int j = (int)(i - s * n_ch);
+    raws[s * c_total + c_offset + j] = __half2float(out[s * out_pad + j]);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+head_dout_kernel(const float* __restrict__ d_raws, int c_total, int c_offset, int n_ch, float scale, int64_t n_cap,
+                 const int32_t* __restrict__ n_dev, __half* __restrict__ dout, int out_pad) {
+  const int64_t n = live_rows(n_cap, n_dev);
+  const int64_t total = n * out_pad, stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int64_t s = i / out_pad;
+    const int j = (int)(i - s * out_pad);
+    dout[i] = __float2half_rn(j < n_ch ? d_raws[s * c_total + c_offset + j] * scale : 0.f);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+bwd_h_kernel(const __half* __restrict__ dx_rgb, const float* __restrict__ d_sigmas, const __half* __restrict__ h,
+             const __half* __restrict__ dx_a, const __half* __restrict__ dx_b, float scale, int64_t n_cap,
+             const int32_t* __restrict__ n_dev, __half* __restrict__ dh) {
+  const int64_t n = live_rows(n_cap, n_dev);
+  const int64_t total = n * 16, stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int64_t s = i >> 4;
+    const int j = (int)(i & 15);
+    float g = __half2float(dx_rgb[s * 32 + 3 + j]);
+    if (dx_a) g += __half2float(dx_a[i]);
+    if (dx_b) g += __half2float(dx_b[i]);
+    if (j == 0) {
+      const float h0 = __half2float(h[s * 16]);
+      g += d_sigmas[s] * expf(fminf(fmaxf(h0, -15.f), 15.f)) * scale;
+    }
+    dh[i] = __float2half_rn(g);
+  }
+}
+
+}  // namespace ncn
+
+using namespace ncn;
+
+extern "C" int ncn_field_prepare_rgb(const float* dirs, const void* h_f16, int64_t n, const int32_t* n_dev, void* x_rgb_f16,
+                                     float* sigmas, ncn_stream_t stream) {
+  NCN_CHECK_SIZE(n >= 0);
+  if (n == 0) return NCN_OK;
+  NCN_CHECK_PTR(dirs); NCN_CHECK_PTR(h_f16); NCN_CHECK_PTR(x_rgb_f16);
+  prepare_rgb_kernel<<<persistent_grid(n * 16, 256, 8), 256, 0, as_stream(stream)>>>(dirs, (const __half*)h_f16, n, n_dev,
+                                                                                     (__half*)x_rgb_f16, sigmas);
+  NCN_LAUNCH_OK();
+  return NCN_OK;
+}
+
+extern "C" int ncn_field_head_out(const void* out_f16, int out_pad, int64_t n, const int32_t* n_dev, float* raws, int c_total,
+                                  int c_offset, int n_ch, ncn_stream_t stream) {
+  NCN_CHECK_SIZE(n >= 0 && n_ch >= 1 && c_offset >= 0 && c_offset + n_ch <= c_total && n_ch <= out_pad);
+  if (n == 0) return NCN_OK;
+  NCN_CHECK_PTR(out_f16); NCN_CHECK_PTR(raws);
+  head_out_kernel<<<persistent_grid(n * n_ch, 256, 8), 256, 0, as_stream(stream)>>>((const __half*)out_f16, out_pad, n, n_dev, raws,
+                                                                                    c_total, c_offset, n_ch);
+  NCN_LAUNCH_OK();
+  return NCN_OK;
+}
+
+extern "C" int ncn_field_head_dout(const float* dL_draws, int c_total, int c_offset, int n_ch, float scale, int64_t n,
+                                   const int32_t* n_dev, void* dout_f16, int out_pad, ncn_stream_t stream) {
+  NCN_CHECK_SIZE(n >= 0 && n_ch >= 1 && c_offset >= 0 && c_offset + n_ch <= c_total && n_ch <= out_pad);
+  if (n == 0) return NCN_OK;
+  NCN_CHECK_PTR(dL_draws); NCN_CHECK_PTR(dout_f16);
+  head_dout_kernel<<<persistent_grid(n * out_pad, 256, 8), 256, 0, as_stream(stream)>>>(dL_draws, c_total, c_offset, n_ch, scale, n,
+                                                                                        n_dev, (__half*)dout_f16, out_pad);
+  NCN_LAUNCH_OK();
+  return NCN_OK;
+}
+
+extern "C" int ncn_field_bwd_h(const void* dx_rgb_f16, const float* dL_dsigmas, const void* h_f16, const void* dx_a_f16,
+                               const void* dx_b_f16, float scale, int64_t n, const int32_t* n_dev, void* dh_f16,
+                               ncn_stream_t stream) {
+  NCN_CHECK_SIZE(n >= 0);
+  if (n == 0) return NCN_OK;
+  NCN_CHECK_PTR(dx_rgb_f16); NCN_CHECK_PTR(dL_dsigmas); NCN_CHECK_PTR(h_f16); NCN_CHECK_PTR(dh_f16);
+  bwd_h_kernel<<<persistent_grid(n * 16, 256, 8), 256, 0, as_stream(stream)>>>((const __half*)dx_rgb_f16, dL_dsigmas,
+                                                                               (const __half*)h_f16, (const __half*)dx_a_f16,
+                                                                               (const __half*)dx_b_f16, scale, n, n_dev, (__half*)dh_f16);
+  NCN_LAUNCH_OK();
+  return NCN_OK;
+}

@@ -12,6 +12,11 @@
 
 namespace ncn {
 
+struct GridXform {         // optional input normalisation x' = (x - lo) / size  (models/ngp_mt.py:166)
+  float lo[3], size[3];
+  int on;
+};
+
 struct GridMeta {          // per-level constants, copied to shared memory by each CTA
   float scale[NCN_GRID_MAX_LEVELS];
   uint32_t res[NCN_GRID_MAX_LEVELS];
@@ -36,11 +41,13 @@ struct Cell8 {
 };
 
 __device__ __forceinline__ void locate8(const float* __restrict__ x, int64_t n, float scale, uint32_t res, uint32_t size,
-                                        Cell8& c) {
+                                        Cell8& c, const GridXform& xf) {
   uint32_t g[3];
 #pragma unroll
   for (int d = 0; d < 3; ++d) {
-    const float pos = fmaf(scale, x[3 * n + d], 0.5f);
+    float xi = x[3 * n + d];
+    if (xf.on) xi = __fdiv_rn(__fsub_rn(xi, xf.lo[d]), xf.size[d]);   // (x - xyz_min) / (xyz_max - xyz_min), IEEE like torch
+    const float pos = fmaf(scale, xi, 0.5f);
     const float fl = floorf(pos);
     g[d] = (uint32_t)(int)fl;
     c.w[d] = pos - fl;
@@ -67,19 +74,21 @@ __device__ __forceinline__ float corner_dw(const float* w, int k, int d) {
     reinterpret_cast<uint32_t*>(&sm)[i] = reinterpret_cast<const uint32_t*>(&meta)[i]; \
   __syncthreads();                                                                 \
   const int L = sm.n_levels;                                                       \
+  int64_t n = n_cap;                                                               \
+  if (n_dev != nullptr) { const int64_t nd = *n_dev; if (nd < n) n = nd; }         \
   const int64_t total = n * L;                                                     \
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
 
 template <int F>
 __global__ void __launch_bounds__(256)
 grid_fwd_kernel(const __grid_constant__ GridMeta meta, const float* __restrict__ x, const __half* __restrict__ table,
-                int64_t n, __half* __restrict__ out) {
+                int64_t n_cap, const int32_t* __restrict__ n_dev, GridXform xf, __half* __restrict__ out) {
   NCN_GRID_PROLOGUE
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
     const int64_t s = i / L;
     const int l = (int)(i - s * L);
     Cell8 c;
-    locate8(x, s, sm.scale[l], sm.res[l], sm.size[l], c);
+    locate8(x, s, sm.scale[l], sm.res[l], sm.size[l], c, xf);
     const __half* tl = table + (size_t)sm.offset[l] * F;
     float acc[F];
 #pragma unroll
@@ -111,7 +120,7 @@ grid_fwd_kernel(const __grid_constant__ GridMeta meta, const float* __restrict__
 template <int F>
 __global__ void __launch_bounds__(256)
 grid_bwd_kernel(const __grid_constant__ GridMeta meta, const float* __restrict__ x, const __half* __restrict__ dy,
-                int64_t n, float grad_scale, float* __restrict__ grad) {
+                int64_t n_cap, const int32_t* __restrict__ n_dev, GridXform xf, float grad_scale, float* __restrict__ grad) {
   NCN_GRID_PROLOGUE
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
     const int64_t s = i / L;
@@ -122,7 +131,7 @@ grid_bwd_kernel(const __grid_constant__ GridMeta meta, const float* __restrict__
     for (int f = 0; f < F; ++f) { g[f] = __half2float(dy[i * F + f]) * grad_scale; any |= (g[f] != 0.f); }
     if (!any) continue;    // samples cut by early ray termination carry exact-zero gradients
     Cell8 c;
-    locate8(x, s, sm.scale[l], sm.res[l], sm.size[l], c);
+    locate8(x, s, sm.scale[l], sm.res[l], sm.size[l], c, xf);
     float* gl = grad + (size_t)sm.offset[l] * F;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
@@ -141,15 +150,15 @@ grid_bwd_kernel(const __grid_constant__ GridMeta meta, const float* __restrict__
 template <int F>
 __global__ void __launch_bounds__(256)
 grid_bwd_input_kernel(const __grid_constant__ GridMeta meta, const float* __restrict__ x,
-                      const __half* __restrict__ table, const __half* __restrict__ dy, int64_t n,
-                      float* __restrict__ dx) {
+                      const __half* __restrict__ table, const __half* __restrict__ dy, int64_t n_cap,
+                      const int32_t* __restrict__ n_dev, GridXform xf, float* __restrict__ dx) {
   NCN_GRID_PROLOGUE
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
     const int64_t s = i / L;
     const int l = (int)(i - s * L);
     Cell8 c;
     const float scale = sm.scale[l];
-    locate8(x, s, scale, sm.res[l], sm.size[l], c);
+    locate8(x, s, scale, sm.res[l], sm.size[l], c, xf);
     const __half* tl = table + (size_t)sm.offset[l] * F;
     float g[F];
 #pragma unroll
@@ -175,15 +184,15 @@ template <int F>
 __global__ void __launch_bounds__(256)
 grid_bwd_bwd_input_kernel(const __grid_constant__ GridMeta meta, const float* __restrict__ x,
                           const __half* __restrict__ table, const float* __restrict__ v,
-                          const __half* __restrict__ dy, int64_t n, float* __restrict__ grad,
-                          __half* __restrict__ ddy) {
+                          const __half* __restrict__ dy, int64_t n_cap, const int32_t* __restrict__ n_dev,
+                          GridXform xf, float* __restrict__ grad, __half* __restrict__ ddy) {
   NCN_GRID_PROLOGUE
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
     const int64_t s = i / L;
     const int l = (int)(i - s * L);
     Cell8 c;
     const float scale = sm.scale[l];
-    locate8(x, s, scale, sm.res[l], sm.size[l], c);
+    locate8(x, s, scale, sm.res[l], sm.size[l], c, xf);
     const float v0 = v[3 * s] * scale, v1 = v[3 * s + 1] * scale, v2 = v[3 * s + 2] * scale;
     float g[F], o[F];
 #pragma unroll
@@ -247,6 +256,13 @@ static int to_meta(const ncn_grid_desc* d, GridMeta* m) {
   return NCN_OK;
 }
 
+static GridXform make_xform(const float* xform_host) {
+  GridXform xf;
+  for (int d = 0; d < 3; ++d) { xf.lo[d] = xform_host ? xform_host[d] : 0.f; xf.size[d] = xform_host ? xform_host[3 + d] : 1.f; }
+  xf.on = xform_host != nullptr;
+  return xf;
+}
+
 #define NCN_GRID_DISPATCH(F, CALL)                 \
   switch (F) {                                     \
     case 1: { constexpr int kF = 1; CALL; } break; \
@@ -257,7 +273,7 @@ static int to_meta(const ncn_grid_desc* d, GridMeta* m) {
   }
 
 extern "C" int ncn_grid_fwd(const ncn_grid_desc* desc, const float* x, const void* table, int64_t n, void* out,
-                            ncn_stream_t stream) {
+                            const float* xform_host, const int32_t* n_dev, ncn_stream_t stream) {
   GridMeta m; int rc = to_meta(desc, &m); if (rc) return rc;
   NCN_CHECK_SIZE(n >= 0);
   if (n == 0) return NCN_OK;
@@ -265,13 +281,13 @@ extern "C" int ncn_grid_fwd(const ncn_grid_desc* desc, const float* x, const voi
   if (((uintptr_t)table | (uintptr_t)out) & 3) return NCN_E_ALIGN;
   const int grid = persistent_grid(n * m.n_levels, 256, 8);
   NCN_GRID_DISPATCH(desc->n_features, (grid_fwd_kernel<kF><<<grid, 256, 0, as_stream(stream)>>>(
-      m, x, (const __half*)table, n, (__half*)out)));
+      m, x, (const __half*)table, n, n_dev, make_xform(xform_host), (__half*)out)));
   NCN_LAUNCH_OK();
   return NCN_OK;
 }
 
 extern "C" int ncn_grid_bwd(const ncn_grid_desc* desc, const float* x, const void* dy, int64_t n, float* grad,
-                            float grad_scale, ncn_stream_t stream) {
+                            float grad_scale, const float* xform_host, const int32_t* n_dev, ncn_stream_t stream) {
   GridMeta m; int rc = to_meta(desc, &m); if (rc) return rc;
   NCN_CHECK_SIZE(n >= 0);
   if (n == 0) return NCN_OK;
@@ -279,7 +295,7 @@ extern "C" int ncn_grid_bwd(const ncn_grid_desc* desc, const float* x, const voi
   if ((uintptr_t)grad & 7) return NCN_E_ALIGN;
   const int grid = persistent_grid(n * m.n_levels, 256, 8);
   NCN_GRID_DISPATCH(desc->n_features, (grid_bwd_kernel<kF><<<grid, 256, 0, as_stream(stream)>>>(
-      m, x, (const __half*)dy, n, grad_scale, grad)));
+      m, x, (const __half*)dy, n, n_dev, make_xform(xform_host), grad_scale, grad)));
   NCN_LAUNCH_OK();
   return NCN_OK;
 }
@@ -293,7 +309,7 @@ extern "C" int ncn_grid_bwd_input(const ncn_grid_desc* desc, const float* x, con
   NCN_CUDA(cudaMemsetAsync(dx, 0, (size_t)n * 3 * sizeof(float), as_stream(stream)));
   const int grid = persistent_grid(n * m.n_levels, 256, 8);
   NCN_GRID_DISPATCH(desc->n_features, (grid_bwd_input_kernel<kF><<<grid, 256, 0, as_stream(stream)>>>(
-      m, x, (const __half*)table, (const __half*)dy, n, dx)));
+      m, x, (const __half*)table, (const __half*)dy, n, nullptr, make_xform(nullptr), dx)));
   NCN_LAUNCH_OK();
   return NCN_OK;
 }
@@ -308,7 +324,7 @@ extern "C" int ncn_grid_bwd_bwd_input(const ncn_grid_desc* desc, const float* x,
   if (grad) NCN_CHECK_PTR(dy);
   const int grid = persistent_grid(n * m.n_levels, 256, 8);
   NCN_GRID_DISPATCH(desc->n_features, (grid_bwd_bwd_input_kernel<kF><<<grid, 256, 0, as_stream(stream)>>>(
-      m, x, (const __half*)table, dL_ddLdx, (const __half*)dy, n, grad, (__half*)ddy)));
+      m, x, (const __half*)table, dL_ddLdx, (const __half*)dy, n, nullptr, make_xform(nullptr), grad, (__half*)ddy)));
   NCN_LAUNCH_OK();
   return NCN_OK;
 }

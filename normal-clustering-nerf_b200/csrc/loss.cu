@@ -90,7 +90,7 @@ normals_bw_kernel(const float* __restrict__ origin, const float* __restrict__ di
 // ---------------------------------------------------------------- spherical k-means (one CTA)
 constexpr int kKmThreads = 1024;
 constexpr int kKmMaxK = 64;
-constexpr double kFix = 1073741824.0;   // 2^30
+constexpr double kFix = 1073741824.0;   // 2^30 fixed point for order-independent (reproducible) sums
 
 __device__ __forceinline__ bool valid_normal(float x, float y, float z) {
   // losses.py:427-429: drop rows that are all zero / contain NaN / contain Inf
@@ -107,12 +107,42 @@ __device__ __forceinline__ int best_centroid(float x, float y, float z, const fl
   return best;
 }
 
+// Shared-memory plan (dynamic): training points xs[nt][3] (<= 256*K points, 60 KB at K=20).  Every Lloyd
+// iteration is (1) thread-per-point assignment (K dot products against the centroids in smem), (2) a WARP-
+// AGGREGATED integer reduction: the warp walks the distinct clusters present among its 32 points and folds
+// each cluster's members with redux.sync (fixed point 2^20, so the sums are order independent and the result is
+// bit-reproducible), one lane adds the warp total to the warp's PRIVATE accumulator row - no atomics, no
+// contention - (3) K*4 threads fold the 32 warp rows, and one warp updates / re-seeds / renormalises.
+constexpr float kKmFix = 1048576.0f;     // 2^20
+
+// folds (x,y,z,1) of the lanes whose `key` equals each distinct key into acc[key*4 + {0,1,2,3}] (warp-private row)
+__device__ __forceinline__ void warp_accumulate_by_key(int key, bool valid, float x, float y, float z, int* __restrict__ acc,
+                                                       int lane) {
+  const int fx = __float2int_rn(x * kKmFix), fy = __float2int_rn(y * kKmFix), fz = __float2int_rn(z * kKmFix);
+  unsigned remaining = __ballot_sync(0xffffffffu, valid);
+  while (remaining) {
+    const int leader = __ffs(remaining) - 1;
+    const int k = __shfl_sync(0xffffffffu, key, leader);
+    const bool mine = valid && key == k;
+    const unsigned m = __ballot_sync(0xffffffffu, mine);
+    const int sx = __reduce_add_sync(0xffffffffu, mine ? fx : 0);
+    const int sy = __reduce_add_sync(0xffffffffu, mine ? fy : 0);
+    const int sz = __reduce_add_sync(0xffffffffu, mine ? fz : 0);
+    if (lane == leader) { acc[4 * k] += sx; acc[4 * k + 1] += sy; acc[4 * k + 2] += sz; acc[4 * k + 3] += __popc(m); }
+    remaining &= ~m;
+  }
+  __syncwarp();
+}
+
 __global__ void __launch_bounds__(kKmThreads, 1)
 kmeans_kernel(const float* __restrict__ x, int64_t n, ncn_kmeans_params p, float* __restrict__ centroids,
-              int32_t* __restrict__ assign, int32_t* __restrict__ n_valid_out, int32_t* __restrict__ valid_idx) {
+              int32_t* __restrict__ assign, int32_t* __restrict__ n_valid_out, int32_t* __restrict__ valid_idx,
+              int nt_cap) {
+  extern __shared__ __align__(16) unsigned char km_smem[];
+  float* xs = reinterpret_cast<float*>(km_smem);                 // [nt_cap][3]
   __shared__ float s_c[kKmMaxK * 3];
-  __shared__ long long s_sum[kKmMaxK * 3];
-  __shared__ int s_cnt[kKmMaxK];
+  __shared__ int s_wacc[32][kKmMaxK * 4];   // per-warp private (sum x, y, z, count) per cluster, fixed point
+  __shared__ float s_acc[kKmMaxK * 4];
   __shared__ int s_nvalid, s_warp_tot[32], s_base;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int K = p.k;
@@ -145,52 +175,54 @@ kmeans_kernel(const float* __restrict__ x, int64_t n, ncn_kmeans_params p, float
     for (int j = tid; j < K * 3; j += kKmThreads) centroids[j] = 0.f;
     return;
   }
-  __threadfence_block();
+  // 2) training subset: at most max_points_per_centroid*K points, taken at a uniform stride over the valid rows
+  //    (faiss draws a random subset; equality with faiss is not a parity criterion), staged in shared memory
+  const int nt = nv > nt_cap ? nt_cap : nv;
+  for (int j = tid; j < nt; j += kKmThreads) {
+    const int r = valid_idx[(int)(((int64_t)j * nv) / nt)];
+    xs[3 * j] = x[3 * r]; xs[3 * j + 1] = x[3 * r + 1]; xs[3 * j + 2] = x[3 * r + 2];
+  }
   __syncthreads();
-  // 2) training subset: at most max_points_per_centroid*K points, taken at a uniform stride over
-  //    the valid rows (faiss draws a random subset; equality with faiss is not a parity criterion)
-  const int64_t cap = (int64_t)p.max_points_per_centroid * K;
-  const int nt = (int)(nv > cap ? cap : nv);
-  auto train_row = [&](int j) -> int { return valid_idx[(int)(((int64_t)j * nv) / nt)]; };
   // 3) init: K training points spread over the subset with a seeded offset
   if (tid < K) {
-    uint32_t h = (uint32_t)p.seed * 2654435761u + 12345u;
-    const int j = (int)((((int64_t)tid * nt) / K + (h % (uint32_t)(nt / K > 0 ? nt / K : 1))) % nt);
-    const int r = train_row(j);
-    float cx = x[3 * r], cy = x[3 * r + 1], cz = x[3 * r + 2];
+    const uint32_t h = (uint32_t)p.seed * 2654435761u + 12345u;
+    const int span = nt / K > 0 ? nt / K : 1;
+    const int j = (int)((((int64_t)tid * nt) / K + (h % (uint32_t)span)) % nt);
+    float cx = xs[3 * j], cy = xs[3 * j + 1], cz = xs[3 * j + 2];
     if (p.spherical) { const float l = sqrtf(cx * cx + cy * cy + cz * cz); if (l > 0.f) { cx /= l; cy /= l; cz /= l; } }
     s_c[3 * tid] = cx; s_c[3 * tid + 1] = cy; s_c[3 * tid + 2] = cz;
   }
   __syncthreads();
   // 4) Lloyd iterations
+  const int nt_round = (nt + 31) & ~31;
   for (int it = 0; it < p.niter; ++it) {
-    for (int j = tid; j < K * 3; j += kKmThreads) s_sum[j] = 0;
-    for (int j = tid; j < K; j += kKmThreads) s_cnt[j] = 0;
+    for (int a = lane; a < K * 4; a += 32) s_wacc[wid][a] = 0;
+    __syncwarp();
+    for (int j = tid; j < nt_round; j += kKmThreads) {
+      const bool v = j < nt;
+      float px = 0.f, py = 0.f, pz = 0.f;
+      int b = 0;
+      if (v) { px = xs[3 * j]; py = xs[3 * j + 1]; pz = xs[3 * j + 2]; b = best_centroid(px, py, pz, s_c, K); }
+      warp_accumulate_by_key(b, v, px, py, pz, s_wacc[wid], lane);
+    }
     __syncthreads();
-    for (int j = tid; j < nt; j += kKmThreads) {
-      const int r = train_row(j);
-      const float px = x[3 * r], py = x[3 * r + 1], pz = x[3 * r + 2];
-      const int b = best_centroid(px, py, pz, s_c, K);
-      atomicAdd((unsigned long long*)&s_sum[3 * b], (unsigned long long)(long long)llrint((double)px * kFix));
-      atomicAdd((unsigned long long*)&s_sum[3 * b + 1], (unsigned long long)(long long)llrint((double)py * kFix));
-      atomicAdd((unsigned long long*)&s_sum[3 * b + 2], (unsigned long long)(long long)llrint((double)pz * kFix));
-      atomicAdd(&s_cnt[b], 1);
+    if (tid < K * 4) {
+      long long t = 0;
+#pragma unroll 8
+      for (int w = 0; w < 32; ++w) t += s_wacc[w][tid];
+      s_acc[tid] = (tid & 3) == 3 ? (float)t : (float)((double)t / (double)kKmFix);
     }
     __syncthreads();
     if (tid == 0) {
       // new centroids = member means; empty clusters split the currently largest one (faiss-style +-eps)
       for (int j = 0; j < K; ++j) {
-        if (s_cnt[j] > 0) {
-          const double inv = 1.0 / ((double)s_cnt[j] * kFix);
-          s_c[3 * j] = (float)((double)s_sum[3 * j] * inv);
-          s_c[3 * j + 1] = (float)((double)s_sum[3 * j + 1] * inv);
-          s_c[3 * j + 2] = (float)((double)s_sum[3 * j + 2] * inv);
-        }
+        const float c = s_acc[4 * j + 3];
+        if (c > 0.f) { s_c[3 * j] = s_acc[4 * j] / c; s_c[3 * j + 1] = s_acc[4 * j + 1] / c; s_c[3 * j + 2] = s_acc[4 * j + 2] / c; }
       }
       for (int j = 0; j < K; ++j) {
-        if (s_cnt[j] == 0) {
+        if (s_acc[4 * j + 3] == 0.f) {
           int big = 0;
-          for (int q = 1; q < K; ++q) if (s_cnt[q] > s_cnt[big]) big = q;
+          for (int q = 1; q < K; ++q) if (s_acc[4 * q + 3] > s_acc[4 * big + 3]) big = q;
           const float eps = 1.0f / 1024.0f;
           for (int d = 0; d < 3; ++d) {
             const float v = s_c[3 * big + d];
@@ -198,7 +230,8 @@ kmeans_kernel(const float* __restrict__ x, int64_t n, ncn_kmeans_params p, float
             s_c[3 * j + d] = v * (1.f + sgn * eps);
             s_c[3 * big + d] = v * (1.f - sgn * eps);
           }
-          s_cnt[j] = s_cnt[big] / 2; s_cnt[big] -= s_cnt[j];
+          const float half = floorf(s_acc[4 * big + 3] * 0.5f);
+          s_acc[4 * j + 3] = half; s_acc[4 * big + 3] -= half;
         }
       }
       if (p.spherical) {
@@ -275,29 +308,40 @@ __device__ __forceinline__ float sgnf(float v) { return v > 0.f ? 1.f : (v < 0.f
 __global__ void __launch_bounds__(1024, 1)
 cluster_loss_fw_kernel(const float* __restrict__ nrm, const int32_t* __restrict__ labels, int64_t n,
                        float* __restrict__ losses, float* __restrict__ stats) {
+  __shared__ int s_wacc[32][16];
   __shared__ long long s_sum[9];
   __shared__ int s_cnt[3];
   __shared__ float s_c[9], s_mu[3];
   __shared__ float s_red[32][8];
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  if (tid < 9) s_sum[tid] = 0;
-  if (tid < 3) s_cnt[tid] = 0;
+  if (lane < 16) s_wacc[wid][lane] = 0;
+  __syncwarp();
+  const int64_t n_round = (n + 31) & ~(int64_t)31;
+  for (int64_t i = tid; i < n_round; i += blockDim.x) {
+    int l = 0;
+    float x = 0.f, y = 0.f, z = 0.f;
+    if (i < n) l = labels[i];
+    const bool v = l != 0;
+    int k = 0;
+    if (v) {
+      k = (l > 0 ? l : -l) - 1;
+      const float sg = l > 0 ? 1.f : -1.f;
+      x = sg * nrm[3 * i]; y = sg * nrm[3 * i + 1]; z = sg * nrm[3 * i + 2];
+    }
+    warp_accumulate_by_key(k, v, x, y, z, s_wacc[wid], lane);
+  }
   __syncthreads();
-  for (int64_t i = tid; i < n; i += blockDim.x) {
-    const int l = labels[i];
-    if (l == 0) continue;
-    const int k = (l > 0 ? l : -l) - 1;
-    const float s = l > 0 ? 1.f : -1.f;
-    atomicAdd((unsigned long long*)&s_sum[3 * k], (unsigned long long)(long long)llrint((double)(s * nrm[3 * i]) * kFix));
-    atomicAdd((unsigned long long*)&s_sum[3 * k + 1], (unsigned long long)(long long)llrint((double)(s * nrm[3 * i + 1]) * kFix));
-    atomicAdd((unsigned long long*)&s_sum[3 * k + 2], (unsigned long long)(long long)llrint((double)(s * nrm[3 * i + 2]) * kFix));
-    atomicAdd(&s_cnt[k], 1);
+  if (tid < 12) {
+    long long t = 0;
+    for (int w = 0; w < 32; ++w) t += s_wacc[w][tid];
+    const int k = tid >> 2, d = tid & 3;
+    if (d == 3) s_cnt[k] = (int)t; else s_sum[3 * k + d] = t;
   }
   __syncthreads();
   if (tid < 3) {
     const int k = tid;
     if (s_cnt[k] > 0) {
-      const double inv = 1.0 / ((double)s_cnt[k] * kFix);
+      const double inv = 1.0 / ((double)s_cnt[k] * (double)kKmFix);
       const float mx = (float)((double)s_sum[3 * k] * inv), my = (float)((double)s_sum[3 * k + 1] * inv), mz = (float)((double)s_sum[3 * k + 2] * inv);
       const float len = sqrtf(mx * mx + my * my + mz * mz);
       const float d = fmaxf(len, 1e-12f);
@@ -496,7 +540,13 @@ extern "C" int ncn_kmeans_spherical(const float* x, int64_t n_points, const ncn_
   NCN_CHECK_SIZE(n_points >= 0 && n_points < ((int64_t)1 << 31));
   if (n_points > 0) { NCN_CHECK_PTR(x); NCN_CHECK_PTR(assign); NCN_CHECK_PTR(workspace); }
   if (workspace_bytes < ncn_kmeans_workspace_bytes(n_points, p->k)) return NCN_E_SIZE;
-  kmeans_kernel<<<1, kKmThreads, 0, as_stream(stream)>>>(x, n_points, *p, centroids, assign, n_valid, (int32_t*)workspace);
+  int64_t cap = (int64_t)p->max_points_per_centroid * p->k;
+  if (cap > 14336) cap = 14336;            // 14336 * 12 B = 168 KB of dynamic shared memory (+ 41 KB static)
+  if (cap > n_points) cap = n_points > 0 ? n_points : 1;
+  const size_t smem = (size_t)cap * 12 + 16;
+  // static (41 KB) + dynamic shared memory exceed the 48 KB default: always opt in
+  NCN_CUDA(cudaFuncSetAttribute(kmeans_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 172 * 1024));
+  kmeans_kernel<<<1, kKmThreads, smem, as_stream(stream)>>>(x, n_points, *p, centroids, assign, n_valid, (int32_t*)workspace, (int)cap);
   NCN_LAUNCH_OK();
   return NCN_OK;
 }

@@ -27,6 +27,7 @@ namespace ncn {
 
 struct MarchCfg {
   int cascades, grid_size, max_samples;
+  int const_dt;            // exp_step_factor == 0: calc_dt(t) == dt_min for every finite t (t*0 = +-0)
   uint32_t grid_size3;
   float scale;             // mip_bound cap (train: scale; test: scale)
   float exp_step_factor;
@@ -36,6 +37,7 @@ struct MarchCfg {
 
 // calc_dt(t) - raymarching.cu:11-13 : clamp(t*f, lo, hi) = fmaxf(lo, fminf(t*f, hi))
 __device__ __forceinline__ float calc_dt(float t, const MarchCfg& c) {
+  if (c.const_dt) return c.dt_min;   // bit-identical: max(dt_min, min(+-0, dt_max)) with dt_max >= dt_min > 0
   return fmaxf(c.dt_min, fminf(__fmul_rn(t, c.exp_step_factor), c.dt_max));
 }
 
@@ -65,6 +67,7 @@ __device__ __forceinline__ Cell locate(float x, float y, float z, float dt, cons
   // scalbnf(1, mip-1): exact power of two
   const float p2 = __int_as_float((126 + mip) << 23);
   k.mip_bound = fminf(p2, c.scale);
+  // IEEE reciprocal (same value every iteration when cascades == 1: the compiler hoists it out of the loop)
   const float mb_inv = __frcp_rn(k.mip_bound);
   k.nx = cell_coord(x, mb_inv, c); k.ny = cell_coord(y, mb_inv, c); k.nz = cell_coord(z, mb_inv, c);
   const uint32_t idx = (uint32_t)mip * c.grid_size3 + morton3d((uint32_t)k.nx, (uint32_t)k.ny, (uint32_t)k.nz);
@@ -253,6 +256,7 @@ static int make_cfg(MarchCfg* c, int cascades, float scale, float dt_scale, floa
   c->dt_min = 1.73205080757f / (float)max_samples;
   volatile float two_sqrt3_scale = dt_scale * 3.4641015529632568359f;   // (SQRT3*2 folded)*scale
   c->dt_max = two_sqrt3_scale / (float)grid_size;
+  c->const_dt = (exp_step_factor == 0.0f && c->dt_max >= c->dt_min && c->dt_min > 0.0f) ? 1 : 0;
   c->gs_f = (float)grid_size; c->gs_inv = 1.0f / (float)grid_size; c->gs_m1 = (float)grid_size - 1.0f;
   return NCN_OK;
 }

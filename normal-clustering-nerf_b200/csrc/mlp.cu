@@ -98,8 +98,10 @@ __device__ __forceinline__ float act_out(float v, int act) {
 // ------------------------------------------------------------------------------ forward
 template <int IN, int OUT>
 __global__ void __launch_bounds__(kMlpThreads)
-mlp_fwd_kernel(const __half* __restrict__ x, const __half* __restrict__ w, int64_t n, int n_hidden, int out_act,
-               __half* __restrict__ out, __half* __restrict__ acts) {
+mlp_fwd_kernel(const __half* __restrict__ x, const __half* __restrict__ w, int64_t n_cap, const int32_t* __restrict__ n_dev,
+               int n_hidden, int out_act, __half* __restrict__ out, __half* __restrict__ acts) {
+  int64_t n = n_cap;
+  if (n_dev != nullptr) { const int64_t nd = *n_dev; if (nd < n) n = nd; }
   extern __shared__ __align__(16) __half smem[];
   __half* W0 = smem;                                   // [64][IN+8]
   __half* Wh = W0 + kW * (IN + kPad);                  // (n_hidden-1) x [64][72]
@@ -129,7 +131,7 @@ mlp_fwd_kernel(const __half* __restrict__ x, const __half* __restrict__ w, int64
 #pragma unroll
       for (int j = 0; j < 8; ++j) { c[j][0] = fmaxf(c[j][0], 0.f); c[j][1] = fmaxf(c[j][1], 0.f); c[j][2] = fmaxf(c[j][2], 0.f); c[j][3] = fmaxf(c[j][3], 0.f); }
       c_to_a64(c, h);
-      if (acts) store_a<kW>(acts + (int64_t)i * n * kW, row0, n, h, g, t);
+      if (acts) store_a<kW>(acts + (int64_t)i * n_cap * kW, row0, n, h, g, t);
     }
     float co[OUT / 8][4];
     warp_layer<kW, OUT>(h, Wl, co, g, t);
@@ -163,8 +165,10 @@ __device__ __forceinline__ void relu_mask(float (*c)[4], const __half* __restric
 template <int IN, int OUT>
 __global__ void __launch_bounds__(kMlpThreads)
 mlp_dgrad_kernel(const __half* __restrict__ w, const __half* __restrict__ out, const __half* __restrict__ acts,
-                 const __half* __restrict__ dout, int64_t n, int n_hidden, int out_act,
+                 const __half* __restrict__ dout, int64_t n_cap, const int32_t* __restrict__ n_dev, int n_hidden, int out_act,
                  __half* __restrict__ dz_last, __half* __restrict__ dz_hidden, __half* __restrict__ dx) {
+  int64_t n = n_cap;
+  if (n_dev != nullptr) { const int64_t nd = *n_dev; if (nd < n) n = nd; }
   extern __shared__ __align__(16) __half smem[];
   __half* WlT = smem;                                        // [64][OUT+8]   (Wl^T)
   __half* WhT = WlT + kW * (OUT + kPad);                     // (n_hidden-1) x [64][72]
@@ -200,9 +204,9 @@ mlp_dgrad_kernel(const __half* __restrict__ w, const __half* __restrict__ out, c
     warp_layer<OUT, kW>(dz, WlT, c, g, t);               // dL/dh (16 x 64)
     uint32_t dh[4][4];
     for (int i = n_hidden - 1; i >= 0; --i) {
-      relu_mask(c, acts + (int64_t)i * n * kW, row0, n, g, t);
+      relu_mask(c, acts + (int64_t)i * n_cap * kW, row0, n, g, t);
       c_to_a64(c, dh);
-      store_a<kW>(dz_hidden + (int64_t)i * n * kW, row0, n, dh, g, t);
+      store_a<kW>(dz_hidden + (int64_t)i * n_cap * kW, row0, n, dh, g, t);
       if (i > 0) warp_layer<kW, kW>(dh, WhT + (i - 1) * kW * (kW + kPad), c, g, t);
     }
     if (dx) {
@@ -224,8 +228,10 @@ mlp_dgrad_kernel(const __half* __restrict__ w, const __half* __restrict__ out, c
 constexpr int kChunk = 64;
 template <int M, int NN>
 __global__ void __launch_bounds__(kMlpThreads)
-mlp_wgrad_kernel(const __half* __restrict__ dz, const __half* __restrict__ a, int64_t n, float scale,
-                 float* __restrict__ grad_w) {
+mlp_wgrad_kernel(const __half* __restrict__ dz, const __half* __restrict__ a, int64_t n_cap, const int32_t* __restrict__ n_dev,
+                 float scale, float* __restrict__ grad_w) {
+  int64_t n = n_cap;
+  if (n_dev != nullptr) { const int64_t nd = *n_dev; if (nd < n) n = nd; }
   constexpr int TM = M / 16, TN = NN / 8, TOTAL = TM * TN;
   constexpr int PER = TOTAL >= 4 ? TOTAL / 4 : 1;
   static_assert(TOTAL < 4 || TOTAL % 4 == 0, "tile split");
@@ -320,28 +326,31 @@ extern "C" size_t ncn_mlp_bwd_workspace_bytes(const ncn_mlp_desc* d, int64_t n) 
 }
 
 template <int IN, int OUT>
-static int launch_fwd(const ncn_mlp_desc* d, const void* x, const void* w, int64_t n, void* out, void* acts, cudaStream_t st) {
+static int launch_fwd(const ncn_mlp_desc* d, const void* x, const void* w, int64_t n, void* out, void* acts, const int32_t* n_dev,
+                      cudaStream_t st) {
   const size_t smem = (size_t)(64 * (IN + kPad) + (d->n_hidden - 1) * 64 * (64 + kPad) + OUT * (64 + kPad)) * sizeof(__half);
   auto k = mlp_fwd_kernel<IN, OUT>;
   if (smem > 48 * 1024) NCN_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int grid = persistent_grid(((n + 15) / 16) * 32, kMlpThreads, 8);
-  k<<<grid, kMlpThreads, smem, st>>>((const __half*)x, (const __half*)w, n, d->n_hidden, d->out_activation, (__half*)out, (__half*)acts);
+  k<<<grid, kMlpThreads, smem, st>>>((const __half*)x, (const __half*)w, n, n_dev, d->n_hidden, d->out_activation, (__half*)out,
+                                     (__half*)acts);
   NCN_LAUNCH_OK();
   return NCN_OK;
 }
 
 template <int M, int NN>
-static int launch_wgrad(const __half* dz, const __half* a, int64_t n, float scale, float* gw, cudaStream_t st) {
+static int launch_wgrad(const __half* dz, const __half* a, int64_t n, const int32_t* n_dev, float scale, float* gw, cudaStream_t st) {
   const int64_t chunks = (n + kChunk - 1) / kChunk;
   int64_t grid = (int64_t)sm_count() * 4;
   if (grid > chunks) grid = chunks;
-  mlp_wgrad_kernel<M, NN><<<(int)grid, kMlpThreads, 0, st>>>(dz, a, n, scale, gw);
+  mlp_wgrad_kernel<M, NN><<<(int)grid, kMlpThreads, 0, st>>>(dz, a, n, n_dev, scale, gw);
   NCN_LAUNCH_OK();
   return NCN_OK;
 }
 
-static int wgrad_dispatch(int M, int NN, const __half* dz, const __half* a, int64_t n, float scale, float* gw, cudaStream_t st) {
-#define NCN_WG(MM, N2) if (M == MM && NN == N2) return launch_wgrad<MM, N2>(dz, a, n, scale, gw, st);
+static int wgrad_dispatch(int M, int NN, const __half* dz, const __half* a, int64_t n, const int32_t* n_dev, float scale, float* gw,
+                          cudaStream_t st) {
+#define NCN_WG(MM, N2) if (M == MM && NN == N2) return launch_wgrad<MM, N2>(dz, a, n, n_dev, scale, gw, st);
   NCN_WG(64, 16) NCN_WG(64, 32) NCN_WG(64, 48) NCN_WG(64, 64)
   NCN_WG(16, 64) NCN_WG(32, 64) NCN_WG(48, 64)
 #undef NCN_WG
@@ -350,26 +359,27 @@ static int wgrad_dispatch(int M, int NN, const __half* dz, const __half* a, int6
 
 template <int IN, int OUT>
 static int launch_bwd(const ncn_mlp_desc* d, const void* x, const void* w, const void* out, const void* acts,
-                      const void* dout, int64_t n, float* grad_w, void* dx, float grad_scale, void* scratch, cudaStream_t st) {
+                      const void* dout, int64_t n, float* grad_w, void* dx, float grad_scale, void* scratch, const int32_t* n_dev,
+                      cudaStream_t st) {
   __half* dz_last = (__half*)scratch;
   __half* dz_hidden = dz_last + (size_t)n * OUT;
   const size_t smem = (size_t)(64 * (OUT + kPad) + (d->n_hidden - 1) * 64 * (64 + kPad) + (dx ? IN * (64 + kPad) : 0)) * sizeof(__half);
   auto k = mlp_dgrad_kernel<IN, OUT>;
   if (smem > 48 * 1024) NCN_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int grid = persistent_grid(((n + 15) / 16) * 32, kMlpThreads, 8);
-  k<<<grid, kMlpThreads, smem, st>>>((const __half*)w, (const __half*)out, (const __half*)acts, (const __half*)dout, n,
+  k<<<grid, kMlpThreads, smem, st>>>((const __half*)w, (const __half*)out, (const __half*)acts, (const __half*)dout, n, n_dev,
                                      d->n_hidden, d->out_activation, dz_last, dz_hidden, (__half*)dx);
   NCN_LAUNCH_OK();
   if (grad_w) {
     // layer 0: dz_hidden[0]^T x
-    int rc = wgrad_dispatch(64, IN, dz_hidden, (const __half*)x, n, grad_scale, grad_w, st);
+    int rc = wgrad_dispatch(64, IN, dz_hidden, (const __half*)x, n, n_dev, grad_scale, grad_w, st);
     if (rc) return rc;
     for (int i = 1; i < d->n_hidden; ++i) {
-      rc = wgrad_dispatch(64, 64, dz_hidden + (size_t)i * n * 64, (const __half*)acts + (size_t)(i - 1) * n * 64, n, grad_scale,
+      rc = wgrad_dispatch(64, 64, dz_hidden + (size_t)i * n * 64, (const __half*)acts + (size_t)(i - 1) * n * 64, n, n_dev, grad_scale,
                           grad_w + 64 * IN + (size_t)(i - 1) * 64 * 64, st);
       if (rc) return rc;
     }
-    rc = wgrad_dispatch(OUT, 64, dz_last, (const __half*)acts + (size_t)(d->n_hidden - 1) * n * 64, n, grad_scale,
+    rc = wgrad_dispatch(OUT, 64, dz_last, (const __half*)acts + (size_t)(d->n_hidden - 1) * n * 64, n, n_dev, grad_scale,
                         grad_w + 64 * IN + (size_t)(d->n_hidden - 1) * 64 * 64, st);
     if (rc) return rc;
   }
@@ -388,19 +398,19 @@ static int launch_bwd(const ncn_mlp_desc* d, const void* x, const void* w, const
   return NCN_E_CONFIG;
 
 extern "C" int ncn_mlp_fwd(const ncn_mlp_desc* d, const void* x, const void* w, int64_t n, void* out, void* acts,
-                           ncn_stream_t stream) {
+                           const int32_t* n_dev, ncn_stream_t stream) {
   int ip, op;
   int rc = check_desc(d, &ip, &op); if (rc) return rc;
   NCN_CHECK_SIZE(n >= 0);
   if (n == 0) return NCN_OK;
   NCN_CHECK_PTR(x); NCN_CHECK_PTR(w); NCN_CHECK_PTR(out);
   if (((uintptr_t)x | (uintptr_t)w | (uintptr_t)out | (uintptr_t)acts) & 15) return NCN_E_ALIGN;
-  NCN_MLP_DISPATCH(ip, op, (launch_fwd<kI, kO>(d, x, w, n, out, acts, as_stream(stream))))
+  NCN_MLP_DISPATCH(ip, op, (launch_fwd<kI, kO>(d, x, w, n, out, acts, n_dev, as_stream(stream))))
 }
 
 extern "C" int ncn_mlp_bwd(const ncn_mlp_desc* d, const void* x, const void* w, const void* out, const void* acts,
                            const void* dL_dout, int64_t n, float* grad_w, void* dL_dx, float grad_scale, void* scratch,
-                           size_t scratch_bytes, ncn_stream_t stream) {
+                           size_t scratch_bytes, const int32_t* n_dev, ncn_stream_t stream) {
   int ip, op;
   int rc = check_desc(d, &ip, &op); if (rc) return rc;
   NCN_CHECK_SIZE(n >= 0);
@@ -409,5 +419,5 @@ extern "C" int ncn_mlp_bwd(const ncn_mlp_desc* d, const void* x, const void* w, 
   if (scratch_bytes < ncn_mlp_bwd_workspace_bytes(d, n)) return NCN_E_SIZE;
   if (((uintptr_t)x | (uintptr_t)w | (uintptr_t)out | (uintptr_t)acts | (uintptr_t)dL_dout | (uintptr_t)scratch | (uintptr_t)dL_dx) & 15)
     return NCN_E_ALIGN;
-  NCN_MLP_DISPATCH(ip, op, (launch_bwd<kI, kO>(d, x, w, out, acts, dL_dout, n, grad_w, dL_dx, grad_scale, scratch, as_stream(stream))))
+  NCN_MLP_DISPATCH(ip, op, (launch_bwd<kI, kO>(d, x, w, out, acts, dL_dout, n, grad_w, dL_dx, grad_scale, scratch, n_dev, as_stream(stream))))
 }

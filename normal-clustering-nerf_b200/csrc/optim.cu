@@ -25,7 +25,8 @@ __device__ __forceinline__ void adam_one(float& p, float& g, float& m, float& v,
 __global__ void __launch_bounds__(256)
 adam_kernel(float* __restrict__ param, float* __restrict__ grad, float* __restrict__ m, float* __restrict__ v,
             __half* __restrict__ p16, int64_t n, AdamArgs a, const float* __restrict__ grad_div,
-            const int32_t* __restrict__ skip, const float* __restrict__ clip_coef) {
+            const int32_t* __restrict__ skip, const float* __restrict__ clip_coef, const float* __restrict__ lr_bc) {
+  if (lr_bc != nullptr) { a.lr = lr_bc[0]; a.bc1 = lr_bc[1]; a.bc2 = lr_bc[2]; }   // device-side schedule (CUDA-graph replay)
   const bool do_skip = skip != nullptr && *skip != 0;
   float gmul = 1.f;
   if (grad_div) gmul = 1.f / *grad_div;
@@ -106,7 +107,7 @@ using namespace ncn;
 extern "C" int ncn_adam_step(float* param, float* grad, float* m, float* v, void* param_f16, int64_t n, float lr,
                              float beta1, float beta2, float eps, float weight_decay, int step,
                              const float* grad_div_dev, const int32_t* skip_dev, const float* clip_coef_dev,
-                             ncn_stream_t stream) {
+                             const float* lr_bc_dev, ncn_stream_t stream) {
   NCN_CHECK_SIZE(n >= 0 && step >= 1);
   if (n == 0) return NCN_OK;
   NCN_CHECK_PTR(param); NCN_CHECK_PTR(grad); NCN_CHECK_PTR(m); NCN_CHECK_PTR(v);
@@ -117,7 +118,7 @@ extern "C" int ncn_adam_step(float* param, float* grad, float* m, float* v, void
   a.bc1 = 1.0f - powf(beta1, (float)step); a.bc2 = 1.0f - powf(beta2, (float)step);
   const int grid = persistent_grid((n + 3) / 4, 256, 8);
   adam_kernel<<<grid, 256, 0, as_stream(stream)>>>(param, grad, m, v, (__half*)param_f16, n, a, grad_div_dev, skip_dev,
-                                                   clip_coef_dev);
+                                                   clip_coef_dev, lr_bc_dev);
   NCN_LAUNCH_OK();
   return NCN_OK;
 }

@@ -1,0 +1,281 @@
+"""FusedStep - the sync-free, CUDA-graph-captured training step (the B200-native form of
+NeRFSystem.training_step, train_nerf.py:314-367, for the RGB+depth ngp_mt configuration with the opacity and
+Manhattan normal-clustering losses).
+
+Same arithmetic as the module path (ncn_b200.rendering.render + ncn_b200.losses.NeRFMTLoss + autograd +
+FlatAdam), but expressed as one linear sequence of libncn kernels on pre-allocated arenas:
+
+  aabb+near -> march (count, scan, expand into a capacity-sized arena; the sample count stays ON THE DEVICE) ->
+  grid encode (input normalisation fused) -> sigma MLP -> [d/|d|, h, 1] + TruncExp -> rgb MLP -> raws ->
+  composite fw -> photometric+opacity loss (+gradient) -> normals-from-depth -> k-means -> triple selection ->
+  cluster loss (+gradient) -> normals bw -> composite bw -> rgb MLP bw -> dh -> sigma MLP bw -> grid bw ->
+  [NCCL all-reduce] -> sum-of-squares -> clip coefficient -> fused Adam (x2 groups)
+
+No torch op, no autograd graph, no allocation and no host synchronisation happen inside the step, so it is
+captured once into a CUDA graph and replayed (the reference's step has >= 6 host syncs).
+Host-visible scalars (losses, sample counts) are read back lazily from a small stats buffer.
+"""
+import ctypes as C
+import math
+
+import torch
+
+from . import _lib
+from ._lib import check, ptr
+
+GSCALE = 131072.0      # 2^17: loss scale carried by the fp16 dL/dy tensors (the module path uses 1024 * 128)
+
+
+class FusedStep:
+    def __init__(self, trainer, capacity_per_ray=64, use_graph=True):
+        self.tr = trainer
+        self.model = m = trainer.model
+        self.opt = trainer.opt
+        self.hp = trainer.hp
+        if m.pred_sem or m.pred_norm:
+            raise NotImplementedError("FusedStep covers the RGB+depth configuration; extra heads use the module path")
+        self.dev = dev = trainer.device
+        self.R = R = self.hp["batch_size"]
+        self.cap = cap = int(R * capacity_per_ray)
+        self.use_graph = use_graph
+        self.graph = None
+        self.L = _lib.lib()
+        f32 = dict(dtype=torch.float32, device=dev); f16 = dict(dtype=torch.float16, device=dev)
+        E = lambda *s, **k: torch.empty(*s, **k)
+        # static inputs
+        self.rays_o, self.rays_d, self.target = E(R, 3, **f32), E(R, 3, **f32), E(R, 3, **f32)
+        self.noise = E(R, **f32)
+        self.tri = None                      # (3, M) int64
+        # marching
+        self.hits_t = E(R, 1, 2, **f32)
+        self.rays_a = E(R, 3, dtype=torch.int64, device=dev)
+        self.counter = torch.zeros(2, dtype=torch.int32, device=dev)
+        ws_bytes = self.L.ncn_march_train_workspace_bytes(R, self.hp["rend_max_samples"])
+        self.march_ws = E(ws_bytes, dtype=torch.uint8, device=dev)
+        self.xyzs, self.dirs = torch.zeros(cap, 3, **f32), torch.zeros(cap, 3, **f32)
+        self.deltas, self.ts = torch.zeros(cap, **f32), torch.zeros(cap, **f32)
+        # field
+        self.feat, self.h = E(cap, 32, **f16), E(cap, 16, **f16)
+        self.sig_acts = E(1, cap, 64, **f16)
+        self.x_rgb, self.rgb_out, self.rgb_acts = E(cap, 32, **f16), E(cap, 16, **f16), E(2, cap, 64, **f16)
+        self.sigmas, self.raws = E(cap, **f32), E(cap, 3, **f32)
+        # compositing + loss
+        self.total_samples = E(R, dtype=torch.int64, device=dev)
+        self.opacity, self.depth, self.rend, self.ws = E(R, **f32), E(R, **f32), E(R, 3, **f32), E(cap, **f32)
+        self.rgb = E(R, 3, **f32)
+        self.zeros = torch.zeros(8, **f32)          # [0:2] photometric sums, [2] grad sumsq, [3] non-finite flag (as int bits)
+        self.d_rend, self.d_opacity, self.d_depth = E(R, 3, **f32), E(R, **f32), torch.zeros(R, **f32)
+        self.losses, self.stats, self.weights = E(3, **f32), E(32, **f32), torch.zeros(3, **f32)
+        self.d_sigmas, self.d_raws = E(cap, **f32), E(cap, 3, **f32)
+        self.dout_rgb, self.dx_rgb, self.dh, self.dfeat = E(cap, 16, **f16), E(cap, 32, **f16), E(cap, 16, **f16), E(cap, 32, **f16)
+        nb = max(self.L.ncn_mlp_bwd_workspace_bytes(C.byref(m.rgb_net.desc), cap),
+                 self.L.ncn_mlp_bwd_workspace_bytes(C.byref(m.sigma_net.desc), cap))
+        self.mlp_ws = E(nb, dtype=torch.uint8, device=dev)
+        # fp16 parameter copies (owned by the optimizer, refreshed by its Adam kernel each step)
+        self.flat16 = self.opt.flat16
+        # per-step schedule scalars (lr, bc1, bc2, w_ort, w_dot, w_l1): a ring of pinned host slots feeds one device
+        # slot with an async H2D per step; the ring + an event throttle keep the host from overwriting a slot
+        # whose copy has not executed yet
+        self.RING = 64
+        self.host_sched = torch.zeros(self.RING, 6, dtype=torch.float32).pin_memory()
+        self.ring_events = [None] * self.RING
+        self.ring_pos = 0
+        self.dev_sched = torch.zeros(6, **f32)
+        self.coef = torch.ones(1, **f32)
+        self.flag = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.grad_div = torch.tensor([float(trainer.world_size)], **f32)
+        self.xform = (C.c_float * 6)(*([float(m.xyz_min[0, i]) for i in range(3)] + [float((m.xyz_max - m.xyz_min)[0, i]) for i in range(3)]))
+        self.bg = (C.c_float * 3)(1.0, 1.0, 1.0) if self.hp["exp_step_factor"] == 0 else (C.c_float * 3)(0.0, 0.0, 0.0)
+        self.km_params = _lib.KmeansParams(20, 20, 1234, 256, 1)
+        self._offsets()
+        self._alloc_tri(None)
+
+    def _offsets(self):
+        """slices of the flat parameter / gradient buffers per module (hash table first: FlatAdam order)"""
+        opt, m = self.opt, self.model
+        base = opt.flat.data_ptr()
+        self.off = {}
+        for name in ("xyz_encoder", "sigma_net", "rgb_net"):
+            p = getattr(m, name).params
+            o = (p.data_ptr() - base) // 4
+            self.off[name] = (o, p.numel())
+
+    def _alloc_tri(self, tri):
+        dev = self.dev
+        M = 0 if tri is None else tri.shape[1]
+        self.tri = tri
+        self.M = M
+        self.normals = torch.empty(max(M, 1), 3, dtype=torch.float32, device=dev)
+        self.dn = torch.empty(max(M, 1), 3, dtype=torch.float32, device=dev)
+        self.assign = torch.empty(max(M, 1), dtype=torch.int32, device=dev)
+        self.labels = torch.empty(max(M, 1), dtype=torch.int32, device=dev)
+        self.centroids = torch.empty(20, 3, dtype=torch.float32, device=dev)
+        self.n_valid = torch.empty(1, dtype=torch.int32, device=dev)
+        self.sel = torch.empty(3, dtype=torch.int32, device=dev)
+        self.km_ws = torch.empty(self.L.ncn_kmeans_workspace_bytes(max(M, 1), 20), dtype=torch.uint8, device=dev)
+
+    # ------------------------------------------------------------------ the kernel sequence
+    def _w16(self, name):
+        o, n = self.off[name]
+        return self.flat16[o:o + n]
+
+    def _g32(self, name):
+        o, n = self.off[name]
+        return self.opt.grad[o:o + n]
+
+    def _run(self):
+        L, m, hp = self.L, self.model, self.hp
+        st = torch.cuda.current_stream().cuda_stream
+        R, cap = self.R, self.cap
+        n_dev = ptr(self.counter)
+        ck = check
+        self.zeros.zero_()
+        self.d_depth.zero_()
+        ck(L.ncn_ray_aabb_near(ptr(self.rays_o), ptr(self.rays_d), ptr(m.center), ptr(m.half_size), float(hp["rend_near_dist"]), R,
+                               ptr(self.hits_t), st), "aabb")
+        ck(L.ncn_march_train(ptr(self.rays_o), ptr(self.rays_d), ptr(self.hits_t), ptr(m.density_bitfield), m.cascades,
+                             float(m.scale), float(hp["exp_step_factor"]), ptr(self.noise), m.grid_size, hp["rend_max_samples"], R,
+                             cap, ptr(self.rays_a), ptr(self.xyzs), ptr(self.dirs), ptr(self.deltas), ptr(self.ts), ptr(self.counter),
+                             ptr(self.march_ws), self.march_ws.numel(), st), "march")
+        enc, sg, rgbn = m.xyz_encoder, m.sigma_net, m.rgb_net
+        ck(L.ncn_grid_fwd(C.byref(enc.desc), ptr(self.xyzs), ptr(self._w16("xyz_encoder")), cap, ptr(self.feat), self.xform, n_dev, st), "grid_fwd")
+        ck(L.ncn_mlp_fwd(C.byref(sg.desc), ptr(self.feat), ptr(self._w16("sigma_net")), cap, ptr(self.h), ptr(self.sig_acts), n_dev, st), "sigma_fwd")
+        ck(L.ncn_field_prepare_rgb(ptr(self.dirs), ptr(self.h), cap, n_dev, ptr(self.x_rgb), ptr(self.sigmas), st), "prepare_rgb")
+        ck(L.ncn_mlp_fwd(C.byref(rgbn.desc), ptr(self.x_rgb), ptr(self._w16("rgb_net")), cap, ptr(self.rgb_out), ptr(self.rgb_acts), n_dev, st), "rgb_fwd")
+        ck(L.ncn_field_head_out(ptr(self.rgb_out), 16, cap, n_dev, ptr(self.raws), 3, 0, 3, st), "head_out")
+        ck(L.ncn_composite_train_fw(ptr(self.sigmas), ptr(self.raws), ptr(self.deltas), ptr(self.ts), ptr(self.rays_a), 1e-4, R, cap, 3,
+                                    ptr(self.total_samples), ptr(self.opacity), ptr(self.depth), ptr(self.rend), ptr(self.ws), st), "composite_fw")
+        # ---- losses (+ their gradients w.r.t. the rendered quantities)
+        ck(L.ncn_photometric_loss(ptr(self.rend), ptr(self.opacity), ptr(self.target), R, 3, self.bg, float(hp["loss_opacity_w"]), GSCALE,
+                                  ptr(self.rgb), ptr(self.zeros), ptr(self.d_rend), ptr(self.d_opacity), st), "photometric")
+        if self.M > 0:
+            x1, x2, x3 = ptr(self.tri[0]), ptr(self.tri[1]), ptr(self.tri[2])
+            # rays_o := rays_d (rendering.py:227 quirk)
+            ck(L.ncn_normals_from_depth_fw(ptr(self.rays_d), ptr(self.rays_d), ptr(self.depth), x1, x2, x3, self.M, ptr(self.normals), st), "normals_fw")
+            ck(L.ncn_kmeans_spherical(ptr(self.normals), self.M, C.byref(self.km_params), ptr(self.centroids), ptr(self.assign),
+                                      ptr(self.n_valid), ptr(self.km_ws), self.km_ws.numel(), st), "kmeans")
+            ck(L.ncn_cluster_select(ptr(self.centroids), ptr(self.assign), self.M, 20, 1.0 - float(hp["loss_norm_can_tres"]),
+                                    ptr(self.labels), ptr(self.sel), st), "select")
+            ck(L.ncn_cluster_loss_fw(ptr(self.normals), ptr(self.labels), self.M, ptr(self.losses), ptr(self.stats), st), "cluster_fw")
+            ck(L.ncn_cluster_loss_bw(ptr(self.normals), ptr(self.labels), self.M, ptr(self.stats), ptr(self.weights), ptr(self.dn), st), "cluster_bw")
+            ck(L.ncn_normals_from_depth_bw(ptr(self.rays_d), ptr(self.rays_d), ptr(self.depth), x1, x2, x3, ptr(self.dn), self.M,
+                                           ptr(self.d_depth), st), "normals_bw")
+        # ---- backward
+        ck(L.ncn_composite_train_bw(ptr(self.d_opacity), ptr(self.d_depth), ptr(self.d_rend), None, ptr(self.sigmas), ptr(self.raws), ptr(self.ws),
+                                    ptr(self.deltas), ptr(self.ts), ptr(self.rays_a), ptr(self.opacity), ptr(self.depth), ptr(self.rend), 1e-4,
+                                    R, cap, 3, ptr(self.d_sigmas), ptr(self.d_raws), st), "composite_bw")
+        ck(L.ncn_field_head_dout(ptr(self.d_raws), 3, 0, 3, 1.0, cap, n_dev, ptr(self.dout_rgb), 16, st), "head_dout")
+        inv = 1.0 / GSCALE
+        ck(L.ncn_mlp_bwd(C.byref(rgbn.desc), ptr(self.x_rgb), ptr(self._w16("rgb_net")), ptr(self.rgb_out), ptr(self.rgb_acts), ptr(self.dout_rgb),
+                         cap, ptr(self._g32("rgb_net")), ptr(self.dx_rgb), inv, ptr(self.mlp_ws), self.mlp_ws.numel(), n_dev, st), "rgb_bwd")
+        ck(L.ncn_field_bwd_h(ptr(self.dx_rgb), ptr(self.d_sigmas), ptr(self.h), None, None, 1.0, cap, n_dev, ptr(self.dh), st), "bwd_h")
+        ck(L.ncn_mlp_bwd(C.byref(sg.desc), ptr(self.feat), ptr(self._w16("sigma_net")), ptr(self.h), ptr(self.sig_acts), ptr(self.dh), cap,
+                         ptr(self._g32("sigma_net")), ptr(self.dfeat), inv, ptr(self.mlp_ws), self.mlp_ws.numel(), n_dev, st), "sigma_bwd")
+        ck(L.ncn_grid_bwd(C.byref(enc.desc), ptr(self.xyzs), ptr(self.dfeat), cap, ptr(self._g32("xyz_encoder")), inv, self.xform, n_dev, st), "grid_bwd")
+
+    def _optimizer(self):
+        L, opt = self.L, self.opt
+        st = torch.cuda.current_stream().cuda_stream
+        sumsq = self.zeros[2:3]
+        self.flag.zero_()
+        check(L.ncn_grad_sumsq(ptr(opt.grad), opt.grad.numel(), ptr(self.grad_div), ptr(sumsq), ptr(self.flag), st), "sumsq")
+        check(L.ncn_clip_coef(ptr(sumsq), float(self.hp["grad_clip"]), ptr(self.coef), st), "clip")
+        for (start, n, wd) in opt.groups:
+            sl = slice(start, start + n)
+            check(L.ncn_adam_step(ptr(opt.flat[sl]), ptr(opt.grad[sl]), ptr(opt.m[sl]), ptr(opt.v[sl]), ptr(self.flat16[sl]), n, 0.0,
+                                  opt.betas[0], opt.betas[1], opt.eps, wd, 1, ptr(self.grad_div), ptr(self.flag), ptr(self.coef),
+                                  ptr(self.dev_sched), st), "adam")
+
+    # ------------------------------------------------------------------ public
+    def set_triangles(self, tri):
+        tri = tri.to(self.dev, torch.int64).contiguous()
+        if self.tri is None or tri.shape != self.tri.shape:
+            self._alloc_tri(tri)
+            self.graph = None
+        else:
+            self.tri.copy_(tri)
+
+    def _schedule(self):
+        tr, hp, opt = self.tr, self.hp, self.opt
+        opt.step_count += 1
+        t = opt.step_count
+        ls = tr.loss
+        step = tr.global_step
+        on = (step <= ls.can_sched_end) or (ls.can_sched_end == -1)
+        slot = self.ring_pos % self.RING
+        self.ring_pos += 1
+        if self.ring_events[slot] is not None:
+            self.ring_events[slot].synchronize()        # the copy issued RING steps ago has executed
+        h = self.host_sched[slot]
+        h[0] = tr.lr_now(); h[1] = 1 - opt.betas[0] ** t; h[2] = 1 - opt.betas[1] ** t
+        h[3] = ls.w_sched(ls.w_ort, step) * GSCALE if on else 0.0
+        h[4] = ls.w_sched(ls.w_dot, step) * GSCALE if on else 0.0
+        h[5] = ls.w_sched(ls.w_l1, step) * GSCALE if on else 0.0
+        self.dev_sched.copy_(h, non_blocking=True)
+        self.weights.copy_(self.dev_sched[3:6])
+        ev = torch.cuda.Event()
+        ev.record()
+        self.ring_events[slot] = ev
+
+    def step(self, rays_o, rays_d, target_rgb, noise=None):
+        """one training step; inputs are device tensors (copied into the graph's static buffers)"""
+        tr = self.tr
+        self.rays_o.copy_(rays_o); self.rays_d.copy_(rays_d); self.target.copy_(target_rgb)
+        if noise is None:
+            self.noise.uniform_()
+        else:
+            self.noise.copy_(noise)
+        self._schedule()
+        multi = tr.world_size > 1
+        if not self.use_graph:
+            self._run()
+            if multi:
+                tr.comm.allreduce_sum_(self.opt.grad)
+            self._optimizer()
+        else:
+            if self.graph is None:
+                self._capture(multi)
+            self.graph[0].replay()
+            if multi:
+                tr.comm.allreduce_sum_(self.opt.grad)
+                self.graph[1].replay()
+        tr.global_step += 1
+
+    def _capture(self, multi):
+        # warm-up on a side stream (sets function attributes, touches every buffer), then capture
+        self.opt.grad.zero_()
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        keep = (self.opt.flat.clone(), self.opt.m.clone(), self.opt.v.clone(), self.flat16.clone())
+        with torch.cuda.stream(s):
+            self._run()
+            self._optimizer()
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        # undo the warm-up update
+        self.opt.flat.copy_(keep[0]); self.opt.m.copy_(keep[1]); self.opt.v.copy_(keep[2]); self.flat16.copy_(keep[3])
+        self.opt.grad.zero_()
+        g0 = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g0):
+            self._run()
+            if not multi:
+                self._optimizer()
+        g1 = None
+        if multi:
+            g1 = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g1):
+                self._optimizer()
+        self.graph = (g0, g1)
+
+    def stats_host(self):
+        """(loss dict, n_samples) - synchronises; call outside the timed region"""
+        torch.cuda.synchronize()
+        R = self.R
+        z = self.zeros.cpu()
+        d = {"rgb": float(z[0]) / (3 * R), "opacity": float(self.hp["loss_opacity_w"]) * float(z[1]) / R}
+        if self.M > 0:
+            l = torch.nan_to_num(self.losses.cpu())
+            w = self.weights.cpu() / GSCALE
+            d.update(norm_D_C_ort_dot=float(w[0] * l[0]), norm_D_C_centr_dot=float(w[1] * l[1]), norm_D_C_centr_L1=float(w[2] * l[2]))
+        d["total"] = sum(d.values())
+        return d, int(self.counter[0])

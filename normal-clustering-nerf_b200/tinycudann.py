@@ -26,6 +26,8 @@ SEED = 1337
 
 def _half_copy(module):
     """fp16 copy of the fp32 master params, refreshed only when the parameter changed."""
+    if module._half_key == "flat":        # a FlatAdam owns the fp16 copy and refreshes it inside its Adam kernel
+        return module._half
     p = module.params
     key = (p.data_ptr(), p._version, p.device)
     if module._half_key != key:
@@ -58,7 +60,7 @@ class _GridBackwardFn(torch.autograd.Function):
         L = _lib.lib()
         dy_s = (dy.float() * LOSS_SCALE).to(torch.float16).contiguous()
         grad = torch.zeros_like(params, dtype=torch.float32)
-        check(L.ncn_grid_bwd(C.byref(mod.desc), ptr(x), ptr(dy_s), n, ptr(grad), 1.0 / LOSS_SCALE, stream()), "grid_bwd")
+        check(L.ncn_grid_bwd(C.byref(mod.desc), ptr(x), ptr(dy_s), n, ptr(grad), 1.0 / LOSS_SCALE, None, None, stream()), "grid_bwd")
         dx = None
         if need_dx:
             dx = torch.empty(n, 3, dtype=torch.float32, device=x.device)
@@ -94,7 +96,7 @@ class _GridFn(torch.autograd.Function):
         table = _half_copy(mod)
         n = x.shape[0]
         out = torch.empty(n, mod.n_output_dims, dtype=torch.float16, device=x.device)
-        check(_lib.lib().ncn_grid_fwd(C.byref(mod.desc), ptr(x), ptr(table), n, ptr(out), stream()), "grid_fwd")
+        check(_lib.lib().ncn_grid_fwd(C.byref(mod.desc), ptr(x), ptr(table), n, ptr(out), None, None, stream()), "grid_fwd")
         ctx.mod = mod
         ctx.save_for_backward(x, params)
         return out
@@ -176,7 +178,7 @@ class _MlpFn(torch.autograd.Function):
         out = torch.empty(n, mod.out_pad, dtype=torch.float16, device=dev)
         keep = ctx.needs_input_grad[1] or ctx.needs_input_grad[2]
         acts = torch.empty(mod.n_hidden, n, 64, dtype=torch.float16, device=dev) if keep else None
-        check(_lib.lib().ncn_mlp_fwd(C.byref(mod.desc), ptr(xp), ptr(w), n, ptr(out), ptr(acts), stream()), "mlp_fwd")
+        check(_lib.lib().ncn_mlp_fwd(C.byref(mod.desc), ptr(xp), ptr(w), n, ptr(out), ptr(acts), None, stream()), "mlp_fwd")
         ctx.mod = mod
         ctx.x_dtype = x.dtype
         ctx.save_for_backward(xp, out, acts, w)
@@ -197,7 +199,7 @@ class _MlpFn(torch.autograd.Function):
         nbytes = L.ncn_mlp_bwd_workspace_bytes(C.byref(mod.desc), n)
         ws = _Workspace.get(dev, nbytes)
         check(L.ncn_mlp_bwd(C.byref(mod.desc), ptr(xp), ptr(w), ptr(out), ptr(acts), ptr(d), n, ptr(grad), ptr(dx),
-                            1.0 / LOSS_SCALE, ptr(ws), ws.numel(), stream()), "mlp_bwd")
+                            1.0 / LOSS_SCALE, ptr(ws), ws.numel(), None, stream()), "mlp_bwd")
         gx = None
         if need_dx:
             gx = (dx[:, :mod.n_input_dims].float() / LOSS_SCALE).to(ctx.x_dtype)

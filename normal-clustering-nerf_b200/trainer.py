@@ -96,6 +96,9 @@ class FlatAdam:
                 off += (k + 3) // 4 * 4
             if off > start:
                 self.groups.append((start, off - start, wd))
+        # fp16 working copy of every parameter, refreshed by the Adam kernel itself (the tcnn binding re-casts the
+        # whole 11.4 M-entry table on every forward call)
+        self.flat16 = self.flat.to(torch.float16)
         self.lr, self.eps, self.betas = lr, eps, betas
         self.loss_scale, self.grad_clip, self.world_size = loss_scale, grad_clip, world_size
         self.step_count = 0
@@ -103,6 +106,17 @@ class FlatAdam:
         self.sumsq = torch.zeros(1, dtype=torch.float32, device=dev)
         self.flag = torch.zeros(1, dtype=torch.int32, device=dev)
         self.coef = torch.ones(1, dtype=torch.float32, device=dev)
+
+    def adopt_half_copies(self, model):
+        """point every tcnn-style module's fp16 working copy at this optimizer's flat16 buffer"""
+        base = self.flat.data_ptr()
+        for mod in model.modules():
+            p = getattr(mod, "params", None)
+            if p is None or p.numel() == 0 or not hasattr(mod, "_half_key"):
+                continue
+            o = (p.data_ptr() - base) // 4
+            mod._half = self.flat16[o:o + p.numel()]
+            mod._half_key = "flat"
 
     def step(self, lr=None):
         L = _lib.lib()
@@ -116,9 +130,9 @@ class FlatAdam:
             coef = self.coef
         for (start, n, wd) in self.groups:
             sl = slice(start, start + n)
-            check(L.ncn_adam_step(ptr(self.flat[sl]), ptr(self.grad[sl]), ptr(self.m[sl]), ptr(self.v[sl]), None, n,
+            check(L.ncn_adam_step(ptr(self.flat[sl]), ptr(self.grad[sl]), ptr(self.m[sl]), ptr(self.v[sl]), ptr(self.flat16[sl]), n,
                                   float(lr if lr is not None else self.lr), self.betas[0], self.betas[1], self.eps, wd,
-                                  self.step_count, ptr(self.grad_div), ptr(self.flag), ptr(coef), st), "adam_step")
+                                  self.step_count, ptr(self.grad_div), ptr(self.flag), ptr(coef), None, st), "adam_step")
 
 
 class NeRFTrainer:
@@ -135,7 +149,9 @@ class NeRFTrainer:
         self.comm = Communicator(rank, world_size)
         self.opt = FlatAdam(list(self.model.named_parameters()), lr=hp["lr"], loss_scale=hp["loss_scale"],
                             grad_clip=hp["grad_clip"], world_size=world_size)
+        self.opt.adopt_half_copies(self.model)
         self.global_step = 0
+        self.fused = None
         self.render_kwargs = dict(near_distance=hp["rend_near_dist"], max_samples=hp["rend_max_samples"],
                                   exp_step_factor=hp["exp_step_factor"], n_sem_cls=n_sem_cls,
                                   pred_norm_nn_norm=False)
@@ -169,6 +185,23 @@ class NeRFTrainer:
         results = render(self.model, rays_o, rays_d, global_step=self.global_step, **self.render_kwargs)
         loss_d = self.loss(results, target, global_step=self.global_step)
         return results, loss_d
+
+    def fused_step(self, capacity_per_ray=64, use_graph=True):
+        """the sync-free CUDA-graph step (ncn_b200.fused.FusedStep) for the RGB+depth configuration"""
+        if self.fused is None:
+            from .fused import FusedStep
+            self.fused = FusedStep(self, capacity_per_ray=capacity_per_ray, use_graph=use_graph)
+            self.opt.grad_div.fill_(float(self.world_size))     # fused gradients are already un-scaled
+        return self.fused
+
+    def train_step_fused(self, rays_o, rays_d, target_rgb, tri=None, update_grid=True, noise=None):
+        """same step as train_step, through the fused path; returns nothing (stats via self.fused.stats_host())"""
+        fs = self.fused_step()
+        if tri is not None and (fs.tri is None or fs.tri.data_ptr() != tri.data_ptr()):
+            fs.set_triangles(tri)
+        if update_grid:
+            self.maybe_update_grid()
+        fs.step(rays_o, rays_d, target_rgb, noise=noise)
 
     def train_step(self, rays_o, rays_d, target, update_grid=True):
         if update_grid:

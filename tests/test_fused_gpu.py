@@ -1,0 +1,90 @@
+"""GPU: the fused CUDA-graph training step (ncn_b200.fused.FusedStep) against the module path
+(render + NeRFMTLoss + autograd) on identical parameters, rays and march noise: same losses, same gradients
+(the module path is itself pinned kernel-by-kernel against the oracles / reference kernels)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _setup(R=2048, seed=0):
+    import ncn_b200
+    from ncn_b200 import synth, vren
+    from ncn_b200.trainer import NeRFTrainer
+    torch.manual_seed(seed)
+    tr = NeRFTrainer(dict(batch_size=R), device="cuda")
+    grid = synth.density_grid_from_occupancy(synth.room_occupancy(128, 0.5, seed=0))
+    tr.model.density_grid.copy_(torch.from_numpy(grid).cuda())
+    vren.packbits(tr.model.density_grid, 5.9, tr.model.density_bitfield)
+    # non-degenerate field: larger table values so densities / colours vary
+    g = torch.Generator(device="cuda").manual_seed(1)
+    o, n = 0, tr.model.xyz_encoder.params.numel()
+    tr.opt.flat[:n].copy_(torch.randn(n, device="cuda", generator=g) * 0.3)
+    tr.opt.flat16.copy_(tr.opt.flat)
+    tr.global_step = 3000
+    b = synth.patch_batch(R, seed=seed)
+    rays_o = torch.from_numpy(b["rays_o"]).cuda(); rays_d = torch.from_numpy(b["rays_d"]).cuda()
+    tri = torch.from_numpy(b["tri"]).cuda()
+    rgb = torch.rand(R, 3, device="cuda", generator=g)
+    target = {"rgb": rgb, "patch_area": 64, "x1_offsets_local": tri[0][:49] % 64, "x2_offsets_local": tri[1][:49] % 64,
+              "x3_offsets_local": tri[2][:49] % 64}
+    return tr, rays_o, rays_d, tri, rgb, target
+
+
+def test_fused_matches_module_path():
+    from ncn_b200.fused import GSCALE
+    tr, rays_o, rays_d, tri, rgb, target = _setup()
+    R = rays_o.shape[0]
+    # module path
+    torch.manual_seed(123)
+    results, loss_d = tr.forward_loss(rays_o, rays_d, target)
+    (loss_d["total"] * tr.hp["loss_scale"]).backward()
+    g_mod = (tr.opt.grad / tr.hp["loss_scale"]).clone()
+    tr.opt.grad.zero_()
+    # fused path, eager (no graph), same noise
+    torch.manual_seed(123)
+    noise = torch.rand(R, device="cuda")
+    fs = tr.fused_step(use_graph=False)
+    fs.set_triangles(tri)
+    fs.rays_o.copy_(rays_o); fs.rays_d.copy_(rays_d); fs.target.copy_(rgb); fs.noise.copy_(noise)
+    fs._schedule()
+    fs._run()
+    torch.cuda.synchronize()
+    assert int(fs.counter[0]) == int(results["rm_samples"])
+    assert torch.equal(fs.rays_a, results["rays_a"])
+    torch.testing.assert_close(fs.depth, results["depth"].detach(), rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(fs.opacity, results["opacity"].detach(), rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(fs.rgb, results["rgb"].detach().float(), rtol=1e-3, atol=1e-3)
+    d, n = fs.stats_host()
+    for k in ("rgb", "opacity", "norm_D_C_ort_dot", "norm_D_C_centr_dot", "norm_D_C_centr_L1"):
+        assert abs(d[k] - float(loss_d[k])) <= 2e-3 * abs(float(loss_d[k])) + 1e-7, (k, d[k], float(loss_d[k]))
+    g_fus = tr.opt.grad.clone()
+    for name in ("rgb_net", "sigma_net", "xyz_encoder"):
+        o, k = fs.off[name]
+        a, b = g_fus[o:o + k], g_mod[o:o + k]
+        assert torch.isfinite(a).all()
+        rel = float((a - b).norm() / b.norm().clamp_min(1e-20))
+        assert rel <= 3e-2, (name, rel, float(b.norm()))
+
+
+def test_fused_graph_replay_trains():
+    """graph replay == eager fused step, and the loss goes down over a few steps on a fixed batch"""
+    tr, rays_o, rays_d, tri, rgb, target = _setup(R=1024, seed=1)
+    tr2, *_ = _setup(R=1024, seed=1)
+    noise = torch.rand(1024, device="cuda")
+    fs = tr.fused_step(use_graph=True); fs.set_triangles(tri)
+    fs2 = tr2.fused_step(use_graph=False); fs2.set_triangles(tri)
+    for i in range(3):
+        fs.step(rays_o, rays_d, rgb, noise=noise)
+        fs2.step(rays_o, rays_d, rgb, noise=noise)
+    torch.cuda.synchronize()
+    rel = float((tr.opt.flat - tr2.opt.flat).norm() / tr2.opt.flat.norm())
+    assert rel < 1e-3, rel
+    l0 = None
+    for i in range(30):
+        fs.step(rays_o, rays_d, rgb, noise=noise)
+        if i == 0:
+            l0 = fs.stats_host()[0]["rgb"]
+    l1 = fs.stats_host()[0]["rgb"]
+    assert l1 < l0, (l0, l1)
