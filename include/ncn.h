@@ -279,6 +279,10 @@ int ncn_mlp_bwd(const ncn_mlp_desc* d, const void* x_f16, const void* w_f16,
                 float* grad_w_f32, void* dL_dx_f16, float grad_scale, void* scratch,
                 size_t scratch_bytes, const int32_t* n_dev, ncn_stream_t stream);
 
+/* Selects the ncn_mlp_bwd implementation: 1 (default) = tcgen05 weight-gradient MMAs with TMEM-resident
+ * accumulators fused into the dgrad kernel; 0 = warp-MMA dgrad + split-K wgrad kernels.  Returns the old value. */
+int ncn_set_mlp_bwd_impl(int impl);
+
 /* Elementwise glue of the NGPMT field (models/ngp_mt.py:157-229, rendering.py:203-212) between the
  * encoder / MLP kernels; every function takes the device-side live row count n_dev (may be NULL).
  *   prepare_rgb: x_rgb (N,32) f16 = [d/||d|| (3), h (16), 1.0 x13], sigmas (N) f32 = exp(h[:,0])

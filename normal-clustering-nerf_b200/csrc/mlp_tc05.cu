@@ -1,0 +1,361 @@
+// MLP backward with the weight gradients on the 5th-generation tensor cores (tcgen05) and their
+// accumulators resident in tensor memory (TMEM) for the whole kernel.
+//
+// Why: dL/dW = dZ^T * A_prev contracts over the SAMPLE dimension.  The warp-MMA implementation (mlp.cu)
+// has to round-trip every layer's dZ through HBM and re-read the activations in a second, split-K kernel
+// per layer (2.4 KB/sample of traffic, 5 extra launches for the sigma + rgb nets).  Here one persistent CTA
+// walks 128-sample tiles:
+//   * the 8 warps run the dgrad chain in registers exactly like mlp.cu (mma.sync, fp32 accumulate) and drop
+//     each layer's dZ tile and input-activation tile into shared memory in the canonical no-swizzle
+//     "MN-major" core-matrix layout ([feature/8][sample][8 halfs]: a warp's fragment store is 128 contiguous
+//     bytes, conflict free);
+//   * ONE thread issues tcgen05.mma (kind::f16, M=64, N=in-width, K=16 per instruction, 8 per tile and layer)
+//     whose A and B operands are those two tiles, both transposed for free by the MN-major descriptors, and
+//     whose fp32 accumulator D = dW stays in TMEM across all tiles of the CTA (112 columns for the rgb net);
+//     tcgen05.commit -> mbarrier releases the tiles while the warps already compute the next tile's dgrad;
+//   * at the end four warps read TMEM (tcgen05.ld 32x32b) and add the CTA's dW to the global gradient.
+// HBM traffic drops to the unavoidable reads (dL/dout, out, activations, x) and the dL/dx write.
+#include "ncn_common.cuh"
+#include "mma.cuh"
+
+namespace ncn {
+
+constexpr int kTcThreads = 256;
+constexpr int kTile = 128;         // samples per CTA iteration (8 warps x 16 rows)
+constexpr int kTcW = 64;
+constexpr int kTcPad = 8;
+
+// ------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "NCN_WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra NCN_DONE_%=;\n"
+      "bra NCN_WAIT_%=;\n"
+      "NCN_DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+template <int COLS>
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "n"(COLS) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+template <int COLS>
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(COLS) : "memory");
+}
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem], fp16 inputs, fp32 accumulate
+__device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n"
+      "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+        "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// shared-memory matrix descriptor: no swizzle, MN-major.  In a panel laid out [feature/8][sample][8 halfs]:
+//   8 K-rows (samples) are 16 B apart, the next 8 samples are LBO = 128 B further (K direction),
+//   the next 8 features are SBO = kTile*16 B further (M/N direction).          (cute/arch/mma_sm100_desc.hpp)
+__device__ __forceinline__ uint64_t make_desc_mn(const void* panel_at_k) {
+  const uint64_t addr = (uint64_t)(smem_u32(panel_at_k) >> 4) & 0x3FFF;
+  const uint64_t lbo = (128 >> 4), sbo = ((kTile * 16) >> 4);
+  return addr | (lbo << 16) | (sbo << 32) | (1ull << 46);   // version = 1 (Blackwell), layout_type = 0 (no swizzle)
+}
+// instruction descriptor: D=f32, A=B=f16, both MN-major, M=64, N
+__host__ __device__ constexpr uint32_t make_idesc(int N) {
+  return (1u << 4) | (1u << 15) | (1u << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(64 >> 4) << 24);
+}
+
+// ------------------------------------------------------------------ fragment helpers (same layouts as mlp.cu)
+template <int K, int N>
+__device__ __forceinline__ void tc_warp_layer(const uint32_t (*a)[4], const __half* __restrict__ W, float (*c)[4], int g, int t) {
+#pragma unroll
+  for (int nt = 0; nt < N / 8; ++nt) { c[nt][0] = c[nt][1] = c[nt][2] = c[nt][3] = 0.f; }
+#pragma unroll
+  for (int kb = 0; kb < K / 16; ++kb) {
+#pragma unroll
+    for (int nt = 0; nt < N / 8; ++nt) {
+      const __half* wr = W + (nt * 8 + g) * (K + kTcPad) + kb * 16 + 2 * t;
+      mma16816(c[nt], a[kb], *reinterpret_cast<const uint32_t*>(wr), *reinterpret_cast<const uint32_t*>(wr + 8));
+    }
+  }
+}
+__device__ __forceinline__ void tc_load_w_t(const __half* __restrict__ w, int rows, int cols, __half* __restrict__ s) {
+  for (int i = threadIdx.x; i < rows * cols; i += blockDim.x) {
+    const int r = i / cols, c = i % cols;
+    s[c * (rows + kTcPad) + r] = w[i];
+  }
+}
+// A-fragment-packed 16 x (16*KB) tile -> panel [feature/8][kTile][8]; `r` = first row of the warp inside the tile
+template <int KB>
+__device__ __forceinline__ void store_panel(__half* __restrict__ P, int r, const uint32_t (*a)[4], int g, int t) {
+#pragma unroll
+  for (int kb = 0; kb < KB; ++kb) {
+    __half* p0 = P + ((size_t)(2 * kb) * kTile + r + g) * 8 + 2 * t;
+    __half* p1 = P + ((size_t)(2 * kb + 1) * kTile + r + g) * 8 + 2 * t;
+    *reinterpret_cast<uint32_t*>(p0) = a[kb][0];
+    *reinterpret_cast<uint32_t*>(p0 + 64) = a[kb][1];     // row g+8: 8 rows * 8 halfs further
+    *reinterpret_cast<uint32_t*>(p1) = a[kb][2];
+    *reinterpret_cast<uint32_t*>(p1 + 64) = a[kb][3];
+  }
+}
+// global row-major (rows, W) fp16 -> panel, 16 B per cp.async; rows >= n are zero filled
+template <int W>
+__device__ __forceinline__ void stage_panel(const __half* __restrict__ src, int64_t row0, int64_t n, __half* __restrict__ P) {
+  for (int i = threadIdx.x; i < kTile * (W / 8); i += kTcThreads) {
+    const int r = i / (W / 8), mb = i % (W / 8);
+    __half* dst = P + ((size_t)mb * kTile + r) * 8;
+    if (row0 + r < n) cp_async16(dst, src + (row0 + r) * W + mb * 8);
+    else *reinterpret_cast<uint4*>(dst) = make_uint4(0, 0, 0, 0);
+  }
+}
+// ReLU gate of the accumulators (C layout, 16 x 64) from an activation panel
+__device__ __forceinline__ void relu_mask_panel(float (*c)[4], const __half* __restrict__ P, int r, int g, int t) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const __half2 a0 = *reinterpret_cast<const __half2*>(P + ((size_t)j * kTile + r + g) * 8 + 2 * t);
+    const __half2 a1 = *reinterpret_cast<const __half2*>(P + ((size_t)j * kTile + r + g + 8) * 8 + 2 * t);
+    if (!(__low2float(a0) > 0.f)) c[j][0] = 0.f;
+    if (!(__high2float(a0) > 0.f)) c[j][1] = 0.f;
+    if (!(__low2float(a1) > 0.f)) c[j][2] = 0.f;
+    if (!(__high2float(a1) > 0.f)) c[j][3] = 0.f;
+  }
+}
+__device__ __forceinline__ void tc_c_to_a64(const float (*c)[4], uint32_t (*a)[4]) {
+#pragma unroll
+  for (int kb = 0; kb < 4; ++kb) {
+    a[kb][0] = pack_half2(c[2 * kb][0], c[2 * kb][1]);
+    a[kb][1] = pack_half2(c[2 * kb][2], c[2 * kb][3]);
+    a[kb][2] = pack_half2(c[2 * kb + 1][0], c[2 * kb + 1][1]);
+    a[kb][3] = pack_half2(c[2 * kb + 1][2], c[2 * kb + 1][3]);
+  }
+}
+
+constexpr int tmem_cols_pow2(int c) { return c <= 32 ? 32 : c <= 64 ? 64 : c <= 128 ? 128 : c <= 256 ? 256 : 512; }
+
+template <int IN, int OUT, int NH>
+struct TcLayout {
+  // shared memory (halfs unless noted)
+  static constexpr int kWlT = 64 * (OUT + kTcPad);
+  static constexpr int kWhT = (NH - 1) * 64 * (64 + kTcPad);
+  static constexpr int kW0T = IN * (64 + kTcPad);
+  static constexpr int kWeights = (kWlT + kWhT + kW0T + 7) / 8 * 8;
+  static constexpr int kPdzLast = OUT * kTile, kPdzH = NH * 64 * kTile, kPx = IN * kTile, kPact = NH * 64 * kTile;
+  static constexpr size_t kBytes = (size_t)(kWeights + kPdzLast + kPdzH + kPx + kPact) * 2 + 32;
+  static constexpr int kTmemColsUsed = IN + 64 * (NH - 1) + OUT;
+  static constexpr int kTmemCols = tmem_cols_pow2(kTmemColsUsed);
+};
+
+template <int IN, int OUT, int NH>
+__global__ void __launch_bounds__(kTcThreads, 1)
+mlp_bwd_tc05_kernel(const __half* __restrict__ x, const __half* __restrict__ w, const __half* __restrict__ out,
+                    const __half* __restrict__ acts, const __half* __restrict__ dout, int64_t n_cap,
+                    const int32_t* __restrict__ n_dev, int out_act, float grad_scale, float* __restrict__ grad_w,
+                    __half* __restrict__ dx) {
+  using LY = TcLayout<IN, OUT, NH>;
+  int64_t n = n_cap;
+  if (n_dev != nullptr) { const int64_t nd = *n_dev; if (nd < n) n = nd; }
+  extern __shared__ __align__(128) unsigned char tc_smem[];
+  __half* WlT = reinterpret_cast<__half*>(tc_smem);
+  __half* WhT = WlT + LY::kWlT;
+  __half* W0T = WhT + LY::kWhT;
+  __half* P_dz_last = WlT + LY::kWeights;
+  __half* P_dz_h = P_dz_last + LY::kPdzLast;
+  __half* P_x = P_dz_h + LY::kPdzH;
+  __half* P_act = P_x + LY::kPx;
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(P_act + LY::kPact);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 1);
+
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, g = lane >> 2, t = lane & 3;
+  tc_load_w_t(w + 64 * IN + (NH - 1) * 64 * 64, OUT, 64, WlT);
+  for (int i = 0; i < NH - 1; ++i) tc_load_w_t(w + 64 * IN + i * 64 * 64, 64, 64, WhT + i * 64 * (64 + kTcPad));
+  if (dx) tc_load_w_t(w, 64, IN, W0T);
+  if (tid == 0) { mbar_init(mbar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+  if (wid == 0) tmem_alloc<LY::kTmemCols>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  const int64_t n_tiles = (n + kTile - 1) / kTile;
+  int it = 0;
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+    const int64_t row0 = tile * kTile;
+    if (it > 0) mbar_wait(mbar, (uint32_t)((it - 1) & 1));     // the previous tile's MMAs have consumed the panels
+    // (1) stage the input / hidden activations of this tile
+    stage_panel<IN>(x, row0, n, P_x);
+    for (int i = 0; i < NH; ++i) stage_panel<64>(acts + (int64_t)i * n_cap * 64, row0, n, P_act + (size_t)i * 64 * kTile);
+    cp_async_wait_all();
+    __syncthreads();
+    // (2) dgrad chain in registers; every layer's dL/dz goes to its panel
+    {
+      const int r = wid * 16;                       // first row of this warp inside the tile
+      const int64_t r0 = row0 + r + g, r1 = r0 + 8;
+      uint32_t dz[OUT / 16][4];
+#pragma unroll
+      for (int kb = 0; kb < OUT / 16; ++kb) {
+        const int col = kb * 16 + 2 * t;
+        dz[kb][0] = r0 < n ? *reinterpret_cast<const uint32_t*>(dout + r0 * OUT + col) : 0u;
+        dz[kb][1] = r1 < n ? *reinterpret_cast<const uint32_t*>(dout + r1 * OUT + col) : 0u;
+        dz[kb][2] = r0 < n ? *reinterpret_cast<const uint32_t*>(dout + r0 * OUT + col + 8) : 0u;
+        dz[kb][3] = r1 < n ? *reinterpret_cast<const uint32_t*>(dout + r1 * OUT + col + 8) : 0u;
+      }
+      if (out_act == NCN_ACT_SIGMOID || out_act == NCN_ACT_EXP) {
+#pragma unroll
+        for (int kb = 0; kb < OUT / 16; ++kb)
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int64_t rr = (q & 1) ? r1 : r0;
+            const int col = kb * 16 + 2 * t + ((q & 2) ? 8 : 0);
+            const uint32_t ou = rr < n ? *reinterpret_cast<const uint32_t*>(out + rr * OUT + col) : 0u;
+            const float2 d = __half22float2(*reinterpret_cast<const __half2*>(&dz[kb][q]));
+            const float2 y = __half22float2(*reinterpret_cast<const __half2*>(&ou));
+            if (out_act == NCN_ACT_SIGMOID) dz[kb][q] = pack_half2(d.x * y.x * (1.f - y.x), d.y * y.y * (1.f - y.y));
+            else dz[kb][q] = pack_half2(d.x * y.x, d.y * y.y);
+          }
+      }
+      store_panel<OUT / 16>(P_dz_last, r, dz, g, t);
+      float c[8][4];
+      tc_warp_layer<OUT, 64>(dz, WlT, c, g, t);
+      uint32_t dh[4][4];
+#pragma unroll
+      for (int i = NH - 1; i >= 0; --i) {
+        relu_mask_panel(c, P_act + (size_t)i * 64 * kTile, r, g, t);
+        tc_c_to_a64(c, dh);
+        store_panel<4>(P_dz_h + (size_t)i * 64 * kTile, r, dh, g, t);
+        if (i > 0) tc_warp_layer<64, 64>(dh, WhT + (i - 1) * 64 * (64 + kTcPad), c, g, t);
+      }
+      if (dx) {
+        float cx[IN / 8][4];
+        tc_warp_layer<64, IN>(dh, W0T, cx, g, t);
+#pragma unroll
+        for (int j = 0; j < IN / 8; ++j) {
+          const int col = j * 8 + 2 * t;
+          if (r0 < n) *reinterpret_cast<uint32_t*>(dx + r0 * IN + col) = pack_half2(cx[j][0], cx[j][1]);
+          if (r1 < n) *reinterpret_cast<uint32_t*>(dx + r1 * IN + col) = pack_half2(cx[j][2], cx[j][3]);
+        }
+      }
+    }
+    // (3) publish the panels to the tensor-core (async) proxy and issue the weight-gradient MMAs
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      const uint32_t acc0 = it > 0 ? 1u : 0u;
+#pragma unroll
+      for (int ks = 0; ks < kTile / 16; ++ks) {
+        const uint32_t acc = (ks > 0) ? 1u : acc0;
+        const size_t koff = (size_t)ks * 16 * 8;          // 16 samples * 8 halfs
+        // layer 0: dW0[out][in] += dz_h[0]^T x
+        tc_mma_f16(tmem + 0, make_desc_mn(P_dz_h + koff), make_desc_mn(P_x + koff), make_idesc(IN), acc);
+        // hidden layers i = 1..NH-1: dWi[out][in] += dz_h[i]^T act[i-1]
+#pragma unroll
+        for (int i = 1; i < NH; ++i)
+          tc_mma_f16(tmem + IN + 64 * (i - 1), make_desc_mn(P_dz_h + (size_t)i * 64 * kTile + koff),
+                     make_desc_mn(P_act + (size_t)(i - 1) * 64 * kTile + koff), make_idesc(64), acc);
+        // last layer, transposed: dWl^T[in][out] += act[NH-1]^T dz_last
+        tc_mma_f16(tmem + IN + 64 * (NH - 1), make_desc_mn(P_act + (size_t)(NH - 1) * 64 * kTile + koff),
+                   make_desc_mn(P_dz_last + koff), make_idesc(OUT), acc);
+      }
+      tc_commit(mbar);
+    }
+  }
+  // (4) epilogue: TMEM -> registers -> global gradient (+=)
+  if (it > 0) {
+    mbar_wait(mbar, (uint32_t)((it - 1) & 1));
+    tc_fence_after();
+    if (wid < 4) {
+      // M = 64 accumulators live in the lower 16 lanes of each 32-lane TMEM sub-partition: row m = 16*wid + lane
+      const int m = 16 * wid + lane;
+      const uint32_t lane_base = tmem + ((uint32_t)(32 * wid) << 16);
+      uint32_t v[16];
+#pragma unroll
+      for (int c0 = 0; c0 < IN; c0 += 16) {
+        tmem_ld16(lane_base + c0, v);
+        if (lane < 16)
+#pragma unroll
+          for (int j = 0; j < 16; ++j) atomicAdd(grad_w + m * IN + c0 + j, __uint_as_float(v[j]) * grad_scale);
+      }
+#pragma unroll
+      for (int i = 1; i < NH; ++i)
+#pragma unroll
+        for (int c0 = 0; c0 < 64; c0 += 16) {
+          tmem_ld16(lane_base + IN + 64 * (i - 1) + c0, v);
+          if (lane < 16)
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              atomicAdd(grad_w + 64 * IN + (i - 1) * 64 * 64 + m * 64 + c0 + j, __uint_as_float(v[j]) * grad_scale);
+        }
+#pragma unroll
+      for (int c0 = 0; c0 < OUT; c0 += 16) {
+        tmem_ld16(lane_base + IN + 64 * (NH - 1) + c0, v);
+        if (lane < 16)
+#pragma unroll
+          for (int j = 0; j < 16; ++j)   // D[m = in][n = out] -> W_last[out][in]
+            atomicAdd(grad_w + 64 * IN + (NH - 1) * 64 * 64 + (c0 + j) * 64 + m, __uint_as_float(v[j]) * grad_scale);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (wid == 0) tmem_dealloc<LY::kTmemCols>(tmem);
+}
+
+}  // namespace ncn
+
+using namespace ncn;
+
+template <int IN, int OUT, int NH>
+static int launch_tc05(const void* x, const void* w, const void* out, const void* acts, const void* dout, int64_t n,
+                       const int32_t* n_dev, int out_act, float grad_scale, float* grad_w, void* dx, cudaStream_t st) {
+  using LY = TcLayout<IN, OUT, NH>;
+  auto k = mlp_bwd_tc05_kernel<IN, OUT, NH>;
+  NCN_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LY::kBytes));
+  const int64_t tiles = (n + kTile - 1) / kTile;
+  int64_t grid = (int64_t)sm_count() * 2;
+  if (grid > tiles) grid = tiles;
+  k<<<(int)grid, kTcThreads, LY::kBytes, st>>>((const __half*)x, (const __half*)w, (const __half*)out, (const __half*)acts,
+                                               (const __half*)dout, n, n_dev, out_act, grad_scale, grad_w, (__half*)dx);
+  NCN_LAUNCH_OK();
+  return NCN_OK;
+}
+
+// returns NCN_E_UNSUPPORTED when the configuration has no tcgen05 instantiation (the caller falls back to mlp.cu)
+int ncn_mlp_bwd_tc05_try(int in_pad, int out_pad, int n_hidden, const void* x, const void* w, const void* out, const void* acts,
+                         const void* dout, int64_t n, const int32_t* n_dev, int out_act, float grad_scale, float* grad_w,
+                         void* dx, cudaStream_t st) {
+  if (!grad_w) return NCN_E_UNSUPPORTED;
+#define NCN_TC(I, O, H) if (in_pad == I && out_pad == O && n_hidden == H) \
+    return launch_tc05<I, O, H>(x, w, out, acts, dout, n, n_dev, out_act, grad_scale, grad_w, dx, st);
+  NCN_TC(32, 16, 1) NCN_TC(32, 16, 2) NCN_TC(16, 16, 2) NCN_TC(16, 16, 1) NCN_TC(16, 48, 2) NCN_TC(16, 32, 2)
+#undef NCN_TC
+  return NCN_E_UNSUPPORTED;
+}
