@@ -115,23 +115,17 @@ __device__ __forceinline__ int best_centroid(float x, float y, float z, const fl
 // contention - (3) K*4 threads fold the 32 warp rows, and one warp updates / re-seeds / renormalises.
 constexpr float kKmFix = 1048576.0f;     // 2^20
 
-// folds (x,y,z,1) of the lanes whose `key` equals each distinct key into acc[key*4 + {0,1,2,3}] (warp-private row)
+// adds (x,y,z,1) of every valid lane to acc[key*4 + {0,1,2,3}], a WARP-PRIVATE row of integer accumulators:
+// integer atomics commute, so the result does not depend on the order in which the lanes are served
 __device__ __forceinline__ void warp_accumulate_by_key(int key, bool valid, float x, float y, float z, int* __restrict__ acc,
                                                        int lane) {
-  const int fx = __float2int_rn(x * kKmFix), fy = __float2int_rn(y * kKmFix), fz = __float2int_rn(z * kKmFix);
-  unsigned remaining = __ballot_sync(0xffffffffu, valid);
-  while (remaining) {
-    const int leader = __ffs(remaining) - 1;
-    const int k = __shfl_sync(0xffffffffu, key, leader);
-    const bool mine = valid && key == k;
-    const unsigned m = __ballot_sync(0xffffffffu, mine);
-    const int sx = __reduce_add_sync(0xffffffffu, mine ? fx : 0);
-    const int sy = __reduce_add_sync(0xffffffffu, mine ? fy : 0);
-    const int sz = __reduce_add_sync(0xffffffffu, mine ? fz : 0);
-    if (lane == leader) { acc[4 * k] += sx; acc[4 * k + 1] += sy; acc[4 * k + 2] += sz; acc[4 * k + 3] += __popc(m); }
-    remaining &= ~m;
+  (void)lane;
+  if (valid) {
+    atomicAdd(acc + 4 * key, __float2int_rn(x * kKmFix));
+    atomicAdd(acc + 4 * key + 1, __float2int_rn(y * kKmFix));
+    atomicAdd(acc + 4 * key + 2, __float2int_rn(z * kKmFix));
+    atomicAdd(acc + 4 * key + 3, 1);
   }
-  __syncwarp();
 }
 
 __global__ void __launch_bounds__(kKmThreads, 1)
@@ -213,12 +207,18 @@ kmeans_kernel(const float* __restrict__ x, int64_t n, ncn_kmeans_params p, float
       s_acc[tid] = (tid & 3) == 3 ? (float)t : (float)((double)t / (double)kKmFix);
     }
     __syncthreads();
-    if (tid == 0) {
-      // new centroids = member means; empty clusters split the currently largest one (faiss-style +-eps)
-      for (int j = 0; j < K; ++j) {
-        const float c = s_acc[4 * j + 3];
-        if (c > 0.f) { s_c[3 * j] = s_acc[4 * j] / c; s_c[3 * j + 1] = s_acc[4 * j + 1] / c; s_c[3 * j + 2] = s_acc[4 * j + 2] / c; }
-      }
+    // new centroids = member means (thread per cluster); empty clusters split the currently largest one
+    // (faiss-style +-eps, rare -> one thread); then renormalise (thread per cluster)
+    __shared__ int s_any_empty;
+    if (tid == 0) s_any_empty = 0;
+    __syncthreads();
+    if (tid < K) {
+      const float c = s_acc[4 * tid + 3];
+      if (c > 0.f) { s_c[3 * tid] = s_acc[4 * tid] / c; s_c[3 * tid + 1] = s_acc[4 * tid + 1] / c; s_c[3 * tid + 2] = s_acc[4 * tid + 2] / c; }
+      else s_any_empty = 1;
+    }
+    __syncthreads();
+    if (tid == 0 && s_any_empty) {
       for (int j = 0; j < K; ++j) {
         if (s_acc[4 * j + 3] == 0.f) {
           int big = 0;
@@ -234,12 +234,11 @@ kmeans_kernel(const float* __restrict__ x, int64_t n, ncn_kmeans_params p, float
           s_acc[4 * j + 3] = half; s_acc[4 * big + 3] -= half;
         }
       }
-      if (p.spherical) {
-        for (int j = 0; j < K; ++j) {
-          const float l = sqrtf(s_c[3 * j] * s_c[3 * j] + s_c[3 * j + 1] * s_c[3 * j + 1] + s_c[3 * j + 2] * s_c[3 * j + 2]);
-          if (l > 0.f) { s_c[3 * j] /= l; s_c[3 * j + 1] /= l; s_c[3 * j + 2] /= l; }
-        }
-      }
+    }
+    __syncthreads();
+    if (tid < K && p.spherical) {
+      const float l = sqrtf(s_c[3 * tid] * s_c[3 * tid] + s_c[3 * tid + 1] * s_c[3 * tid + 1] + s_c[3 * tid + 2] * s_c[3 * tid + 2]);
+      if (l > 0.f) { s_c[3 * tid] /= l; s_c[3 * tid + 1] /= l; s_c[3 * tid + 2] /= l; }
     }
     __syncthreads();
   }
