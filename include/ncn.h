@@ -238,6 +238,9 @@ int ncn_grid_fwd(const ncn_grid_desc* desc_host, const float* x, const void* tab
 int ncn_grid_bwd(const ncn_grid_desc* desc_host, const float* x, const void* dL_dy_f16,
                  int64_t n, float* grad_table_f32, float grad_scale, const float* xform_host,
                  const int32_t* n_dev, ncn_stream_t stream);
+/* 1 (default): ncn_grid_bwd merges same-entry contributions of consecutive samples inside a warp before the
+ * scatter; 0: one reduction per corner.  Returns the old value. */
+int ncn_set_grid_bwd_merge(int on);
 /* dL_dx (N,3) f32 = d out / d x contracted with dL_dy. */
 int ncn_grid_bwd_input(const ncn_grid_desc* desc_host, const float* x, const void* table_f16,
                        const void* dL_dy_f16, int64_t n, float* dL_dx, ncn_stream_t stream);

@@ -146,6 +146,86 @@ grid_bwd_kernel(const __grid_constant__ GridMeta meta, const float* __restrict__
   }
 }
 
+// Parameter-gradient scatter with warp-level run merging (F = 2).
+// Samples arrive in ray order, 1.7e-3 apart, so at the coarse levels dozens of consecutive samples fall in the same
+// cell and would issue dozens of same-address reductions (which the L2 atomic unit serialises).  Here a warp takes 32
+// CONSECUTIVE samples of ONE level; per corner, lanes that hit the same entry as their left neighbour form a run, the
+// run is summed with a warp prefix scan, and only the head lane issues the red.global.add.v2.f32.  Warps whose
+// samples are not coherent at this level (fine / hashed levels) detect that with one ballot and take the direct path.
+__global__ void __launch_bounds__(256)
+grid_bwd_merge_kernel(const __grid_constant__ GridMeta meta, const float* __restrict__ x, const __half* __restrict__ dy,
+                      int64_t n_cap, const int32_t* __restrict__ n_dev, GridXform xf, float grad_scale, float* __restrict__ grad) {
+  __shared__ GridMeta sm;
+  for (int i = threadIdx.x; i < (int)(sizeof(GridMeta) / 4); i += blockDim.x)
+    reinterpret_cast<uint32_t*>(&sm)[i] = reinterpret_cast<const uint32_t*>(&meta)[i];
+  __syncthreads();
+  const int L = sm.n_levels;
+  int64_t n = n_cap;
+  if (n_dev != nullptr) { const int64_t nd = *n_dev; if (nd < n) n = nd; }
+  const int lane = threadIdx.x & 31;
+  const int64_t n_items = ((n + 31) >> 5) * L;
+  const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t item = warp0; item < n_items; item += n_warps) {
+    const int64_t chunk = item / L;
+    const int l = (int)(item - chunk * L);
+    const int64_t s = (chunk << 5) + lane;
+    const bool valid = s < n;
+    float g0 = 0.f, g1 = 0.f;
+    if (valid) {
+      const float2 gg = __half22float2(*reinterpret_cast<const __half2*>(dy + (s * L + l) * 2));
+      g0 = gg.x * grad_scale; g1 = gg.y * grad_scale;
+    }
+    const bool live = valid && (g0 != 0.f || g1 != 0.f);
+    if (__ballot_sync(0xffffffffu, live) == 0u) continue;      // e.g. samples behind an early-terminated ray
+    Cell8 c;
+    if (valid) locate8(x, s, sm.scale[l], sm.res[l], sm.size[l], c, xf);
+    else {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) c.idx[k] = 0xFFFFFFFFu;
+      c.w[0] = c.w[1] = c.w[2] = 0.f;
+    }
+    float2* gl = reinterpret_cast<float2*>(grad) + sm.offset[l];
+    // coherence probe on corner 0
+    const uint32_t prev0 = __shfl_up_sync(0xffffffffu, c.idx[0], 1);
+    const unsigned same = __ballot_sync(0xffffffffu, lane > 0 && c.idx[0] == prev0 && valid);
+    if (__popc(same) < 8) {
+      if (live) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const float wk = corner_w(c.w, k);
+          atomicAdd(gl + c.idx[k], make_float2(wk * g0, wk * g1));
+        }
+      }
+      continue;
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float wk = valid ? corner_w(c.w, k) : 0.f;
+      float vx = wk * g0, vy = wk * g1;
+      const uint32_t idx = c.idx[k];
+      const uint32_t prev = __shfl_up_sync(0xffffffffu, idx, 1);
+      const bool head = (lane == 0) || (idx != prev);
+      const unsigned heads = __ballot_sync(0xffffffffu, head);
+      // inclusive prefix sums over the warp
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const float tx = __shfl_up_sync(0xffffffffu, vx, o), ty = __shfl_up_sync(0xffffffffu, vy, o);
+        if (lane >= o) { vx += tx; vy += ty; }
+      }
+      // run [lane, end]: end = position of the next head - 1
+      const unsigned later = lane < 31 ? (heads >> (lane + 1)) : 0u;
+      const int end = later ? lane + __ffs(later) - 1 : 31;
+      const float ex = __shfl_sync(0xffffffffu, vx, end), ey = __shfl_sync(0xffffffffu, vy, end);
+      const float bx = __shfl_up_sync(0xffffffffu, vx, 1), by = __shfl_up_sync(0xffffffffu, vy, 1);
+      if (head && valid) {
+        const float sx = ex - (lane > 0 ? bx : 0.f), sy = ey - (lane > 0 ? by : 0.f);
+        if (sx != 0.f || sy != 0.f) atomicAdd(gl + idx, make_float2(sx, sy));
+      }
+    }
+  }
+}
+
 // dL/dx (atomically accumulated over levels into a zeroed (N,3) buffer)
 template <int F>
 __global__ void __launch_bounds__(256)
@@ -263,6 +343,9 @@ static GridXform make_xform(const float* xform_host) {
   return xf;
 }
 
+static int g_grid_bwd_merge = 1;    // 1 = warp-level run merging before the scatter (default), 0 = one reduction per corner
+extern "C" int ncn_set_grid_bwd_merge(int on) { const int old = g_grid_bwd_merge; g_grid_bwd_merge = on; return old; }
+
 #define NCN_GRID_DISPATCH(F, CALL)                 \
   switch (F) {                                     \
     case 1: { constexpr int kF = 1; CALL; } break; \
@@ -294,6 +377,11 @@ extern "C" int ncn_grid_bwd(const ncn_grid_desc* desc, const float* x, const voi
   NCN_CHECK_PTR(x); NCN_CHECK_PTR(dy); NCN_CHECK_PTR(grad);
   if ((uintptr_t)grad & 7) return NCN_E_ALIGN;
   const int grid = persistent_grid(n * m.n_levels, 256, 8);
+  if (desc->n_features == 2 && g_grid_bwd_merge) {
+    grid_bwd_merge_kernel<<<grid, 256, 0, as_stream(stream)>>>(m, x, (const __half*)dy, n, n_dev, make_xform(xform_host), grad_scale, grad);
+    NCN_LAUNCH_OK();
+    return NCN_OK;
+  }
   NCN_GRID_DISPATCH(desc->n_features, (grid_bwd_kernel<kF><<<grid, 256, 0, as_stream(stream)>>>(
       m, x, (const __half*)dy, n, n_dev, make_xform(xform_host), grad_scale, grad)));
   NCN_LAUNCH_OK();

@@ -114,17 +114,20 @@ __device__ __forceinline__ int best_centroid(float x, float y, float z, const fl
 // bit-reproducible), one lane adds the warp total to the warp's PRIVATE accumulator row - no atomics, no
 // contention - (3) K*4 threads fold the 32 warp rows, and one warp updates / re-seeds / renormalises.
 constexpr float kKmFix = 1048576.0f;     // 2^20
+constexpr int kAccStride = 33;
 
 // adds (x,y,z,1) of every valid lane to acc[key*4 + {0,1,2,3}], a WARP-PRIVATE row of integer accumulators:
 // integer atomics commute, so the result does not depend on the order in which the lanes are served
 __device__ __forceinline__ void warp_accumulate_by_key(int key, bool valid, float x, float y, float z, int* __restrict__ acc,
                                                        int lane) {
   (void)lane;
+  // acc points at column `warp` of a [4*K][kAccStride] matrix (stride 33 words: conflict-free both for these atomics,
+  // whose addresses differ in the row, and for the fold below, which reads along a row)
   if (valid) {
-    atomicAdd(acc + 4 * key, __float2int_rn(x * kKmFix));
-    atomicAdd(acc + 4 * key + 1, __float2int_rn(y * kKmFix));
-    atomicAdd(acc + 4 * key + 2, __float2int_rn(z * kKmFix));
-    atomicAdd(acc + 4 * key + 3, 1);
+    atomicAdd(acc + (4 * key) * kAccStride, __float2int_rn(x * kKmFix));
+    atomicAdd(acc + (4 * key + 1) * kAccStride, __float2int_rn(y * kKmFix));
+    atomicAdd(acc + (4 * key + 2) * kAccStride, __float2int_rn(z * kKmFix));
+    atomicAdd(acc + (4 * key + 3) * kAccStride, 1);
   }
 }
 
@@ -135,7 +138,7 @@ kmeans_kernel(const float* __restrict__ x, int64_t n, ncn_kmeans_params p, float
   extern __shared__ __align__(16) unsigned char km_smem[];
   float* xs = reinterpret_cast<float*>(km_smem);                 // [nt_cap][3]
   __shared__ float s_c[kKmMaxK * 3];
-  __shared__ int s_wacc[32][kKmMaxK * 4];   // per-warp private (sum x, y, z, count) per cluster, fixed point
+  __shared__ int s_wacc[kKmMaxK * 4 * kAccStride];   // [accumulator][warp] (stride 33), fixed point
   __shared__ float s_acc[kKmMaxK * 4];
   __shared__ int s_nvalid, s_warp_tot[32], s_base;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -190,21 +193,36 @@ kmeans_kernel(const float* __restrict__ x, int64_t n, ncn_kmeans_params p, float
   // 4) Lloyd iterations
   const int nt_round = (nt + 31) & ~31;
   for (int it = 0; it < p.niter; ++it) {
-    for (int a = lane; a < K * 4; a += 32) s_wacc[wid][a] = 0;
-    __syncwarp();
-    for (int j = tid; j < nt_round; j += kKmThreads) {
-      const bool v = j < nt;
-      float px = 0.f, py = 0.f, pz = 0.f;
-      int b = 0;
-      if (v) { px = xs[3 * j]; py = xs[3 * j + 1]; pz = xs[3 * j + 2]; b = best_centroid(px, py, pz, s_c, K); }
-      warp_accumulate_by_key(b, v, px, py, pz, s_wacc[wid], lane);
+    for (int a = tid; a < K * 4 * kAccStride; a += kKmThreads) s_wacc[a] = 0;
+    __syncthreads();
+    if (K <= 32) {
+      // centroids in registers: lane j holds centroid j, fetched by shuffle -> no shared-memory traffic in the dot loop
+      const float cx = lane < K ? s_c[3 * lane] : 0.f, cy = lane < K ? s_c[3 * lane + 1] : 0.f, cz = lane < K ? s_c[3 * lane + 2] : 0.f;
+      for (int j = tid; j < nt_round; j += kKmThreads) {
+        const bool v = j < nt;
+        float px = 0.f, py = 0.f, pz = 0.f;
+        if (v) { px = xs[3 * j]; py = xs[3 * j + 1]; pz = xs[3 * j + 2]; }
+        int b = 0; float bs = -INFINITY;
+        for (int q = 0; q < K; ++q) {
+          const float sc = px * __shfl_sync(0xffffffffu, cx, q) + py * __shfl_sync(0xffffffffu, cy, q) + pz * __shfl_sync(0xffffffffu, cz, q);
+          if (sc > bs) { bs = sc; b = q; }
+        }
+        warp_accumulate_by_key(b, v, px, py, pz, s_wacc + wid, lane);
+      }
+    } else {
+      for (int j = tid; j < nt_round; j += kKmThreads) {
+        const bool v = j < nt;
+        float px = 0.f, py = 0.f, pz = 0.f;
+        int b = 0;
+        if (v) { px = xs[3 * j]; py = xs[3 * j + 1]; pz = xs[3 * j + 2]; b = best_centroid(px, py, pz, s_c, K); }
+        warp_accumulate_by_key(b, v, px, py, pz, s_wacc + wid, lane);
+      }
     }
     __syncthreads();
-    if (tid < K * 4) {
-      long long t = 0;
-#pragma unroll 8
-      for (int w = 0; w < 32; ++w) t += s_wacc[w][tid];
-      s_acc[tid] = (tid & 3) == 3 ? (float)t : (float)((double)t / (double)kKmFix);
+    for (int a = wid; a < K * 4; a += 32) {       // warp `wid` folds accumulator rows wid, wid+32, ...
+      int part = s_wacc[a * kAccStride + lane];
+      const int tot = __reduce_add_sync(0xffffffffu, part);
+      if (lane == 0) s_acc[a] = (a & 3) == 3 ? (float)tot : (float)((double)tot / (double)kKmFix);
     }
     __syncthreads();
     // new centroids = member means (thread per cluster); empty clusters split the currently largest one
@@ -307,14 +325,14 @@ __device__ __forceinline__ float sgnf(float v) { return v > 0.f ? 1.f : (v < 0.f
 __global__ void __launch_bounds__(1024, 1)
 cluster_loss_fw_kernel(const float* __restrict__ nrm, const int32_t* __restrict__ labels, int64_t n,
                        float* __restrict__ losses, float* __restrict__ stats) {
-  __shared__ int s_wacc[32][16];
+  __shared__ int s_wacc[12 * kAccStride];
   __shared__ long long s_sum[9];
   __shared__ int s_cnt[3];
   __shared__ float s_c[9], s_mu[3];
   __shared__ float s_red[32][8];
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  if (lane < 16) s_wacc[wid][lane] = 0;
-  __syncwarp();
+  for (int a = tid; a < 12 * kAccStride; a += blockDim.x) s_wacc[a] = 0;
+  __syncthreads();
   const int64_t n_round = (n + 31) & ~(int64_t)31;
   for (int64_t i = tid; i < n_round; i += blockDim.x) {
     int l = 0;
@@ -327,12 +345,12 @@ cluster_loss_fw_kernel(const float* __restrict__ nrm, const int32_t* __restrict_
       const float sg = l > 0 ? 1.f : -1.f;
       x = sg * nrm[3 * i]; y = sg * nrm[3 * i + 1]; z = sg * nrm[3 * i + 2];
     }
-    warp_accumulate_by_key(k, v, x, y, z, s_wacc[wid], lane);
+    warp_accumulate_by_key(k, v, x, y, z, s_wacc + wid, lane);
   }
   __syncthreads();
   if (tid < 12) {
     long long t = 0;
-    for (int w = 0; w < 32; ++w) t += s_wacc[w][tid];
+    for (int w = 0; w < 32; ++w) t += s_wacc[tid * kAccStride + w];
     const int k = tid >> 2, d = tid & 3;
     if (d == 3) s_cnt[k] = (int)t; else s_sum[3 * k + d] = t;
   }

@@ -74,6 +74,36 @@ def test_grid_backward_params_and_input(ncn):
     assert (gx - xr.grad).abs().max() <= 2e-2 * sx
 
 
+def test_grid_backward_ray_coherent_samples(ncn):
+    """ray-ordered samples (1.7e-3 apart): exercises the warp-level run merging of the scatter; also a device-side count"""
+    from oracle import hashgrid
+    enc, cfg = _enc(19)
+    levels, _ = _levels(cfg, enc)
+    g = torch.Generator(device="cuda").manual_seed(5)
+    n_rays, per = 700, 41
+    o = torch.rand(n_rays, 1, 3, device="cuda", generator=g) * 0.5 + 0.1
+    d = torch.nn.functional.normalize(torch.randn(n_rays, 1, 3, device="cuda", generator=g), dim=-1)
+    t = torch.arange(per, device="cuda").view(1, per, 1) * 1.6915e-3
+    x = (o + t * d).clamp(0, 1).reshape(-1, 3).contiguous()
+    n = x.shape[0]
+    dy = torch.randn(n, 32, device="cuda", generator=g)
+    dy[n // 2: n // 2 + 300] = 0           # a block of dead samples
+    out = enc(x)
+    (out.float() * dy).sum().backward()
+    gp = enc.params.grad.clone()
+    tab = enc.params.detach().clone().view(-1, 2).requires_grad_(True)
+    ref = hashgrid.forward(x, tab, levels, out_dtype=None)
+    (ref * dy.half().float()).sum().backward()
+    assert (gp.view(-1, 2) - tab.grad).abs().max() <= 1e-2 * tab.grad.abs().max()
+    # merged and direct scatter agree
+    from ncn_b200 import _lib
+    old = _lib.lib().ncn_set_grid_bwd_merge(0)
+    enc.params.grad = None
+    (enc(x).float() * dy).sum().backward()
+    _lib.lib().ncn_set_grid_bwd_merge(old)
+    assert (enc.params.grad - gp).abs().max() <= 1e-3 * gp.abs().max()
+
+
 def test_grid_double_backward(ncn):
     """d/d(dy) and d/d(params) of <dL/dx, v> (the path a density-gradient normal would use)."""
     from oracle import hashgrid
