@@ -162,12 +162,7 @@ def run_ours(args):
     # number of steps run.  To keep the synthetic room stationary the pre-update grid / bitfield are restored after
     # each update (two extra device copies; no work is skipped).
     grid0, bits0 = tr.model.density_grid.clone(), tr.model.density_bitfield.clone()
-    _update = tr.model.update_density_grid
-
-    def _update_and_restore(*a, **k):
-        _update(*a, **k)
-        tr.model.density_grid.copy_(grid0); tr.model.density_bitfield.copy_(bits0)
-    tr.model.update_density_grid = _update_and_restore
+    restore = (grid0, bits0)
     NB = 8
     host = []
     for i in range(NB):
@@ -183,7 +178,7 @@ def run_ours(args):
     resident = []
     for h in host:
         ro, rd = tr.rays_from_batch(h["img"].to(dev), h["pix"].to(dev))
-        resident.append((ro, rd, target_of(h["rgb"].to(dev))))
+        resident.append(torch.stack([ro, rd, h["rgb"].to(dev)]).contiguous())      # (3,R,3) [rays_o | rays_d | rgb]
     h2d_bytes = sum(host[0][k].numel() * host[0][k].element_size() for k in ("img", "pix", "rgb"))
 
     tri_dev = torch.from_numpy(host[0]["tri"]).to(dev)      # identical triangle topology for every patch batch
@@ -192,15 +187,16 @@ def run_ours(args):
     loss_pin = torch.zeros(8, dtype=torch.float32).pin_memory()
 
     def step_resident(i):
-        ro, rd, tg = resident[i % NB]
-        tr.train_step_fused(ro, rd, tg["rgb"])
+        tr.train_step_fused(packed=resident[i % NB], grid_restore=restore)
+
+    d_img = torch.empty(R, dtype=torch.int64, device=dev); d_pix = torch.empty(R, dtype=torch.int64, device=dev)
 
     def step_e2e(i):
         h = host[i % NB]
-        img = h["img"].to(dev, non_blocking=True); pix = h["pix"].to(dev, non_blocking=True)
-        rgb = h["rgb"].to(dev, non_blocking=True)
-        ro, rd = tr.rays_from_batch(img, pix)
-        tr.train_step_fused(ro, rd, rgb)
+        d_img.copy_(h["img"], non_blocking=True); d_pix.copy_(h["pix"], non_blocking=True)     # H2D of the batch ...
+        fs.target.copy_(h["rgb"], non_blocking=True)
+        fs.rays_from_pixels(d_img, d_pix)
+        tr.train_step_fused(grid_restore=restore)
         loss_pin.copy_(fs.zeros, non_blocking=True)      # D2H of the step's loss sums (32 B) ...
         torch.cuda.current_stream().synchronize()         # ... which the caller reads -> one sync per step
         return float(loss_pin[0]) / (3 * R)

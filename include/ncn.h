@@ -299,6 +299,12 @@ int ncn_field_head_out(const void* out_f16, int out_pad, int64_t n, const int32_
 int ncn_field_head_dout(const float* dL_draws, int c_total, int c_offset, int n_ch, float scale,
                         int64_t n, const int32_t* n_dev, void* dout_f16, int out_pad,
                         ncn_stream_t stream);
+/* rays from (image, pixel) indices: rays_d = directions[pix] @ poses[img][:, :3]^T, rays_o = poses[img][:, 3]
+ * (NeRFSystem.forward gather + get_rays: train_nerf.py:167-182, datasets/ray_utils.py:46-71).
+ * poses (P,3,4) f32, directions (HW,3) f32, img_idx / pix_idx (n) i64 -> rays_o, rays_d (n,3) f32. */
+int ncn_rays_from_pixels(const float* poses, const float* directions, const int64_t* img_idx,
+                         const int64_t* pix_idx, int64_t n, float* rays_o, float* rays_d,
+                         ncn_stream_t stream);
 int ncn_field_bwd_h(const void* dx_rgb_f16, const float* dL_dsigmas, const void* h_f16,
                     const void* dx_a_f16, const void* dx_b_f16, float scale, int64_t n,
                     const int32_t* n_dev, void* dh_f16, ncn_stream_t stream);

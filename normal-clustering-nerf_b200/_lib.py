@@ -187,6 +187,7 @@ SIGNATURES.update({
     "ncn_adam_step": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_f32, c_f32, c_f32, c_f32, c_f32, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "ncn_set_mlp_bwd_impl": (c_i32, [c_i32]),
     "ncn_set_grid_bwd_merge": (c_i32, [c_i32]),
+    "ncn_rays_from_pixels": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp]),
     "ncn_field_prepare_rgb": (c_i32, [c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp]),
     "ncn_field_head_out": (c_i32, [c_vp, c_i32, c_i64, c_vp, c_vp, c_i32, c_i32, c_i32, c_vp]),
     "ncn_field_head_dout": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_f32, c_i64, c_vp, c_vp, c_i32, c_vp]),

@@ -87,9 +87,38 @@ bwd_h_kernel(const __half* __restrict__ dx_rgb, const float* __restrict__ d_sigm
   }
 }
 
+// rays from (image index, pixel index): rays_d = directions[pix] @ c2w[img][:, :3]^T, rays_o = c2w[img][:, 3]
+// (NeRFSystem.forward gather + get_rays, train_nerf.py:167-182, datasets/ray_utils.py:46-71) in one launch
+__global__ void __launch_bounds__(256)
+rays_kernel(const float* __restrict__ poses, const float* __restrict__ directions, const int64_t* __restrict__ img_idx,
+            const int64_t* __restrict__ pix_idx, int64_t n, float* __restrict__ rays_o, float* __restrict__ rays_d) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const float* c2w = poses + img_idx[i] * 12;
+    const float* d = directions + pix_idx[i] * 3;
+    const float dx = d[0], dy = d[1], dz = d[2];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      // matmul accumulation order of a (1x3)@(3x3) product: ((d0*R[r][0] + d1*R[r][1]) + d2*R[r][2])
+      rays_d[3 * i + r] = __fmaf_rn(dz, c2w[4 * r + 2], __fmaf_rn(dy, c2w[4 * r + 1], __fmul_rn(dx, c2w[4 * r])));
+      rays_o[3 * i + r] = c2w[4 * r + 3];
+    }
+  }
+}
+
 }  // namespace ncn
 
 using namespace ncn;
+
+extern "C" int ncn_rays_from_pixels(const float* poses, const float* directions, const int64_t* img_idx, const int64_t* pix_idx,
+                                    int64_t n, float* rays_o, float* rays_d, ncn_stream_t stream) {
+  NCN_CHECK_SIZE(n >= 0);
+  if (n == 0) return NCN_OK;
+  NCN_CHECK_PTR(poses); NCN_CHECK_PTR(directions); NCN_CHECK_PTR(img_idx); NCN_CHECK_PTR(pix_idx); NCN_CHECK_PTR(rays_o); NCN_CHECK_PTR(rays_d);
+  rays_kernel<<<persistent_grid(n, 256, 8), 256, 0, as_stream(stream)>>>(poses, directions, img_idx, pix_idx, n, rays_o, rays_d);
+  NCN_LAUNCH_OK();
+  return NCN_OK;
+}
 
 extern "C" int ncn_field_prepare_rgb(const float* dirs, const void* h_f16, int64_t n, const int32_t* n_dev, void* x_rgb_f16,
                                      float* sigmas, ncn_stream_t stream) {

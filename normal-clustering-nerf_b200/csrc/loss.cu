@@ -13,6 +13,7 @@
 // fixed point (2^-30 resolution) so the result is independent of the atomic ordering
 // (bit-reproducible run to run, unlike float atomics).
 #include "ncn_common.cuh"
+#include "mma.cuh"
 
 namespace ncn {
 
@@ -87,10 +88,19 @@ normals_bw_kernel(const float* __restrict__ origin, const float* __restrict__ di
   }
 }
 
-// ---------------------------------------------------------------- spherical k-means (one CTA)
-constexpr int kKmThreads = 1024;
+// ---------------------------------------------------------------- spherical k-means (one thread-block cluster)
+// The problem is tiny (<= 5120 training points x K = 20 x 20 iterations) but a single SM can issue only 4 warp
+// instructions per clock, and one Lloyd iteration is ~10^5 (point, centroid) pairs: on one CTA the kernel is
+// instruction-issue bound (measured: 1.4 M warp instructions, 300 us).  It therefore runs on a CLUSTER of 8 CTAs
+// (8 SMs): each CTA owns 1/8 of the training points in its shared memory, does assignment + a warp-aggregated
+// integer reduction (redux.sync; fixed point 2^20 => order independent => bit-reproducible), publishes its K x 4
+// partial sums in its own shared memory, and after one barrier.cluster every CTA folds all 8 partials through
+// distributed shared memory and updates the (replicated) centroids.  No atomics, no host round trip.
+constexpr int kKmThreads = 256;
+constexpr int kKmCluster = 8;
 constexpr int kKmMaxK = 64;
-constexpr double kFix = 1073741824.0;   // 2^30 fixed point for order-independent (reproducible) sums
+constexpr float kKmFix = 1048576.0f;     // 2^20
+constexpr int kAccStride = 33;
 
 __device__ __forceinline__ bool valid_normal(float x, float y, float z) {
   // losses.py:427-429: drop rows that are all zero / contain NaN / contain Inf
@@ -107,43 +117,80 @@ __device__ __forceinline__ int best_centroid(float x, float y, float z, const fl
   return best;
 }
 
-// Shared-memory plan (dynamic): training points xs[nt][3] (<= 256*K points, 60 KB at K=20).  Every Lloyd
-// iteration is (1) thread-per-point assignment (K dot products against the centroids in smem), (2) a WARP-
-// AGGREGATED integer reduction: the warp walks the distinct clusters present among its 32 points and folds
-// each cluster's members with redux.sync (fixed point 2^20, so the sums are order independent and the result is
-// bit-reproducible), one lane adds the warp total to the warp's PRIVATE accumulator row - no atomics, no
-// contention - (3) K*4 threads fold the 32 warp rows, and one warp updates / re-seeds / renormalises.
-constexpr float kKmFix = 1048576.0f;     // 2^20
-constexpr int kAccStride = 33;
-
-// adds (x,y,z,1) of every valid lane to acc[key*4 + {0,1,2,3}], a WARP-PRIVATE row of integer accumulators:
-// integer atomics commute, so the result does not depend on the order in which the lanes are served
+// adds (x,y,z,1) of every valid lane to acc[key*4 + {0,1,2,3}] (a warp-private row of int accumulators): the warp walks
+// the distinct keys present and folds each key's members with redux.sync
 __device__ __forceinline__ void warp_accumulate_by_key(int key, bool valid, float x, float y, float z, int* __restrict__ acc,
                                                        int lane) {
-  (void)lane;
-  // acc points at column `warp` of a [4*K][kAccStride] matrix (stride 33 words: conflict-free both for these atomics,
-  // whose addresses differ in the row, and for the fold below, which reads along a row)
-  if (valid) {
-    atomicAdd(acc + (4 * key) * kAccStride, __float2int_rn(x * kKmFix));
-    atomicAdd(acc + (4 * key + 1) * kAccStride, __float2int_rn(y * kKmFix));
-    atomicAdd(acc + (4 * key + 2) * kAccStride, __float2int_rn(z * kKmFix));
-    atomicAdd(acc + (4 * key + 3) * kAccStride, 1);
+  const int fx = __float2int_rn(x * kKmFix), fy = __float2int_rn(y * kKmFix), fz = __float2int_rn(z * kKmFix);
+  unsigned remaining = __ballot_sync(0xffffffffu, valid);
+  while (remaining) {
+    const int leader = __ffs(remaining) - 1;
+    const int k = __shfl_sync(0xffffffffu, key, leader);
+    const bool mine = valid && key == k;
+    const unsigned m = __ballot_sync(0xffffffffu, mine);
+    const int sx = __reduce_add_sync(0xffffffffu, mine ? fx : 0);
+    const int sy = __reduce_add_sync(0xffffffffu, mine ? fy : 0);
+    const int sz = __reduce_add_sync(0xffffffffu, mine ? fz : 0);
+    if (lane == leader) { acc[4 * k] += sx; acc[4 * k + 1] += sy; acc[4 * k + 2] += sz; acc[4 * k + 3] += __popc(m); }
+    remaining &= ~m;
   }
+  __syncwarp();
 }
 
-__global__ void __launch_bounds__(kKmThreads, 1)
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+// read an int from the same shared-memory variable of CTA `rank` of the cluster (DSMEM)
+__device__ __forceinline__ int dsmem_ld_int(const int* local_ptr, uint32_t rank) {
+  uint32_t a = (uint32_t)__cvta_generic_to_shared(local_ptr), ra;
+  int v;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(a), "r"(rank));
+  asm volatile("ld.shared::cluster.s32 %0, [%1];" : "=r"(v) : "r"(ra) : "memory");
+  return v;
+}
+
+__device__ __forceinline__ float dsmem_ld_float(const float* local_ptr, uint32_t rank) {
+  uint32_t a = (uint32_t)__cvta_generic_to_shared(local_ptr), ra;
+  float v;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(a), "r"(rank));
+  asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(ra) : "memory");
+  return v;
+}
+
+// ---- tensor-core Lloyd iteration (K <= 32) ---------------------------------------------------------------
+// Both halves of an iteration are tiny GEMMs over 16-point tiles, so they run on the warp MMA units:
+//   assignment : S[16 points x 8 clusters] = P[16 x 16] * C[16 x 8],  P row = (xh,yh,zh, xh,yh,zh, xl,yl,zl, 0..),
+//                C col = (ch, cl, ch, 0..): fp16 hi/lo splits, exact fp32 products, ~2^-22 relative accuracy
+//   accumulate : SUM[16 clusters x 8] += ONEHOT[16 clusters x 16 points] * Q[16 points x 8], Q row = (xh,yh,zh,xl,yl,zl,1,0)
+// ~120 instructions per 16-point tile instead of ~8 per (point, centroid) pair + a serial redux chain.
+__device__ __forceinline__ void split_hl(float v, float& hi, float& lo) {
+  hi = __half2float(__float2half_rn(v));
+  lo = v - hi;
+}
+__device__ __forceinline__ float centroid_row(const float* __restrict__ c, int row) {
+  if (row >= 9) return 0.f;
+  float hi, lo; split_hl(c[row % 3], hi, lo);
+  return (row >= 3 && row < 6) ? lo : hi;
+}
+
+__global__ void __cluster_dims__(kKmCluster, 1, 1) __launch_bounds__(kKmThreads, 1)
 kmeans_kernel(const float* __restrict__ x, int64_t n, ncn_kmeans_params p, float* __restrict__ centroids,
               int32_t* __restrict__ assign, int32_t* __restrict__ n_valid_out, int32_t* __restrict__ valid_idx,
               int nt_cap) {
   extern __shared__ __align__(16) unsigned char km_smem[];
-  float* xs = reinterpret_cast<float*>(km_smem);                 // [nt_cap][3]
+  float* xs = reinterpret_cast<float*>(km_smem);                 // this CTA's training points [my_n][3]
   __shared__ float s_c[kKmMaxK * 3];
-  __shared__ int s_wacc[kKmMaxK * 4 * kAccStride];   // [accumulator][warp] (stride 33), fixed point
+  __shared__ int s_wacc[(kKmThreads / 32) * kKmMaxK * 4];        // per-warp private accumulators
+  __shared__ int s_part[2][kKmMaxK * 4];                         // this CTA's partial sums (double buffered), read by peers
   __shared__ float s_acc[kKmMaxK * 4];
-  __shared__ int s_nvalid, s_warp_tot[32], s_base;
+  __shared__ float s_fw[(kKmThreads / 32) * 32 * 8];             // tensor-core path: per-warp (32 clusters x 8) partial sums
+  __shared__ float s_fpart[2][32 * 8];                           // this CTA's partial sums (double buffered), read by peers
+  __shared__ int s_nvalid, s_warp_tot[32], s_base, s_any_empty;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int K = p.k;
-  // 1) compact the valid rows (stable order) into valid_idx
+  const uint32_t rank = cluster_ctarank();
+  // 1) every CTA compacts the valid rows (stable order) - identical results, CTA 0 publishes them
   if (tid == 0) { s_base = 0; }
   __syncthreads();
   for (int64_t b0 = 0; b0 < n; b0 += kKmThreads) {
@@ -154,82 +201,190 @@ kmeans_kernel(const float* __restrict__ x, int64_t n, ncn_kmeans_params p, float
     if (lane == 0) s_warp_tot[wid] = __popc(bal);
     __syncthreads();
     if (wid == 0) {
-      const int w = s_warp_tot[lane];
+      const int w = lane < kKmThreads / 32 ? s_warp_tot[lane] : 0;
       const int inc = warp_scan_incl_i(w, lane);
-      s_warp_tot[lane] = inc - w;
+      if (lane < kKmThreads / 32) s_warp_tot[lane] = inc - w;
       if (lane == 31) s_nvalid = inc;
     }
     __syncthreads();
-    if (v) valid_idx[s_base + s_warp_tot[wid] + __popc(bal & ((1u << lane) - 1))] = (int32_t)i;
-    if (i < n && !v) assign[i] = -1;
+    if (rank == 0) {
+      if (v) valid_idx[s_base + s_warp_tot[wid] + __popc(bal & ((1u << lane) - 1))] = (int32_t)i;
+      if (i < n && !v) assign[i] = -1;
+    }
     __syncthreads();
     if (tid == 0) s_base += s_nvalid;
     __syncthreads();
   }
   const int nv = s_base;
-  if (tid == 0) *n_valid_out = nv;
+  if (rank == 0 && tid == 0) *n_valid_out = nv;
   if (nv == 0) {
-    for (int j = tid; j < K * 3; j += kKmThreads) centroids[j] = 0.f;
-    return;
+    if (rank == 0) for (int j = tid; j < K * 3; j += kKmThreads) centroids[j] = 0.f;
+    return;                         // uniform across the cluster: nobody reaches a cluster barrier
   }
-  // 2) training subset: at most max_points_per_centroid*K points, taken at a uniform stride over the valid rows
-  //    (faiss draws a random subset; equality with faiss is not a parity criterion), staged in shared memory
+  __threadfence();
+  cluster_sync_all();               // valid_idx (written by CTA 0) is visible to the whole cluster
+  // 2) training subset: at most max_points_per_centroid*K points at a uniform stride over the valid rows (faiss draws a
+  //    random subset; equality with faiss is not a parity criterion); CTA r owns training points r, r+8, r+16, ...
   const int nt = nv > nt_cap ? nt_cap : nv;
-  for (int j = tid; j < nt; j += kKmThreads) {
-    const int r = valid_idx[(int)(((int64_t)j * nv) / nt)];
+  const int my_n = (nt - (int)rank + kKmCluster - 1) / kKmCluster;
+  for (int j = tid; j < my_n; j += kKmThreads) {
+    const int gj = j * kKmCluster + (int)rank;
+    const int r = valid_idx[(int)(((int64_t)gj * nv) / nt)];
     xs[3 * j] = x[3 * r]; xs[3 * j + 1] = x[3 * r + 1]; xs[3 * j + 2] = x[3 * r + 2];
   }
-  __syncthreads();
-  // 3) init: K training points spread over the subset with a seeded offset
+  // 3) init (replicated): K training points spread over the subset with a seeded offset
   if (tid < K) {
     const uint32_t h = (uint32_t)p.seed * 2654435761u + 12345u;
     const int span = nt / K > 0 ? nt / K : 1;
     const int j = (int)((((int64_t)tid * nt) / K + (h % (uint32_t)span)) % nt);
-    float cx = xs[3 * j], cy = xs[3 * j + 1], cz = xs[3 * j + 2];
+    const int r = valid_idx[(int)(((int64_t)j * nv) / nt)];
+    float cx = x[3 * r], cy = x[3 * r + 1], cz = x[3 * r + 2];
     if (p.spherical) { const float l = sqrtf(cx * cx + cy * cy + cz * cz); if (l > 0.f) { cx /= l; cy /= l; cz /= l; } }
     s_c[3 * tid] = cx; s_c[3 * tid + 1] = cy; s_c[3 * tid + 2] = cz;
   }
   __syncthreads();
   // 4) Lloyd iterations
-  const int nt_round = (nt + 31) & ~31;
+  const int my_round = (my_n + 31) & ~31;
+  const bool use_tc = K <= 32;
+  const int g = lane >> 2, t = lane & 3;
+  const int n_tiles = (my_n + 15) >> 4;
+  __half* hq = reinterpret_cast<__half*>(km_smem + (((size_t)((nt_cap + kKmCluster - 1) / kKmCluster) * 12 + 15) & ~(size_t)15));
+  if (use_tc) {
+    // iteration-invariant fp16 point rows: hq[point] = (xh,yh,zh,xl,yl,zl,1,0); all-zero rows pad the last tile
+    for (int j = tid; j < n_tiles * 16; j += kKmThreads) {
+      uint4 row = make_uint4(0u, 0u, 0u, 0u);
+      if (j < my_n) {
+        float xh, xl, yh, yl, zh, zl;
+        split_hl(xs[3 * j], xh, xl); split_hl(xs[3 * j + 1], yh, yl); split_hl(xs[3 * j + 2], zh, zl);
+        row.x = pack_half2(xh, yh); row.y = pack_half2(zh, xl); row.z = pack_half2(yl, zl); row.w = pack_half2(1.f, 0.f);
+      }
+      reinterpret_cast<uint4*>(hq)[j] = row;
+    }
+    __syncthreads();
+  }
   for (int it = 0; it < p.niter; ++it) {
-    for (int a = tid; a < K * 4 * kAccStride; a += kKmThreads) s_wacc[a] = 0;
-    __syncthreads();
-    if (K <= 32) {
-      // centroids in registers: lane j holds centroid j, fetched by shuffle -> no shared-memory traffic in the dot loop
-      const float cx = lane < K ? s_c[3 * lane] : 0.f, cy = lane < K ? s_c[3 * lane + 1] : 0.f, cz = lane < K ? s_c[3 * lane + 2] : 0.f;
-      for (int j = tid; j < nt_round; j += kKmThreads) {
-        const bool v = j < nt;
-        float px = 0.f, py = 0.f, pz = 0.f;
-        if (v) { px = xs[3 * j]; py = xs[3 * j + 1]; pz = xs[3 * j + 2]; }
-        int b = 0; float bs = -INFINITY;
-        for (int q = 0; q < K; ++q) {
-          const float sc = px * __shfl_sync(0xffffffffu, cx, q) + py * __shfl_sync(0xffffffffu, cy, q) + pz * __shfl_sync(0xffffffffu, cz, q);
-          if (sc > bs) { bs = sc; b = q; }
+    if (use_tc) {
+      uint32_t cb[4][2];        // centroid fragments: clusters 8j+g, rows 2t,2t+1 / 2t+8,2t+9 of the expanded column
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int c = 8 * j + g;
+        const float zero3[3] = {0.f, 0.f, 0.f};
+        const float* cp = c < K ? s_c + 3 * c : zero3;
+        cb[j][0] = pack_half2(centroid_row(cp, 2 * t), centroid_row(cp, 2 * t + 1));
+        cb[j][1] = pack_half2(centroid_row(cp, 2 * t + 8), centroid_row(cp, 2 * t + 9));
+      }
+      float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+      for (int tile = wid; tile < n_tiles; tile += kKmThreads / 32) {
+        const int p0 = tile * 16;
+        uint32_t pa[4];
+        {
+          const uint4 r0 = reinterpret_cast<const uint4*>(hq)[p0 + g], r1 = reinterpret_cast<const uint4*>(hq)[p0 + g + 8];
+          // words: x=(xh,yh) y=(zh,xl) z=(yl,zl);  pairs needed: t0:(xh,yh) t1:(zh,xh) t2:(yh,zh) t3:(xl,yl) | t0:(zl,0)
+          auto sel = [&](const uint4& r) -> uint32_t {
+            if (t == 0) return r.x;
+            if (t == 1) return (r.y & 0xFFFFu) | (r.x << 16);
+            if (t == 2) return (r.x >> 16) | (r.y << 16);
+            return (r.y >> 16) | (r.z << 16);
+          };
+          pa[0] = sel(r0); pa[1] = sel(r1);
+          pa[2] = t == 0 ? (r0.z >> 16) : 0u; pa[3] = t == 0 ? (r1.z >> 16) : 0u;
         }
-        warp_accumulate_by_key(b, v, px, py, pz, s_wacc + wid, lane);
+        uint32_t pq[2];       // accumulation B fragment: column g of points 2t,2t+1 / 2t+8,2t+9
+        ldmatrix_x2_trans(pq, hq + (size_t)(p0 + (lane & 15)) * 8);
+        float best0 = -INFINITY, best1 = -INFINITY;
+        int bi0 = 0, bi1 = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (8 * j >= K) break;
+          float sc[4] = {0.f, 0.f, 0.f, 0.f};
+          mma16816(sc, pa, cb[j][0], cb[j][1]);
+          const int c0 = 8 * j + 2 * t;
+          if (c0 < K && sc[0] > best0) { best0 = sc[0]; bi0 = c0; }
+          if (c0 + 1 < K && sc[1] > best0) { best0 = sc[1]; bi0 = c0 + 1; }
+          if (c0 < K && sc[2] > best1) { best1 = sc[2]; bi1 = c0; }
+          if (c0 + 1 < K && sc[3] > best1) { best1 = sc[3]; bi1 = c0 + 1; }
+        }
+#pragma unroll
+        for (int o = 1; o <= 2; o <<= 1) {      // reduce over the quad (ties -> lowest cluster index)
+          const float ob0 = __shfl_xor_sync(0xffffffffu, best0, o), ob1 = __shfl_xor_sync(0xffffffffu, best1, o);
+          const int oi0 = __shfl_xor_sync(0xffffffffu, bi0, o), oi1 = __shfl_xor_sync(0xffffffffu, bi1, o);
+          if (ob0 > best0 || (ob0 == best0 && oi0 < bi0)) { best0 = ob0; bi0 = oi0; }
+          if (ob1 > best1 || (ob1 == best1 && oi1 < bi1)) { best1 = ob1; bi1 = oi1; }
+        }
+        // one-hot A fragments: assignments of points 2t, 2t+1 (quads 2t, 2t+1: "point g") and 2t+8, 2t+9 ("point g+8")
+        const int a_p0 = __shfl_sync(0xffffffffu, bi0, 8 * t), a_p1 = __shfl_sync(0xffffffffu, bi0, 8 * t + 4);
+        const int a_p8 = __shfl_sync(0xffffffffu, bi1, 8 * t), a_p9 = __shfl_sync(0xffffffffu, bi1, 8 * t + 4);
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+          if (16 * mt >= K) break;
+          const int c_lo = g + 16 * mt, c_hi = c_lo + 8;
+          uint32_t oh[4];
+          oh[0] = pack_half2(a_p0 == c_lo ? 1.f : 0.f, a_p1 == c_lo ? 1.f : 0.f);
+          oh[1] = pack_half2(a_p0 == c_hi ? 1.f : 0.f, a_p1 == c_hi ? 1.f : 0.f);
+          oh[2] = pack_half2(a_p8 == c_lo ? 1.f : 0.f, a_p9 == c_lo ? 1.f : 0.f);
+          oh[3] = pack_half2(a_p8 == c_hi ? 1.f : 0.f, a_p9 == c_hi ? 1.f : 0.f);
+          mma16816(acc[mt], oh, pq[0], pq[1]);
+        }
       }
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        float* row0 = s_fw + ((size_t)wid * 32 + g + 16 * mt) * 8 + 2 * t;
+        row0[0] = acc[mt][0]; row0[1] = acc[mt][1];
+        row0[64] = acc[mt][2]; row0[65] = acc[mt][3];            // cluster +8 -> 8 rows * 8 floats further
+      }
+      __syncthreads();
+      float* fpart = s_fpart[it & 1];
+      {
+        float tot = 0.f;                                          // 256 threads <-> 32 clusters x 8 columns, fixed order
+#pragma unroll
+        for (int w = 0; w < kKmThreads / 32; ++w) tot += s_fw[(size_t)w * 256 + tid];
+        fpart[tid] = tot;
+      }
+      cluster_sync_all();
+      {
+        float tot = 0.f;
+#pragma unroll
+        for (uint32_t r = 0; r < kKmCluster; ++r) tot += dsmem_ld_float(fpart + tid, r);
+        s_fw[tid] = tot;                                          // cluster total of (cluster tid/8, column tid%8)
+      }
+      if (tid == 0) s_any_empty = 0;
+      __syncthreads();
+      if (tid < K) {
+        const float* r = s_fw + tid * 8;
+        s_acc[4 * tid] = r[0] + r[3]; s_acc[4 * tid + 1] = r[1] + r[4]; s_acc[4 * tid + 2] = r[2] + r[5]; s_acc[4 * tid + 3] = r[6];
+      }
+      __syncthreads();
     } else {
-      for (int j = tid; j < nt_round; j += kKmThreads) {
-        const bool v = j < nt;
-        float px = 0.f, py = 0.f, pz = 0.f;
-        int b = 0;
-        if (v) { px = xs[3 * j]; py = xs[3 * j + 1]; pz = xs[3 * j + 2]; b = best_centroid(px, py, pz, s_c, K); }
-        warp_accumulate_by_key(b, v, px, py, pz, s_wacc + wid, lane);
-      }
+    int* wacc = s_wacc + wid * K * 4;
+    for (int a = lane; a < K * 4; a += 32) wacc[a] = 0;
+    __syncwarp();
+    for (int j = tid; j < my_round; j += kKmThreads) {
+      const bool v = j < my_n;
+      float px = 0.f, py = 0.f, pz = 0.f;
+      int b = 0;
+      if (v) { px = xs[3 * j]; py = xs[3 * j + 1]; pz = xs[3 * j + 2]; b = best_centroid(px, py, pz, s_c, K); }
+      warp_accumulate_by_key(b, v, px, py, pz, wacc, lane);
     }
     __syncthreads();
-    for (int a = wid; a < K * 4; a += 32) {       // warp `wid` folds accumulator rows wid, wid+32, ...
-      int part = s_wacc[a * kAccStride + lane];
-      const int tot = __reduce_add_sync(0xffffffffu, part);
-      if (lane == 0) s_acc[a] = (a & 3) == 3 ? (float)tot : (float)((double)tot / (double)kKmFix);
+    int* part = s_part[it & 1];
+    for (int a = tid; a < K * 4; a += kKmThreads) {
+      int t = 0;
+#pragma unroll
+      for (int w = 0; w < kKmThreads / 32; ++w) t += s_wacc[w * K * 4 + a];
+      part[a] = t;
     }
-    __syncthreads();
-    // new centroids = member means (thread per cluster); empty clusters split the currently largest one
-    // (faiss-style +-eps, rare -> one thread); then renormalise (thread per cluster)
-    __shared__ int s_any_empty;
+    cluster_sync_all();             // every CTA's partials are published
+    for (int a = tid; a < K * 4; a += kKmThreads) {
+      long long t = 0;
+#pragma unroll
+      for (uint32_t r = 0; r < kKmCluster; ++r) t += dsmem_ld_int(part + a, r);
+      s_acc[a] = (a & 3) == 3 ? (float)t : (float)((double)t / (double)kKmFix);
+    }
     if (tid == 0) s_any_empty = 0;
     __syncthreads();
+    }   // scalar path (K > 32)
+    // new centroids = member means (thread per cluster); empty clusters split the currently largest one
+    // (faiss-style +-eps, rare -> one thread); then renormalise.  Replicated identically in every CTA.
     if (tid < K) {
       const float c = s_acc[4 * tid + 3];
       if (c > 0.f) { s_c[3 * tid] = s_acc[4 * tid] / c; s_c[3 * tid + 1] = s_acc[4 * tid + 1] / c; s_c[3 * tid + 2] = s_acc[4 * tid + 2] / c; }
@@ -259,13 +414,16 @@ kmeans_kernel(const float* __restrict__ x, int64_t n, ncn_kmeans_params p, float
       if (l > 0.f) { s_c[3 * tid] /= l; s_c[3 * tid + 1] /= l; s_c[3 * tid + 2] /= l; }
     }
     __syncthreads();
+    // the partial buffer of iteration `it` is only overwritten in iteration it+2, i.e. after the barrier of it+1,
+    // which every CTA reaches only after it finished reading buffer `it`
   }
-  // 5) final assignment of every valid row (kmeans.index.search, losses.py:89) + centroids out
-  for (int j = tid; j < nv; j += kKmThreads) {
+  cluster_sync_all();               // no CTA may exit while a peer can still read its shared memory
+  // 5) final assignment of every valid row (kmeans.index.search, losses.py:89), split over the cluster + centroids out
+  for (int j = tid + (int)rank * kKmThreads; j < nv; j += kKmThreads * kKmCluster) {
     const int r = valid_idx[j];
     assign[r] = best_centroid(x[3 * r], x[3 * r + 1], x[3 * r + 2], s_c, K);
   }
-  for (int j = tid; j < K * 3; j += kKmThreads) centroids[j] = s_c[j];
+  if (rank == 0) for (int j = tid; j < K * 3; j += kKmThreads) centroids[j] = s_c[j];
 }
 
 // ---------------------------------------------------------------- orthogonal-triple selection (one CTA)
@@ -325,13 +483,13 @@ __device__ __forceinline__ float sgnf(float v) { return v > 0.f ? 1.f : (v < 0.f
 __global__ void __launch_bounds__(1024, 1)
 cluster_loss_fw_kernel(const float* __restrict__ nrm, const int32_t* __restrict__ labels, int64_t n,
                        float* __restrict__ losses, float* __restrict__ stats) {
-  __shared__ int s_wacc[12 * kAccStride];
+  __shared__ int s_wacc[32 * 12];
   __shared__ long long s_sum[9];
   __shared__ int s_cnt[3];
   __shared__ float s_c[9], s_mu[3];
   __shared__ float s_red[32][8];
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  for (int a = tid; a < 12 * kAccStride; a += blockDim.x) s_wacc[a] = 0;
+  for (int a = tid; a < 32 * 12; a += blockDim.x) s_wacc[a] = 0;
   __syncthreads();
   const int64_t n_round = (n + 31) & ~(int64_t)31;
   for (int64_t i = tid; i < n_round; i += blockDim.x) {
@@ -345,12 +503,12 @@ cluster_loss_fw_kernel(const float* __restrict__ nrm, const int32_t* __restrict_
       const float sg = l > 0 ? 1.f : -1.f;
       x = sg * nrm[3 * i]; y = sg * nrm[3 * i + 1]; z = sg * nrm[3 * i + 2];
     }
-    warp_accumulate_by_key(k, v, x, y, z, s_wacc + wid, lane);
+    warp_accumulate_by_key(k, v, x, y, z, s_wacc + wid * 12, lane);
   }
   __syncthreads();
   if (tid < 12) {
     long long t = 0;
-    for (int w = 0; w < 32; ++w) t += s_wacc[tid * kAccStride + w];
+    for (int w = 0; w < 32; ++w) t += s_wacc[w * 12 + tid];
     const int k = tid >> 2, d = tid & 3;
     if (d == 3) s_cnt[k] = (int)t; else s_sum[3 * k + d] = t;
   }
@@ -558,12 +716,12 @@ extern "C" int ncn_kmeans_spherical(const float* x, int64_t n_points, const ncn_
   if (n_points > 0) { NCN_CHECK_PTR(x); NCN_CHECK_PTR(assign); NCN_CHECK_PTR(workspace); }
   if (workspace_bytes < ncn_kmeans_workspace_bytes(n_points, p->k)) return NCN_E_SIZE;
   int64_t cap = (int64_t)p->max_points_per_centroid * p->k;
-  if (cap > 14336) cap = 14336;            // 14336 * 12 B = 168 KB of dynamic shared memory (+ 41 KB static)
+  if (cap > 65536) cap = 65536;
   if (cap > n_points) cap = n_points > 0 ? n_points : 1;
-  const size_t smem = (size_t)cap * 12 + 16;
-  // static (41 KB) + dynamic shared memory exceed the 48 KB default: always opt in
-  NCN_CUDA(cudaFuncSetAttribute(kmeans_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 172 * 1024));
-  kmeans_kernel<<<1, kKmThreads, smem, as_stream(stream)>>>(x, n_points, *p, centroids, assign, n_valid, (int32_t*)workspace, (int)cap);
+  const size_t per_cta = (size_t)(cap + kKmCluster - 1) / kKmCluster;
+  const size_t smem = per_cta * 12 + 16 + (per_cta + 16) * 16 + 16;               // this CTA's points (fp32) + fp16 rows
+  if (smem > 48 * 1024) NCN_CUDA(cudaFuncSetAttribute(kmeans_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kmeans_kernel<<<kKmCluster, kKmThreads, smem, as_stream(stream)>>>(x, n_points, *p, centroids, assign, n_valid, (int32_t*)workspace, (int)cap);
   NCN_LAUNCH_OK();
   return NCN_OK;
 }

@@ -42,9 +42,11 @@ class FusedStep:
         self.L = _lib.lib()
         f32 = dict(dtype=torch.float32, device=dev); f16 = dict(dtype=torch.float16, device=dev)
         E = lambda *s, **k: torch.empty(*s, **k)
-        # static inputs
-        self.rays_o, self.rays_d, self.target = E(R, 3, **f32), E(R, 3, **f32), E(R, 3, **f32)
+        # static inputs: ONE (3,R,3) buffer [rays_o | rays_d | target rgb] so a step needs a single input copy
+        self.inp = E(3, R, 3, **f32)
+        self.rays_o, self.rays_d, self.target = self.inp[0], self.inp[1], self.inp[2]
         self.noise = E(R, **f32)
+        self.gen_noise = True                # march jitter drawn inside the step (torch.rand_like of custom_functions.py:83)
         self.tri = None                      # (3, M) int64
         # marching
         self.hits_t = E(R, 1, 2, **f32)
@@ -131,6 +133,8 @@ class FusedStep:
         ck = check
         self.zeros.zero_()
         self.d_depth.zero_()
+        if self.gen_noise:
+            self.noise.uniform_()
         ck(L.ncn_ray_aabb_near(ptr(self.rays_o), ptr(self.rays_d), ptr(m.center), ptr(m.half_size), float(hp["rend_near_dist"]), R,
                                ptr(self.hits_t), st), "aabb")
         ck(L.ncn_march_train(ptr(self.rays_o), ptr(self.rays_d), ptr(self.hits_t), ptr(m.density_bitfield), m.cascades,
@@ -157,7 +161,7 @@ class FusedStep:
             ck(L.ncn_cluster_select(ptr(self.centroids), ptr(self.assign), self.M, 20, 1.0 - float(hp["loss_norm_can_tres"]),
                                     ptr(self.labels), ptr(self.sel), st), "select")
             ck(L.ncn_cluster_loss_fw(ptr(self.normals), ptr(self.labels), self.M, ptr(self.losses), ptr(self.stats), st), "cluster_fw")
-            ck(L.ncn_cluster_loss_bw(ptr(self.normals), ptr(self.labels), self.M, ptr(self.stats), ptr(self.weights), ptr(self.dn), st), "cluster_bw")
+            ck(L.ncn_cluster_loss_bw(ptr(self.normals), ptr(self.labels), self.M, ptr(self.stats), ptr(self.dev_sched[3:6]), ptr(self.dn), st), "cluster_bw")
             ck(L.ncn_normals_from_depth_bw(ptr(self.rays_d), ptr(self.rays_d), ptr(self.depth), x1, x2, x3, ptr(self.dn), self.M,
                                            ptr(self.d_depth), st), "normals_bw")
         # ---- backward
@@ -212,18 +216,23 @@ class FusedStep:
         h[4] = ls.w_sched(ls.w_dot, step) * GSCALE if on else 0.0
         h[5] = ls.w_sched(ls.w_l1, step) * GSCALE if on else 0.0
         self.dev_sched.copy_(h, non_blocking=True)
-        self.weights.copy_(self.dev_sched[3:6])
         ev = torch.cuda.Event()
         ev.record()
         self.ring_events[slot] = ev
 
-    def step(self, rays_o, rays_d, target_rgb, noise=None):
-        """one training step; inputs are device tensors (copied into the graph's static buffers)"""
+    def step(self, rays_o=None, rays_d=None, target_rgb=None, noise=None, packed=None):
+        """one training step.  Inputs are device tensors copied into the graph's static buffers: either
+        rays_o/rays_d/target_rgb (R,3) each, or `packed` (3,R,3) = [rays_o, rays_d, rgb] (one copy), or nothing when the
+        caller filled self.inp in place (e.g. rays_from_pixels)."""
         tr = self.tr
-        self.rays_o.copy_(rays_o); self.rays_d.copy_(rays_d); self.target.copy_(target_rgb)
-        if noise is None:
-            self.noise.uniform_()
-        else:
+        if packed is not None:
+            self.inp.copy_(packed)
+        elif rays_o is not None:
+            self.rays_o.copy_(rays_o); self.rays_d.copy_(rays_d); self.target.copy_(target_rgb)
+        if (noise is None) != self.gen_noise:
+            self.gen_noise = noise is None
+            self.graph = None                 # noise source is part of the captured sequence
+        if noise is not None:
             self.noise.copy_(noise)
         self._schedule()
         multi = tr.world_size > 1
@@ -240,6 +249,36 @@ class FusedStep:
                 tr.comm.allreduce_sum_(self.opt.grad)
                 self.graph[1].replay()
         tr.global_step += 1
+
+    def rays_from_pixels(self, img_idx, pix_idx):
+        """fill the static rays_o / rays_d buffers from (image, pixel) indices (one kernel)"""
+        tr = self.tr
+        check(self.L.ncn_rays_from_pixels(ptr(tr.poses), ptr(tr.directions), ptr(img_idx), ptr(pix_idx), self.R, ptr(self.rays_o),
+                                          ptr(self.rays_d), torch.cuda.current_stream().cuda_stream), "rays_from_pixels")
+
+    def update_grid(self, restore=None):
+        """occupancy-grid upkeep (models/ngp_mt.py:339-368), replayed as its own CUDA graph (steady state: warmup=False)"""
+        hp = self.hp
+        thr = 0.01 * hp["rend_max_samples"] / 3 ** 0.5 * hp["density_tresh_decay"]
+        if not self.use_graph:
+            self.model.update_density_grid(thr, warmup=False)
+            if restore is not None:
+                self.model.density_grid.copy_(restore[0]); self.model.density_bitfield.copy_(restore[1])
+            return
+        if getattr(self, "grid_graph", None) is None:
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                self.model.update_density_grid(thr, warmup=False)
+            torch.cuda.current_stream().wait_stream(s)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self.model.update_density_grid(thr, warmup=False)
+                if restore is not None:
+                    self.model.density_grid.copy_(restore[0]); self.model.density_bitfield.copy_(restore[1])
+            self.grid_graph = g
+        self.grid_graph.replay()
 
     def _capture(self, multi):
         # warm-up on a side stream (sets function attributes, touches every buffer), then capture
@@ -275,7 +314,7 @@ class FusedStep:
         d = {"rgb": float(z[0]) / (3 * R), "opacity": float(self.hp["loss_opacity_w"]) * float(z[1]) / R}
         if self.M > 0:
             l = torch.nan_to_num(self.losses.cpu())
-            w = self.weights.cpu() / GSCALE
+            w = self.dev_sched[3:6].cpu() / GSCALE
             d.update(norm_D_C_ort_dot=float(w[0] * l[0]), norm_D_C_centr_dot=float(w[1] * l[1]), norm_D_C_centr_L1=float(w[2] * l[2]))
         d["total"] = sum(d.values())
         return d, int(self.counter[0])

@@ -194,14 +194,25 @@ class NeRFTrainer:
             self.opt.grad_div.fill_(float(self.world_size))     # fused gradients are already un-scaled
         return self.fused
 
-    def train_step_fused(self, rays_o, rays_d, target_rgb, tri=None, update_grid=True, noise=None):
+    def train_step_fused(self, rays_o=None, rays_d=None, target_rgb=None, tri=None, update_grid=True, noise=None, packed=None,
+                         grid_restore=None):
         """same step as train_step, through the fused path; returns nothing (stats via self.fused.stats_host())"""
         fs = self.fused_step()
         if tri is not None and (fs.tri is None or fs.tri.data_ptr() != tri.data_ptr()):
             fs.set_triangles(tri)
-        if update_grid:
-            self.maybe_update_grid()
-        fs.step(rays_o, rays_d, target_rgb, noise=noise)
+        if update_grid and self.global_step % self.hp["update_interval"] == 0:
+            if self.global_step < self.hp["warmup_steps"]:
+                self.maybe_update_grid()
+            else:
+                fs.update_grid(restore=grid_restore)
+        fs.step(rays_o, rays_d, target_rgb, noise=noise, packed=packed)
+
+    def train_step_from_pixels(self, img_idx, pix_idx, target_rgb, update_grid=True, grid_restore=None):
+        """public end-to-end entry: (image, pixel) indices + target colours on the device -> one fused training step"""
+        fs = self.fused_step()
+        fs.rays_from_pixels(img_idx, pix_idx)
+        fs.target.copy_(target_rgb)
+        self.train_step_fused(update_grid=update_grid, grid_restore=grid_restore)
 
     def train_step(self, rays_o, rays_d, target, update_grid=True):
         if update_grid:

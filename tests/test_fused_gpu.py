@@ -48,6 +48,7 @@ def test_fused_matches_module_path():
     fs = tr.fused_step(use_graph=False)
     fs.set_triangles(tri)
     fs.rays_o.copy_(rays_o); fs.rays_d.copy_(rays_d); fs.target.copy_(rgb); fs.noise.copy_(noise)
+    fs.gen_noise = False
     fs._schedule()
     fs._run()
     torch.cuda.synchronize()
@@ -88,3 +89,19 @@ def test_fused_graph_replay_trains():
             l0 = fs.stats_host()[0]["rgb"]
     l1 = fs.stats_host()[0]["rgb"]
     assert l1 < l0, (l0, l1)
+
+
+def test_rays_from_pixels_matches_get_rays():
+    """ncn_rays_from_pixels == the reference's gather + get_rays (datasets/ray_utils.py:46-71) restated in torch"""
+    from ncn_b200 import synth
+    tr, *_ = _setup(R=1024, seed=2)
+    poses = torch.from_numpy(synth.camera_poses(50, 0)).cuda(); dirs = torch.from_numpy(synth.pixel_directions("hypersim")).cuda()
+    tr.set_cameras(poses, dirs)
+    g = torch.Generator(device="cuda").manual_seed(0)
+    img = torch.randint(0, 50, (1024,), device="cuda", generator=g); pix = torch.randint(0, 1024 * 768, (1024,), device="cuda", generator=g)
+    fs = tr.fused_step(use_graph=False)
+    fs.rays_from_pixels(img, pix)
+    c2w = poses[img]
+    rays_d = (dirs[pix][:, None, :] @ c2w[..., :3].transpose(1, 2))[:, 0]
+    torch.testing.assert_close(fs.rays_d, rays_d, rtol=1e-6, atol=1e-7)
+    assert torch.equal(fs.rays_o, c2w[..., 3])
