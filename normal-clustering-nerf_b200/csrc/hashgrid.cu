@@ -32,6 +32,10 @@ __device__ __forceinline__ uint32_t grid_index(uint32_t gx, uint32_t gy, uint32_
   if (stride <= size) { index += gy * stride; stride *= res;
     if (stride <= size) { index += gz * stride; stride *= res; } }
   if (size < stride) index = gx ^ (gy * 2654435761u) ^ (gz * 805459861u);
+  // hashed levels hold exactly T = 2^log2_T entries (mask); on a dense level index < res^3 <= size for every in-range corner,
+  // so the general modulo is only reached by out-of-range inputs
+  if ((size & (size - 1u)) == 0u) return index & (size - 1u);
+  if (index < size) return index;
   return index % size;
 }
 

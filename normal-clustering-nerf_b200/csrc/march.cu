@@ -54,6 +54,10 @@ __device__ __forceinline__ int mip_from_dt(float dt, float gs_f, int cascades) {
 
 struct Cell { int nx, ny, nz; float mip_bound; bool occ; };
 
+// kSimple = (cascades == 1 && exp_step_factor == 0): dt, the mip bound and its reciprocal are per-launch constants, so the
+// serial per-ray chain sheds the calc_dt / frexp / IEEE-reciprocal work (the values are bit-identical, see const_dt)
+struct SimpleCfg { float dt, mip_bound, mb_inv; };
+
 __device__ __forceinline__ int cell_coord(float x, float mb_inv, const MarchCfg& c) {
   const float v = __fmul_rn(__fmul_rn(__fmaf_rn(x, mb_inv, 1.0f), 0.5f), c.gs_f);
   return (int)fmaxf(0.0f, fminf(v, c.gs_m1));   // clamp(v, 0, G-1) then float->int truncation
@@ -96,13 +100,23 @@ __device__ __forceinline__ float skip_cell(float t, const Cell& k, float x, floa
 }
 
 // ---- train: pass 1 (one thread per ray): march, record sample ts, count -------------------
+// The DDA is a serial, divergent fp32 chain: a warp costs the UNION of its lanes' paths and there is nothing to hide
+// latency with.  Only kRaysPerWarp lanes of each warp carry a ray, which shrinks the union and gives every SM
+// scheduler several warps to interleave (8192 rays -> 1024 warps instead of 256).
+constexpr int kRaysPerWarp = 8;
+
+template <bool kSimple>
 __global__ void __launch_bounds__(64)
 march_train_count_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d,
                          const float* __restrict__ hits_t, const uint8_t* __restrict__ bitfield,
                          const float* __restrict__ noise, MarchCfg c, int64_t n_rays,
                          int32_t* __restrict__ counts, float* __restrict__ ts_scratch) {
-  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  if (lane >= kRaysPerWarp) return;
+  const int64_t r = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * kRaysPerWarp + lane;
   if (r >= n_rays) return;
+  SimpleCfg sc;
+  sc.dt = c.dt_min; sc.mip_bound = fminf(0.5f, c.scale); sc.mb_inv = __frcp_rn(sc.mip_bound);
   const float ox = rays_o[3 * r], oy = rays_o[3 * r + 1], oz = rays_o[3 * r + 2];
   const float dx = rays_d[3 * r], dy = rays_d[3 * r + 1], dz = rays_d[3 * r + 2];
   const float ix = __frcp_rn(dx), iy = __frcp_rn(dy), iz = __frcp_rn(dz);
@@ -113,15 +127,38 @@ march_train_count_kernel(const float* __restrict__ rays_o, const float* __restri
   if (t >= 0.0f && noise != nullptr) t = __fmaf_rn(calc_dt(t, c), noise[r], t);   // raymarching.cu:195-198
   float* out = ts_scratch + r * (int64_t)c.max_samples;
   int n = 0;
-  while (0.0f <= t && t < t2 && n < c.max_samples) {
-    const float x = __fmaf_rn(dx, t, ox), y = __fmaf_rn(dy, t, oy), z = __fmaf_rn(dz, t, oz);
-    const float dt = calc_dt(t, c);
-    const Cell k = locate(x, y, z, dt, c, bitfield);
-    if (k.occ) {
-      out[n++] = t;
-      t = __fadd_rn(t, dt);
-    } else {
-      t = skip_cell(t, k, x, y, z, sx, sy, sz, ix, iy, iz, c);
+  if (kSimple) {
+    const int max_samples = c.max_samples;
+    const float gs_f = c.gs_f, gs_m1 = c.gs_m1, gs_inv = c.gs_inv;
+    while (0.0f <= t && t < t2 && n < max_samples) {
+      const float x = __fmaf_rn(dx, t, ox), y = __fmaf_rn(dy, t, oy), z = __fmaf_rn(dz, t, oz);
+      const int nx = (int)fmaxf(0.0f, fminf(__fmul_rn(__fmul_rn(__fmaf_rn(x, sc.mb_inv, 1.0f), 0.5f), gs_f), gs_m1));
+      const int ny = (int)fmaxf(0.0f, fminf(__fmul_rn(__fmul_rn(__fmaf_rn(y, sc.mb_inv, 1.0f), 0.5f), gs_f), gs_m1));
+      const int nz = (int)fmaxf(0.0f, fminf(__fmul_rn(__fmul_rn(__fmaf_rn(z, sc.mb_inv, 1.0f), 0.5f), gs_f), gs_m1));
+      const uint32_t idx = morton3d((uint32_t)nx, (uint32_t)ny, (uint32_t)nz);
+      const bool occ = (__ldg(bitfield + (idx >> 3)) >> (idx & 7u)) & 1u;
+      if (occ) {
+        out[n++] = t;
+        t = __fadd_rn(t, sc.dt);
+      } else {
+        const float tx = __fmul_rn(__fmaf_rn(sc.mip_bound, __fmaf_rn(__fmul_rn(__fadd_rn(__fadd_rn((float)nx, 0.5f), sx), gs_inv), 2.0f, -1.0f), -x), ix);
+        const float ty = __fmul_rn(__fmaf_rn(sc.mip_bound, __fmaf_rn(__fmul_rn(__fadd_rn(__fadd_rn((float)ny, 0.5f), sy), gs_inv), 2.0f, -1.0f), -y), iy);
+        const float tz = __fmul_rn(__fmaf_rn(sc.mip_bound, __fmaf_rn(__fmul_rn(__fadd_rn(__fadd_rn((float)nz, 0.5f), sz), gs_inv), 2.0f, -1.0f), -z), iz);
+        const float t_target = __fadd_rn(t, fmaxf(0.0f, fminf(tx, fminf(ty, tz))));
+        do { t = __fadd_rn(t, sc.dt); } while (t < t_target);
+      }
+    }
+  } else {
+    while (0.0f <= t && t < t2 && n < c.max_samples) {
+      const float x = __fmaf_rn(dx, t, ox), y = __fmaf_rn(dy, t, oy), z = __fmaf_rn(dz, t, oz);
+      const float dt = calc_dt(t, c);
+      const Cell k = locate(x, y, z, dt, c, bitfield);
+      if (k.occ) {
+        out[n++] = t;
+        t = __fadd_rn(t, dt);
+      } else {
+        t = skip_cell(t, k, x, y, z, sx, sy, sz, ix, iy, iz, c);
+      }
     }
   }
   counts[r] = n;
@@ -285,9 +322,14 @@ extern "C" int ncn_march_train_count(const float* rays_o, const float* rays_d, c
     if (((uintptr_t)hits_t & 7) || ((uintptr_t)workspace & 255)) return NCN_E_ALIGN;
     int32_t* counts = (int32_t*)workspace;
     float* ts_scratch = (float*)((char*)workspace + align256((size_t)n_rays * sizeof(int32_t)));
-    const int threads = 64;
-    march_train_count_kernel<<<(unsigned)ceil_div(n_rays, threads), threads, 0, as_stream(stream)>>>(
-        rays_o, rays_d, hits_t, density_bitfield, noise, c, n_rays, counts, ts_scratch);
+    const int threads = 64;                                   // 2 warps x kRaysPerWarp rays
+    const unsigned blocks = (unsigned)ceil_div(n_rays, (threads / 32) * kRaysPerWarp);
+    if (c.cascades == 1 && c.const_dt)
+      march_train_count_kernel<true><<<blocks, threads, 0, as_stream(stream)>>>(rays_o, rays_d, hits_t, density_bitfield, noise, c,
+                                                                             n_rays, counts, ts_scratch);
+    else
+      march_train_count_kernel<false><<<blocks, threads, 0, as_stream(stream)>>>(rays_o, rays_d, hits_t, density_bitfield, noise, c,
+                                                                              n_rays, counts, ts_scratch);
     NCN_LAUNCH_OK();
     march_scan_kernel<<<1, kScanThreads, 0, as_stream(stream)>>>(counts, n_rays, rays_a, counter);
   } else {

@@ -12,17 +12,21 @@ struct AdamArgs {
   float lr, beta1, beta2, eps, weight_decay, bc1, bc2;
 };
 
-__device__ __forceinline__ void adam_one(float& p, float& g, float& m, float& v, const AdamArgs& a, float gmul) {
+// apex FusedAdam (adam_w_mode) update.  The two bias corrections are applied as reciprocals computed once per thread
+// and the final quotient uses the fast divider (<= 2 ulp from the IEEE quotient apex computes; the pass stays
+// bandwidth bound instead of spending ~40 instructions per element on three IEEE divisions)
+__device__ __forceinline__ void adam_one(float& p, float& g, float& m, float& v, const AdamArgs& a, float gmul, float inv_bc1,
+                                         float inv_bc2) {
   const float gr = g * gmul;
   m = a.beta1 * m + (1.f - a.beta1) * gr;
   v = a.beta2 * v + (1.f - a.beta2) * gr * gr;
-  const float denom = sqrtf(v / a.bc2) + a.eps;
-  const float upd = (m / a.bc1) / denom + a.weight_decay * p;
+  const float denom = sqrtf(v * inv_bc2) + a.eps;
+  const float upd = __fdividef(m * inv_bc1, denom) + a.weight_decay * p;
   p = p - a.lr * upd;
   g = 0.f;
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 adam_kernel(float* __restrict__ param, float* __restrict__ grad, float* __restrict__ m, float* __restrict__ v,
             __half* __restrict__ p16, int64_t n, AdamArgs a, const float* __restrict__ grad_div,
             const int32_t* __restrict__ skip, const float* __restrict__ clip_coef, const float* __restrict__ lr_bc) {
@@ -31,24 +35,43 @@ adam_kernel(float* __restrict__ param, float* __restrict__ grad, float* __restri
   float gmul = 1.f;
   if (grad_div) gmul = 1.f / *grad_div;
   if (clip_coef) gmul *= *clip_coef;
+  const float inv_bc1 = 1.f / a.bc1, inv_bc2 = 1.f / a.bc2;
   const int64_t n4 = n >> 2;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
-    float4 g = reinterpret_cast<float4*>(grad)[i];
-    if (do_skip) { reinterpret_cast<float4*>(grad)[i] = make_float4(0.f, 0.f, 0.f, 0.f); continue; }
-    float4 p = reinterpret_cast<float4*>(param)[i];
-    float4 mm = reinterpret_cast<float4*>(m)[i];
-    float4 vv = reinterpret_cast<float4*>(v)[i];
-    adam_one(p.x, g.x, mm.x, vv.x, a, gmul); adam_one(p.y, g.y, mm.y, vv.y, a, gmul);
-    adam_one(p.z, g.z, mm.z, vv.z, a, gmul); adam_one(p.w, g.w, mm.w, vv.w, a, gmul);
-    reinterpret_cast<float4*>(param)[i] = p;
-    reinterpret_cast<float4*>(m)[i] = mm;
-    reinterpret_cast<float4*>(v)[i] = vv;
-    reinterpret_cast<float4*>(grad)[i] = g;
+  // two float4 per array per iteration: 8 independent 16 B loads in flight per thread
+  for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < n4; i0 += 2 * stride) {
+    const int64_t i1 = i0 + stride;
+    const bool two = i1 < n4;
+    float4 g0 = __ldcs(reinterpret_cast<const float4*>(grad) + i0);
+    float4 g1 = two ? __ldcs(reinterpret_cast<const float4*>(grad) + i1) : make_float4(0.f, 0.f, 0.f, 0.f);
+    if (do_skip) {
+      reinterpret_cast<float4*>(grad)[i0] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (two) reinterpret_cast<float4*>(grad)[i1] = make_float4(0.f, 0.f, 0.f, 0.f);
+      continue;
+    }
+    float4 p0 = __ldcs(reinterpret_cast<const float4*>(param) + i0), m0 = __ldcs(reinterpret_cast<const float4*>(m) + i0),
+           v0 = __ldcs(reinterpret_cast<const float4*>(v) + i0);
+    float4 p1 = p0, m1 = m0, v1 = v0;
+    if (two) { p1 = __ldcs(reinterpret_cast<const float4*>(param) + i1); m1 = __ldcs(reinterpret_cast<const float4*>(m) + i1); v1 = __ldcs(reinterpret_cast<const float4*>(v) + i1); }
+    adam_one(p0.x, g0.x, m0.x, v0.x, a, gmul, inv_bc1, inv_bc2); adam_one(p0.y, g0.y, m0.y, v0.y, a, gmul, inv_bc1, inv_bc2);
+    adam_one(p0.z, g0.z, m0.z, v0.z, a, gmul, inv_bc1, inv_bc2); adam_one(p0.w, g0.w, m0.w, v0.w, a, gmul, inv_bc1, inv_bc2);
+    reinterpret_cast<float4*>(param)[i0] = p0; reinterpret_cast<float4*>(m)[i0] = m0; reinterpret_cast<float4*>(v)[i0] = v0;
+    reinterpret_cast<float4*>(grad)[i0] = g0;
     if (p16) {
-      const __half2 lo = __floats2half2_rn(p.x, p.y), hi = __floats2half2_rn(p.z, p.w);
+      const __half2 lo = __floats2half2_rn(p0.x, p0.y), hi = __floats2half2_rn(p0.z, p0.w);
       uint2 pk; pk.x = *reinterpret_cast<const uint32_t*>(&lo); pk.y = *reinterpret_cast<const uint32_t*>(&hi);
-      reinterpret_cast<uint2*>(p16)[i] = pk;
+      reinterpret_cast<uint2*>(p16)[i0] = pk;
+    }
+    if (two) {
+      adam_one(p1.x, g1.x, m1.x, v1.x, a, gmul, inv_bc1, inv_bc2); adam_one(p1.y, g1.y, m1.y, v1.y, a, gmul, inv_bc1, inv_bc2);
+      adam_one(p1.z, g1.z, m1.z, v1.z, a, gmul, inv_bc1, inv_bc2); adam_one(p1.w, g1.w, m1.w, v1.w, a, gmul, inv_bc1, inv_bc2);
+      reinterpret_cast<float4*>(param)[i1] = p1; reinterpret_cast<float4*>(m)[i1] = m1; reinterpret_cast<float4*>(v)[i1] = v1;
+      reinterpret_cast<float4*>(grad)[i1] = g1;
+      if (p16) {
+        const __half2 lo = __floats2half2_rn(p1.x, p1.y), hi = __floats2half2_rn(p1.z, p1.w);
+        uint2 pk; pk.x = *reinterpret_cast<const uint32_t*>(&lo); pk.y = *reinterpret_cast<const uint32_t*>(&hi);
+        reinterpret_cast<uint2*>(p16)[i1] = pk;
+      }
     }
   }
   const int64_t t = (n4 << 2) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -56,7 +79,7 @@ adam_kernel(float* __restrict__ param, float* __restrict__ grad, float* __restri
     float g = grad[t];
     if (!do_skip) {
       float p = param[t], mm = m[t], vv = v[t];
-      adam_one(p, g, mm, vv, a, gmul);
+      adam_one(p, g, mm, vv, a, gmul, inv_bc1, inv_bc2);
       param[t] = p; m[t] = mm; v[t] = vv;
       if (p16) p16[t] = __float2half_rn(p);
     }
@@ -116,7 +139,7 @@ extern "C" int ncn_adam_step(float* param, float* grad, float* m, float* v, void
   AdamArgs a;
   a.lr = lr; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.weight_decay = weight_decay;
   a.bc1 = 1.0f - powf(beta1, (float)step); a.bc2 = 1.0f - powf(beta2, (float)step);
-  const int grid = persistent_grid((n + 3) / 4, 256, 8);
+  const int grid = persistent_grid((n + 7) / 8, 256, 4);
   adam_kernel<<<grid, 256, 0, as_stream(stream)>>>(param, grad, m, v, (__half*)param_f16, n, a, grad_div_dev, skip_dev,
                                                    clip_coef_dev, lr_bc_dev);
   NCN_LAUNCH_OK();

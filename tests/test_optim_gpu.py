@@ -1,0 +1,71 @@
+"""GPU: fused Adam / clip / sum-of-squares kernels against the apex FusedAdam (adam_w_mode) update restated in fp64
+(train_nerf.py:262-285: eps 1e-15, weight decay 0 / 1e-6; clip_grad_norm_ 0.05, train_nerf.py:955)."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _ref_step(p, g, m, v, lr, b1, b2, eps, wd, t, gdiv, coef):
+    g = g.double() / gdiv * coef
+    m = b1 * m.double() + (1 - b1) * g
+    v = b2 * v.double() + (1 - b2) * g * g
+    bc1, bc2 = 1 - b1 ** t, 1 - b2 ** t
+    upd = (m / bc1) / ((v / bc2).sqrt() + eps) + wd * p.double()
+    return p.double() - lr * upd, m, v
+
+
+@pytest.mark.parametrize("n,wd", [(11445040, 0.0), (10243, 1e-6), (5, 1e-6)])
+def test_adam_matches_reference_formula(ncn, n, wd):
+    from ncn_b200 import _lib
+    from ncn_b200._lib import check, ptr, stream
+    L = _lib.lib()
+    g = torch.Generator(device="cuda").manual_seed(n)
+    n_pad = (n + 3) // 4 * 4
+    p = torch.randn(n_pad, device="cuda", generator=g) * 0.1
+    grad = torch.randn(n_pad, device="cuda", generator=g) * 3.0
+    grad[::7] = 0
+    m = torch.randn(n_pad, device="cuda", generator=g) * 0.01
+    v = torch.rand(n_pad, device="cuda", generator=g) * 1e-4
+    p16 = torch.zeros(n_pad, dtype=torch.float16, device="cuda")
+    gdiv = torch.tensor([1024.0], device="cuda")
+    sumsq = torch.zeros(1, device="cuda"); flag = torch.zeros(1, dtype=torch.int32, device="cuda"); coef = torch.ones(1, device="cuda")
+    check(L.ncn_grad_sumsq(ptr(grad), n, ptr(gdiv), ptr(sumsq), ptr(flag), stream()))
+    check(L.ncn_clip_coef(ptr(sumsq), 0.05, ptr(coef), stream()))
+    want_norm = float((grad[:n].double() / 1024).norm())
+    assert abs(math.sqrt(float(sumsq)) - want_norm) <= 1e-4 * want_norm and int(flag) == 0
+    want_coef = min(1.0, 0.05 / (want_norm + 1e-6))
+    assert abs(float(coef) - want_coef) <= 1e-4 * want_coef
+    p_old = p.clone()
+    rp, rm, rv = _ref_step(p[:n], grad[:n], m[:n], v[:n], 1e-2, 0.9, 0.999, 1e-15, wd, 7, 1024.0, float(coef))
+    check(L.ncn_adam_step(ptr(p), ptr(grad), ptr(m), ptr(v), ptr(p16), n, 1e-2, 0.9, 0.999, 1e-15, wd, 7, ptr(gdiv), ptr(flag), ptr(coef),
+                          None, stream()))
+    # compare the applied update (fp32 storage of p bounds the absolute error by ulp(p))
+    torch.testing.assert_close((p[:n] - p_old[:n]).double(), rp - p_old[:n].double(), rtol=1e-4, atol=2e-7)
+    torch.testing.assert_close(m[:n].double(), rm, rtol=1e-5, atol=1e-9)
+    torch.testing.assert_close(v[:n].double(), rv, rtol=1e-5, atol=1e-12)
+    assert (grad[:n] == 0).all()                                   # the pass zeroes the gradient
+    assert torch.equal(p16[:n], p[:n].half())                      # and refreshes the fp16 working copy
+    # device-side schedule (graph replay) == host scalars
+    p2 = p.clone(); m2 = m.clone(); v2 = v.clone(); g2 = torch.randn(n_pad, device="cuda", generator=g)
+    p3 = p.clone(); m3 = m.clone(); v3 = v.clone(); g3 = g2.clone()
+    check(L.ncn_adam_step(ptr(p2), ptr(g2), ptr(m2), ptr(v2), None, n, 3e-3, 0.9, 0.999, 1e-15, wd, 9, None, None, None, None, stream()))
+    sched = torch.tensor([3e-3, 1 - 0.9 ** 9, 1 - 0.999 ** 9], device="cuda")
+    check(L.ncn_adam_step(ptr(p3), ptr(g3), ptr(m3), ptr(v3), None, n, 0.0, 0.9, 0.999, 1e-15, wd, 1, None, None, None, ptr(sched), stream()))
+    torch.testing.assert_close(p2, p3, rtol=1e-6, atol=1e-9)
+
+
+def test_adam_skips_on_nonfinite(ncn):
+    from ncn_b200 import _lib
+    from ncn_b200._lib import check, ptr, stream
+    L = _lib.lib()
+    n = 4096
+    p = torch.ones(n, device="cuda"); grad = torch.ones(n, device="cuda"); grad[100] = float("inf")
+    m = torch.zeros(n, device="cuda"); v = torch.zeros(n, device="cuda")
+    sumsq = torch.zeros(1, device="cuda"); flag = torch.zeros(1, dtype=torch.int32, device="cuda")
+    check(L.ncn_grad_sumsq(ptr(grad), n, None, ptr(sumsq), ptr(flag), stream()))
+    assert int(flag) == 1
+    check(L.ncn_adam_step(ptr(p), ptr(grad), ptr(m), ptr(v), None, n, 1e-2, 0.9, 0.999, 1e-15, 0.0, 1, None, ptr(flag), None, None, stream()))
+    assert (p == 1).all() and (m == 0).all() and (grad == 0).all()

@@ -1,0 +1,26 @@
+"""One eager fused training step for ncu captures (no CUDA graph). Not part of the product."""
+import os
+import sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import ncn_b200
+from ncn_b200 import synth, vren
+from ncn_b200.trainer import NeRFTrainer
+
+dev = torch.device("cuda:0")
+torch.manual_seed(0)
+R = 8192
+tr = NeRFTrainer(dict(batch_size=R), device=dev)
+grid = synth.density_grid_from_occupancy(synth.room_occupancy(128, 0.5, seed=0))
+tr.model.density_grid.copy_(torch.from_numpy(grid).to(dev))
+vren.packbits(tr.model.density_grid, 5.9, tr.model.density_bitfield)
+tr.global_step = 3009
+b = synth.patch_batch(R, seed=0)
+ro = torch.from_numpy(b["rays_o"]).to(dev); rd = torch.from_numpy(b["rays_d"]).to(dev)
+rgb = torch.rand(R, 3, device=dev)
+fs = tr.fused_step(use_graph=False)
+fs.set_triangles(torch.from_numpy(b["tri"]).to(dev))
+for i in range(int(sys.argv[1]) if len(sys.argv) > 1 else 3):
+    tr.train_step_fused(ro, rd, rgb, update_grid=False)
+torch.cuda.synchronize()
+print("ok", fs.stats_host())
