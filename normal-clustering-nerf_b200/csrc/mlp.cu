@@ -411,7 +411,7 @@ extern "C" int ncn_mlp_fwd(const ncn_mlp_desc* d, const void* x, const void* w, 
 // tcgen05 / TMEM implementation (mlp_tc05.cu)
 int ncn_mlp_bwd_tc05_try(int in_pad, int out_pad, int n_hidden, const void* x, const void* w, const void* out, const void* acts,
                          const void* dout, int64_t n, const int32_t* n_dev, int out_act, float grad_scale, float* grad_w,
-                         void* dx, cudaStream_t st);
+                         void* dx, int* tile_counter, cudaStream_t st);
 static int g_mlp_bwd_impl = 1;     // 1 = tcgen05/TMEM weight gradients (default), 0 = warp-MMA dgrad + split-K wgrad kernels
 extern "C" int ncn_set_mlp_bwd_impl(int impl) { const int old = g_mlp_bwd_impl; g_mlp_bwd_impl = impl; return old; }
 
@@ -427,8 +427,10 @@ extern "C" int ncn_mlp_bwd(const ncn_mlp_desc* d, const void* x, const void* w, 
   if (((uintptr_t)x | (uintptr_t)w | (uintptr_t)out | (uintptr_t)acts | (uintptr_t)dL_dout | (uintptr_t)scratch | (uintptr_t)dL_dx) & 15)
     return NCN_E_ALIGN;
   if (g_mlp_bwd_impl == 1) {
+    // the last 256 bytes of the caller's scratch hold the tile counter of the persistent kernel
+    int* tile_counter = (int*)((char*)scratch + ((ncn_mlp_bwd_workspace_bytes(d, n) - 256) & ~(size_t)15));
     rc = ncn_mlp_bwd_tc05_try(ip, op, d->n_hidden, x, w, out, acts, dL_dout, n, n_dev, d->out_activation, grad_scale, grad_w, dL_dx,
-                              as_stream(stream));
+                              tile_counter, as_stream(stream));
     if (rc != NCN_E_UNSUPPORTED) return rc;
   }
   NCN_MLP_DISPATCH(ip, op, (launch_bwd<kI, kO>(d, x, w, out, acts, dL_dout, n, grad_w, dL_dx, grad_scale, scratch, n_dev, as_stream(stream))))

@@ -178,8 +178,9 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 mlp_bwd_tc05_kernel(const __half* __restrict__ x, const __half* __restrict__ w, const __half* __restrict__ out,
                     const __half* __restrict__ acts, const __half* __restrict__ dout, int64_t n_cap,
                     const int32_t* __restrict__ n_dev, int out_act, float grad_scale, float* __restrict__ grad_w,
-                    __half* __restrict__ dx) {
+                    __half* __restrict__ dx, int* __restrict__ tile_counter) {
   using LY = TcLayout<IN, OUT, NH>;
+  __shared__ int s_next_tile;
   int64_t n = n_cap;
   if (n_dev != nullptr) { const int64_t nd = *n_dev; if (nd < n) n = nd; }
   extern __shared__ __align__(128) unsigned char tc_smem[];
@@ -206,35 +207,45 @@ mlp_bwd_tc05_kernel(const __half* __restrict__ x, const __half* __restrict__ w, 
 
   const int64_t n_tiles = (n + kTile - 1) / kTile;
   int it = 0;
-  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+  // dynamic tile scheduler: CTAs draw 128-sample tiles from a global counter (even finish times; the static split
+  // left 1/7 of the CTAs with an extra tile)
+  int64_t tile = blockIdx.x;
+  for (; tile < n_tiles; ++it) {
     const int64_t row0 = tile * kTile;
+    if (tid == 0) s_next_tile = atomicAdd(tile_counter, 1) + (int)gridDim.x;
     if (it > 0) mbar_wait(mbar, (uint32_t)((it - 1) & 1));     // the previous tile's MMAs have consumed the panels
     // (1) stage the input / hidden activations of this tile
     stage_panel<IN>(x, row0, n, P_x);
     for (int i = 0; i < NH; ++i) stage_panel<64>(acts + (int64_t)i * n_cap * 64, row0, n, P_act + (size_t)i * 64 * kTile);
+    // the warp's dL/dout (and out) fragments are fetched while the cp.async panels are still in flight
+    const int r = wid * 16;                       // first row of this warp inside the tile
+    const int64_t r0 = row0 + r + g, r1 = r0 + 8;
+    uint32_t dz[OUT / 16][4], ov[OUT / 16][4];
+#pragma unroll
+    for (int kb = 0; kb < OUT / 16; ++kb) {
+      const int col = kb * 16 + 2 * t;
+      dz[kb][0] = r0 < n ? *reinterpret_cast<const uint32_t*>(dout + r0 * OUT + col) : 0u;
+      dz[kb][1] = r1 < n ? *reinterpret_cast<const uint32_t*>(dout + r1 * OUT + col) : 0u;
+      dz[kb][2] = r0 < n ? *reinterpret_cast<const uint32_t*>(dout + r0 * OUT + col + 8) : 0u;
+      dz[kb][3] = r1 < n ? *reinterpret_cast<const uint32_t*>(dout + r1 * OUT + col + 8) : 0u;
+      if (out_act == NCN_ACT_SIGMOID || out_act == NCN_ACT_EXP) {
+        ov[kb][0] = r0 < n ? *reinterpret_cast<const uint32_t*>(out + r0 * OUT + col) : 0u;
+        ov[kb][1] = r1 < n ? *reinterpret_cast<const uint32_t*>(out + r1 * OUT + col) : 0u;
+        ov[kb][2] = r0 < n ? *reinterpret_cast<const uint32_t*>(out + r0 * OUT + col + 8) : 0u;
+        ov[kb][3] = r1 < n ? *reinterpret_cast<const uint32_t*>(out + r1 * OUT + col + 8) : 0u;
+      }
+    }
     cp_async_wait_all();
     __syncthreads();
+    const int next_tile = s_next_tile;       // read between this barrier and the next one; rewritten only after the latter
     // (2) dgrad chain in registers; every layer's dL/dz goes to its panel
     {
-      const int r = wid * 16;                       // first row of this warp inside the tile
-      const int64_t r0 = row0 + r + g, r1 = r0 + 8;
-      uint32_t dz[OUT / 16][4];
-#pragma unroll
-      for (int kb = 0; kb < OUT / 16; ++kb) {
-        const int col = kb * 16 + 2 * t;
-        dz[kb][0] = r0 < n ? *reinterpret_cast<const uint32_t*>(dout + r0 * OUT + col) : 0u;
-        dz[kb][1] = r1 < n ? *reinterpret_cast<const uint32_t*>(dout + r1 * OUT + col) : 0u;
-        dz[kb][2] = r0 < n ? *reinterpret_cast<const uint32_t*>(dout + r0 * OUT + col + 8) : 0u;
-        dz[kb][3] = r1 < n ? *reinterpret_cast<const uint32_t*>(dout + r1 * OUT + col + 8) : 0u;
-      }
       if (out_act == NCN_ACT_SIGMOID || out_act == NCN_ACT_EXP) {
 #pragma unroll
         for (int kb = 0; kb < OUT / 16; ++kb)
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            const int64_t rr = (q & 1) ? r1 : r0;
-            const int col = kb * 16 + 2 * t + ((q & 2) ? 8 : 0);
-            const uint32_t ou = rr < n ? *reinterpret_cast<const uint32_t*>(out + rr * OUT + col) : 0u;
+            const uint32_t ou = ov[kb][q];
             const float2 d = __half22float2(*reinterpret_cast<const __half2*>(&dz[kb][q]));
             const float2 y = __half22float2(*reinterpret_cast<const __half2*>(&ou));
             if (out_act == NCN_ACT_SIGMOID) dz[kb][q] = pack_half2(d.x * y.x * (1.f - y.x), d.y * y.y * (1.f - y.y));
@@ -287,6 +298,7 @@ mlp_bwd_tc05_kernel(const __half* __restrict__ x, const __half* __restrict__ w, 
       }
       tc_commit(mbar);
     }
+    tile = next_tile;
   }
   // (4) epilogue: TMEM -> registers -> global gradient (+=)
   if (it > 0) {
@@ -335,15 +347,17 @@ using namespace ncn;
 
 template <int IN, int OUT, int NH>
 static int launch_tc05(const void* x, const void* w, const void* out, const void* acts, const void* dout, int64_t n,
-                       const int32_t* n_dev, int out_act, float grad_scale, float* grad_w, void* dx, cudaStream_t st) {
+                       const int32_t* n_dev, int out_act, float grad_scale, float* grad_w, void* dx, int* tile_counter,
+                       cudaStream_t st) {
   using LY = TcLayout<IN, OUT, NH>;
+  NCN_CUDA(cudaMemsetAsync(tile_counter, 0, sizeof(int), st));
   auto k = mlp_bwd_tc05_kernel<IN, OUT, NH>;
   NCN_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LY::kBytes));
   const int64_t tiles = (n + kTile - 1) / kTile;
   int64_t grid = (int64_t)sm_count() * 2;
   if (grid > tiles) grid = tiles;
   k<<<(int)grid, kTcThreads, LY::kBytes, st>>>((const __half*)x, (const __half*)w, (const __half*)out, (const __half*)acts,
-                                               (const __half*)dout, n, n_dev, out_act, grad_scale, grad_w, (__half*)dx);
+                                               (const __half*)dout, n, n_dev, out_act, grad_scale, grad_w, (__half*)dx, tile_counter);
   NCN_LAUNCH_OK();
   return NCN_OK;
 }
@@ -351,10 +365,10 @@ static int launch_tc05(const void* x, const void* w, const void* out, const void
 // returns NCN_E_UNSUPPORTED when the configuration has no tcgen05 instantiation (the caller falls back to mlp.cu)
 int ncn_mlp_bwd_tc05_try(int in_pad, int out_pad, int n_hidden, const void* x, const void* w, const void* out, const void* acts,
                          const void* dout, int64_t n, const int32_t* n_dev, int out_act, float grad_scale, float* grad_w,
-                         void* dx, cudaStream_t st) {
+                         void* dx, int* tile_counter, cudaStream_t st) {
   if (!grad_w) return NCN_E_UNSUPPORTED;
 #define NCN_TC(I, O, H) if (in_pad == I && out_pad == O && n_hidden == H) \
-    return launch_tc05<I, O, H>(x, w, out, acts, dout, n, n_dev, out_act, grad_scale, grad_w, dx, st);
+    return launch_tc05<I, O, H>(x, w, out, acts, dout, n, n_dev, out_act, grad_scale, grad_w, dx, tile_counter, st);
   NCN_TC(32, 16, 1) NCN_TC(32, 16, 2) NCN_TC(16, 16, 2) NCN_TC(16, 16, 1) NCN_TC(16, 48, 2) NCN_TC(16, 32, 2)
 #undef NCN_TC
   return NCN_E_UNSUPPORTED;
