@@ -282,8 +282,9 @@ int ncn_mlp_bwd(const ncn_mlp_desc* d, const void* x_f16, const void* w_f16,
                 float* grad_w_f32, void* dL_dx_f16, float grad_scale, void* scratch,
                 size_t scratch_bytes, const int32_t* n_dev, ncn_stream_t stream);
 
-/* Selects the ncn_mlp_bwd implementation: 1 (default) = tcgen05 weight-gradient MMAs with TMEM-resident
- * accumulators fused into the dgrad kernel; 0 = warp-MMA dgrad + split-K wgrad kernels.  Returns the old value. */
+/* Selects the ncn_mlp_bwd implementation: 2 (default) = every GEMM (dgrad and wgrad) on tcgen05 with TMEM accumulators,
+ * 128-row tiles; 1 = warp-MMA dgrad in registers + tcgen05/TMEM wgrad; 0 = warp-MMA dgrad + split-K wgrad kernels.
+ * Returns the old value. */
 int ncn_set_mlp_bwd_impl(int impl);
 
 /* Elementwise glue of the NGPMT field (models/ngp_mt.py:157-229, rendering.py:203-212) between the

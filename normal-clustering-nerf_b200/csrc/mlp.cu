@@ -411,8 +411,8 @@ extern "C" int ncn_mlp_fwd(const ncn_mlp_desc* d, const void* x, const void* w, 
 // tcgen05 / TMEM implementation (mlp_tc05.cu)
 int ncn_mlp_bwd_tc05_try(int in_pad, int out_pad, int n_hidden, const void* x, const void* w, const void* out, const void* acts,
                          const void* dout, int64_t n, const int32_t* n_dev, int out_act, float grad_scale, float* grad_w,
-                         void* dx, int* tile_counter, cudaStream_t st);
-static int g_mlp_bwd_impl = 1;     // 1 = tcgen05/TMEM weight gradients (default), 0 = warp-MMA dgrad + split-K wgrad kernels
+                         void* dx, int* tile_counter, int impl, cudaStream_t st);
+static int g_mlp_bwd_impl = 2;     // 2 = every GEMM on tcgen05 (default), 1 = warp-MMA dgrad + tcgen05/TMEM wgrad, 0 = warp-MMA + split-K wgrad kernels
 extern "C" int ncn_set_mlp_bwd_impl(int impl) { const int old = g_mlp_bwd_impl; g_mlp_bwd_impl = impl; return old; }
 
 extern "C" int ncn_mlp_bwd(const ncn_mlp_desc* d, const void* x, const void* w, const void* out, const void* acts,
@@ -426,11 +426,11 @@ extern "C" int ncn_mlp_bwd(const ncn_mlp_desc* d, const void* x, const void* w, 
   if (scratch_bytes < ncn_mlp_bwd_workspace_bytes(d, n)) return NCN_E_SIZE;
   if (((uintptr_t)x | (uintptr_t)w | (uintptr_t)out | (uintptr_t)acts | (uintptr_t)dL_dout | (uintptr_t)scratch | (uintptr_t)dL_dx) & 15)
     return NCN_E_ALIGN;
-  if (g_mlp_bwd_impl == 1) {
+  if (g_mlp_bwd_impl >= 1) {
     // the last 256 bytes of the caller's scratch hold the tile counter of the persistent kernel
     int* tile_counter = (int*)((char*)scratch + ((ncn_mlp_bwd_workspace_bytes(d, n) - 256) & ~(size_t)15));
     rc = ncn_mlp_bwd_tc05_try(ip, op, d->n_hidden, x, w, out, acts, dL_dout, n, n_dev, d->out_activation, grad_scale, grad_w, dL_dx,
-                              tile_counter, as_stream(stream));
+                              tile_counter, g_mlp_bwd_impl, as_stream(stream));
     if (rc != NCN_E_UNSUPPORTED) return rc;
   }
   NCN_MLP_DISPATCH(ip, op, (launch_bwd<kI, kO>(d, x, w, out, acts, dL_dout, n, grad_w, dL_dx, grad_scale, scratch, n_dev, as_stream(stream))))

@@ -129,7 +129,7 @@ __device__ __forceinline__ void store_panel(__half* __restrict__ P, int r, const
 // global row-major (rows, W) fp16 -> panel, 16 B per cp.async; rows >= n are zero filled
 template <int W>
 __device__ __forceinline__ void stage_panel(const __half* __restrict__ src, int64_t row0, int64_t n, __half* __restrict__ P) {
-  for (int i = threadIdx.x; i < kTile * (W / 8); i += kTcThreads) {
+  for (int i = threadIdx.x; i < kTile * (W / 8); i += blockDim.x) {
     const int r = i / (W / 8), mb = i % (W / 8);
     __half* dst = P + ((size_t)mb * kTile + r) * 8;
     if (row0 + r < n) cp_async16(dst, src + (row0 + r) * W + mb * 8);
@@ -341,6 +341,255 @@ mlp_bwd_tc05_kernel(const __half* __restrict__ x, const __half* __restrict__ w, 
   if (wid == 0) tmem_dealloc<LY::kTmemCols>(tmem);
 }
 
+// =====================================================================================================================
+// v2: EVERY GEMM of the backward pass on tcgen05 (dgrad as well as wgrad), 128-row tiles, one thread per row.
+//
+//   dgrad layer:  D[128 x in] = dZ[128 x out] * W[out x in]       A = dZ panel read K-MAJOR  (M = sample), B = W panel MN-major
+//   wgrad layer:  dW[out x in] += dZ^T[out x 128] * A_prev[128 x in]   A = the SAME dZ panel read MN-MAJOR (M = feature)
+// The panel layout [feature/8][sample][8 halfs] is the canonical no-swizzle layout for both readings, so a dZ tile is
+// written once (by the epilogue of the layer above) and consumed by two different MMAs.  The per-tile chain is
+//   stage(x, acts; dL/dout * act') -> MMA -> [tcgen05.ld row, ReLU gate, fp16, st.shared row] -> MMA -> ... -> dx rows
+// with one thread issuing all MMAs and 128 threads doing ~25 instructions per 16 accumulator columns in the epilogues
+// (the warp-MMA v1 kernel spends ~60 instructions per row on fragment shuffling; this one ~10).
+constexpr int kV2Threads = 128;
+
+// K-major A operand over a panel [feature/8][kTile][8]: rows (M = samples) 16 B apart, next 8 rows SBO = 128 B,
+// next 8 K-elements (next feature group) LBO = kTile*16 B
+__device__ __forceinline__ uint64_t make_desc_k(const void* panel_at_k) {
+  const uint64_t addr = (uint64_t)(smem_u32(panel_at_k) >> 4) & 0x3FFF;
+  const uint64_t lbo = ((kTile * 16) >> 4), sbo = (128 >> 4);
+  return addr | (lbo << 16) | (sbo << 32) | (1ull << 46);
+}
+// MN-major B operand over a weight panel [n/8][K][8]: K rows 16 B apart, next 8 K rows LBO = 128 B, next 8 n: SBO = K*16 B
+__device__ __forceinline__ uint64_t make_desc_w(const void* panel_at_k, int K) {
+  const uint64_t addr = (uint64_t)(smem_u32(panel_at_k) >> 4) & 0x3FFF;
+  const uint64_t lbo = (128 >> 4), sbo = (uint64_t)((K * 16) >> 4);
+  return addr | (lbo << 16) | (sbo << 32) | (1ull << 46);
+}
+// D=f32, A=f16 K-major, B=f16 MN-major, M=128, N
+__host__ __device__ constexpr uint32_t make_idesc_dgrad(int N) {
+  return (1u << 4) | (1u << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+// weight matrix W (K=out rows, N=in cols, row-major) -> MN-major panel [n/8][K][8]
+__device__ __forceinline__ void load_w_panel(const __half* __restrict__ w, int K, int N, __half* __restrict__ P) {
+  for (int i = threadIdx.x; i < K * N; i += blockDim.x) {
+    const int k = i / N, n = i % N;
+    P[((size_t)(n >> 3) * K + k) * 8 + (n & 7)] = w[i];
+  }
+}
+
+template <int IN, int OUT, int NH>
+struct TcLayout2 {
+  static constexpr int kWBl = 64 * OUT, kWBh = (NH - 1) * 64 * 64, kWB0 = IN * 64;
+  static constexpr int kWeights = kWBl + kWBh + kWB0;
+  static constexpr int kPdzLast = OUT * kTile, kPdzH = NH * 64 * kTile, kPx = IN * kTile, kPact = NH * 64 * kTile;
+  static constexpr size_t kBytes = (size_t)(kWeights + kPdzLast + kPdzH + kPx + kPact) * 2 + 64;
+  static constexpr int kDcols = 64;                                   // dgrad accumulator tile (reused layer after layer)
+  static constexpr int kWgradCols = IN + 64 * (NH - 1) + OUT;
+  static constexpr int kTmemCols = tmem_cols_pow2(kDcols + kWgradCols);
+};
+
+template <int IN, int OUT, int NH>
+__global__ void __launch_bounds__(kV2Threads, 2)
+mlp_bwd_tc05_v2_kernel(const __half* __restrict__ x, const __half* __restrict__ w, const __half* __restrict__ out,
+                       const __half* __restrict__ acts, const __half* __restrict__ dout, int64_t n_cap,
+                       const int32_t* __restrict__ n_dev, int out_act, float grad_scale, float* __restrict__ grad_w,
+                       __half* __restrict__ dx, int* __restrict__ tile_counter) {
+  using LY = TcLayout2<IN, OUT, NH>;
+  int64_t n = n_cap;
+  if (n_dev != nullptr) { const int64_t nd = *n_dev; if (nd < n) n = nd; }
+  extern __shared__ __align__(128) unsigned char tc_smem[];
+  __half* WBl = reinterpret_cast<__half*>(tc_smem);          // last layer: K = OUT, N = 64
+  __half* WBh = WBl + LY::kWBl;                              // hidden layers: K = 64, N = 64
+  __half* WB0 = WBh + LY::kWBh;                              // first layer: K = 64, N = IN
+  __half* P_dz_last = WB0 + LY::kWB0;
+  __half* P_dz_h = P_dz_last + LY::kPdzLast;
+  __half* P_x = P_dz_h + LY::kPdzH;
+  __half* P_act = P_x + LY::kPx;
+  uint64_t* mbar_w = reinterpret_cast<uint64_t*>(P_act + LY::kPact);
+  uint64_t* mbar_d = mbar_w + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar_d + 1);
+  __shared__ int s_next_tile;
+
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  load_w_panel(w + 64 * IN + (NH - 1) * 64 * 64, OUT, 64, WBl);
+  for (int i = 0; i < NH - 1; ++i) load_w_panel(w + 64 * IN + i * 64 * 64, 64, 64, WBh + i * 64 * 64);
+  if (dx) load_w_panel(w, 64, IN, WB0);
+  if (tid == 0) { mbar_init(mbar_w, 1); mbar_init(mbar_d, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+  if (wid == 0) tmem_alloc<LY::kTmemCols>(tmem_slot);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t tmem_d = tmem;                              // dgrad tile: columns [0, 64)
+  const uint32_t tmem_w = tmem + LY::kDcols;                 // weight-gradient accumulators
+  const uint32_t my_lane = tmem_d + ((uint32_t)(32 * wid) << 16);   // this warp's TMEM sub-partition (row = tid)
+
+  const int64_t n_tiles = (n + kTile - 1) / kTile;
+  int it = 0;
+  uint32_t d_phase = 0;
+  int64_t tile = blockIdx.x;
+  for (; tile < n_tiles; ++it) {
+    const int64_t row0 = tile * kTile;
+    const int64_t row = row0 + tid;
+    if (tid == 0) s_next_tile = atomicAdd(tile_counter, 1) + (int)gridDim.x;
+    if (it > 0) mbar_wait(mbar_w, (uint32_t)((it - 1) & 1));        // the previous tile's wgrad MMAs released the panels
+    // (1) stage x / activations; this thread's dL/dout row (times the output activation derivative) -> dz_last panel
+    stage_panel<IN>(x, row0, n, P_x);
+    for (int i = 0; i < NH; ++i) stage_panel<64>(acts + (int64_t)i * n_cap * 64, row0, n, P_act + (size_t)i * 64 * kTile);
+#pragma unroll
+    for (int j = 0; j < OUT / 8; ++j) {
+      uint4 d = make_uint4(0u, 0u, 0u, 0u);
+      if (row < n) {
+        d = *reinterpret_cast<const uint4*>(dout + row * OUT + j * 8);
+        if (out_act == NCN_ACT_SIGMOID || out_act == NCN_ACT_EXP) {
+          const uint4 o = *reinterpret_cast<const uint4*>(out + row * OUT + j * 8);
+          uint32_t* dp = reinterpret_cast<uint32_t*>(&d);
+          const uint32_t* op = reinterpret_cast<const uint32_t*>(&o);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float2 dv = __half22float2(*reinterpret_cast<const __half2*>(&dp[q]));
+            const float2 y = __half22float2(*reinterpret_cast<const __half2*>(&op[q]));
+            dp[q] = out_act == NCN_ACT_SIGMOID ? pack_half2(dv.x * y.x * (1.f - y.x), dv.y * y.y * (1.f - y.y))
+                                               : pack_half2(dv.x * y.x, dv.y * y.y);
+          }
+        }
+      }
+      *reinterpret_cast<uint4*>(P_dz_last + ((size_t)j * kTile + tid) * 8) = d;
+    }
+    cp_async_wait_all();
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    const int next_tile = s_next_tile;
+    // (2) dgrad chain: MMA -> epilogue (gate, fp16, panel row) -> MMA ...
+    if (tid == 0) {
+      tc_fence_after();
+#pragma unroll
+      for (int ks = 0; ks < OUT / 16; ++ks)
+        tc_mma_f16(tmem_d, make_desc_k(P_dz_last + (size_t)ks * 2 * kTile * 8), make_desc_w(WBl + (size_t)ks * 16 * 8, OUT),
+                   make_idesc_dgrad(64), ks > 0 ? 1u : 0u);
+      tc_commit(mbar_d);
+    }
+#pragma unroll
+    for (int i = NH - 1; i >= 0; --i) {
+      mbar_wait(mbar_d, d_phase); d_phase ^= 1u;
+      tc_fence_after();
+      // dL/dh_i row: 64 fp32 accumulators in 4 chunks of 16 columns
+      const __half* Pa = P_act + (size_t)i * 64 * kTile;
+      __half* Pz = P_dz_h + (size_t)i * 64 * kTile;
+#pragma unroll
+      for (int c0 = 0; c0 < 64; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld16(my_lane + c0, v);
+        const uint4 a0 = *reinterpret_cast<const uint4*>(Pa + ((size_t)(c0 / 8) * kTile + tid) * 8);
+        const uint4 a1 = *reinterpret_cast<const uint4*>(Pa + ((size_t)(c0 / 8 + 1) * kTile + tid) * 8);
+        const uint32_t am[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+        uint32_t o[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&am[q]));
+          const float lo = a.x > 0.f ? __uint_as_float(v[2 * q]) : 0.f, hi = a.y > 0.f ? __uint_as_float(v[2 * q + 1]) : 0.f;
+          o[q] = pack_half2(lo, hi);
+        }
+        *reinterpret_cast<uint4*>(Pz + ((size_t)(c0 / 8) * kTile + tid) * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+        *reinterpret_cast<uint4*>(Pz + ((size_t)(c0 / 8 + 1) * kTile + tid) * 8) = make_uint4(o[4], o[5], o[6], o[7]);
+      }
+      fence_proxy_async();
+      tc_fence_before();
+      __syncthreads();
+      if (tid == 0) {
+        tc_fence_after();
+        if (i > 0) {
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks)
+            tc_mma_f16(tmem_d, make_desc_k(Pz + (size_t)ks * 2 * kTile * 8), make_desc_w(WBh + (size_t)(i - 1) * 64 * 64 + (size_t)ks * 16 * 8, 64),
+                       make_idesc_dgrad(64), ks > 0 ? 1u : 0u);
+          tc_commit(mbar_d);
+        } else {
+          if (dx) {
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks)
+              tc_mma_f16(tmem_d, make_desc_k(Pz + (size_t)ks * 2 * kTile * 8), make_desc_w(WB0 + (size_t)ks * 16 * 8, 64),
+                         make_idesc_dgrad(IN), ks > 0 ? 1u : 0u);
+            tc_commit(mbar_d);
+          }
+          // (3) all dZ panels are final: weight-gradient MMAs, accumulators stay in TMEM
+          const uint32_t acc0 = it > 0 ? 1u : 0u;
+#pragma unroll
+          for (int ks = 0; ks < kTile / 16; ++ks) {
+            const uint32_t acc = (ks > 0) ? 1u : acc0;
+            const size_t koff = (size_t)ks * 16 * 8;
+            tc_mma_f16(tmem_w + 0, make_desc_mn(P_dz_h + koff), make_desc_mn(P_x + koff), make_idesc(IN), acc);
+#pragma unroll
+            for (int q = 1; q < NH; ++q)
+              tc_mma_f16(tmem_w + IN + 64 * (q - 1), make_desc_mn(P_dz_h + (size_t)q * 64 * kTile + koff),
+                         make_desc_mn(P_act + (size_t)(q - 1) * 64 * kTile + koff), make_idesc(64), acc);
+            tc_mma_f16(tmem_w + IN + 64 * (NH - 1), make_desc_mn(P_act + (size_t)(NH - 1) * 64 * kTile + koff),
+                       make_desc_mn(P_dz_last + koff), make_idesc(OUT), acc);
+          }
+          tc_commit(mbar_w);
+        }
+      }
+    }
+    if (dx) {
+      mbar_wait(mbar_d, d_phase); d_phase ^= 1u;
+      tc_fence_after();
+#pragma unroll
+      for (int c0 = 0; c0 < IN; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld16(my_lane + c0, v);
+        if (row < n) {
+          uint32_t o[8];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) o[q] = pack_half2(__uint_as_float(v[2 * q]), __uint_as_float(v[2 * q + 1]));
+          *reinterpret_cast<uint4*>(dx + row * IN + c0) = make_uint4(o[0], o[1], o[2], o[3]);
+          *reinterpret_cast<uint4*>(dx + row * IN + c0 + 8) = make_uint4(o[4], o[5], o[6], o[7]);
+        }
+      }
+      tc_fence_before();     // the next tile's first MMA overwrites the dgrad tile this thread just read
+    }
+    tile = next_tile;
+  }
+  // (4) epilogue: weight gradients TMEM -> global (+=)
+  if (it > 0) {
+    mbar_wait(mbar_w, (uint32_t)((it - 1) & 1));
+    tc_fence_after();
+    const int m = 16 * wid + lane;        // M = 64 accumulators: rows 16*wid + lane, lanes 0..15 of each sub-partition
+    const uint32_t lane_base = tmem_w + ((uint32_t)(32 * wid) << 16);
+    uint32_t v[16];
+#pragma unroll
+    for (int c0 = 0; c0 < IN; c0 += 16) {
+      tmem_ld16(lane_base + c0, v);
+      if (lane < 16)
+#pragma unroll
+        for (int j = 0; j < 16; ++j) atomicAdd(grad_w + m * IN + c0 + j, __uint_as_float(v[j]) * grad_scale);
+    }
+#pragma unroll
+    for (int i = 1; i < NH; ++i)
+#pragma unroll
+      for (int c0 = 0; c0 < 64; c0 += 16) {
+        tmem_ld16(lane_base + IN + 64 * (i - 1) + c0, v);
+        if (lane < 16)
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            atomicAdd(grad_w + 64 * IN + (i - 1) * 64 * 64 + m * 64 + c0 + j, __uint_as_float(v[j]) * grad_scale);
+      }
+#pragma unroll
+    for (int c0 = 0; c0 < OUT; c0 += 16) {
+      tmem_ld16(lane_base + IN + 64 * (NH - 1) + c0, v);
+      if (lane < 16)
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          atomicAdd(grad_w + 64 * IN + (NH - 1) * 64 * 64 + (c0 + j) * 64 + m, __uint_as_float(v[j]) * grad_scale);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (wid == 0) tmem_dealloc<LY::kTmemCols>(tmem);
+}
+
 }  // namespace ncn
 
 using namespace ncn;
@@ -362,11 +611,34 @@ static int launch_tc05(const void* x, const void* w, const void* out, const void
   return NCN_OK;
 }
 
+template <int IN, int OUT, int NH>
+static int launch_tc05_v2(const void* x, const void* w, const void* out, const void* acts, const void* dout, int64_t n,
+                          const int32_t* n_dev, int out_act, float grad_scale, float* grad_w, void* dx, int* tile_counter,
+                          cudaStream_t st) {
+  using LY = TcLayout2<IN, OUT, NH>;
+  auto k = mlp_bwd_tc05_v2_kernel<IN, OUT, NH>;
+  NCN_CUDA(cudaMemsetAsync(tile_counter, 0, sizeof(int), st));
+  NCN_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LY::kBytes));
+  const int64_t tiles = (n + kTile - 1) / kTile;
+  int64_t grid = (int64_t)sm_count() * 2;
+  if (grid > tiles) grid = tiles;
+  k<<<(int)grid, kV2Threads, LY::kBytes, st>>>((const __half*)x, (const __half*)w, (const __half*)out, (const __half*)acts,
+                                               (const __half*)dout, n, n_dev, out_act, grad_scale, grad_w, (__half*)dx, tile_counter);
+  NCN_LAUNCH_OK();
+  return NCN_OK;
+}
+
 // returns NCN_E_UNSUPPORTED when the configuration has no tcgen05 instantiation (the caller falls back to mlp.cu)
 int ncn_mlp_bwd_tc05_try(int in_pad, int out_pad, int n_hidden, const void* x, const void* w, const void* out, const void* acts,
                          const void* dout, int64_t n, const int32_t* n_dev, int out_act, float grad_scale, float* grad_w,
-                         void* dx, int* tile_counter, cudaStream_t st) {
+                         void* dx, int* tile_counter, int impl, cudaStream_t st) {
   if (!grad_w) return NCN_E_UNSUPPORTED;
+  if (impl == 2) {
+#define NCN_TC2(I, O, H) if (in_pad == I && out_pad == O && n_hidden == H) \
+    return launch_tc05_v2<I, O, H>(x, w, out, acts, dout, n, n_dev, out_act, grad_scale, grad_w, dx, tile_counter, st);
+    NCN_TC2(32, 16, 1) NCN_TC2(32, 16, 2) NCN_TC2(16, 16, 2) NCN_TC2(16, 16, 1) NCN_TC2(16, 48, 2) NCN_TC2(16, 32, 2)
+#undef NCN_TC2
+  }
 #define NCN_TC(I, O, H) if (in_pad == I && out_pad == O && n_hidden == H) \
     return launch_tc05<I, O, H>(x, w, out, acts, dout, n, n_dev, out_act, grad_scale, grad_w, dx, tile_counter, st);
   NCN_TC(32, 16, 1) NCN_TC(32, 16, 2) NCN_TC(16, 16, 2) NCN_TC(16, 16, 1) NCN_TC(16, 48, 2) NCN_TC(16, 32, 2)
