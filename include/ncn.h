@@ -172,7 +172,9 @@ int ncn_composite_train_fw(const float* sigmas, const float* raws, const float* 
                            int64_t* total_samples, float* opacity, float* depth, float* rend,
                            float* ws, ncn_stream_t stream);
 /* out: dL_dsigmas (N), dL_draws (N,C) fully written for the samples the rays_a rows
- * cover.  dL_dopacity / dL_ddepth / dL_drend / dL_dws may each be NULL (= zeros). */
+ * cover.  dL_dopacity / dL_ddepth / dL_drend / dL_dws may each be NULL (= zeros).
+ * Either output pointer (not both) may be NULL to skip it: dL_draws depends on dL_drend only, so a caller
+ * can start the colour-head backward before the depth / opacity gradients exist. */
 int ncn_composite_train_bw(const float* dL_dopacity, const float* dL_ddepth,
                            const float* dL_drend, const float* dL_dws,
                            const float* sigmas, const float* raws, const float* ws,

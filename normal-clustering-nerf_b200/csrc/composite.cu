@@ -127,7 +127,7 @@ composite_train_bw_kernel(const float* __restrict__ dL_dopacity, const float* __
       const int cnt = min(32, N - base);
       const int64_t s = start + k;
       if (dead) {
-        if (k < N) { dL_dsigmas[s] = 0.f; for (int c = 0; c < C; ++c) dL_draws[s * C + c] = 0.f; }
+        if (k < N) { if (dL_dsigmas) dL_dsigmas[s] = 0.f; if (dL_draws) for (int c = 0; c < C; ++c) dL_draws[s * C + c] = 0.f; }
         continue;
       }
       float a = 0.f, t = 0.f, delta = 0.f, g = 0.f, gw = 0.f;
@@ -148,8 +148,8 @@ composite_train_bw_kernel(const float* __restrict__ dL_dopacity, const float* __
       const float q = active ? (w * lin + gw * w) : 0.f;
       const float incl = warp_scan_incl_f(q, lane) + carry;
       if (k < N) {
-        dL_dsigmas[s] = active ? delta * (gO_term + T_after * (lin + gw) - (Q_total - incl)) : 0.f;
-        for (int c = 0; c < C; ++c) dL_draws[s * C + c] = (active && gR) ? gR[c] * w : 0.f;
+        if (dL_dsigmas) dL_dsigmas[s] = active ? delta * (gO_term + T_after * (lin + gw) - (Q_total - incl)) : 0.f;
+        if (dL_draws) for (int c = 0; c < C; ++c) dL_draws[s * C + c] = (active && gR) ? gR[c] * w : 0.f;
       }
       carry = __shfl_sync(0xffffffffu, incl, 31);
       if (stop >= 0) dead = true;
@@ -220,8 +220,9 @@ extern "C" int ncn_composite_train_bw(const float* dL_dopacity, const float* dL_
   NCN_CHECK_SIZE(n_rays >= 0 && capacity >= 0 && n_channels >= 0 && n_channels <= 32 * kMaxChanWords);
   if (n_rays == 0 || capacity == 0) return NCN_OK;
   NCN_CHECK_PTR(sigmas); NCN_CHECK_PTR(deltas); NCN_CHECK_PTR(ts); NCN_CHECK_PTR(rays_a);
-  NCN_CHECK_PTR(opacity); NCN_CHECK_PTR(depth); NCN_CHECK_PTR(dL_dsigmas);
-  if (n_channels > 0) { NCN_CHECK_PTR(raws); NCN_CHECK_PTR(rend); NCN_CHECK_PTR(dL_draws); }
+  NCN_CHECK_PTR(opacity); NCN_CHECK_PTR(depth);
+  if (!dL_dsigmas && !dL_draws) return NCN_E_NULL;          // either output may be skipped (two-branch backward), not both
+  if (n_channels > 0) { NCN_CHECK_PTR(raws); NCN_CHECK_PTR(rend); }
   if (dL_dws) NCN_CHECK_PTR(ws);
   const int grid = persistent_grid(n_rays * 32, 256, 8);
   composite_train_bw_kernel<<<grid, 256, 0, as_stream(stream)>>>(dL_dopacity, dL_ddepth, dL_drend, dL_dws, sigmas, raws,

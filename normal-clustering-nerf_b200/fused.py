@@ -73,6 +73,9 @@ class FusedStep:
         nb = max(self.L.ncn_mlp_bwd_workspace_bytes(C.byref(m.rgb_net.desc), cap),
                  self.L.ncn_mlp_bwd_workspace_bytes(C.byref(m.sigma_net.desc), cap))
         self.mlp_ws = E(nb, dtype=torch.uint8, device=dev)
+        self.mlp_ws2 = E(nb, dtype=torch.uint8, device=dev)      # the colour-head backward runs concurrently on a side stream
+        self.side_stream = torch.cuda.Stream(device=dev)
+        self.ev_fork, self.ev_join = torch.cuda.Event(), torch.cuda.Event()
         # fp16 parameter copies (owned by the optimizer, refreshed by its Adam kernel each step)
         self.flat16 = self.opt.flat16
         # per-step schedule scalars (lr, bc1, bc2, w_ort, w_dot, w_l1): a ring of pinned host slots feeds one device
@@ -152,6 +155,24 @@ class FusedStep:
         # ---- losses (+ their gradients w.r.t. the rendered quantities)
         ck(L.ncn_photometric_loss(ptr(self.rend), ptr(self.opacity), ptr(self.target), R, 3, self.bg, float(hp["loss_opacity_w"]), GSCALE,
                                   ptr(self.rgb), ptr(self.zeros), ptr(self.d_rend), ptr(self.d_opacity), st), "photometric")
+        inv = 1.0 / GSCALE
+        # Two independent branches from here (forked onto a side stream; inside a CUDA graph they become parallel
+        # branches): (A) the colour head's backward needs only dL/draws = dL/drend * w, (B) the normal-clustering
+        # chain (normals -> k-means on an 8-CTA cluster -> selection -> cluster loss -> dL/ddepth) and then the
+        # density part of the compositing backward.  They join at dL/dh.
+        main = torch.cuda.current_stream()
+        side = self.side_stream
+        self.ev_fork.record(main)
+        side.wait_event(self.ev_fork)
+        with torch.cuda.stream(side):
+            sst = side.cuda_stream
+            ck(L.ncn_composite_train_bw(None, None, ptr(self.d_rend), None, ptr(self.sigmas), ptr(self.raws), ptr(self.ws),
+                                        ptr(self.deltas), ptr(self.ts), ptr(self.rays_a), ptr(self.opacity), ptr(self.depth), ptr(self.rend), 1e-4,
+                                        R, cap, 3, None, ptr(self.d_raws), sst), "composite_bw_raws")
+            ck(L.ncn_field_head_dout(ptr(self.d_raws), 3, 0, 3, 1.0, cap, n_dev, ptr(self.dout_rgb), 16, sst), "head_dout")
+            ck(L.ncn_mlp_bwd(C.byref(rgbn.desc), ptr(self.x_rgb), ptr(self._w16("rgb_net")), ptr(self.rgb_out), ptr(self.rgb_acts), ptr(self.dout_rgb),
+                             cap, ptr(self._g32("rgb_net")), ptr(self.dx_rgb), inv, ptr(self.mlp_ws2), self.mlp_ws2.numel(), n_dev, sst), "rgb_bwd")
+            self.ev_join.record(side)
         if self.M > 0:
             x1, x2, x3 = ptr(self.tri[0]), ptr(self.tri[1]), ptr(self.tri[2])
             # rays_o := rays_d (rendering.py:227 quirk)
@@ -164,14 +185,10 @@ class FusedStep:
             ck(L.ncn_cluster_loss_bw(ptr(self.normals), ptr(self.labels), self.M, ptr(self.stats), ptr(self.dev_sched[3:6]), ptr(self.dn), st), "cluster_bw")
             ck(L.ncn_normals_from_depth_bw(ptr(self.rays_d), ptr(self.rays_d), ptr(self.depth), x1, x2, x3, ptr(self.dn), self.M,
                                            ptr(self.d_depth), st), "normals_bw")
-        # ---- backward
         ck(L.ncn_composite_train_bw(ptr(self.d_opacity), ptr(self.d_depth), ptr(self.d_rend), None, ptr(self.sigmas), ptr(self.raws), ptr(self.ws),
                                     ptr(self.deltas), ptr(self.ts), ptr(self.rays_a), ptr(self.opacity), ptr(self.depth), ptr(self.rend), 1e-4,
-                                    R, cap, 3, ptr(self.d_sigmas), ptr(self.d_raws), st), "composite_bw")
-        ck(L.ncn_field_head_dout(ptr(self.d_raws), 3, 0, 3, 1.0, cap, n_dev, ptr(self.dout_rgb), 16, st), "head_dout")
-        inv = 1.0 / GSCALE
-        ck(L.ncn_mlp_bwd(C.byref(rgbn.desc), ptr(self.x_rgb), ptr(self._w16("rgb_net")), ptr(self.rgb_out), ptr(self.rgb_acts), ptr(self.dout_rgb),
-                         cap, ptr(self._g32("rgb_net")), ptr(self.dx_rgb), inv, ptr(self.mlp_ws), self.mlp_ws.numel(), n_dev, st), "rgb_bwd")
+                                    R, cap, 3, ptr(self.d_sigmas), None, st), "composite_bw_sigma")
+        main.wait_event(self.ev_join)
         ck(L.ncn_field_bwd_h(ptr(self.dx_rgb), ptr(self.d_sigmas), ptr(self.h), None, None, 1.0, cap, n_dev, ptr(self.dh), st), "bwd_h")
         ck(L.ncn_mlp_bwd(C.byref(sg.desc), ptr(self.feat), ptr(self._w16("sigma_net")), ptr(self.h), ptr(self.sig_acts), ptr(self.dh), cap,
                          ptr(self._g32("sigma_net")), ptr(self.dfeat), inv, ptr(self.mlp_ws), self.mlp_ws.numel(), n_dev, st), "sigma_bwd")
