@@ -284,6 +284,23 @@ int ncn_mlp_bwd(const ncn_mlp_desc* d, const void* x_f16, const void* w_f16,
                 float* grad_w_f32, void* dL_dx_f16, float grad_scale, void* scratch,
                 size_t scratch_bytes, const int32_t* n_dev, ncn_stream_t stream);
 
+/* ncn_mlp_bwd whose dL/dout rows are assembled on the fly (tcgen05 implementation, n_out_pad == 16):
+ *   mode 1 (colour head): dL/dout[:, j] = d_raws[:, c_off + j] * scale for j < n_ch, 0 otherwise   (= ncn_field_head_dout)
+ *   mode 2 (density trunk): dL/dh = dx_rgb[:, 3:19] + e0 * d_sigmas * exp(clamp(h[:,0],-15,15)) * scale   (= ncn_field_bwd_h) */
+typedef struct ncn_mlp_bwd_src {
+  int32_t mode;
+  const float* d_raws;    /* (N, c_total) f32 */
+  int32_t c_total, c_off, n_ch;
+  const void* dx_rgb;     /* (N, 32) f16 */
+  const float* d_sigmas;  /* (N) f32 */
+  const void* h;          /* (N, 16) f16 */
+  float scale;
+} ncn_mlp_bwd_src;
+int ncn_mlp_bwd_src_fused(const ncn_mlp_desc* d, const ncn_mlp_bwd_src* src, const void* x_f16, const void* w_f16,
+                          const void* out_f16, const void* acts_f16, int64_t n, float* grad_w_f32, void* dL_dx_f16,
+                          float grad_scale, void* scratch, size_t scratch_bytes, const int32_t* n_dev,
+                          ncn_stream_t stream);
+
 /* Selects the ncn_mlp_bwd implementation: 2 (default) = every GEMM (dgrad and wgrad) on tcgen05 with TMEM accumulators,
  * 128-row tiles; 1 = warp-MMA dgrad in registers + tcgen05/TMEM wgrad; 0 = warp-MMA dgrad + split-K wgrad kernels.
  * Returns the old value. */

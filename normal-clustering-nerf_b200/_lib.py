@@ -155,6 +155,11 @@ class MlpDesc(C.Structure):
                 ("activation", C.c_int32), ("out_activation", C.c_int32)]
 
 
+class MlpBwdSrc(C.Structure):
+    _fields_ = [("mode", C.c_int32), ("d_raws", C.c_void_p), ("c_total", C.c_int32), ("c_off", C.c_int32), ("n_ch", C.c_int32),
+                ("dx_rgb", C.c_void_p), ("d_sigmas", C.c_void_p), ("h", C.c_void_p), ("scale", C.c_float)]
+
+
 ACT = {"None": 0, "ReLU": 1, "Sigmoid": 2, "Exponential": 3}
 
 SIGNATURES.update({
@@ -186,6 +191,7 @@ SIGNATURES.update({
     "ncn_photometric_loss": (c_i32, [c_vp, c_vp, c_vp, c_i64, c_i32, C.POINTER(c_f32), c_f32, c_f32, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "ncn_adam_step": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_f32, c_f32, c_f32, c_f32, c_f32, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "ncn_set_mlp_bwd_impl": (c_i32, [c_i32]),
+    "ncn_mlp_bwd_src_fused": (c_i32, [C.POINTER(MlpDesc), C.POINTER(MlpBwdSrc), c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_f32, c_vp, c_sz, c_vp, c_vp]),
     "ncn_set_grid_bwd_merge": (c_i32, [c_i32]),
     "ncn_rays_from_pixels": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp]),
     "ncn_field_prepare_rgb": (c_i32, [c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp]),

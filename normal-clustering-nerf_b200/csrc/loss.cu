@@ -444,19 +444,29 @@ cluster_select_kernel(const float* __restrict__ centroids, const int32_t* __rest
                centroids[3 * i + 2] * centroids[3 * j + 2];
   }
   __syncthreads();
+  __shared__ float s_mn[kKmMaxK];
+  __shared__ int s_arg[kKmMaxK], s_c1;
   if (tid == 0) {
     int c1 = 0;
     for (int j = 1; j < K; ++j) if (s_size[j] > s_size[c1]) c1 = j;            // biggest cluster (losses.py:104-107)
-    // criteria[i][j] = |sim[i,c1]| + |sim[c1,j]| + |sim[i,j]|; mins over i, then argmin over j (losses.py:117-120)
-    int c2 = 0, c3 = 0; float best = INFINITY;
-    for (int j = 0; j < K; ++j) {
-      float mn = INFINITY; int arg = 0;
-      for (int i = 0; i < K; ++i) {
-        const float v = fabsf(s_sim[i * K + c1]) + fabsf(s_sim[c1 * K + j]) + fabsf(s_sim[i * K + j]);
-        if (v < mn) { mn = v; arg = i; }
-      }
-      if (mn < best) { best = mn; c2 = j; c3 = arg; }
+    s_c1 = c1;
+  }
+  __syncthreads();
+  if (tid < K) {
+    // criteria[i][j] = |sim[i,c1]| + |sim[c1,j]| + |sim[i,j]|; column j = tid: min / argmin over i (losses.py:117-118)
+    const int c1 = s_c1, j = tid;
+    float mn = INFINITY; int arg = 0;
+    for (int i = 0; i < K; ++i) {
+      const float v = fabsf(s_sim[i * K + c1]) + fabsf(s_sim[c1 * K + j]) + fabsf(s_sim[i * K + j]);
+      if (v < mn) { mn = v; arg = i; }
     }
+    s_mn[j] = mn; s_arg[j] = arg;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    const int c1 = s_c1;
+    int c2 = 0, c3 = 0; float best = INFINITY;
+    for (int j = 0; j < K; ++j) if (s_mn[j] < best) { best = s_mn[j]; c2 = j; c3 = s_arg[j]; }      // losses.py:119-120
     for (int j = 0; j < K; ++j) s_lab[j] = 0;
     const int cs[3] = {c1, c2, c3};
     for (int q = 0; q < 3; ++q)                                                // merge similar (losses.py:47-54)

@@ -411,7 +411,7 @@ extern "C" int ncn_mlp_fwd(const ncn_mlp_desc* d, const void* x, const void* w, 
 // tcgen05 / TMEM implementation (mlp_tc05.cu)
 int ncn_mlp_bwd_tc05_try(int in_pad, int out_pad, int n_hidden, const void* x, const void* w, const void* out, const void* acts,
                          const void* dout, int64_t n, const int32_t* n_dev, int out_act, float grad_scale, float* grad_w,
-                         void* dx, int* tile_counter, int impl, cudaStream_t st);
+                         void* dx, int* tile_counter, int impl, const ncn_mlp_bwd_src* src, cudaStream_t st);
 static int g_mlp_bwd_impl = 2;     // 2 = every GEMM on tcgen05 (default), 1 = warp-MMA dgrad + tcgen05/TMEM wgrad, 0 = warp-MMA + split-K wgrad kernels
 extern "C" int ncn_set_mlp_bwd_impl(int impl) { const int old = g_mlp_bwd_impl; g_mlp_bwd_impl = impl; return old; }
 
@@ -430,8 +430,29 @@ extern "C" int ncn_mlp_bwd(const ncn_mlp_desc* d, const void* x, const void* w, 
     // the last 256 bytes of the caller's scratch hold the tile counter of the persistent kernel
     int* tile_counter = (int*)((char*)scratch + ((ncn_mlp_bwd_workspace_bytes(d, n) - 256) & ~(size_t)15));
     rc = ncn_mlp_bwd_tc05_try(ip, op, d->n_hidden, x, w, out, acts, dL_dout, n, n_dev, d->out_activation, grad_scale, grad_w, dL_dx,
-                              tile_counter, g_mlp_bwd_impl, as_stream(stream));
+                              tile_counter, g_mlp_bwd_impl, nullptr, as_stream(stream));
     if (rc != NCN_E_UNSUPPORTED) return rc;
   }
   NCN_MLP_DISPATCH(ip, op, (launch_bwd<kI, kO>(d, x, w, out, acts, dL_dout, n, grad_w, dL_dx, grad_scale, scratch, n_dev, as_stream(stream))))
+}
+
+// ncn_mlp_bwd with the gradient w.r.t. the network output assembled on the fly from the compositing backward's outputs
+// (removes the ncn_field_head_dout / ncn_field_bwd_h passes).  tcgen05 implementation only.
+extern "C" int ncn_mlp_bwd_src_fused(const ncn_mlp_desc* d, const ncn_mlp_bwd_src* src, const void* x, const void* w, const void* out,
+                                     const void* acts, int64_t n, float* grad_w, void* dL_dx, float grad_scale, void* scratch,
+                                     size_t scratch_bytes, const int32_t* n_dev, ncn_stream_t stream) {
+  int ip, op;
+  int rc = check_desc(d, &ip, &op); if (rc) return rc;
+  NCN_CHECK_SIZE(n >= 0);
+  NCN_CHECK_PTR(src);
+  if (n == 0) return NCN_OK;
+  NCN_CHECK_PTR(x); NCN_CHECK_PTR(w); NCN_CHECK_PTR(acts); NCN_CHECK_PTR(scratch); NCN_CHECK_PTR(grad_w);
+  if (src->mode == 1) { NCN_CHECK_PTR(src->d_raws); NCN_CHECK_PTR(out); }
+  else if (src->mode == 2) { NCN_CHECK_PTR(src->dx_rgb); NCN_CHECK_PTR(src->d_sigmas); NCN_CHECK_PTR(src->h); }
+  else return NCN_E_CONFIG;
+  if (scratch_bytes < ncn_mlp_bwd_workspace_bytes(d, n)) return NCN_E_SIZE;
+  if (g_mlp_bwd_impl != 2) return NCN_E_UNSUPPORTED;
+  int* tile_counter = (int*)((char*)scratch + ((ncn_mlp_bwd_workspace_bytes(d, n) - 256) & ~(size_t)15));
+  return ncn_mlp_bwd_tc05_try(ip, op, d->n_hidden, x, w, out, acts, nullptr, n, n_dev, d->out_activation, grad_scale, grad_w, dL_dx,
+                              tile_counter, 2, src, as_stream(stream));
 }

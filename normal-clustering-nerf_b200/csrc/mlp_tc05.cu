@@ -394,7 +394,7 @@ __global__ void __launch_bounds__(kV2Threads, 2)
 mlp_bwd_tc05_v2_kernel(const __half* __restrict__ x, const __half* __restrict__ w, const __half* __restrict__ out,
                        const __half* __restrict__ acts, const __half* __restrict__ dout, int64_t n_cap,
                        const int32_t* __restrict__ n_dev, int out_act, float grad_scale, float* __restrict__ grad_w,
-                       __half* __restrict__ dx, int* __restrict__ tile_counter) {
+                       __half* __restrict__ dx, int* __restrict__ tile_counter, ncn_mlp_bwd_src src) {
   using LY = TcLayout2<IN, OUT, NH>;
   int64_t n = n_cap;
   if (n_dev != nullptr) { const int64_t nd = *n_dev; if (nd < n) n = nd; }
@@ -438,24 +438,55 @@ mlp_bwd_tc05_v2_kernel(const __half* __restrict__ x, const __half* __restrict__ 
     // (1) stage x / activations; this thread's dL/dout row (times the output activation derivative) -> dz_last panel
     stage_panel<IN>(x, row0, n, P_x);
     for (int i = 0; i < NH; ++i) stage_panel<64>(acts + (int64_t)i * n_cap * 64, row0, n, P_act + (size_t)i * 64 * kTile);
+    // dL/dout row of this thread, from one of three sources (src.mode):
+    //   0: the (N,OUT) fp16 matrix `dout`
+    //   1: colour head - columns [c_off, c_off+n_ch) of the fp32 dL/draws matrix (ncn_field_head_dout fused in)
+    //   2: density trunk - dL/dh = dL/dx_rgb[:, 3:19] + e0 * dL/dsigma * exp(clamp(h0,-15,15))  (ncn_field_bwd_h fused in)
+    uint32_t drow[OUT / 2];
 #pragma unroll
-    for (int j = 0; j < OUT / 8; ++j) {
-      uint4 d = make_uint4(0u, 0u, 0u, 0u);
-      if (row < n) {
-        d = *reinterpret_cast<const uint4*>(dout + row * OUT + j * 8);
-        if (out_act == NCN_ACT_SIGMOID || out_act == NCN_ACT_EXP) {
+    for (int q = 0; q < OUT / 2; ++q) drow[q] = 0u;
+    if (row < n) {
+      if (src.mode == 0) {
+#pragma unroll
+        for (int j = 0; j < OUT / 8; ++j) {
+          const uint4 d = *reinterpret_cast<const uint4*>(dout + row * OUT + j * 8);
+          drow[4 * j] = d.x; drow[4 * j + 1] = d.y; drow[4 * j + 2] = d.z; drow[4 * j + 3] = d.w;
+        }
+      } else if (src.mode == 1) {
+        const float* rr = src.d_raws + row * src.c_total + src.c_off;
+#pragma unroll
+        for (int q = 0; q < OUT / 2; ++q) {
+          const float a = 2 * q < src.n_ch ? rr[2 * q] * src.scale : 0.f, b = 2 * q + 1 < src.n_ch ? rr[2 * q + 1] * src.scale : 0.f;
+          drow[q] = pack_half2(a, b);
+        }
+      } else {
+        const uint4* xr = reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(src.dx_rgb) + row * 32);
+        const uint4 w0 = xr[0], w1 = xr[1], w2 = xr[2];
+        const uint32_t wv[12] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w, w2.x, w2.y, w2.z, w2.w};
+#pragma unroll
+        for (int q = 0; q < 8; ++q) drow[q] = __funnelshift_r(wv[q + 1], wv[q + 2], 16);     // halfs 3+2q, 4+2q
+        const float h0 = __half2float(reinterpret_cast<const __half*>(src.h)[row * 16]);
+        const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&drow[0]));
+        drow[0] = pack_half2(f.x + src.d_sigmas[row] * __expf(fminf(fmaxf(h0, -15.f), 15.f)) * src.scale, f.y);
+      }
+      if (out_act == NCN_ACT_SIGMOID || out_act == NCN_ACT_EXP) {
+#pragma unroll
+        for (int j = 0; j < OUT / 8; ++j) {
           const uint4 o = *reinterpret_cast<const uint4*>(out + row * OUT + j * 8);
-          uint32_t* dp = reinterpret_cast<uint32_t*>(&d);
-          const uint32_t* op = reinterpret_cast<const uint32_t*>(&o);
+          const uint32_t op[4] = {o.x, o.y, o.z, o.w};
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            const float2 dv = __half22float2(*reinterpret_cast<const __half2*>(&dp[q]));
+            const float2 dv = __half22float2(*reinterpret_cast<const __half2*>(&drow[4 * j + q]));
             const float2 y = __half22float2(*reinterpret_cast<const __half2*>(&op[q]));
-            dp[q] = out_act == NCN_ACT_SIGMOID ? pack_half2(dv.x * y.x * (1.f - y.x), dv.y * y.y * (1.f - y.y))
-                                               : pack_half2(dv.x * y.x, dv.y * y.y);
+            drow[4 * j + q] = out_act == NCN_ACT_SIGMOID ? pack_half2(dv.x * y.x * (1.f - y.x), dv.y * y.y * (1.f - y.y))
+                                                         : pack_half2(dv.x * y.x, dv.y * y.y);
           }
         }
       }
+    }
+#pragma unroll
+    for (int j = 0; j < OUT / 8; ++j) {
+      const uint4 d = make_uint4(drow[4 * j], drow[4 * j + 1], drow[4 * j + 2], drow[4 * j + 3]);
       *reinterpret_cast<uint4*>(P_dz_last + ((size_t)j * kTile + tid) * 8) = d;
     }
     cp_async_wait_all();
@@ -614,7 +645,7 @@ static int launch_tc05(const void* x, const void* w, const void* out, const void
 template <int IN, int OUT, int NH>
 static int launch_tc05_v2(const void* x, const void* w, const void* out, const void* acts, const void* dout, int64_t n,
                           const int32_t* n_dev, int out_act, float grad_scale, float* grad_w, void* dx, int* tile_counter,
-                          cudaStream_t st) {
+                          const ncn_mlp_bwd_src& src, cudaStream_t st) {
   using LY = TcLayout2<IN, OUT, NH>;
   auto k = mlp_bwd_tc05_v2_kernel<IN, OUT, NH>;
   NCN_CUDA(cudaMemsetAsync(tile_counter, 0, sizeof(int), st));
@@ -623,7 +654,7 @@ static int launch_tc05_v2(const void* x, const void* w, const void* out, const v
   int64_t grid = (int64_t)sm_count() * 2;
   if (grid > tiles) grid = tiles;
   k<<<(int)grid, kV2Threads, LY::kBytes, st>>>((const __half*)x, (const __half*)w, (const __half*)out, (const __half*)acts,
-                                               (const __half*)dout, n, n_dev, out_act, grad_scale, grad_w, (__half*)dx, tile_counter);
+                                               (const __half*)dout, n, n_dev, out_act, grad_scale, grad_w, (__half*)dx, tile_counter, src);
   NCN_LAUNCH_OK();
   return NCN_OK;
 }
@@ -631,11 +662,14 @@ static int launch_tc05_v2(const void* x, const void* w, const void* out, const v
 // returns NCN_E_UNSUPPORTED when the configuration has no tcgen05 instantiation (the caller falls back to mlp.cu)
 int ncn_mlp_bwd_tc05_try(int in_pad, int out_pad, int n_hidden, const void* x, const void* w, const void* out, const void* acts,
                          const void* dout, int64_t n, const int32_t* n_dev, int out_act, float grad_scale, float* grad_w,
-                         void* dx, int* tile_counter, int impl, cudaStream_t st) {
+                         void* dx, int* tile_counter, int impl, const ncn_mlp_bwd_src* src_in, cudaStream_t st) {
   if (!grad_w) return NCN_E_UNSUPPORTED;
+  ncn_mlp_bwd_src src;
+  if (src_in) src = *src_in; else { src = ncn_mlp_bwd_src(); src.mode = 0; }
+  if (src.mode != 0 && (impl != 2 || out_pad != 16)) return NCN_E_UNSUPPORTED;
   if (impl == 2) {
 #define NCN_TC2(I, O, H) if (in_pad == I && out_pad == O && n_hidden == H) \
-    return launch_tc05_v2<I, O, H>(x, w, out, acts, dout, n, n_dev, out_act, grad_scale, grad_w, dx, tile_counter, st);
+    return launch_tc05_v2<I, O, H>(x, w, out, acts, dout, n, n_dev, out_act, grad_scale, grad_w, dx, tile_counter, src, st);
     NCN_TC2(32, 16, 1) NCN_TC2(32, 16, 2) NCN_TC2(16, 16, 2) NCN_TC2(16, 16, 1) NCN_TC2(16, 48, 2) NCN_TC2(16, 32, 2)
 #undef NCN_TC2
   }

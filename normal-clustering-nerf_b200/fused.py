@@ -74,6 +74,8 @@ class FusedStep:
                  self.L.ncn_mlp_bwd_workspace_bytes(C.byref(m.sigma_net.desc), cap))
         self.mlp_ws = E(nb, dtype=torch.uint8, device=dev)
         self.mlp_ws2 = E(nb, dtype=torch.uint8, device=dev)      # the colour-head backward runs concurrently on a side stream
+        self.src_rgb = _lib.MlpBwdSrc(1, ptr(self.d_raws), 3, 0, 3, None, None, None, 1.0)
+        self.src_sig = _lib.MlpBwdSrc(2, None, 0, 0, 0, ptr(self.dx_rgb), ptr(self.d_sigmas), ptr(self.h), 1.0)
         self.side_stream = torch.cuda.Stream(device=dev)
         self.ev_fork, self.ev_join = torch.cuda.Event(), torch.cuda.Event()
         # fp16 parameter copies (owned by the optimizer, refreshed by its Adam kernel each step)
@@ -169,9 +171,9 @@ class FusedStep:
             ck(L.ncn_composite_train_bw(None, None, ptr(self.d_rend), None, ptr(self.sigmas), ptr(self.raws), ptr(self.ws),
                                         ptr(self.deltas), ptr(self.ts), ptr(self.rays_a), ptr(self.opacity), ptr(self.depth), ptr(self.rend), 1e-4,
                                         R, cap, 3, None, ptr(self.d_raws), sst), "composite_bw_raws")
-            ck(L.ncn_field_head_dout(ptr(self.d_raws), 3, 0, 3, 1.0, cap, n_dev, ptr(self.dout_rgb), 16, sst), "head_dout")
-            ck(L.ncn_mlp_bwd(C.byref(rgbn.desc), ptr(self.x_rgb), ptr(self._w16("rgb_net")), ptr(self.rgb_out), ptr(self.rgb_acts), ptr(self.dout_rgb),
-                             cap, ptr(self._g32("rgb_net")), ptr(self.dx_rgb), inv, ptr(self.mlp_ws2), self.mlp_ws2.numel(), n_dev, sst), "rgb_bwd")
+            ck(L.ncn_mlp_bwd_src_fused(C.byref(rgbn.desc), C.byref(self.src_rgb), ptr(self.x_rgb), ptr(self._w16("rgb_net")), ptr(self.rgb_out),
+                                       ptr(self.rgb_acts), cap, ptr(self._g32("rgb_net")), ptr(self.dx_rgb), inv, ptr(self.mlp_ws2),
+                                       self.mlp_ws2.numel(), n_dev, sst), "rgb_bwd")
             self.ev_join.record(side)
         if self.M > 0:
             x1, x2, x3 = ptr(self.tri[0]), ptr(self.tri[1]), ptr(self.tri[2])
@@ -189,9 +191,9 @@ class FusedStep:
                                     ptr(self.deltas), ptr(self.ts), ptr(self.rays_a), ptr(self.opacity), ptr(self.depth), ptr(self.rend), 1e-4,
                                     R, cap, 3, ptr(self.d_sigmas), None, st), "composite_bw_sigma")
         main.wait_event(self.ev_join)
-        ck(L.ncn_field_bwd_h(ptr(self.dx_rgb), ptr(self.d_sigmas), ptr(self.h), None, None, 1.0, cap, n_dev, ptr(self.dh), st), "bwd_h")
-        ck(L.ncn_mlp_bwd(C.byref(sg.desc), ptr(self.feat), ptr(self._w16("sigma_net")), ptr(self.h), ptr(self.sig_acts), ptr(self.dh), cap,
-                         ptr(self._g32("sigma_net")), ptr(self.dfeat), inv, ptr(self.mlp_ws), self.mlp_ws.numel(), n_dev, st), "sigma_bwd")
+        ck(L.ncn_mlp_bwd_src_fused(C.byref(sg.desc), C.byref(self.src_sig), ptr(self.feat), ptr(self._w16("sigma_net")), ptr(self.h),
+                                   ptr(self.sig_acts), cap, ptr(self._g32("sigma_net")), ptr(self.dfeat), inv, ptr(self.mlp_ws),
+                                   self.mlp_ws.numel(), n_dev, st), "sigma_bwd")
         ck(L.ncn_grid_bwd(C.byref(enc.desc), ptr(self.xyzs), ptr(self.dfeat), cap, ptr(self._g32("xyz_encoder")), inv, self.xform, n_dev, st), "grid_bwd")
 
     def _optimizer(self):
