@@ -84,10 +84,16 @@ class FusedStep:
         # slot with an async H2D per step; the ring + an event throttle keep the host from overwriting a slot
         # whose copy has not executed yet
         self.RING = 64
-        self.host_sched = torch.zeros(self.RING, 6, dtype=torch.float32).pin_memory()
+        self.host_sched = torch.zeros(self.RING, 12, dtype=torch.float32).pin_memory()   # [this step 6 | previous step 6]
         self.ring_events = [None] * self.RING
         self.ring_pos = 0
-        self.dev_sched = torch.zeros(6, **f32)
+        self.dev_sched = torch.zeros(12, **f32)
+        self.prev_sched = [0.0] * 6
+        self.flag_init = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.pending = False                 # deferred mode: a gradient is waiting for its optimizer pass
+        self.defer = use_graph               # deferred optimizer only in graph mode
+        self.opt_stream = torch.cuda.Stream(device=dev)
+        self.ev_fork2, self.ev_join2 = torch.cuda.Event(), torch.cuda.Event()
         self.coef = torch.ones(1, **f32)
         self.flag = torch.zeros(1, dtype=torch.int32, device=dev)
         self.grad_div = torch.tensor([float(trainer.world_size)], **f32)
@@ -131,12 +137,16 @@ class FusedStep:
         return self.opt.grad[o:o + n]
 
     def _run(self):
+        self._run_march()
+        self._run_field()
+
+    def _run_march(self):
+        """the part of the step that does not depend on the parameters: jitter, AABB, occupancy march"""
         L, m, hp = self.L, self.model, self.hp
         st = torch.cuda.current_stream().cuda_stream
         R, cap = self.R, self.cap
-        n_dev = ptr(self.counter)
         ck = check
-        self.zeros.zero_()
+        self.zeros[0:2].zero_()
         self.d_depth.zero_()
         if self.gen_noise:
             self.noise.uniform_()
@@ -146,6 +156,14 @@ class FusedStep:
                              float(m.scale), float(hp["exp_step_factor"]), ptr(self.noise), m.grid_size, hp["rend_max_samples"], R,
                              cap, ptr(self.rays_a), ptr(self.xyzs), ptr(self.dirs), ptr(self.deltas), ptr(self.ts), ptr(self.counter),
                              ptr(self.march_ws), self.march_ws.numel(), st), "march")
+
+    def _run_field(self):
+        """field forward, compositing, losses and the whole backward pass (needs the current parameters)"""
+        L, m, hp = self.L, self.model, self.hp
+        st = torch.cuda.current_stream().cuda_stream
+        R, cap = self.R, self.cap
+        n_dev = ptr(self.counter)
+        ck = check
         enc, sg, rgbn = m.xyz_encoder, m.sigma_net, m.rgb_net
         ck(L.ncn_grid_fwd(C.byref(enc.desc), ptr(self.xyzs), ptr(self._w16("xyz_encoder")), cap, ptr(self.feat), self.xform, n_dev, st), "grid_fwd")
         ck(L.ncn_mlp_fwd(C.byref(sg.desc), ptr(self.feat), ptr(self._w16("sigma_net")), cap, ptr(self.h), ptr(self.sig_acts), n_dev, st), "sigma_fwd")
@@ -196,18 +214,39 @@ class FusedStep:
                                    self.mlp_ws.numel(), n_dev, st), "sigma_bwd")
         ck(L.ncn_grid_bwd(C.byref(enc.desc), ptr(self.xyzs), ptr(self.dfeat), cap, ptr(self._g32("xyz_encoder")), inv, self.xform, n_dev, st), "grid_bwd")
 
-    def _optimizer(self):
+    def _optimizer(self, sched_off=0):
+        """sum of squares -> clip coefficient -> fused Adam (both parameter groups); sched_off selects the schedule slot
+        (0 = this step's lr / bias corrections, 6 = the previous step's, for the deferred update)"""
         L, opt = self.L, self.opt
         st = torch.cuda.current_stream().cuda_stream
         sumsq = self.zeros[2:3]
-        self.flag.zero_()
+        sumsq.zero_()
+        self.flag.copy_(self.flag_init)          # 0, or 1 to skip the (empty) update of the very first deferred step
         check(L.ncn_grad_sumsq(ptr(opt.grad), opt.grad.numel(), ptr(self.grad_div), ptr(sumsq), ptr(self.flag), st), "sumsq")
         check(L.ncn_clip_coef(ptr(sumsq), float(self.hp["grad_clip"]), ptr(self.coef), st), "clip")
         for (start, n, wd) in opt.groups:
             sl = slice(start, start + n)
             check(L.ncn_adam_step(ptr(opt.flat[sl]), ptr(opt.grad[sl]), ptr(opt.m[sl]), ptr(opt.v[sl]), ptr(self.flat16[sl]), n, 0.0,
                                   opt.betas[0], opt.betas[1], opt.eps, wd, 1, ptr(self.grad_div), ptr(self.flag), ptr(self.coef),
-                                  ptr(self.dev_sched), st), "adam")
+                                  ptr(self.dev_sched[sched_off:sched_off + 3]), st), "adam")
+
+    def _run_deferred(self, multi):
+        """One replay = [apply the PREVIOUS step's update] || [jitter + AABB + march of THIS step] -> field/backward.
+        The optimizer pass (dense, HBM bound) and the march (serial, latency bound) do not depend on each other, so they
+        run as parallel graph branches; the sequence of updates is unchanged (Adam_k still precedes forward_k+1),
+        `flush()` applies the last pending update."""
+        main = torch.cuda.current_stream()
+        opt_stream = self.opt_stream
+        self.ev_fork2.record(main)
+        opt_stream.wait_event(self.ev_fork2)
+        with torch.cuda.stream(opt_stream):
+            if multi:
+                self.tr.comm.allreduce_sum_(self.opt.grad)
+            self._optimizer(sched_off=6)
+            self.ev_join2.record(opt_stream)
+        self._run_march()
+        main.wait_event(self.ev_join2)
+        self._run_field()
 
     # ------------------------------------------------------------------ public
     def set_triangles(self, tri):
@@ -234,6 +273,9 @@ class FusedStep:
         h[3] = ls.w_sched(ls.w_ort, step) * GSCALE if on else 0.0
         h[4] = ls.w_sched(ls.w_dot, step) * GSCALE if on else 0.0
         h[5] = ls.w_sched(ls.w_l1, step) * GSCALE if on else 0.0
+        for i in range(6):
+            h[6 + i] = self.prev_sched[i]
+        self.prev_sched = [float(h[i]) for i in range(6)]
         self.dev_sched.copy_(h, non_blocking=True)
         ev = torch.cuda.Event()
         ev.record()
@@ -260,6 +302,15 @@ class FusedStep:
             if multi:
                 tr.comm.allreduce_sum_(self.opt.grad)
             self._optimizer()
+        elif self.defer:
+            if self.graph is None:
+                self._capture(multi)
+            if not self.pending:
+                self.flag_init.fill_(1)          # nothing to apply yet: the optimizer branch of this replay is a no-op
+            self.graph[0].replay()
+            if not self.pending:
+                self.flag_init.zero_()
+                self.pending = True
         else:
             if self.graph is None:
                 self._capture(multi)
@@ -268,6 +319,14 @@ class FusedStep:
                 tr.comm.allreduce_sum_(self.opt.grad)
                 self.graph[1].replay()
         tr.global_step += 1
+
+    def flush(self):
+        """deferred mode: apply the pending optimizer pass of the last step (call before reading parameters / evaluating)"""
+        if self.defer and self.pending:
+            if self.tr.world_size > 1:
+                self.tr.comm.allreduce_sum_(self.opt.grad)
+            self._optimizer(sched_off=0)          # slot 0 still holds the last step's schedule
+            self.pending = False
 
     def rays_from_pixels(self, img_idx, pix_idx):
         """fill the static rays_o / rays_d buffers from (image, pixel) indices (one kernel)"""
@@ -313,6 +372,12 @@ class FusedStep:
         # undo the warm-up update
         self.opt.flat.copy_(keep[0]); self.opt.m.copy_(keep[1]); self.opt.v.copy_(keep[2]); self.flat16.copy_(keep[3])
         self.opt.grad.zero_()
+        if self.defer:
+            g0 = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g0):
+                self._run_deferred(multi)
+            self.graph = (g0, None)
+            return
         g0 = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g0):
             self._run()
@@ -327,6 +392,7 @@ class FusedStep:
 
     def stats_host(self):
         """(loss dict, n_samples) - synchronises; call outside the timed region"""
+        self.flush()
         torch.cuda.synchronize()
         R = self.R
         z = self.zeros.cpu()

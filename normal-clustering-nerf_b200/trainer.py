@@ -201,6 +201,7 @@ class NeRFTrainer:
         if tri is not None and (fs.tri is None or fs.tri.data_ptr() != tri.data_ptr()):
             fs.set_triangles(tri)
         if update_grid and self.global_step % self.hp["update_interval"] == 0:
+            fs.flush()                            # the grid update evaluates the field: it must see the latest parameters
             if self.global_step < self.hp["warmup_steps"]:
                 self.maybe_update_grid()
             else:

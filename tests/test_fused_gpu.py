@@ -79,6 +79,7 @@ def test_fused_graph_replay_trains():
     for i in range(3):
         fs.step(rays_o, rays_d, rgb, noise=noise)
         fs2.step(rays_o, rays_d, rgb, noise=noise)
+    fs.flush()
     torch.cuda.synchronize()
     rel = float((tr.opt.flat - tr2.opt.flat).norm() / tr2.opt.flat.norm())
     assert rel < 1e-3, rel
