@@ -129,6 +129,9 @@ ALGO = {  # algorithmic bytes (or flops) per unit, SURVEY.md section 8d / DESIGN
     "ncn_adam_step": ("hbm", "param", 32.0), "ncn_grad_sumsq": ("hbm", "param", 4.0),
     "ncn_composite_train_fw": ("hbm", "sample", 28.0), "ncn_composite_train_bw": ("hbm", "sample", 48.0),
     "ncn_march_train_expand": ("hbm", "sample", 36.0),
+    # tcgen05 MLP backward, two launches per step (colour head 448 B/sample, density trunk 288 B/sample): average per launch
+    "ncn_mlp_bwd_src_fused": ("hbm", "sample", 368.0), "ncn_mlp_bwd": ("hbm", "sample", 368.0),
+    "ncn_mlp_fwd": ("hbm", "sample", 288.0),
 }
 
 
@@ -258,6 +261,15 @@ def run_ours(args):
         with open(args.breakdown, "w") as f:
             json.dump({k: {"calls_per_step": c / nprof, "us_per_step": 1e3 * t / nprof} for k, (c, t) in sorted(summ.items(), key=lambda kv: -kv[1][1])}, f, indent=1)
 
+    ranks_in_sync = None
+    if world > 1:      # replicated parameters must be bit-identical on every rank after the run (same all-reduced gradient, same Adam)
+        fs.flush()
+        ref_p = tr.opt.flat.clone()
+        dist.broadcast(ref_p, 0)
+        diff = (tr.opt.flat - ref_p).abs().max()
+        dist.all_reduce(diff, op=dist.ReduceOp.MAX)
+        ranks_in_sync = bool(diff.item() == 0.0)
+
     roofline = None
     if top and top_stats:
         peaks = {}
@@ -290,7 +302,7 @@ def run_ours(args):
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f16", "data": "synthetic",
                 "config": {"workload": WORKLOAD, "rays_per_step_per_gpu": R, "samples_per_step_per_gpu": n_samples,
-                           "parallelism": f"dp{world}", "path": "fused CUDA-graph step (ncn_b200.fused.FusedStep)" if not args.no_graph else "fused eager step",
+                           "parallelism": f"dp{world}", "ranks_in_sync": ranks_in_sync, "path": "fused CUDA-graph step (ncn_b200.fused.FusedStep)" if not args.no_graph else "fused eager step",
                            "occupancy": "synthetic room (13.6 % of 128^3 cells); grid update every 16 steps runs in full, its result is reverted to keep samples/ray stationary",
                            "init": "random (tcnn-style U(-1e-4,1e-4) table, Xavier MLPs)",
                            "l2": "no explicit flush: per-step working set (fp32 params+grads+Adam m,v = 183 MB, + 22 MB fp16 table) exceeds the 126 MB L2"},

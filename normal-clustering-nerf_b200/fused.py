@@ -91,7 +91,12 @@ class FusedStep:
         self.prev_sched = [0.0] * 6
         self.flag_init = torch.zeros(1, dtype=torch.int32, device=dev)
         self.pending = False                 # deferred mode: a gradient is waiting for its optimizer pass
-        self.defer = use_graph               # deferred optimizer only in graph mode
+        # deferred optimizer: graph mode, single rank (the gradient all-reduce stays an eager NCCL call between two graphs;
+        # capturing it inside the step graph dead-locked on 2 GPUs)
+        self.defer = use_graph and trainer.world_size == 1
+        # multi-rank: the same overlap with three graphs on two streams and an EAGER all-reduce in between
+        #   opt stream : [all-reduce(prev grads) -> graph(adam)]      main stream: graph(march) -> join -> graph(field)
+        self.defer_multi = use_graph and trainer.world_size > 1
         self.opt_stream = torch.cuda.Stream(device=dev)
         self.ev_fork2, self.ev_join2 = torch.cuda.Event(), torch.cuda.Event()
         self.coef = torch.ones(1, **f32)
@@ -302,6 +307,20 @@ class FusedStep:
             if multi:
                 tr.comm.allreduce_sum_(self.opt.grad)
             self._optimizer()
+        elif self.defer_multi:
+            if self.graph is None:
+                self._capture_multi()
+            g_march, g_adam, g_field = self.graph
+            main = torch.cuda.current_stream()
+            self.opt_stream.wait_stream(main)             # the previous step's backward (gradients) is complete
+            if self.pending:
+                with torch.cuda.stream(self.opt_stream):
+                    tr.comm.allreduce_sum_(self.opt.grad)
+                    g_adam.replay()
+            g_march.replay()
+            main.wait_stream(self.opt_stream)
+            g_field.replay()
+            self.pending = True
         elif self.defer:
             if self.graph is None:
                 self._capture(multi)
@@ -320,9 +339,29 @@ class FusedStep:
                 self.graph[1].replay()
         tr.global_step += 1
 
+    def _capture_multi(self):
+        self.opt.grad.zero_()
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        keep = (self.opt.flat.clone(), self.opt.m.clone(), self.opt.v.clone(), self.flat16.clone())
+        with torch.cuda.stream(s):
+            self._run()
+            self._optimizer()
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        self.opt.flat.copy_(keep[0]); self.opt.m.copy_(keep[1]); self.opt.v.copy_(keep[2]); self.flat16.copy_(keep[3])
+        self.opt.grad.zero_()
+        graphs = []
+        for fn in (self._run_march, lambda: self._optimizer(sched_off=6), self._run_field):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                fn()
+            graphs.append(g)
+        self.graph = tuple(graphs)
+
     def flush(self):
         """deferred mode: apply the pending optimizer pass of the last step (call before reading parameters / evaluating)"""
-        if self.defer and self.pending:
+        if (self.defer or self.defer_multi) and self.pending:
             if self.tr.world_size > 1:
                 self.tr.comm.allreduce_sum_(self.opt.grad)
             self._optimizer(sched_off=0)          # slot 0 still holds the last step's schedule
