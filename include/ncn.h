@@ -243,6 +243,9 @@ int ncn_grid_bwd(const ncn_grid_desc* desc_host, const float* x, const void* dL_
 /* 1 (default): ncn_grid_bwd merges same-entry contributions of consecutive samples inside a warp before the
  * scatter; 0: one reduction per corner.  Returns the old value. */
 int ncn_set_grid_bwd_merge(int on);
+/* 1 (default): ncn_grid_fwd (L=16, F=2) evaluates one level for 32 consecutive samples per warp (coherent gathers);
+ * 0: one thread per (sample, level).  Returns the old value. */
+int ncn_set_grid_fwd_coherent(int on);
 /* dL_dx (N,3) f32 = d out / d x contracted with dL_dy. */
 int ncn_grid_bwd_input(const ncn_grid_desc* desc_host, const float* x, const void* table_f16,
                        const void* dL_dy_f16, int64_t n, float* dL_dx, ncn_stream_t stream);
@@ -295,11 +298,24 @@ typedef struct ncn_mlp_bwd_src {
   const float* d_sigmas;  /* (N) f32 */
   const void* h;          /* (N, 16) f16 */
   float scale;
+  int32_t perm;           /* bit 0: this net's input columns are in the fused-forward order [h(16) | d(3) | 1(13)] (colour head):
+                             W0 columns and dW0 are re-indexed accordingly and dL/dx comes out in that order;
+                             bit 1 (mode 2): dx_rgb is in that order, i.e. dL/dh = dx_rgb[:, 0:16] */
 } ncn_mlp_bwd_src;
 int ncn_mlp_bwd_src_fused(const ncn_mlp_desc* d, const ncn_mlp_bwd_src* src, const void* x_f16, const void* w_f16,
                           const void* out_f16, const void* acts_f16, int64_t n, float* grad_w_f32, void* dL_dx_f16,
                           float grad_scale, void* scratch, size_t scratch_bytes, const int32_t* n_dev,
                           ncn_stream_t stream);
+
+/* Fused field forward for the RGB+density configuration (models/ngp_mt.py:157-229): hash-grid gather -> sigma net ->
+ * TruncExp -> [h | d/|d| | 1] -> rgb net (sigmoid), one kernel.  x, dirs (N,3) f32; L=16, F=2 grid; w_sigma (32->64->16),
+ * w_rgb (32->64->64->16) in the tcnn layout.  Outputs: sigmas (N) f32, raws[:, 0:3] (row stride c_total) f32, and - each
+ * optional (NULL) - what the backward needs: feat (N,32), h (N,16), sig_acts (1,N,64), x_rgb (N,32) in the order
+ * [h | d | 1] (see ncn_mlp_bwd_src.perm), rgb_acts (2,N,64), rgb_out (N,16), all f16. */
+int ncn_field_fwd(const ncn_grid_desc* desc_host, const float* x, const float* dirs, const void* table_f16,
+                  const void* w_sigma_f16, const void* w_rgb_f16, int64_t n, const int32_t* n_dev,
+                  const float* xform_host, float* sigmas, float* raws, int c_total, void* feat_f16, void* h_f16,
+                  void* sig_acts_f16, void* x_rgb_f16, void* rgb_acts_f16, void* rgb_out_f16, ncn_stream_t stream);
 
 /* Selects the ncn_mlp_bwd implementation: 2 (default) = every GEMM (dgrad and wgrad) on tcgen05 with TMEM accumulators,
  * 128-row tiles; 1 = warp-MMA dgrad in registers + tcgen05/TMEM wgrad; 0 = warp-MMA dgrad + split-K wgrad kernels.

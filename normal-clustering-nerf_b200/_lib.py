@@ -54,7 +54,7 @@ class Profiler:
     events = []            # (name, start_event, end_event, n_items)
     KERNELS_PER_CALL = {"ncn_march_train": 3, "ncn_march_train_count": 2, "ncn_kmeans_workspace_bytes": 0,
                         "ncn_march_train_workspace_bytes": 0, "ncn_mlp_bwd_workspace_bytes": 0, "ncn_mlp_n_params": 0,
-                        "ncn_grid_desc_init": 0, "ncn_version": 0, "ncn_set_mlp_bwd_impl": 0, "ncn_set_grid_bwd_merge": 0, "ncn_error_string": 0, "ncn_device_info": 0,
+                        "ncn_grid_desc_init": 0, "ncn_version": 0, "ncn_set_mlp_bwd_impl": 0, "ncn_set_grid_bwd_merge": 0, "ncn_set_grid_fwd_coherent": 0, "ncn_error_string": 0, "ncn_device_info": 0,
                         "ncn_comm_unique_id": 0, "ncn_comm_init": 0, "ncn_comm_destroy": 0, "ncn_comm_last_error": 0}
 
     @classmethod
@@ -157,7 +157,7 @@ class MlpDesc(C.Structure):
 
 class MlpBwdSrc(C.Structure):
     _fields_ = [("mode", C.c_int32), ("d_raws", C.c_void_p), ("c_total", C.c_int32), ("c_off", C.c_int32), ("n_ch", C.c_int32),
-                ("dx_rgb", C.c_void_p), ("d_sigmas", C.c_void_p), ("h", C.c_void_p), ("scale", C.c_float)]
+                ("dx_rgb", C.c_void_p), ("d_sigmas", C.c_void_p), ("h", C.c_void_p), ("scale", C.c_float), ("perm", C.c_int32)]
 
 
 ACT = {"None": 0, "ReLU": 1, "Sigmoid": 2, "Exponential": 3}
@@ -193,6 +193,9 @@ SIGNATURES.update({
     "ncn_set_mlp_bwd_impl": (c_i32, [c_i32]),
     "ncn_mlp_bwd_src_fused": (c_i32, [C.POINTER(MlpDesc), C.POINTER(MlpBwdSrc), c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_f32, c_vp, c_sz, c_vp, c_vp]),
     "ncn_set_grid_bwd_merge": (c_i32, [c_i32]),
+    "ncn_set_grid_fwd_coherent": (c_i32, [c_i32]),
+    "ncn_field_fwd": (c_i32, [C.POINTER(GridDesc), c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, C.POINTER(c_f32), c_vp, c_vp, c_i32,
+                              c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "ncn_rays_from_pixels": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp]),
     "ncn_field_prepare_rgb": (c_i32, [c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp]),
     "ncn_field_head_out": (c_i32, [c_vp, c_i32, c_i64, c_vp, c_vp, c_i32, c_i32, c_i32, c_vp]),

@@ -121,6 +121,63 @@ grid_fwd_kernel(const __grid_constant__ GridMeta meta, const float* __restrict__
   }
 }
 
+// Forward with a sample-coherent mapping (F = 2): a warp evaluates ONE level for 32 CONSECUTIVE samples, so at the coarse
+// levels its 8 corner gathers touch a handful of cache lines instead of 32 different ones (the (sample, level)-interleaved
+// mapping above is bound by L1 wavefronts: every lane reads a different level's table).  A CTA of 8 warps covers 32
+// samples x 16 levels (2 levels per warp) and transposes the 32 x 32 fp16 tile through shared memory so the output rows
+// are still written as full 64 B segments.
+__global__ void __launch_bounds__(256)
+grid_fwd_coherent_kernel(const __grid_constant__ GridMeta meta, const float* __restrict__ x, const __half* __restrict__ table,
+                         int64_t n_cap, const int32_t* __restrict__ n_dev, GridXform xf, __half* __restrict__ out) {
+  __shared__ GridMeta sm;
+  __shared__ __align__(16) __half2 tile[32][17];      // [sample][level] (+1 pad)
+  for (int i = threadIdx.x; i < (int)(sizeof(GridMeta) / 4); i += blockDim.x)
+    reinterpret_cast<uint32_t*>(&sm)[i] = reinterpret_cast<const uint32_t*>(&meta)[i];
+  __syncthreads();
+  int64_t n = n_cap;
+  if (n_dev != nullptr) { const int64_t nd = *n_dev; if (nd < n) n = nd; }
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int64_t n_chunks = (n + 31) >> 5;
+  for (int64_t chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
+    const int64_t s = (chunk << 5) + lane;
+    const bool valid = s < n;
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int l = wid + 8 * q;
+      __half2 r = __floats2half2_rn(0.f, 0.f);
+      if (valid) {
+        Cell8 c;
+        locate8(x, s, sm.scale[l], sm.res[l], sm.size[l], c, xf);
+        const __half2* tl = reinterpret_cast<const __half2*>(table) + sm.offset[l];
+        __half2 v[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = __ldg(tl + c.idx[k]);
+        float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const float wk = corner_w(c.w, k);
+          const float2 f2 = __half22float2(v[k]);
+          a0 = fmaf(wk, f2.x, a0); a1 = fmaf(wk, f2.y, a1);
+        }
+        r = __floats2half2_rn(a0, a1);
+      }
+      tile[lane][l] = r;
+    }
+    __syncthreads();
+    // 32 samples x 16 half2: thread -> (sample = tid / 8, two half2 = 8 B) : rows of 64 B, fully coalesced
+    {
+      const int sr = threadIdx.x >> 3, c2 = (threadIdx.x & 7) * 2;
+      const int64_t so = (chunk << 5) + sr;
+      if (so < n) {
+        const __half2 a = tile[sr][c2], b = tile[sr][c2 + 1];
+        uint2 pk; pk.x = *reinterpret_cast<const uint32_t*>(&a); pk.y = *reinterpret_cast<const uint32_t*>(&b);
+        reinterpret_cast<uint2*>(out + so * 32)[c2 >> 1] = pk;
+      }
+    }
+    __syncthreads();
+  }
+}
+
 template <int F>
 __global__ void __launch_bounds__(256)
 grid_bwd_kernel(const __grid_constant__ GridMeta meta, const float* __restrict__ x, const __half* __restrict__ dy,
@@ -347,6 +404,8 @@ static GridXform make_xform(const float* xform_host) {
   return xf;
 }
 
+static int g_grid_fwd_coherent = 1; // 1 = warp-per-(32 samples, level) forward with smem transposition (default), 0 = thread-per-(sample, level)
+extern "C" int ncn_set_grid_fwd_coherent(int on) { const int old = g_grid_fwd_coherent; g_grid_fwd_coherent = on; return old; }
 static int g_grid_bwd_merge = 1;    // 1 = warp-level run merging before the scatter (default), 0 = one reduction per corner
 extern "C" int ncn_set_grid_bwd_merge(int on) { const int old = g_grid_bwd_merge; g_grid_bwd_merge = on; return old; }
 
@@ -366,6 +425,14 @@ extern "C" int ncn_grid_fwd(const ncn_grid_desc* desc, const float* x, const voi
   if (n == 0) return NCN_OK;
   NCN_CHECK_PTR(x); NCN_CHECK_PTR(table); NCN_CHECK_PTR(out);
   if (((uintptr_t)table | (uintptr_t)out) & 3) return NCN_E_ALIGN;
+  if (desc->n_features == 2 && m.n_levels == 16 && g_grid_fwd_coherent) {
+    const int64_t chunks = (n + 31) / 32;
+    int64_t cg = (int64_t)sm_count() * 8;
+    if (cg > chunks) cg = chunks;
+    grid_fwd_coherent_kernel<<<(int)cg, 256, 0, as_stream(stream)>>>(m, x, (const __half*)table, n, n_dev, make_xform(xform_host), (__half*)out);
+    NCN_LAUNCH_OK();
+    return NCN_OK;
+  }
   const int grid = persistent_grid(n * m.n_levels, 256, 8);
   NCN_GRID_DISPATCH(desc->n_features, (grid_fwd_kernel<kF><<<grid, 256, 0, as_stream(stream)>>>(
       m, x, (const __half*)table, n, n_dev, make_xform(xform_host), (__half*)out)));

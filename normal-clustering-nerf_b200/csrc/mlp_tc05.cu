@@ -371,10 +371,11 @@ __host__ __device__ constexpr uint32_t make_idesc_dgrad(int N) {
   return (1u << 4) | (1u << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 }
 // weight matrix W (K=out rows, N=in cols, row-major) -> MN-major panel [n/8][K][8]
-__device__ __forceinline__ void load_w_panel(const __half* __restrict__ w, int K, int N, __half* __restrict__ P) {
+__device__ __forceinline__ int perm_col(int c) { return c < 16 ? c + 3 : (c < 19 ? c - 16 : c); }   // fused-forward order -> tcnn order
+__device__ __forceinline__ void load_w_panel(const __half* __restrict__ w, int K, int N, __half* __restrict__ P, bool perm = false) {
   for (int i = threadIdx.x; i < K * N; i += blockDim.x) {
-    const int k = i / N, n = i % N;
-    P[((size_t)(n >> 3) * K + k) * 8 + (n & 7)] = w[i];
+    const int k = i / N, n = i % N;                  // n = kernel-internal column
+    P[((size_t)(n >> 3) * K + k) * 8 + (n & 7)] = w[k * N + (perm ? perm_col(n) : n)];
   }
 }
 
@@ -414,7 +415,7 @@ mlp_bwd_tc05_v2_kernel(const __half* __restrict__ x, const __half* __restrict__ 
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   load_w_panel(w + 64 * IN + (NH - 1) * 64 * 64, OUT, 64, WBl);
   for (int i = 0; i < NH - 1; ++i) load_w_panel(w + 64 * IN + i * 64 * 64, 64, 64, WBh + i * 64 * 64);
-  if (dx) load_w_panel(w, 64, IN, WB0);
+  if (dx) load_w_panel(w, 64, IN, WB0, (src.perm & 1) != 0);
   if (tid == 0) { mbar_init(mbar_w, 1); mbar_init(mbar_d, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
   if (wid == 0) tmem_alloc<LY::kTmemCols>(tmem_slot);
   fence_proxy_async();
@@ -461,10 +462,15 @@ mlp_bwd_tc05_v2_kernel(const __half* __restrict__ x, const __half* __restrict__ 
         }
       } else {
         const uint4* xr = reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(src.dx_rgb) + row * 32);
-        const uint4 w0 = xr[0], w1 = xr[1], w2 = xr[2];
-        const uint32_t wv[12] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w, w2.x, w2.y, w2.z, w2.w};
+        const uint4 w0 = xr[0], w1 = xr[1];
+        if (src.perm & 2) {                                       // fused-forward order: dL/dh = dx_rgb[:, 0:16]
+          drow[0] = w0.x; drow[1] = w0.y; drow[2] = w0.z; drow[3] = w0.w; drow[4] = w1.x; drow[5] = w1.y; drow[6] = w1.z; drow[7] = w1.w;
+        } else {
+          const uint4 w2 = xr[2];
+          const uint32_t wv[12] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w, w2.x, w2.y, w2.z, w2.w};
 #pragma unroll
-        for (int q = 0; q < 8; ++q) drow[q] = __funnelshift_r(wv[q + 1], wv[q + 2], 16);     // halfs 3+2q, 4+2q
+          for (int q = 0; q < 8; ++q) drow[q] = __funnelshift_r(wv[q + 1], wv[q + 2], 16);   // halfs 3+2q, 4+2q
+        }
         const float h0 = __half2float(reinterpret_cast<const __half*>(src.h)[row * 16]);
         const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&drow[0]));
         drow[0] = pack_half2(f.x + src.d_sigmas[row] * __expf(fminf(fmaxf(h0, -15.f), 15.f)) * src.scale, f.y);
@@ -595,7 +601,8 @@ mlp_bwd_tc05_v2_kernel(const __half* __restrict__ x, const __half* __restrict__ 
       tmem_ld16(lane_base + c0, v);
       if (lane < 16)
 #pragma unroll
-        for (int j = 0; j < 16; ++j) atomicAdd(grad_w + m * IN + c0 + j, __uint_as_float(v[j]) * grad_scale);
+        for (int j = 0; j < 16; ++j)
+          atomicAdd(grad_w + m * IN + ((src.perm & 1) ? perm_col(c0 + j) : c0 + j), __uint_as_float(v[j]) * grad_scale);
     }
 #pragma unroll
     for (int i = 1; i < NH; ++i)

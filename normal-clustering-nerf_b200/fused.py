@@ -27,7 +27,7 @@ GSCALE = 131072.0      # 2^17: loss scale carried by the fp16 dL/dy tensors (the
 
 
 class FusedStep:
-    def __init__(self, trainer, capacity_per_ray=64, use_graph=True):
+    def __init__(self, trainer, capacity_per_ray=64, use_graph=True, fuse_fwd=False):
         self.tr = trainer
         self.model = m = trainer.model
         self.opt = trainer.opt
@@ -74,8 +74,9 @@ class FusedStep:
                  self.L.ncn_mlp_bwd_workspace_bytes(C.byref(m.sigma_net.desc), cap))
         self.mlp_ws = E(nb, dtype=torch.uint8, device=dev)
         self.mlp_ws2 = E(nb, dtype=torch.uint8, device=dev)      # the colour-head backward runs concurrently on a side stream
-        self.src_rgb = _lib.MlpBwdSrc(1, ptr(self.d_raws), 3, 0, 3, None, None, None, 1.0)
-        self.src_sig = _lib.MlpBwdSrc(2, None, 0, 0, 0, ptr(self.dx_rgb), ptr(self.d_sigmas), ptr(self.h), 1.0)
+        self.fuse_fwd = fuse_fwd             # one fused forward kernel (x_rgb / dx_rgb then use the [h | d | 1] column order)
+        self.src_rgb = _lib.MlpBwdSrc(1, ptr(self.d_raws), 3, 0, 3, None, None, None, 1.0, 1 if fuse_fwd else 0)
+        self.src_sig = _lib.MlpBwdSrc(2, None, 0, 0, 0, ptr(self.dx_rgb), ptr(self.d_sigmas), ptr(self.h), 1.0, 2 if fuse_fwd else 0)
         self.side_stream = torch.cuda.Stream(device=dev)
         self.ev_fork, self.ev_join = torch.cuda.Event(), torch.cuda.Event()
         # fp16 parameter copies (owned by the optimizer, refreshed by its Adam kernel each step)
@@ -170,11 +171,16 @@ class FusedStep:
         n_dev = ptr(self.counter)
         ck = check
         enc, sg, rgbn = m.xyz_encoder, m.sigma_net, m.rgb_net
-        ck(L.ncn_grid_fwd(C.byref(enc.desc), ptr(self.xyzs), ptr(self._w16("xyz_encoder")), cap, ptr(self.feat), self.xform, n_dev, st), "grid_fwd")
-        ck(L.ncn_mlp_fwd(C.byref(sg.desc), ptr(self.feat), ptr(self._w16("sigma_net")), cap, ptr(self.h), ptr(self.sig_acts), n_dev, st), "sigma_fwd")
-        ck(L.ncn_field_prepare_rgb(ptr(self.dirs), ptr(self.h), cap, n_dev, ptr(self.x_rgb), ptr(self.sigmas), st), "prepare_rgb")
-        ck(L.ncn_mlp_fwd(C.byref(rgbn.desc), ptr(self.x_rgb), ptr(self._w16("rgb_net")), cap, ptr(self.rgb_out), ptr(self.rgb_acts), n_dev, st), "rgb_fwd")
-        ck(L.ncn_field_head_out(ptr(self.rgb_out), 16, cap, n_dev, ptr(self.raws), 3, 0, 3, st), "head_out")
+        if self.fuse_fwd:
+            ck(L.ncn_field_fwd(C.byref(enc.desc), ptr(self.xyzs), ptr(self.dirs), ptr(self._w16("xyz_encoder")), ptr(self._w16("sigma_net")),
+                               ptr(self._w16("rgb_net")), cap, n_dev, self.xform, ptr(self.sigmas), ptr(self.raws), 3, ptr(self.feat),
+                               ptr(self.h), ptr(self.sig_acts), ptr(self.x_rgb), ptr(self.rgb_acts), ptr(self.rgb_out), st), "field_fwd")
+        else:
+            ck(L.ncn_grid_fwd(C.byref(enc.desc), ptr(self.xyzs), ptr(self._w16("xyz_encoder")), cap, ptr(self.feat), self.xform, n_dev, st), "grid_fwd")
+            ck(L.ncn_mlp_fwd(C.byref(sg.desc), ptr(self.feat), ptr(self._w16("sigma_net")), cap, ptr(self.h), ptr(self.sig_acts), n_dev, st), "sigma_fwd")
+            ck(L.ncn_field_prepare_rgb(ptr(self.dirs), ptr(self.h), cap, n_dev, ptr(self.x_rgb), ptr(self.sigmas), st), "prepare_rgb")
+            ck(L.ncn_mlp_fwd(C.byref(rgbn.desc), ptr(self.x_rgb), ptr(self._w16("rgb_net")), cap, ptr(self.rgb_out), ptr(self.rgb_acts), n_dev, st), "rgb_fwd")
+            ck(L.ncn_field_head_out(ptr(self.rgb_out), 16, cap, n_dev, ptr(self.raws), 3, 0, 3, st), "head_out")
         ck(L.ncn_composite_train_fw(ptr(self.sigmas), ptr(self.raws), ptr(self.deltas), ptr(self.ts), ptr(self.rays_a), 1e-4, R, cap, 3,
                                     ptr(self.total_samples), ptr(self.opacity), ptr(self.depth), ptr(self.rend), ptr(self.ws), st), "composite_fw")
         # ---- losses (+ their gradients w.r.t. the rendered quantities)

@@ -186,11 +186,11 @@ class NeRFTrainer:
         loss_d = self.loss(results, target, global_step=self.global_step)
         return results, loss_d
 
-    def fused_step(self, capacity_per_ray=64, use_graph=True):
+    def fused_step(self, capacity_per_ray=64, use_graph=True, fuse_fwd=False):
         """the sync-free CUDA-graph step (ncn_b200.fused.FusedStep) for the RGB+depth configuration"""
         if self.fused is None:
             from .fused import FusedStep
-            self.fused = FusedStep(self, capacity_per_ray=capacity_per_ray, use_graph=use_graph)
+            self.fused = FusedStep(self, capacity_per_ray=capacity_per_ray, use_graph=use_graph, fuse_fwd=fuse_fwd)
             self.opt.grad_div.fill_(float(self.world_size))     # fused gradients are already un-scaled
         return self.fused
 

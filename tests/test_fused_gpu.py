@@ -32,7 +32,8 @@ def _setup(R=2048, seed=0):
     return tr, rays_o, rays_d, tri, rgb, target
 
 
-def test_fused_matches_module_path():
+@pytest.mark.parametrize("fuse_fwd", [True, False])
+def test_fused_matches_module_path(fuse_fwd):
     from ncn_b200.fused import GSCALE
     tr, rays_o, rays_d, tri, rgb, target = _setup()
     R = rays_o.shape[0]
@@ -45,7 +46,7 @@ def test_fused_matches_module_path():
     # fused path, eager (no graph), same noise
     torch.manual_seed(123)
     noise = torch.rand(R, device="cuda")
-    fs = tr.fused_step(use_graph=False)
+    fs = tr.fused_step(use_graph=False, fuse_fwd=fuse_fwd)
     fs.set_triangles(tri)
     fs.rays_o.copy_(rays_o); fs.rays_d.copy_(rays_d); fs.target.copy_(rgb); fs.noise.copy_(noise)
     fs.gen_noise = False
