@@ -658,7 +658,15 @@ static int launch_tc05_v2(const void* x, const void* w, const void* out, const v
   NCN_CUDA(cudaMemsetAsync(tile_counter, 0, sizeof(int), st));
   NCN_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LY::kBytes));
   const int64_t tiles = (n + kTile - 1) / kTile;
-  int64_t grid = (int64_t)sm_count() * 2;
+  // persistent grid = every CTA slot the SMs offer (shared memory bound: 2 for the colour head, 4 for the density trunk);
+  // the dynamic tile scheduler keeps them evenly loaded
+  static int occ = 0;
+  if (occ == 0) {
+    int o = 0;
+    NCN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, k, kV2Threads, LY::kBytes));
+    occ = o < 1 ? 1 : (o > 512 / LY::kTmemCols ? 512 / LY::kTmemCols : o);      // TMEM: 512 columns per SM
+  }
+  int64_t grid = (int64_t)sm_count() * occ;
   if (grid > tiles) grid = tiles;
   k<<<(int)grid, kV2Threads, LY::kBytes, st>>>((const __half*)x, (const __half*)w, (const __half*)out, (const __half*)acts,
                                                (const __half*)dout, n, n_dev, out_act, grad_scale, grad_w, (__half*)dx, tile_counter, src);
