@@ -271,12 +271,18 @@ typedef struct ncn_mlp_desc {
 } ncn_mlp_desc;
 int64_t ncn_mlp_n_params(const ncn_mlp_desc* d);
 size_t ncn_mlp_bwd_workspace_bytes(const ncn_mlp_desc* d, int64_t n);
+size_t ncn_mlp_acts_bytes(const ncn_mlp_desc* d, int64_t n);
 /* x (N, n_in_pad) f16, weights f16 (tcnn layout: consecutive (out,in) row-major
  * matrices: (64,in_pad), (n_hidden-1) x (64,64), (out_pad,64)); out (N, n_out_pad) f16.
- * If `acts` != NULL the post-activation hidden states (n_hidden, N, 64) f16 are kept
- * for the backward pass.  Padded dims are multiples of 16 and <= 64.
- * n_dev: NULL or a DEVICE int32 live row count (rows = min(n, *n_dev)); the (n_hidden, n, 64)
- * strides stay those of n. */
+ * If `acts` != NULL (ncn_mlp_acts_bytes(d, n) bytes, 128 B aligned) the post-activation hidden
+ * states are kept for the backward pass - an opaque buffer between ncn_mlp_fwd / ncn_field_fwd
+ * and ncn_mlp_bwd*: per layer ceil(n/128) tiles of 128 rows, each tile stored as the
+ * [feature/8][row][8] f16 panel the tcgen05 backward multiplies from, so that a tile is one
+ * contiguous 16 KB bulk copy (element (r, f) of layer l at
+ * l*ceil128(n)*64 + (r/128)*8192 + ((f/8)*128 + r%128)*8 + f%8).
+ * Padded dims are multiples of 16 and <= 64.
+ * n_dev: NULL or a DEVICE int32 live row count (rows = min(n, *n_dev)); the layer stride
+ * stays that of n. */
 int ncn_mlp_fwd(const ncn_mlp_desc* d, const void* x_f16, const void* w_f16, int64_t n,
                 void* out_f16, void* acts_f16, const int32_t* n_dev, ncn_stream_t stream);
 /* dL_dout (N,n_out_pad) f16 -> grad_w f32 += grad_scale * dL/dW (ACCUMULATED; may be
@@ -310,16 +316,16 @@ int ncn_mlp_bwd_src_fused(const ncn_mlp_desc* d, const ncn_mlp_bwd_src* src, con
 /* Fused field forward for the RGB+density configuration (models/ngp_mt.py:157-229): hash-grid gather -> sigma net ->
  * TruncExp -> [h | d/|d| | 1] -> rgb net (sigmoid), one kernel.  x, dirs (N,3) f32; L=16, F=2 grid; w_sigma (32->64->16),
  * w_rgb (32->64->64->16) in the tcnn layout.  Outputs: sigmas (N) f32, raws[:, 0:3] (row stride c_total) f32, and - each
- * optional (NULL) - what the backward needs: feat (N,32), h (N,16), sig_acts (1,N,64), x_rgb (N,32) in the order
- * [h | d | 1] (see ncn_mlp_bwd_src.perm), rgb_acts (2,N,64), rgb_out (N,16), all f16. */
+ * optional (NULL) - what the backward needs: feat (N,32), h (N,16), sig_acts (ncn_mlp_acts_bytes), x_rgb (N,32) in the order
+ * [h | d | 1] (see ncn_mlp_bwd_src.perm), rgb_acts (ncn_mlp_acts_bytes), rgb_out (N,16), all f16. */
 int ncn_field_fwd(const ncn_grid_desc* desc_host, const float* x, const float* dirs, const void* table_f16,
                   const void* w_sigma_f16, const void* w_rgb_f16, int64_t n, const int32_t* n_dev,
                   const float* xform_host, float* sigmas, float* raws, int c_total, void* feat_f16, void* h_f16,
                   void* sig_acts_f16, void* x_rgb_f16, void* rgb_acts_f16, void* rgb_out_f16, ncn_stream_t stream);
 
-/* Selects the ncn_mlp_bwd implementation: 2 (default) = every GEMM (dgrad and wgrad) on tcgen05 with TMEM accumulators,
- * 128-row tiles; 1 = warp-MMA dgrad in registers + tcgen05/TMEM wgrad; 0 = warp-MMA dgrad + split-K wgrad kernels.
- * Returns the old value. */
+/* Selects the ncn_mlp_bwd implementation: 1 (default) = every GEMM (dgrad and wgrad) on tcgen05 with TMEM
+ * accumulators, 128-row tiles fed by bulk copies (shapes without an instantiation fall back to 0);
+ * 0 = warp-MMA dgrad in registers + split-K wgrad kernels.  Returns the old value. */
 int ncn_set_mlp_bwd_impl(int impl);
 
 /* Elementwise glue of the NGPMT field (models/ngp_mt.py:157-229, rendering.py:203-212) between the

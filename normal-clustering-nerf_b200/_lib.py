@@ -53,7 +53,7 @@ class Profiler:
     launches = 0
     events = []            # (name, start_event, end_event, n_items)
     KERNELS_PER_CALL = {"ncn_march_train": 3, "ncn_march_train_count": 2, "ncn_kmeans_workspace_bytes": 0,
-                        "ncn_march_train_workspace_bytes": 0, "ncn_mlp_bwd_workspace_bytes": 0, "ncn_mlp_n_params": 0,
+                        "ncn_march_train_workspace_bytes": 0, "ncn_mlp_bwd_workspace_bytes": 0, "ncn_mlp_acts_bytes": 0, "ncn_mlp_n_params": 0,
                         "ncn_grid_desc_init": 0, "ncn_version": 0, "ncn_set_mlp_bwd_impl": 0, "ncn_set_grid_bwd_merge": 0, "ncn_set_grid_fwd_coherent": 0, "ncn_error_string": 0, "ncn_device_info": 0,
                         "ncn_comm_unique_id": 0, "ncn_comm_init": 0, "ncn_comm_destroy": 0, "ncn_comm_last_error": 0}
 
@@ -170,6 +170,7 @@ SIGNATURES.update({
     "ncn_grid_bwd_bwd_input": (c_i32, [C.POINTER(GridDesc), c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp]),
     "ncn_mlp_n_params": (c_i64, [C.POINTER(MlpDesc)]),
     "ncn_mlp_bwd_workspace_bytes": (c_sz, [C.POINTER(MlpDesc), c_i64]),
+    "ncn_mlp_acts_bytes": (c_sz, [C.POINTER(MlpDesc), c_i64]),
     "ncn_mlp_fwd": (c_i32, [C.POINTER(MlpDesc), c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp]),
     "ncn_mlp_bwd": (c_i32, [C.POINTER(MlpDesc), c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_f32, c_vp, c_sz, c_vp, c_vp]),
 })

@@ -53,7 +53,7 @@ def build(force=False, verbose=False):
         obj = os.path.join(OBJ, f + ".o")
         if not force and os.path.exists(obj) and os.path.getmtime(obj) >= max(os.path.getmtime(src), hdr_time):
             continue
-        cmd = [NVCC] + ARCH + COMMON + EXTRA.get(f, []) + ["-c", src, "-o", obj]
+        cmd = [NVCC] + ARCH + COMMON + EXTRA.get(f, []) + os.environ.get("NCN_NVCC_EXTRA", "").split() + ["-c", src, "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         jobs.append(cmd)

@@ -93,6 +93,16 @@ __device__ __forceinline__ void ff_store_a(__half* __restrict__ y, int64_t row0,
     if (r1 < n) { *reinterpret_cast<uint32_t*>(y + r1 * K + col) = a[kb][1]; *reinterpret_cast<uint32_t*>(y + r1 * K + col + 8) = a[kb][3]; }
   }
 }
+// hidden-state tile -> tiled activation layout (ncn_common.cuh act_offset)
+__device__ __forceinline__ void ff_store_act(__half* __restrict__ y, int64_t row0, int64_t n, const uint32_t (*a)[4], int g, int t) {
+  const int64_t r0 = row0 + g, r1 = row0 + g + 8;
+#pragma unroll
+  for (int kb = 0; kb < 4; ++kb) {
+    const int col = kb * 16 + 2 * t;
+    if (r0 < n) { *reinterpret_cast<uint32_t*>(y + act_offset(r0, col)) = a[kb][0]; *reinterpret_cast<uint32_t*>(y + act_offset(r0, col + 8)) = a[kb][2]; }
+    if (r1 < n) { *reinterpret_cast<uint32_t*>(y + act_offset(r1, col)) = a[kb][1]; *reinterpret_cast<uint32_t*>(y + act_offset(r1, col + 8)) = a[kb][3]; }
+  }
+}
 __device__ __forceinline__ void ff_load_w(const __half* __restrict__ w, int rows, int cols, __half* __restrict__ s, bool perm) {
   for (int i = threadIdx.x; i < rows * cols; i += blockDim.x) {
     const int r = i / cols, c = i % cols;             // c = kernel-internal column
@@ -155,7 +165,7 @@ field_fwd_kernel(const __grid_constant__ FfGridMeta meta, const float* __restric
     ff_layer<32, 64>(af, S0, c, g, t);
     uint32_t hid[4][4];
     ff_relu_pack(c, hid);
-    if (sig_acts) ff_store_a<64>(sig_acts, row0, n, hid, g, t);
+    if (sig_acts) ff_store_act(sig_acts, row0, n, hid, g, t);
     float ch[2][4];
     ff_layer<64, 16>(hid, S1, ch, g, t);
     // h (fp16, as the tcnn module returns it) is both an output and k-block 0 of the colour head's input
@@ -184,10 +194,10 @@ field_fwd_kernel(const __grid_constant__ FfGridMeta meta, const float* __restric
     // ---- colour head
     ff_layer<32, 64>(xin, R0, c, g, t);
     ff_relu_pack(c, hid);
-    if (rgb_acts) ff_store_a<64>(rgb_acts, row0, n, hid, g, t);
+    if (rgb_acts) ff_store_act(rgb_acts, row0, n, hid, g, t);
     ff_layer<64, 64>(hid, R1, c, g, t);
     ff_relu_pack(c, hid);
-    if (rgb_acts) ff_store_a<64>(rgb_acts + n_cap * 64, row0, n, hid, g, t);
+    if (rgb_acts) ff_store_act(rgb_acts + act_rows(n_cap) * 64, row0, n, hid, g, t);
     float co[2][4];
     ff_layer<64, 16>(hid, R2, co, g, t);
     uint32_t o[4];

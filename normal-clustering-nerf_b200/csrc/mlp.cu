@@ -73,6 +73,18 @@ __device__ __forceinline__ void store_a(__half* __restrict__ y, int64_t row0, in
   }
 }
 
+// store an A-fragment-packed 16 x 64 hidden-state tile into the tiled activation layout (act_offset): the 8 rows x 4
+// lanes of one fragment register land in 8 x 16 B = 128 contiguous bytes
+__device__ __forceinline__ void store_act(__half* __restrict__ y, int64_t row0, int64_t n, const uint32_t (*a)[4], int g, int t) {
+  const int64_t r0 = row0 + g, r1 = row0 + g + 8;
+#pragma unroll
+  for (int kb = 0; kb < 4; ++kb) {
+    const int col = kb * 16 + 2 * t;
+    if (r0 < n) { *reinterpret_cast<uint32_t*>(y + act_offset(r0, col)) = a[kb][0]; *reinterpret_cast<uint32_t*>(y + act_offset(r0, col + 8)) = a[kb][2]; }
+    if (r1 < n) { *reinterpret_cast<uint32_t*>(y + act_offset(r1, col)) = a[kb][1]; *reinterpret_cast<uint32_t*>(y + act_offset(r1, col + 8)) = a[kb][3]; }
+  }
+}
+
 // cooperative copy of a (rows, cols) row-major fp16 matrix into smem with row stride cols+kPad
 __device__ __forceinline__ void load_w(const __half* __restrict__ w, int rows, int cols, __half* __restrict__ s) {
   for (int i = threadIdx.x; i < rows * cols / 2; i += blockDim.x) {
@@ -125,13 +137,13 @@ mlp_fwd_kernel(const __half* __restrict__ x, const __half* __restrict__ w, int64
 #pragma unroll
     for (int j = 0; j < 8; ++j) { c[j][0] = fmaxf(c[j][0], 0.f); c[j][1] = fmaxf(c[j][1], 0.f); c[j][2] = fmaxf(c[j][2], 0.f); c[j][3] = fmaxf(c[j][3], 0.f); }
     c_to_a64(c, h);
-    if (acts) store_a<kW>(acts, row0, n, h, g, t);
+    if (acts) store_act(acts, row0, n, h, g, t);
     for (int i = 1; i < n_hidden; ++i) {
       warp_layer<kW, kW>(h, Wh + (i - 1) * kW * (kW + kPad), c, g, t);
 #pragma unroll
       for (int j = 0; j < 8; ++j) { c[j][0] = fmaxf(c[j][0], 0.f); c[j][1] = fmaxf(c[j][1], 0.f); c[j][2] = fmaxf(c[j][2], 0.f); c[j][3] = fmaxf(c[j][3], 0.f); }
       c_to_a64(c, h);
-      if (acts) store_a<kW>(acts + (int64_t)i * n_cap * kW, row0, n, h, g, t);
+      if (acts) store_act(acts + (int64_t)i * act_rows(n_cap) * kW, row0, n, h, g, t);
     }
     float co[OUT / 8][4];
     warp_layer<kW, OUT>(h, Wl, co, g, t);
@@ -146,15 +158,15 @@ mlp_fwd_kernel(const __half* __restrict__ x, const __half* __restrict__ w, int64
 }
 
 // ------------------------------------------------------------------------------ dgrad
-// mask accumulators (C layout, 16 x 64) with relu'(act) read from a row-major (n, 64) fp16 matrix
+// mask accumulators (C layout, 16 x 64) with relu'(act) read from one layer of the tiled activations (act_offset)
 __device__ __forceinline__ void relu_mask(float (*c)[4], const __half* __restrict__ act, int64_t row0, int64_t n, int g, int t) {
   const int64_t r0 = row0 + g, r1 = row0 + g + 8;
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const int col = j * 8 + 2 * t;
     const __half2 z = __floats2half2_rn(0.f, 0.f);
-    const __half2 a0 = r0 < n ? *reinterpret_cast<const __half2*>(act + r0 * kW + col) : z;
-    const __half2 a1 = r1 < n ? *reinterpret_cast<const __half2*>(act + r1 * kW + col) : z;
+    const __half2 a0 = r0 < n ? *reinterpret_cast<const __half2*>(act + act_offset(r0, col)) : z;
+    const __half2 a1 = r1 < n ? *reinterpret_cast<const __half2*>(act + act_offset(r1, col)) : z;
     if (!(__low2float(a0) > 0.f)) c[j][0] = 0.f;
     if (!(__high2float(a0) > 0.f)) c[j][1] = 0.f;
     if (!(__low2float(a1) > 0.f)) c[j][2] = 0.f;
@@ -204,7 +216,7 @@ mlp_dgrad_kernel(const __half* __restrict__ w, const __half* __restrict__ out, c
     warp_layer<OUT, kW>(dz, WlT, c, g, t);               // dL/dh (16 x 64)
     uint32_t dh[4][4];
     for (int i = n_hidden - 1; i >= 0; --i) {
-      relu_mask(c, acts + (int64_t)i * n_cap * kW, row0, n, g, t);
+      relu_mask(c, acts + (int64_t)i * act_rows(n_cap) * kW, row0, n, g, t);
       c_to_a64(c, dh);
       store_a<kW>(dz_hidden + (int64_t)i * n_cap * kW, row0, n, dh, g, t);
       if (i > 0) warp_layer<kW, kW>(dh, WhT + (i - 1) * kW * (kW + kPad), c, g, t);
@@ -224,12 +236,13 @@ mlp_dgrad_kernel(const __half* __restrict__ w, const __half* __restrict__ out, c
 }
 
 // ------------------------------------------------------------------------------ wgrad
-// grad_w[M x NN] += scale * dz^T (M x n) * a (n x NN);  dz (n, M), a (n, NN) row-major fp16.
+// grad_w[M x NN] += scale * dz^T (M x n) * a (n x NN);  dz (n, M) row-major fp16; a (n, NN) row-major fp16, or
+// (a_tiled, NN == 64) one layer of the tiled activations.
 constexpr int kChunk = 64;
 template <int M, int NN>
 __global__ void __launch_bounds__(kMlpThreads)
-mlp_wgrad_kernel(const __half* __restrict__ dz, const __half* __restrict__ a, int64_t n_cap, const int32_t* __restrict__ n_dev,
-                 float scale, float* __restrict__ grad_w) {
+mlp_wgrad_kernel(const __half* __restrict__ dz, const __half* __restrict__ a, int a_tiled, int64_t n_cap,
+                 const int32_t* __restrict__ n_dev, float scale, float* __restrict__ grad_w) {
   int64_t n = n_cap;
   if (n_dev != nullptr) { const int64_t nd = *n_dev; if (nd < n) n = nd; }
   constexpr int TM = M / 16, TN = NN / 8, TOTAL = TM * TN;
@@ -255,7 +268,7 @@ mlp_wgrad_kernel(const __half* __restrict__ dz, const __half* __restrict__ a, in
     for (int i = threadIdx.x; i < kChunk * (NN / 8); i += kMlpThreads) {
       const int r = i / (NN / 8), c8 = i % (NN / 8);
       uint4 v = make_uint4(0, 0, 0, 0);
-      if (row0 + r < n) v = *reinterpret_cast<const uint4*>(a + (row0 + r) * NN + c8 * 8);
+      if (row0 + r < n) v = *reinterpret_cast<const uint4*>(a_tiled ? a + act_offset(row0 + r, c8 * 8) : a + (row0 + r) * NN + c8 * 8);
       *reinterpret_cast<uint4*>(&Sa[r][c8 * 8]) = v;
     }
     __syncthreads();
@@ -319,6 +332,12 @@ extern "C" int64_t ncn_mlp_n_params(const ncn_mlp_desc* d) {
   return (int64_t)64 * ip + (int64_t)(d->n_hidden - 1) * 64 * 64 + (int64_t)op * 64;
 }
 
+extern "C" size_t ncn_mlp_acts_bytes(const ncn_mlp_desc* d, int64_t n) {
+  int ip, op;
+  if (check_desc(d, &ip, &op) || n < 0) return 0;
+  return (size_t)d->n_hidden * (size_t)act_rows(n) * 64 * sizeof(__half);
+}
+
 extern "C" size_t ncn_mlp_bwd_workspace_bytes(const ncn_mlp_desc* d, int64_t n) {
   int ip, op;
   if (check_desc(d, &ip, &op) || n < 0) return 0;
@@ -339,18 +358,18 @@ static int launch_fwd(const ncn_mlp_desc* d, const void* x, const void* w, int64
 }
 
 template <int M, int NN>
-static int launch_wgrad(const __half* dz, const __half* a, int64_t n, const int32_t* n_dev, float scale, float* gw, cudaStream_t st) {
+static int launch_wgrad(const __half* dz, const __half* a, int a_tiled, int64_t n, const int32_t* n_dev, float scale, float* gw, cudaStream_t st) {
   const int64_t chunks = (n + kChunk - 1) / kChunk;
   int64_t grid = (int64_t)sm_count() * 4;
   if (grid > chunks) grid = chunks;
-  mlp_wgrad_kernel<M, NN><<<(int)grid, kMlpThreads, 0, st>>>(dz, a, n, n_dev, scale, gw);
+  mlp_wgrad_kernel<M, NN><<<(int)grid, kMlpThreads, 0, st>>>(dz, a, a_tiled, n, n_dev, scale, gw);
   NCN_LAUNCH_OK();
   return NCN_OK;
 }
 
-static int wgrad_dispatch(int M, int NN, const __half* dz, const __half* a, int64_t n, const int32_t* n_dev, float scale, float* gw,
-                          cudaStream_t st) {
-#define NCN_WG(MM, N2) if (M == MM && NN == N2) return launch_wgrad<MM, N2>(dz, a, n, n_dev, scale, gw, st);
+static int wgrad_dispatch(int M, int NN, const __half* dz, const __half* a, int a_tiled, int64_t n, const int32_t* n_dev, float scale,
+                          float* gw, cudaStream_t st) {
+#define NCN_WG(MM, N2) if (M == MM && NN == N2) return launch_wgrad<MM, N2>(dz, a, a_tiled, n, n_dev, scale, gw, st);
   NCN_WG(64, 16) NCN_WG(64, 32) NCN_WG(64, 48) NCN_WG(64, 64)
   NCN_WG(16, 64) NCN_WG(32, 64) NCN_WG(48, 64)
 #undef NCN_WG
@@ -372,14 +391,14 @@ static int launch_bwd(const ncn_mlp_desc* d, const void* x, const void* w, const
   NCN_LAUNCH_OK();
   if (grad_w) {
     // layer 0: dz_hidden[0]^T x
-    int rc = wgrad_dispatch(64, IN, dz_hidden, (const __half*)x, n, n_dev, grad_scale, grad_w, st);
+    int rc = wgrad_dispatch(64, IN, dz_hidden, (const __half*)x, 0, n, n_dev, grad_scale, grad_w, st);
     if (rc) return rc;
     for (int i = 1; i < d->n_hidden; ++i) {
-      rc = wgrad_dispatch(64, 64, dz_hidden + (size_t)i * n * 64, (const __half*)acts + (size_t)(i - 1) * n * 64, n, n_dev, grad_scale,
+      rc = wgrad_dispatch(64, 64, dz_hidden + (size_t)i * n * 64, (const __half*)acts + (size_t)(i - 1) * act_rows(n) * 64, 1, n, n_dev, grad_scale,
                           grad_w + 64 * IN + (size_t)(i - 1) * 64 * 64, st);
       if (rc) return rc;
     }
-    rc = wgrad_dispatch(OUT, 64, dz_last, (const __half*)acts + (size_t)(d->n_hidden - 1) * n * 64, n, n_dev, grad_scale,
+    rc = wgrad_dispatch(OUT, 64, dz_last, (const __half*)acts + (size_t)(d->n_hidden - 1) * act_rows(n) * 64, 1, n, n_dev, grad_scale,
                         grad_w + 64 * IN + (size_t)(d->n_hidden - 1) * 64 * 64, st);
     if (rc) return rc;
   }
@@ -412,7 +431,7 @@ extern "C" int ncn_mlp_fwd(const ncn_mlp_desc* d, const void* x, const void* w, 
 int ncn_mlp_bwd_tc05_try(int in_pad, int out_pad, int n_hidden, const void* x, const void* w, const void* out, const void* acts,
                          const void* dout, int64_t n, const int32_t* n_dev, int out_act, float grad_scale, float* grad_w,
                          void* dx, int* tile_counter, int impl, const ncn_mlp_bwd_src* src, cudaStream_t st);
-static int g_mlp_bwd_impl = 2;     // 2 = every GEMM on tcgen05 (default), 1 = warp-MMA dgrad + tcgen05/TMEM wgrad, 0 = warp-MMA + split-K wgrad kernels
+static int g_mlp_bwd_impl = 1;     // 1 = tcgen05 / TMEM kernel (default; falls back per shape), 0 = warp-MMA dgrad + split-K wgrad kernels
 extern "C" int ncn_set_mlp_bwd_impl(int impl) { const int old = g_mlp_bwd_impl; g_mlp_bwd_impl = impl; return old; }
 
 extern "C" int ncn_mlp_bwd(const ncn_mlp_desc* d, const void* x, const void* w, const void* out, const void* acts,
@@ -451,8 +470,8 @@ extern "C" int ncn_mlp_bwd_src_fused(const ncn_mlp_desc* d, const ncn_mlp_bwd_sr
   else if (src->mode == 2) { NCN_CHECK_PTR(src->dx_rgb); NCN_CHECK_PTR(src->d_sigmas); NCN_CHECK_PTR(src->h); }
   else return NCN_E_CONFIG;
   if (scratch_bytes < ncn_mlp_bwd_workspace_bytes(d, n)) return NCN_E_SIZE;
-  if (g_mlp_bwd_impl != 2) return NCN_E_UNSUPPORTED;
+  if (g_mlp_bwd_impl < 1) return NCN_E_UNSUPPORTED;
   int* tile_counter = (int*)((char*)scratch + ((ncn_mlp_bwd_workspace_bytes(d, n) - 256) & ~(size_t)15));
   return ncn_mlp_bwd_tc05_try(ip, op, d->n_hidden, x, w, out, acts, nullptr, n, n_dev, d->out_activation, grad_scale, grad_w, dL_dx,
-                              tile_counter, 2, src, as_stream(stream));
+                              tile_counter, g_mlp_bwd_impl, src, as_stream(stream));
 }

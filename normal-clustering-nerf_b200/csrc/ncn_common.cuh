@@ -25,6 +25,15 @@ int sm_count();
 
 static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
+// Saved hidden activations of the MLPs ("acts", include/ncn.h ncn_mlp_fwd): per layer ceil(N/128) tiles of 128 rows,
+// each tile stored as the [feature/8][row][8 halfs] panel the tcgen05 backward multiplies from - one contiguous
+// 16 KB block per tile and layer, fetched by a single bulk copy (TMA) without any layout change on the way.
+constexpr int kActTile = 128;
+__host__ __device__ __forceinline__ int64_t act_rows(int64_t n) { return (n + (kActTile - 1)) & ~(int64_t)(kActTile - 1); }
+__host__ __device__ __forceinline__ int64_t act_offset(int64_t row, int f) {        // halfs, within one layer
+  return (row >> 7) * (64 * kActTile) + ((int64_t)((f >> 3) * kActTile + (int)(row & (kActTile - 1))) << 3) + (f & 7);
+}
+
 // grid for a grid-stride kernel: enough CTAs for `n` items but at most `waves`
 // resident waves of the 148-SM part (blocks_per_sm resident CTAs each).
 static inline int persistent_grid(int64_t n, int threads, int blocks_per_sm) {

@@ -58,8 +58,9 @@ class FusedStep:
         self.deltas, self.ts = torch.zeros(cap, **f32), torch.zeros(cap, **f32)
         # field
         self.feat, self.h = E(cap, 32, **f16), E(cap, 16, **f16)
-        self.sig_acts = E(1, cap, 64, **f16)
-        self.x_rgb, self.rgb_out, self.rgb_acts = E(cap, 32, **f16), E(cap, 16, **f16), E(2, cap, 64, **f16)
+        cap_t = (cap + 127) // 128 * 128                         # saved activations: whole 128-row tiles (ncn_mlp_acts_bytes)
+        self.sig_acts = E(1, cap_t, 64, **f16)
+        self.x_rgb, self.rgb_out, self.rgb_acts = E(cap, 32, **f16), E(cap, 16, **f16), E(2, cap_t, 64, **f16)
         self.sigmas, self.raws = E(cap, **f32), E(cap, 3, **f32)
         # compositing + loss
         self.total_samples = E(R, dtype=torch.int64, device=dev)

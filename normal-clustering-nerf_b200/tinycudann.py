@@ -177,7 +177,8 @@ class _MlpFn(torch.autograd.Function):
             xp[:, :mod.n_input_dims] = x                       # Identity encoding pads with 1.0
         out = torch.empty(n, mod.out_pad, dtype=torch.float16, device=dev)
         keep = ctx.needs_input_grad[1] or ctx.needs_input_grad[2]
-        acts = torch.empty(mod.n_hidden, n, 64, dtype=torch.float16, device=dev) if keep else None
+        # opaque saved activations in the backward kernel's tiled panel layout (include/ncn.h ncn_mlp_fwd)
+        acts = torch.empty(_lib.lib().ncn_mlp_acts_bytes(C.byref(mod.desc), n) // 2, dtype=torch.float16, device=dev) if keep else None
         check(_lib.lib().ncn_mlp_fwd(C.byref(mod.desc), ptr(xp), ptr(w), n, ptr(out), ptr(acts), None, stream()), "mlp_fwd")
         ctx.mod = mod
         ctx.x_dtype = x.dtype

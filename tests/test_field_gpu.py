@@ -129,6 +129,35 @@ def test_grid_double_backward(ncn):
     assert (gp.view(-1, 2) - tab.grad).abs().max() <= 2e-2 * tab.grad.abs().max()
 
 
+@pytest.mark.parametrize("impl", [0, 1])
+@pytest.mark.parametrize("n_in,n_out,n_hidden,act", [(32, 16, 1, "None"), (32, 3, 2, "Sigmoid")])
+def test_mlp_backward_implementations_agree(ncn, impl, n_in, n_out, n_hidden, act):
+    """ncn_set_mlp_bwd_impl: the warp-MMA kernels and the tcgen05 kernel against the same restatement, ragged tail and
+    enough rows that every persistent CTA walks several tiles (prefetch + accumulate paths)."""
+    from ncn_b200 import _lib, tinycudann as tcnn
+    from oracle import mlp
+    n = 148 * 3 * 128 * 3 + 77
+    net = tcnn.Network(n_in, n_out, dict(otype="FullyFusedMLP", activation="ReLU", output_activation=act,
+                                         n_neurons=64, n_hidden_layers=n_hidden)).cuda()
+    with torch.no_grad():
+        net.params.copy_(net.params.half().float())
+    g = torch.Generator(device="cuda").manual_seed(impl + 10)
+    x = (torch.randn(n, n_in, device="cuda", generator=g)).half().float().requires_grad_(True)
+    dy = torch.randn(n, n_out, device="cuda", generator=g)
+    old = _lib.lib().ncn_set_mlp_bwd_impl(impl)
+    try:
+        (net(x).float() * dy).sum().backward()
+    finally:
+        _lib.lib().ncn_set_mlp_bwd_impl(old)
+    xr = x.detach().clone().requires_grad_(True)
+    pr = net.params.detach().clone().requires_grad_(True)
+    refo = mlp.forward(xr, pr, n_in, n_out, n_hidden, act, emulate_half=True)
+    (refo.float() * dy.half().float()).sum().backward()
+    for got, want in ((x.grad, xr.grad), (net.params.grad, pr.grad)):
+        assert (got - want).norm() <= 1e-2 * want.norm() + 1e-5
+        assert (got - want).abs().max() <= 8e-2 * want.abs().max() + 1e-4
+
+
 NETS = [(32, 16, 1, "None"), (19, 3, 2, "Sigmoid"), (16, 3, 2, "None"), (16, 40, 2, "None"), (1, 1, 1, "Sigmoid")]
 
 
