@@ -89,6 +89,29 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
       : "r"(taddr));
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+// 32 accumulator columns of this thread's TMEM lane (no wait: pair with tmem_ld_wait)
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];\n"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+        "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+        "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+        "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// one lane of a converged warp (CUTLASS elect_one_sync): keeps the tcgen05 issue path on the uniform datapath
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n"
+      ".reg .pred px;\n"
+      "elect.sync _|px, 0xffffffff;\n"
+      "selp.b32 %0, 1, 0, px;\n"
+      "}\n" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
 }
@@ -130,6 +153,8 @@ __host__ __device__ constexpr uint32_t make_idesc_wgrad(int N) {      // A, B MN
 __host__ __device__ constexpr uint32_t make_idesc_dgrad(int N) {      // A K-major, B MN-major, M = 128
   return (1u << 4) | (1u << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 }
+// advance a descriptor's start address by `bytes` (address field = addr >> 4 in the low 14 bits; no carry out below 256 KB)
+__device__ __forceinline__ uint64_t desc_add(uint64_t desc, uint32_t bytes) { return desc + (uint64_t)(bytes >> 4); }
 constexpr int tmem_cols_pow2(int c) { return c <= 32 ? 32 : c <= 64 ? 64 : c <= 128 ? 128 : c <= 256 ? 256 : 512; }
 
 // ------------------------------------------------------------------ staging helpers
@@ -281,6 +306,7 @@ mlp_bwd_tc05_kernel(const __half* __restrict__ x, const __half* __restrict__ w, 
   int* s_tile = reinterpret_cast<int*>(tmem_slot + 1);
 
   const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
+  const bool mma_warp = __shfl_sync(0xffffffffu, wid, 0) == 0;      // provably warp-uniform: the issue path stays on the uniform datapath
   const int64_t n_tiles = (n + kTile - 1) / kTile;
   const int64_t layer_stride = act_rows(n_cap) * 64;
   const bool perm_in = (src.perm & 1) != 0;
@@ -361,20 +387,25 @@ mlp_bwd_tc05_kernel(const __half* __restrict__ x, const __half* __restrict__ w, 
     __syncthreads();
     const uint32_t acc0 = it > 0 ? 1u : 0u;
     int after_next = 0;
+    if (mma_warp) {
+      if (elect_one()) {
+        tc_fence_after();
+        // dgrad: D = dz_last * W_last ; wgrad: dW_last^T += act_{NH-1}^T * dz_last
+        const uint64_t a_k = make_desc_k(P_dzl), b_w = make_desc_w(WBl, OUT);
+#pragma unroll
+        for (int ks = 0; ks < OUT / 16; ++ks)
+          tc_mma_f16(tmem_d, desc_add(a_k, ks * 2 * kTile * 16), desc_add(b_w, ks * 256), make_idesc_dgrad(64), ks > 0 ? 1u : 0u);
+        const uint64_t a_mn = make_desc_mn(P_act + (size_t)(NH - 1) * 64 * kTile), b_mn = make_desc_mn(P_dzl);
+#pragma unroll
+        for (int ks = 0; ks < kTile / 16; ++ks)
+          tc_mma_f16(tmem_w + IN + 64 * (NH - 1), desc_add(a_mn, ks * 256), desc_add(b_mn, ks * 256), make_idesc_wgrad(OUT), ks > 0 ? 1u : acc0);
+        tc_commit(mbar_d);
+      }
+      __syncwarp();
+    }
     if (tid == 0) {
       after_next = atomicAdd(tile_counter, 1);                 // the tile after next; consumed at the end of the chain
       if (nxt < n_tiles) fetch_acts(nxt, set ^ 1);             // the other set's last readers (previous tile) were waited for
-      tc_fence_after();
-      // dgrad: D = dz_last * W_last ; wgrad: dW_last^T += act_{NH-1}^T * dz_last
-#pragma unroll
-      for (int ks = 0; ks < OUT / 16; ++ks)
-        tc_mma_f16(tmem_d, make_desc_k(P_dzl + (size_t)ks * 2 * kTile * 8), make_desc_w(WBl + (size_t)ks * 16 * 8, OUT),
-                   make_idesc_dgrad(64), ks > 0 ? 1u : 0u);
-#pragma unroll
-      for (int ks = 0; ks < kTile / 16; ++ks)
-        tc_mma_f16(tmem_w + IN + 64 * (NH - 1), make_desc_mn(P_act + (size_t)(NH - 1) * 64 * kTile + (size_t)ks * 16 * 8),
-                   make_desc_mn(P_dzl + (size_t)ks * 16 * 8), make_idesc_wgrad(OUT), ks > 0 ? 1u : acc0);
-      tc_commit(mbar_d);
     }
     NCN_TRACE(3);
     // prefetch the next tile's x rows (cp.async) and dL/dout row (registers)
@@ -391,24 +422,28 @@ mlp_bwd_tc05_kernel(const __half* __restrict__ x, const __half* __restrict__ w, 
       NCN_TRACE(5 + 3 * i);
       tc_fence_after();
       __half* Pz = P_act + (size_t)i * 64 * kTile;
+      {
+        uint32_t v0[32], v1[32];                               // the whole 64-column accumulator row: two loads in flight, one wait
+        tmem_ld32_nowait(my_lane, v0);
+        tmem_ld32_nowait(my_lane + 32, v1);
+        uint4 am[8];
 #pragma unroll
-      for (int c0 = 0; c0 < 64; c0 += 16) {
-        uint32_t v[16];
-        tmem_ld16(my_lane + c0, v);
-        uint4* q0 = reinterpret_cast<uint4*>(Pz + ((size_t)(c0 / 8) * kTile + tid) * 8);
-        uint4* q1 = reinterpret_cast<uint4*>(Pz + ((size_t)(c0 / 8 + 1) * kTile + tid) * 8);
-        const uint4 a0 = *q0, a1 = *q1;
-        const uint32_t am[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-        uint32_t o[8];
+        for (int c = 0; c < 8; ++c) am[c] = *reinterpret_cast<const uint4*>(Pz + ((size_t)c * kTile + tid) * 8);
+        tmem_ld_wait();
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const __half2 gate = __hgt2(*reinterpret_cast<const __half2*>(&am[q]), __float2half2_rn(0.f));     // 1.0 / 0.0
-          const uint32_t pk = pack_half2(__uint_as_float(v[2 * q]), __uint_as_float(v[2 * q + 1]));
-          const __half2 r = __hmul2(*reinterpret_cast<const __half2*>(&pk), gate);
-          o[q] = *reinterpret_cast<const uint32_t*>(&r);
+        for (int c = 0; c < 8; ++c) {
+          const uint32_t* v = (c < 4 ? v0 : v1) + (c & 3) * 8;
+          const uint32_t a4[4] = {am[c].x, am[c].y, am[c].z, am[c].w};
+          uint32_t o[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const __half2 gate = __hgt2(*reinterpret_cast<const __half2*>(&a4[q]), __float2half2_rn(0.f));     // 1.0 / 0.0
+            const uint32_t pk = pack_half2(__uint_as_float(v[2 * q]), __uint_as_float(v[2 * q + 1]));
+            const __half2 r = __hmul2(*reinterpret_cast<const __half2*>(&pk), gate);
+            o[q] = *reinterpret_cast<const uint32_t*>(&r);
+          }
+          *reinterpret_cast<uint4*>(Pz + ((size_t)c * kTile + tid) * 8) = make_uint4(o[0], o[1], o[2], o[3]);
         }
-        *q0 = make_uint4(o[0], o[1], o[2], o[3]);
-        *q1 = make_uint4(o[4], o[5], o[6], o[7]);
       }
       NCN_TRACE(6 + 3 * i);
       if (i == 0 && tid == 0) *s_tile = after_next + (int)gridDim.x;
@@ -416,29 +451,33 @@ mlp_bwd_tc05_kernel(const __half* __restrict__ x, const __half* __restrict__ w, 
       tc_fence_before();
       __syncthreads();
       NCN_TRACE(7 + 3 * i);
-      if (tid == 0) {
-        tc_fence_after();
-        if (i > 0) {
-#pragma unroll
-          for (int ks = 0; ks < 4; ++ks)
-            tc_mma_f16(tmem_d, make_desc_k(Pz + (size_t)ks * 2 * kTile * 8), make_desc_w(WBh + (size_t)(i - 1) * 64 * 64 + (size_t)ks * 16 * 8, 64),
-                       make_idesc_dgrad(64), ks > 0 ? 1u : 0u);
-#pragma unroll
-          for (int ks = 0; ks < kTile / 16; ++ks)
-            tc_mma_f16(tmem_w + IN + 64 * (i - 1), make_desc_mn(Pz + (size_t)ks * 16 * 8),
-                       make_desc_mn(P_act + (size_t)(i - 1) * 64 * kTile + (size_t)ks * 16 * 8), make_idesc_wgrad(64), ks > 0 ? 1u : acc0);
-        } else {
-          if (dx) {
+      if (mma_warp) {
+        if (elect_one()) {
+          tc_fence_after();
+          const uint64_t a_k = make_desc_k(Pz), a_mn = make_desc_mn(Pz);
+          if (i > 0) {
+            const uint64_t b_w = make_desc_w(WBh + (size_t)(i - 1) * 64 * 64, 64), b_mn = make_desc_mn(P_act + (size_t)(i - 1) * 64 * kTile);
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks)
-              tc_mma_f16(tmem_d, make_desc_k(Pz + (size_t)ks * 2 * kTile * 8), make_desc_w(WB0 + (size_t)ks * 16 * 8, 64),
-                         make_idesc_dgrad(IN), ks > 0 ? 1u : 0u);
-          }
+              tc_mma_f16(tmem_d, desc_add(a_k, ks * 2 * kTile * 16), desc_add(b_w, ks * 256), make_idesc_dgrad(64), ks > 0 ? 1u : 0u);
 #pragma unroll
-          for (int ks = 0; ks < kTile / 16; ++ks)
-            tc_mma_f16(tmem_w, make_desc_mn(Pz + (size_t)ks * 16 * 8), make_desc_mn(P_x + (size_t)ks * 16 * 8), make_idesc_wgrad(IN), ks > 0 ? 1u : acc0);
+            for (int ks = 0; ks < kTile / 16; ++ks)
+              tc_mma_f16(tmem_w + IN + 64 * (i - 1), desc_add(a_mn, ks * 256), desc_add(b_mn, ks * 256), make_idesc_wgrad(64), ks > 0 ? 1u : acc0);
+          } else {
+            if (dx) {
+              const uint64_t b_w = make_desc_w(WB0, 64);
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks)
+                tc_mma_f16(tmem_d, desc_add(a_k, ks * 2 * kTile * 16), desc_add(b_w, ks * 256), make_idesc_dgrad(IN), ks > 0 ? 1u : 0u);
+            }
+            const uint64_t b_mn = make_desc_mn(P_x);
+#pragma unroll
+            for (int ks = 0; ks < kTile / 16; ++ks)
+              tc_mma_f16(tmem_w, desc_add(a_mn, ks * 256), desc_add(b_mn, ks * 256), make_idesc_wgrad(IN), ks > 0 ? 1u : acc0);
+          }
+          tc_commit(mbar_d);
         }
-        tc_commit(mbar_d);
+        __syncwarp();
       }
     }
     // (2) dL/dx rows; the wait also retires the last reads of this panel set
@@ -446,16 +485,29 @@ mlp_bwd_tc05_kernel(const __half* __restrict__ x, const __half* __restrict__ w, 
     NCN_TRACE(11);
     tc_fence_after();
     if (dx) {
-#pragma unroll
-      for (int c0 = 0; c0 < IN; c0 += 16) {
-        uint32_t v[16];
-        tmem_ld16(my_lane + c0, v);
+      if constexpr (IN == 32) {
+        uint32_t v[32];
+        tmem_ld32_nowait(my_lane, v);
+        tmem_ld_wait();
         if (row < n) {
-          uint32_t o[8];
 #pragma unroll
-          for (int q = 0; q < 8; ++q) o[q] = pack_half2(__uint_as_float(v[2 * q]), __uint_as_float(v[2 * q + 1]));
-          *reinterpret_cast<uint4*>(dx + row * IN + c0) = make_uint4(o[0], o[1], o[2], o[3]);
-          *reinterpret_cast<uint4*>(dx + row * IN + c0 + 8) = make_uint4(o[4], o[5], o[6], o[7]);
+          for (int c = 0; c < 4; ++c)
+            *reinterpret_cast<uint4*>(dx + row * IN + c * 8) =
+                make_uint4(pack_half2(__uint_as_float(v[8 * c]), __uint_as_float(v[8 * c + 1])), pack_half2(__uint_as_float(v[8 * c + 2]), __uint_as_float(v[8 * c + 3])),
+                           pack_half2(__uint_as_float(v[8 * c + 4]), __uint_as_float(v[8 * c + 5])), pack_half2(__uint_as_float(v[8 * c + 6]), __uint_as_float(v[8 * c + 7])));
+        }
+      } else {
+#pragma unroll
+        for (int c0 = 0; c0 < IN; c0 += 16) {
+          uint32_t v[16];
+          tmem_ld16(my_lane + c0, v);
+          if (row < n) {
+            uint32_t o[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) o[q] = pack_half2(__uint_as_float(v[2 * q]), __uint_as_float(v[2 * q + 1]));
+            *reinterpret_cast<uint4*>(dx + row * IN + c0) = make_uint4(o[0], o[1], o[2], o[3]);
+            *reinterpret_cast<uint4*>(dx + row * IN + c0 + 8) = make_uint4(o[4], o[5], o[6], o[7]);
+          }
         }
       }
       tc_fence_before();     // the next tile's first MMA overwrites the dgrad tile this thread just read
