@@ -39,13 +39,17 @@ __device__ __forceinline__ uint32_t grid_index(uint32_t gx, uint32_t gy, uint32_
   return index % size;
 }
 
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
 struct Cell8 {
   uint32_t idx[8];
   float w[3];       // fractional position
 };
 
 __device__ __forceinline__ void locate8(const float* __restrict__ x, int64_t n, float scale, uint32_t res, uint32_t size,
-                                        Cell8& c, const GridXform& xf) {
+                                        Cell8& c, const GridXform& xf, uint32_t* cell = nullptr) {
   uint32_t g[3];
 #pragma unroll
   for (int d = 0; d < 3; ++d) {
@@ -59,6 +63,7 @@ __device__ __forceinline__ void locate8(const float* __restrict__ x, int64_t n, 
 #pragma unroll
   for (int k = 0; k < 8; ++k)
     c.idx[k] = grid_index(g[0] + (k & 1), g[1] + ((k >> 1) & 1), g[2] + ((k >> 2) & 1), res, size);
+  if (cell) { cell[0] = g[0] | (g[1] << 16); cell[1] = g[2]; }
 }
 
 __device__ __forceinline__ float corner_w(const float* w, int k) {
@@ -210,9 +215,36 @@ grid_bwd_kernel(const __grid_constant__ GridMeta meta, const float* __restrict__
 // Parameter-gradient scatter with warp-level run merging (F = 2).
 // Samples arrive in ray order, 1.7e-3 apart, so at the coarse levels dozens of consecutive samples fall in the same
 // cell and would issue dozens of same-address reductions (which the L2 atomic unit serialises).  Here a warp takes 32
-// CONSECUTIVE samples of ONE level; per corner, lanes that hit the same entry as their left neighbour form a run, the
-// run is summed with a warp prefix scan, and only the head lane issues the red.global.add.v2.f32.  Warps whose
-// samples are not coherent at this level (fine / hashed levels) detect that with one ballot and take the direct path.
+// CONSECUTIVE samples of ONE level; lanes in the same grid cell as their left neighbour form a run (found once per
+// sample, not per corner), each corner's contributions are summed over the run with a windowed warp prefix scan whose
+// depth follows the average run length, and only the head lane issues the red.global.add.v2.f32.  Warps whose samples
+// are not coherent at this level (fine / hashed levels) detect that with one ballot and take the direct path.
+// segmented sums of the 8 corner contributions over runs of lanes in the same cell; runs are cut at W-lane windows so
+// the prefix scan needs log2(W) steps.  `heads` already contains the window starts.
+template <int W>
+__device__ __forceinline__ void merge_corners(const Cell8& c, bool valid, float g0, float g1, unsigned heads, int lane, float2* __restrict__ gl) {
+  const bool head = (heads >> lane) & 1u;
+  const unsigned later = lane < 31 ? (heads >> (lane + 1)) : 0u;
+  const int end = later ? lane + __ffs(later) - 1 : 31;          // last lane of this lane's run (inside the window)
+  const int wl = lane & (W - 1);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const float wk = valid ? corner_w(c.w, k) : 0.f;
+    float vx = wk * g0, vy = wk * g1;
+#pragma unroll
+    for (int o = 1; o < W; o <<= 1) {                            // inclusive prefix sums inside the window
+      const float tx = __shfl_up_sync(0xffffffffu, vx, o), ty = __shfl_up_sync(0xffffffffu, vy, o);
+      if (wl >= o) { vx += tx; vy += ty; }
+    }
+    const float ex = __shfl_sync(0xffffffffu, vx, end), ey = __shfl_sync(0xffffffffu, vy, end);
+    const float bx = __shfl_up_sync(0xffffffffu, vx, 1), by = __shfl_up_sync(0xffffffffu, vy, 1);
+    if (head && valid) {
+      const float sx = ex - (wl > 0 ? bx : 0.f), sy = ey - (wl > 0 ? by : 0.f);
+      if (sx != 0.f || sy != 0.f) atomicAdd(gl + c.idx[k], make_float2(sx, sy));
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256)
 grid_bwd_merge_kernel(const __grid_constant__ GridMeta meta, const float* __restrict__ x, const __half* __restrict__ dy,
                       int64_t n_cap, const int32_t* __restrict__ n_dev, GridXform xf, float grad_scale, float* __restrict__ grad) {
@@ -240,50 +272,44 @@ grid_bwd_merge_kernel(const __grid_constant__ GridMeta meta, const float* __rest
     const bool live = valid && (g0 != 0.f || g1 != 0.f);
     if (__ballot_sync(0xffffffffu, live) == 0u) continue;      // e.g. samples behind an early-terminated ray
     Cell8 c;
-    if (valid) locate8(x, s, sm.scale[l], sm.res[l], sm.size[l], c, xf);
+    uint32_t cell[2] = {0xFFFFFFFFu, 0xFFFFFFFFu};
+    if (valid) locate8(x, s, sm.scale[l], sm.res[l], sm.size[l], c, xf, cell);
     else {
 #pragma unroll
       for (int k = 0; k < 8; ++k) c.idx[k] = 0xFFFFFFFFu;
       c.w[0] = c.w[1] = c.w[2] = 0.f;
     }
     float2* gl = reinterpret_cast<float2*>(grad) + sm.offset[l];
-    // coherence probe on corner 0
-    const uint32_t prev0 = __shfl_up_sync(0xffffffffu, c.idx[0], 1);
-    const unsigned same = __ballot_sync(0xffffffffu, lane > 0 && c.idx[0] == prev0 && valid);
-    if (__popc(same) < 8) {
+    // runs of consecutive samples in the SAME cell share all 8 table entries (exact: compared on the integer cell)
+    const uint32_t pa = __shfl_up_sync(0xffffffffu, cell[0], 1), pb = __shfl_up_sync(0xffffffffu, cell[1], 1);
+    const unsigned heads0 = __ballot_sync(0xffffffffu, lane == 0 || cell[0] != pa || cell[1] != pb || !valid);
+    const int nh = __popc(heads0);
+    if (nh > 20) {                                              // incoherent at this level (fine / hashed): direct path
       if (live) {
+        // corners k and k+1 differ in x only.  For an even cell x the two entries are neighbours in the dense layout AND
+        // in the hashed one (x enters the hash with multiplier 1, so x ^ h and (x+1) ^ h differ in bit 0 only): one
+        // 16-byte reduction instead of two 8-byte ones
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const float wk = corner_w(c.w, k);
-          atomicAdd(gl + c.idx[k], make_float2(wk * g0, wk * g1));
+        for (int k = 0; k < 8; k += 2) {
+          const float w0 = corner_w(c.w, k), w1 = corner_w(c.w, k + 1);
+          const uint32_t i0 = c.idx[k], i1 = c.idx[k + 1];
+          if ((i0 ^ i1) == 1u) {
+            const uint32_t lo = i0 & ~1u;
+            const bool sw = (i0 & 1u) != 0;                     // hashed: the pair may come out swapped
+            red_add_v4(reinterpret_cast<float*>(gl + lo), (sw ? w1 : w0) * g0, (sw ? w1 : w0) * g1, (sw ? w0 : w1) * g0, (sw ? w0 : w1) * g1);
+          } else {
+            atomicAdd(gl + i0, make_float2(w0 * g0, w0 * g1));
+            atomicAdd(gl + i1, make_float2(w1 * g0, w1 * g1));
+          }
         }
       }
       continue;
     }
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const float wk = valid ? corner_w(c.w, k) : 0.f;
-      float vx = wk * g0, vy = wk * g1;
-      const uint32_t idx = c.idx[k];
-      const uint32_t prev = __shfl_up_sync(0xffffffffu, idx, 1);
-      const bool head = (lane == 0) || (idx != prev);
-      const unsigned heads = __ballot_sync(0xffffffffu, head);
-      // inclusive prefix sums over the warp
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const float tx = __shfl_up_sync(0xffffffffu, vx, o), ty = __shfl_up_sync(0xffffffffu, vy, o);
-        if (lane >= o) { vx += tx; vy += ty; }
-      }
-      // run [lane, end]: end = position of the next head - 1
-      const unsigned later = lane < 31 ? (heads >> (lane + 1)) : 0u;
-      const int end = later ? lane + __ffs(later) - 1 : 31;
-      const float ex = __shfl_sync(0xffffffffu, vx, end), ey = __shfl_sync(0xffffffffu, vy, end);
-      const float bx = __shfl_up_sync(0xffffffffu, vx, 1), by = __shfl_up_sync(0xffffffffu, vy, 1);
-      if (head && valid) {
-        const float sx = ex - (lane > 0 ? bx : 0.f), sy = ey - (lane > 0 ? by : 0.f);
-        if (sx != 0.f || sy != 0.f) atomicAdd(gl + idx, make_float2(sx, sy));
-      }
-    }
+    // window = about twice the average run: short scans where runs are short, whole-warp sums on the coarse levels
+    if (nh <= 2) merge_corners<32>(c, valid, g0, g1, heads0 | 0x00000001u, lane, gl);
+    else if (nh <= 4) merge_corners<16>(c, valid, g0, g1, heads0 | 0x00010001u, lane, gl);
+    else if (nh <= 10) merge_corners<8>(c, valid, g0, g1, heads0 | 0x01010101u, lane, gl);
+    else merge_corners<4>(c, valid, g0, g1, heads0 | 0x11111111u, lane, gl);
   }
 }
 
@@ -448,7 +474,7 @@ extern "C" int ncn_grid_bwd(const ncn_grid_desc* desc, const float* x, const voi
   NCN_CHECK_PTR(x); NCN_CHECK_PTR(dy); NCN_CHECK_PTR(grad);
   if ((uintptr_t)grad & 7) return NCN_E_ALIGN;
   const int grid = persistent_grid(n * m.n_levels, 256, 8);
-  if (desc->n_features == 2 && g_grid_bwd_merge) {
+  if (desc->n_features == 2 && g_grid_bwd_merge && ((uintptr_t)grad & 15) == 0) {      // 16-byte paired reductions
     grid_bwd_merge_kernel<<<grid, 256, 0, as_stream(stream)>>>(m, x, (const __half*)dy, n, n_dev, make_xform(xform_host), grad_scale, grad);
     NCN_LAUNCH_OK();
     return NCN_OK;
