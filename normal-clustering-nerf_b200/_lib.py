@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libncn.so")
+LIB_PATH = os.environ.get("NCN_LIB_PATH") or os.path.join(_HERE, "libncn.so")      # override: developer A/B builds only
 _lib = None
 
 c_i64, c_i32, c_f32, c_vp, c_sz = C.c_int64, C.c_int, C.c_float, C.c_void_p, C.c_size_t

@@ -96,7 +96,7 @@ normals_bw_kernel(const float* __restrict__ origin, const float* __restrict__ di
 // integer reduction (redux.sync; fixed point 2^20 => order independent => bit-reproducible), publishes its K x 4
 // partial sums in its own shared memory, and after one barrier.cluster every CTA folds all 8 partials through
 // distributed shared memory and updates the (replicated) centroids.  No atomics, no host round trip.
-constexpr int kKmThreads = 256;
+constexpr int kKmThreads = 256;     // (512 threads: same iteration time - the tile phase is issue bound, not latency bound)
 constexpr int kKmCluster = 8;
 constexpr int kKmMaxK = 64;
 constexpr float kKmFix = 1048576.0f;     // 2^20
@@ -174,6 +174,32 @@ __device__ __forceinline__ float centroid_row(const float* __restrict__ c, int r
   return (row >= 3 && row < 6) ? lo : hi;
 }
 
+#ifdef NCN_KM_TRACE      // developer build only
+__device__ long long g_km_trace[64];
+#define KM_TRACE(slot) do { if (threadIdx.x == 0 && cluster_ctarank() == 0) g_km_trace[slot] = clock64(); } while (0)
+#else
+#define KM_TRACE(slot) do { } while (0)
+#endif
+
+// empty clusters split the currently largest one (faiss-style +-eps); rare, one thread
+__device__ __forceinline__ void split_empty_clusters(float* __restrict__ s_c, float* __restrict__ s_acc, int K) {
+  for (int j = 0; j < K; ++j) {
+    if (s_acc[4 * j + 3] == 0.f) {
+      int big = 0;
+      for (int q = 1; q < K; ++q) if (s_acc[4 * q + 3] > s_acc[4 * big + 3]) big = q;
+      const float eps = 1.0f / 1024.0f;
+      for (int d = 0; d < 3; ++d) {
+        const float v = s_c[3 * big + d];
+        const float sgn = (d & 1) ? -1.f : 1.f;
+        s_c[3 * j + d] = v * (1.f + sgn * eps);
+        s_c[3 * big + d] = v * (1.f - sgn * eps);
+      }
+      const float half = floorf(s_acc[4 * big + 3] * 0.5f);
+      s_acc[4 * j + 3] = half; s_acc[4 * big + 3] -= half;
+    }
+  }
+}
+
 __global__ void __cluster_dims__(kKmCluster, 1, 1) __launch_bounds__(kKmThreads, 1)
 kmeans_kernel(const float* __restrict__ x, int64_t n, ncn_kmeans_params p, float* __restrict__ centroids,
               int32_t* __restrict__ assign, int32_t* __restrict__ n_valid_out, int32_t* __restrict__ valid_idx,
@@ -190,31 +216,47 @@ kmeans_kernel(const float* __restrict__ x, int64_t n, ncn_kmeans_params p, float
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int K = p.k;
   const uint32_t rank = cluster_ctarank();
-  // 1) every CTA compacts the valid rows (stable order) - identical results, CTA 0 publishes them
-  if (tid == 0) { s_base = 0; }
-  __syncthreads();
-  for (int64_t b0 = 0; b0 < n; b0 += kKmThreads) {
-    const int64_t i = b0 + tid;
-    bool v = false;
-    if (i < n) v = valid_normal(x[3 * i], x[3 * i + 1], x[3 * i + 2]);
-    const unsigned bal = __ballot_sync(0xffffffffu, v);
-    if (lane == 0) s_warp_tot[wid] = __popc(bal);
+  KM_TRACE(0);
+  // 1) every CTA compacts the valid rows (stable order) - identical results, CTA 0 publishes them.  Warp w owns a
+  //    contiguous slice of rows, walked in chunks of 32 x 32 rows whose validity bits a lane gathers with independent
+  //    (pipelined) loads: count, one block-wide exclusive scan of the 8 warp totals, then write.
+  {
+    const int64_t per_warp = (((n + (kKmThreads / 32) - 1) / (kKmThreads / 32)) + 31) & ~(int64_t)31;
+    const int64_t r_begin = (int64_t)wid * per_warp, r_end = r_begin + per_warp < n ? r_begin + per_warp : n;
+    auto chunk_mask = [&](int64_t c0) -> uint32_t {            // bit b: row c0 + 32*b + lane is a valid normal
+      uint32_t vm = 0u;
+#pragma unroll 8
+      for (int b = 0; b < 32; ++b) {
+        const int64_t i = c0 + 32 * b + lane;
+        if (i < r_end && valid_normal(x[3 * i], x[3 * i + 1], x[3 * i + 2])) vm |= 1u << b;
+      }
+      return vm;
+    };
+    int cnt = 0;
+    for (int64_t c0 = r_begin; c0 < r_end; c0 += 1024) cnt += __popc(chunk_mask(c0));
+    cnt = warp_sum_i(cnt);
+    if (lane == 0) s_warp_tot[wid] = cnt;
     __syncthreads();
-    if (wid == 0) {
-      const int w = lane < kKmThreads / 32 ? s_warp_tot[lane] : 0;
-      const int inc = warp_scan_incl_i(w, lane);
-      if (lane < kKmThreads / 32) s_warp_tot[lane] = inc - w;
-      if (lane == 31) s_nvalid = inc;
-    }
-    __syncthreads();
+    int base = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < kKmThreads / 32; ++w) { const int c = s_warp_tot[w]; if (w < wid) base += c; total += c; }
     if (rank == 0) {
-      if (v) valid_idx[s_base + s_warp_tot[wid] + __popc(bal & ((1u << lane) - 1))] = (int32_t)i;
-      if (i < n && !v) assign[i] = -1;
+      for (int64_t c0 = r_begin; c0 < r_end; c0 += 1024) {
+        const uint32_t vm = chunk_mask(c0);
+        for (int b = 0; b < 32 && c0 + 32 * b < r_end; ++b) {
+          const int64_t i = c0 + 32 * b + lane;
+          const bool v = (vm >> b) & 1u;
+          const unsigned bal = __ballot_sync(0xffffffffu, v);
+          if (v) valid_idx[base + __popc(bal & ((1u << lane) - 1))] = (int32_t)i;
+          else if (i < r_end) assign[i] = -1;
+          base += __popc(bal);
+        }
+      }
     }
-    __syncthreads();
-    if (tid == 0) s_base += s_nvalid;
+    if (tid == 0) s_base = total;
     __syncthreads();
   }
+  KM_TRACE(1);
   const int nv = s_base;
   if (rank == 0 && tid == 0) *n_valid_out = nv;
   if (nv == 0) {
@@ -223,6 +265,7 @@ kmeans_kernel(const float* __restrict__ x, int64_t n, ncn_kmeans_params p, float
   }
   __threadfence();
   cluster_sync_all();               // valid_idx (written by CTA 0) is visible to the whole cluster
+  KM_TRACE(2);
   // 2) training subset: at most max_points_per_centroid*K points at a uniform stride over the valid rows (faiss draws a
   //    random subset; equality with faiss is not a parity criterion); CTA r owns training points r, r+8, r+16, ...
   const int nt = nv > nt_cap ? nt_cap : nv;
@@ -262,7 +305,9 @@ kmeans_kernel(const float* __restrict__ x, int64_t n, ncn_kmeans_params p, float
     }
     __syncthreads();
   }
+  KM_TRACE(3);
   for (int it = 0; it < p.niter; ++it) {
+    if (it < 4) KM_TRACE(8 + 8 * it);
     if (use_tc) {
       uint32_t cb[4][2];        // centroid fragments: clusters 8j+g, rows 2t,2t+1 / 2t+8,2t+9 of the expanded column
 #pragma unroll
@@ -326,6 +371,7 @@ kmeans_kernel(const float* __restrict__ x, int64_t n, ncn_kmeans_params p, float
           mma16816(acc[mt], oh, pq[0], pq[1]);
         }
       }
+      if (it < 4) KM_TRACE(9 + 8 * it);
 #pragma unroll
       for (int mt = 0; mt < 2; ++mt) {
         float* row0 = s_fw + ((size_t)wid * 32 + g + 16 * mt) * 8 + 2 * t;
@@ -334,26 +380,51 @@ kmeans_kernel(const float* __restrict__ x, int64_t n, ncn_kmeans_params p, float
       }
       __syncthreads();
       float* fpart = s_fpart[it & 1];
-      {
+      if (tid < 256) {
         float tot = 0.f;                                          // 256 threads <-> 32 clusters x 8 columns, fixed order
 #pragma unroll
         for (int w = 0; w < kKmThreads / 32; ++w) tot += s_fw[(size_t)w * 256 + tid];
         fpart[tid] = tot;
       }
+      if (it < 4) KM_TRACE(10 + 8 * it);
       cluster_sync_all();
-      {
+      if (it < 4) KM_TRACE(11 + 8 * it);
+      if (tid < 256) {
         float tot = 0.f;
 #pragma unroll
         for (uint32_t r = 0; r < kKmCluster; ++r) tot += dsmem_ld_float(fpart + tid, r);
         s_fw[tid] = tot;                                          // cluster total of (cluster tid/8, column tid%8)
       }
-      if (tid == 0) s_any_empty = 0;
+      if (it < 4) KM_TRACE(12 + 8 * it);
       __syncthreads();
-      if (tid < K) {
-        const float* r = s_fw + tid * 8;
-        s_acc[4 * tid] = r[0] + r[3]; s_acc[4 * tid + 1] = r[1] + r[4]; s_acc[4 * tid + 2] = r[2] + r[5]; s_acc[4 * tid + 3] = r[6];
+      if (it < 4) KM_TRACE(13 + 8 * it);
+      // centroid update by warp 0 alone (K <= 32: one lane per cluster) - warp-level syncs only
+      if (wid == 0) {
+        if (lane < K) {
+          const float* r = s_fw + lane * 8;
+          s_acc[4 * lane] = r[0] + r[3]; s_acc[4 * lane + 1] = r[1] + r[4]; s_acc[4 * lane + 2] = r[2] + r[5]; s_acc[4 * lane + 3] = r[6];
+        }
+        __syncwarp();
+        bool empty = false;
+        if (lane < K) {
+          const float c = s_acc[4 * lane + 3];
+          if (c > 0.f) { s_c[3 * lane] = s_acc[4 * lane] / c; s_c[3 * lane + 1] = s_acc[4 * lane + 1] / c; s_c[3 * lane + 2] = s_acc[4 * lane + 2] / c; }
+          else empty = true;
+        }
+        const unsigned any_empty = __ballot_sync(0xffffffffu, empty);
+        if (any_empty) {
+          __syncwarp();
+          if (lane == 0) split_empty_clusters(s_c, s_acc, K);
+          __syncwarp();
+        }
+        if (lane < K && p.spherical) {
+          const float l = sqrtf(s_c[3 * lane] * s_c[3 * lane] + s_c[3 * lane + 1] * s_c[3 * lane + 1] + s_c[3 * lane + 2] * s_c[3 * lane + 2]);
+          if (l > 0.f) { s_c[3 * lane] /= l; s_c[3 * lane + 1] /= l; s_c[3 * lane + 2] /= l; }
+        }
       }
+      if (it < 4) KM_TRACE(14 + 8 * it);
       __syncthreads();
+      continue;
     } else {
     int* wacc = s_wacc + wid * K * 4;
     for (int a = lane; a < K * 4; a += 32) wacc[a] = 0;
@@ -391,23 +462,7 @@ kmeans_kernel(const float* __restrict__ x, int64_t n, ncn_kmeans_params p, float
       else s_any_empty = 1;
     }
     __syncthreads();
-    if (tid == 0 && s_any_empty) {
-      for (int j = 0; j < K; ++j) {
-        if (s_acc[4 * j + 3] == 0.f) {
-          int big = 0;
-          for (int q = 1; q < K; ++q) if (s_acc[4 * q + 3] > s_acc[4 * big + 3]) big = q;
-          const float eps = 1.0f / 1024.0f;
-          for (int d = 0; d < 3; ++d) {
-            const float v = s_c[3 * big + d];
-            const float sgn = (d & 1) ? -1.f : 1.f;
-            s_c[3 * j + d] = v * (1.f + sgn * eps);
-            s_c[3 * big + d] = v * (1.f - sgn * eps);
-          }
-          const float half = floorf(s_acc[4 * big + 3] * 0.5f);
-          s_acc[4 * j + 3] = half; s_acc[4 * big + 3] -= half;
-        }
-      }
-    }
+    if (tid == 0 && s_any_empty) split_empty_clusters(s_c, s_acc, K);
     __syncthreads();
     if (tid < K && p.spherical) {
       const float l = sqrtf(s_c[3 * tid] * s_c[3 * tid] + s_c[3 * tid + 1] * s_c[3 * tid + 1] + s_c[3 * tid + 2] * s_c[3 * tid + 2]);
@@ -417,14 +472,22 @@ kmeans_kernel(const float* __restrict__ x, int64_t n, ncn_kmeans_params p, float
     // the partial buffer of iteration `it` is only overwritten in iteration it+2, i.e. after the barrier of it+1,
     // which every CTA reaches only after it finished reading buffer `it`
   }
+  KM_TRACE(4);
   cluster_sync_all();               // no CTA may exit while a peer can still read its shared memory
+  KM_TRACE(5);
   // 5) final assignment of every valid row (kmeans.index.search, losses.py:89), split over the cluster + centroids out
   for (int j = tid + (int)rank * kKmThreads; j < nv; j += kKmThreads * kKmCluster) {
     const int r = valid_idx[j];
     assign[r] = best_centroid(x[3 * r], x[3 * r + 1], x[3 * r + 2], s_c, K);
   }
   if (rank == 0) for (int j = tid; j < K * 3; j += kKmThreads) centroids[j] = s_c[j];
+  KM_TRACE(6);
 }
+#ifdef NCN_KM_TRACE
+extern "C" int ncn_debug_km_trace(long long* host_dst) {
+  return cudaMemcpyFromSymbol(host_dst, g_km_trace, sizeof(long long) * 64) == cudaSuccess ? 0 : 1;
+}
+#endif
 
 // ---------------------------------------------------------------- orthogonal-triple selection (one CTA)
 __global__ void __launch_bounds__(1024, 1)
@@ -730,7 +793,8 @@ extern "C" int ncn_kmeans_spherical(const float* x, int64_t n_points, const ncn_
   if (cap > n_points) cap = n_points > 0 ? n_points : 1;
   const size_t per_cta = (size_t)(cap + kKmCluster - 1) / kKmCluster;
   const size_t smem = per_cta * 12 + 16 + (per_cta + 16) * 16 + 16;               // this CTA's points (fp32) + fp16 rows
-  if (smem > 48 * 1024) NCN_CUDA(cudaFuncSetAttribute(kmeans_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  // static (~38 KB) + dynamic shared memory crosses the 48 KB default limit: always opt in
+  NCN_CUDA(cudaFuncSetAttribute(kmeans_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kmeans_kernel<<<kKmCluster, kKmThreads, smem, as_stream(stream)>>>(x, n_points, *p, centroids, assign, n_valid, (int32_t*)workspace, (int)cap);
   NCN_LAUNCH_OK();
   return NCN_OK;
