@@ -135,6 +135,14 @@ ALGO = {  # algorithmic bytes (or flops) per unit, SURVEY.md section 8d / DESIGN
 }
 
 
+NOTES = {
+    "ncn_grid_bwd": "algorithmic bytes = x (12) + dL/dfeat (64) + 16 levels x 8 corners x 8 B of red.global.add (1024) per sample; the "
+                    "reductions are absorbed by the L2 atomic units (the 46 MB fp32 gradient stays L2-resident until Adam reads it), so "
+                    "DRAM traffic is far BELOW the algorithmic bytes and the limiter is L2 reduction transactions, not HBM",
+    "ncn_mlp_bwd_src_fused": "two launches per step (colour head 448 B/sample, density trunk 288 B/sample); average per launch",
+}
+
+
 def run_ours(args):
     import numpy as np
     import torch
@@ -286,8 +294,14 @@ def run_ours(args):
             units = n_params / 2.0
         achieved = per_unit * units / (avg_ms * 1e-3) / 1e9
         peak = float(peaks.get("hbm_gbs", 6650.0))
+        traffic = None
+        try:      # DRAM bytes per launch of this kernel from the committed ncu --set full capture (profiles/)
+            traffic = float(json.load(open(os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")))[top]["bytes_per_launch"])
+        except Exception:  # noqa: BLE001
+            pass
         roofline = {"kernel": top, "bound": bound, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": None, "avg_launch_ms": avg_ms, "launches_timed": calls,
+                    "traffic": traffic, "traffic_source": "profiles/r1_ncu_traffic.json (ncu --set full, dram read+write per launch)" if traffic else None,
+                    "note": NOTES.get(top), "avg_launch_ms": avg_ms, "launches_timed": calls,
                     "timed_in": "instrumented eager pass of the same step right after the timed region (CUDA events around the launch)",
                     "algorithmic_bytes_per_launch": per_unit * units,
                     "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"}
