@@ -16,42 +16,55 @@ __device__ __forceinline__ int64_t live_rows(int64_t n_cap, const int32_t* __res
   return n;
 }
 
+// thread per sample: two 16-byte loads of h, the direction, four 16-byte stores of the 32-wide row
+//   x = [d/|d| (3) | h (16) | 1.0 x 13]:  32-bit words X0=(d0,d1) X1=(d2,h0) X_j=(h_{2j-3},h_{2j-2}) j=2..8, X9=(h15,1), X10..15=(1,1)
 __global__ void __launch_bounds__(256)
 prepare_rgb_kernel(const float* __restrict__ dirs, const __half* __restrict__ h, int64_t n_cap,
                    const int32_t* __restrict__ n_dev, __half* __restrict__ x_rgb, float* __restrict__ sigmas) {
   const int64_t n = live_rows(n_cap, n_dev);
-  const int64_t total = n * 16, stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
-    const int64_t s = i >> 4;
-    const int c = (int)(i & 15);          // this thread writes columns 2c, 2c+1 of the 32-wide row
-    float v[2];
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < n; s += stride) {
+    const uint4 ha = *reinterpret_cast<const uint4*>(h + s * 16), hb = *reinterpret_cast<const uint4*>(h + s * 16 + 8);
+    const float dx = dirs[3 * s], dy = dirs[3 * s + 1], dz = dirs[3 * s + 2];
+    const float nrm = sqrtf(dx * dx + dy * dy + dz * dz);
+    const uint32_t w[8] = {ha.x, ha.y, ha.z, ha.w, hb.x, hb.y, hb.z, hb.w};
+    const __half2 d01 = __floats2half2_rn(dx / nrm, dy / nrm);
+    const __half d2 = __float2half_rn(dz / nrm);
+    uint32_t X[16];
+    X[0] = *reinterpret_cast<const uint32_t*>(&d01);
+    X[1] = (uint32_t)__half_as_ushort(d2) | (w[0] << 16);
 #pragma unroll
-    for (int q = 0; q < 2; ++q) {
-      const int col = 2 * c + q;
-      if (col < 3) {
-        const float dx = dirs[3 * s], dy = dirs[3 * s + 1], dz = dirs[3 * s + 2];
-        const float nrm = sqrtf(dx * dx + dy * dy + dz * dz);
-        v[q] = dirs[3 * s + col] / nrm;
-      } else if (col < 19) {
-        v[q] = __half2float(h[s * 16 + (col - 3)]);
-      } else {
-        v[q] = 1.0f;
-      }
-    }
-    reinterpret_cast<__half2*>(x_rgb)[i] = __floats2half2_rn(v[0], v[1]);
-    if (c == 0 && sigmas) sigmas[s] = expf(__half2float(h[s * 16]));
+    for (int q = 2; q <= 8; ++q) X[q] = __funnelshift_r(w[q - 2], w[q - 1], 16);
+    X[9] = (w[7] >> 16) | 0x3C000000u;                       // (h15, 1.0)
+#pragma unroll
+    for (int q = 10; q < 16; ++q) X[q] = 0x3C003C00u;        // (1.0, 1.0)
+    uint4* o = reinterpret_cast<uint4*>(x_rgb + s * 32);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) o[q] = make_uint4(X[4 * q], X[4 * q + 1], X[4 * q + 2], X[4 * q + 3]);
+    if (sigmas) sigmas[s] = expf(__half2float(__ushort_as_half((unsigned short)(w[0] & 0xFFFFu))));
   }
 }
 
+// thread per sample: the first n_ch (<= 8) halfs of the 16-byte-aligned head row -> fp32 columns of raws
 __global__ void __launch_bounds__(256)
 head_out_kernel(const __half* __restrict__ out, int out_pad, int64_t n_cap, const int32_t* __restrict__ n_dev,
                 float* __restrict__ raws, int c_total, int c_offset, int n_ch) {
   const int64_t n = live_rows(n_cap, n_dev);
-  const int64_t total = n * n_ch, stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
-    const int64_t s = i / n_ch;
-    const int j = (int)(i - s * n_ch);
-    raws[s * c_total + c_offset + j] = __half2float(out[s * out_pad + j]);
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < n; s += stride) {
+    float* r = raws + s * c_total + c_offset;
+    if (n_ch <= 8) {
+      const uint4 v = *reinterpret_cast<const uint4*>(out + s * out_pad);
+      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[q]));
+        if (2 * q < n_ch) r[2 * q] = f.x;
+        if (2 * q + 1 < n_ch) r[2 * q + 1] = f.y;
+      }
+    } else {
+      for (int j = 0; j < n_ch; ++j) r[j] = __half2float(out[s * out_pad + j]);
+    }
   }
 }
 
@@ -125,7 +138,8 @@ extern "C" int ncn_field_prepare_rgb(const float* dirs, const void* h_f16, int64
   NCN_CHECK_SIZE(n >= 0);
   if (n == 0) return NCN_OK;
   NCN_CHECK_PTR(dirs); NCN_CHECK_PTR(h_f16); NCN_CHECK_PTR(x_rgb_f16);
-  prepare_rgb_kernel<<<persistent_grid(n * 16, 256, 8), 256, 0, as_stream(stream)>>>(dirs, (const __half*)h_f16, n, n_dev,
+  if (((uintptr_t)h_f16 | (uintptr_t)x_rgb_f16) & 15) return NCN_E_ALIGN;
+  prepare_rgb_kernel<<<persistent_grid(n, 256, 8), 256, 0, as_stream(stream)>>>(dirs, (const __half*)h_f16, n, n_dev,
                                                                                      (__half*)x_rgb_f16, sigmas);
   NCN_LAUNCH_OK();
   return NCN_OK;
@@ -136,7 +150,8 @@ extern "C" int ncn_field_head_out(const void* out_f16, int out_pad, int64_t n, c
   NCN_CHECK_SIZE(n >= 0 && n_ch >= 1 && c_offset >= 0 && c_offset + n_ch <= c_total && n_ch <= out_pad);
   if (n == 0) return NCN_OK;
   NCN_CHECK_PTR(out_f16); NCN_CHECK_PTR(raws);
-  head_out_kernel<<<persistent_grid(n * n_ch, 256, 8), 256, 0, as_stream(stream)>>>((const __half*)out_f16, out_pad, n, n_dev, raws,
+  if (((uintptr_t)out_f16 & 15) || (out_pad & 7)) return NCN_E_ALIGN;
+  head_out_kernel<<<persistent_grid(n, 256, 8), 256, 0, as_stream(stream)>>>((const __half*)out_f16, out_pad, n, n_dev, raws,
                                                                                     c_total, c_offset, n_ch);
   NCN_LAUNCH_OK();
   return NCN_OK;
