@@ -29,18 +29,23 @@ __device__ __forceinline__ float warp_scan_incl_f(float v, int lane) {
   return v;
 }
 
-// Replays T *= (1-a_j) for j = 0..cnt-1 in order (uniform across the warp).
+// Replays T *= (1-a_j) for j = 0..31 in order (uniform across the warp; lanes past the ray's end carry 1-a = 1, which
+// leaves T bit-identical).  Fully unrolled: the 32 broadcasts are independent of the running product and pipeline, so the
+// serial part is the 32 dependent multiplies only (the rolled loop with an early break exposed a shuffle latency per
+// sample, which made the long rays - hundreds of samples - the tail of the whole kernel).
 // in : om = 1-a of this lane's sample, T = transmittance before the chunk
-// out: T_before for this lane's sample, T = transmittance after the processed part,
+// out: T_before for this lane's sample, T = transmittance after the chunk (unused once a stop was found),
 //      returns index of the terminating sample within the chunk or -1.
 __device__ __forceinline__ int replay_transmittance(float om, int cnt, float thr, float& T, float& T_before, int lane) {
+  (void)cnt;
   int stop = -1;
   T_before = T;
-  for (int j = 0; j < cnt; ++j) {
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
     const float omj = __shfl_sync(0xffffffffu, om, j);
     if (lane == j) T_before = T;
     T = __fmul_rn(T, omj);
-    if (T <= thr) { stop = j; break; }
+    if (stop < 0 && T <= thr) stop = j;
   }
   return stop;
 }
@@ -88,6 +93,77 @@ composite_train_fw_kernel(const float* __restrict__ sigmas, const float* __restr
     }
     if (lane == 0) { total_samples[ray_idx] = samples; opacity[ray_idx] = acc_o; depth[ray_idx] = acc_d; }
     for (int c = lane; c < C; c += 32) rend[ray_idx * C + c] = acc_r[c >> 5];
+  }
+}
+
+// Fast path for a compile-time channel count: every load of a chunk (sigma, delta, t, CT raws) is issued in ONE round,
+// and the next chunk's round is issued before the current chunk is processed, so a ray costs one exposed memory latency
+// plus ~300 clocks per 32 samples instead of (2 + CT) dependent latencies per chunk.
+template <int CT>
+__global__ void __launch_bounds__(256)
+composite_train_fw_ct_kernel(const float* __restrict__ sigmas, const float* __restrict__ raws,
+                             const float* __restrict__ deltas, const float* __restrict__ ts,
+                             const int64_t* __restrict__ rays_a, float thr, int64_t n_rays, int64_t capacity,
+                             int64_t* __restrict__ total_samples, float* __restrict__ opacity,
+                             float* __restrict__ depth, float* __restrict__ rend, float* __restrict__ ws) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t n = warp; n < n_rays; n += n_warps) {
+    const int64_t ray_idx = rays_a[3 * n], start = rays_a[3 * n + 1];
+    int64_t N64 = rays_a[3 * n + 2];
+    if (start + N64 > capacity) N64 = capacity > start ? capacity - start : 0;
+    const int N = (int)N64;
+    float T = 1.0f, acc_o = 0.f, acc_d = 0.f;
+    float acc_r[CT];
+#pragma unroll
+    for (int c = 0; c < CT; ++c) acc_r[c] = 0.f;
+    int samples = N;
+    bool dead = false;
+    float sg = 0.f, dl = 0.f, tt = 0.f, rw[CT];
+#pragma unroll
+    for (int c = 0; c < CT; ++c) rw[c] = 0.f;
+    auto fetch = [&](int base, float& o_sg, float& o_dl, float& o_tt, float (&o_rw)[CT]) {
+      const int k = base + lane;
+      o_sg = 0.f; o_dl = 0.f; o_tt = 0.f;
+#pragma unroll
+      for (int c = 0; c < CT; ++c) o_rw[c] = 0.f;
+      if (k < N) {
+        const int64_t s = start + k;
+        o_sg = sigmas[s]; o_dl = deltas[s]; o_tt = ts[s];
+#pragma unroll
+        for (int c = 0; c < CT; ++c) o_rw[c] = raws[s * CT + c];
+      }
+    };
+    if (N > 0) fetch(0, sg, dl, tt, rw);
+    for (int base = 0; base < N; base += 32) {
+      const int k = base + lane;
+      const int64_t s = start + k;
+      if (dead) { if (k < N) ws[s] = 0.f; continue; }
+      float n_sg = 0.f, n_dl = 0.f, n_tt = 0.f, n_rw[CT];
+#pragma unroll
+      for (int c = 0; c < CT; ++c) n_rw[c] = 0.f;
+      if (base + 32 < N) fetch(base + 32, n_sg, n_dl, n_tt, n_rw);
+      const float a = k < N ? __fsub_rn(1.0f, __expf(__fmul_rn(-sg, dl))) : 0.f;
+      float T_before;
+      const int stop = replay_transmittance(__fsub_rn(1.0f, a), 32, thr, T, T_before, lane);
+      const bool active = (k < N) && (stop < 0 || lane <= stop);
+      const float w = active ? __fmul_rn(a, T_before) : 0.f;
+      if (k < N) ws[s] = w;
+      acc_o += warp_sum(w);
+      acc_d += warp_sum(w * tt);
+#pragma unroll
+      for (int c = 0; c < CT; ++c) acc_r[c] += warp_sum(active ? w * rw[c] : 0.f);
+      if (stop >= 0) { samples = base + stop; dead = true; }
+      sg = n_sg; dl = n_dl; tt = n_tt;
+#pragma unroll
+      for (int c = 0; c < CT; ++c) rw[c] = n_rw[c];
+    }
+    if (lane == 0) {
+      total_samples[ray_idx] = samples; opacity[ray_idx] = acc_o; depth[ray_idx] = acc_d;
+#pragma unroll
+      for (int c = 0; c < CT; ++c) rend[ray_idx * CT + c] = acc_r[c];
+    }
   }
 }
 
@@ -204,6 +280,18 @@ extern "C" int ncn_composite_train_fw(const float* sigmas, const float* raws, co
     if (n_channels > 0) NCN_CHECK_PTR(raws);
   }
   const int grid = persistent_grid(n_rays * 32, 256, 8);
+  if (n_channels == 3) {
+    composite_train_fw_ct_kernel<3><<<grid, 256, 0, as_stream(stream)>>>(sigmas, raws, deltas, ts, rays_a, T_threshold, n_rays, capacity,
+                                                                         total_samples, opacity, depth, rend, ws);
+    NCN_LAUNCH_OK();
+    return NCN_OK;
+  }
+  if (n_channels == 6) {
+    composite_train_fw_ct_kernel<6><<<grid, 256, 0, as_stream(stream)>>>(sigmas, raws, deltas, ts, rays_a, T_threshold, n_rays, capacity,
+                                                                         total_samples, opacity, depth, rend, ws);
+    NCN_LAUNCH_OK();
+    return NCN_OK;
+  }
   composite_train_fw_kernel<<<grid, 256, 0, as_stream(stream)>>>(sigmas, raws, deltas, ts, rays_a, T_threshold, n_rays,
                                                                  capacity, n_channels, total_samples, opacity, depth,
                                                                  rend, ws);
