@@ -396,6 +396,15 @@ int ncn_cluster_loss_fw(const float* normals, const int32_t* labels, int64_t n_p
 int ncn_cluster_loss_bw(const float* normals, const int32_t* labels, int64_t n_points,
                         const float* stats, const float* weights_dev, float* dL_dnormals,
                         ncn_stream_t stream);
+/* ncn_cluster_select -> ncn_cluster_loss_fw -> ncn_cluster_loss_bw -> ncn_normals_from_depth_bw in ONE launch
+ * (one CTA; same arguments and results as the four calls, dL_ddepth accumulated into a caller-zeroed buffer):
+ * the step between the k-means result and the depth gradient of losses.py:441-509.  For small M where launch latency
+ * dominates; at M = 6272 the four launches (two of them multi-CTA) are as fast (measured 42 us vs 50 us eager). */
+int ncn_cluster_tail(const float* centroids, const int32_t* assign, int64_t n_points, int k, float t_similar,
+                     int32_t* labels, int32_t* sel, const float* normals, float* losses, float* stats,
+                     const float* weights_dev, float* dL_dnormals, const float* origin, const float* dir,
+                     const float* depth, const int64_t* idx1, const int64_t* idx2, const int64_t* idx3,
+                     float* dL_ddepth, ncn_stream_t stream);
 
 /* Photometric terms fused with the background composite (rendering.py:231-241,
  * losses.py:347-361): rgb = rend[:, :3] + bg*(1-opacity); sums[0] += sum((rgb-target)^2),

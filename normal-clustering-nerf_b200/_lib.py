@@ -189,6 +189,7 @@ SIGNATURES.update({
     "ncn_cluster_select": (c_i32, [c_vp, c_vp, c_i64, c_i32, c_f32, c_vp, c_vp, c_vp]),
     "ncn_cluster_loss_fw": (c_i32, [c_vp, c_vp, c_i64, c_vp, c_vp, c_vp]),
     "ncn_cluster_loss_bw": (c_i32, [c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp]),
+    "ncn_cluster_tail": (c_i32, [c_vp, c_vp, c_i64, c_i32, c_f32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "ncn_photometric_loss": (c_i32, [c_vp, c_vp, c_vp, c_i64, c_i32, C.POINTER(c_f32), c_f32, c_f32, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "ncn_adam_step": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_f32, c_f32, c_f32, c_f32, c_f32, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "ncn_set_mlp_bwd_impl": (c_i32, [c_i32]),

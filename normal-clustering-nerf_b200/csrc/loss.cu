@@ -45,12 +45,11 @@ normals_fw_kernel(const float* __restrict__ origin, const float* __restrict__ di
   }
 }
 
-__global__ void __launch_bounds__(256)
-normals_bw_kernel(const float* __restrict__ origin, const float* __restrict__ dir, const float* __restrict__ depth,
-                  const int64_t* __restrict__ i1, const int64_t* __restrict__ i2, const int64_t* __restrict__ i3,
-                  const float* __restrict__ dn, int64_t n_tri, float* __restrict__ ddepth) {
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; m < n_tri; m += stride) {
+__device__ __forceinline__ void normals_bw_body(const float* __restrict__ origin, const float* __restrict__ dir, const float* __restrict__ depth,
+                                                const int64_t* __restrict__ i1, const int64_t* __restrict__ i2, const int64_t* __restrict__ i3,
+                                                const float* __restrict__ dn, int64_t n_tri, float* __restrict__ ddepth,
+                                                int64_t first, int64_t stride) {
+  for (int64_t m = first; m < n_tri; m += stride) {
     const float g[3] = {dn[3 * m], dn[3 * m + 1], dn[3 * m + 2]};
     if (g[0] == 0.f && g[1] == 0.f && g[2] == 0.f) continue;
     const int64_t idx[3] = {i1[m], i2[m], i3[m]};
@@ -86,6 +85,13 @@ normals_bw_kernel(const float* __restrict__ origin, const float* __restrict__ di
     for (int c = 0; c < 3; ++c) { g1 -= (ga[c] + gb[c]) * D[0][c]; g2 += ga[c] * D[1][c]; g3 += gb[c] * D[2][c]; }
     atomicAdd(ddepth + idx[0], g1); atomicAdd(ddepth + idx[1], g2); atomicAdd(ddepth + idx[2], g3);
   }
+}
+__global__ void __launch_bounds__(256)
+normals_bw_kernel(const float* __restrict__ origin, const float* __restrict__ dir, const float* __restrict__ depth,
+                  const int64_t* __restrict__ i1, const int64_t* __restrict__ i2, const int64_t* __restrict__ i3,
+                  const float* __restrict__ dn, int64_t n_tri, float* __restrict__ ddepth) {
+  normals_bw_body(origin, dir, depth, i1, i2, i3, dn, n_tri, ddepth, (int64_t)blockIdx.x * blockDim.x + threadIdx.x,
+                  (int64_t)gridDim.x * blockDim.x);
 }
 
 // ---------------------------------------------------------------- spherical k-means (one thread-block cluster)
@@ -490,9 +496,8 @@ extern "C" int ncn_debug_km_trace(long long* host_dst) {
 #endif
 
 // ---------------------------------------------------------------- orthogonal-triple selection (one CTA)
-__global__ void __launch_bounds__(1024, 1)
-cluster_select_kernel(const float* __restrict__ centroids, const int32_t* __restrict__ assign, int64_t n, int K,
-                      float t_similar, int32_t* __restrict__ labels, int32_t* __restrict__ sel) {
+__device__ __forceinline__ void cluster_select_body(const float* __restrict__ centroids, const int32_t* __restrict__ assign, int64_t n, int K,
+                                                    float t_similar, int32_t* __restrict__ labels, int32_t* __restrict__ sel) {
   __shared__ int s_size[kKmMaxK];
   __shared__ int s_lab[kKmMaxK];
   __shared__ float s_sim[kKmMaxK * kKmMaxK];
@@ -545,6 +550,11 @@ cluster_select_kernel(const float* __restrict__ centroids, const int32_t* __rest
   __syncthreads();
   for (int64_t i = tid; i < n; i += blockDim.x) { const int a = assign[i]; labels[i] = a >= 0 ? s_lab[a] : 0; }
 }
+__global__ void __launch_bounds__(1024, 1)
+cluster_select_kernel(const float* __restrict__ centroids, const int32_t* __restrict__ assign, int64_t n, int K,
+                      float t_similar, int32_t* __restrict__ labels, int32_t* __restrict__ sel) {
+  cluster_select_body(centroids, assign, n, K, t_similar, labels, sel);
+}
 
 // ---------------------------------------------------------------- cluster statistics and loss (one CTA)
 // stats layout (floats): per cluster k in 0..2 at stats[8k..]: [count, cx, cy, cz, |mu|, gl1x, gl1y, gl1z]
@@ -553,9 +563,8 @@ constexpr int kStats = 32;
 
 __device__ __forceinline__ float sgnf(float v) { return v > 0.f ? 1.f : (v < 0.f ? -1.f : 0.f); }
 
-__global__ void __launch_bounds__(1024, 1)
-cluster_loss_fw_kernel(const float* __restrict__ nrm, const int32_t* __restrict__ labels, int64_t n,
-                       float* __restrict__ losses, float* __restrict__ stats) {
+__device__ __forceinline__ void cluster_loss_fw_body(const float* __restrict__ nrm, const int32_t* __restrict__ labels, int64_t n,
+                                                     float* __restrict__ losses, float* __restrict__ stats) {
   __shared__ int s_wacc[32 * 12];
   __shared__ long long s_sum[9];
   __shared__ int s_cnt[3];
@@ -647,11 +656,16 @@ cluster_loss_fw_kernel(const float* __restrict__ nrm, const int32_t* __restrict_
     stats[24] = l_ort; stats[25] = l_dot; stats[26] = l_l1; stats[27] = ok ? 1.f : 0.f;
   }
 }
+__global__ void __launch_bounds__(1024, 1)
+cluster_loss_fw_kernel(const float* __restrict__ nrm, const int32_t* __restrict__ labels, int64_t n,
+                       float* __restrict__ losses, float* __restrict__ stats) {
+  cluster_loss_fw_body(nrm, labels, n, losses, stats);
+}
 
 // dL/dn for  L = w[0] L_ort + w[1] L_dot + w[2] L_L1   (w read from device memory)
-__global__ void __launch_bounds__(256)
-cluster_loss_bw_kernel(const float* __restrict__ nrm, const int32_t* __restrict__ labels, int64_t n,
-                       const float* __restrict__ stats, const float* __restrict__ w, float* __restrict__ dn) {
+__device__ __forceinline__ void cluster_loss_bw_body(const float* __restrict__ nrm, const int32_t* __restrict__ labels, int64_t n,
+                                                     const float* __restrict__ stats, const float* __restrict__ w, float* __restrict__ dn,
+                                                     int64_t first, int64_t stride) {
   __shared__ float s_A[9], s_c[9], s_m[3];
   __shared__ int s_ok;
   if (threadIdx.x == 0) {
@@ -683,8 +697,7 @@ cluster_loss_bw_kernel(const float* __restrict__ nrm, const int32_t* __restrict_
     }
   }
   __syncthreads();
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+  for (int64_t i = first; i < n; i += stride) {
     const int l = labels[i];
     float gx = 0.f, gy = 0.f, gz = 0.f;
     if (l != 0 && s_ok) {
@@ -697,6 +710,30 @@ cluster_loss_bw_kernel(const float* __restrict__ nrm, const int32_t* __restrict_
     }
     dn[3 * i] = gx; dn[3 * i + 1] = gy; dn[3 * i + 2] = gz;
   }
+}
+__global__ void __launch_bounds__(256)
+cluster_loss_bw_kernel(const float* __restrict__ nrm, const int32_t* __restrict__ labels, int64_t n,
+                       const float* __restrict__ stats, const float* __restrict__ w, float* __restrict__ dn) {
+  cluster_loss_bw_body(nrm, labels, n, stats, w, dn, (int64_t)blockIdx.x * blockDim.x + threadIdx.x, (int64_t)gridDim.x * blockDim.x);
+}
+
+// Everything between the k-means result and dL/ddepth in ONE launch (one CTA: M <= a few thousand triangles):
+// selection -> cluster statistics + losses -> dL/dnormals -> dL/ddepth.  Same bodies as the four separate kernels; the
+// stages communicate through the same global buffers (visible to the whole CTA after __syncthreads).
+__global__ void __launch_bounds__(1024, 1)
+cluster_tail_kernel(const float* __restrict__ centroids, const int32_t* __restrict__ assign, int64_t n, int K, float t_similar,
+                    int32_t* __restrict__ labels, int32_t* __restrict__ sel, const float* __restrict__ nrm,
+                    float* __restrict__ losses, float* __restrict__ stats, const float* __restrict__ w, float* __restrict__ dn,
+                    const float* __restrict__ origin, const float* __restrict__ dir, const float* __restrict__ depth,
+                    const int64_t* __restrict__ i1, const int64_t* __restrict__ i2, const int64_t* __restrict__ i3,
+                    float* __restrict__ ddepth) {
+  cluster_select_body(centroids, assign, n, K, t_similar, labels, sel);
+  __syncthreads();
+  cluster_loss_fw_body(nrm, labels, n, losses, stats);
+  __syncthreads();
+  cluster_loss_bw_body(nrm, labels, n, stats, w, dn, threadIdx.x, blockDim.x);
+  __syncthreads();
+  normals_bw_body(origin, dir, depth, i1, i2, i3, dn, n, ddepth, threadIdx.x, blockDim.x);
 }
 
 // ---------------------------------------------------------------- photometric terms (fused fwd + grad)
@@ -828,6 +865,24 @@ extern "C" int ncn_cluster_loss_bw(const float* normals, const int32_t* labels, 
   NCN_CHECK_PTR(normals); NCN_CHECK_PTR(labels); NCN_CHECK_PTR(stats); NCN_CHECK_PTR(weights_dev); NCN_CHECK_PTR(dL_dnormals);
   cluster_loss_bw_kernel<<<persistent_grid(n_points, 256, 8), 256, 0, as_stream(stream)>>>(normals, labels, n_points, stats,
                                                                                           weights_dev, dL_dnormals);
+  NCN_LAUNCH_OK();
+  return NCN_OK;
+}
+
+extern "C" int ncn_cluster_tail(const float* centroids, const int32_t* assign, int64_t n_points, int k, float t_similar,
+                                int32_t* labels, int32_t* sel, const float* normals, float* losses, float* stats,
+                                const float* weights_dev, float* dL_dnormals, const float* origin, const float* dir,
+                                const float* depth, const int64_t* idx1, const int64_t* idx2, const int64_t* idx3,
+                                float* dL_ddepth, ncn_stream_t stream) {
+  NCN_CHECK_PTR(centroids); NCN_CHECK_PTR(sel); NCN_CHECK_PTR(losses); NCN_CHECK_PTR(stats); NCN_CHECK_PTR(weights_dev);
+  if (k < 3 || k > kKmMaxK) return NCN_E_CONFIG;
+  NCN_CHECK_SIZE(n_points >= 0);
+  if (n_points > 0) {
+    NCN_CHECK_PTR(assign); NCN_CHECK_PTR(labels); NCN_CHECK_PTR(normals); NCN_CHECK_PTR(dL_dnormals); NCN_CHECK_PTR(origin);
+    NCN_CHECK_PTR(dir); NCN_CHECK_PTR(depth); NCN_CHECK_PTR(idx1); NCN_CHECK_PTR(idx2); NCN_CHECK_PTR(idx3); NCN_CHECK_PTR(dL_ddepth);
+  }
+  cluster_tail_kernel<<<1, 1024, 0, as_stream(stream)>>>(centroids, assign, n_points, k, t_similar, labels, sel, normals, losses, stats,
+                                                         weights_dev, dL_dnormals, origin, dir, depth, idx1, idx2, idx3, dL_ddepth);
   NCN_LAUNCH_OK();
   return NCN_OK;
 }

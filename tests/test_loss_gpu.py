@@ -100,3 +100,47 @@ def test_empty_cluster_is_nan_and_zero_grad(ncn):
     assert torch.isnan(terms).all()
     torch.nan_to_num(terms).sum().backward()
     assert (n.grad == 0).all()
+
+
+def test_cluster_tail_equals_the_four_calls(ncn):
+    """ncn_cluster_tail (one launch) against ncn_cluster_select -> _loss_fw -> _loss_bw -> ncn_normals_from_depth_bw."""
+    import ctypes as C
+    from ncn_b200 import _lib, clustering, synth
+    from ncn_b200.vren import ptr, stream
+    L = _lib.lib()
+    dev = "cuda"
+    b = synth.patch_batch(8192, seed=5)
+    rays_d = torch.from_numpy(b["rays_d"]).to(dev)
+    tri = torch.from_numpy(b["tri"]).to(dev)
+    g = torch.Generator(device=dev).manual_seed(0)
+    depth = (1.0 + 0.3 * torch.rand(8192, device=dev, generator=g)).contiguous()
+    x123 = {k: tri[i] for i, k in enumerate(("x1", "x2", "x3"))}
+    normals = clustering.normals_from_depth(rays_d, rays_d, depth, x123).detach().contiguous()
+    M = normals.shape[0]
+    cent, assign, nv = clustering.kmeans_spherical(normals, 20, 20)
+    w = torch.tensor([0.3, 0.5, 0.7], device=dev)
+
+    def run(tail):
+        labels = torch.empty(M, dtype=torch.int32, device=dev); sel = torch.empty(3, dtype=torch.int32, device=dev)
+        losses = torch.empty(3, device=dev); stats = torch.empty(32, device=dev)
+        dn = torch.empty(M, 3, device=dev); dd = torch.zeros(8192, device=dev)
+        st = stream()
+        if tail:
+            rc = L.ncn_cluster_tail(ptr(cent), ptr(assign), M, 20, 0.99, ptr(labels), ptr(sel), ptr(normals), ptr(losses), ptr(stats),
+                                    ptr(w), ptr(dn), ptr(rays_d), ptr(rays_d), ptr(depth), ptr(tri[0]), ptr(tri[1]), ptr(tri[2]), ptr(dd), st)
+            assert rc == 0
+        else:
+            assert L.ncn_cluster_select(ptr(cent), ptr(assign), M, 20, 0.99, ptr(labels), ptr(sel), st) == 0
+            assert L.ncn_cluster_loss_fw(ptr(normals), ptr(labels), M, ptr(losses), ptr(stats), st) == 0
+            assert L.ncn_cluster_loss_bw(ptr(normals), ptr(labels), M, ptr(stats), ptr(w), ptr(dn), st) == 0
+            assert L.ncn_normals_from_depth_bw(ptr(rays_d), ptr(rays_d), ptr(depth), ptr(tri[0]), ptr(tri[1]), ptr(tri[2]), ptr(dn), M, ptr(dd), st) == 0
+        torch.cuda.synchronize()
+        return labels, sel, losses, stats[:28], dn, dd
+
+    a, bb = run(False), run(True)
+    assert torch.equal(a[0], bb[0]) and torch.equal(a[1], bb[1])
+    assert (a[0] != 0).any()
+    torch.testing.assert_close(a[2], bb[2], rtol=1e-6, atol=0, equal_nan=True)
+    torch.testing.assert_close(a[3], bb[3], rtol=1e-6, atol=1e-7, equal_nan=True)
+    torch.testing.assert_close(a[4], bb[4], rtol=1e-6, atol=1e-9)
+    torch.testing.assert_close(a[5], bb[5], rtol=1e-4, atol=1e-7)      # float atomics: order differs
