@@ -103,7 +103,8 @@ normals_bw_kernel(const float* __restrict__ origin, const float* __restrict__ di
 // partial sums in its own shared memory, and after one barrier.cluster every CTA folds all 8 partials through
 // distributed shared memory and updates the (replicated) centroids.  No atomics, no host round trip.
 constexpr int kKmThreads = 256;     // (512 threads: same iteration time - the tile phase is issue bound, not latency bound)
-constexpr int kKmCluster = 8;
+constexpr int kKmCluster = 8;        // portable cluster size (fallback)
+constexpr int kKmClusterMax = 16;    // non-portable size tried first: half the tiles per CTA and Lloyd iteration
 constexpr int kKmMaxK = 64;
 constexpr float kKmFix = 1048576.0f;     // 2^20
 constexpr int kAccStride = 33;
@@ -206,7 +207,8 @@ __device__ __forceinline__ void split_empty_clusters(float* __restrict__ s_c, fl
   }
 }
 
-__global__ void __cluster_dims__(kKmCluster, 1, 1) __launch_bounds__(kKmThreads, 1)
+template <int CL>
+__global__ void __launch_bounds__(kKmThreads, 1)
 kmeans_kernel(const float* __restrict__ x, int64_t n, ncn_kmeans_params p, float* __restrict__ centroids,
               int32_t* __restrict__ assign, int32_t* __restrict__ n_valid_out, int32_t* __restrict__ valid_idx,
               int nt_cap) {
@@ -231,15 +233,16 @@ kmeans_kernel(const float* __restrict__ x, int64_t n, ncn_kmeans_params p, float
     const int64_t r_begin = (int64_t)wid * per_warp, r_end = r_begin + per_warp < n ? r_begin + per_warp : n;
     auto chunk_mask = [&](int64_t c0) -> uint32_t {            // bit b: row c0 + 32*b + lane is a valid normal
       uint32_t vm = 0u;
-#pragma unroll 8
+#pragma unroll
       for (int b = 0; b < 32; ++b) {
         const int64_t i = c0 + 32 * b + lane;
         if (i < r_end && valid_normal(x[3 * i], x[3 * i + 1], x[3 * i + 2])) vm |= 1u << b;
       }
       return vm;
     };
-    int cnt = 0;
-    for (int64_t c0 = r_begin; c0 < r_end; c0 += 1024) cnt += __popc(chunk_mask(c0));
+    const uint32_t vm0 = r_begin < r_end ? chunk_mask(r_begin) : 0u;      // kept for the write pass (n <= 8192: the only chunk)
+    int cnt = __popc(vm0);
+    for (int64_t c0 = r_begin + 1024; c0 < r_end; c0 += 1024) cnt += __popc(chunk_mask(c0));
     cnt = warp_sum_i(cnt);
     if (lane == 0) s_warp_tot[wid] = cnt;
     __syncthreads();
@@ -248,7 +251,7 @@ kmeans_kernel(const float* __restrict__ x, int64_t n, ncn_kmeans_params p, float
     for (int w = 0; w < kKmThreads / 32; ++w) { const int c = s_warp_tot[w]; if (w < wid) base += c; total += c; }
     if (rank == 0) {
       for (int64_t c0 = r_begin; c0 < r_end; c0 += 1024) {
-        const uint32_t vm = chunk_mask(c0);
+        const uint32_t vm = c0 == r_begin ? vm0 : chunk_mask(c0);
         for (int b = 0; b < 32 && c0 + 32 * b < r_end; ++b) {
           const int64_t i = c0 + 32 * b + lane;
           const bool v = (vm >> b) & 1u;
@@ -275,9 +278,9 @@ kmeans_kernel(const float* __restrict__ x, int64_t n, ncn_kmeans_params p, float
   // 2) training subset: at most max_points_per_centroid*K points at a uniform stride over the valid rows (faiss draws a
   //    random subset; equality with faiss is not a parity criterion); CTA r owns training points r, r+8, r+16, ...
   const int nt = nv > nt_cap ? nt_cap : nv;
-  const int my_n = (nt - (int)rank + kKmCluster - 1) / kKmCluster;
+  const int my_n = (nt - (int)rank + CL - 1) / CL;
   for (int j = tid; j < my_n; j += kKmThreads) {
-    const int gj = j * kKmCluster + (int)rank;
+    const int gj = j * CL + (int)rank;
     const int r = valid_idx[(int)(((int64_t)gj * nv) / nt)];
     xs[3 * j] = x[3 * r]; xs[3 * j + 1] = x[3 * r + 1]; xs[3 * j + 2] = x[3 * r + 2];
   }
@@ -297,7 +300,7 @@ kmeans_kernel(const float* __restrict__ x, int64_t n, ncn_kmeans_params p, float
   const bool use_tc = K <= 32;
   const int g = lane >> 2, t = lane & 3;
   const int n_tiles = (my_n + 15) >> 4;
-  __half* hq = reinterpret_cast<__half*>(km_smem + (((size_t)((nt_cap + kKmCluster - 1) / kKmCluster) * 12 + 15) & ~(size_t)15));
+  __half* hq = reinterpret_cast<__half*>(km_smem + (((size_t)((nt_cap + CL - 1) / CL) * 12 + 15) & ~(size_t)15));
   if (use_tc) {
     // iteration-invariant fp16 point rows: hq[point] = (xh,yh,zh,xl,yl,zl,1,0); all-zero rows pad the last tile
     for (int j = tid; j < n_tiles * 16; j += kKmThreads) {
@@ -398,7 +401,7 @@ kmeans_kernel(const float* __restrict__ x, int64_t n, ncn_kmeans_params p, float
       if (tid < 256) {
         float tot = 0.f;
 #pragma unroll
-        for (uint32_t r = 0; r < kKmCluster; ++r) tot += dsmem_ld_float(fpart + tid, r);
+        for (uint32_t r = 0; r < CL; ++r) tot += dsmem_ld_float(fpart + tid, r);
         s_fw[tid] = tot;                                          // cluster total of (cluster tid/8, column tid%8)
       }
       if (it < 4) KM_TRACE(12 + 8 * it);
@@ -414,8 +417,11 @@ kmeans_kernel(const float* __restrict__ x, int64_t n, ncn_kmeans_params p, float
         bool empty = false;
         if (lane < K) {
           const float c = s_acc[4 * lane + 3];
-          if (c > 0.f) { s_c[3 * lane] = s_acc[4 * lane] / c; s_c[3 * lane + 1] = s_acc[4 * lane + 1] / c; s_c[3 * lane + 2] = s_acc[4 * lane + 2] / c; }
-          else empty = true;
+          if (c > 0.f) {
+            // spherical: normalize(sum / c) == normalize(sum) - the member count only scales the vector, skip the divisions
+            const float ic = p.spherical ? 1.0f : 1.0f / c;
+            s_c[3 * lane] = s_acc[4 * lane] * ic; s_c[3 * lane + 1] = s_acc[4 * lane + 1] * ic; s_c[3 * lane + 2] = s_acc[4 * lane + 2] * ic;
+          } else empty = true;
         }
         const unsigned any_empty = __ballot_sync(0xffffffffu, empty);
         if (any_empty) {
@@ -425,7 +431,7 @@ kmeans_kernel(const float* __restrict__ x, int64_t n, ncn_kmeans_params p, float
         }
         if (lane < K && p.spherical) {
           const float l = sqrtf(s_c[3 * lane] * s_c[3 * lane] + s_c[3 * lane + 1] * s_c[3 * lane + 1] + s_c[3 * lane + 2] * s_c[3 * lane + 2]);
-          if (l > 0.f) { s_c[3 * lane] /= l; s_c[3 * lane + 1] /= l; s_c[3 * lane + 2] /= l; }
+          if (l > 0.f) { const float il = 1.0f / l; s_c[3 * lane] *= il; s_c[3 * lane + 1] *= il; s_c[3 * lane + 2] *= il; }
         }
       }
       if (it < 4) KM_TRACE(14 + 8 * it);
@@ -454,7 +460,7 @@ kmeans_kernel(const float* __restrict__ x, int64_t n, ncn_kmeans_params p, float
     for (int a = tid; a < K * 4; a += kKmThreads) {
       long long t = 0;
 #pragma unroll
-      for (uint32_t r = 0; r < kKmCluster; ++r) t += dsmem_ld_int(part + a, r);
+      for (uint32_t r = 0; r < CL; ++r) t += dsmem_ld_int(part + a, r);
       s_acc[a] = (a & 3) == 3 ? (float)t : (float)((double)t / (double)kKmFix);
     }
     if (tid == 0) s_any_empty = 0;
@@ -482,7 +488,7 @@ kmeans_kernel(const float* __restrict__ x, int64_t n, ncn_kmeans_params p, float
   cluster_sync_all();               // no CTA may exit while a peer can still read its shared memory
   KM_TRACE(5);
   // 5) final assignment of every valid row (kmeans.index.search, losses.py:89), split over the cluster + centroids out
-  for (int j = tid + (int)rank * kKmThreads; j < nv; j += kKmThreads * kKmCluster) {
+  for (int j = tid + (int)rank * kKmThreads; j < nv; j += kKmThreads * CL) {
     const int r = valid_idx[j];
     assign[r] = best_centroid(x[3 * r], x[3 * r + 1], x[3 * r + 2], s_c, K);
   }
@@ -828,11 +834,39 @@ extern "C" int ncn_kmeans_spherical(const float* x, int64_t n_points, const ncn_
   int64_t cap = (int64_t)p->max_points_per_centroid * p->k;
   if (cap > 65536) cap = 65536;
   if (cap > n_points) cap = n_points > 0 ? n_points : 1;
-  const size_t per_cta = (size_t)(cap + kKmCluster - 1) / kKmCluster;
+  // 16-CTA cluster (non-portable size, one GPC) when the device grants it, else the portable 8
+  static int cluster = 0;
+  if (cluster == 0) {
+    cluster = kKmCluster;
+    if (cudaFuncSetAttribute(kmeans_kernel<kKmClusterMax>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess) {
+      cudaLaunchConfig_t q = {};
+      q.gridDim = dim3(kKmClusterMax); q.blockDim = dim3(kKmThreads); q.dynamicSmemBytes = 64 * 1024;
+      cudaLaunchAttribute qa[1];
+      qa[0].id = cudaLaunchAttributeClusterDimension; qa[0].val.clusterDim.x = kKmClusterMax; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
+      q.attrs = qa; q.numAttrs = 1;
+      int n_clusters = 0;
+      cudaFuncSetAttribute(kmeans_kernel<kKmClusterMax>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+      if (cudaOccupancyMaxActiveClusters(&n_clusters, kmeans_kernel<kKmClusterMax>, &q) == cudaSuccess && n_clusters >= 1) cluster = kKmClusterMax;
+    }
+    (void)cudaGetLastError();
+  }
+  const size_t per_cta = (size_t)(cap + cluster - 1) / cluster;
   const size_t smem = per_cta * 12 + 16 + (per_cta + 16) * 16 + 16;               // this CTA's points (fp32) + fp16 rows
-  // static (~38 KB) + dynamic shared memory crosses the 48 KB default limit: always opt in
-  NCN_CUDA(cudaFuncSetAttribute(kmeans_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kmeans_kernel<<<kKmCluster, kKmThreads, smem, as_stream(stream)>>>(x, n_points, *p, centroids, assign, n_valid, (int32_t*)workspace, (int)cap);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(cluster); cfg.blockDim = dim3(kKmThreads); cfg.dynamicSmemBytes = smem; cfg.stream = as_stream(stream);
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = cluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  int32_t* wsp = (int32_t*)workspace;
+  const int cap_i = (int)cap;
+  // static (~22 KB) + dynamic shared memory can cross the 48 KB default limit: always opt in
+  if (cluster == kKmClusterMax) {
+    NCN_CUDA(cudaFuncSetAttribute(kmeans_kernel<kKmClusterMax>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    NCN_CUDA(cudaLaunchKernelEx(&cfg, kmeans_kernel<kKmClusterMax>, x, n_points, *p, centroids, assign, n_valid, wsp, cap_i));
+  } else {
+    NCN_CUDA(cudaFuncSetAttribute(kmeans_kernel<kKmCluster>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    NCN_CUDA(cudaLaunchKernelEx(&cfg, kmeans_kernel<kKmCluster>, x, n_points, *p, centroids, assign, n_valid, wsp, cap_i));
+  }
   NCN_LAUNCH_OK();
   return NCN_OK;
 }
