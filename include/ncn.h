@@ -52,6 +52,8 @@ int ncn_version(void);
 const char* ncn_error_string(int code);
 /* number of SMs / compute capability of the current device (for grid sizing / checks) */
 int ncn_device_info(int* sm_count, int* cc_major, int* cc_minor);
+/* developer aid: slots[slot] = %globaltimer (ns) when `stream` reaches this point (works inside a captured graph) */
+int ncn_debug_stamp(uint64_t* slots, int slot, ncn_stream_t stream);
 
 /* ------------------------------------------------------------------------- */
 /* (1) ray / volume intersection          replaces vren.ray_aabb_intersect,  */
@@ -432,6 +434,24 @@ int ncn_adam_step(float* param, float* grad, float* m, float* v, void* param_f16
                   int64_t n, float lr, float beta1, float beta2, float eps, float weight_decay,
                   int step, const float* grad_div_dev, const int32_t* skip_dev,
                   const float* clip_coef_dev, const float* lr_bc_dev, ncn_stream_t stream);
+/* The same update for SEVERAL parameter groups of one flat buffer in ONE launch (the reference's two FusedAdam groups,
+ * train_nerf.py:264-274: hash table wd 0, MLPs wd 1e-6).  Group q covers [start[q], start[q+1]) (start[0] = 0, every
+ * start a multiple of 4).  max_norm > 0 folds clip_grad_norm_(max_norm) in: sumsq_dev then holds the squared norm of the
+ * unscaled gradient (ncn_grad_sumsq) and the coefficient min(1, max_norm/(sqrt(sumsq)+1e-6)) is derived in the kernel.
+ * lr and the bias corrections always come from lr_bc_dev (3 device floats). */
+#define NCN_ADAM_MAX_GROUPS 4
+typedef struct ncn_adam_groups {
+  int32_t n_groups;
+  int32_t reserved;
+  int64_t start[NCN_ADAM_MAX_GROUPS];
+  float weight_decay[NCN_ADAM_MAX_GROUPS];
+  float max_norm;
+  float reserved2;
+} ncn_adam_groups;
+int ncn_adam_step_groups(float* param, float* grad, float* m, float* v, void* param_f16, int64_t n,
+                         const ncn_adam_groups* groups, float beta1, float beta2, float eps,
+                         const float* grad_div_dev, const int32_t* skip_dev, const float* sumsq_dev,
+                         const float* lr_bc_dev, ncn_stream_t stream);
 /* sum of squares of grad/(div) into out[0] (ACCUMULATED), and non-finite flag into flag[0] */
 int ncn_grad_sumsq(const float* grad, int64_t n, const float* grad_div_dev,
                    float* out, int32_t* flag, ncn_stream_t stream);

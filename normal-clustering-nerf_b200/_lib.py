@@ -160,6 +160,11 @@ class MlpBwdSrc(C.Structure):
                 ("dx_rgb", C.c_void_p), ("d_sigmas", C.c_void_p), ("h", C.c_void_p), ("scale", C.c_float), ("perm", C.c_int32)]
 
 
+class AdamGroups(C.Structure):
+    _fields_ = [("n_groups", C.c_int32), ("reserved", C.c_int32), ("start", C.c_int64 * 4), ("weight_decay", C.c_float * 4),
+                ("max_norm", C.c_float), ("reserved2", C.c_float)]
+
+
 ACT = {"None": 0, "ReLU": 1, "Sigmoid": 2, "Exponential": 3}
 
 SIGNATURES.update({
@@ -192,6 +197,8 @@ SIGNATURES.update({
     "ncn_cluster_tail": (c_i32, [c_vp, c_vp, c_i64, c_i32, c_f32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "ncn_photometric_loss": (c_i32, [c_vp, c_vp, c_vp, c_i64, c_i32, C.POINTER(c_f32), c_f32, c_f32, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "ncn_adam_step": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_f32, c_f32, c_f32, c_f32, c_f32, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "ncn_adam_step_groups": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, C.POINTER(AdamGroups), c_f32, c_f32, c_f32, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "ncn_debug_stamp": (c_i32, [c_vp, c_i32, c_vp]),
     "ncn_set_mlp_bwd_impl": (c_i32, [c_i32]),
     "ncn_mlp_bwd_src_fused": (c_i32, [C.POINTER(MlpDesc), C.POINTER(MlpBwdSrc), c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_f32, c_vp, c_sz, c_vp, c_vp]),
     "ncn_set_grid_bwd_merge": (c_i32, [c_i32]),

@@ -46,3 +46,19 @@ extern "C" int ncn_device_info(int* sm, int* cc_major, int* cc_minor) {
   if (cc_minor) NCN_CUDA(cudaDeviceGetAttribute(cc_minor, cudaDevAttrComputeCapabilityMinor, dev));
   return NCN_OK;
 }
+
+// developer aid: writes the GPU global timer (ns) into slots[slot] when the stream reaches this point - a timeline of a
+// captured CUDA graph, where CUDA events cannot be read (tools/timeline.py)
+namespace ncn {
+__global__ void stamp_kernel(unsigned long long* slots, int slot) {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  slots[slot] = t;
+}
+}  // namespace ncn
+extern "C" int ncn_debug_stamp(uint64_t* slots, int slot, ncn_stream_t stream) {
+  NCN_CHECK_PTR(slots);
+  ncn::stamp_kernel<<<1, 1, 0, ncn::as_stream(stream)>>>((unsigned long long*)slots, slot);
+  NCN_LAUNCH_OK();
+  return NCN_OK;
+}

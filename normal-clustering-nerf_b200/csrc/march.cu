@@ -165,7 +165,10 @@ march_train_count_kernel(const float* __restrict__ rays_o, const float* __restri
 }
 
 // ---- train: pass 2 (single CTA): exclusive scan of counts -> rays_a, counter ---------------
+// A thread owns 8 CONSECUTIVE rays (two 16-byte loads, scanned in registers), so 8192 rays are one pass with one
+// memory round trip and two block barriers (the per-1024 loop paid a load latency and four barriers per pass).
 constexpr int kScanThreads = 1024;
+constexpr int kScanItems = 8;
 __global__ void __launch_bounds__(kScanThreads)
 march_scan_kernel(const int32_t* __restrict__ counts, int64_t n_rays, int64_t* __restrict__ rays_a,
                   int32_t* __restrict__ counter) {
@@ -174,10 +177,20 @@ march_scan_kernel(const int32_t* __restrict__ counts, int64_t n_rays, int64_t* _
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   if (threadIdx.x == 0) s_carry = 0;
   __syncthreads();
-  for (int64_t base = 0; base < n_rays; base += kScanThreads) {
-    const int64_t r = base + threadIdx.x;
-    const int v = r < n_rays ? counts[r] : 0;
-    int incl = warp_scan_incl_i(v, lane);
+  for (int64_t base = 0; base < n_rays; base += kScanThreads * kScanItems) {
+    const int64_t r0 = base + (int64_t)threadIdx.x * kScanItems;
+    int v[kScanItems];
+    if (r0 + kScanItems <= n_rays) {
+      const int4 a = *reinterpret_cast<const int4*>(counts + r0), b = *reinterpret_cast<const int4*>(counts + r0 + 4);
+      v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    } else {
+#pragma unroll
+      for (int q = 0; q < kScanItems; ++q) v[q] = r0 + q < n_rays ? counts[r0 + q] : 0;
+    }
+    int tot = 0;
+#pragma unroll
+    for (int q = 0; q < kScanItems; ++q) tot += v[q];
+    const int incl = warp_scan_incl_i(tot, lane);
     if (lane == 31) s_warp[wid] = incl;
     __syncthreads();
     if (wid == 0) {
@@ -186,15 +199,15 @@ march_scan_kernel(const int32_t* __restrict__ counts, int64_t n_rays, int64_t* _
       s_warp[lane] = wi - w;   // exclusive offset of each warp
     }
     __syncthreads();
-    const int carry = s_carry;
-    const int excl = carry + s_warp[wid] + incl - v;
-    if (r < n_rays) {
-      rays_a[3 * r + 0] = r;
-      rays_a[3 * r + 1] = excl;
-      rays_a[3 * r + 2] = v;
+    int excl = s_carry + s_warp[wid] + incl - tot;
+#pragma unroll
+    for (int q = 0; q < kScanItems; ++q) {
+      const int64_t r = r0 + q;
+      if (r < n_rays) { rays_a[3 * r + 0] = r; rays_a[3 * r + 1] = excl; rays_a[3 * r + 2] = v[q]; }
+      excl += v[q];
     }
     __syncthreads();
-    if (threadIdx.x == kScanThreads - 1) s_carry = excl + v;
+    if (threadIdx.x == kScanThreads - 1) s_carry = excl;
     __syncthreads();
   }
   if (threadIdx.x == 0) { counter[0] = s_carry; counter[1] = (int32_t)n_rays; }

@@ -8,14 +8,32 @@
 
 namespace ncn {
 
+// CTAs per SM of the streaming pass.  2 x 256 threads x 8 float4 loads in flight still saturate HBM, and leave half of the
+// register file / thread slots to the latency-bound march kernels that run beside the deferred optimizer in the step graph
+// (at 4 the optimizer owned every register of the SM and the march simply queued behind it).
+constexpr int kAdamCtasPerSm = 2;
+
 struct AdamArgs {
   float lr, beta1, beta2, eps, weight_decay, bc1, bc2;
+  // several parameter groups in one launch (ncn_adam_step_groups): group q covers [start[q], start[q+1]) with its own
+  // weight decay; max_norm > 0: the clip coefficient is derived in the kernel from the squared gradient norm
+  int n_groups;
+  long long start[NCN_ADAM_MAX_GROUPS];
+  float wd[NCN_ADAM_MAX_GROUPS];
+  float max_norm;
 };
 
 // apex FusedAdam (adam_w_mode) update.  The two bias corrections are applied as reciprocals computed once per thread
 // and the final quotient uses the fast divider (<= 2 ulp from the IEEE quotient apex computes; the pass stays
 // bandwidth bound instead of spending ~40 instructions per element on three IEEE divisions)
-__device__ __forceinline__ void adam_one(float& p, float& g, float& m, float& v, const AdamArgs& a, float gmul, float inv_bc1,
+__device__ __forceinline__ float adam_wd_at(const AdamArgs& a, long long idx) {
+  float wd = a.weight_decay;
+#pragma unroll
+  for (int q = 0; q < NCN_ADAM_MAX_GROUPS; ++q) if (q < a.n_groups && idx >= a.start[q]) wd = a.wd[q];
+  return wd;
+}
+
+__device__ __forceinline__ void adam_one(float& p, float& g, float& m, float& v, AdamArgs a, float gmul, float inv_bc1,
                                          float inv_bc2) {
   const float gr = g * gmul;
   m = a.beta1 * m + (1.f - a.beta1) * gr;
@@ -34,7 +52,14 @@ adam_kernel(float* __restrict__ param, float* __restrict__ grad, float* __restri
   const bool do_skip = skip != nullptr && *skip != 0;
   float gmul = 1.f;
   if (grad_div) gmul = 1.f / *grad_div;
-  if (clip_coef) gmul *= *clip_coef;
+  if (clip_coef) {
+    if (a.max_norm > 0.f) {        // clip_coef points at the squared gradient norm: min(1, max_norm / (|g| + 1e-6)) (clip_grad_norm_)
+      const float c = a.max_norm / (sqrtf(*clip_coef) + 1e-6f);
+      gmul *= c < 1.f ? c : 1.f;
+    } else {
+      gmul *= *clip_coef;
+    }
+  }
   const float inv_bc1 = 1.f / a.bc1, inv_bc2 = 1.f / a.bc2;
   const int64_t n4 = n >> 2;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -52,6 +77,8 @@ adam_kernel(float* __restrict__ param, float* __restrict__ grad, float* __restri
     float4 p0 = __ldcs(reinterpret_cast<const float4*>(param) + i0), m0 = __ldcs(reinterpret_cast<const float4*>(m) + i0),
            v0 = __ldcs(reinterpret_cast<const float4*>(v) + i0);
     float4 p1 = p0, m1 = m0, v1 = v0;
+    const float wd1 = a.n_groups > 0 ? adam_wd_at(a, i1 << 2) : a.weight_decay;
+    if (a.n_groups > 0) a.weight_decay = adam_wd_at(a, i0 << 2);
     if (two) { p1 = __ldcs(reinterpret_cast<const float4*>(param) + i1); m1 = __ldcs(reinterpret_cast<const float4*>(m) + i1); v1 = __ldcs(reinterpret_cast<const float4*>(v) + i1); }
     adam_one(p0.x, g0.x, m0.x, v0.x, a, gmul, inv_bc1, inv_bc2); adam_one(p0.y, g0.y, m0.y, v0.y, a, gmul, inv_bc1, inv_bc2);
     adam_one(p0.z, g0.z, m0.z, v0.z, a, gmul, inv_bc1, inv_bc2); adam_one(p0.w, g0.w, m0.w, v0.w, a, gmul, inv_bc1, inv_bc2);
@@ -63,6 +90,7 @@ adam_kernel(float* __restrict__ param, float* __restrict__ grad, float* __restri
       reinterpret_cast<uint2*>(p16)[i0] = pk;
     }
     if (two) {
+      a.weight_decay = wd1;
       adam_one(p1.x, g1.x, m1.x, v1.x, a, gmul, inv_bc1, inv_bc2); adam_one(p1.y, g1.y, m1.y, v1.y, a, gmul, inv_bc1, inv_bc2);
       adam_one(p1.z, g1.z, m1.z, v1.z, a, gmul, inv_bc1, inv_bc2); adam_one(p1.w, g1.w, m1.w, v1.w, a, gmul, inv_bc1, inv_bc2);
       reinterpret_cast<float4*>(param)[i1] = p1; reinterpret_cast<float4*>(m)[i1] = m1; reinterpret_cast<float4*>(v)[i1] = v1;
@@ -79,6 +107,7 @@ adam_kernel(float* __restrict__ param, float* __restrict__ grad, float* __restri
     float g = grad[t];
     if (!do_skip) {
       float p = param[t], mm = m[t], vv = v[t];
+      if (a.n_groups > 0) a.weight_decay = adam_wd_at(a, t);
       adam_one(p, g, mm, vv, a, gmul, inv_bc1, inv_bc2);
       param[t] = p; m[t] = mm; v[t] = vv;
       if (p16) p16[t] = __float2half_rn(p);
@@ -139,9 +168,38 @@ extern "C" int ncn_adam_step(float* param, float* grad, float* m, float* v, void
   AdamArgs a;
   a.lr = lr; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.weight_decay = weight_decay;
   a.bc1 = 1.0f - powf(beta1, (float)step); a.bc2 = 1.0f - powf(beta2, (float)step);
-  const int grid = persistent_grid((n + 7) / 8, 256, 4);
+  a.n_groups = 0; a.max_norm = 0.f;
+  const int grid = persistent_grid((n + 7) / 8, 256, kAdamCtasPerSm);
   adam_kernel<<<grid, 256, 0, as_stream(stream)>>>(param, grad, m, v, (__half*)param_f16, n, a, grad_div_dev, skip_dev,
                                                    clip_coef_dev, lr_bc_dev);
+  NCN_LAUNCH_OK();
+  return NCN_OK;
+}
+
+extern "C" int ncn_adam_step_groups(float* param, float* grad, float* m, float* v, void* param_f16, int64_t n,
+                                    const ncn_adam_groups* groups, float beta1, float beta2, float eps,
+                                    const float* grad_div_dev, const int32_t* skip_dev, const float* sumsq_dev,
+                                    const float* lr_bc_dev, ncn_stream_t stream) {
+  NCN_CHECK_SIZE(n >= 0);
+  NCN_CHECK_PTR(groups); NCN_CHECK_PTR(lr_bc_dev);
+  if (groups->n_groups < 1 || groups->n_groups > NCN_ADAM_MAX_GROUPS || groups->start[0] != 0) return NCN_E_CONFIG;
+  if (groups->max_norm > 0.f) NCN_CHECK_PTR(sumsq_dev);
+  if (n == 0) return NCN_OK;
+  NCN_CHECK_PTR(param); NCN_CHECK_PTR(grad); NCN_CHECK_PTR(m); NCN_CHECK_PTR(v);
+  if (((uintptr_t)param | (uintptr_t)grad | (uintptr_t)m | (uintptr_t)v) & 15) return NCN_E_ALIGN;
+  if ((uintptr_t)param_f16 & 7) return NCN_E_ALIGN;
+  AdamArgs a;
+  a.lr = 0.f; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.weight_decay = groups->weight_decay[0]; a.bc1 = 1.f; a.bc2 = 1.f;
+  a.n_groups = groups->n_groups; a.max_norm = groups->max_norm;
+  for (int q = 0; q < NCN_ADAM_MAX_GROUPS; ++q) {
+    const bool on = q < groups->n_groups;
+    a.start[q] = on ? groups->start[q] : n; a.wd[q] = on ? groups->weight_decay[q] : 0.f;
+    if (on && (groups->start[q] & 3)) return NCN_E_ALIGN;            // a float4 never straddles two groups
+    if (on && q > 0 && groups->start[q] < groups->start[q - 1]) return NCN_E_CONFIG;
+  }
+  const int grid = persistent_grid((n + 7) / 8, 256, kAdamCtasPerSm);
+  adam_kernel<<<grid, 256, 0, as_stream(stream)>>>(param, grad, m, v, (__half*)param_f16, n, a, grad_div_dev, skip_dev,
+                                                   groups->max_norm > 0.f ? sumsq_dev : nullptr, lr_bc_dev);
   NCN_LAUNCH_OK();
   return NCN_OK;
 }

@@ -17,6 +17,7 @@ Host-visible scalars (losses, sample counts) are read back lazily from a small s
 """
 import ctypes as C
 import math
+import os
 
 import torch
 
@@ -95,7 +96,7 @@ class FusedStep:
         self.pending = False                 # deferred mode: a gradient is waiting for its optimizer pass
         # deferred optimizer: graph mode, single rank (the gradient all-reduce stays an eager NCCL call between two graphs;
         # capturing it inside the step graph dead-locked on 2 GPUs)
-        self.defer = use_graph and trainer.world_size == 1
+        self.defer = use_graph and trainer.world_size == 1 and not os.environ.get("NCN_NO_DEFER")      # env: developer A/B only
         # multi-rank: the same overlap with three graphs on two streams and an EAGER all-reduce in between
         #   opt stream : [all-reduce(prev grads) -> graph(adam)]      main stream: graph(march) -> join -> graph(field)
         self.defer_multi = use_graph and trainer.world_size > 1
@@ -103,6 +104,12 @@ class FusedStep:
         self.ev_fork2, self.ev_join2 = torch.cuda.Event(), torch.cuda.Event()
         self.coef = torch.ones(1, **f32)
         self.flag = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.adam_groups = _lib.AdamGroups()
+        self.adam_groups.n_groups = len(self.opt.groups)
+        for q, (start, _, wd) in enumerate(self.opt.groups):
+            self.adam_groups.start[q] = start
+            self.adam_groups.weight_decay[q] = wd
+        self.adam_groups.max_norm = float(self.hp["grad_clip"])
         self.grad_div = torch.tensor([float(trainer.world_size)], **f32)
         self.xform = (C.c_float * 6)(*([float(m.xyz_min[0, i]) for i in range(3)] + [float((m.xyz_max - m.xyz_min)[0, i]) for i in range(3)]))
         self.bg = (C.c_float * 3)(1.0, 1.0, 1.0) if self.hp["exp_step_factor"] == 0 else (C.c_float * 3)(0.0, 0.0, 0.0)
@@ -235,12 +242,10 @@ class FusedStep:
         sumsq.zero_()
         self.flag.copy_(self.flag_init)          # 0, or 1 to skip the (empty) update of the very first deferred step
         check(L.ncn_grad_sumsq(ptr(opt.grad), opt.grad.numel(), ptr(self.grad_div), ptr(sumsq), ptr(self.flag), st), "sumsq")
-        check(L.ncn_clip_coef(ptr(sumsq), float(self.hp["grad_clip"]), ptr(self.coef), st), "clip")
-        for (start, n, wd) in opt.groups:
-            sl = slice(start, start + n)
-            check(L.ncn_adam_step(ptr(opt.flat[sl]), ptr(opt.grad[sl]), ptr(opt.m[sl]), ptr(opt.v[sl]), ptr(self.flat16[sl]), n, 0.0,
-                                  opt.betas[0], opt.betas[1], opt.eps, wd, 1, ptr(self.grad_div), ptr(self.flag), ptr(self.coef),
-                                  ptr(self.dev_sched[sched_off:sched_off + 3]), st), "adam")
+        # both parameter groups (hash table wd 0 / MLPs wd 1e-6) and the clip coefficient in ONE launch
+        check(L.ncn_adam_step_groups(ptr(opt.flat), ptr(opt.grad), ptr(opt.m), ptr(opt.v), ptr(self.flat16), opt.flat.numel(),
+                                     C.byref(self.adam_groups), opt.betas[0], opt.betas[1], opt.eps, ptr(self.grad_div), ptr(self.flag),
+                                     ptr(sumsq), ptr(self.dev_sched[sched_off:sched_off + 3]), st), "adam")
 
     def _run_deferred(self, multi):
         """One replay = [apply the PREVIOUS step's update] || [jitter + AABB + march of THIS step] -> field/backward.

@@ -69,3 +69,41 @@ def test_adam_skips_on_nonfinite(ncn):
     assert int(flag) == 1
     check(L.ncn_adam_step(ptr(p), ptr(grad), ptr(m), ptr(v), None, n, 1e-2, 0.9, 0.999, 1e-15, 0.0, 1, None, ptr(flag), None, None, stream()))
     assert (p == 1).all() and (m == 0).all() and (grad == 0).all()
+
+
+def test_adam_groups_equals_per_group_launches(ncn):
+    """ncn_adam_step_groups (both parameter groups + the clip coefficient in one launch) == ncn_clip_coef + one
+    ncn_adam_step per group, bit for bit."""
+    import ctypes as C
+    from ncn_b200 import _lib
+    from ncn_b200._lib import check, ptr, stream
+    L = _lib.lib()
+    g = torch.Generator(device="cuda").manual_seed(3)
+    n0, n1 = 400004, 10244                       # hash-table group (wd 0) and MLP group (wd 1e-6), starts multiples of 4
+    n = n0 + n1
+    mk = lambda s: torch.randn(n, device="cuda", generator=g) * s
+    p, grad, m, v = mk(0.1), mk(3.0), mk(0.01), mk(1e-2).abs() * 1e-2
+    gdiv = torch.tensor([128.0], device="cuda")
+    sched = torch.tensor([1e-2, 1 - 0.9 ** 5, 1 - 0.999 ** 5], device="cuda")
+    flag = torch.zeros(1, dtype=torch.int32, device="cuda")
+    sumsq = torch.zeros(1, device="cuda"); coef = torch.ones(1, device="cuda")
+    check(L.ncn_grad_sumsq(ptr(grad), n, ptr(gdiv), ptr(sumsq), ptr(flag), stream()))
+    check(L.ncn_clip_coef(ptr(sumsq), 0.05, ptr(coef), stream()))
+    assert float(coef) < 1.0                      # the clip is active
+    a = [t.clone() for t in (p, grad, m, v)]; a16 = torch.zeros(n, dtype=torch.float16, device="cuda")
+    b = [t.clone() for t in (p, grad, m, v)]; b16 = torch.zeros(n, dtype=torch.float16, device="cuda")
+    for (start, cnt, wd) in ((0, n0, 0.0), (n0, n1, 1e-6)):
+        sl = slice(start, start + cnt)
+        check(L.ncn_adam_step(ptr(a[0][sl]), ptr(a[1][sl]), ptr(a[2][sl]), ptr(a[3][sl]), ptr(a16[sl]), cnt, 0.0, 0.9, 0.999, 1e-15, wd, 1,
+                              ptr(gdiv), ptr(flag), ptr(coef), ptr(sched), stream()))
+    grp = _lib.AdamGroups()
+    grp.n_groups = 2
+    grp.start[0], grp.start[1] = 0, n0
+    grp.weight_decay[0], grp.weight_decay[1] = 0.0, 1e-6
+    grp.max_norm = 0.05
+    check(L.ncn_adam_step_groups(ptr(b[0]), ptr(b[1]), ptr(b[2]), ptr(b[3]), ptr(b16), n, C.byref(grp), 0.9, 0.999, 1e-15,
+                                 ptr(gdiv), ptr(flag), ptr(sumsq), ptr(sched), stream()))
+    torch.cuda.synchronize()
+    for x, y in zip(a + [a16], b + [b16]):
+        assert torch.equal(x, y)
+    assert not torch.equal(b[0], p)
