@@ -452,7 +452,8 @@ int ncn_adam_step_groups(float* param, float* grad, float* m, float* v, void* pa
                          const ncn_adam_groups* groups, float beta1, float beta2, float eps,
                          const float* grad_div_dev, const int32_t* skip_dev, const float* sumsq_dev,
                          const float* lr_bc_dev, ncn_stream_t stream);
-/* sum of squares of grad/(div) into out[0] (ACCUMULATED), and non-finite flag into flag[0] */
+/* sum of squares of grad/(div) into out[0] (ACCUMULATED), and non-finite flag into flag[0].  Deterministic (fixed
+ * summation order: bit-identical on every rank of a data-parallel job); not re-entrant across streams of one device. */
 int ncn_grad_sumsq(const float* grad, int64_t n, const float* grad_div_dev,
                    float* out, int32_t* flag, ncn_stream_t stream);
 /* coef[0] = min(1, max_norm / (sqrt(sumsq[0]) + 1e-6))  (torch clip_grad_norm_), on device */

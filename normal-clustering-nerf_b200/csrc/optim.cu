@@ -116,6 +116,14 @@ adam_kernel(float* __restrict__ param, float* __restrict__ grad, float* __restri
   }
 }
 
+// Squared L2 norm of the (unscaled) gradient, DETERMINISTIC: block partials are parked in a device buffer and the last
+// block to finish (atomic ticket) adds them up in a fixed order, so the same gradient gives the same bits on every rank
+// and every run - the clip coefficient, and with it the replicated parameters of a data-parallel job, stay bit-identical
+// (an atomicAdd of the block partials made the ranks drift apart by ulps).  Not re-entrant across streams of one device.
+constexpr int kSumsqMaxBlocks = 2048;
+__device__ float g_sumsq_partials[kSumsqMaxBlocks];
+__device__ unsigned int g_sumsq_ticket = 0;
+
 __global__ void __launch_bounds__(256)
 sumsq_kernel(const float* __restrict__ grad, int64_t n, const float* __restrict__ grad_div, float* __restrict__ out,
              int32_t* __restrict__ flag) {
@@ -134,6 +142,7 @@ sumsq_kernel(const float* __restrict__ grad, int64_t n, const float* __restrict_
   if (t < n) { const float a = grad[t] * gmul; acc += a * a; bad |= !isfinite(a); }
   acc = warp_sum(acc);
   __shared__ float s[8];
+  __shared__ bool s_last;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   if (lane == 0) s[wid] = acc;
   if (bad && flag) atomicOr(flag, 1);
@@ -141,7 +150,24 @@ sumsq_kernel(const float* __restrict__ grad, int64_t n, const float* __restrict_
   if (wid == 0) {
     acc = lane < 8 ? s[lane] : 0.f;
     acc = warp_sum(acc);
-    if (lane == 0) atomicAdd(out, acc);
+    if (lane == 0) {
+      g_sumsq_partials[blockIdx.x] = acc;
+      __threadfence();
+      s_last = atomicAdd(&g_sumsq_ticket, 1u) == gridDim.x - 1;
+    }
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  float tot = 0.f;                                     // fixed order: thread t adds partials t, t+256, ...; then a fixed tree
+  for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x) tot += __ldcg(&g_sumsq_partials[b]);
+  tot = warp_sum(tot);
+  if (lane == 0) s[wid] = tot;
+  __syncthreads();
+  if (wid == 0) {
+    tot = lane < 8 ? s[lane] : 0.f;
+    tot = warp_sum(tot);
+    if (lane == 0) { *out += tot; g_sumsq_ticket = 0; }
   }
 }
 
@@ -210,7 +236,8 @@ extern "C" int ncn_grad_sumsq(const float* grad, int64_t n, const float* grad_di
   if (n == 0) return NCN_OK;
   NCN_CHECK_PTR(grad); NCN_CHECK_PTR(out);
   if ((uintptr_t)grad & 15) return NCN_E_ALIGN;
-  const int grid = persistent_grid((n + 3) / 4, 256, 8);
+  int grid = persistent_grid((n + 3) / 4, 256, 8);
+  if (grid > kSumsqMaxBlocks) grid = kSumsqMaxBlocks;
   sumsq_kernel<<<grid, 256, 0, as_stream(stream)>>>(grad, n, grad_div_dev, out, flag);
   NCN_LAUNCH_OK();
   return NCN_OK;

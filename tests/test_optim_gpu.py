@@ -107,3 +107,21 @@ def test_adam_groups_equals_per_group_launches(ncn):
     for x, y in zip(a + [a16], b + [b16]):
         assert torch.equal(x, y)
     assert not torch.equal(b[0], p)
+
+
+def test_sumsq_is_deterministic(ncn):
+    """same gradient -> same bits, call after call (the data-parallel ranks derive the clip coefficient from it)"""
+    from ncn_b200 import _lib
+    from ncn_b200._lib import check, ptr, stream
+    L = _lib.lib()
+    g = torch.Generator(device="cuda").manual_seed(11)
+    grad = torch.randn(11445040 + 10240, device="cuda", generator=g)
+    outs = []
+    for _ in range(6):
+        out = torch.zeros(1, device="cuda"); flag = torch.zeros(1, dtype=torch.int32, device="cuda")
+        check(L.ncn_grad_sumsq(ptr(grad), grad.numel(), None, ptr(out), ptr(flag), stream()))
+        outs.append(out.clone())
+    torch.cuda.synchronize()
+    assert all(torch.equal(outs[0], o) for o in outs[1:])
+    want = float((grad.double() ** 2).sum())
+    assert abs(float(outs[0]) - want) <= 1e-5 * want
