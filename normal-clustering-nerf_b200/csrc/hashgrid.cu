@@ -60,9 +60,26 @@ __device__ __forceinline__ void locate8(const float* __restrict__ x, int64_t n, 
     g[d] = (uint32_t)(int)fl;
     c.w[d] = pos - fl;
   }
+  // The 8 corner indices share their per-axis terms (same values as 8 calls of grid_index, ~4x fewer instructions):
+  //   dense level  (res^3 <= size): base + dx + dy*res + dz*res^2, valid while every corner is inside the level;
+  //   hashed level (size = 2^k)   : (x+dx) ^ (y*P1 + dy*P1) ^ (z*P2 + dz*P2), masked.
+  const bool dense = (uint64_t)res * res * res <= (uint64_t)size;
+  if (dense && g[0] + 1u < res && g[1] + 1u < res && g[2] + 1u < res) {
+    const uint32_t r2 = res * res;
+    const uint32_t base = g[0] + g[1] * res + g[2] * r2;
 #pragma unroll
-  for (int k = 0; k < 8; ++k)
-    c.idx[k] = grid_index(g[0] + (k & 1), g[1] + ((k >> 1) & 1), g[2] + ((k >> 2) & 1), res, size);
+    for (int k = 0; k < 8; ++k) c.idx[k] = base + (k & 1) + ((k >> 1) & 1) * res + ((k >> 2) & 1) * r2;
+  } else if (!dense && (size & (size - 1u)) == 0u) {
+    const uint32_t hy0 = g[1] * 2654435761u, hz0 = g[2] * 805459861u;
+    const uint32_t hx[2] = {g[0], g[0] + 1u}, hy[2] = {hy0, hy0 + 2654435761u}, hz[2] = {hz0, hz0 + 805459861u};
+    const uint32_t mask = size - 1u;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) c.idx[k] = (hx[k & 1] ^ hy[(k >> 1) & 1] ^ hz[(k >> 2) & 1]) & mask;
+  } else {
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+      c.idx[k] = grid_index(g[0] + (k & 1), g[1] + ((k >> 1) & 1), g[2] + ((k >> 2) & 1), res, size);
+  }
   if (cell) { cell[0] = g[0] | (g[1] << 16); cell[1] = g[2]; }
 }
 

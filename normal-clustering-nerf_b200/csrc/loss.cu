@@ -102,7 +102,7 @@ normals_bw_kernel(const float* __restrict__ origin, const float* __restrict__ di
 // integer reduction (redux.sync; fixed point 2^20 => order independent => bit-reproducible), publishes its K x 4
 // partial sums in its own shared memory, and after one barrier.cluster every CTA folds all 8 partials through
 // distributed shared memory and updates the (replicated) centroids.  No atomics, no host round trip.
-constexpr int kKmThreads = 256;     // (512 threads: same iteration time - the tile phase is issue bound, not latency bound)
+constexpr int kKmThreads = 512;     // 16 warps: with a 16-CTA cluster a warp owns 1-2 sixteen-point tiles per Lloyd iteration
 constexpr int kKmCluster = 8;        // portable cluster size (fallback)
 constexpr int kKmClusterMax = 16;    // non-portable size tried first: half the tiles per CTA and Lloyd iteration
 constexpr int kKmMaxK = 64;
