@@ -329,6 +329,10 @@ int ncn_field_fwd(const ncn_grid_desc* desc_host, const float* x, const float* d
  * accumulators, 128-row tiles fed by bulk copies (shapes without an instantiation fall back to 0);
  * 0 = warp-MMA dgrad in registers + split-K wgrad kernels.  Returns the old value. */
 int ncn_set_mlp_bwd_impl(int impl);
+/* ncn_march_train* on the constant-step path (cascades == 1, exp_step_factor == 0): 1 (default) = four lanes per ray, each
+ * marching a quarter of the candidate sequence (bit-identical output); 0 = one lane per ray; 2 = four lanes with every
+ * segment re-marched from its predecessor's landing point (test mode for the repair path).  Returns the old value. */
+int ncn_set_march_segments(int mode);
 
 /* Elementwise glue of the NGPMT field (models/ngp_mt.py:157-229, rendering.py:203-212) between the
  * encoder / MLP kernels; every function takes the device-side live row count n_dev (may be NULL).

@@ -110,7 +110,7 @@ __global__ void __launch_bounds__(64)
 march_train_count_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d,
                          const float* __restrict__ hits_t, const uint8_t* __restrict__ bitfield,
                          const float* __restrict__ noise, MarchCfg c, int64_t n_rays,
-                         int32_t* __restrict__ counts, float* __restrict__ ts_scratch) {
+                         int32_t* __restrict__ counts, int32_t* __restrict__ segcnt, float* __restrict__ ts_scratch, int slab_stride) {
   const int lane = threadIdx.x & 31;
   if (lane >= kRaysPerWarp) return;
   const int64_t r = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * kRaysPerWarp + lane;
@@ -125,7 +125,7 @@ march_train_count_kernel(const float* __restrict__ rays_o, const float* __restri
   float t = h.x;
   const float t2 = h.y;
   if (t >= 0.0f && noise != nullptr) t = __fmaf_rn(calc_dt(t, c), noise[r], t);   // raymarching.cu:195-198
-  float* out = ts_scratch + r * (int64_t)c.max_samples;
+  float* out = ts_scratch + r * (int64_t)slab_stride;
   int n = 0;
   if (kSimple) {
     const int max_samples = c.max_samples;
@@ -162,6 +162,123 @@ march_train_count_kernel(const float* __restrict__ rays_o, const float* __restri
     }
   }
   counts[r] = n;
+  reinterpret_cast<int4*>(segcnt)[r] = make_int4(n, 0, 0, 0);
+}
+
+// ---- train: pass 1, constant-dt fast path: FOUR lanes per ray, each marching a quarter of the candidate sequence -----
+// With exp_step_factor == 0 every march visits a subset of ONE fixed sequence of candidate times T_0 = t_start,
+// T_{k+1} = fl(T_k + dt) - an occupied cell emits the candidate and moves to the next one, an empty cell skips forward to
+// the first candidate at or beyond the cell's exit - so the sequence itself does not depend on the occupancy grid.  Lane s
+// of a ray starts at candidate s*Q (Q = max_samples/4; it gets there with s*Q dependent additions, a few clocks each) and
+// marches until it passes candidate (s+1)*Q, writing its samples to its own region of the ray's slab.  The speculation
+// "candidate s*Q is visited by the real march" is then checked segment by segment: the previous segment must have landed
+// exactly on s*Q, or - the common case in empty space - on the candidate this segment's first (empty-cell) skip reached;
+// otherwise the lane re-marches its segment from the true landing point.  Every emitted t is the value the serial march
+// produces (same chain, same cell tests, same skip targets), so the result stays bit-identical to the reference while the
+// serial dependent chain per lane is 4x shorter.
+constexpr int kSegs = 4;
+constexpr int kSegPad = 16;        // slack behind each segment region (a segment holds at most Q (+1 for the last) samples)
+
+struct SegWalk { float t; int idx; int n; float v1; bool first_occ; bool any; };
+
+__device__ __forceinline__ void march_segment(SegWalk& w, bool go, int idx_end, int cap, float t2, float ox, float oy, float oz,
+                                              float dx, float dy, float dz, float ix, float iy, float iz, float sx, float sy,
+                                              float sz, float dt, float mip_bound, float mb_inv, float gs_f, float gs_m1,
+                                              float gs_inv, const uint8_t* __restrict__ bitfield, float* __restrict__ out) {
+  float t = w.t;
+  int idx = w.idx, n = 0;
+  bool first = true;
+  w.first_occ = false; w.any = false; w.v1 = t;
+  while (go && t < t2 && idx < idx_end && n < cap) {
+    const float x = __fmaf_rn(dx, t, ox), y = __fmaf_rn(dy, t, oy), z = __fmaf_rn(dz, t, oz);
+    const int nx = (int)fmaxf(0.0f, fminf(__fmul_rn(__fmul_rn(__fmaf_rn(x, mb_inv, 1.0f), 0.5f), gs_f), gs_m1));
+    const int ny = (int)fmaxf(0.0f, fminf(__fmul_rn(__fmul_rn(__fmaf_rn(y, mb_inv, 1.0f), 0.5f), gs_f), gs_m1));
+    const int nz = (int)fmaxf(0.0f, fminf(__fmul_rn(__fmul_rn(__fmaf_rn(z, mb_inv, 1.0f), 0.5f), gs_f), gs_m1));
+    const uint32_t cell = morton3d((uint32_t)nx, (uint32_t)ny, (uint32_t)nz);
+    const bool occ = (__ldg(bitfield + (cell >> 3)) >> (cell & 7u)) & 1u;
+    if (occ) {
+      out[n++] = t;
+      t = __fadd_rn(t, dt);
+      ++idx;
+    } else {
+      const float tx = __fmul_rn(__fmaf_rn(mip_bound, __fmaf_rn(__fmul_rn(__fadd_rn(__fadd_rn((float)nx, 0.5f), sx), gs_inv), 2.0f, -1.0f), -x), ix);
+      const float ty = __fmul_rn(__fmaf_rn(mip_bound, __fmaf_rn(__fmul_rn(__fadd_rn(__fadd_rn((float)ny, 0.5f), sy), gs_inv), 2.0f, -1.0f), -y), iy);
+      const float tz = __fmul_rn(__fmaf_rn(mip_bound, __fmaf_rn(__fmul_rn(__fadd_rn(__fadd_rn((float)nz, 0.5f), sz), gs_inv), 2.0f, -1.0f), -z), iz);
+      const float t_target = __fadd_rn(t, fmaxf(0.0f, fminf(tx, fminf(ty, tz))));
+      do { t = __fadd_rn(t, dt); ++idx; } while (t < t_target);
+    }
+    if (first) { first = false; w.first_occ = occ; w.v1 = t; w.any = true; }
+  }
+  w.t = t; w.idx = idx; w.n = n;
+}
+
+__global__ void __launch_bounds__(64)
+march_train_count_seg_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d,
+                             const float* __restrict__ hits_t, const uint8_t* __restrict__ bitfield,
+                             const float* __restrict__ noise, MarchCfg c, int64_t n_rays, int32_t* __restrict__ counts,
+                             int32_t* __restrict__ segcnt, float* __restrict__ slabs, int slab_stride, int seg_stride, int force_redo) {
+  const int lane = threadIdx.x & 31;
+  const int seg = lane & (kSegs - 1);
+  const int64_t r = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * (32 / kSegs) + (lane >> 2);
+  const bool have_ray = r < n_rays;
+  const int64_t rr = have_ray ? r : 0;
+  const float dt = c.dt_min, mip_bound = fminf(0.5f, c.scale), mb_inv = __frcp_rn(mip_bound);
+  const float gs_f = c.gs_f, gs_m1 = c.gs_m1, gs_inv = c.gs_inv;
+  const float ox = rays_o[3 * rr], oy = rays_o[3 * rr + 1], oz = rays_o[3 * rr + 2];
+  const float dx = rays_d[3 * rr], dy = rays_d[3 * rr + 1], dz = rays_d[3 * rr + 2];
+  const float ix = __frcp_rn(dx), iy = __frcp_rn(dy), iz = __frcp_rn(dz);
+  const float sx = copysignf(0.5f, dx), sy = copysignf(0.5f, dy), sz = copysignf(0.5f, dz);
+  const float2 h = reinterpret_cast<const float2*>(hits_t)[rr];
+  float t0 = h.x;
+  const float t2 = h.y;
+  if (t0 >= 0.0f && noise != nullptr) t0 = __fmaf_rn(dt, noise[rr], t0);            // raymarching.cu:195-198
+  const bool ray_live = have_ray && 0.0f <= t0;
+  const int Q = c.max_samples / kSegs;
+  const int idx_begin = seg * Q, idx_end = seg == kSegs - 1 ? 0x7fffffff : (seg + 1) * Q;
+  const int cap = seg == kSegs - 1 ? Q + kSegPad : Q;
+  float* out = slabs + rr * (int64_t)slab_stride + seg * seg_stride;
+  // candidate time at the start of this lane's segment: idx_begin dependent additions
+  float ts = t0;
+#pragma unroll 8
+  for (int i = 0; i < idx_begin; ++i) ts = __fadd_rn(ts, dt);
+  const float start_t = ts;
+  SegWalk w;
+  w.t = start_t; w.idx = idx_begin;
+  march_segment(w, ray_live, idx_end, cap, t2, ox, oy, oz, dx, dy, dz, ix, iy, iz, sx, sy, sz, dt, mip_bound, mb_inv, gs_f, gs_m1, gs_inv,
+                bitfield, out);
+  // ---- stitch: validate (or re-march) segments 1..3 in order.  All lanes run the loop; shuffles stay inside the 4-lane group
+  const int grp = lane & ~(kSegs - 1);
+#pragma unroll
+  for (int s = 1; s < kSegs; ++s) {
+    const float L_t = __shfl_sync(0xffffffffu, w.t, grp + s - 1);
+    const int L_idx = __shfl_sync(0xffffffffu, w.idx, grp + s - 1);
+    const bool mine = seg == s;
+    const bool over = !(L_t < t2);                                  // the ray ended inside an earlier segment
+    bool redo = false;
+    if (mine && ray_live) {
+      if (over) { w.n = 0; w.t = L_t; w.idx = L_idx; }
+      else if (force_redo) { redo = true; w.t = L_t; w.idx = L_idx; }                         // test mode: always repair
+      else if (L_idx == idx_begin) { /* landed exactly on this segment's first candidate */ }
+      else if (w.any && !w.first_occ && L_t == w.v1) { /* both skipped to the same candidate out of the shared empty cell */ }
+      else { redo = true; w.t = L_t; w.idx = L_idx; }
+    }
+    if (__any_sync(0xffffffffu, redo)) {
+      SegWalk w2 = w;
+      march_segment(w2, redo, idx_end, cap, t2, ox, oy, oz, dx, dy, dz, ix, iy, iz, sx, sy, sz, dt, mip_bound, mb_inv, gs_f, gs_m1,
+                    gs_inv, bitfield, out);
+      if (redo) w = w2;
+    }
+  }
+  // ---- counts (the reference stops at max_samples samples: trim from the back)
+  int n = ray_live ? w.n : 0;
+  int n0 = __shfl_sync(0xffffffffu, n, grp), n1 = __shfl_sync(0xffffffffu, n, grp + 1), n2 = __shfl_sync(0xffffffffu, n, grp + 2),
+      n3 = __shfl_sync(0xffffffffu, n, grp + 3);
+  const int m = c.max_samples;
+  n0 = min(n0, m); n1 = min(n1, m - n0); n2 = min(n2, m - n0 - n1); n3 = min(n3, m - n0 - n1 - n2);
+  if (have_ray && seg == 0) {
+    counts[r] = n0 + n1 + n2 + n3;
+    reinterpret_cast<int4*>(segcnt)[r] = make_int4(n0, n1, n2, n3);
+  }
 }
 
 // ---- train: pass 2 (single CTA): exclusive scan of counts -> rays_a, counter ---------------
@@ -217,6 +334,7 @@ march_scan_kernel(const int32_t* __restrict__ counts, int64_t n_rays, int64_t* _
 __global__ void __launch_bounds__(256)
 march_train_expand_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d,
                           const int64_t* __restrict__ rays_a, const float* __restrict__ ts_scratch,
+                          const int32_t* __restrict__ segcnt, int slab_stride, int seg_stride,
                           MarchCfg c, int64_t n_rays, int64_t capacity,
                           float* __restrict__ xyzs, float* __restrict__ dirs,
                           float* __restrict__ deltas, float* __restrict__ ts) {
@@ -229,11 +347,15 @@ march_train_expand_kernel(const float* __restrict__ rays_o, const float* __restr
     if (n == 0) continue;
     const float ox = rays_o[3 * r], oy = rays_o[3 * r + 1], oz = rays_o[3 * r + 2];
     const float dx = rays_d[3 * r], dy = rays_d[3 * r + 1], dz = rays_d[3 * r + 2];
-    const float* src = ts_scratch + r * (int64_t)c.max_samples;
+    const float* src = ts_scratch + r * (int64_t)slab_stride;
+    const int4 sc = reinterpret_cast<const int4*>(segcnt)[r];      // samples per segment region of the ray's slab
+    const int p1 = sc.x, p2 = p1 + sc.y, p3 = p2 + sc.z;
     for (int k = lane; k < n; k += 32) {
       const int64_t s = start + k;
       if (s >= capacity) break;
-      const float t = src[k];
+      const int sg = k < p1 ? 0 : (k < p2 ? 1 : (k < p3 ? 2 : 3));
+      const int off = sg * seg_stride + (k - (sg == 0 ? 0 : (sg == 1 ? p1 : (sg == 2 ? p2 : p3))));
+      const float t = src[off];
       float* p = xyzs + 3 * s;
       p[0] = __fmaf_rn(dx, t, ox); p[1] = __fmaf_rn(dy, t, oy); p[2] = __fmaf_rn(dz, t, oz);
       float* q = dirs + 3 * s;
@@ -313,10 +435,21 @@ static int make_cfg(MarchCfg* c, int cascades, float scale, float dt_scale, floa
 
 static inline size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 
+// workspace = [counts (R) i32 | samples per segment region (R,4) i32 | per-ray slabs of sample times (R, slab_stride) f32];
+// a slab is 4 segment regions of seg_stride floats (the general kernel uses it as one region of >= max_samples floats)
+static inline int march_seg_stride(int max_samples) { return (max_samples + kSegs - 1) / kSegs + kSegPad; }
+static inline int march_slab_stride(int max_samples) { return kSegs * march_seg_stride(max_samples); }
+static inline size_t march_off_segcnt(int64_t n_rays) { return align256((size_t)n_rays * sizeof(int32_t)); }
+static inline size_t march_off_slabs(int64_t n_rays) { return march_off_segcnt(n_rays) + align256((size_t)n_rays * kSegs * sizeof(int32_t)); }
+
 extern "C" size_t ncn_march_train_workspace_bytes(int64_t n_rays, int max_samples) {
   if (n_rays < 0 || max_samples < 1) return 0;
-  return align256((size_t)n_rays * sizeof(int32_t)) + align256((size_t)n_rays * (size_t)max_samples * sizeof(float));
+  return march_off_slabs(n_rays) + align256((size_t)n_rays * (size_t)march_slab_stride(max_samples) * sizeof(float));
 }
+
+static int g_march_segments = 1;   // 1 = four lanes per ray on the constant-dt path (default), 0 = one lane per ray, 2 = four lanes and
+                                   // every segment re-marched from its predecessor's landing point (exercises the repair path)
+extern "C" int ncn_set_march_segments(int mode) { const int old = g_march_segments; g_march_segments = mode; return old; }
 
 extern "C" int ncn_march_train_count(const float* rays_o, const float* rays_d, const float* hits_t,
                                      const uint8_t* density_bitfield, int cascades, float scale,
@@ -334,15 +467,21 @@ extern "C" int ncn_march_train_count(const float* rays_o, const float* rays_d, c
     if (workspace_bytes < ncn_march_train_workspace_bytes(n_rays, max_samples)) return NCN_E_SIZE;
     if (((uintptr_t)hits_t & 7) || ((uintptr_t)workspace & 255)) return NCN_E_ALIGN;
     int32_t* counts = (int32_t*)workspace;
-    float* ts_scratch = (float*)((char*)workspace + align256((size_t)n_rays * sizeof(int32_t)));
+    int32_t* segcnt = (int32_t*)((char*)workspace + march_off_segcnt(n_rays));
+    float* ts_scratch = (float*)((char*)workspace + march_off_slabs(n_rays));
+    const int slab_stride = march_slab_stride(max_samples), seg_stride = march_seg_stride(max_samples);
     const int threads = 64;                                   // 2 warps x kRaysPerWarp rays
     const unsigned blocks = (unsigned)ceil_div(n_rays, (threads / 32) * kRaysPerWarp);
-    if (c.cascades == 1 && c.const_dt)
+    if (c.cascades == 1 && c.const_dt && g_march_segments != 0 && max_samples % kSegs == 0 && max_samples >= 64)
+      march_train_count_seg_kernel<<<blocks, threads, 0, as_stream(stream)>>>(rays_o, rays_d, hits_t, density_bitfield, noise, c, n_rays,
+                                                                              counts, segcnt, ts_scratch, slab_stride, seg_stride,
+                                                                              g_march_segments == 2 ? 1 : 0);
+    else if (c.cascades == 1 && c.const_dt)
       march_train_count_kernel<true><<<blocks, threads, 0, as_stream(stream)>>>(rays_o, rays_d, hits_t, density_bitfield, noise, c,
-                                                                             n_rays, counts, ts_scratch);
+                                                                             n_rays, counts, segcnt, ts_scratch, slab_stride);
     else
       march_train_count_kernel<false><<<blocks, threads, 0, as_stream(stream)>>>(rays_o, rays_d, hits_t, density_bitfield, noise, c,
-                                                                              n_rays, counts, ts_scratch);
+                                                                              n_rays, counts, segcnt, ts_scratch, slab_stride);
     NCN_LAUNCH_OK();
     march_scan_kernel<<<1, kScanThreads, 0, as_stream(stream)>>>(counts, n_rays, rays_a, counter);
   } else {
@@ -365,10 +504,11 @@ extern "C" int ncn_march_train_expand(const float* rays_o, const float* rays_d, 
   NCN_CHECK_PTR(rays_o); NCN_CHECK_PTR(rays_d); NCN_CHECK_PTR(rays_a); NCN_CHECK_PTR(workspace);
   NCN_CHECK_PTR(xyzs); NCN_CHECK_PTR(dirs); NCN_CHECK_PTR(deltas); NCN_CHECK_PTR(ts);
   if (workspace_bytes < ncn_march_train_workspace_bytes(n_rays, max_samples)) return NCN_E_SIZE;
-  const float* ts_scratch = (const float*)((const char*)workspace + align256((size_t)n_rays * sizeof(int32_t)));
+  const int32_t* segcnt = (const int32_t*)((const char*)workspace + march_off_segcnt(n_rays));
+  const float* ts_scratch = (const float*)((const char*)workspace + march_off_slabs(n_rays));
   const int grid = persistent_grid(n_rays * 32, 256, 8);
-  march_train_expand_kernel<<<grid, 256, 0, as_stream(stream)>>>(rays_o, rays_d, rays_a, ts_scratch, c, n_rays,
-                                                                 capacity, xyzs, dirs, deltas, ts);
+  march_train_expand_kernel<<<grid, 256, 0, as_stream(stream)>>>(rays_o, rays_d, rays_a, ts_scratch, segcnt, march_slab_stride(max_samples),
+                                                                 march_seg_stride(max_samples), c, n_rays, capacity, xyzs, dirs, deltas, ts);
   NCN_LAUNCH_OK();
   return NCN_OK;
 }

@@ -144,6 +144,32 @@ def test_march_train_bit_exact(ncn, vren_ref, scene, kind, n, exp_step_factor, c
         assert total > 5 * n      # the scene is not degenerate
 
 
+@pytest.mark.parametrize("mode", [0, 1, 2])
+@pytest.mark.parametrize("kind,n", [("patch", 8192), ("random", 30000)])
+def test_march_train_segment_modes(ncn, vren_ref, scene, kind, n, mode):
+    """constant-step path: one lane per ray (0), four speculative lanes per ray (1, default) and four lanes with every
+    segment re-marched from its predecessor's landing point (2, the repair path) - all bit-identical to the reference."""
+    from ncn_b200 import _lib, vren
+    rays_o, rays_d = _batch(scene, kind, n, seed=11, cam="hypersim")
+    rays_d = rays_d.clone(); rays_d[:64, 1] = 0.0
+    rays_o = rays_o.clone(); rays_o[64:128] *= 5.0
+    hits_t = _hits(vren_ref, scene, rays_o, rays_d)
+    noise = torch.rand(n, device="cuda", generator=torch.Generator(device="cuda").manual_seed(2))
+    args = (rays_o, rays_d, hits_t[:, 0], scene["bitfield"], scene["cascades"], scene["scale"], 0.0,
+            noise, scene["grid_size"], scene["max_samples"])
+    old = _lib.lib().ncn_set_march_segments(mode)
+    try:
+        ra, xyzs, dirs, deltas, ts, counter = vren.raymarching_train(*args)
+    finally:
+        _lib.lib().ncn_set_march_segments(old)
+    rra, rxyzs, rdirs, rdeltas, rts, rcounter = vren_ref.raymarching_train(*args)
+    assert counter.tolist() == rcounter.tolist()
+    cra, (cx, cd, cdt, ct) = _canon(rra, [rxyzs, rdirs, rdeltas, rts])
+    assert torch.equal(ra[:, 2], cra[:, 2])
+    assert _bits_equal(ts, ct) and _bits_equal(deltas, cdt) and _bits_equal(xyzs, cx) and _bits_equal(dirs, cd)
+    assert int(counter[0]) > 5 * n            # non-degenerate scene: rays cross several 256-candidate segments
+
+
 def test_march_train_multi_cascade(ncn, vren_ref):
     """cascades > 1 (scale 2): mip selection from position and step size."""
     from ncn_b200 import vren, synth
