@@ -4,6 +4,7 @@
 // the hash table / 1e-6 for the MLPs), GradScaler.unscale_, clip_grad_norm_(0.05)
 // (train_nerf.py:954-955, opt.py:159) and the per-call fp32->fp16 parameter cast of the tcnn
 // binding - fused into ONE streaming pass: read p, g, m, v (16 B) - write p, m, v, g=0, p16 (18 B).
+#include <cstdlib>
 #include "ncn_common.cuh"
 
 namespace ncn {
@@ -11,7 +12,12 @@ namespace ncn {
 // CTAs per SM of the streaming pass.  2 x 256 threads x 8 float4 loads in flight still saturate HBM, and leave half of the
 // register file / thread slots to the latency-bound march kernels that run beside the deferred optimizer in the step graph
 // (at 4 the optimizer owned every register of the SM and the march simply queued behind it).
-constexpr int kAdamCtasPerSm = 2;
+static int adam_ctas_per_sm() {      // developer knob NCN_ADAM_CTAS (A/B measurements); default 2
+  static int v = 0;
+  if (v == 0) { const char* e = getenv("NCN_ADAM_CTAS"); v = e ? atoi(e) : 2; if (v < 1 || v > 8) v = 2; }
+  return v;
+}
+#define kAdamCtasPerSm adam_ctas_per_sm()
 
 struct AdamArgs {
   float lr, beta1, beta2, eps, weight_decay, bc1, bc2;
