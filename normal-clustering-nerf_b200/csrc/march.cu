@@ -287,7 +287,7 @@ march_train_count_seg_kernel(const float* __restrict__ rays_o, const float* __re
 constexpr int kScanThreads = 1024;
 constexpr int kScanItems = 8;
 __global__ void __launch_bounds__(kScanThreads)
-march_scan_kernel(const int32_t* __restrict__ counts, int64_t n_rays, int64_t* __restrict__ rays_a,
+march_scan_kernel(const int32_t* __restrict__ counts, int64_t n_rays, int32_t* __restrict__ starts,
                   int32_t* __restrict__ counter) {
   __shared__ int s_warp[32];
   __shared__ int s_carry;
@@ -317,11 +317,15 @@ march_scan_kernel(const int32_t* __restrict__ counts, int64_t n_rays, int64_t* _
     }
     __syncthreads();
     int excl = s_carry + s_warp[wid] + incl - tot;
+    int st[kScanItems];
 #pragma unroll
-    for (int q = 0; q < kScanItems; ++q) {
-      const int64_t r = r0 + q;
-      if (r < n_rays) { rays_a[3 * r + 0] = r; rays_a[3 * r + 1] = excl; rays_a[3 * r + 2] = v[q]; }
-      excl += v[q];
+    for (int q = 0; q < kScanItems; ++q) { st[q] = excl; excl += v[q]; }
+    if (r0 + kScanItems <= n_rays) {      // two 16-byte stores; the (R,3) i64 rays_a rows are written by a parallel kernel
+      *reinterpret_cast<int4*>(starts + r0) = make_int4(st[0], st[1], st[2], st[3]);
+      *reinterpret_cast<int4*>(starts + r0 + 4) = make_int4(st[4], st[5], st[6], st[7]);
+    } else {
+#pragma unroll
+      for (int q = 0; q < kScanItems; ++q) if (r0 + q < n_rays) starts[r0 + q] = st[q];
     }
     __syncthreads();
     if (threadIdx.x == kScanThreads - 1) s_carry = excl;
@@ -330,10 +334,24 @@ march_scan_kernel(const int32_t* __restrict__ counts, int64_t n_rays, int64_t* _
   if (threadIdx.x == 0) { counter[0] = s_carry; counter[1] = (int32_t)n_rays; }
 }
 
+// rays_a (R,3) i64 = [ray, start, n] from the compact count / start arrays (all SMs; one CTA writing 196 KB of 8-byte
+// rows was 12 us of the old scan kernel)
+__global__ void __launch_bounds__(256)
+march_rays_a_kernel(const int32_t* __restrict__ counts, const int32_t* __restrict__ starts, int64_t n_rays,
+                    int64_t* __restrict__ rays_a) {
+  const int64_t total = n_rays * 3, stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int64_t r = i / 3;
+    const int j = (int)(i - 3 * r);
+    rays_a[i] = j == 0 ? r : (j == 1 ? (int64_t)starts[r] : (int64_t)counts[r]);
+  }
+}
+
 // ---- train: pass 3 (one warp per ray): expand recorded ts into the sample arrays -----------
 __global__ void __launch_bounds__(256)
 march_train_expand_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d,
-                          const int64_t* __restrict__ rays_a, const float* __restrict__ ts_scratch,
+                          const int32_t* __restrict__ counts, const int32_t* __restrict__ starts,
+                          int64_t* __restrict__ rays_a_out, const float* __restrict__ ts_scratch,
                           const int32_t* __restrict__ segcnt, int slab_stride, int seg_stride,
                           MarchCfg c, int64_t n_rays, int64_t capacity,
                           float* __restrict__ xyzs, float* __restrict__ dirs,
@@ -342,8 +360,9 @@ march_train_expand_kernel(const float* __restrict__ rays_o, const float* __restr
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   for (int64_t r = warp; r < n_rays; r += n_warps) {
-    const int64_t start = rays_a[3 * r + 1];
-    const int n = (int)rays_a[3 * r + 2];
+    const int64_t start = starts[r];
+    const int n = counts[r];
+    if (rays_a_out != nullptr && lane < 3) rays_a_out[3 * r + lane] = lane == 0 ? r : (lane == 1 ? start : (int64_t)n);
     if (n == 0) continue;
     const float ox = rays_o[3 * r], oy = rays_o[3 * r + 1], oz = rays_o[3 * r + 2];
     const float dx = rays_d[3 * r], dy = rays_d[3 * r + 1], dz = rays_d[3 * r + 2];
@@ -435,11 +454,12 @@ static int make_cfg(MarchCfg* c, int cascades, float scale, float dt_scale, floa
 
 static inline size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 
-// workspace = [counts (R) i32 | samples per segment region (R,4) i32 | per-ray slabs of sample times (R, slab_stride) f32];
+// workspace = [counts (R) i32 | starts (R) i32 | samples per segment region (R,4) i32 | per-ray slabs of sample times (R, slab_stride) f32];
 // a slab is 4 segment regions of seg_stride floats (the general kernel uses it as one region of >= max_samples floats)
 static inline int march_seg_stride(int max_samples) { return (max_samples + kSegs - 1) / kSegs + kSegPad; }
 static inline int march_slab_stride(int max_samples) { return kSegs * march_seg_stride(max_samples); }
-static inline size_t march_off_segcnt(int64_t n_rays) { return align256((size_t)n_rays * sizeof(int32_t)); }
+static inline size_t march_off_starts(int64_t n_rays) { return align256((size_t)n_rays * sizeof(int32_t)); }
+static inline size_t march_off_segcnt(int64_t n_rays) { return 2 * align256((size_t)n_rays * sizeof(int32_t)); }
 static inline size_t march_off_slabs(int64_t n_rays) { return march_off_segcnt(n_rays) + align256((size_t)n_rays * kSegs * sizeof(int32_t)); }
 
 extern "C" size_t ncn_march_train_workspace_bytes(int64_t n_rays, int max_samples) {
@@ -451,11 +471,11 @@ static int g_march_segments = 1;   // 1 = four lanes per ray on the constant-dt 
                                    // every segment re-marched from its predecessor's landing point (exercises the repair path)
 extern "C" int ncn_set_march_segments(int mode) { const int old = g_march_segments; g_march_segments = mode; return old; }
 
-extern "C" int ncn_march_train_count(const float* rays_o, const float* rays_d, const float* hits_t,
-                                     const uint8_t* density_bitfield, int cascades, float scale,
-                                     float exp_step_factor, const float* noise, int grid_size, int max_samples,
-                                     int64_t n_rays, int64_t* rays_a, int32_t* counter, void* workspace,
-                                     size_t workspace_bytes, ncn_stream_t stream) {
+static int march_count_impl(const float* rays_o, const float* rays_d, const float* hits_t,
+                            const uint8_t* density_bitfield, int cascades, float scale,
+                            float exp_step_factor, const float* noise, int grid_size, int max_samples,
+                            int64_t n_rays, int64_t* rays_a, bool write_rays_a, int32_t* counter, void* workspace,
+                            size_t workspace_bytes, ncn_stream_t stream) {
   MarchCfg c;
   int rc = make_cfg(&c, cascades, scale, scale, exp_step_factor, grid_size, max_samples);
   if (rc) return rc;
@@ -467,6 +487,7 @@ extern "C" int ncn_march_train_count(const float* rays_o, const float* rays_d, c
     if (workspace_bytes < ncn_march_train_workspace_bytes(n_rays, max_samples)) return NCN_E_SIZE;
     if (((uintptr_t)hits_t & 7) || ((uintptr_t)workspace & 255)) return NCN_E_ALIGN;
     int32_t* counts = (int32_t*)workspace;
+    int32_t* starts = (int32_t*)((char*)workspace + march_off_starts(n_rays));
     int32_t* segcnt = (int32_t*)((char*)workspace + march_off_segcnt(n_rays));
     float* ts_scratch = (float*)((char*)workspace + march_off_slabs(n_rays));
     const int slab_stride = march_slab_stride(max_samples), seg_stride = march_seg_stride(max_samples);
@@ -483,19 +504,31 @@ extern "C" int ncn_march_train_count(const float* rays_o, const float* rays_d, c
       march_train_count_kernel<false><<<blocks, threads, 0, as_stream(stream)>>>(rays_o, rays_d, hits_t, density_bitfield, noise, c,
                                                                               n_rays, counts, segcnt, ts_scratch, slab_stride);
     NCN_LAUNCH_OK();
-    march_scan_kernel<<<1, kScanThreads, 0, as_stream(stream)>>>(counts, n_rays, rays_a, counter);
+    march_scan_kernel<<<1, kScanThreads, 0, as_stream(stream)>>>(counts, n_rays, starts, counter);
+    NCN_LAUNCH_OK();
+    if (write_rays_a)
+      march_rays_a_kernel<<<persistent_grid(n_rays * 3, 256, 4), 256, 0, as_stream(stream)>>>(counts, starts, n_rays, rays_a);
   } else {
-    march_scan_kernel<<<1, kScanThreads, 0, as_stream(stream)>>>(nullptr, 0, rays_a, counter);
+    march_scan_kernel<<<1, kScanThreads, 0, as_stream(stream)>>>(nullptr, 0, nullptr, counter);
   }
   NCN_LAUNCH_OK();
   return NCN_OK;
 }
 
-extern "C" int ncn_march_train_expand(const float* rays_o, const float* rays_d, const int64_t* rays_a,
-                                      float exp_step_factor, float scale, int grid_size, int max_samples,
-                                      int64_t n_rays, int64_t capacity, float* xyzs, float* dirs, float* deltas,
-                                      float* ts, const void* workspace, size_t workspace_bytes,
-                                      ncn_stream_t stream) {
+extern "C" int ncn_march_train_count(const float* rays_o, const float* rays_d, const float* hits_t,
+                                     const uint8_t* density_bitfield, int cascades, float scale,
+                                     float exp_step_factor, const float* noise, int grid_size, int max_samples,
+                                     int64_t n_rays, int64_t* rays_a, int32_t* counter, void* workspace,
+                                     size_t workspace_bytes, ncn_stream_t stream) {
+  return march_count_impl(rays_o, rays_d, hits_t, density_bitfield, cascades, scale, exp_step_factor, noise, grid_size, max_samples,
+                          n_rays, rays_a, true, counter, workspace, workspace_bytes, stream);
+}
+
+static int march_expand_impl(const float* rays_o, const float* rays_d, const int64_t* rays_a, int64_t* rays_a_out,
+                             float exp_step_factor, float scale, int grid_size, int max_samples,
+                             int64_t n_rays, int64_t capacity, float* xyzs, float* dirs, float* deltas,
+                             float* ts, const void* workspace, size_t workspace_bytes,
+                             ncn_stream_t stream) {
   MarchCfg c;
   int rc = make_cfg(&c, 1, scale, scale, exp_step_factor, grid_size, max_samples);
   if (rc) return rc;
@@ -504,13 +537,26 @@ extern "C" int ncn_march_train_expand(const float* rays_o, const float* rays_d, 
   NCN_CHECK_PTR(rays_o); NCN_CHECK_PTR(rays_d); NCN_CHECK_PTR(rays_a); NCN_CHECK_PTR(workspace);
   NCN_CHECK_PTR(xyzs); NCN_CHECK_PTR(dirs); NCN_CHECK_PTR(deltas); NCN_CHECK_PTR(ts);
   if (workspace_bytes < ncn_march_train_workspace_bytes(n_rays, max_samples)) return NCN_E_SIZE;
+  const int32_t* counts = (const int32_t*)workspace;
+  const int32_t* starts = (const int32_t*)((const char*)workspace + march_off_starts(n_rays));
   const int32_t* segcnt = (const int32_t*)((const char*)workspace + march_off_segcnt(n_rays));
   const float* ts_scratch = (const float*)((const char*)workspace + march_off_slabs(n_rays));
   const int grid = persistent_grid(n_rays * 32, 256, 8);
-  march_train_expand_kernel<<<grid, 256, 0, as_stream(stream)>>>(rays_o, rays_d, rays_a, ts_scratch, segcnt, march_slab_stride(max_samples),
-                                                                 march_seg_stride(max_samples), c, n_rays, capacity, xyzs, dirs, deltas, ts);
+  march_train_expand_kernel<<<grid, 256, 0, as_stream(stream)>>>(rays_o, rays_d, counts, starts, rays_a_out, ts_scratch, segcnt,
+                                                                 march_slab_stride(max_samples), march_seg_stride(max_samples), c, n_rays,
+                                                                 capacity, xyzs, dirs, deltas, ts);
   NCN_LAUNCH_OK();
   return NCN_OK;
+}
+
+// rays_a must be the array ncn_march_train_count filled (the per-ray counts / starts are re-read from the workspace)
+extern "C" int ncn_march_train_expand(const float* rays_o, const float* rays_d, const int64_t* rays_a,
+                                      float exp_step_factor, float scale, int grid_size, int max_samples,
+                                      int64_t n_rays, int64_t capacity, float* xyzs, float* dirs, float* deltas,
+                                      float* ts, const void* workspace, size_t workspace_bytes,
+                                      ncn_stream_t stream) {
+  return march_expand_impl(rays_o, rays_d, rays_a, nullptr, exp_step_factor, scale, grid_size, max_samples, n_rays, capacity, xyzs, dirs,
+                           deltas, ts, workspace, workspace_bytes, stream);
 }
 
 extern "C" int ncn_march_train(const float* rays_o, const float* rays_d, const float* hits_t,
@@ -518,11 +564,13 @@ extern "C" int ncn_march_train(const float* rays_o, const float* rays_d, const f
                                const float* noise, int grid_size, int max_samples, int64_t n_rays, int64_t capacity,
                                int64_t* rays_a, float* xyzs, float* dirs, float* deltas, float* ts,
                                int32_t* counter, void* workspace, size_t workspace_bytes, ncn_stream_t stream) {
-  int rc = ncn_march_train_count(rays_o, rays_d, hits_t, density_bitfield, cascades, scale, exp_step_factor, noise,
-                                 grid_size, max_samples, n_rays, rays_a, counter, workspace, workspace_bytes, stream);
+  // count -> scan -> expand; the (R,3) rays_a rows are written by the (all-SM) expansion kernel instead of a separate pass
+  const bool expand_writes = n_rays > 0 && capacity > 0;
+  int rc = march_count_impl(rays_o, rays_d, hits_t, density_bitfield, cascades, scale, exp_step_factor, noise, grid_size, max_samples,
+                            n_rays, rays_a, !expand_writes, counter, workspace, workspace_bytes, stream);
   if (rc) return rc;
-  return ncn_march_train_expand(rays_o, rays_d, rays_a, exp_step_factor, scale, grid_size, max_samples, n_rays,
-                                capacity, xyzs, dirs, deltas, ts, workspace, workspace_bytes, stream);
+  return march_expand_impl(rays_o, rays_d, rays_a, expand_writes ? rays_a : nullptr, exp_step_factor, scale, grid_size, max_samples,
+                           n_rays, capacity, xyzs, dirs, deltas, ts, workspace, workspace_bytes, stream);
 }
 
 extern "C" int ncn_march_test(const float* rays_o, const float* rays_d, float* hits_t,
