@@ -36,6 +36,7 @@ def parse():
     ap.add_argument("--rays", type=int, default=8192)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--breakdown", default=None, help="write a per-call CUDA-event breakdown (json) to this path")
+    ap.add_argument("--update-interval", type=int, default=None, help="occupancy-grid update period in steps (default: the reference's 16)")
     ap.add_argument("--no-graph", action="store_true", help="run the fused step eagerly instead of replaying its CUDA graph")
     return ap.parse_args()
 
@@ -167,6 +168,8 @@ def run_ours(args):
     vren.packbits(tr.model.density_grid, 5.9, tr.model.density_bitfield)
     poses = synth.camera_poses(50, 0); dirs = synth.pixel_directions("hypersim")
     tr.set_cameras(poses, dirs)
+    if args.update_interval:
+        tr.hp["update_interval"] = args.update_interval
     tr.global_step = 3008          # steady state: clustering weights on, past the occupancy warm-up
     # The occupancy-grid update (1 M-point density query + decay/max + packbits, every 16 steps) runs in full, but
     # with a RANDOM-INIT field it would flood the grid within a few updates and the samples/ray would drift with the

@@ -97,6 +97,18 @@ int ncn_packbits(const float* density_grid, int64_t n_bytes, float threshold,
  * stats[0] (f32 sum) / stats[1] (f32 count) which the caller zeroed. */
 int ncn_density_grid_update(float* density_grid, const float* density_tmp, int64_t n_cells,
                             float decay, float* stats, ncn_stream_t stream);
+/* Sampling half of the occupancy-grid update (models/ngp_mt.py:254-271 sample_uniform_and_occupied_cells + the jittered
+ * cell centres of :345-357) in one launch: m uniformly drawn cells followed by m cells drawn uniformly among the occupied
+ * ones (occ_csum = inclusive cumsum (G^3) i32 of density_grid > threshold; upper_bound = searchsorted(right=True), clamped
+ * to G^3-1) -> indices (2m) i32 Morton order, xyz (2m,3) f32 = cell centre * (s - s/G) + U(-1,1) * s/G.
+ * Random numbers come from a counter hash of *seed_dev (device i64; ncn_grid_scatter_density advances it), so a captured
+ * CUDA graph draws new cells on every replay.  The random stream is not the reference's torch stream (no parity there). */
+int ncn_grid_sample_cells(const int32_t* occ_csum, int grid_size, int64_t m, float s, const int64_t* seed_dev,
+                          int32_t* indices, float* xyz, ncn_stream_t stream);
+/* density_tmp[indices[i]] = exp(h[i*h_stride]) for i < n (TruncExp forward of the density head output, f16);
+ * seed_dev (may be NULL) is incremented once. */
+int ncn_grid_scatter_density(const void* h_f16, int h_stride, const int32_t* indices, int64_t n, float* density_tmp,
+                             int64_t* seed_dev, ncn_stream_t stream);
 /* packbits with threshold = min(stats[0]/stats[1], density_threshold) read on device:
  * removes the .item() host sync of models/ngp_mt.py:365. */
 int ncn_packbits_auto(const float* density_grid, int64_t n_bytes, const float* stats,

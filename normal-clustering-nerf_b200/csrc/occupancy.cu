@@ -146,6 +146,66 @@ density_grid_update_kernel(float* __restrict__ grid, const float* __restrict__ t
   }
 }
 
+
+// ---- occupancy-grid upkeep, sampling half (models/ngp_mt.py:254-271, 339-357) ---------------------------------------
+// One launch replaces randint + morton3D + cumsum lookup (searchsorted) + morton3D_invert + two cats + the jittered
+// cell-centre arithmetic + the (M,3) temporaries of the reference's sample_uniform_and_occupied_cells /
+// update_density_grid: thread i < M draws a uniform cell, thread M <= i < 2M draws the k-th occupied cell for a uniform k
+// (upper_bound over the inclusive cumsum of the occupied flags = torch.searchsorted(right=True), clamped like the
+// reference), and both emit the Morton index and a uniformly jittered point inside the cell.
+__device__ __forceinline__ uint32_t rng_hash(uint64_t seed, uint64_t i, uint32_t k) {      // splitmix64 finaliser
+  uint64_t z = seed + 0x9E3779B97F4A7C15ull * (i * 8ull + k + 1ull);
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z ^= z >> 31;
+  return (uint32_t)(z >> 32);
+}
+__device__ __forceinline__ float rng_unit(uint32_t r) { return (float)(r >> 8) * (1.0f / 16777216.0f); }   // [0, 1)
+
+__global__ void __launch_bounds__(256)
+grid_sample_cells_kernel(const int32_t* __restrict__ occ_csum, int G, int64_t M, float s, const int64_t* __restrict__ seed_dev,
+                         int32_t* __restrict__ indices, float* __restrict__ xyz) {
+  const int64_t G3 = (int64_t)G * G * G;
+  const uint64_t seed = (uint64_t)*seed_dev;
+  const float half_cell = s / (float)G;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < 2 * M; i += stride) {
+    uint32_t cx, cy, cz, idx;
+    if (i < M) {
+      cx = rng_hash(seed, i, 0) % (uint32_t)G; cy = rng_hash(seed, i, 1) % (uint32_t)G; cz = rng_hash(seed, i, 2) % (uint32_t)G;
+      idx = morton3d(cx, cy, cz);
+    } else {
+      const int32_t total = occ_csum[G3 - 1];
+      const int32_t r = (int32_t)(rng_unit(rng_hash(seed, i, 0)) * (float)total);
+      int64_t lo = 0, hi = G3;                               // first position with csum > r
+      while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (occ_csum[mid] > r) hi = mid; else lo = mid + 1;
+      }
+      idx = (uint32_t)(lo < G3 - 1 ? lo : G3 - 1);
+      cx = morton3d_invert(idx); cy = morton3d_invert(idx >> 1); cz = morton3d_invert(idx >> 2);
+    }
+    indices[i] = (int32_t)idx;
+    const uint32_t c3[3] = {cx, cy, cz};
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      const float centre = ((float)c3[d] / (float)(G - 1) * 2.0f - 1.0f) * (s - half_cell);
+      xyz[3 * i + d] = centre + (rng_unit(rng_hash(seed, i, 3 + d)) * 2.0f - 1.0f) * half_cell;
+    }
+  }
+}
+
+// density_tmp[indices[i]] = exp(h[i, 0])  (TruncExp forward of the density head; duplicate cells: any one of the draws,
+// like the reference's index_put); also advances the sampling seed once per launch
+__global__ void __launch_bounds__(256)
+grid_scatter_density_kernel(const __half* __restrict__ h, int h_stride, const int32_t* __restrict__ indices, int64_t n,
+                            float* __restrict__ density_tmp, int64_t* __restrict__ seed_dev) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    density_tmp[indices[i]] = expf(__half2float(h[i * h_stride]));
+  if (seed_dev != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *seed_dev += 1;
+}
+
 }  // namespace ncn
 
 using namespace ncn;
@@ -206,6 +266,27 @@ extern "C" int ncn_density_grid_update(float* density_grid, const float* density
   const int grid = persistent_grid((n_cells + 3) / 4, 256, 4);
   density_grid_update_kernel<<<grid, 256, 0, as_stream(stream)>>>(density_grid, density_tmp, n_cells,
                                                                   decay, stats);
+  NCN_LAUNCH_OK();
+  return NCN_OK;
+}
+
+extern "C" int ncn_grid_sample_cells(const int32_t* occ_csum, int grid_size, int64_t m, float s, const int64_t* seed_dev,
+                                     int32_t* indices, float* xyz, ncn_stream_t stream) {
+  NCN_CHECK_SIZE(m >= 0 && grid_size >= 2 && grid_size <= 1024);
+  if (m == 0) return NCN_OK;
+  NCN_CHECK_PTR(occ_csum); NCN_CHECK_PTR(seed_dev); NCN_CHECK_PTR(indices); NCN_CHECK_PTR(xyz);
+  grid_sample_cells_kernel<<<persistent_grid(2 * m, 256, 8), 256, 0, as_stream(stream)>>>(occ_csum, grid_size, m, s, seed_dev, indices, xyz);
+  NCN_LAUNCH_OK();
+  return NCN_OK;
+}
+
+extern "C" int ncn_grid_scatter_density(const void* h_f16, int h_stride, const int32_t* indices, int64_t n, float* density_tmp,
+                                        int64_t* seed_dev, ncn_stream_t stream) {
+  NCN_CHECK_SIZE(n >= 0 && h_stride >= 1);
+  if (n == 0) return NCN_OK;
+  NCN_CHECK_PTR(h_f16); NCN_CHECK_PTR(indices); NCN_CHECK_PTR(density_tmp);
+  grid_scatter_density_kernel<<<persistent_grid(n, 256, 8), 256, 0, as_stream(stream)>>>((const __half*)h_f16, h_stride, indices, n,
+                                                                                      density_tmp, seed_dev);
   NCN_LAUNCH_OK();
   return NCN_OK;
 }

@@ -385,12 +385,51 @@ class FusedStep:
         check(self.L.ncn_rays_from_pixels(ptr(tr.poses), ptr(tr.directions), ptr(img_idx), ptr(pix_idx), self.R, ptr(self.rays_o),
                                           ptr(self.rays_d), torch.cuda.current_stream().cuda_stream), "rays_from_pixels")
 
+    def _update_grid_impl(self, thr, decay=0.95):
+        """models/ngp_mt.py:339-368 (warmup=False) on the step's arenas: one sampling kernel, the encoder + density trunk
+        through the C-ABI (no module temporaries), one scatter, then decay/max + packbits.  Multi-cascade grids take the
+        module path (ncn_b200.ngp.NGPMT.update_density_grid)."""
+        m = self.model
+        if m.cascades != 1:
+            m.update_density_grid(thr, warmup=False, decay=decay)
+            return
+        L = self.L
+        st = torch.cuda.current_stream().cuda_stream
+        G = m.grid_size
+        G3 = G ** 3
+        M = G3 // 4
+        if getattr(self, "grid_tmp", None) is None:
+            dev = self.dev
+            self.grid_tmp = torch.zeros(G3, dtype=torch.float32, device=dev)
+            self.grid_idx = torch.empty(2 * M, dtype=torch.int32, device=dev)
+            self.grid_xyz = torch.empty(2 * M, 3, dtype=torch.float32, device=dev)
+            self.grid_seed = torch.full((1,), 20240531, dtype=torch.int64, device=dev)
+            self.grid_stats = torch.zeros(2, dtype=torch.float32, device=dev)
+        csum = torch.cumsum(m.density_grid[0] > thr, 0, dtype=torch.int32)
+        self.grid_tmp.zero_()
+        s = min(2.0 ** -1, float(m.scale))
+        check(L.ncn_grid_sample_cells(ptr(csum), G, M, s, ptr(self.grid_seed), ptr(self.grid_idx), ptr(self.grid_xyz), st), "grid_sample_cells")
+        enc, sg = m.xyz_encoder, m.sigma_net
+        cap = self.cap
+        for c0 in range(0, 2 * M, cap):
+            n = min(cap, 2 * M - c0)
+            last = c0 + n >= 2 * M
+            check(L.ncn_grid_fwd(C.byref(enc.desc), ptr(self.grid_xyz[c0:]), ptr(self._w16("xyz_encoder")), n, ptr(self.feat), self.xform,
+                                 None, st), "grid_fwd(update)")
+            check(L.ncn_mlp_fwd(C.byref(sg.desc), ptr(self.feat), ptr(self._w16("sigma_net")), n, ptr(self.h), None, None, st), "sigma_fwd(update)")
+            check(L.ncn_grid_scatter_density(ptr(self.h), 16, ptr(self.grid_idx[c0:]), n, ptr(self.grid_tmp),
+                                             ptr(self.grid_seed) if last else None, st), "grid_scatter")
+        self.grid_stats.zero_()
+        check(L.ncn_density_grid_update(ptr(m.density_grid), ptr(self.grid_tmp), G3, float(decay), ptr(self.grid_stats), st), "density_grid_update")
+        check(L.ncn_packbits_auto(ptr(m.density_grid), m.density_bitfield.numel(), ptr(self.grid_stats), float(thr),
+                                  ptr(m.density_bitfield), st), "packbits_auto")
+
     def update_grid(self, restore=None):
         """occupancy-grid upkeep (models/ngp_mt.py:339-368), replayed as its own CUDA graph (steady state: warmup=False)"""
         hp = self.hp
         thr = 0.01 * hp["rend_max_samples"] / 3 ** 0.5 * hp["density_tresh_decay"]
         if not self.use_graph:
-            self.model.update_density_grid(thr, warmup=False)
+            self._update_grid_impl(thr)
             if restore is not None:
                 self.model.density_grid.copy_(restore[0]); self.model.density_bitfield.copy_(restore[1])
             return
@@ -398,12 +437,12 @@ class FusedStep:
             s = torch.cuda.Stream()
             s.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(s):
-                self.model.update_density_grid(thr, warmup=False)
+                self._update_grid_impl(thr)
             torch.cuda.current_stream().wait_stream(s)
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
-                self.model.update_density_grid(thr, warmup=False)
+                self._update_grid_impl(thr)
                 if restore is not None:
                     self.model.density_grid.copy_(restore[0]); self.model.density_bitfield.copy_(restore[1])
             self.grid_graph = g

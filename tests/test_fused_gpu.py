@@ -107,3 +107,65 @@ def test_rays_from_pixels_matches_get_rays():
     rays_d = (dirs[pix][:, None, :] @ c2w[..., :3].transpose(1, 2))[:, 0]
     torch.testing.assert_close(fs.rays_d, rays_d, rtol=1e-6, atol=1e-7)
     assert torch.equal(fs.rays_o, c2w[..., 3])
+
+
+def test_grid_update_sampling_kernels():
+    """ncn_grid_sample_cells / ncn_grid_scatter_density (models/ngp_mt.py:254-271, 345-357): index ranges, the second half
+    hits occupied cells only and uniformly, every point lies inside its cell, the seed advances, the scatter writes exp(h0)."""
+    import ncn_b200  # noqa: F401
+    from ncn_b200 import _lib, vren
+    from ncn_b200._lib import check, ptr, stream
+    L = _lib.lib()
+    dev = "cuda"
+    G, s = 128, 0.5
+    G3, M = G ** 3, G ** 3 // 4
+    g = torch.Generator(device=dev).manual_seed(0)
+    grid = torch.rand(G3, device=dev, generator=g)
+    thr = 0.9
+    occ = grid > thr
+    csum = torch.cumsum(occ, 0, dtype=torch.int32)
+    idx = torch.empty(2 * M, dtype=torch.int32, device=dev); xyz = torch.empty(2 * M, 3, device=dev)
+    seed = torch.full((1,), 7, dtype=torch.int64, device=dev)
+    check(L.ncn_grid_sample_cells(ptr(csum), G, M, s, ptr(seed), ptr(idx), ptr(xyz), stream()))
+    assert int(idx.min()) >= 0 and int(idx.max()) < G3
+    assert bool(occ[idx[M:].long()].all())                                  # occupied half: occupied cells only
+    hist = torch.bincount(idx[M:].long(), minlength=G3)[occ].float()        # ... drawn uniformly among them
+    assert abs(float(hist.mean()) - M / int(occ.sum())) < 1e-3 and float(hist.std()) < 3.0 * float(hist.mean().sqrt())
+    coords = vren.morton3D_invert(idx).float()
+    assert abs(float(coords[:M].mean()) - (G - 1) / 2) < 0.5                # uniform half
+    half = s / G
+    centre = (coords / (G - 1) * 2 - 1) * (s - half)
+    assert float((xyz - centre).abs().max()) <= half * (1 + 1e-5)           # jitter stays inside the cell
+    assert float((xyz - centre).abs().mean()) > 0.4 * half                  # ... and is not degenerate
+    # a second draw with the advanced seed differs; the scatter writes exp(h0) and advances the seed
+    h = torch.randn(2 * M, 16, device=dev, generator=g).half()
+    tmp = torch.zeros(G3, device=dev)
+    check(L.ncn_grid_scatter_density(ptr(h), 16, ptr(idx), 2 * M, ptr(tmp), ptr(seed), stream()))
+    assert int(seed) == 8
+    k = int(idx[12345])
+    cand = torch.exp(h[(idx == k).nonzero().flatten(), 0].float())
+    assert bool((cand == tmp[k]).any())
+    assert float(tmp[(torch.bincount(idx.long(), minlength=G3) == 0)].abs().max()) == 0.0
+    idx2 = torch.empty_like(idx); xyz2 = torch.empty_like(xyz)
+    check(L.ncn_grid_sample_cells(ptr(csum), G, M, s, ptr(seed), ptr(idx2), ptr(xyz2), stream()))
+    assert not torch.equal(idx, idx2)
+
+
+def test_fused_grid_update_matches_module_path_statistically():
+    """FusedStep.update_grid (sampling kernel + C-ABI field + scatter) against NGPMT.update_density_grid (the reference's
+    torch sequence): different random streams, so compare the resulting occupancy statistics."""
+    tr, rays_o, rays_d, tri, rgb, target = _setup(R=2048)
+    fs = tr.fused_step(use_graph=False)
+    hp = tr.hp
+    thr = 0.01 * hp["rend_max_samples"] / 3 ** 0.5 * hp["density_tresh_decay"]
+    g0, b0 = tr.model.density_grid.clone(), tr.model.density_bitfield.clone()
+    torch.manual_seed(0)
+    tr.model.update_density_grid(thr, warmup=False)
+    ga, ba = tr.model.density_grid.clone(), tr.model.density_bitfield.clone()
+    tr.model.density_grid.copy_(g0); tr.model.density_bitfield.copy_(b0)
+    fs.update_grid()
+    gb, bb = tr.model.density_grid.clone(), tr.model.density_bitfield.clone()
+    pop = lambda b: float(sum(((b >> i) & 1).sum() for i in range(8)))
+    assert abs(pop(ba) - pop(bb)) <= 0.02 * max(pop(ba), 1.0)
+    assert abs(float(ga.clamp(min=0).mean()) - float(gb.clamp(min=0).mean())) <= 0.05 * float(ga.clamp(min=0).mean())
+    assert float((gb != g0).float().mean()) > 0.2                            # the update touched a large part of the grid
