@@ -502,12 +502,22 @@ extern "C" int ncn_debug_km_trace(long long* host_dst) {
 #endif
 
 // ---------------------------------------------------------------- orthogonal-triple selection (one CTA)
+// warp arg-min / arg-max over (value, index) pairs with ties to the LOWEST index (the reference's argmin / first-max loops)
+__device__ __forceinline__ void warp_argmin(float& v, int& i) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, v, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, i, o);
+    if (ov < v || (ov == v && oi < i)) { v = ov; i = oi; }
+  }
+}
+
 __device__ __forceinline__ void cluster_select_body(const float* __restrict__ centroids, const int32_t* __restrict__ assign, int64_t n, int K,
                                                     float t_similar, int32_t* __restrict__ labels, int32_t* __restrict__ sel) {
   __shared__ int s_size[kKmMaxK];
   __shared__ int s_lab[kKmMaxK];
   __shared__ float s_sim[kKmMaxK * kKmMaxK];
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31;
   for (int j = tid; j < K; j += blockDim.x) s_size[j] = 0;
   __syncthreads();
   for (int64_t i = tid; i < n; i += blockDim.x) { const int a = assign[i]; if (a >= 0) atomicAdd(&s_size[a], 1); }
@@ -518,6 +528,42 @@ __device__ __forceinline__ void cluster_select_body(const float* __restrict__ ce
                centroids[3 * i + 2] * centroids[3 * j + 2];
   }
   __syncthreads();
+  if (K <= 32) {
+    // one lane per cluster, warp 0 only: the selection is a handful of warp arg-min / arg-max reductions
+    if (tid < 32) {
+      const int j = lane;
+      const bool on = j < K;
+      // biggest cluster (losses.py:104-107): first maximum
+      float negsz = on ? -(float)s_size[j] : INFINITY; int c1 = j;
+      warp_argmin(negsz, c1);
+      // criteria[i][j] = |sim[i,c1]| + |sim[c1,j]| + |sim[i,j]|; column j: min / argmin over i (losses.py:117-118)
+      float mn = INFINITY; int arg = 0;
+      if (on)
+        for (int i = 0; i < K; ++i) {
+          const float v = fabsf(s_sim[i * K + c1]) + fabsf(s_sim[c1 * K + j]) + fabsf(s_sim[i * K + j]);
+          if (v < mn) { mn = v; arg = i; }
+        }
+      float best = mn; int c2 = j;                                            // losses.py:119-120
+      warp_argmin(best, c2);
+      const int c3 = __shfl_sync(0xffffffffu, arg, c2);
+      int lab = 0;
+      const int cs[3] = {c1, c2, c3};
+#pragma unroll
+      for (int q = 0; q < 3; ++q)                                             // merge similar (losses.py:47-54)
+        if (on && s_sim[cs[q] * K + j] > t_similar) lab = q + 1;
+#pragma unroll
+      for (int q = 0; q < 3; ++q) {                                           // opposite clusters (losses.py:57-72)
+        float v = on ? s_sim[cs[q] * K + j] : INFINITY; int o = j;
+        warp_argmin(v, o);
+        if (-v > t_similar && on && s_sim[o * K + j] > t_similar) lab = -(q + 1);
+      }
+      if (on) s_lab[j] = lab;
+      if (lane == 0) { sel[0] = c1; sel[1] = c2; sel[2] = c3; }
+    }
+    __syncthreads();
+    for (int64_t i = tid; i < n; i += blockDim.x) { const int a = assign[i]; labels[i] = a >= 0 ? s_lab[a] : 0; }
+    return;
+  }
   __shared__ float s_mn[kKmMaxK];
   __shared__ int s_arg[kKmMaxK], s_c1;
   if (tid == 0) {
@@ -580,18 +626,48 @@ __device__ __forceinline__ void cluster_loss_fw_body(const float* __restrict__ n
   for (int a = tid; a < 32 * 12; a += blockDim.x) s_wacc[a] = 0;
   __syncthreads();
   const int64_t n_round = (n + 31) & ~(int64_t)31;
-  for (int64_t i = tid; i < n_round; i += blockDim.x) {
-    int l = 0;
-    float x = 0.f, y = 0.f, z = 0.f;
-    if (i < n) l = labels[i];
-    const bool v = l != 0;
-    int k = 0;
-    if (v) {
-      k = (l > 0 ? l : -l) - 1;
-      const float sg = l > 0 ? 1.f : -1.f;
-      x = sg * nrm[3 * i]; y = sg * nrm[3 * i + 1]; z = sg * nrm[3 * i + 2];
+  // up to kPer points per thread are fetched ONCE, in one batch of independent loads, and kept in registers for both passes
+  constexpr int kPer = 8;
+  const bool in_regs = n <= (int64_t)kPer * blockDim.x;
+  int rl[kPer];
+  float rx[kPer], ry[kPer], rz[kPer];
+  if (in_regs) {
+#pragma unroll
+    for (int q = 0; q < kPer; ++q) {
+      const int64_t i = tid + (int64_t)q * blockDim.x;
+      rl[q] = i < n ? labels[i] : 0;
     }
-    warp_accumulate_by_key(k, v, x, y, z, s_wacc + wid * 12, lane);
+#pragma unroll
+    for (int q = 0; q < kPer; ++q) {
+      const int64_t i = tid + (int64_t)q * blockDim.x;
+      rx[q] = ry[q] = rz[q] = 0.f;
+      if (rl[q] != 0) {
+        const float sg = rl[q] > 0 ? 1.f : -1.f;
+        rx[q] = sg * nrm[3 * i]; ry[q] = sg * nrm[3 * i + 1]; rz[q] = sg * nrm[3 * i + 2];
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < kPer; ++q) {
+      const int64_t i = tid + (int64_t)q * blockDim.x;
+      if (i < n_round) {
+        const int l = rl[q];
+        warp_accumulate_by_key(l != 0 ? (l > 0 ? l : -l) - 1 : 0, l != 0, rx[q], ry[q], rz[q], s_wacc + wid * 12, lane);
+      }
+    }
+  } else {
+    for (int64_t i = tid; i < n_round; i += blockDim.x) {
+      int l = 0;
+      float x = 0.f, y = 0.f, z = 0.f;
+      if (i < n) l = labels[i];
+      const bool v = l != 0;
+      int k = 0;
+      if (v) {
+        k = (l > 0 ? l : -l) - 1;
+        const float sg = l > 0 ? 1.f : -1.f;
+        x = sg * nrm[3 * i]; y = sg * nrm[3 * i + 1]; z = sg * nrm[3 * i + 2];
+      }
+      warp_accumulate_by_key(k, v, x, y, z, s_wacc + wid * 12, lane);
+    }
   }
   __syncthreads();
   if (tid < 12) {
@@ -615,18 +691,25 @@ __device__ __forceinline__ void cluster_loss_fw_body(const float* __restrict__ n
   // second pass: per cluster sum of dots, sum of L1 distances and sum of sign(n' - c)
   float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // generic slots reused per cluster below
   float dotv[3] = {0, 0, 0}, l1v[3] = {0, 0, 0}, sg[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-  for (int64_t i = tid; i < n; i += blockDim.x) {
-    const int l = labels[i];
-    if (l == 0) continue;
+  auto second_pass = [&](int l, float x, float y, float z) {
     const int k = (l > 0 ? l : -l) - 1;
-    const float s = l > 0 ? 1.f : -1.f;
-    const float x = s * nrm[3 * i], y = s * nrm[3 * i + 1], z = s * nrm[3 * i + 2];
     const float dx = x - s_c[3 * k], dy = y - s_c[3 * k + 1], dz = z - s_c[3 * k + 2];
 #pragma unroll
     for (int q = 0; q < 3; ++q) if (q == k) {
       dotv[q] += x * s_c[3 * q] + y * s_c[3 * q + 1] + z * s_c[3 * q + 2];
       l1v[q] += fabsf(dx) + fabsf(dy) + fabsf(dz);
       sg[3 * q] += sgnf(dx); sg[3 * q + 1] += sgnf(dy); sg[3 * q + 2] += sgnf(dz);
+    }
+  };
+  if (in_regs) {
+#pragma unroll
+    for (int q = 0; q < kPer; ++q) if (rl[q] != 0) second_pass(rl[q], rx[q], ry[q], rz[q]);
+  } else {
+    for (int64_t i = tid; i < n; i += blockDim.x) {
+      const int l = labels[i];
+      if (l == 0) continue;
+      const float s = l > 0 ? 1.f : -1.f;
+      second_pass(l, s * nrm[3 * i], s * nrm[3 * i + 1], s * nrm[3 * i + 2]);
     }
   }
   (void)acc;
