@@ -37,6 +37,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--breakdown", default=None, help="write a per-call CUDA-event breakdown (json) to this path")
     ap.add_argument("--update-interval", type=int, default=None, help="occupancy-grid update period in steps (default: the reference's 16)")
+    ap.add_argument("--fuse-fwd", default="mlp", choices=["none", "mlp", "all"], help="forward fusion of the fused step (A/B)")
     ap.add_argument("--no-graph", action="store_true", help="run the fused step eagerly instead of replaying its CUDA graph")
     return ap.parse_args()
 
@@ -196,7 +197,7 @@ def run_ours(args):
     h2d_bytes = sum(host[0][k].numel() * host[0][k].element_size() for k in ("img", "pix", "rgb"))
 
     tri_dev = torch.from_numpy(host[0]["tri"]).to(dev)      # identical triangle topology for every patch batch
-    fs = tr.fused_step(use_graph=not args.no_graph)
+    fs = tr.fused_step(use_graph=not args.no_graph, fuse_fwd={"none": False, "mlp": "mlp", "all": True}[args.fuse_fwd])
     fs.set_triangles(tri_dev)
     loss_pin = torch.zeros(8, dtype=torch.float32).pin_memory()
 

@@ -336,6 +336,11 @@ int ncn_field_fwd(const ncn_grid_desc* desc_host, const float* x, const float* d
                   const void* w_sigma_f16, const void* w_rgb_f16, int64_t n, const int32_t* n_dev,
                   const float* xform_host, float* sigmas, float* raws, int c_total, void* feat_f16, void* h_f16,
                   void* sig_acts_f16, void* x_rgb_f16, void* rgb_acts_f16, void* rgb_out_f16, ncn_stream_t stream);
+/* The same without the encoder: density trunk + colour head in ONE launch on precomputed features feat (N,32) f16
+ * (replaces ncn_mlp_fwd(sigma) -> ncn_field_prepare_rgb -> ncn_mlp_fwd(rgb) -> ncn_field_head_out). */
+int ncn_field_mlp_fwd(const void* feat_f16, const float* dirs, const void* w_sigma_f16, const void* w_rgb_f16, int64_t n,
+                      const int32_t* n_dev, float* sigmas, float* raws, int c_total, void* h_f16, void* sig_acts_f16,
+                      void* x_rgb_f16, void* rgb_acts_f16, void* rgb_out_f16, ncn_stream_t stream);
 
 /* Selects the ncn_mlp_bwd implementation: 1 (default) = every GEMM (dgrad and wgrad) on tcgen05 with TMEM
  * accumulators, 128-row tiles fed by bulk copies (shapes without an instantiation fall back to 0);

@@ -201,6 +201,7 @@ SIGNATURES.update({
     "ncn_debug_stamp": (c_i32, [c_vp, c_i32, c_vp]),
     "ncn_grid_sample_cells": (c_i32, [c_vp, c_i32, c_i64, c_f32, c_vp, c_vp, c_vp, c_vp]),
     "ncn_grid_scatter_density": (c_i32, [c_vp, c_i32, c_vp, c_i64, c_vp, c_vp, c_vp]),
+    "ncn_field_mlp_fwd": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "ncn_set_march_segments": (c_i32, [c_i32]),
     "ncn_set_mlp_bwd_impl": (c_i32, [c_i32]),
     "ncn_mlp_bwd_src_fused": (c_i32, [C.POINTER(MlpDesc), C.POINTER(MlpBwdSrc), c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_f32, c_vp, c_sz, c_vp, c_vp]),

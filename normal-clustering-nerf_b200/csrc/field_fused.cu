@@ -111,6 +111,9 @@ __device__ __forceinline__ void ff_load_w(const __half* __restrict__ w, int rows
   }
 }
 
+// kGrid = true : hash-grid encode -> density trunk -> colour head (ncn_field_fwd)
+// kGrid = false: the two MLPs only; `feat` is the INPUT (N,32) f16 produced by ncn_grid_fwd (ncn_field_mlp_fwd)
+template <bool kGrid>
 __global__ void __launch_bounds__(kFfThreads)
 field_fwd_kernel(const __grid_constant__ FfGridMeta meta, const float* __restrict__ x, const float* __restrict__ dirs,
                  const __half* __restrict__ table, const __half* __restrict__ w_sigma, const __half* __restrict__ w_rgb,
@@ -144,13 +147,23 @@ field_fwd_kernel(const __grid_constant__ FfGridMeta meta, const float* __restric
     // ---- hash-grid features straight into the A fragments (levels t, t+4 -> k-block 0; t+8, t+12 -> k-block 1)
     float xn0[3] = {0.f, 0.f, 0.f}, xn1[3] = {0.f, 0.f, 0.f};
 #pragma unroll
-    for (int d = 0; d < 3; ++d) {
+    for (int d = 0; d < 3 && kGrid; ++d) {
       if (r0 < n) { const float v = x[3 * r0 + d]; xn0[d] = sm.xform_on ? __fdiv_rn(__fsub_rn(v, sm.lo[d]), sm.size3[d]) : v; }
       if (r1 < n) { const float v = x[3 * r1 + d]; xn1[d] = sm.xform_on ? __fdiv_rn(__fsub_rn(v, sm.lo[d]), sm.size3[d]) : v; }
     }
     uint32_t af[2][4];
+    if (!kGrid) {      // A fragments of the 16 x 32 feature tile straight from the row-major matrix
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
+      for (int kb = 0; kb < 2; ++kb) {
+        const int col = kb * 16 + 2 * t;
+        af[kb][0] = r0 < n ? *reinterpret_cast<const uint32_t*>(feat + r0 * 32 + col) : 0u;
+        af[kb][1] = r1 < n ? *reinterpret_cast<const uint32_t*>(feat + r1 * 32 + col) : 0u;
+        af[kb][2] = r0 < n ? *reinterpret_cast<const uint32_t*>(feat + r0 * 32 + col + 8) : 0u;
+        af[kb][3] = r1 < n ? *reinterpret_cast<const uint32_t*>(feat + r1 * 32 + col + 8) : 0u;
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 4 && kGrid; ++q) {
       const int l = t + 4 * q;
       const __half2* tl = reinterpret_cast<const __half2*>(table) + sm.offset[l];
       const float2 f0 = ff_lookup(xn0, tl, sm.scale[l], sm.res[l], sm.size[l]);
@@ -159,7 +172,7 @@ field_fwd_kernel(const __grid_constant__ FfGridMeta meta, const float* __restric
       af[q >> 1][(q & 1) * 2 + 0] = pack_half2(f0.x, f0.y);
       af[q >> 1][(q & 1) * 2 + 1] = pack_half2(f1.x, f1.y);
     }
-    if (feat) ff_store_a<32>(feat, row0, n, af, g, t);
+    if (kGrid && feat) ff_store_a<32>(feat, row0, n, af, g, t);
     // ---- density trunk
     float c[8][4];
     ff_layer<32, 64>(af, S0, c, g, t);
@@ -242,10 +255,28 @@ extern "C" int ncn_field_fwd(const ncn_grid_desc* desc, const float* x, const fl
   m.inv_size_dummy = 0.f;
   m.xform_on = xform_host != nullptr;
   const int grid = persistent_grid(((n + 15) / 16) * 32, kFfThreads, 6);
-  field_fwd_kernel<<<grid, kFfThreads, 0, as_stream(stream)>>>(m, x, dirs, (const __half*)table_f16, (const __half*)w_sigma_f16,
+  field_fwd_kernel<true><<<grid, kFfThreads, 0, as_stream(stream)>>>(m, x, dirs, (const __half*)table_f16, (const __half*)w_sigma_f16,
                                                               (const __half*)w_rgb_f16, n, n_dev, sigmas, raws, c_total, (__half*)feat_f16,
                                                               (__half*)h_f16, (__half*)sig_acts_f16, (__half*)x_rgb_f16,
                                                               (__half*)rgb_acts_f16, (__half*)rgb_out_f16);
+  NCN_LAUNCH_OK();
+  return NCN_OK;
+}
+
+// density trunk + colour head in one launch on precomputed hash-grid features (replaces ncn_mlp_fwd(sigma) ->
+// ncn_field_prepare_rgb -> ncn_mlp_fwd(rgb) -> ncn_field_head_out; same outputs as ncn_field_fwd, x_rgb in [h | d | 1] order)
+extern "C" int ncn_field_mlp_fwd(const void* feat_f16, const float* dirs, const void* w_sigma_f16, const void* w_rgb_f16, int64_t n,
+                                 const int32_t* n_dev, float* sigmas, float* raws, int c_total, void* h_f16, void* sig_acts_f16,
+                                 void* x_rgb_f16, void* rgb_acts_f16, void* rgb_out_f16, ncn_stream_t stream) {
+  NCN_CHECK_SIZE(n >= 0 && c_total >= 3);
+  if (n == 0) return NCN_OK;
+  NCN_CHECK_PTR(feat_f16); NCN_CHECK_PTR(dirs); NCN_CHECK_PTR(w_sigma_f16); NCN_CHECK_PTR(w_rgb_f16); NCN_CHECK_PTR(sigmas); NCN_CHECK_PTR(raws);
+  FfGridMeta m = {};
+  const int grid = persistent_grid(((n + 15) / 16) * 32, kFfThreads, 6);
+  field_fwd_kernel<false><<<grid, kFfThreads, 0, as_stream(stream)>>>(m, nullptr, dirs, nullptr, (const __half*)w_sigma_f16,
+                                                                     (const __half*)w_rgb_f16, n, n_dev, sigmas, raws, c_total,
+                                                                     (__half*)feat_f16, (__half*)h_f16, (__half*)sig_acts_f16,
+                                                                     (__half*)x_rgb_f16, (__half*)rgb_acts_f16, (__half*)rgb_out_f16);
   NCN_LAUNCH_OK();
   return NCN_OK;
 }

@@ -28,7 +28,7 @@ GSCALE = 131072.0      # 2^17: loss scale carried by the fp16 dL/dy tensors (the
 
 
 class FusedStep:
-    def __init__(self, trainer, capacity_per_ray=64, use_graph=True, fuse_fwd=False):
+    def __init__(self, trainer, capacity_per_ray=64, use_graph=True, fuse_fwd="mlp"):
         self.tr = trainer
         self.model = m = trainer.model
         self.opt = trainer.opt
@@ -76,7 +76,9 @@ class FusedStep:
                  self.L.ncn_mlp_bwd_workspace_bytes(C.byref(m.sigma_net.desc), cap))
         self.mlp_ws = E(nb, dtype=torch.uint8, device=dev)
         self.mlp_ws2 = E(nb, dtype=torch.uint8, device=dev)      # the colour-head backward runs concurrently on a side stream
-        self.fuse_fwd = fuse_fwd             # one fused forward kernel (x_rgb / dx_rgb then use the [h | d | 1] column order)
+        # False: encoder, density trunk, glue, colour head, glue (5 launches); "mlp": encoder + ONE launch for both MLPs; True: ONE
+        # launch for everything.  The fused kernels build x_rgb / dx_rgb in the [h | d | 1] column order (ncn_mlp_bwd_src.perm)
+        self.fuse_fwd = fuse_fwd
         self.src_rgb = _lib.MlpBwdSrc(1, ptr(self.d_raws), 3, 0, 3, None, None, None, 1.0, 1 if fuse_fwd else 0)
         self.src_sig = _lib.MlpBwdSrc(2, None, 0, 0, 0, ptr(self.dx_rgb), ptr(self.d_sigmas), ptr(self.h), 1.0, 2 if fuse_fwd else 0)
         self.side_stream = torch.cuda.Stream(device=dev)
@@ -179,7 +181,12 @@ class FusedStep:
         n_dev = ptr(self.counter)
         ck = check
         enc, sg, rgbn = m.xyz_encoder, m.sigma_net, m.rgb_net
-        if self.fuse_fwd:
+        if self.fuse_fwd == "mlp":      # encoder, then both MLPs in one launch
+            ck(L.ncn_grid_fwd(C.byref(enc.desc), ptr(self.xyzs), ptr(self._w16("xyz_encoder")), cap, ptr(self.feat), self.xform, n_dev, st), "grid_fwd")
+            ck(L.ncn_field_mlp_fwd(ptr(self.feat), ptr(self.dirs), ptr(self._w16("sigma_net")), ptr(self._w16("rgb_net")), cap, n_dev,
+                                   ptr(self.sigmas), ptr(self.raws), 3, ptr(self.h), ptr(self.sig_acts), ptr(self.x_rgb), ptr(self.rgb_acts),
+                                   ptr(self.rgb_out), st), "field_mlp_fwd")
+        elif self.fuse_fwd:
             ck(L.ncn_field_fwd(C.byref(enc.desc), ptr(self.xyzs), ptr(self.dirs), ptr(self._w16("xyz_encoder")), ptr(self._w16("sigma_net")),
                                ptr(self._w16("rgb_net")), cap, n_dev, self.xform, ptr(self.sigmas), ptr(self.raws), 3, ptr(self.feat),
                                ptr(self.h), ptr(self.sig_acts), ptr(self.x_rgb), ptr(self.rgb_acts), ptr(self.rgb_out), st), "field_fwd")

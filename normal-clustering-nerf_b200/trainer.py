@@ -186,7 +186,7 @@ class NeRFTrainer:
         loss_d = self.loss(results, target, global_step=self.global_step)
         return results, loss_d
 
-    def fused_step(self, capacity_per_ray=64, use_graph=True, fuse_fwd=False):
+    def fused_step(self, capacity_per_ray=64, use_graph=True, fuse_fwd="mlp"):
         """the sync-free CUDA-graph step (ncn_b200.fused.FusedStep) for the RGB+depth configuration"""
         if self.fused is None:
             from .fused import FusedStep

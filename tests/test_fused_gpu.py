@@ -32,7 +32,7 @@ def _setup(R=2048, seed=0):
     return tr, rays_o, rays_d, tri, rgb, target
 
 
-@pytest.mark.parametrize("fuse_fwd", [True, False])
+@pytest.mark.parametrize("fuse_fwd", [True, False, "mlp"])
 def test_fused_matches_module_path(fuse_fwd):
     from ncn_b200.fused import GSCALE
     tr, rays_o, rays_d, tri, rgb, target = _setup()
