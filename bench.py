@@ -128,12 +128,13 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------- our arm
 ALGO = {  # algorithmic bytes (or flops) per unit, SURVEY.md section 8d / DESIGN.md
     "ncn_grid_fwd": ("hbm", "sample", 588.0), "ncn_grid_bwd": ("hbm", "sample", 12 + 64 + 1024.0),
-    "ncn_adam_step": ("hbm", "param", 32.0), "ncn_grad_sumsq": ("hbm", "param", 4.0),
+    "ncn_adam_step": ("hbm", "param", 34.0), "ncn_adam_step_groups": ("hbm", "param", 34.0), "ncn_grad_sumsq": ("hbm", "param", 4.0),
     "ncn_composite_train_fw": ("hbm", "sample", 28.0), "ncn_composite_train_bw": ("hbm", "sample", 48.0),
     "ncn_march_train_expand": ("hbm", "sample", 36.0),
     # tcgen05 MLP backward, two launches per step (colour head 448 B/sample, density trunk 288 B/sample): average per launch
     "ncn_mlp_bwd_src_fused": ("hbm", "sample", 368.0), "ncn_mlp_bwd": ("hbm", "sample", 368.0),
     "ncn_mlp_fwd": ("hbm", "sample", 288.0),
+    "ncn_field_mlp_fwd": ("hbm", "sample", 64 + 12 + 128 + 32 + 64 + 256 + 32 + 12 + 4.0),     # feat, dirs in; sig_acts, h, x_rgb, rgb_acts, rgb_out, raws, sigmas out
 }
 
 
@@ -289,6 +290,7 @@ def run_ours(args):
     # ---- instrumented pass: the SAME step, same buffers, eager (no graph) with CUDA events around every libncn call
     #      -> launch count and the dominant kernel's average launch time (events cannot be read inside a replayed graph)
     fs.use_graph = False
+    fs.serial = True                    # no concurrent branches: every call is timed alone
     _lib.Profiler.reset(); _lib.Profiler.counting = True; _lib.Profiler.timing = {"*"}
     nprof = 8
     saved_interval = tr.hp["update_interval"]; tr.hp["update_interval"] = 1 << 30      # time the step itself
@@ -299,6 +301,7 @@ def run_ours(args):
     _lib.Profiler.counting = False; _lib.Profiler.timing = None
     tr.hp["update_interval"] = saved_interval
     fs.use_graph = not args.no_graph
+    fs.serial = False
     launches = int(round(launches_per_step * args.steps))
     top = max((k for k in summ if k in ALGO), key=lambda k: summ[k][1], default=None)
     top_stats = summ.get(top) if top else None

@@ -207,7 +207,7 @@ class FusedStep:
         # chain (normals -> k-means on an 8-CTA cluster -> selection -> cluster loss -> dL/ddepth) and then the
         # density part of the compositing backward.  They join at dL/dh.
         main = torch.cuda.current_stream()
-        side = self.side_stream
+        side = main if getattr(self, "serial", False) else self.side_stream      # serial: instrumented passes time every call alone
         self.ev_fork.record(main)
         side.wait_event(self.ev_fork)
         with torch.cuda.stream(side):
