@@ -106,6 +106,7 @@ class FusedStep:
         self.ev_fork2, self.ev_join2 = torch.cuda.Event(), torch.cuda.Event()
         self.coef = torch.ones(1, **f32)
         self.flag = torch.zeros(1, dtype=torch.int32, device=dev)
+        self._flat_mods = [mod for mod in self.model.modules() if getattr(mod, "_half_key", None) == "flat"]
         self.adam_groups = _lib.AdamGroups()
         self.adam_groups.n_groups = len(self.opt.groups)
         for q, (start, _, wd) in enumerate(self.opt.groups):
@@ -319,6 +320,10 @@ class FusedStep:
             self.graph = None                 # noise source is part of the captured sequence
         if noise is not None:
             self.noise.copy_(noise)
+        for mod in self._flat_mods:           # parameters written from outside (load_state_dict, tests): refresh the fp16 working copy
+            if mod.params._version != mod._flat_version:
+                mod._half.copy_(mod.params.detach())
+                mod._flat_version = mod.params._version
         self._schedule()
         multi = tr.world_size > 1
         if not self.use_graph:

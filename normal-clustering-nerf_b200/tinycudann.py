@@ -27,6 +27,11 @@ SEED = 1337
 def _half_copy(module):
     """fp16 copy of the fp32 master params, refreshed only when the parameter changed."""
     if module._half_key == "flat":        # a FlatAdam owns the fp16 copy and refreshes it inside its Adam kernel
+        v = module.params._version          # ... which does not bump the version; a user-side in-place write does
+        if getattr(module, "_flat_version", None) != v:
+            if getattr(module, "_flat_version", None) is not None:
+                module._half.copy_(module.params.detach())
+            module._flat_version = v
         return module._half
     p = module.params
     key = (p.data_ptr(), p._version, p.device)

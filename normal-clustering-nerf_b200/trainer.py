@@ -117,6 +117,7 @@ class FlatAdam:
             o = (p.data_ptr() - base) // 4
             mod._half = self.flat16[o:o + p.numel()]
             mod._half_key = "flat"
+            mod._flat_version = p._version        # in sync now; a later user-side in-place write bumps the version
 
     def step(self, lr=None):
         L = _lib.lib()
