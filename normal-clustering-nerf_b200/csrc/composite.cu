@@ -233,6 +233,108 @@ composite_train_bw_kernel(const float* __restrict__ dL_dopacity, const float* __
   }
 }
 
+// Backward fast path for a compile-time channel count: the first chunk's sample loads are issued together with the ray-level
+// loads (they only need `start`), and each later chunk is fetched one chunk ahead - a ray costs two exposed memory
+// latencies instead of three plus one per chunk.  Same arithmetic, same order as composite_train_bw_kernel.
+template <int CT>
+__global__ void __launch_bounds__(256)
+composite_train_bw_ct_kernel(const float* __restrict__ dL_dopacity, const float* __restrict__ dL_ddepth,
+                             const float* __restrict__ dL_drend, const float* __restrict__ dL_dws,
+                             const float* __restrict__ sigmas, const float* __restrict__ raws,
+                             const float* __restrict__ ws, const float* __restrict__ deltas,
+                             const float* __restrict__ ts, const int64_t* __restrict__ rays_a,
+                             const float* __restrict__ opacity, const float* __restrict__ depth,
+                             const float* __restrict__ rend, float thr, int64_t n_rays, int64_t capacity,
+                             float* __restrict__ dL_dsigmas, float* __restrict__ dL_draws) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t n = warp; n < n_rays; n += n_warps) {
+    const int64_t ray_idx = rays_a[3 * n], start = rays_a[3 * n + 1];
+    int64_t N64 = rays_a[3 * n + 2];
+    if (start + N64 > capacity) N64 = capacity > start ? capacity - start : 0;
+    const int N = (int)N64;
+    if (N == 0) continue;
+    float sg = 0.f, dl = 0.f, tt = 0.f, gwv = 0.f, rw[CT];
+    auto fetch = [&](int base, float& o_sg, float& o_dl, float& o_tt, float& o_gw, float (&o_rw)[CT]) {
+      const int k = base + lane;
+      o_sg = 0.f; o_dl = 0.f; o_tt = 0.f; o_gw = 0.f;
+#pragma unroll
+      for (int c = 0; c < CT; ++c) o_rw[c] = 0.f;
+      if (k < N) {
+        const int64_t s = start + k;
+        o_sg = sigmas[s]; o_dl = deltas[s]; o_tt = ts[s];
+        if (dL_drend) {
+#pragma unroll
+          for (int c = 0; c < CT; ++c) o_rw[c] = raws[s * CT + c];
+        }
+        if (dL_dws) o_gw = dL_dws[s];
+      }
+    };
+    fetch(0, sg, dl, tt, gwv, rw);                         // in flight together with the ray-level loads below
+    const float gO = dL_dopacity ? dL_dopacity[ray_idx] : 0.f;
+    const float gD = dL_ddepth ? dL_ddepth[ray_idx] : 0.f;
+    float gR[CT];
+#pragma unroll
+    for (int c = 0; c < CT; ++c) gR[c] = dL_drend ? dL_drend[ray_idx * CT + c] : 0.f;
+    const float O = opacity[ray_idx], D = depth[ray_idx];
+    float part = 0.f;
+    if (dL_drend && lane < CT) part += dL_drend[ray_idx * CT + lane] * rend[ray_idx * CT + lane];
+    if (dL_dws) for (int k = lane; k < N; k += 32) part += dL_dws[start + k] * ws[start + k];
+    const float Q_total = warp_sum(part) + gD * D;
+    const float gO_term = gO * (1.0f - O);
+    float T = 1.0f, carry = 0.f;
+    bool dead = false;
+    for (int base = 0; base < N; base += 32) {
+      const int k = base + lane;
+      const int64_t s = start + k;
+      if (dead) {
+        if (k < N) {
+          if (dL_dsigmas) dL_dsigmas[s] = 0.f;
+          if (dL_draws) {
+#pragma unroll
+            for (int c = 0; c < CT; ++c) dL_draws[s * CT + c] = 0.f;
+          }
+        }
+        continue;
+      }
+      float n_sg = 0.f, n_dl = 0.f, n_tt = 0.f, n_gw = 0.f, n_rw[CT];
+#pragma unroll
+      for (int c = 0; c < CT; ++c) n_rw[c] = 0.f;
+      if (base + 32 < N) fetch(base + 32, n_sg, n_dl, n_tt, n_gw, n_rw);
+      float a = 0.f, g = 0.f;
+      if (k < N) {
+        a = __fsub_rn(1.0f, __expf(__fmul_rn(-sg, dl)));
+        if (dL_drend) {
+#pragma unroll
+          for (int c = 0; c < CT; ++c) g += gR[c] * rw[c];
+        }
+      }
+      const float om = __fsub_rn(1.0f, a);
+      float T_before;
+      const int stop = replay_transmittance(om, 32, thr, T, T_before, lane);
+      const bool active = (k < N) && (stop < 0 || lane <= stop);
+      const float w = active ? __fmul_rn(a, T_before) : 0.f;
+      const float T_after = __fmul_rn(T_before, om);
+      const float lin = gD * tt + g;
+      const float q = active ? (w * lin + gwv * w) : 0.f;
+      const float incl = warp_scan_incl_f(q, lane) + carry;
+      if (k < N) {
+        if (dL_dsigmas) dL_dsigmas[s] = active ? dl * (gO_term + T_after * (lin + gwv) - (Q_total - incl)) : 0.f;
+        if (dL_draws) {
+#pragma unroll
+          for (int c = 0; c < CT; ++c) dL_draws[s * CT + c] = (active && dL_drend) ? gR[c] * w : 0.f;
+        }
+      }
+      carry = __shfl_sync(0xffffffffu, incl, 31);
+      if (stop >= 0) dead = true;
+      sg = n_sg; dl = n_dl; tt = n_tt; gwv = n_gw;
+#pragma unroll
+      for (int c = 0; c < CT; ++c) rw[c] = n_rw[c];
+    }
+  }
+}
+
 // Test-time incremental compositing: one thread per alive ray (S is 1..64 and the layout
 // is (A,S[,C]), so consecutive threads read consecutive rows).
 __global__ void __launch_bounds__(256)
@@ -313,6 +415,13 @@ extern "C" int ncn_composite_train_bw(const float* dL_dopacity, const float* dL_
   if (n_channels > 0) { NCN_CHECK_PTR(raws); NCN_CHECK_PTR(rend); }
   if (dL_dws) NCN_CHECK_PTR(ws);
   const int grid = persistent_grid(n_rays * 32, 256, 8);
+  if (n_channels == 3) {
+    composite_train_bw_ct_kernel<3><<<grid, 256, 0, as_stream(stream)>>>(dL_dopacity, dL_ddepth, dL_drend, dL_dws, sigmas, raws, ws, deltas, ts,
+                                                                         rays_a, opacity, depth, rend, T_threshold, n_rays, capacity,
+                                                                         dL_dsigmas, dL_draws);
+    NCN_LAUNCH_OK();
+    return NCN_OK;
+  }
   composite_train_bw_kernel<<<grid, 256, 0, as_stream(stream)>>>(dL_dopacity, dL_ddepth, dL_drend, dL_dws, sigmas, raws,
                                                                  ws, deltas, ts, rays_a, opacity, depth, rend,
                                                                  T_threshold, n_rays, capacity, n_channels, dL_dsigmas,
