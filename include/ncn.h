@@ -419,10 +419,10 @@ int ncn_cluster_loss_fw(const float* normals, const int32_t* labels, int64_t n_p
 int ncn_cluster_loss_bw(const float* normals, const int32_t* labels, int64_t n_points,
                         const float* stats, const float* weights_dev, float* dL_dnormals,
                         ncn_stream_t stream);
-/* ncn_cluster_select -> ncn_cluster_loss_fw -> ncn_cluster_loss_bw -> ncn_normals_from_depth_bw in ONE launch
- * (one CTA; same arguments and results as the four calls, dL_ddepth accumulated into a caller-zeroed buffer):
- * the step between the k-means result and the depth gradient of losses.py:441-509.  For small M where launch latency
- * dominates; at M = 6272 the four launches (two of them multi-CTA) are as fast (measured 42 us vs 50 us eager). */
+/* ncn_cluster_select -> ncn_cluster_loss_fw -> ncn_cluster_loss_bw -> ncn_normals_from_depth_bw in TWO launches (the two
+ * single-CTA stages share one, the two per-triangle stages the other); same arguments and results as the four calls,
+ * dL_ddepth accumulated into a caller-zeroed buffer: the step between the k-means result and the depth gradient of
+ * losses.py:441-509. */
 int ncn_cluster_tail(const float* centroids, const int32_t* assign, int64_t n_points, int k, float t_similar,
                      int32_t* labels, int32_t* sel, const float* normals, float* losses, float* stats,
                      const float* weights_dev, float* dL_dnormals, const float* origin, const float* dir,

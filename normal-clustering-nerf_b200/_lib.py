@@ -52,7 +52,7 @@ class Profiler:
     timing = None          # None, or a set of call names to time ("*" = all)
     launches = 0
     events = []            # (name, start_event, end_event, n_items)
-    KERNELS_PER_CALL = {"ncn_march_train": 3, "ncn_march_train_count": 3, "ncn_kmeans_workspace_bytes": 0,
+    KERNELS_PER_CALL = {"ncn_march_train": 3, "ncn_march_train_count": 3, "ncn_cluster_tail": 2, "ncn_kmeans_workspace_bytes": 0,
                         "ncn_march_train_workspace_bytes": 0, "ncn_mlp_bwd_workspace_bytes": 0, "ncn_mlp_acts_bytes": 0, "ncn_mlp_n_params": 0,
                         "ncn_grid_desc_init": 0, "ncn_version": 0, "ncn_set_mlp_bwd_impl": 0, "ncn_set_march_segments": 0, "ncn_debug_stamp": 1, "ncn_set_grid_bwd_merge": 0, "ncn_set_grid_fwd_coherent": 0, "ncn_error_string": 0, "ncn_device_info": 0,
                         "ncn_comm_unique_id": 0, "ncn_comm_init": 0, "ncn_comm_destroy": 0, "ncn_comm_last_error": 0}

@@ -806,23 +806,25 @@ cluster_loss_bw_kernel(const float* __restrict__ nrm, const int32_t* __restrict_
   cluster_loss_bw_body(nrm, labels, n, stats, w, dn, (int64_t)blockIdx.x * blockDim.x + threadIdx.x, (int64_t)gridDim.x * blockDim.x);
 }
 
-// Everything between the k-means result and dL/ddepth in ONE launch (one CTA: M <= a few thousand triangles):
-// selection -> cluster statistics + losses -> dL/dnormals -> dL/ddepth.  Same bodies as the four separate kernels; the
-// stages communicate through the same global buffers (visible to the whole CTA after __syncthreads).
+// Everything between the k-means result and dL/ddepth in TWO launches instead of four: the two single-CTA stages
+// (selection -> cluster statistics + losses) share one launch, the two per-triangle stages (dL/dnormals -> dL/ddepth) the
+// other - a thread consumes the dL/dnormal it has just written, so no grid-wide ordering is needed.
 __global__ void __launch_bounds__(1024, 1)
-cluster_tail_kernel(const float* __restrict__ centroids, const int32_t* __restrict__ assign, int64_t n, int K, float t_similar,
-                    int32_t* __restrict__ labels, int32_t* __restrict__ sel, const float* __restrict__ nrm,
-                    float* __restrict__ losses, float* __restrict__ stats, const float* __restrict__ w, float* __restrict__ dn,
-                    const float* __restrict__ origin, const float* __restrict__ dir, const float* __restrict__ depth,
-                    const int64_t* __restrict__ i1, const int64_t* __restrict__ i2, const int64_t* __restrict__ i3,
-                    float* __restrict__ ddepth) {
+cluster_select_loss_kernel(const float* __restrict__ centroids, const int32_t* __restrict__ assign, int64_t n, int K, float t_similar,
+                           int32_t* __restrict__ labels, int32_t* __restrict__ sel, const float* __restrict__ nrm,
+                           float* __restrict__ losses, float* __restrict__ stats) {
   cluster_select_body(centroids, assign, n, K, t_similar, labels, sel);
   __syncthreads();
   cluster_loss_fw_body(nrm, labels, n, losses, stats);
-  __syncthreads();
-  cluster_loss_bw_body(nrm, labels, n, stats, w, dn, threadIdx.x, blockDim.x);
-  __syncthreads();
-  normals_bw_body(origin, dir, depth, i1, i2, i3, dn, n, ddepth, threadIdx.x, blockDim.x);
+}
+__global__ void __launch_bounds__(256)
+cluster_bw_depth_kernel(const float* __restrict__ nrm, const int32_t* __restrict__ labels, int64_t n, const float* __restrict__ stats,
+                        const float* __restrict__ w, float* __restrict__ dn, const float* __restrict__ origin,
+                        const float* __restrict__ dir, const float* __restrict__ depth, const int64_t* __restrict__ i1,
+                        const int64_t* __restrict__ i2, const int64_t* __restrict__ i3, float* __restrict__ ddepth) {
+  const int64_t first = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (int64_t)gridDim.x * blockDim.x;
+  cluster_loss_bw_body(nrm, labels, n, stats, w, dn, first, stride);
+  normals_bw_body(origin, dir, depth, i1, i2, i3, dn, n, ddepth, first, stride);
 }
 
 // ---------------------------------------------------------------- photometric terms (fused fwd + grad)
@@ -998,8 +1000,12 @@ extern "C" int ncn_cluster_tail(const float* centroids, const int32_t* assign, i
     NCN_CHECK_PTR(assign); NCN_CHECK_PTR(labels); NCN_CHECK_PTR(normals); NCN_CHECK_PTR(dL_dnormals); NCN_CHECK_PTR(origin);
     NCN_CHECK_PTR(dir); NCN_CHECK_PTR(depth); NCN_CHECK_PTR(idx1); NCN_CHECK_PTR(idx2); NCN_CHECK_PTR(idx3); NCN_CHECK_PTR(dL_ddepth);
   }
-  cluster_tail_kernel<<<1, 1024, 0, as_stream(stream)>>>(centroids, assign, n_points, k, t_similar, labels, sel, normals, losses, stats,
-                                                         weights_dev, dL_dnormals, origin, dir, depth, idx1, idx2, idx3, dL_ddepth);
+  cluster_select_loss_kernel<<<1, 1024, 0, as_stream(stream)>>>(centroids, assign, n_points, k, t_similar, labels, sel, normals, losses, stats);
+  NCN_LAUNCH_OK();
+  if (n_points > 0)
+    cluster_bw_depth_kernel<<<persistent_grid(n_points, 256, 8), 256, 0, as_stream(stream)>>>(normals, labels, n_points, stats, weights_dev,
+                                                                                             dL_dnormals, origin, dir, depth, idx1, idx2, idx3,
+                                                                                             dL_ddepth);
   NCN_LAUNCH_OK();
   return NCN_OK;
 }

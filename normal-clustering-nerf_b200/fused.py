@@ -226,12 +226,11 @@ class FusedStep:
             ck(L.ncn_normals_from_depth_fw(ptr(self.rays_d), ptr(self.rays_d), ptr(self.depth), x1, x2, x3, self.M, ptr(self.normals), st), "normals_fw")
             ck(L.ncn_kmeans_spherical(ptr(self.normals), self.M, C.byref(self.km_params), ptr(self.centroids), ptr(self.assign),
                                       ptr(self.n_valid), ptr(self.km_ws), self.km_ws.numel(), st), "kmeans")
-            ck(L.ncn_cluster_select(ptr(self.centroids), ptr(self.assign), self.M, 20, 1.0 - float(hp["loss_norm_can_tres"]),
-                                    ptr(self.labels), ptr(self.sel), st), "select")
-            ck(L.ncn_cluster_loss_fw(ptr(self.normals), ptr(self.labels), self.M, ptr(self.losses), ptr(self.stats), st), "cluster_fw")
-            ck(L.ncn_cluster_loss_bw(ptr(self.normals), ptr(self.labels), self.M, ptr(self.stats), ptr(self.dev_sched[3:6]), ptr(self.dn), st), "cluster_bw")
-            ck(L.ncn_normals_from_depth_bw(ptr(self.rays_d), ptr(self.rays_d), ptr(self.depth), x1, x2, x3, ptr(self.dn), self.M,
-                                           ptr(self.d_depth), st), "normals_bw")
+            # selection + cluster losses (one single-CTA launch), dL/dnormals + dL/ddepth (one multi-CTA launch)
+            ck(L.ncn_cluster_tail(ptr(self.centroids), ptr(self.assign), self.M, 20, 1.0 - float(hp["loss_norm_can_tres"]),
+                                  ptr(self.labels), ptr(self.sel), ptr(self.normals), ptr(self.losses), ptr(self.stats),
+                                  ptr(self.dev_sched[3:6]), ptr(self.dn), ptr(self.rays_d), ptr(self.rays_d), ptr(self.depth),
+                                  x1, x2, x3, ptr(self.d_depth), st), "cluster_tail")
         ck(L.ncn_composite_train_bw(ptr(self.d_opacity), ptr(self.d_depth), ptr(self.d_rend), None, ptr(self.sigmas), ptr(self.raws), ptr(self.ws),
                                     ptr(self.deltas), ptr(self.ts), ptr(self.rays_a), ptr(self.opacity), ptr(self.depth), ptr(self.rend), 1e-4,
                                     R, cap, 3, ptr(self.d_sigmas), None, st), "composite_bw_sigma")

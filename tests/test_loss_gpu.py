@@ -103,7 +103,7 @@ def test_empty_cluster_is_nan_and_zero_grad(ncn):
 
 
 def test_cluster_tail_equals_the_four_calls(ncn):
-    """ncn_cluster_tail (one launch) against ncn_cluster_select -> _loss_fw -> _loss_bw -> ncn_normals_from_depth_bw."""
+    """ncn_cluster_tail (two launches) against ncn_cluster_select -> _loss_fw -> _loss_bw -> ncn_normals_from_depth_bw."""
     import ctypes as C
     from ncn_b200 import _lib, clustering, synth
     from ncn_b200.vren import ptr, stream
