@@ -254,6 +254,12 @@ int ncn_grid_fwd(const ncn_grid_desc* desc_host, const float* x, const void* tab
 int ncn_grid_bwd(const ncn_grid_desc* desc_host, const float* x, const void* dL_dy_f16,
                  int64_t n, float* grad_table_f32, float grad_scale, const float* xform_host,
                  const int32_t* n_dev, ncn_stream_t stream);
+/* ncn_grid_bwd restricted to levels [level_begin, level_end) (F = 2 tables; the gradient regions of consecutive levels are
+ * contiguous, offsets in the desc), with at most ctas_per_sm (1..8) CTAs per SM - a data-parallel caller all-reduces the
+ * first range while the second is still being computed. */
+int ncn_grid_bwd_levels(const ncn_grid_desc* desc_host, const float* x, const void* dL_dy_f16, int64_t n, float* grad_table,
+                        float grad_scale, const float* xform_host, const int32_t* n_dev, int level_begin, int level_end,
+                        int ctas_per_sm, ncn_stream_t stream);
 /* 1 (default): ncn_grid_bwd merges same-entry contributions of consecutive samples inside a warp before the
  * scatter; 0: one reduction per corner.  Returns the old value. */
 int ncn_set_grid_bwd_merge(int on);

@@ -171,6 +171,7 @@ SIGNATURES.update({
     "ncn_grid_desc_init": (c_i64, [C.POINTER(GridDesc)]),
     "ncn_grid_fwd": (c_i32, [C.POINTER(GridDesc), c_vp, c_vp, c_i64, c_vp, C.POINTER(c_f32), c_vp, c_vp]),
     "ncn_grid_bwd": (c_i32, [C.POINTER(GridDesc), c_vp, c_vp, c_i64, c_vp, c_f32, C.POINTER(c_f32), c_vp, c_vp]),
+    "ncn_grid_bwd_levels": (c_i32, [C.POINTER(GridDesc), c_vp, c_vp, c_i64, c_vp, c_f32, C.POINTER(c_f32), c_vp, c_i32, c_i32, c_i32, c_vp]),
     "ncn_grid_bwd_input": (c_i32, [C.POINTER(GridDesc), c_vp, c_vp, c_vp, c_i64, c_vp, c_vp]),
     "ncn_grid_bwd_bwd_input": (c_i32, [C.POINTER(GridDesc), c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp]),
     "ncn_mlp_n_params": (c_i64, [C.POINTER(MlpDesc)]),

@@ -264,7 +264,8 @@ __device__ __forceinline__ void merge_corners(const Cell8& c, bool valid, float 
 
 __global__ void __launch_bounds__(256)
 grid_bwd_merge_kernel(const __grid_constant__ GridMeta meta, const float* __restrict__ x, const __half* __restrict__ dy,
-                      int64_t n_cap, const int32_t* __restrict__ n_dev, GridXform xf, float grad_scale, float* __restrict__ grad) {
+                      int64_t n_cap, const int32_t* __restrict__ n_dev, GridXform xf, float grad_scale, float* __restrict__ grad,
+                      int level_begin, int level_end) {
   __shared__ GridMeta sm;
   for (int i = threadIdx.x; i < (int)(sizeof(GridMeta) / 4); i += blockDim.x)
     reinterpret_cast<uint32_t*>(&sm)[i] = reinterpret_cast<const uint32_t*>(&meta)[i];
@@ -273,12 +274,13 @@ grid_bwd_merge_kernel(const __grid_constant__ GridMeta meta, const float* __rest
   int64_t n = n_cap;
   if (n_dev != nullptr) { const int64_t nd = *n_dev; if (nd < n) n = nd; }
   const int lane = threadIdx.x & 31;
-  const int64_t n_items = ((n + 31) >> 5) * L;
+  const int LR = level_end - level_begin;                      // levels handled by this launch
+  const int64_t n_items = ((n + 31) >> 5) * LR;
   const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   for (int64_t item = warp0; item < n_items; item += n_warps) {
-    const int64_t chunk = item / L;
-    const int l = (int)(item - chunk * L);
+    const int64_t chunk = item / LR;
+    const int l = level_begin + (int)(item - chunk * LR);
     const int64_t s = (chunk << 5) + lane;
     const bool valid = s < n;
     float g0 = 0.f, g1 = 0.f;
@@ -483,23 +485,45 @@ extern "C" int ncn_grid_fwd(const ncn_grid_desc* desc, const float* x, const voi
   return NCN_OK;
 }
 
-extern "C" int ncn_grid_bwd(const ncn_grid_desc* desc, const float* x, const void* dy, int64_t n, float* grad,
-                            float grad_scale, const float* xform_host, const int32_t* n_dev, ncn_stream_t stream) {
+// level_begin/level_end restrict the launch to a range of levels (their gradient regions are contiguous in the table), so a
+// data-parallel caller can all-reduce the first range while the second is still being computed; ctas_per_sm < 8 leaves
+// room on the SMs for the collective's kernels
+static int grid_bwd_impl(const ncn_grid_desc* desc, const float* x, const void* dy, int64_t n, float* grad, float grad_scale,
+                         const float* xform_host, const int32_t* n_dev, int level_begin, int level_end, int ctas_per_sm,
+                         ncn_stream_t stream) {
   GridMeta m; int rc = to_meta(desc, &m); if (rc) return rc;
   NCN_CHECK_SIZE(n >= 0);
+  if (level_begin < 0 || level_end > m.n_levels || level_begin >= level_end || ctas_per_sm < 1 || ctas_per_sm > 8) return NCN_E_CONFIG;
   if (n == 0) return NCN_OK;
   NCN_CHECK_PTR(x); NCN_CHECK_PTR(dy); NCN_CHECK_PTR(grad);
   if ((uintptr_t)grad & 7) return NCN_E_ALIGN;
-  const int grid = persistent_grid(n * m.n_levels, 256, 8);
-  if (desc->n_features == 2 && g_grid_bwd_merge && ((uintptr_t)grad & 15) == 0) {      // 16-byte paired reductions
-    grid_bwd_merge_kernel<<<grid, 256, 0, as_stream(stream)>>>(m, x, (const __half*)dy, n, n_dev, make_xform(xform_host), grad_scale, grad);
+  const bool whole = level_begin == 0 && level_end == m.n_levels;
+  if (desc->n_features == 2 && (g_grid_bwd_merge || !whole) && ((uintptr_t)grad & 15) == 0) {      // 16-byte paired reductions
+    const int grid = persistent_grid(n * (level_end - level_begin), 256, ctas_per_sm);
+    grid_bwd_merge_kernel<<<grid, 256, 0, as_stream(stream)>>>(m, x, (const __half*)dy, n, n_dev, make_xform(xform_host), grad_scale, grad,
+                                                               level_begin, level_end);
     NCN_LAUNCH_OK();
     return NCN_OK;
   }
+  if (!whole) return NCN_E_UNSUPPORTED;
+  const int grid = persistent_grid(n * m.n_levels, 256, 8);
   NCN_GRID_DISPATCH(desc->n_features, (grid_bwd_kernel<kF><<<grid, 256, 0, as_stream(stream)>>>(
       m, x, (const __half*)dy, n, n_dev, make_xform(xform_host), grad_scale, grad)));
   NCN_LAUNCH_OK();
   return NCN_OK;
+}
+
+extern "C" int ncn_grid_bwd(const ncn_grid_desc* desc, const float* x, const void* dy, int64_t n, float* grad,
+                            float grad_scale, const float* xform_host, const int32_t* n_dev, ncn_stream_t stream) {
+  if (!desc) return NCN_E_NULL;
+  return grid_bwd_impl(desc, x, dy, n, grad, grad_scale, xform_host, n_dev, 0, desc->n_levels, 8, stream);
+}
+
+extern "C" int ncn_grid_bwd_levels(const ncn_grid_desc* desc, const float* x, const void* dy, int64_t n, float* grad,
+                                   float grad_scale, const float* xform_host, const int32_t* n_dev, int level_begin, int level_end,
+                                   int ctas_per_sm, ncn_stream_t stream) {
+  if (!desc) return NCN_E_NULL;
+  return grid_bwd_impl(desc, x, dy, n, grad, grad_scale, xform_host, n_dev, level_begin, level_end, ctas_per_sm, stream);
 }
 
 extern "C" int ncn_grid_bwd_input(const ncn_grid_desc* desc, const float* x, const void* table, const void* dy,

@@ -158,6 +158,26 @@ def test_mlp_backward_implementations_agree(ncn, impl, n_in, n_out, n_hidden, ac
         assert (got - want).abs().max() <= 8e-2 * want.abs().max() + 1e-4
 
 
+def test_grid_backward_level_ranges_sum_to_the_whole(ncn):
+    """ncn_grid_bwd_levels over [0, 11) and [11, 16) accumulates exactly what one ncn_grid_bwd launch does."""
+    import ctypes as C
+    from ncn_b200 import _lib
+    from ncn_b200._lib import check, ptr, stream
+    enc, cfg = _enc(19, std=0.1)
+    L = _lib.lib()
+    g = torch.Generator(device="cuda").manual_seed(5)
+    n = 20000
+    x = torch.rand(n, 3, device="cuda", generator=g)
+    dy = torch.randn(n, 32, device="cuda", generator=g).half()
+    ga = torch.zeros_like(enc.params); gb = torch.zeros_like(enc.params)
+    check(L.ncn_grid_bwd(C.byref(enc.desc), ptr(x), ptr(dy), n, ptr(ga), 1.0, None, None, stream()))
+    check(L.ncn_grid_bwd_levels(C.byref(enc.desc), ptr(x), ptr(dy), n, ptr(gb), 1.0, None, None, 0, 11, 8, stream()))
+    lo = int(enc.desc.level_offset[11]) * 2
+    assert float(gb[lo:].abs().max()) == 0.0 and float(gb[:lo].abs().max()) > 0.0
+    check(L.ncn_grid_bwd_levels(C.byref(enc.desc), ptr(x), ptr(dy), n, ptr(gb), 1.0, None, None, 11, 16, 6, stream()))
+    assert (ga - gb).abs().max() <= 1e-5 * ga.abs().max()
+
+
 NETS = [(32, 16, 1, "None"), (19, 3, 2, "Sigmoid"), (16, 3, 2, "None"), (16, 40, 2, "None"), (1, 1, 1, "Sigmoid")]
 
 
