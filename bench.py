@@ -38,6 +38,8 @@ def parse():
     ap.add_argument("--breakdown", default=None, help="write a per-call CUDA-event breakdown (json) to this path")
     ap.add_argument("--update-interval", type=int, default=None, help="occupancy-grid update period in steps (default: the reference's 16)")
     ap.add_argument("--fuse-fwd", default="mlp", choices=["none", "mlp", "all"], help="forward fusion of the fused step (A/B)")
+    ap.add_argument("--heads", default="", help="extra heads of BASELINE config 3, e.g. 'sem,norm' (semantic head with 3 classes + "
+                    "cross-entropy, normal head); default: the headline RGB+depth configuration")
     ap.add_argument("--no-graph", action="store_true", help="run the fused step eagerly instead of replaying its CUDA graph")
     return ap.parse_args()
 
@@ -164,7 +166,9 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     torch.manual_seed(1234 + rank)
     R = args.rays
-    tr = NeRFTrainer(dict(batch_size=R), device=dev, rank=rank, world_size=world)
+    heads = [h for h in args.heads.split(",") if h]
+    hp_extra = dict(pred_sem="sem" in heads, pred_norm_nn="norm" in heads, loss_sem_w=4e-2 if "sem" in heads else 0)
+    tr = NeRFTrainer(dict(batch_size=R, **hp_extra), device=dev, rank=rank, world_size=world, n_sem_cls=3 if "sem" in heads else 0)
     grid = synth.density_grid_from_occupancy(synth.room_occupancy(128, 0.5, seed=0))
     tr.model.density_grid.copy_(torch.from_numpy(grid).to(dev))
     vren.packbits(tr.model.density_grid, 5.9, tr.model.density_bitfield)
@@ -200,6 +204,8 @@ def run_ours(args):
     tri_dev = torch.from_numpy(host[0]["tri"]).to(dev)      # identical triangle topology for every patch batch
     fs = tr.fused_step(use_graph=not args.no_graph, fuse_fwd={"none": False, "mlp": "mlp", "all": True}[args.fuse_fwd])
     fs.set_triangles(tri_dev)
+    if "sem" in heads:          # semantics_WF-style labels (0 = void, 1..3), resident: 64 KB per step if they were copied
+        fs.sem_target.copy_(torch.randint(0, 4, (R,), generator=torch.Generator().manual_seed(7 + rank)).to(dev))
     loss_pin = torch.zeros(8, dtype=torch.float32).pin_memory()
 
     def step_resident(i):
@@ -355,7 +361,8 @@ def run_ours(args):
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f16", "data": "synthetic",
-                "config": {"workload": WORKLOAD, "rays_per_step_per_gpu": R, "samples_per_step_per_gpu": n_samples,
+                "config": {"workload": WORKLOAD if not heads else WORKLOAD.replace("RGB+depth heads", "RGB+depth+" + "+".join(heads) + " heads (config 3: n_sem_cls 3, cross-entropy w 4e-2)"),
+                           "rays_per_step_per_gpu": R, "samples_per_step_per_gpu": n_samples,
                            "parallelism": f"dp{world}", "ranks_in_sync": ranks_in_sync, "path": "fused CUDA-graph step (ncn_b200.fused.FusedStep)" if not args.no_graph else "fused eager step",
                            "occupancy": "synthetic room (13.6 % of 128^3 cells); grid update every 16 steps runs in full, its result is reverted to keep samples/ray stationary",
                            "init": "random (tcnn-style U(-1e-4,1e-4) table, Xavier MLPs)",

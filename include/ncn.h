@@ -315,7 +315,8 @@ int ncn_mlp_bwd(const ncn_mlp_desc* d, const void* x_f16, const void* w_f16,
 
 /* ncn_mlp_bwd whose dL/dout rows are assembled on the fly (tcgen05 implementation, n_out_pad == 16):
  *   mode 1 (colour head): dL/dout[:, j] = d_raws[:, c_off + j] * scale for j < n_ch, 0 otherwise   (= ncn_field_head_dout)
- *   mode 2 (density trunk): dL/dh = dx_rgb[:, 3:19] + e0 * d_sigmas * exp(clamp(h[:,0],-15,15)) * scale   (= ncn_field_bwd_h) */
+ *   mode 2 (density trunk): dL/dh = dx_rgb[:, 3:19] (+ dx_extra) + e0 * d_sigmas * exp(clamp(h[:,0],-15,15)) * scale
+ *                           (= ncn_field_bwd_h; dx_extra = dL/dh of a further head that reads h, e.g. sem_net, ngp_mt.py:217-224) */
 typedef struct ncn_mlp_bwd_src {
   int32_t mode;
   const float* d_raws;    /* (N, c_total) f32 */
@@ -327,6 +328,7 @@ typedef struct ncn_mlp_bwd_src {
   int32_t perm;           /* bit 0: this net's input columns are in the fused-forward order [h(16) | d(3) | 1(13)] (colour head):
                              W0 columns and dW0 are re-indexed accordingly and dL/dx comes out in that order;
                              bit 1 (mode 2): dx_rgb is in that order, i.e. dL/dh = dx_rgb[:, 0:16] */
+  const void* dx_extra;   /* mode 2: NULL or (N, 16) f16 added to dL/dh (net without output activation only) */
 } ncn_mlp_bwd_src;
 int ncn_mlp_bwd_src_fused(const ncn_mlp_desc* d, const ncn_mlp_bwd_src* src, const void* x_f16, const void* w_f16,
                           const void* out_f16, const void* acts_f16, int64_t n, float* grad_w_f32, void* dL_dx_f16,
@@ -445,6 +447,16 @@ int ncn_photometric_loss(const float* rend, const float* opacity, const float* t
                          int64_t n_rays, int n_channels, const float* bg_rgb_host,
                          float opacity_w, float grad_scale, float* rgb_out, float* sums,
                          float* dL_drend, float* dL_dopacity, ncn_stream_t stream);
+
+/* Semantic cross-entropy on the rendered logits (losses.py:226-242, 569-573: nn.CrossEntropyLoss(ignore_index=-1)
+ * applied to (sem_pred, target - 1), mean over the non-void rays): logits = rend[:, c_off : c_off + n_cls] (row stride
+ * c_total), labels (R) i64 in [0, n_cls] with 0 = void (ignored).  sums[0] += sum over valid rays of -log softmax[label-1],
+ * sums[1] = number of valid rays (caller zeroes sums[0]; loss = sums[0] / sums[1], NaN when no ray is valid - the
+ * reference then drops the term).  Writes (not accumulates) dL_drend[:, c_off : c_off + n_cls] =
+ * grad_scale * (softmax - onehot) / n_valid for valid rays, 0 otherwise; other columns are left untouched.  n_cls <= 64. */
+int ncn_semantic_ce_loss(const float* rend, int c_total, int c_off, int n_cls, const int64_t* labels,
+                         int64_t n_rays, float grad_scale, float* sums, float* dL_drend,
+                         ncn_stream_t stream);
 
 /* ------------------------------------------------------------------------- */
 /* (9) optimizer + data-parallel all-reduce  (the step either side of the path)*/

@@ -157,7 +157,8 @@ class MlpDesc(C.Structure):
 
 class MlpBwdSrc(C.Structure):
     _fields_ = [("mode", C.c_int32), ("d_raws", C.c_void_p), ("c_total", C.c_int32), ("c_off", C.c_int32), ("n_ch", C.c_int32),
-                ("dx_rgb", C.c_void_p), ("d_sigmas", C.c_void_p), ("h", C.c_void_p), ("scale", C.c_float), ("perm", C.c_int32)]
+                ("dx_rgb", C.c_void_p), ("d_sigmas", C.c_void_p), ("h", C.c_void_p), ("scale", C.c_float), ("perm", C.c_int32),
+                ("dx_extra", C.c_void_p)]
 
 
 class AdamGroups(C.Structure):
@@ -197,6 +198,7 @@ SIGNATURES.update({
     "ncn_cluster_loss_bw": (c_i32, [c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp]),
     "ncn_cluster_tail": (c_i32, [c_vp, c_vp, c_i64, c_i32, c_f32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "ncn_photometric_loss": (c_i32, [c_vp, c_vp, c_vp, c_i64, c_i32, C.POINTER(c_f32), c_f32, c_f32, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "ncn_semantic_ce_loss": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_vp, c_i64, c_f32, c_vp, c_vp, c_vp]),
     "ncn_adam_step": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_f32, c_f32, c_f32, c_f32, c_f32, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "ncn_adam_step_groups": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, C.POINTER(AdamGroups), c_f32, c_f32, c_f32, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "ncn_debug_stamp": (c_i32, [c_vp, c_i32, c_vp]),

@@ -874,6 +874,59 @@ photometric_kernel(const float* __restrict__ rend, const float* __restrict__ opa
   }
 }
 
+// ---------------------------------------------------------------- semantic cross-entropy (fused fwd + grad)
+// losses.py:226-242, 569-573: CrossEntropyLoss(ignore_index=-1)(sem_pred, target - 1), mean over non-void rays.
+// Thread per ray; every CTA counts the valid rays itself (R labels from L2) so the mean's divisor needs no second launch.
+constexpr int kCeMaxCls = 64;
+__global__ void __launch_bounds__(256)
+semantic_ce_kernel(const float* __restrict__ rend, int C, int c_off, int n_cls, const int64_t* __restrict__ labels,
+                   int64_t n_rays, float gscale, float* __restrict__ sums, float* __restrict__ d_rend) {
+  __shared__ int s_cnt[8];
+  __shared__ float s_sum[8];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  int cnt = 0;
+  for (int64_t r = threadIdx.x; r < n_rays; r += blockDim.x) {
+    const int64_t t = labels[r] - 1;
+    cnt += (t >= 0 && t < n_cls) ? 1 : 0;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  if (lane == 0) s_cnt[wid] = cnt;
+  __syncthreads();
+  int n_valid = 0;
+#pragma unroll
+  for (int q = 0; q < 8; ++q) n_valid += s_cnt[q];
+  const float inv = n_valid > 0 ? gscale / (float)n_valid : 0.f;
+  float acc = 0.f;
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < n_rays) {
+    const float* row = rend + r * C + c_off;
+    const int64_t t = labels[r] - 1;
+    const bool valid = t >= 0 && t < n_cls;
+    float mx = -INFINITY;
+    for (int c = 0; c < n_cls; ++c) mx = fmaxf(mx, row[c]);
+    float se = 0.f;
+    for (int c = 0; c < n_cls; ++c) se += expf(row[c] - mx);
+    const float lse = mx + logf(se);
+    if (valid) acc = lse - row[t];
+    if (d_rend) {
+      float* g = d_rend + r * C + c_off;
+      for (int c = 0; c < n_cls; ++c)
+        g[c] = valid ? (expf(row[c] - lse) - (c == (int)t ? 1.f : 0.f)) * inv : 0.f;
+    }
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) s_sum[wid] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float tot = 0.f;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) tot += s_sum[q];
+    atomicAdd(sums, tot);
+    if (blockIdx.x == 0) sums[1] = (float)n_valid;
+  }
+}
+
 }  // namespace ncn
 
 using namespace ncn;
@@ -1020,6 +1073,17 @@ extern "C" int ncn_photometric_loss(const float* rend, const float* opacity, con
   photometric_kernel<<<persistent_grid(n_rays, 256, 4), 256, 0, as_stream(stream)>>>(
       rend, opacity, target_rgb, n_rays, n_channels, bg_rgb_host[0], bg_rgb_host[1], bg_rgb_host[2], opacity_w, grad_scale,
       rgb_out, sums, dL_drend, dL_dopacity);
+  NCN_LAUNCH_OK();
+  return NCN_OK;
+}
+
+extern "C" int ncn_semantic_ce_loss(const float* rend, int c_total, int c_off, int n_cls, const int64_t* labels, int64_t n_rays,
+                                    float grad_scale, float* sums, float* dL_drend, ncn_stream_t stream) {
+  NCN_CHECK_SIZE(n_rays >= 0 && n_cls >= 1 && n_cls <= kCeMaxCls && c_off >= 0 && c_off + n_cls <= c_total);
+  if (n_rays == 0) return NCN_OK;
+  NCN_CHECK_PTR(rend); NCN_CHECK_PTR(labels); NCN_CHECK_PTR(sums);
+  semantic_ce_kernel<<<(unsigned)ceil_div(n_rays, 256), 256, 0, as_stream(stream)>>>(rend, c_total, c_off, n_cls, labels, n_rays,
+                                                                                    grad_scale, sums, dL_drend);
   NCN_LAUNCH_OK();
   return NCN_OK;
 }

@@ -231,6 +231,10 @@ __device__ __forceinline__ void dout_fetch(DoutRaw<OUT>& R, int64_t row, int64_t
     if (!(src.perm & 2)) R.a[2] = xr[2];
     R.f[0] = src.d_sigmas[row];
     R.f[1] = __half2float(reinterpret_cast<const __half*>(src.h)[row * 16]);
+    if (src.dx_extra != nullptr) {          // dL/dh of a further head on h (sem_net); R.o is free: this net has no output activation
+      const uint4* er = reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(src.dx_extra) + row * 16);
+      R.o[0] = er[0]; R.o[1] = er[1];
+    }
   }
   if (out_act == NCN_ACT_SIGMOID || out_act == NCN_ACT_EXP) {
 #pragma unroll
@@ -258,7 +262,17 @@ __device__ __forceinline__ void dout_finish(const DoutRaw<OUT>& R, bool valid, i
 #pragma unroll
       for (int q = 0; q < 8; ++q) drow[q] = __funnelshift_r(wv[q + 1], wv[q + 2], 16);   // halfs 3+2q, 4+2q
     }
-    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&drow[0]));
+    float2 f = __half22float2(*reinterpret_cast<const __half2*>(&drow[0]));
+    if (src.dx_extra != nullptr) {
+      const uint32_t ev[8] = {R.o[0].x, R.o[0].y, R.o[0].z, R.o[0].w, R.o[1].x, R.o[1].y, R.o[1].z, R.o[1].w};
+#pragma unroll
+      for (int q = 1; q < 8; ++q) {
+        const __half2 sum = __hadd2(*reinterpret_cast<const __half2*>(&drow[q]), *reinterpret_cast<const __half2*>(&ev[q]));
+        drow[q] = *reinterpret_cast<const uint32_t*>(&sum);
+      }
+      const float2 e0 = __half22float2(*reinterpret_cast<const __half2*>(&ev[0]));
+      f.x += e0.x; f.y += e0.y;
+    }
     drow[0] = pack_half2(f.x + R.f[0] * __expf(fminf(fmaxf(R.f[1], -15.f), 15.f)) * src.scale, f.y);
   }
   if (out_act == NCN_ACT_SIGMOID || out_act == NCN_ACT_EXP) {
@@ -607,6 +621,7 @@ int ncn_mlp_bwd_tc05_try(int in_pad, int out_pad, int n_hidden, const void* x, c
   ncn_mlp_bwd_src src;
   if (src_in) src = *src_in; else { src = ncn_mlp_bwd_src(); src.mode = 0; }
   if (src.mode == 1 && src.n_ch > 3) return NCN_E_UNSUPPORTED;
+  if (src.mode == 2 && src.dx_extra != nullptr && (out_act == NCN_ACT_SIGMOID || out_act == NCN_ACT_EXP)) return NCN_E_UNSUPPORTED;
   if (((uintptr_t)acts & 127) != 0) return NCN_E_UNSUPPORTED;      // bulk copies want the tiles 128-byte aligned
 #define NCN_TC(I, O, H) if (in_pad == I && out_pad == O && n_hidden == H) \
     return launch_tc05<I, O, H>(x, w, out, acts, dout, n, n_dev, out_act, grad_scale, grad_w, dx, tile_counter, src, st);

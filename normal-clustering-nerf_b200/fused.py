@@ -1,6 +1,7 @@
 """FusedStep - the sync-free, CUDA-graph-captured training step (the B200-native form of
-NeRFSystem.training_step, train_nerf.py:314-367, for the RGB+depth ngp_mt configuration with the opacity and
-Manhattan normal-clustering losses).
+NeRFSystem.training_step, train_nerf.py:314-367, for the ngp_mt configurations: RGB+depth with the opacity and
+Manhattan normal-clustering losses, optionally with the semantic head (+ cross-entropy, losses.py:569-573) and the
+normal head (--pred_sem / --pred_norm_nn: extra compositing channels, rendering.py:203-224)).
 
 Same arithmetic as the module path (ncn_b200.rendering.render + ncn_b200.losses.NeRFMTLoss + autograd +
 FlatAdam), but expressed as one linear sequence of libncn kernels on pre-allocated arenas:
@@ -33,8 +34,14 @@ class FusedStep:
         self.model = m = trainer.model
         self.opt = trainer.opt
         self.hp = trainer.hp
-        if m.pred_sem or m.pred_norm:
-            raise NotImplementedError("FusedStep covers the RGB+depth configuration; extra heads use the module path")
+        # rendered channels (rendering.py:203-224): rgb | norm_nn (3) | sem (n_cls)
+        self.n_cls = int(trainer.render_kwargs.get("n_sem_cls", 0)) if m.pred_sem else 0
+        if m.pred_sem and not 1 <= self.n_cls <= 16:
+            raise NotImplementedError("FusedStep: the semantic head is padded to 16 outputs (n_sem_cls <= 16)")
+        self.norm_off = 3
+        self.sem_off = 3 + (3 if m.pred_norm else 0)
+        self.Ct = Ct = self.sem_off + self.n_cls
+        self.sem_w = float(self.hp.get("loss_sem_w", 0.0)) if m.pred_sem else 0.0
         self.dev = dev = trainer.device
         self.R = R = self.hp["batch_size"]
         self.cap = cap = int(R * capacity_per_ray)
@@ -62,25 +69,36 @@ class FusedStep:
         cap_t = (cap + 127) // 128 * 128                         # saved activations: whole 128-row tiles (ncn_mlp_acts_bytes)
         self.sig_acts = E(1, cap_t, 64, **f16)
         self.x_rgb, self.rgb_out, self.rgb_acts = E(cap, 32, **f16), E(cap, 16, **f16), E(2, cap_t, 64, **f16)
-        self.sigmas, self.raws = E(cap, **f32), E(cap, 3, **f32)
+        self.sigmas, self.raws = E(cap, **f32), E(cap, Ct, **f32)
         # compositing + loss
         self.total_samples = E(R, dtype=torch.int64, device=dev)
-        self.opacity, self.depth, self.rend, self.ws = E(R, **f32), E(R, **f32), E(R, 3, **f32), E(cap, **f32)
+        self.opacity, self.depth, self.rend, self.ws = E(R, **f32), E(R, **f32), E(R, Ct, **f32), E(cap, **f32)
         self.rgb = E(R, 3, **f32)
-        self.zeros = torch.zeros(8, **f32)          # [0:2] photometric sums, [2] grad sumsq, [3] non-finite flag (as int bits)
-        self.d_rend, self.d_opacity, self.d_depth = E(R, 3, **f32), E(R, **f32), torch.zeros(R, **f32)
+        self.zeros = torch.zeros(8, **f32)          # [0:2] photometric sums, [2] grad sumsq, [3] non-finite flag (as int bits), [4:6] CE sum, valid rays
+        self.d_rend, self.d_opacity, self.d_depth = E(R, Ct, **f32), E(R, **f32), torch.zeros(R, **f32)
         self.losses, self.stats, self.weights = E(3, **f32), E(32, **f32), torch.zeros(3, **f32)
-        self.d_sigmas, self.d_raws = E(cap, **f32), E(cap, 3, **f32)
+        self.d_sigmas, self.d_raws = E(cap, **f32), E(cap, Ct, **f32)
         self.dout_rgb, self.dx_rgb, self.dh, self.dfeat = E(cap, 16, **f16), E(cap, 32, **f16), E(cap, 16, **f16), E(cap, 32, **f16)
         nb = max(self.L.ncn_mlp_bwd_workspace_bytes(C.byref(m.rgb_net.desc), cap),
                  self.L.ncn_mlp_bwd_workspace_bytes(C.byref(m.sigma_net.desc), cap))
+        # extra heads on h (ngp_mt.py:217-224).  The reference puts no loss on the rendered norm_nn channels (losses.py only
+        # slices them, :279/:294), so norm_net gets an exactly-zero gradient: its backward is not launched.
+        if m.pred_norm:
+            self.norm_out = E(cap, 16, **f16)
+        if m.pred_sem:
+            self.sem_out, self.sem_acts, self.dh_sem = E(cap, 16, **f16), E(2, cap_t, 64, **f16), E(cap, 16, **f16)
+            self.sem_dout = E(cap, 16, **f16) if self.n_cls > 3 else None
+            self.sem_target = torch.zeros(R, dtype=torch.int64, device=dev)      # labels in [0, n_cls], 0 = void
+            nb = max(nb, self.L.ncn_mlp_bwd_workspace_bytes(C.byref(m.sem_net.desc), cap))
         self.mlp_ws = E(nb, dtype=torch.uint8, device=dev)
         self.mlp_ws2 = E(nb, dtype=torch.uint8, device=dev)      # the colour-head backward runs concurrently on a side stream
         # False: encoder, density trunk, glue, colour head, glue (5 launches); "mlp": encoder + ONE launch for both MLPs; True: ONE
         # launch for everything.  The fused kernels build x_rgb / dx_rgb in the [h | d | 1] column order (ncn_mlp_bwd_src.perm)
         self.fuse_fwd = fuse_fwd
-        self.src_rgb = _lib.MlpBwdSrc(1, ptr(self.d_raws), 3, 0, 3, None, None, None, 1.0, 1 if fuse_fwd else 0)
-        self.src_sig = _lib.MlpBwdSrc(2, None, 0, 0, 0, ptr(self.dx_rgb), ptr(self.d_sigmas), ptr(self.h), 1.0, 2 if fuse_fwd else 0)
+        self.src_rgb = _lib.MlpBwdSrc(1, ptr(self.d_raws), Ct, 0, 3, None, None, None, 1.0, 1 if fuse_fwd else 0)
+        self.src_sig = _lib.MlpBwdSrc(2, None, 0, 0, 0, ptr(self.dx_rgb), ptr(self.d_sigmas), ptr(self.h), 1.0, 2 if fuse_fwd else 0,
+                                      ptr(self.dh_sem) if m.pred_sem else None)
+        self.src_sem = _lib.MlpBwdSrc(1, ptr(self.d_raws), Ct, self.sem_off, self.n_cls, None, None, None, 1.0, 0) if m.pred_sem else None
         self.side_stream = torch.cuda.Stream(device=dev)
         self.ev_fork, self.ev_join = torch.cuda.Event(), torch.cuda.Event()
         # fp16 parameter copies (owned by the optimizer, refreshed by its Adam kernel each step)
@@ -125,7 +143,9 @@ class FusedStep:
         opt, m = self.opt, self.model
         base = opt.flat.data_ptr()
         self.off = {}
-        for name in ("xyz_encoder", "sigma_net", "rgb_net"):
+        for name in ("xyz_encoder", "sigma_net", "rgb_net", "sem_net", "norm_net"):
+            if not hasattr(m, name):
+                continue
             p = getattr(m, name).params
             o = (p.data_ptr() - base) // 4
             self.off[name] = (o, p.numel())
@@ -164,6 +184,8 @@ class FusedStep:
         R, cap = self.R, self.cap
         ck = check
         self.zeros[0:2].zero_()
+        if self.n_cls:
+            self.zeros[4:6].zero_()
         self.d_depth.zero_()
         if self.gen_noise:
             self.noise.uniform_()
@@ -178,30 +200,39 @@ class FusedStep:
         """field forward, compositing, losses and the whole backward pass (needs the current parameters)"""
         L, m, hp = self.L, self.model, self.hp
         st = torch.cuda.current_stream().cuda_stream
-        R, cap = self.R, self.cap
+        R, cap, Ct = self.R, self.cap, self.Ct
         n_dev = ptr(self.counter)
         ck = check
         enc, sg, rgbn = m.xyz_encoder, m.sigma_net, m.rgb_net
         if self.fuse_fwd == "mlp":      # encoder, then both MLPs in one launch
             ck(L.ncn_grid_fwd(C.byref(enc.desc), ptr(self.xyzs), ptr(self._w16("xyz_encoder")), cap, ptr(self.feat), self.xform, n_dev, st), "grid_fwd")
             ck(L.ncn_field_mlp_fwd(ptr(self.feat), ptr(self.dirs), ptr(self._w16("sigma_net")), ptr(self._w16("rgb_net")), cap, n_dev,
-                                   ptr(self.sigmas), ptr(self.raws), 3, ptr(self.h), ptr(self.sig_acts), ptr(self.x_rgb), ptr(self.rgb_acts),
+                                   ptr(self.sigmas), ptr(self.raws), Ct, ptr(self.h), ptr(self.sig_acts), ptr(self.x_rgb), ptr(self.rgb_acts),
                                    ptr(self.rgb_out), st), "field_mlp_fwd")
         elif self.fuse_fwd:
             ck(L.ncn_field_fwd(C.byref(enc.desc), ptr(self.xyzs), ptr(self.dirs), ptr(self._w16("xyz_encoder")), ptr(self._w16("sigma_net")),
-                               ptr(self._w16("rgb_net")), cap, n_dev, self.xform, ptr(self.sigmas), ptr(self.raws), 3, ptr(self.feat),
+                               ptr(self._w16("rgb_net")), cap, n_dev, self.xform, ptr(self.sigmas), ptr(self.raws), Ct, ptr(self.feat),
                                ptr(self.h), ptr(self.sig_acts), ptr(self.x_rgb), ptr(self.rgb_acts), ptr(self.rgb_out), st), "field_fwd")
         else:
             ck(L.ncn_grid_fwd(C.byref(enc.desc), ptr(self.xyzs), ptr(self._w16("xyz_encoder")), cap, ptr(self.feat), self.xform, n_dev, st), "grid_fwd")
             ck(L.ncn_mlp_fwd(C.byref(sg.desc), ptr(self.feat), ptr(self._w16("sigma_net")), cap, ptr(self.h), ptr(self.sig_acts), n_dev, st), "sigma_fwd")
             ck(L.ncn_field_prepare_rgb(ptr(self.dirs), ptr(self.h), cap, n_dev, ptr(self.x_rgb), ptr(self.sigmas), st), "prepare_rgb")
             ck(L.ncn_mlp_fwd(C.byref(rgbn.desc), ptr(self.x_rgb), ptr(self._w16("rgb_net")), cap, ptr(self.rgb_out), ptr(self.rgb_acts), n_dev, st), "rgb_fwd")
-            ck(L.ncn_field_head_out(ptr(self.rgb_out), 16, cap, n_dev, ptr(self.raws), 3, 0, 3, st), "head_out")
-        ck(L.ncn_composite_train_fw(ptr(self.sigmas), ptr(self.raws), ptr(self.deltas), ptr(self.ts), ptr(self.rays_a), 1e-4, R, cap, 3,
+            ck(L.ncn_field_head_out(ptr(self.rgb_out), 16, cap, n_dev, ptr(self.raws), Ct, 0, 3, st), "head_out")
+        if m.pred_norm:                 # raws[:, 3:6] = norm_net(h)   (ngp_mt.py:221-224, rendering.py:203-206)
+            ck(L.ncn_mlp_fwd(C.byref(m.norm_net.desc), ptr(self.h), ptr(self._w16("norm_net")), cap, ptr(self.norm_out), None, n_dev, st), "norm_fwd")
+            ck(L.ncn_field_head_out(ptr(self.norm_out), 16, cap, n_dev, ptr(self.raws), Ct, self.norm_off, 3, st), "norm_head_out")
+        if m.pred_sem:                  # raws[:, sem_off:] = sem_net(h)  (ngp_mt.py:217-220, rendering.py:207-208)
+            ck(L.ncn_mlp_fwd(C.byref(m.sem_net.desc), ptr(self.h), ptr(self._w16("sem_net")), cap, ptr(self.sem_out), ptr(self.sem_acts), n_dev, st), "sem_fwd")
+            ck(L.ncn_field_head_out(ptr(self.sem_out), 16, cap, n_dev, ptr(self.raws), Ct, self.sem_off, self.n_cls, st), "sem_head_out")
+        ck(L.ncn_composite_train_fw(ptr(self.sigmas), ptr(self.raws), ptr(self.deltas), ptr(self.ts), ptr(self.rays_a), 1e-4, R, cap, Ct,
                                     ptr(self.total_samples), ptr(self.opacity), ptr(self.depth), ptr(self.rend), ptr(self.ws), st), "composite_fw")
-        # ---- losses (+ their gradients w.r.t. the rendered quantities)
-        ck(L.ncn_photometric_loss(ptr(self.rend), ptr(self.opacity), ptr(self.target), R, 3, self.bg, float(hp["loss_opacity_w"]), GSCALE,
+        # ---- losses (+ their gradients w.r.t. the rendered quantities; channels without a loss get a zero gradient)
+        ck(L.ncn_photometric_loss(ptr(self.rend), ptr(self.opacity), ptr(self.target), R, Ct, self.bg, float(hp["loss_opacity_w"]), GSCALE,
                                   ptr(self.rgb), ptr(self.zeros), ptr(self.d_rend), ptr(self.d_opacity), st), "photometric")
+        if m.pred_sem and self.sem_w > 0:
+            ck(L.ncn_semantic_ce_loss(ptr(self.rend), Ct, self.sem_off, self.n_cls, ptr(self.sem_target), R, self.sem_w * GSCALE,
+                                      ptr(self.zeros[4:6]), ptr(self.d_rend), st), "semantic_ce")
         inv = 1.0 / GSCALE
         # Two independent branches from here (forked onto a side stream; inside a CUDA graph they become parallel
         # branches): (A) the colour head's backward needs only dL/draws = dL/drend * w, (B) the normal-clustering
@@ -215,10 +246,21 @@ class FusedStep:
             sst = side.cuda_stream
             ck(L.ncn_composite_train_bw(None, None, ptr(self.d_rend), None, ptr(self.sigmas), ptr(self.raws), ptr(self.ws),
                                         ptr(self.deltas), ptr(self.ts), ptr(self.rays_a), ptr(self.opacity), ptr(self.depth), ptr(self.rend), 1e-4,
-                                        R, cap, 3, None, ptr(self.d_raws), sst), "composite_bw_raws")
+                                        R, cap, Ct, None, ptr(self.d_raws), sst), "composite_bw_raws")
             ck(L.ncn_mlp_bwd_src_fused(C.byref(rgbn.desc), C.byref(self.src_rgb), ptr(self.x_rgb), ptr(self._w16("rgb_net")), ptr(self.rgb_out),
                                        ptr(self.rgb_acts), cap, ptr(self._g32("rgb_net")), ptr(self.dx_rgb), inv, ptr(self.mlp_ws2),
                                        self.mlp_ws2.numel(), n_dev, sst), "rgb_bwd")
+            if m.pred_sem:              # semantic head backward: dL/dh of this head joins the density trunk's dL/dout (src_sig.dx_extra)
+                semn = m.sem_net
+                if self.sem_dout is None:
+                    ck(L.ncn_mlp_bwd_src_fused(C.byref(semn.desc), C.byref(self.src_sem), ptr(self.h), ptr(self._w16("sem_net")), ptr(self.sem_out),
+                                               ptr(self.sem_acts), cap, ptr(self._g32("sem_net")), ptr(self.dh_sem), inv, ptr(self.mlp_ws2),
+                                               self.mlp_ws2.numel(), n_dev, sst), "sem_bwd")
+                else:
+                    ck(L.ncn_field_head_dout(ptr(self.d_raws), Ct, self.sem_off, self.n_cls, 1.0, cap, n_dev, ptr(self.sem_dout), 16, sst), "sem_head_dout")
+                    ck(L.ncn_mlp_bwd(C.byref(semn.desc), ptr(self.h), ptr(self._w16("sem_net")), ptr(self.sem_out), ptr(self.sem_acts),
+                                     ptr(self.sem_dout), cap, ptr(self._g32("sem_net")), ptr(self.dh_sem), inv, ptr(self.mlp_ws2),
+                                     self.mlp_ws2.numel(), n_dev, sst), "sem_bwd")
             self.ev_join.record(side)
         if self.M > 0:
             x1, x2, x3 = ptr(self.tri[0]), ptr(self.tri[1]), ptr(self.tri[2])
@@ -233,7 +275,7 @@ class FusedStep:
                                   x1, x2, x3, ptr(self.d_depth), st), "cluster_tail")
         ck(L.ncn_composite_train_bw(ptr(self.d_opacity), ptr(self.d_depth), ptr(self.d_rend), None, ptr(self.sigmas), ptr(self.raws), ptr(self.ws),
                                     ptr(self.deltas), ptr(self.ts), ptr(self.rays_a), ptr(self.opacity), ptr(self.depth), ptr(self.rend), 1e-4,
-                                    R, cap, 3, ptr(self.d_sigmas), None, st), "composite_bw_sigma")
+                                    R, cap, Ct, ptr(self.d_sigmas), None, st), "composite_bw_sigma")
         main.wait_event(self.ev_join)
         ck(L.ncn_mlp_bwd_src_fused(C.byref(sg.desc), C.byref(self.src_sig), ptr(self.feat), ptr(self._w16("sigma_net")), ptr(self.h),
                                    ptr(self.sig_acts), cap, ptr(self._g32("sigma_net")), ptr(self.dfeat), inv, ptr(self.mlp_ws),
@@ -305,7 +347,7 @@ class FusedStep:
         ev.record()
         self.ring_events[slot] = ev
 
-    def step(self, rays_o=None, rays_d=None, target_rgb=None, noise=None, packed=None):
+    def step(self, rays_o=None, rays_d=None, target_rgb=None, noise=None, packed=None, sem_target=None):
         """one training step.  Inputs are device tensors copied into the graph's static buffers: either
         rays_o/rays_d/target_rgb (R,3) each, or `packed` (3,R,3) = [rays_o, rays_d, rgb] (one copy), or nothing when the
         caller filled self.inp in place (e.g. rays_from_pixels)."""
@@ -314,6 +356,8 @@ class FusedStep:
             self.inp.copy_(packed)
         elif rays_o is not None:
             self.rays_o.copy_(rays_o); self.rays_d.copy_(rays_d); self.target.copy_(target_rgb)
+        if sem_target is not None:
+            self.sem_target.copy_(sem_target)
         if (noise is None) != self.gen_noise:
             self.gen_noise = noise is None
             self.graph = None                 # noise source is part of the captured sequence
@@ -502,5 +546,7 @@ class FusedStep:
             l = torch.nan_to_num(self.losses.cpu())
             w = self.dev_sched[3:6].cpu() / GSCALE
             d.update(norm_D_C_ort_dot=float(w[0] * l[0]), norm_D_C_centr_dot=float(w[1] * l[1]), norm_D_C_centr_L1=float(w[2] * l[2]))
+        if self.n_cls and self.sem_w > 0:
+            d["sem"] = self.sem_w * float(z[4]) / float(z[5]) if float(z[5]) > 0 else 0.0
         d["total"] = sum(d.values())
         return d, int(self.counter[0])

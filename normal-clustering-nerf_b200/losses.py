@@ -73,6 +73,9 @@ class NeRFMTLoss(nn.Module):
         self.can_sched_end = g("loss_norm_can_end", -1)
         self.can_grow = g("loss_norm_can_grow", 1)
         self.kmeans_k, self.kmeans_niter = g("kmeans_k", 20), g("kmeans_niter", 20)   # losses.py:436-437 literals
+        self.sem_w = g("loss_sem_w", 0)
+        if self.sem_w > 0 and not g("pred_sem", False):
+            raise AssertionError("loss_sem_w > 0 needs pred_sem")                    # losses.py:239
 
     def w_sched(self, w, step):
         return max(0, min(w, (step - self.can_sched_start) * (w / self.can_grow)))   # losses.py:217
@@ -112,5 +115,9 @@ class NeRFMTLoss(nn.Module):
             loss_d["norm_D_C_centr_dot"] = _valid(self.w_sched(self.w_dot, step) * terms[1])
             loss_d["norm_D_C_centr_L1"] = _valid(self.w_sched(self.w_l1, step) * terms[2])
             pred["norm_depth"] = normals
+        if self.sem_w > 0 and "semantics" in target:
+            # losses.py:240-242, 569-573: void class 0 -> -1 (ignored); mean over the labelled rays; NaN (none labelled) -> 0
+            ce = torch.nn.functional.cross_entropy(pred["sem"][:gt_l].float(), target["semantics"] - 1, ignore_index=-1)
+            loss_d["sem"] = _valid(self.sem_w * ce)
         loss_d["total"] = sum(v for v in loss_d.values())
         return loss_d

@@ -12,6 +12,8 @@ What differs from the reference (all host-side, results equivalent):
 """
 import math
 
+import ctypes as C
+
 import numpy as np
 import torch
 from torch import nn
@@ -82,6 +84,43 @@ class NGPMT(nn.Module):
         if self.pred_norm:
             out["norms"] = self.norm_net(h)
         return out
+
+    @torch.no_grad()
+    def field_eval(self, x, d):
+        """Inference form of forward() for the evaluation renderer: hash-grid encode (input
+        normalisation fused) + ONE launch for density trunk, TruncExp, [h | d/|d| | 1] and colour head
+        (ncn_field_mlp_fwd), then the optional semantic / normal heads; nothing is saved for a backward.
+        x, d (N,3) f32 -> sigmas (N) f32, raws (N, 3 [+3] [+n_cls]) f32 in the channel order of rendering.py:203-208."""
+        if self.rgb_act != "Sigmoid":
+            raise NotImplementedError("field_eval covers the sigmoid colour head (ngp_mt with rgb_act='Sigmoid')")
+        from .tinycudann import _half_copy
+        L = _lib.lib()
+        st = stream()
+        n = x.shape[0]
+        dev = x.device
+        x = x.float().contiguous(); d = d.float().contiguous()
+        n_cls = self.sem_net.n_output_dims if self.pred_sem else 0
+        Ct = 3 + (3 if self.pred_norm else 0) + n_cls
+        f16 = dict(dtype=torch.float16, device=dev)
+        feat, h = torch.empty(n, 32, **f16), torch.empty(n, 16, **f16)
+        sigmas, raws = torch.empty(n, dtype=torch.float32, device=dev), torch.empty(n, Ct, dtype=torch.float32, device=dev)
+        if n == 0:
+            return sigmas, raws
+        xform = (C.c_float * 6)(*([float(self.xyz_min[0, i]) for i in range(3)] + [float((self.xyz_max - self.xyz_min)[0, i]) for i in range(3)])) \
+            if getattr(self, "_xform", None) is None else self._xform
+        self._xform = xform
+        check(L.ncn_grid_fwd(C.byref(self.xyz_encoder.desc), ptr(x), ptr(_half_copy(self.xyz_encoder)), n, ptr(feat), xform, None, st), "grid_fwd")
+        check(L.ncn_field_mlp_fwd(ptr(feat), ptr(d), ptr(_half_copy(self.sigma_net)), ptr(_half_copy(self.rgb_net)), n, None, ptr(sigmas),
+                                  ptr(raws), Ct, ptr(h), None, None, None, None, st), "field_mlp_fwd")
+        off = 3
+        for on, name, k in ((self.pred_norm, "norm_net", 3), (self.pred_sem, "sem_net", n_cls)):
+            if on:
+                net = getattr(self, name)
+                out = torch.empty(n, 16, **f16)
+                check(L.ncn_mlp_fwd(C.byref(net.desc), ptr(h), ptr(_half_copy(net)), n, ptr(out), None, None, st), name + "_fwd")
+                check(L.ncn_field_head_out(ptr(out), 16, n, None, ptr(raws), Ct, off, k, st), name + "_head_out")
+                off += k
+        return sigmas, raws
 
     # ------------------------------------------------------------------ occupancy grid
     @torch.no_grad()

@@ -29,7 +29,7 @@ def default_hparams(**over):
               num_epochs=30, steps_per_epoch=1000, density_tresh_decay=1.0, update_interval=16, warmup_steps=256,
               grad_clip=0.05, loss_scale=1024.0,
               ray_sampling_strategy="all_images_triang_patch", pred_norm_depth=True, pred_norm_nn=False, pred_sem=False,
-              loss_opacity_w=1e-3, loss_distortion_w=0, loss_depth_w=0, loss_norm_can_tres=0.01,
+              loss_opacity_w=1e-3, loss_distortion_w=0, loss_depth_w=0, loss_sem_w=0, loss_norm_can_tres=0.01,
               loss_norm_D_C_ort_dot_w=2e-3, loss_norm_D_C_centr_dot_w=2e-3, loss_norm_D_C_centr_L1_w=2e-3,
               loss_norm_can_start=500, loss_norm_can_grow=2500, loss_norm_can_end=-1, exp_step_factor=0.0)
     hp.update(over)
@@ -188,7 +188,7 @@ class NeRFTrainer:
         return results, loss_d
 
     def fused_step(self, capacity_per_ray=64, use_graph=True, fuse_fwd="mlp"):
-        """the sync-free CUDA-graph step (ncn_b200.fused.FusedStep) for the RGB+depth configuration"""
+        """the sync-free CUDA-graph step (ncn_b200.fused.FusedStep)"""
         if self.fused is None:
             from .fused import FusedStep
             self.fused = FusedStep(self, capacity_per_ray=capacity_per_ray, use_graph=use_graph, fuse_fwd=fuse_fwd)
@@ -196,7 +196,7 @@ class NeRFTrainer:
         return self.fused
 
     def train_step_fused(self, rays_o=None, rays_d=None, target_rgb=None, tri=None, update_grid=True, noise=None, packed=None,
-                         grid_restore=None):
+                         grid_restore=None, sem_target=None):
         """same step as train_step, through the fused path; returns nothing (stats via self.fused.stats_host())"""
         fs = self.fused_step()
         if tri is not None and (fs.tri is None or fs.tri.data_ptr() != tri.data_ptr()):
@@ -207,7 +207,7 @@ class NeRFTrainer:
                 self.maybe_update_grid()
             else:
                 fs.update_grid(restore=grid_restore)
-        fs.step(rays_o, rays_d, target_rgb, noise=noise, packed=packed)
+        fs.step(rays_o, rays_d, target_rgb, noise=noise, packed=packed, sem_target=sem_target)
 
     def train_step_from_pixels(self, img_idx, pix_idx, target_rgb, update_grid=True, grid_restore=None):
         """public end-to-end entry: (image, pixel) indices + target colours on the device -> one fused training step"""

@@ -46,3 +46,42 @@ def test_test_time_loop_matches_train_kernels(n_rays):
     torch.testing.assert_close(res["rgb"], rgb, rtol=1e-4, atol=5e-4)
     # the loop marches whole rounds of N_samples, so it may visit more samples than the ones composited in training, never fewer
     assert int(res["total_samples"]) >= int(n_used.sum())
+
+
+@pytest.mark.parametrize("heads,n_cls", [((False, False), 0), ((True, True), 5)])
+def test_render_fast_matches_test_time_loop(heads, n_cls):
+    """render_fast (one march + one field pass + one composite per tile) against the reference-shaped
+    round loop render(test_time=True): same rgb / depth / opacity (+ norm_nn, sem), with a tile size that does not divide
+    the ray count (ragged last tile) and rays that miss the box."""
+    import ncn_b200  # noqa: F401
+    from ncn_b200 import synth, vren
+    from ncn_b200.rendering import render, render_fast
+    from ncn_b200.trainer import NeRFTrainer
+    torch.manual_seed(0)
+    pred_sem, pred_norm = heads
+    tr = NeRFTrainer(dict(batch_size=1024, pred_sem=pred_sem, pred_norm_nn=pred_norm), device="cuda", n_sem_cls=n_cls)
+    model = tr.model
+    grid = synth.density_grid_from_occupancy(synth.room_occupancy(128, 0.5, seed=0))
+    model.density_grid.copy_(torch.from_numpy(grid).cuda())
+    vren.packbits(model.density_grid, 5.9, model.density_bitfield)
+    g = torch.Generator(device="cuda").manual_seed(1)
+    n = model.xyz_encoder.params.numel()
+    tr.opt.flat[:n].copy_(torch.randn(n, device="cuda", generator=g) * 0.5)
+    for name in ("sem_net", "norm_net"):
+        if hasattr(model, name):
+            p = getattr(model, name).params
+            p.data.copy_(torch.randn(p.numel(), device="cuda", generator=g) * 0.2)
+    tr.opt.flat16.copy_(tr.opt.flat)
+    b = synth.patch_batch(1024, seed=3)
+    rays_o = torch.from_numpy(b["rays_o"]).cuda()[:1000].contiguous()
+    rays_d = torch.from_numpy(b["rays_d"]).cuda()[:1000].contiguous()
+    rays_o[::50] += 10.0                                  # some rays start far outside and miss the box
+    kw = dict(near_distance=0.01, max_samples=1024, exp_step_factor=0.0, T_threshold=1e-4, n_sem_cls=n_cls)
+    ref = render(model, rays_o, rays_d, test_time=True, **kw)
+    out = render_fast(model, rays_o, rays_d, tile=384, **kw)
+    assert (ref["opacity"] > 0).float().mean() > 0.5
+    for k in ("opacity", "depth", "rgb") + (("norm_nn",) if pred_norm else ()) + (("sem",) if pred_sem else ()):
+        torch.testing.assert_close(out[k], ref[k].float(), rtol=1e-3, atol=1e-3, msg=lambda m, k=k: f"{k}: {m}")
+    assert int(ref["total_samples"]) >= int(out["total_samples"]) > 0
+    empty = render_fast(model, rays_o[:0], rays_d[:0], **kw)
+    assert empty["rgb"].shape == (0, 3)

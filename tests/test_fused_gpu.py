@@ -8,12 +8,12 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
-def _setup(R=2048, seed=0):
+def _setup(R=2048, seed=0, hp=None, n_sem_cls=0):
     import ncn_b200
     from ncn_b200 import synth, vren
     from ncn_b200.trainer import NeRFTrainer
     torch.manual_seed(seed)
-    tr = NeRFTrainer(dict(batch_size=R), device="cuda")
+    tr = NeRFTrainer(dict(batch_size=R, **(hp or {})), device="cuda", n_sem_cls=n_sem_cls)
     grid = synth.density_grid_from_occupancy(synth.room_occupancy(128, 0.5, seed=0))
     tr.model.density_grid.copy_(torch.from_numpy(grid).cuda())
     vren.packbits(tr.model.density_grid, 5.9, tr.model.density_bitfield)
@@ -68,6 +68,85 @@ def test_fused_matches_module_path(fuse_fwd):
         assert torch.isfinite(a).all()
         rel = float((a - b).norm() / b.norm().clamp_min(1e-20))
         assert rel <= 3e-2, (name, rel, float(b.norm()))
+
+
+@pytest.mark.parametrize("n_cls,fuse_fwd", [(3, "mlp"), (13, "mlp"), (3, False)])
+def test_fused_extra_heads_match_module_path(n_cls, fuse_fwd):
+    """config 3 (--pred_sem --pred_norm_nn, loss_sem_w > 0): semantic + normal heads as extra compositing channels, semantic
+    cross-entropy on the rendered logits; n_cls = 3 takes the on-the-fly dL/dout rows (tcgen05 mode 1), 13 the head_dout path.
+    The reference puts no loss on norm_nn, so norm_net's gradient must be exactly zero on both paths."""
+    hp = dict(pred_sem=True, pred_norm_nn=True, loss_sem_w=4e-2)
+    tr, rays_o, rays_d, tri, rgb, target = _setup(hp=hp, n_sem_cls=n_cls)
+    R = rays_o.shape[0]
+    g = torch.Generator(device="cuda").manual_seed(5)
+    for name in ("sem_net", "norm_net"):                      # larger head weights so the logits are not all ~0
+        p = getattr(tr.model, name).params
+        p.data.copy_(torch.randn(p.numel(), device="cuda", generator=g) * 0.2)
+    tr.opt.flat16.copy_(tr.opt.flat)
+    sem = torch.randint(0, n_cls + 1, (R,), device="cuda", generator=g)          # 0 = void (ignored)
+    target["semantics"] = sem
+    torch.manual_seed(123)
+    results, loss_d = tr.forward_loss(rays_o, rays_d, target)
+    (loss_d["total"] * tr.hp["loss_scale"]).backward()
+    g_mod = (tr.opt.grad / tr.hp["loss_scale"]).clone()
+    tr.opt.grad.zero_()
+    torch.manual_seed(123)
+    noise = torch.rand(R, device="cuda")
+    fs = tr.fused_step(use_graph=False, fuse_fwd=fuse_fwd)
+    fs.set_triangles(tri)
+    fs.rays_o.copy_(rays_o); fs.rays_d.copy_(rays_d); fs.target.copy_(rgb); fs.noise.copy_(noise); fs.sem_target.copy_(sem)
+    fs.gen_noise = False
+    fs._schedule()
+    fs._run()
+    torch.cuda.synchronize()
+    assert int(fs.counter[0]) == int(results["rm_samples"])
+    assert fs.Ct == 6 + n_cls
+    torch.testing.assert_close(fs.depth, results["depth"].detach(), rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(fs.rend[:, 3:6], results["norm_nn"].detach().float(), rtol=2e-3, atol=2e-3)
+    torch.testing.assert_close(fs.rend[:, 6:], results["sem"].detach().float(), rtol=2e-3, atol=2e-3)
+    d, n = fs.stats_host()
+    for k in ("rgb", "opacity", "sem", "norm_D_C_ort_dot", "norm_D_C_centr_dot", "norm_D_C_centr_L1"):
+        assert abs(d[k] - float(loss_d[k])) <= 2e-3 * abs(float(loss_d[k])) + 1e-7, (k, d[k], float(loss_d[k]))
+    g_fus = tr.opt.grad.clone()
+    for name in ("sem_net", "rgb_net", "sigma_net", "xyz_encoder"):
+        o, k = fs.off[name]
+        a, b = g_fus[o:o + k], g_mod[o:o + k]
+        assert torch.isfinite(a).all()
+        rel = float((a - b).norm() / b.norm().clamp_min(1e-20))
+        assert rel <= 3e-2, (name, rel, float(b.norm()))
+    o, k = fs.off["norm_net"]
+    assert float(g_fus[o:o + k].abs().max()) == 0.0 and float(g_mod[o:o + k].abs().max()) == 0.0
+
+
+def test_semantic_ce_kernel_matches_torch():
+    """ncn_semantic_ce_loss vs torch.nn.CrossEntropyLoss(ignore_index=-1)(logits, label - 1) (losses.py:240-242): value,
+    gradient, untouched neighbouring columns, and the all-void batch (NaN loss in the reference -> term dropped, zero gradient)"""
+    import ncn_b200  # noqa: F401
+    from ncn_b200 import _lib
+    from ncn_b200._lib import check, ptr, stream
+    L = _lib.lib()
+    g = torch.Generator(device="cuda").manual_seed(0)
+    for R, n_cls, c_off, Ct in ((8192, 3, 6, 9), (1000, 40, 3, 45), (1, 1, 0, 1)):
+        rend = torch.randn(R, Ct, device="cuda", generator=g) * 3
+        lab = torch.randint(0, n_cls + 1, (R,), device="cuda", generator=g)
+        sums = torch.zeros(2, device="cuda"); d = torch.full((R, Ct), 7.0, device="cuda")
+        check(L.ncn_semantic_ce_loss(ptr(rend), Ct, c_off, n_cls, ptr(lab), R, 2.5, ptr(sums), ptr(d), stream()))
+        x = rend[:, c_off:c_off + n_cls].clone().requires_grad_(True)
+        n_valid = int((lab > 0).sum())
+        assert int(sums[1]) == n_valid
+        if n_valid == 0:
+            assert float(d[:, c_off:c_off + n_cls].abs().max()) == 0.0
+            continue
+        ce = torch.nn.functional.cross_entropy(x, lab - 1, ignore_index=-1)
+        (2.5 * ce).backward()
+        torch.testing.assert_close(sums[0] / sums[1], ce.detach(), rtol=1e-5, atol=1e-6)
+        torch.testing.assert_close(d[:, c_off:c_off + n_cls], x.grad, rtol=1e-4, atol=1e-8)
+        keep = torch.ones(Ct, dtype=torch.bool, device="cuda"); keep[c_off:c_off + n_cls] = False
+        assert bool((d[:, keep] == 7.0).all())
+    lab = torch.zeros(64, dtype=torch.int64, device="cuda")
+    rend = torch.randn(64, 9, device="cuda", generator=g); sums = torch.zeros(2, device="cuda"); d = torch.ones(64, 9, device="cuda")
+    check(L.ncn_semantic_ce_loss(ptr(rend), 9, 6, 3, ptr(lab), 64, 1.0, ptr(sums), ptr(d), stream()))
+    assert float(sums[1]) == 0.0 and float(d[:, 6:].abs().max()) == 0.0
 
 
 def test_fused_graph_replay_trains():
