@@ -40,6 +40,8 @@ def parse():
     ap.add_argument("--fuse-fwd", default="mlp", choices=["none", "mlp", "all"], help="forward fusion of the fused step (A/B)")
     ap.add_argument("--heads", default="", help="extra heads of BASELINE config 3, e.g. 'sem,norm' (semantic head with 3 classes + "
                     "cross-entropy, normal head); default: the headline RGB+depth configuration")
+    ap.add_argument("--exchange", default="auto", choices=["auto", "peer", "nccl"], help="N>1 gradient exchange: sharded optimizer over NVLink "
+                    "peer memory (default when every rank can map every peer) or ncclAllReduce + replicated Adam")
     ap.add_argument("--no-graph", action="store_true", help="run the fused step eagerly instead of replaying its CUDA graph")
     return ap.parse_args()
 
@@ -168,7 +170,8 @@ def run_ours(args):
     R = args.rays
     heads = [h for h in args.heads.split(",") if h]
     hp_extra = dict(pred_sem="sem" in heads, pred_norm_nn="norm" in heads, loss_sem_w=4e-2 if "sem" in heads else 0)
-    tr = NeRFTrainer(dict(batch_size=R, **hp_extra), device=dev, rank=rank, world_size=world, n_sem_cls=3 if "sem" in heads else 0)
+    tr = NeRFTrainer(dict(batch_size=R, **hp_extra), device=dev, rank=rank, world_size=world, n_sem_cls=3 if "sem" in heads else 0,
+                     shard_optimizer={"auto": None, "peer": True, "nccl": False}[args.exchange] if world > 1 else False)
     grid = synth.density_grid_from_occupancy(synth.room_occupancy(128, 0.5, seed=0))
     tr.model.density_grid.copy_(torch.from_numpy(grid).to(dev))
     vren.packbits(tr.model.density_grid, 5.9, tr.model.density_bitfield)
@@ -318,11 +321,14 @@ def run_ours(args):
     ranks_in_sync = None
     if world > 1:      # replicated parameters must be bit-identical on every rank after the run (same all-reduced gradient, same Adam)
         fs.flush()
-        ref_p = tr.opt.flat.clone()
+        # sharded peer-memory optimizer: the replicated state is the fp16 working copy (each slice written by its owner into
+        # every rank's buffer); the fp32 master is only current inside a rank's own slice
+        mine = tr.opt.flat16.float() if tr.peer is not None else tr.opt.flat
+        ref_p = mine.clone()
         dist.broadcast(ref_p, 0)
-        diff = (tr.opt.flat - ref_p).abs().max()
+        diff = (mine - ref_p).abs().max()
         dist.all_reduce(diff, op=dist.ReduceOp.MAX)
-        ranks_in_sync = bool(diff.item() == 0.0)
+        ranks_in_sync = bool(diff.item() == 0.0) and (tr.peer is None or tr.peer.error() == 0)
 
     roofline = None
     if top and top_stats:
@@ -363,7 +369,8 @@ def run_ours(args):
                 "dtype": "f16", "data": "synthetic",
                 "config": {"workload": WORKLOAD if not heads else WORKLOAD.replace("RGB+depth heads", "RGB+depth+" + "+".join(heads) + " heads (config 3: n_sem_cls 3, cross-entropy w 4e-2)"),
                            "rays_per_step_per_gpu": R, "samples_per_step_per_gpu": n_samples,
-                           "parallelism": f"dp{world}", "ranks_in_sync": ranks_in_sync, "path": "fused CUDA-graph step (ncn_b200.fused.FusedStep)" if not args.no_graph else "fused eager step",
+                           "parallelism": f"dp{world}", "ranks_in_sync": ranks_in_sync,
+                           "exchange": None if world == 1 else ("sharded reduce + Adam + fp16 publish over NVLink peer memory (ncn_peer_step)" if tr.peer is not None else "ncclAllReduce(fp32 flat gradient) + replicated Adam"), "path": "fused CUDA-graph step (ncn_b200.fused.FusedStep)" if not args.no_graph else "fused eager step",
                            "occupancy": "synthetic room (13.6 % of 128^3 cells); grid update every 16 steps runs in full, its result is reverted to keep samples/ray stationary",
                            "init": "random (tcnn-style U(-1e-4,1e-4) table, Xavier MLPs)",
                            "l2": "no explicit flush: per-step working set (fp32 params+grads+Adam m,v = 183 MB, + 22 MB fp16 table) exceeds the 126 MB L2"},

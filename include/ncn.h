@@ -350,6 +350,16 @@ int ncn_field_mlp_fwd(const void* feat_f16, const float* dirs, const void* w_sig
                       const int32_t* n_dev, float* sigmas, float* raws, int c_total, void* h_f16, void* sig_acts_f16,
                       void* x_rgb_f16, void* rgb_acts_f16, void* rgb_out_f16, ncn_stream_t stream);
 
+/* The extra heads on h (models/ngp_mt.py:104-140, 217-224: sem_net / norm_net, 16 -> 64 -> 64 -> n_out <= 16, ReLU hidden,
+ * no output activation), evaluated together in ONE launch: h (N,16) f16 is read once, outputs are written straight into
+ * raws[:, c_off : c_off + n_ch] (f32, row stride c_total; the channel layout of rendering.py:203-208).  Head a / head b:
+ * w NULL = absent; acts (ncn_mlp_acts_bytes of the net) and out (N,16) f16 are optional (NULL when no backward follows).
+ * Replaces 2 x (ncn_mlp_fwd + ncn_field_head_out). */
+int ncn_field_heads_fwd(const void* h_f16, int64_t n, const int32_t* n_dev, float* raws, int c_total,
+                        const void* w_a_f16, int c_off_a, int n_ch_a, void* acts_a_f16, void* out_a_f16,
+                        const void* w_b_f16, int c_off_b, int n_ch_b, void* acts_b_f16, void* out_b_f16,
+                        ncn_stream_t stream);
+
 /* Selects the ncn_mlp_bwd implementation: 1 (default) = every GEMM (dgrad and wgrad) on tcgen05 with TMEM
  * accumulators, 128-row tiles fed by bulk copies (shapes without an instantiation fall back to 0);
  * 0 = warp-MMA dgrad in registers + split-K wgrad kernels.  Returns the old value. */
@@ -506,6 +516,35 @@ int ncn_comm_init(ncn_comm** comm, const void* id128_host, int world_size, int r
 int ncn_comm_allreduce_sum_f32(ncn_comm* comm, float* buf, int64_t n, ncn_stream_t stream);
 int ncn_comm_destroy(ncn_comm* comm);
 const char* ncn_comm_last_error(void);
+
+/* The same exchange step WITHOUT a collective library: gradient reduction, ||g||^2, clip, Adam and the refresh of the fp16
+ * working parameters as two kernels over NVLink peer memory (one process per GPU, buffers shared by CUDA IPC).
+ * Rank r owns the r-th 1/W slice of the flat parameter vector: it sums that slice out of every rank's gradient buffer
+ * (P2P loads, fixed rank order), applies Adam to it (its p / m / v slices are the only ones kept current on this rank) and
+ * stores the fp16 result into EVERY rank's fp16 parameter buffer - the buffer the forward kernels read.  Equivalent to
+ * ncn_comm_allreduce_sum_f32 + ncn_grad_sumsq + ncn_adam_step_groups on every rank (train_nerf.py:949-955) up to the
+ * summation order of the W gradient terms; the fp32 master outside a rank's own slice is stale by design.
+ *   create : cudaMalloc's the gradient buffer (n f32, zeroed), the fp16 parameter buffer (n f16) and a sync block;
+ *            n_params % 4 == 0, world <= 8.  The backward must accumulate into ncn_peer_grad(), the forward must read
+ *            ncn_peer_p16().
+ *   handles: 3 cudaIpcMemHandle_t (192 bytes) to ship to the other ranks out of band; connect: all ranks' handles
+ *            (world x 192 bytes, rank order).  world == 1 needs neither.
+ *   step   : asynchronous on `stream`, graph-capturable; groups / lr_bc_dev / skip_dev / grad_div_dev as in
+ *            ncn_adam_step_groups; sumsq_out_dev (optional) receives the squared norm of the averaged gradient.
+ *            Every rank must call it the same number of times.  Cross-GPU waits are bounded (4 s) and set the error word
+ *            (ncn_peer_error) instead of hanging. */
+typedef struct ncn_peer ncn_peer;
+int ncn_peer_create(ncn_peer** out, int rank, int world, int64_t n_params);
+float* ncn_peer_grad(ncn_peer* p);
+void* ncn_peer_p16(ncn_peer* p);
+int ncn_peer_handles(ncn_peer* p, void* handles192_host);
+int ncn_peer_connect(ncn_peer* p, const void* all_handles_host);
+void ncn_peer_shard(int64_t n_params, int rank, int world, int64_t* lo, int64_t* hi);
+int ncn_peer_step(ncn_peer* p, float* param, float* m, float* v, const ncn_adam_groups* groups, float beta1,
+                  float beta2, float eps, const float* grad_div_dev, const int32_t* skip_dev,
+                  const float* lr_bc_dev, float* sumsq_out_dev, ncn_stream_t stream);
+int ncn_peer_error(ncn_peer* p, unsigned int* error_host);
+int ncn_peer_destroy(ncn_peer* p);
 
 #ifdef __cplusplus
 }

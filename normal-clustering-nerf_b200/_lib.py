@@ -55,7 +55,9 @@ class Profiler:
     KERNELS_PER_CALL = {"ncn_march_train": 3, "ncn_march_train_count": 3, "ncn_cluster_tail": 2, "ncn_kmeans_workspace_bytes": 0,
                         "ncn_march_train_workspace_bytes": 0, "ncn_mlp_bwd_workspace_bytes": 0, "ncn_mlp_acts_bytes": 0, "ncn_mlp_n_params": 0,
                         "ncn_grid_desc_init": 0, "ncn_version": 0, "ncn_set_mlp_bwd_impl": 0, "ncn_set_march_segments": 0, "ncn_debug_stamp": 1, "ncn_set_grid_bwd_merge": 0, "ncn_set_grid_fwd_coherent": 0, "ncn_error_string": 0, "ncn_device_info": 0,
-                        "ncn_comm_unique_id": 0, "ncn_comm_init": 0, "ncn_comm_destroy": 0, "ncn_comm_last_error": 0}
+                        "ncn_comm_unique_id": 0, "ncn_comm_init": 0, "ncn_comm_destroy": 0, "ncn_comm_last_error": 0,
+                        "ncn_peer_create": 0, "ncn_peer_grad": 0, "ncn_peer_p16": 0, "ncn_peer_handles": 0, "ncn_peer_connect": 0,
+                        "ncn_peer_shard": 0, "ncn_peer_step": 2, "ncn_peer_error": 0, "ncn_peer_destroy": 0}
 
     @classmethod
     def reset(cls):
@@ -214,6 +216,7 @@ SIGNATURES.update({
                               c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "ncn_rays_from_pixels": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp]),
     "ncn_field_prepare_rgb": (c_i32, [c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp]),
+    "ncn_field_heads_fwd": (c_i32, [c_vp, c_i64, c_vp, c_vp, c_i32, c_vp, c_i32, c_i32, c_vp, c_vp, c_vp, c_i32, c_i32, c_vp, c_vp, c_vp]),
     "ncn_field_head_out": (c_i32, [c_vp, c_i32, c_i64, c_vp, c_vp, c_i32, c_i32, c_i32, c_vp]),
     "ncn_field_head_dout": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_f32, c_i64, c_vp, c_vp, c_i32, c_vp]),
     "ncn_field_bwd_h": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_f32, c_i64, c_vp, c_vp, c_vp]),
@@ -224,4 +227,13 @@ SIGNATURES.update({
     "ncn_comm_allreduce_sum_f32": (c_i32, [c_vp, c_vp, c_i64, c_vp]),
     "ncn_comm_destroy": (c_i32, [c_vp]),
     "ncn_comm_last_error": (C.c_char_p, []),
+    "ncn_peer_create": (c_i32, [C.POINTER(c_vp), c_i32, c_i32, c_i64]),
+    "ncn_peer_grad": (c_vp, [c_vp]),
+    "ncn_peer_p16": (c_vp, [c_vp]),
+    "ncn_peer_handles": (c_i32, [c_vp, c_vp]),
+    "ncn_peer_connect": (c_i32, [c_vp, c_vp]),
+    "ncn_peer_shard": (None, [c_i64, c_i32, c_i32, C.POINTER(c_i64), C.POINTER(c_i64)]),
+    "ncn_peer_step": (c_i32, [c_vp, c_vp, c_vp, c_vp, C.POINTER(AdamGroups), c_f32, c_f32, c_f32, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "ncn_peer_error": (c_i32, [c_vp, C.POINTER(C.c_uint32)]),
+    "ncn_peer_destroy": (c_i32, [c_vp]),
 })

@@ -235,9 +235,106 @@ field_fwd_kernel(const __grid_constant__ FfGridMeta meta, const float* __restric
   }
 }
 
+// ---------------------------------------------------------------- extra heads on h (ngp_mt.py:217-224)
+// sem_net / norm_net (16 -> 64 -> 64 -> n_out <= 16, ReLU hidden, no output activation) evaluated together: h is read
+// once, each net's three layers are chained in registers, the hidden states go out in the tiled activation layout (only
+// when a backward will need them) and the outputs land directly in their raws columns (fp32 of the fp16 network output,
+// as the tcnn module returns half) - replaces 2 x (ncn_mlp_fwd + ncn_field_head_out).
+struct FfHead {
+  const __half* w;      // tcnn layout: [64][16] | [64][64] | [16][64]; nullptr = head absent
+  __half* acts;         // (2, act_rows(n_cap), 64) tiled, or nullptr
+  __half* out;          // (N,16) f16 or nullptr
+  int c_off, n_ch;
+};
+constexpr int kHeadW = 64 * (16 + kFfPad) + 64 * (64 + kFfPad) + 16 * (64 + kFfPad);
+
+__global__ void __launch_bounds__(kFfThreads)
+field_heads_fwd_kernel(const __half* __restrict__ h, int64_t n_cap, const int32_t* __restrict__ n_dev, float* __restrict__ raws,
+                       int c_total, FfHead ha, FfHead hb) {
+  __shared__ __align__(16) __half sW[2 * kHeadW];
+  const FfHead heads[2] = {ha, hb};
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    if (heads[q].w == nullptr) continue;
+    __half* W0 = sW + q * kHeadW;
+    ff_load_w(heads[q].w, 64, 16, W0, false);
+    ff_load_w(heads[q].w + 64 * 16, 64, 64, W0 + 64 * (16 + kFfPad), false);
+    ff_load_w(heads[q].w + 64 * 16 + 64 * 64, 16, 64, W0 + 64 * (16 + kFfPad) + 64 * (64 + kFfPad), false);
+  }
+  __syncthreads();
+  int64_t n = n_cap;
+  if (n_dev != nullptr) { const int64_t nd = *n_dev; if (nd < n) n = nd; }
+  const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int64_t n_tiles = (n + 15) >> 4;
+  for (int64_t tile = warp; tile < n_tiles; tile += n_warps) {
+    const int64_t row0 = tile << 4;
+    const int64_t r0 = row0 + g, r1 = r0 + 8;
+    uint32_t ah[1][4];
+    ah[0][0] = r0 < n ? *reinterpret_cast<const uint32_t*>(h + r0 * 16 + 2 * t) : 0u;
+    ah[0][1] = r1 < n ? *reinterpret_cast<const uint32_t*>(h + r1 * 16 + 2 * t) : 0u;
+    ah[0][2] = r0 < n ? *reinterpret_cast<const uint32_t*>(h + r0 * 16 + 8 + 2 * t) : 0u;
+    ah[0][3] = r1 < n ? *reinterpret_cast<const uint32_t*>(h + r1 * 16 + 8 + 2 * t) : 0u;
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const FfHead& hd = heads[q];
+      if (hd.w == nullptr) continue;
+      const __half* W0 = sW + q * kHeadW;
+      const __half* W1 = W0 + 64 * (16 + kFfPad);
+      const __half* W2 = W1 + 64 * (64 + kFfPad);
+      float c[8][4];
+      uint32_t hid[4][4];
+      ff_layer<16, 64>(ah, W0, c, g, t);
+      ff_relu_pack(c, hid);
+      if (hd.acts) ff_store_act(hd.acts, row0, n, hid, g, t);
+      ff_layer<64, 64>(hid, W1, c, g, t);
+      ff_relu_pack(c, hid);
+      if (hd.acts) ff_store_act(hd.acts + act_rows(n_cap) * 64, row0, n, hid, g, t);
+      float co[2][4];
+      ff_layer<64, 16>(hid, W2, co, g, t);
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int col = j * 8 + 2 * t;
+        const uint32_t p0 = pack_half2(co[j][0], co[j][1]), p1 = pack_half2(co[j][2], co[j][3]);
+        if (hd.out) {
+          if (r0 < n) *reinterpret_cast<uint32_t*>(hd.out + r0 * 16 + col) = p0;
+          if (r1 < n) *reinterpret_cast<uint32_t*>(hd.out + r1 * 16 + col) = p1;
+        }
+        const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&p0)), f1 = __half22float2(*reinterpret_cast<const __half2*>(&p1));
+        if (col < hd.n_ch) {
+          if (r0 < n) raws[r0 * c_total + hd.c_off + col] = f0.x;
+          if (r1 < n) raws[r1 * c_total + hd.c_off + col] = f1.x;
+        }
+        if (col + 1 < hd.n_ch) {
+          if (r0 < n) raws[r0 * c_total + hd.c_off + col + 1] = f0.y;
+          if (r1 < n) raws[r1 * c_total + hd.c_off + col + 1] = f1.y;
+        }
+      }
+    }
+  }
+}
+
 }  // namespace ncn
 
 using namespace ncn;
+
+extern "C" int ncn_field_heads_fwd(const void* h_f16, int64_t n, const int32_t* n_dev, float* raws, int c_total,
+                                   const void* w_a_f16, int c_off_a, int n_ch_a, void* acts_a_f16, void* out_a_f16,
+                                   const void* w_b_f16, int c_off_b, int n_ch_b, void* acts_b_f16, void* out_b_f16,
+                                   ncn_stream_t stream) {
+  NCN_CHECK_SIZE(n >= 0 && c_total >= 1);
+  if (n == 0 || (w_a_f16 == nullptr && w_b_f16 == nullptr)) return NCN_OK;
+  NCN_CHECK_PTR(h_f16); NCN_CHECK_PTR(raws);
+  if (w_a_f16) NCN_CHECK_SIZE(n_ch_a >= 1 && n_ch_a <= 16 && c_off_a >= 0 && c_off_a + n_ch_a <= c_total);
+  if (w_b_f16) NCN_CHECK_SIZE(n_ch_b >= 1 && n_ch_b <= 16 && c_off_b >= 0 && c_off_b + n_ch_b <= c_total);
+  FfHead ha{(const __half*)w_a_f16, (__half*)acts_a_f16, (__half*)out_a_f16, c_off_a, n_ch_a};
+  FfHead hb{(const __half*)w_b_f16, (__half*)acts_b_f16, (__half*)out_b_f16, c_off_b, n_ch_b};
+  const int grid = persistent_grid(((n + 15) / 16) * 32, kFfThreads, 6);
+  field_heads_fwd_kernel<<<grid, kFfThreads, 0, as_stream(stream)>>>((const __half*)h_f16, n, n_dev, raws, c_total, ha, hb);
+  NCN_LAUNCH_OK();
+  return NCN_OK;
+}
 
 extern "C" int ncn_field_fwd(const ncn_grid_desc* desc, const float* x, const float* dirs, const void* table_f16,
                              const void* w_sigma_f16, const void* w_rgb_f16, int64_t n, const int32_t* n_dev,

@@ -885,9 +885,12 @@ semantic_ce_kernel(const float* __restrict__ rend, int C, int c_off, int n_cls, 
   __shared__ float s_sum[8];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   int cnt = 0;
-  for (int64_t r = threadIdx.x; r < n_rays; r += blockDim.x) {
-    const int64_t t = labels[r] - 1;
-    cnt += (t >= 0 && t < n_cls) ? 1 : 0;
+  for (int64_t base = 0; base < n_rays; base += 8 * 256) {      // 8 independent loads in flight per thread
+    int64_t v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) { const int64_t r = base + u * 256 + threadIdx.x; v[u] = r < n_rays ? __ldg(labels + r) : 0; }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) cnt += (v[u] >= 1 && v[u] <= n_cls) ? 1 : 0;
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);

@@ -255,3 +255,318 @@ extern "C" int ncn_clip_coef(const float* sumsq_dev, float max_norm, float* coef
   NCN_LAUNCH_OK();
   return NCN_OK;
 }
+
+// =====================================================================================================================
+// Data-parallel optimizer over NVLink PEER MEMORY (the one exchange step of the path).
+// Replaces [ncclAllReduce(flat gradient) -> ||g||^2 -> Adam on every rank] (train_nerf.py:949-955) by a sharded form whose
+// result is the same replicated parameter set:
+//   K1  rank r sums shard r of the gradient straight out of every peer's gradient buffer (P2P loads, fixed rank order ->
+//       deterministic), parks the sum in its own buffer, reduces ||g_shard||^2 and posts it to every peer;
+//   K2  total norm (same fixed-order sum on every rank -> identical clip coefficient), Adam on the shard only (1/W of the
+//       p/m/v traffic), the fp16 working copy of the shard is STORED INTO EVERY PEER's fp16 parameter buffer (the only form
+//       of the parameters the forward reads), the whole local gradient buffer is zeroed for the next backward.
+// Per rank and step: (W-1)/W * 4 B/param in over NVLink, (W-1)/W * 2 B/param out - vs 2 * (W-1)/W * 4 B each way for a ring
+// all-reduce - no NCCL call, so the whole step stays ONE CUDA graph.  Cross-GPU ordering uses epoch flags in each rank's
+// sync block (release/acquire at system scope); every wait has a wall-clock bound and raises `error` instead of hanging.
+namespace ncn {
+
+constexpr int kPeerMax = 8;
+struct PeerSync {                       // lives in each rank's own device memory, written by peers
+  unsigned int flag[3][kPeerMax];       // [phase][source rank] = last epoch that rank signalled
+  float norm[2][kPeerMax];              // [epoch & 1][source rank] partial squared norms (NaN = non-finite gradient there)
+  unsigned int epoch;                   // local: completed steps
+  unsigned int ticket[2];               // local: block tickets of K1 / K2
+  unsigned int error;                   // local: a wait timed out
+  float partials[kSumsqMaxBlocks];      // local: K1 block partials
+};
+struct PeerPtrs {
+  const float* grad[kPeerMax];
+  __half* p16[kPeerMax];
+  PeerSync* sync[kPeerMax];
+};
+
+__device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long peer_now_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+// one thread: wait until every rank's flag of `phase` reached `epoch` (bounded: 4 s)
+__device__ __forceinline__ void peer_wait(PeerSync* me, int phase, int world, unsigned int epoch) {
+  const unsigned long long t0 = peer_now_ns();
+  for (int q = 0; q < world; ++q) {
+    while ((int)(ld_acquire_sys(&me->flag[phase][q]) - epoch) < 0) {
+      __nanosleep(64);
+      if (peer_now_ns() - t0 > 4000000000ull) { atomicExch(&me->error, 1u + (unsigned)phase); return; }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256, 2)
+peer_reduce_kernel(PeerPtrs pp, int rank, int world, int64_t lo4, int64_t hi4, float* my_grad /* == pp.grad[rank] */,
+                   const float* __restrict__ grad_div) {
+  PeerSync* me = pp.sync[rank];
+  __shared__ unsigned int s_epoch;
+  if (threadIdx.x == 0) {
+    const unsigned int e = *reinterpret_cast<volatile unsigned int*>(&me->epoch) + 1u;
+    if (blockIdx.x == 0) {                     // "my backward is complete": stream order put this kernel after it
+      __threadfence_system();
+      for (int q = 0; q < world; ++q) st_release_sys(&pp.sync[q]->flag[0][rank], e);
+    }
+    peer_wait(me, 0, world, e);
+    s_epoch = e;
+  }
+  __syncthreads();
+  const unsigned int epoch = s_epoch;
+  const float gmul = grad_div ? 1.f / *grad_div : 1.f;
+  float acc = 0.f;
+  bool bad = false;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i0 = lo4 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < hi4; i0 += 2 * stride) {
+    const int64_t i1 = i0 + stride;
+    const bool two = i1 < hi4;
+    float4 a[kPeerMax], b[kPeerMax];
+#pragma unroll
+    for (int q = 0; q < kPeerMax; ++q) {
+      if (q < world) {
+        a[q] = __ldcs(reinterpret_cast<const float4*>(pp.grad[q]) + i0);
+        if (two) b[q] = __ldcs(reinterpret_cast<const float4*>(pp.grad[q]) + i1);
+      }
+    }
+    float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0;
+#pragma unroll
+    for (int q = 0; q < kPeerMax; ++q) {         // fixed order 0..W-1: the sum does not depend on who computes it or when
+      if (q < world) {
+        s0.x += a[q].x; s0.y += a[q].y; s0.z += a[q].z; s0.w += a[q].w;
+        if (two) { s1.x += b[q].x; s1.y += b[q].y; s1.z += b[q].z; s1.w += b[q].w; }
+      }
+    }
+    reinterpret_cast<float4*>(my_grad)[i0] = s0;
+    { const float x = s0.x * gmul, y = s0.y * gmul, z = s0.z * gmul, w = s0.w * gmul;
+      acc += x * x + y * y + z * z + w * w; bad |= !(isfinite(x) && isfinite(y) && isfinite(z) && isfinite(w)); }
+    if (two) {
+      reinterpret_cast<float4*>(my_grad)[i1] = s1;
+      const float x = s1.x * gmul, y = s1.y * gmul, z = s1.z * gmul, w = s1.w * gmul;
+      acc += x * x + y * y + z * z + w * w; bad |= !(isfinite(x) && isfinite(y) && isfinite(z) && isfinite(w));
+    }
+  }
+  if (bad) acc = __int_as_float(0x7fc00000);
+  acc = warp_sum(acc);
+  __shared__ float s[8];
+  __shared__ bool s_last;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane == 0) s[wid] = acc;
+  __syncthreads();
+  if (wid == 0) {
+    acc = lane < 8 ? s[lane] : 0.f;
+    acc = warp_sum(acc);
+    if (lane == 0) {
+      me->partials[blockIdx.x] = acc;
+      __threadfence();
+      s_last = atomicAdd(&me->ticket[0], 1u) == gridDim.x - 1;
+    }
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  float tot = 0.f;                               // fixed order (see sumsq_kernel)
+  for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x) tot += __ldcg(&me->partials[b]);
+  tot = warp_sum(tot);
+  if (lane == 0) s[wid] = tot;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    tot = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) tot += s[w];
+    me->ticket[0] = 0;
+    // every block of this rank has finished reading the peers' gradients: post the partial norm, then the flag
+    for (int q = 0; q < world; ++q) *reinterpret_cast<volatile float*>(&pp.sync[q]->norm[epoch & 1][rank]) = tot;
+    __threadfence_system();
+    for (int q = 0; q < world; ++q) st_release_sys(&pp.sync[q]->flag[1][rank], epoch);
+  }
+}
+
+__global__ void __launch_bounds__(256, 2)
+peer_adam_kernel(PeerPtrs pp, int rank, int world, int64_t lo4, int64_t hi4, int64_t n4, float* __restrict__ param,
+                 float* __restrict__ grad, float* __restrict__ m, float* __restrict__ v, AdamArgs a,
+                 const float* __restrict__ grad_div, const int32_t* __restrict__ skip, const float* __restrict__ lr_bc,
+                 float* __restrict__ sumsq_out) {
+  PeerSync* me = pp.sync[rank];
+  __shared__ unsigned int s_epoch;
+  __shared__ float s_tot;
+  if (threadIdx.x == 0) {
+    const unsigned int e = *reinterpret_cast<volatile unsigned int*>(&me->epoch) + 1u;
+    peer_wait(me, 1, world, e);                // every rank's partial norm is here AND every rank is done reading my gradient
+    float tot = 0.f;
+    for (int q = 0; q < world; ++q) tot += *reinterpret_cast<volatile float*>(&me->norm[e & 1][q]);
+    s_tot = tot; s_epoch = e;
+  }
+  __syncthreads();
+  const unsigned int epoch = s_epoch;
+  const float total = s_tot;
+  if (blockIdx.x == 0 && threadIdx.x == 0 && sumsq_out) *sumsq_out = total;
+  if (lr_bc != nullptr) { a.lr = lr_bc[0]; a.bc1 = lr_bc[1]; a.bc2 = lr_bc[2]; }
+  const bool do_skip = (skip != nullptr && *skip != 0) || !isfinite(total);
+  float gmul = grad_div ? 1.f / *grad_div : 1.f;
+  if (a.max_norm > 0.f) { const float c = a.max_norm / (sqrtf(total) + 1e-6f); gmul *= c < 1.f ? c : 1.f; }
+  const float inv_bc1 = 1.f / a.bc1, inv_bc2 = 1.f / a.bc2;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (!do_skip) {
+    for (int64_t i = lo4 + tid; i < hi4; i += stride) {
+      float4 g = reinterpret_cast<const float4*>(grad)[i];
+      float4 p = __ldcs(reinterpret_cast<const float4*>(param) + i), mm = __ldcs(reinterpret_cast<const float4*>(m) + i),
+             vv = __ldcs(reinterpret_cast<const float4*>(v) + i);
+      if (a.n_groups > 0) a.weight_decay = adam_wd_at(a, i << 2);
+      adam_one(p.x, g.x, mm.x, vv.x, a, gmul, inv_bc1, inv_bc2); adam_one(p.y, g.y, mm.y, vv.y, a, gmul, inv_bc1, inv_bc2);
+      adam_one(p.z, g.z, mm.z, vv.z, a, gmul, inv_bc1, inv_bc2); adam_one(p.w, g.w, mm.w, vv.w, a, gmul, inv_bc1, inv_bc2);
+      reinterpret_cast<float4*>(param)[i] = p; reinterpret_cast<float4*>(m)[i] = mm; reinterpret_cast<float4*>(v)[i] = vv;
+      reinterpret_cast<float4*>(grad)[i] = g;      // adam_one zeroed it
+      const __half2 lo = __floats2half2_rn(p.x, p.y), hi = __floats2half2_rn(p.z, p.w);
+      uint2 pk; pk.x = *reinterpret_cast<const uint32_t*>(&lo); pk.y = *reinterpret_cast<const uint32_t*>(&hi);
+#pragma unroll
+      for (int q = 0; q < kPeerMax; ++q)         // publish the shard's fp16 working copy into every rank's parameter buffer
+        if (q < world) reinterpret_cast<uint2*>(pp.p16[q])[i] = pk;
+    }
+  }
+  // the next backward accumulates into a zeroed buffer; peers are done reading it (barrier above)
+  // (the shard itself was zeroed element by element by the thread that consumed it)
+  for (int64_t i = tid; i < n4; i += stride)
+    if (do_skip || i < lo4 || i >= hi4) reinterpret_cast<float4*>(grad)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  __threadfence_system();
+  __shared__ bool s_last;
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = atomicAdd(&me->ticket[1], 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (!s_last) return;
+  if (threadIdx.x == 0) {
+    me->ticket[1] = 0;
+    __threadfence_system();
+    for (int q = 0; q < world; ++q) st_release_sys(&pp.sync[q]->flag[2][rank], epoch);
+    peer_wait(me, 2, world, epoch);            // every shard of MY fp16 parameter buffer has been written by its owner
+    *reinterpret_cast<volatile unsigned int*>(&me->epoch) = epoch;
+    __threadfence();
+  }
+}
+
+}  // namespace ncn
+
+struct ncn_peer {
+  int rank, world, device;
+  int64_t n;
+  float* grad;
+  void* p16;
+  ncn::PeerSync* sync;
+  ncn::PeerPtrs ptrs;
+  void* opened[3][ncn::kPeerMax];
+  bool connected;
+};
+
+extern "C" int ncn_peer_create(ncn_peer** out, int rank, int world, int64_t n_params) {
+  NCN_CHECK_PTR(out);
+  NCN_CHECK_SIZE(world >= 1 && world <= ncn::kPeerMax && rank >= 0 && rank < world && n_params > 0 && (n_params & 3) == 0);
+  ncn_peer* p = new ncn_peer();
+  p->rank = rank; p->world = world; p->n = n_params; p->connected = false;
+  NCN_CUDA(cudaGetDevice(&p->device));
+  NCN_CUDA(cudaMalloc(&p->grad, (size_t)n_params * 4));
+  NCN_CUDA(cudaMalloc(&p->p16, (size_t)n_params * 2));
+  NCN_CUDA(cudaMalloc(&p->sync, sizeof(ncn::PeerSync)));
+  NCN_CUDA(cudaMemset(p->grad, 0, (size_t)n_params * 4));
+  NCN_CUDA(cudaMemset(p->p16, 0, (size_t)n_params * 2));
+  NCN_CUDA(cudaMemset(p->sync, 0, sizeof(ncn::PeerSync)));
+  NCN_CUDA(cudaDeviceSynchronize());
+  for (int k = 0; k < 3; ++k) for (int q = 0; q < ncn::kPeerMax; ++q) p->opened[k][q] = nullptr;
+  if (world == 1) {
+    p->ptrs.grad[0] = p->grad; p->ptrs.p16[0] = (__half*)p->p16; p->ptrs.sync[0] = p->sync;
+    p->connected = true;
+  }
+  *out = p;
+  return NCN_OK;
+}
+
+extern "C" float* ncn_peer_grad(ncn_peer* p) { return p ? p->grad : nullptr; }
+extern "C" void* ncn_peer_p16(ncn_peer* p) { return p ? p->p16 : nullptr; }
+
+extern "C" int ncn_peer_handles(ncn_peer* p, void* handles_out) {
+  NCN_CHECK_PTR(p); NCN_CHECK_PTR(handles_out);
+  cudaIpcMemHandle_t* h = (cudaIpcMemHandle_t*)handles_out;
+  NCN_CUDA(cudaIpcGetMemHandle(&h[0], p->grad));
+  NCN_CUDA(cudaIpcGetMemHandle(&h[1], p->p16));
+  NCN_CUDA(cudaIpcGetMemHandle(&h[2], p->sync));
+  return NCN_OK;
+}
+
+extern "C" int ncn_peer_connect(ncn_peer* p, const void* all_handles) {
+  NCN_CHECK_PTR(p); NCN_CHECK_PTR(all_handles);
+  const cudaIpcMemHandle_t* h = (const cudaIpcMemHandle_t*)all_handles;
+  for (int q = 0; q < p->world; ++q) {
+    if (q == p->rank) {
+      p->ptrs.grad[q] = p->grad; p->ptrs.p16[q] = (__half*)p->p16; p->ptrs.sync[q] = p->sync;
+      continue;
+    }
+    for (int k = 0; k < 3; ++k)
+      NCN_CUDA(cudaIpcOpenMemHandle(&p->opened[k][q], h[3 * q + k], cudaIpcMemLazyEnablePeerAccess));
+    p->ptrs.grad[q] = (const float*)p->opened[0][q];
+    p->ptrs.p16[q] = (__half*)p->opened[1][q];
+    p->ptrs.sync[q] = (ncn::PeerSync*)p->opened[2][q];
+  }
+  p->connected = true;
+  return NCN_OK;
+}
+
+extern "C" void ncn_peer_shard(int64_t n_params, int rank, int world, int64_t* lo, int64_t* hi) {
+  const int64_t n4 = n_params >> 2;
+  if (lo) *lo = (n4 * rank / world) << 2;
+  if (hi) *hi = (n4 * (rank + 1) / world) << 2;
+}
+
+extern "C" int ncn_peer_step(ncn_peer* p, float* param, float* m, float* v, const ncn_adam_groups* groups, float beta1,
+                             float beta2, float eps, const float* grad_div_dev, const int32_t* skip_dev,
+                             const float* lr_bc_dev, float* sumsq_out_dev, ncn_stream_t stream) {
+  NCN_CHECK_PTR(p); NCN_CHECK_PTR(param); NCN_CHECK_PTR(m); NCN_CHECK_PTR(v); NCN_CHECK_PTR(groups); NCN_CHECK_PTR(lr_bc_dev);
+  if (!p->connected) return NCN_E_CONFIG;
+  if (groups->n_groups < 1 || groups->n_groups > NCN_ADAM_MAX_GROUPS || groups->start[0] != 0) return NCN_E_CONFIG;
+  if (((uintptr_t)param | (uintptr_t)m | (uintptr_t)v) & 15) return NCN_E_ALIGN;
+  ncn::AdamArgs a;
+  a.lr = 0.f; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.weight_decay = groups->weight_decay[0]; a.bc1 = 1.f; a.bc2 = 1.f;
+  a.n_groups = groups->n_groups; a.max_norm = groups->max_norm;
+  for (int q = 0; q < NCN_ADAM_MAX_GROUPS; ++q) {
+    const bool on = q < groups->n_groups;
+    a.start[q] = on ? groups->start[q] : p->n; a.wd[q] = on ? groups->weight_decay[q] : 0.f;
+    if (on && (groups->start[q] & 3)) return NCN_E_ALIGN;
+  }
+  int64_t lo, hi;
+  ncn_peer_shard(p->n, p->rank, p->world, &lo, &hi);
+  const int64_t lo4 = lo >> 2, hi4 = hi >> 2, n4 = p->n >> 2;
+  int grid = ncn::sm_count() * 2;
+  if (grid > ncn::kSumsqMaxBlocks) grid = ncn::kSumsqMaxBlocks;
+  cudaStream_t st = ncn::as_stream(stream);
+  ncn::peer_reduce_kernel<<<grid, 256, 0, st>>>(p->ptrs, p->rank, p->world, lo4, hi4, p->grad, grad_div_dev);
+  NCN_LAUNCH_OK();
+  ncn::peer_adam_kernel<<<grid, 256, 0, st>>>(p->ptrs, p->rank, p->world, lo4, hi4, n4, param, p->grad, m, v, a, grad_div_dev,
+                                              skip_dev, lr_bc_dev, sumsq_out_dev);
+  NCN_LAUNCH_OK();
+  return NCN_OK;
+}
+
+extern "C" int ncn_peer_error(ncn_peer* p, unsigned int* error_host) {
+  NCN_CHECK_PTR(p); NCN_CHECK_PTR(error_host);
+  NCN_CUDA(cudaMemcpy(error_host, &p->sync->error, sizeof(unsigned int), cudaMemcpyDeviceToHost));
+  return NCN_OK;
+}
+
+extern "C" int ncn_peer_destroy(ncn_peer* p) {
+  if (!p) return NCN_OK;
+  cudaDeviceSynchronize();
+  for (int k = 0; k < 3; ++k) for (int q = 0; q < ncn::kPeerMax; ++q) if (p->opened[k][q]) cudaIpcCloseMemHandle(p->opened[k][q]);
+  cudaFree(p->grad); cudaFree(p->p16); cudaFree(p->sync);
+  delete p;
+  return NCN_OK;
+}

@@ -116,10 +116,13 @@ class FusedStep:
         self.pending = False                 # deferred mode: a gradient is waiting for its optimizer pass
         # deferred optimizer: graph mode, single rank (the gradient all-reduce stays an eager NCCL call between two graphs;
         # capturing it inside the step graph dead-locked on 2 GPUs)
-        self.defer = use_graph and trainer.world_size == 1 and not os.environ.get("NCN_NO_DEFER")      # env: developer A/B only
+        # ... unless the optimizer is the sharded peer-memory one (trainer.peer): its two kernels carry the exchange themselves
+        self.peer = trainer.peer
+        self.nccl = trainer.world_size > 1 and self.peer is None
+        self.defer = use_graph and not self.nccl and not os.environ.get("NCN_NO_DEFER")      # env: developer A/B only
         # multi-rank: the same overlap with three graphs on two streams and an EAGER all-reduce in between
         #   opt stream : [all-reduce(prev grads) -> graph(adam)]      main stream: graph(march) -> join -> graph(field)
-        self.defer_multi = use_graph and trainer.world_size > 1
+        self.defer_multi = use_graph and self.nccl
         self.opt_stream = torch.cuda.Stream(device=dev)
         self.ev_fork2, self.ev_join2 = torch.cuda.Event(), torch.cuda.Event()
         self.coef = torch.ones(1, **f32)
@@ -219,10 +222,15 @@ class FusedStep:
             ck(L.ncn_field_prepare_rgb(ptr(self.dirs), ptr(self.h), cap, n_dev, ptr(self.x_rgb), ptr(self.sigmas), st), "prepare_rgb")
             ck(L.ncn_mlp_fwd(C.byref(rgbn.desc), ptr(self.x_rgb), ptr(self._w16("rgb_net")), cap, ptr(self.rgb_out), ptr(self.rgb_acts), n_dev, st), "rgb_fwd")
             ck(L.ncn_field_head_out(ptr(self.rgb_out), 16, cap, n_dev, ptr(self.raws), Ct, 0, 3, st), "head_out")
-        if m.pred_norm:                 # raws[:, 3:6] = norm_net(h)   (ngp_mt.py:221-224, rendering.py:203-206)
+        if (m.pred_norm or m.pred_sem) and self.fuse_fwd:      # both extra heads in ONE launch, outputs written into their raws columns
+            ck(L.ncn_field_heads_fwd(ptr(self.h), cap, n_dev, ptr(self.raws), Ct,
+                                     ptr(self._w16("norm_net")) if m.pred_norm else None, self.norm_off, 3, None, None,
+                                     ptr(self._w16("sem_net")) if m.pred_sem else None, self.sem_off, max(self.n_cls, 1),
+                                     ptr(self.sem_acts) if m.pred_sem else None, ptr(self.sem_out) if m.pred_sem else None, st), "heads_fwd")
+        elif m.pred_norm:               # raws[:, 3:6] = norm_net(h)   (ngp_mt.py:221-224, rendering.py:203-206)
             ck(L.ncn_mlp_fwd(C.byref(m.norm_net.desc), ptr(self.h), ptr(self._w16("norm_net")), cap, ptr(self.norm_out), None, n_dev, st), "norm_fwd")
             ck(L.ncn_field_head_out(ptr(self.norm_out), 16, cap, n_dev, ptr(self.raws), Ct, self.norm_off, 3, st), "norm_head_out")
-        if m.pred_sem:                  # raws[:, sem_off:] = sem_net(h)  (ngp_mt.py:217-220, rendering.py:207-208)
+        if m.pred_sem and not self.fuse_fwd:   # raws[:, sem_off:] = sem_net(h)  (ngp_mt.py:217-220, rendering.py:207-208)
             ck(L.ncn_mlp_fwd(C.byref(m.sem_net.desc), ptr(self.h), ptr(self._w16("sem_net")), cap, ptr(self.sem_out), ptr(self.sem_acts), n_dev, st), "sem_fwd")
             ck(L.ncn_field_head_out(ptr(self.sem_out), 16, cap, n_dev, ptr(self.raws), Ct, self.sem_off, self.n_cls, st), "sem_head_out")
         ck(L.ncn_composite_train_fw(ptr(self.sigmas), ptr(self.raws), ptr(self.deltas), ptr(self.ts), ptr(self.rays_a), 1e-4, R, cap, Ct,
@@ -290,6 +298,10 @@ class FusedStep:
         sumsq = self.zeros[2:3]
         sumsq.zero_()
         self.flag.copy_(self.flag_init)          # 0, or 1 to skip the (empty) update of the very first deferred step
+        if self.peer is not None:                # gradient exchange + norm + clip + Adam + fp16 refresh over NVLink peer memory
+            self.peer.step(opt.flat, opt.m, opt.v, self.adam_groups, opt.betas, opt.eps, self.grad_div, self.flag,
+                           self.dev_sched[sched_off:sched_off + 3], sumsq, st)
+            return
         check(L.ncn_grad_sumsq(ptr(opt.grad), opt.grad.numel(), ptr(self.grad_div), ptr(sumsq), ptr(self.flag), st), "sumsq")
         # both parameter groups (hash table wd 0 / MLPs wd 1e-6) and the clip coefficient in ONE launch
         check(L.ncn_adam_step_groups(ptr(opt.flat), ptr(opt.grad), ptr(opt.m), ptr(opt.v), ptr(self.flat16), opt.flat.numel(),
@@ -368,7 +380,7 @@ class FusedStep:
                 mod._half.copy_(mod.params.detach())
                 mod._flat_version = mod.params._version
         self._schedule()
-        multi = tr.world_size > 1
+        multi = self.nccl
         if not self.use_graph:
             self._run()
             if multi:
@@ -429,7 +441,7 @@ class FusedStep:
     def flush(self):
         """deferred mode: apply the pending optimizer pass of the last step (call before reading parameters / evaluating)"""
         if (self.defer or self.defer_multi) and self.pending:
-            if self.tr.world_size > 1:
+            if self.nccl:
                 self.tr.comm.allreduce_sum_(self.opt.grad)
             self._optimizer(sched_off=0)          # slot 0 still holds the last step's schedule
             self.pending = False

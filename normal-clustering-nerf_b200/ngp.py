@@ -112,14 +112,12 @@ class NGPMT(nn.Module):
         check(L.ncn_grid_fwd(C.byref(self.xyz_encoder.desc), ptr(x), ptr(_half_copy(self.xyz_encoder)), n, ptr(feat), xform, None, st), "grid_fwd")
         check(L.ncn_field_mlp_fwd(ptr(feat), ptr(d), ptr(_half_copy(self.sigma_net)), ptr(_half_copy(self.rgb_net)), n, None, ptr(sigmas),
                                   ptr(raws), Ct, ptr(h), None, None, None, None, st), "field_mlp_fwd")
-        off = 3
-        for on, name, k in ((self.pred_norm, "norm_net", 3), (self.pred_sem, "sem_net", n_cls)):
-            if on:
-                net = getattr(self, name)
-                out = torch.empty(n, 16, **f16)
-                check(L.ncn_mlp_fwd(C.byref(net.desc), ptr(h), ptr(_half_copy(net)), n, ptr(out), None, None, st), name + "_fwd")
-                check(L.ncn_field_head_out(ptr(out), 16, n, None, ptr(raws), Ct, off, k, st), name + "_head_out")
-                off += k
+        if self.pred_norm or self.pred_sem:      # both extra heads in one launch, straight into their raws columns
+            sem_off = 3 + (3 if self.pred_norm else 0)
+            check(L.ncn_field_heads_fwd(ptr(h), n, None, ptr(raws), Ct,
+                                        ptr(_half_copy(self.norm_net)) if self.pred_norm else None, 3, 3, None, None,
+                                        ptr(_half_copy(self.sem_net)) if self.pred_sem else None, sem_off, max(n_cls, 1), None, None, st),
+                  "field_heads_fwd")
         return sigmas, raws
 
     # ------------------------------------------------------------------ occupancy grid

@@ -71,10 +71,66 @@ class Communicator:
             self.handle = None
 
 
+class _DeviceMemory:
+    """__cuda_array_interface__ view of memory owned by libncn (torch.as_tensor wraps it without a copy)"""
+
+    def __init__(self, address, n, typestr, owner):
+        self.owner = owner
+        self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": typestr, "data": (int(address), False), "version": 2,
+                                         "strides": None}
+
+
+class PeerLink:
+    """Sharded data-parallel optimizer over NVLink peer memory (include/ncn.h ncn_peer_*): this rank's gradient and fp16
+    parameter buffers are allocated by libncn, exported with CUDA IPC and mapped by every other rank; ``step`` replaces
+    all-reduce + ||g||^2 + Adam with two kernels (no NCCL in the step, so it stays one CUDA graph).
+    torch.distributed only ships the 192-byte handle blocks at start-up."""
+
+    def __init__(self, rank, world_size, n_params, device):
+        L = _lib.lib()
+        self.rank, self.world_size, self.n = rank, world_size, int(n_params)
+        h = C.c_void_p()
+        check(L.ncn_peer_create(C.byref(h), rank, world_size, self.n), "peer_create")
+        self.handle = h
+        if world_size > 1:
+            import torch.distributed as dist
+            buf = (C.c_ubyte * 192)()
+            check(L.ncn_peer_handles(h, buf), "peer_handles")
+            mine = torch.tensor(list(bytes(buf)), dtype=torch.uint8)
+            if dist.get_backend() == "nccl":
+                mine = mine.to(device)
+            every = [torch.empty_like(mine) for _ in range(world_size)]
+            dist.all_gather(every, mine)
+            raw = b"".join(bytes(t.cpu().tolist()) for t in every)
+            check(L.ncn_peer_connect(h, raw), "peer_connect")
+            dist.barrier()
+        self.grad = torch.as_tensor(_DeviceMemory(L.ncn_peer_grad(h), self.n, "<f4", self), device=device)
+        self.p16 = torch.as_tensor(_DeviceMemory(L.ncn_peer_p16(h), self.n, "<f2", self), device=device)
+        lo, hi = C.c_int64(), C.c_int64()
+        L.ncn_peer_shard(self.n, rank, world_size, C.byref(lo), C.byref(hi))
+        self.shard = (lo.value, hi.value)
+
+    def step(self, flat, m, v, groups, betas, eps, grad_div, flag, lr_bc, sumsq_out, st):
+        check(_lib.lib().ncn_peer_step(self.handle, ptr(flat), ptr(m), ptr(v), C.byref(groups), betas[0], betas[1], eps, ptr(grad_div),
+                                       ptr(flag), ptr(lr_bc), ptr(sumsq_out), st), "peer_step")
+
+    def error(self):
+        e = C.c_uint32()
+        check(_lib.lib().ncn_peer_error(self.handle, C.byref(e)), "peer_error")
+        return e.value
+
+    def close(self):
+        if self.handle is not None:
+            self.grad = self.p16 = None
+            _lib.lib().ncn_peer_destroy(self.handle)
+            self.handle = None
+
+
 class FlatAdam:
     """Flat-buffer Adam over [(name, parameter, weight_decay)] groups (apex FusedAdam adam_w_mode semantics)."""
 
-    def __init__(self, named_params, lr, eps=1e-15, betas=(0.9, 0.999), loss_scale=1.0, grad_clip=0.05, world_size=1):
+    def __init__(self, named_params, lr, eps=1e-15, betas=(0.9, 0.999), loss_scale=1.0, grad_clip=0.05, world_size=1, rank=0,
+                 shard=False):
         named_params = [(n, p) for n, p in named_params if p.numel() > 0]
         dev = named_params[0][1].device
         enc = [(n, p) for n, p in named_params if "xyz_encoder" in n]          # train_nerf.py:264-274
@@ -82,7 +138,10 @@ class FlatAdam:
         self.groups = []
         total = sum((p.numel() + 3) // 4 * 4 for _, p in enc + net)
         self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
-        self.grad = torch.zeros(total, dtype=torch.float32, device=dev)
+        # shard=True: gradient + fp16 parameter buffers live in IPC-shared memory and the update runs sharded over NVLink peer
+        # memory (PeerLink); the fp32 master / m / v are then current only inside this rank's slice (self.peer.shard)
+        self.peer = PeerLink(rank, world_size, total, dev) if shard else None
+        self.grad = self.peer.grad if shard else torch.zeros(total, dtype=torch.float32, device=dev)
         self.m = torch.zeros(total, dtype=torch.float32, device=dev)
         self.v = torch.zeros(total, dtype=torch.float32, device=dev)
         off = 0
@@ -98,7 +157,11 @@ class FlatAdam:
                 self.groups.append((start, off - start, wd))
         # fp16 working copy of every parameter, refreshed by the Adam kernel itself (the tcnn binding re-casts the
         # whole 11.4 M-entry table on every forward call)
-        self.flat16 = self.flat.to(torch.float16)
+        if shard:
+            self.flat16 = self.peer.p16
+            self.flat16.copy_(self.flat)
+        else:
+            self.flat16 = self.flat.to(torch.float16)
         self.lr, self.eps, self.betas = lr, eps, betas
         self.loss_scale, self.grad_clip, self.world_size = loss_scale, grad_clip, world_size
         self.step_count = 0
@@ -124,6 +187,18 @@ class FlatAdam:
         st = stream()
         self.step_count += 1
         self.sumsq.zero_(); self.flag.zero_()
+        if self.peer is not None:
+            t = self.step_count
+            lr_bc = torch.tensor([float(lr if lr is not None else self.lr), 1 - self.betas[0] ** t, 1 - self.betas[1] ** t],
+                                 dtype=torch.float32, device=self.flat.device)
+            groups = _lib.AdamGroups()
+            groups.n_groups = len(self.groups)
+            for q, (start, _, wd) in enumerate(self.groups):
+                groups.start[q] = start
+                groups.weight_decay[q] = wd
+            groups.max_norm = float(self.grad_clip or 0.0)
+            self.peer.step(self.flat, self.m, self.v, groups, self.betas, self.eps, self.grad_div, self.flag, lr_bc, self.sumsq, st)
+            return
         check(L.ncn_grad_sumsq(ptr(self.grad), self.grad.numel(), ptr(self.grad_div), ptr(self.sumsq), ptr(self.flag), st), "grad_sumsq")
         coef = None
         if self.grad_clip and self.grad_clip > 0:
@@ -139,7 +214,9 @@ class FlatAdam:
 class NeRFTrainer:
     """One process = one GPU = one ray shard.  ``train_step(batch)`` is the unit bench.py times."""
 
-    def __init__(self, hparams=None, device="cuda", rank=0, world_size=1, seed=0, n_sem_cls=0, log2_T=19):
+    def __init__(self, hparams=None, device="cuda", rank=0, world_size=1, seed=0, n_sem_cls=0, log2_T=19, shard_optimizer=None):
+        """shard_optimizer: None = sharded peer-memory optimizer whenever world_size > 1 (falls back to the NCCL all-reduce +
+        replicated Adam when CUDA IPC / peer access is not available on every rank); True / False force it."""
         self.hp = hp = default_hparams(**(hparams or {}))
         self.device = torch.device(device)
         self.rank, self.world_size = rank, world_size
@@ -148,8 +225,12 @@ class NeRFTrainer:
                            pred_norm=hp["pred_norm_nn"], log2_T=log2_T, **kw).to(self.device)
         self.loss = NeRFMTLoss(hp)
         self.comm = Communicator(rank, world_size)
+        shard = world_size > 1 if shard_optimizer is None else bool(shard_optimizer)
+        if shard and world_size > 1:
+            shard = self._peer_access_everywhere()
         self.opt = FlatAdam(list(self.model.named_parameters()), lr=hp["lr"], loss_scale=hp["loss_scale"],
-                            grad_clip=hp["grad_clip"], world_size=world_size)
+                            grad_clip=hp["grad_clip"], world_size=world_size, rank=rank, shard=shard)
+        self.peer = self.opt.peer
         self.opt.adopt_half_copies(self.model)
         self.global_step = 0
         self.fused = None
@@ -158,6 +239,35 @@ class NeRFTrainer:
                                   pred_norm_nn_norm=False)
         self.poses = None
         self.directions = None
+
+    def _peer_access_everywhere(self):
+        """every rank can map every other rank's device (one GPU per rank on one NVSwitch box); agreed on by all ranks"""
+        import torch.distributed as dist
+        ok = 1
+        try:
+            me = self.device.index if self.device.index is not None else torch.cuda.current_device()
+            n_dev = torch.cuda.device_count()
+            ok = int(n_dev >= self.world_size and all(torch.cuda.can_device_access_peer(me, q) for q in range(self.world_size) if q != me))
+        except Exception:  # noqa: BLE001
+            ok = 0
+        t = torch.tensor([ok], dtype=torch.int32, device=self.device if dist.get_backend() == "nccl" else "cpu")
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        return bool(int(t.item()))
+
+    def gather_master_params(self):
+        """sharded optimizer: make the fp32 master copy complete on every rank (checkpointing / evaluation of fp32 state);
+        each rank owns opt.peer.shard, the rest is rebuilt from the owners"""
+        if self.peer is None or self.world_size == 1:
+            return
+        import torch.distributed as dist
+        if self.fused is not None:
+            self.fused.flush()
+        L = _lib.lib()
+        for q in range(self.world_size):
+            lo, hi = C.c_int64(), C.c_int64()
+            L.ncn_peer_shard(self.opt.flat.numel(), q, self.world_size, C.byref(lo), C.byref(hi))
+            for buf in (self.opt.flat, self.opt.m, self.opt.v):
+                dist.broadcast(buf[lo.value:hi.value], q)
 
     # dataset tensors that NeRFSystem keeps on the device (train_nerf.py:239-240)
     def set_cameras(self, poses, directions):
@@ -221,7 +331,8 @@ class NeRFTrainer:
             self.maybe_update_grid()
         results, loss_d = self.forward_loss(rays_o, rays_d, target)
         (loss_d["total"] * self.hp["loss_scale"]).backward()
-        self.comm.allreduce_sum_(self.opt.grad)
+        if self.peer is None:
+            self.comm.allreduce_sum_(self.opt.grad)
         self.opt.step(self.lr_now())
         self.global_step += 1
         return results, loss_d

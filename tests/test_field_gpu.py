@@ -209,3 +209,44 @@ def test_mlp_forward_backward(ncn, n_in, n_out, n_hidden, act, n):
     for got, want in ((gx, xr.grad), (gp, pr.grad)):
         assert (got - want).norm() <= 1e-2 * want.norm() + 1e-5
         assert (got - want).abs().max() <= 8e-2 * want.abs().max() + 1e-4
+
+
+@pytest.mark.parametrize("n,n_cls", [(1, 3), (1000, 3), (40000 + 7, 13)])
+def test_field_heads_fwd_equals_separate_launches(ncn, n, n_cls):
+    """ncn_field_heads_fwd (sem_net + norm_net on h in one launch, outputs straight into their raws columns) against
+    ncn_mlp_fwd + ncn_field_head_out per head: same MMA chain, so outputs, saved activations and raws are identical;
+    untouched raws columns stay untouched; a NULL head is skipped."""
+    import ctypes as C
+    from ncn_b200 import _lib
+    from ncn_b200 import tinycudann as tcnn
+    from ncn_b200._lib import check, ptr, stream
+    L = _lib.lib()
+    cfg = dict(otype="FullyFusedMLP", activation="ReLU", output_activation="None", n_neurons=64, n_hidden_layers=2)
+    sem, nrm = tcnn.Network(16, n_cls, cfg).cuda(), tcnn.Network(16, 3, cfg, seed=7).cuda()
+    g = torch.Generator(device="cuda").manual_seed(n)
+    ws = (torch.randn(sem.params.numel(), device="cuda", generator=g) * 0.2).half()
+    wn = (torch.randn(nrm.params.numel(), device="cuda", generator=g) * 0.2).half()
+    h = torch.randn(n, 16, device="cuda", generator=g).half()
+    Ct = 6 + n_cls
+    n_t = (n + 127) // 128 * 128
+    st = stream()
+    # reference: separate launches
+    raws_ref = torch.full((n, Ct), -7.0, device="cuda")
+    out_s, out_n = torch.empty(n, 16, dtype=torch.float16, device="cuda"), torch.empty(n, 16, dtype=torch.float16, device="cuda")
+    acts_s = torch.zeros(2, n_t, 64, dtype=torch.float16, device="cuda")
+    check(L.ncn_mlp_fwd(C.byref(sem.desc), ptr(h), ptr(ws), n, ptr(out_s), ptr(acts_s), None, st))
+    check(L.ncn_mlp_fwd(C.byref(nrm.desc), ptr(h), ptr(wn), n, ptr(out_n), None, None, st))
+    check(L.ncn_field_head_out(ptr(out_n), 16, n, None, ptr(raws_ref), Ct, 3, 3, st))
+    check(L.ncn_field_head_out(ptr(out_s), 16, n, None, ptr(raws_ref), Ct, 6, n_cls, st))
+    # one launch
+    raws = torch.full((n, Ct), -7.0, device="cuda")
+    out_s2 = torch.empty_like(out_s); acts_s2 = torch.zeros_like(acts_s)
+    check(L.ncn_field_heads_fwd(ptr(h), n, None, ptr(raws), Ct, ptr(wn), 3, 3, None, None, ptr(ws), 6, n_cls, ptr(acts_s2), ptr(out_s2), st))
+    assert torch.equal(raws, raws_ref)
+    assert torch.equal(out_s2, out_s) and torch.equal(acts_s2, acts_s)
+    assert bool((raws[:, :3] == -7.0).all())
+    # device-side row count + absent head
+    n_dev = torch.tensor([n // 2], dtype=torch.int32, device="cuda")
+    raws3 = torch.full((n, Ct), -7.0, device="cuda")
+    check(L.ncn_field_heads_fwd(ptr(h), n, ptr(n_dev), ptr(raws3), Ct, None, 0, 0, None, None, ptr(ws), 6, n_cls, None, None, st))
+    assert torch.equal(raws3[:n // 2, 6:], raws_ref[:n // 2, 6:]) and bool((raws3[n // 2:] == -7.0).all()) and bool((raws3[:, :6] == -7.0).all())

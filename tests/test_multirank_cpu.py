@@ -89,3 +89,22 @@ def test_two_rank_data_parallel_gradient(tmp_path):
     r = torch.load(out)
     assert r["id_ok"]
     torch.testing.assert_close(r["dp"], r["single"], rtol=1e-5, atol=1e-7)
+
+
+def test_peer_shards_partition_the_parameter_vector():
+    """ncn_peer_shard (host arithmetic of the sharded peer-memory optimizer): the W slices tile [0, n) exactly, in rank order,
+    on float4 boundaries, balanced to within one float4"""
+    import ctypes as C
+    import ncn_b200  # noqa: F401
+    from ncn_b200 import _lib
+    L = _lib.lib()
+    for n in (4, 64, 11468464, 70224656):
+        for world in (1, 2, 3, 4, 8):
+            prev, sizes = 0, []
+            for r in range(world):
+                lo, hi = C.c_int64(), C.c_int64()
+                L.ncn_peer_shard(n, r, world, C.byref(lo), C.byref(hi))
+                assert lo.value == prev and hi.value >= lo.value and lo.value % 4 == 0 and hi.value % 4 == 0
+                prev = hi.value
+                sizes.append(hi.value - lo.value)
+            assert prev == n and max(sizes) - min(sizes) <= 4

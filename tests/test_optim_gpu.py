@@ -125,3 +125,75 @@ def test_sumsq_is_deterministic(ncn):
     assert all(torch.equal(outs[0], o) for o in outs[1:])
     want = float((grad.double() ** 2).sum())
     assert abs(float(outs[0]) - want) <= 1e-5 * want
+
+
+def test_peer_step_single_rank_equals_sumsq_plus_adam(ncn):
+    """ncn_peer_step at world_size 1 (no peers: the shard is the whole vector) against ncn_grad_sumsq + ncn_adam_step_groups:
+    same parameters / moments / fp16 copy (the norm is summed in a different block order -> the clip coefficient may differ
+    in the last ulp), gradient buffer zeroed, non-finite gradient skips the update, epoch advances once per step."""
+    import ctypes as C
+    from ncn_b200 import _lib
+    from ncn_b200._lib import check, ptr, stream
+    from ncn_b200.trainer import PeerLink
+    L = _lib.lib()
+    n = 1 << 20
+    dev = torch.device("cuda", torch.cuda.current_device())
+    g = torch.Generator(device="cuda").manual_seed(0)
+    link = PeerLink(0, 1, n, dev)
+    assert link.shard == (0, n) and link.grad.numel() == n and link.p16.dtype == torch.float16
+    p0 = torch.randn(n, device="cuda", generator=g) * 0.1
+    groups = _lib.AdamGroups(); groups.n_groups = 2; groups.start[0] = 0; groups.start[1] = n - 4096
+    groups.weight_decay[0] = 0.0; groups.weight_decay[1] = 1e-6; groups.max_norm = 0.05
+    div = torch.tensor([2.0], device="cuda")
+    state = {k: [p0.clone(), torch.zeros(n, device="cuda"), torch.zeros(n, device="cuda")] for k in ("peer", "ref")}
+    p16_ref = torch.zeros(n, dtype=torch.float16, device="cuda")
+    flag = torch.zeros(1, dtype=torch.int32, device="cuda")
+    for step in range(1, 4):
+        grad = torch.randn(n, device="cuda", generator=g) * (10.0 ** -step)
+        lr_bc = torch.tensor([1e-2, 1 - 0.9 ** step, 1 - 0.999 ** step], device="cuda")
+        link.grad.copy_(grad)
+        sumsq_p = torch.zeros(1, device="cuda")
+        p, m, v = state["peer"]
+        link.step(p, m, v, groups, (0.9, 0.999), 1e-15, div, flag, lr_bc, sumsq_p, stream())
+        gr = grad.clone(); sumsq = torch.zeros(1, device="cuda")
+        p, m, v = state["ref"]
+        check(L.ncn_grad_sumsq(ptr(gr), n, ptr(div), ptr(sumsq), ptr(flag), stream()))
+        check(L.ncn_adam_step_groups(ptr(p), ptr(gr), ptr(m), ptr(v), ptr(p16_ref), n, C.byref(groups), 0.9, 0.999, 1e-15, ptr(div), ptr(flag),
+                                     ptr(sumsq), ptr(lr_bc), stream()))
+        torch.testing.assert_close(sumsq_p, sumsq, rtol=1e-5, atol=0)
+        for a, b in zip(state["peer"], state["ref"]):
+            torch.testing.assert_close(a, b, rtol=2e-5, atol=1e-9)
+        torch.testing.assert_close(link.p16.float(), p16_ref.float(), rtol=2e-3, atol=1e-7)
+        assert float(link.grad.abs().max()) == 0.0
+    assert link.error() == 0
+    before = state["peer"][0].clone()
+    link.grad.copy_(torch.full((n,), float("nan"), device="cuda"))
+    link.step(*state["peer"], groups, (0.9, 0.999), 1e-15, div, flag, lr_bc, sumsq_p, stream())
+    torch.cuda.synchronize()
+    assert torch.equal(state["peer"][0], before) and float(link.grad.abs().max()) == 0.0 and not torch.isfinite(sumsq_p).all()
+    link.close()
+
+
+def test_fused_step_with_sharded_optimizer_single_rank():
+    """the fused CUDA-graph step driven by the peer-memory optimizer (world_size 1) trains like the replicated one"""
+    from tests.test_fused_gpu import _setup
+    from ncn_b200.trainer import NeRFTrainer
+    tr, rays_o, rays_d, tri, rgb, target = _setup(R=1024, seed=1)
+    torch.manual_seed(1)
+    tr2 = NeRFTrainer(dict(batch_size=1024), device="cuda", shard_optimizer=True)
+    assert tr2.peer is not None and tr2.opt.grad.data_ptr() == tr2.peer.grad.data_ptr()
+    tr2.model.density_grid.copy_(tr.model.density_grid); tr2.model.density_bitfield.copy_(tr.model.density_bitfield)
+    tr2.opt.flat.copy_(tr.opt.flat); tr2.opt.flat16.copy_(tr.opt.flat16); tr2.global_step = tr.global_step
+    noise = torch.rand(1024, device="cuda")
+    fs = tr.fused_step(use_graph=True); fs.set_triangles(tri)
+    fs2 = tr2.fused_step(use_graph=True); fs2.set_triangles(tri)
+    assert fs2.defer and not fs2.nccl
+    for i in range(4):
+        fs.step(rays_o, rays_d, rgb, noise=noise)
+        fs2.step(rays_o, rays_d, rgb, noise=noise)
+    fs.flush(); fs2.flush()
+    torch.cuda.synchronize()
+    assert tr2.peer.error() == 0
+    rel = float((tr.opt.flat - tr2.opt.flat).norm() / tr.opt.flat.norm())
+    assert rel < 1e-4, rel
+    torch.testing.assert_close(tr2.opt.flat16.float(), tr.opt.flat16.float(), rtol=5e-3, atol=1e-6)
