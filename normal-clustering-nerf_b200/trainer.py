@@ -89,21 +89,37 @@ class PeerLink:
     def __init__(self, rank, world_size, n_params, device):
         L = _lib.lib()
         self.rank, self.world_size, self.n = rank, world_size, int(n_params)
+        self.handle = None
         h = C.c_void_p()
-        check(L.ncn_peer_create(C.byref(h), rank, world_size, self.n), "peer_create")
-        self.handle = h
-        if world_size > 1:
+        if world_size == 1:
+            check(L.ncn_peer_create(C.byref(h), rank, world_size, self.n), "peer_create")
+            self.handle = h
+        else:
+            # every phase ends with an agreement (MIN all-reduce) so that a failure on one rank raises on ALL ranks instead of
+            # leaving the others inside a collective - the caller then falls back to the NCCL exchange everywhere
             import torch.distributed as dist
+            on_dev = dist.get_backend() == "nccl"
+
+            def agree(ok, what):
+                t = torch.tensor([1 if ok else 0], dtype=torch.int32, device=device if on_dev else "cpu")
+                dist.all_reduce(t, op=dist.ReduceOp.MIN)
+                if int(t.item()) == 0:
+                    self.close()
+                    raise RuntimeError(f"PeerLink: {what} failed on at least one rank")
+
             buf = (C.c_ubyte * 192)()
-            check(L.ncn_peer_handles(h, buf), "peer_handles")
+            ok = L.ncn_peer_create(C.byref(h), rank, world_size, self.n) == 0
+            if ok:
+                self.handle = h
+                ok = L.ncn_peer_handles(h, buf) == 0
+            agree(ok, "buffer allocation / cudaIpcGetMemHandle")
             mine = torch.tensor(list(bytes(buf)), dtype=torch.uint8)
-            if dist.get_backend() == "nccl":
+            if on_dev:
                 mine = mine.to(device)
             every = [torch.empty_like(mine) for _ in range(world_size)]
             dist.all_gather(every, mine)
             raw = b"".join(bytes(t.cpu().tolist()) for t in every)
-            check(L.ncn_peer_connect(h, raw), "peer_connect")
-            dist.barrier()
+            agree(L.ncn_peer_connect(h, raw) == 0, "cudaIpcOpenMemHandle")
         self.grad = torch.as_tensor(_DeviceMemory(L.ncn_peer_grad(h), self.n, "<f4", self), device=device)
         self.p16 = torch.as_tensor(_DeviceMemory(L.ncn_peer_p16(h), self.n, "<f2", self), device=device)
         lo, hi = C.c_int64(), C.c_int64()
@@ -228,8 +244,16 @@ class NeRFTrainer:
         shard = world_size > 1 if shard_optimizer is None else bool(shard_optimizer)
         if shard and world_size > 1:
             shard = self._peer_access_everywhere()
-        self.opt = FlatAdam(list(self.model.named_parameters()), lr=hp["lr"], loss_scale=hp["loss_scale"],
-                            grad_clip=hp["grad_clip"], world_size=world_size, rank=rank, shard=shard)
+        mk = lambda sh: FlatAdam(list(self.model.named_parameters()), lr=hp["lr"], loss_scale=hp["loss_scale"],
+                                 grad_clip=hp["grad_clip"], world_size=world_size, rank=rank, shard=sh)
+        try:
+            self.opt = mk(shard)
+        except RuntimeError as e:
+            if not (shard and shard_optimizer is None and "PeerLink" in str(e)):
+                raise
+            import sys
+            print(f"[ncn_b200] rank {rank}: {e}; using the NCCL all-reduce exchange", file=sys.stderr)
+            self.opt = mk(False)
         self.peer = self.opt.peer
         self.opt.adopt_half_copies(self.model)
         self.global_step = 0

@@ -176,7 +176,7 @@ def test_peer_step_single_rank_equals_sumsq_plus_adam(ncn):
 
 def test_fused_step_with_sharded_optimizer_single_rank():
     """the fused CUDA-graph step driven by the peer-memory optimizer (world_size 1) trains like the replicated one"""
-    from tests.test_fused_gpu import _setup
+    from test_fused_gpu import _setup
     from ncn_b200.trainer import NeRFTrainer
     tr, rays_o, rays_d, tri, rgb, target = _setup(R=1024, seed=1)
     torch.manual_seed(1)
