@@ -214,7 +214,6 @@ def run_ours(args):
     def step_resident(i):
         tr.train_step_fused(packed=resident[i % NB], grid_restore=restore)
 
-    d_img = torch.empty(R, dtype=torch.int64, device=dev); d_pix = torch.empty(R, dtype=torch.int64, device=dev)
 
     # End to end: every step copies its batch from pinned host memory, runs, and copies its loss sums back to pinned host
     # memory; the host READS the loss of step i-1 while step i is already enqueued (double-buffered slots + events), the
@@ -229,11 +228,13 @@ def run_ours(args):
             e2e_losses.append(float(loss_slots[slot][0]) / (3 * R))
             loss_events[slot] = None
 
+    for h in host:      # the batch as ONE pinned record [img_idx i64 | pix_idx i64 | rgb f32] = a single H2D copy per step
+        h["packed"] = fs.pack_pixel_batch(h["img"], h["pix"], h["rgb"])
+    assert host[0]["packed"].numel() == h2d_bytes
+
     def step_e2e(i):
         h = host[i % NB]
-        d_img.copy_(h["img"], non_blocking=True); d_pix.copy_(h["pix"], non_blocking=True)     # H2D of the batch ...
-        fs.target.copy_(h["rgb"], non_blocking=True)
-        fs.rays_from_pixels(d_img, d_pix)
+        fs.batch.copy_(h["packed"], non_blocking=True)            # H2D of the batch; rays are generated inside the step graph
         tr.train_step_fused(grid_restore=restore)
         slot = i & 1
         loss_slots[slot].copy_(fs.zeros, non_blocking=True)      # D2H of this step's loss sums (32 B)
@@ -271,6 +272,7 @@ def run_ours(args):
     value = world * R * args.steps / (ms * 1e-3)
 
     # ---- timed region 2: end to end from pinned host buffers, loss read back every step
+    fs.use_pixel_batches(True)
     for i in range(2):
         step_e2e(i)
 
@@ -295,6 +297,7 @@ def run_ours(args):
     assert len(e2e_losses) >= args.steps and all(np.isfinite(e2e_losses))
     e2e = world * R * args.steps / (ms_e2e * 1e-3)
     _, n_samples = fs.stats_host()
+    fs.use_pixel_batches(False)
 
     # ---- instrumented pass: the SAME step, same buffers, eager (no graph) with CUDA events around every libncn call
     #      -> launch count and the dominant kernel's average launch time (events cannot be read inside a replayed graph)

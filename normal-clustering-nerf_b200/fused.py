@@ -53,6 +53,7 @@ class FusedStep:
         # static inputs: ONE (3,R,3) buffer [rays_o | rays_d | target rgb] so a step needs a single input copy
         self.inp = E(3, R, 3, **f32)
         self.rays_o, self.rays_d, self.target = self.inp[0], self.inp[1], self.inp[2]
+        self.pix_inputs = False              # use_pixel_batches(): rays are generated inside the step from (image, pixel) indices
         self.noise = E(R, **f32)
         self.gen_noise = True                # march jitter drawn inside the step (torch.rand_like of custom_functions.py:83)
         self.tri = None                      # (3, M) int64
@@ -190,6 +191,10 @@ class FusedStep:
         if self.n_cls:
             self.zeros[4:6].zero_()
         self.d_depth.zero_()
+        if self.pix_inputs:                  # NeRFSystem.forward gather + get_rays (train_nerf.py:167-182) as the step's first node
+            tr = self.tr
+            ck(L.ncn_rays_from_pixels(ptr(tr.poses), ptr(tr.directions), ptr(self.b_img), ptr(self.b_pix), R, ptr(self.rays_o),
+                                      ptr(self.rays_d), st), "rays_from_pixels")
         if self.gen_noise:
             self.noise.uniform_()
         ck(L.ncn_ray_aabb_near(ptr(self.rays_o), ptr(self.rays_d), ptr(m.center), ptr(m.half_size), float(hp["rend_near_dist"]), R,
@@ -445,6 +450,40 @@ class FusedStep:
                 self.tr.comm.allreduce_sum_(self.opt.grad)
             self._optimizer(sched_off=0)          # slot 0 still holds the last step's schedule
             self.pending = False
+
+    def use_pixel_batches(self, on=True):
+        """End-to-end input form (what a DataLoader hands over, base.py:94-173): ONE record of 28 bytes per ray
+        [img_idx i64 (R) | pix_idx i64 (R) | target rgb f32 (R,3)] = a single host->device copy per step into ``self.batch``;
+        ray generation runs inside the step graph.  ``step_pixels(record)`` copies and steps.  Needs trainer.set_cameras()."""
+        R = self.R
+        if on:
+            if self.tr.poses is None or self.tr.directions is None:
+                raise RuntimeError("use_pixel_batches: call trainer.set_cameras(poses, directions) first")
+            if getattr(self, "batch", None) is None:
+                self.batch = torch.zeros(R * 28, dtype=torch.uint8, device=self.dev)
+                self.b_img = self.batch[:8 * R].view(torch.int64)
+                self.b_pix = self.batch[8 * R:16 * R].view(torch.int64)
+            self.target = self.batch[16 * R:].view(torch.float32).view(R, 3)
+        else:
+            self.target = self.inp[2]
+        if on != self.pix_inputs:
+            self.pix_inputs = on
+            self.graph = None                 # the captured sequence and the target pointer change
+
+    @staticmethod
+    def pack_pixel_batch(img_idx, pix_idx, rgb, pin=True):
+        """host-side record for step_pixels: uint8 (R*28) = [img_idx i64 | pix_idx i64 | rgb f32]"""
+        rec = torch.cat([img_idx.to(torch.int64).contiguous().view(torch.uint8).reshape(-1),
+                         pix_idx.to(torch.int64).contiguous().view(torch.uint8).reshape(-1),
+                         rgb.to(torch.float32).contiguous().view(torch.uint8).reshape(-1)])
+        return rec.pin_memory() if pin and not rec.is_cuda else rec
+
+    def step_pixels(self, record, **kw):
+        """one training step from a packed pixel batch (host pinned or device): one copy + one graph replay"""
+        if not self.pix_inputs:
+            self.use_pixel_batches(True)
+        self.batch.copy_(record, non_blocking=True)
+        self.step(**kw)
 
     def rays_from_pixels(self, img_idx, pix_idx):
         """fill the static rays_o / rays_d buffers from (image, pixel) indices (one kernel)"""

@@ -188,6 +188,37 @@ def test_rays_from_pixels_matches_get_rays():
     assert torch.equal(fs.rays_o, c2w[..., 3])
 
 
+def test_pixel_batch_step_equals_ray_step():
+    """step_pixels (ONE packed [img | pix | rgb] record copied per step, ray generation as the first node of the step graph)
+    against rays_from_pixels + step on a second trainer: identical rays, targets and sample counts, same losses; also from a
+    pinned HOST record, and switching the mode off restores the (3,R,3) input buffer."""
+    from ncn_b200 import synth
+    R = 1024
+    tr, _, _, tri, rgb, _ = _setup(R=R, seed=2)
+    tr2, *_ = _setup(R=R, seed=2)
+    poses = torch.from_numpy(synth.camera_poses(50, 0)).cuda(); dirs = torch.from_numpy(synth.pixel_directions("hypersim")).cuda()
+    b = synth.patch_batch(R, seed=5)
+    img = torch.from_numpy(b["img_idx"]).cuda(); pix = torch.from_numpy(b["pix_idx"]).cuda()
+    noise = torch.rand(R, device="cuda")
+    for t in (tr, tr2):
+        t.set_cameras(poses, dirs)
+    fs = tr.fused_step(use_graph=True); fs.set_triangles(tri)
+    fs2 = tr2.fused_step(use_graph=True); fs2.set_triangles(tri)
+    rec = fs.pack_pixel_batch(img.cpu(), pix.cpu(), rgb.cpu())
+    assert rec.is_pinned() and rec.numel() == R * 28
+    fs.step_pixels(rec, noise=noise)
+    fs2.rays_from_pixels(img, pix); fs2.target.copy_(rgb)
+    fs2.step(noise=noise)
+    torch.cuda.synchronize()
+    assert torch.equal(fs.rays_o, fs2.rays_o) and torch.equal(fs.rays_d, fs2.rays_d) and torch.equal(fs.target, fs2.target)
+    assert torch.equal(fs.rays_a, fs2.rays_a) and int(fs.counter[0]) == int(fs2.counter[0]) > R
+    d1, _ = fs.stats_host(); d2, _ = fs2.stats_host()
+    for k in d2:
+        assert abs(d1[k] - d2[k]) <= 1e-4 * abs(d2[k]) + 1e-9, (k, d1[k], d2[k])
+    fs.use_pixel_batches(False)
+    assert fs.target.data_ptr() == fs.inp[2].data_ptr() and fs.graph is None
+
+
 def test_grid_update_sampling_kernels():
     """ncn_grid_sample_cells / ncn_grid_scatter_density (models/ngp_mt.py:254-271, 345-357): index ranges, the second half
     hits occupied cells only and uniformly, every point lies inside its cell, the seed advances, the scatter writes exp(h0)."""
