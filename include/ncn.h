@@ -408,6 +408,25 @@ int ncn_normals_from_depth_bw(const float* origin, const float* dir, const float
                               const float* dL_dnormals, int64_t n_tri, float* dL_ddepth,
                               ncn_stream_t stream);
 
+/* Training-batch sampling on the device: the index half of BaseDataset.__getitem__ (datasets/base.py:94-173, max_expand = 0)
+ * and the target gather (:175-183).  strategy 0 = all_images_triang_patch, 1 = same_image_triang_patch (patch_size^2 rays per
+ * patch: pix = corner_INDEX + dy*W + dx - the reference adds the offsets to the index into valid_idx['patch_corners'],
+ * base.py:164-166, reproduced), 2 = all_images_triang, 3 = same_image_triang (3 rays per triangle: x1, x1 - W, x1 - 1).
+ * seed_dev: device int64 read for this batch and advanced by one (graph replays draw fresh batches).  Rays beyond the last
+ * whole patch / triangle get (0, 0).  The numpy MT19937 stream is not reproduced; index arithmetic and distributions are.
+ * gather_pixels: out[r, :] = table[img_idx[r], pix_idx[r], :] with rows of words_per_pixel 4-byte words (rgb f32 x3, labels ...). */
+int ncn_sample_ray_batch(int strategy, int64_t* seed_dev, int n_rays, int n_poses, int height, int width, int patch_size,
+                         int64_t* img_idx, int64_t* pix_idx, ncn_stream_t stream);
+int ncn_gather_pixels(const void* table, const int64_t* img_idx, const int64_t* pix_idx, int64_t n, int64_t pixels_per_image,
+                      int words_per_pixel, void* out, ncn_stream_t stream);
+
+/* Normals of rendered depth IMAGES for the evaluation loop (datasets/hypersim_src/utils.py:544-611,
+ * _extract_normals_from_depth_batch): depth (B,H,W) f32, ray_dirs_cc (H*W,3) f32 camera-frame directions, poses
+ * (B, pose_rows = 3 or 4, 4) f32 row-major camera-to-world -> normals (B,H,W,3) f32 in the world frame;
+ * (0,0,0) on the one-pixel border and where the pixel's own depth is 0 / NaN / Inf. */
+int ncn_normals_from_depth_image(const float* depth, const float* ray_dirs_cc, const float* poses, int pose_rows,
+                                 int n_images, int height, int width, float* normals, ncn_stream_t stream);
+
 typedef struct ncn_kmeans_params {
   int32_t k;                      /* 20  (losses.py:436) */
   int32_t niter;                  /* 20  (losses.py:437) */

@@ -5,6 +5,8 @@
   cluster_select       losses.py:97-166 (orthogonal triple, merge, opposite) - on the GPU, no .item()
   cluster_loss         losses.py:441-478 (L_ort, L_dot, L_L1) with its analytic gradient
   normals_clustering   drop-in for losses._normals_clustering(normals, ...) on device tensors
+  normals_from_depth_image   datasets/hypersim_src/utils.py:544-611 (_extract_normals_from_depth_batch), evaluation loop
+  rotation_from_normals      train_nerf.py:491-517: scene rotation recovered from the clustered normals of the rendered views
 """
 import ctypes as C
 
@@ -102,3 +104,41 @@ def normals_clustering(normals, K=10, niter=10, t_similar=0.99, seed=1234):
     cent, assign, _ = kmeans_spherical(normals, K, niter, seed=seed)
     labels, sel = cluster_select(cent, assign, t_similar)
     return labels, assign, cent[sel.long()]
+
+
+@torch.no_grad()
+def normals_from_depth_image(depth, ray_dirs_cc, poses):
+    """_extract_normals_from_depth_batch: depth (B,H,W), ray_dirs_cc (H*W,3), poses (B,3|4,4) -> world-frame normals (B,H,W,3);
+    zero on the border and where the pixel's depth is 0 / NaN / Inf."""
+    depth = depth.float().contiguous(); ray_dirs_cc = ray_dirs_cc.float().contiguous(); poses = poses.float().contiguous()
+    B, H, W = depth.shape
+    if ray_dirs_cc.shape != (H * W, 3) or poses.shape[0] != B or poses.shape[1] not in (3, 4) or poses.shape[2] != 4:
+        raise RuntimeError("normals_from_depth_image: expected depth (B,H,W), ray_dirs_cc (H*W,3), poses (B,3|4,4)")
+    out = torch.empty(B, H, W, 3, dtype=torch.float32, device=depth.device)
+    check(_lib.lib().ncn_normals_from_depth_image(ptr(depth), ptr(ray_dirs_cc), ptr(poses), poses.shape[1], B, H, W, ptr(out), stream()),
+          "normals_from_depth_image")
+    return out
+
+
+def rotation_from_centroids(centrs_new, R_offset):
+    """train_nerf.py:505-517 downstream of the clustering: the three selected centroids (rows) and their negatives are matched
+    to the columns of R_offset by largest dot product, and the result is projected onto SO(3) (scipy Rotation.from_matrix,
+    as the reference).  3x3 host arithmetic; returns a float64 (3,3) tensor."""
+    from scipy.spatial.transform import Rotation
+    c = centrs_new.detach().cpu().double().T                           # columns = cluster directions
+    both = torch.cat([c, -c], 1)                                        # (3,6)
+    sim = (R_offset.detach().cpu().double().unsqueeze(1) * both.unsqueeze(-1)).sum(0)      # (6,3)
+    rot = both[:, torch.argmax(sim, 0)]
+    return torch.from_numpy(Rotation.from_matrix(rot.numpy()).as_matrix())
+
+
+@torch.no_grad()
+def rotation_from_normals(normals, R_offset, K=30, niter=30, t_similar=0.99, seed=1234):
+    """validation_epoch_end (train_nerf.py:491-517): cluster all rendered-view normals (invalid rows skipped on the device),
+    take the most orthogonal triple and read the scene rotation off it.  normals: (...,3) CUDA tensor."""
+    n = normals.reshape(-1, 3).float()
+    # the reference drops rows whose components SUM to zero (train_nerf.py:496) - a superset of the all-zero invalid code;
+    # zeroing them lets the device-side validity filter of the k-means skip exactly those rows
+    n = torch.where((n.sum(-1) != 0.0).unsqueeze(-1), n, torch.zeros_like(n))
+    _, _, centrs = normals_clustering(n, K=K, niter=niter, t_similar=t_similar, seed=seed)
+    return rotation_from_centroids(centrs, R_offset)

@@ -874,6 +874,40 @@ photometric_kernel(const float* __restrict__ rend, const float* __restrict__ opa
   }
 }
 
+// ---------------------------------------------------------------- normals of a rendered depth IMAGE (evaluation)
+// datasets/hypersim_src/utils.py:544-611 (_extract_normals_from_depth_batch): P = ray_dir_cc * depth (camera frame),
+// n(y,x) = normalize(cross(P(y-1,x) - P(y,x), P(y,x-1) - P(y,x))) (eps 1e-12), rotated to the world frame by the pose's 3x3
+// block; the one-pixel border and pixels whose own depth is 0 / NaN / Inf get (0,0,0).  One thread per pixel; the three
+// points of a pixel are recomputed from depth + directions (28 B/pixel of reads that neighbours share through L1/L2, 12 B written).
+__global__ void __launch_bounds__(256)
+normals_image_kernel(const float* __restrict__ depth, const float* __restrict__ dirs, const float* __restrict__ poses,
+                     int pose_stride, int B, int H, int W, float* __restrict__ out) {
+  const int64_t hw = (int64_t)H * W;
+  const int64_t total = (int64_t)B * hw;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int b = (int)(i / hw);
+    const int64_t p = i - (int64_t)b * hw;
+    const int y = (int)(p / W), x = (int)(p - (int64_t)y * W);
+    float n0 = 0.f, n1 = 0.f, n2 = 0.f;
+    const float d1 = depth[i];
+    if (y >= 1 && y < H - 1 && x >= 1 && x < W - 1 && d1 != 0.f && isfinite(d1)) {
+      const float d2 = depth[i - W], d3 = depth[i - 1];
+      const float* r1 = dirs + 3 * p; const float* r2 = dirs + 3 * (p - W); const float* r3 = dirs + 3 * (p - 1);
+      const float p1x = r1[0] * d1, p1y = r1[1] * d1, p1z = r1[2] * d1;
+      const float ax = r2[0] * d2 - p1x, ay = r2[1] * d2 - p1y, az = r2[2] * d2 - p1z;
+      const float bx = r3[0] * d3 - p1x, by = r3[1] * d3 - p1y, bz = r3[2] * d3 - p1z;
+      float cx = ay * bz - az * by, cy = az * bx - ax * bz, cz = ax * by - ay * bx;
+      const float inv = 1.f / fmaxf(sqrtf(cx * cx + cy * cy + cz * cz), 1e-12f);
+      cx *= inv; cy *= inv; cz *= inv;
+      const float* R = poses + (int64_t)b * pose_stride;       // row-major (3|4, 4): R[r][c] = R[4 r + c]
+      n0 = R[0] * cx + R[1] * cy + R[2] * cz;
+      n1 = R[4] * cx + R[5] * cy + R[6] * cz;
+      n2 = R[8] * cx + R[9] * cy + R[10] * cz;
+    }
+    out[3 * i] = n0; out[3 * i + 1] = n1; out[3 * i + 2] = n2;
+  }
+}
+
 // ---------------------------------------------------------------- semantic cross-entropy (fused fwd + grad)
 // losses.py:226-242, 569-573: CrossEntropyLoss(ignore_index=-1)(sem_pred, target - 1), mean over non-void rays.
 // Thread per ray; every CTA counts the valid rays itself (R labels from L2) so the mean's divisor needs no second launch.
@@ -1087,6 +1121,18 @@ extern "C" int ncn_semantic_ce_loss(const float* rend, int c_total, int c_off, i
   NCN_CHECK_PTR(rend); NCN_CHECK_PTR(labels); NCN_CHECK_PTR(sums);
   semantic_ce_kernel<<<(unsigned)ceil_div(n_rays, 256), 256, 0, as_stream(stream)>>>(rend, c_total, c_off, n_cls, labels, n_rays,
                                                                                     grad_scale, sums, dL_drend);
+  NCN_LAUNCH_OK();
+  return NCN_OK;
+}
+
+extern "C" int ncn_normals_from_depth_image(const float* depth, const float* ray_dirs_cc, const float* poses, int pose_rows,
+                                            int n_images, int height, int width, float* normals, ncn_stream_t stream) {
+  NCN_CHECK_SIZE(n_images >= 0 && height >= 0 && width >= 0 && (pose_rows == 3 || pose_rows == 4));
+  const int64_t total = (int64_t)n_images * height * width;
+  if (total == 0) return NCN_OK;
+  NCN_CHECK_PTR(depth); NCN_CHECK_PTR(ray_dirs_cc); NCN_CHECK_PTR(poses); NCN_CHECK_PTR(normals);
+  normals_image_kernel<<<persistent_grid(total, 256, 8), 256, 0, as_stream(stream)>>>(depth, ray_dirs_cc, poses, pose_rows * 4, n_images,
+                                                                                     height, width, normals);
   NCN_LAUNCH_OK();
   return NCN_OK;
 }

@@ -53,6 +53,7 @@ class FusedStep:
         # static inputs: ONE (3,R,3) buffer [rays_o | rays_d | target rgb] so a step needs a single input copy
         self.inp = E(3, R, 3, **f32)
         self.rays_o, self.rays_d, self.target = self.inp[0], self.inp[1], self.inp[2]
+        self.dev_sampling = None             # use_device_sampling(): the batch itself is drawn inside the step
         self.pix_inputs = False              # use_pixel_batches(): rays are generated inside the step from (image, pixel) indices
         self.noise = E(R, **f32)
         self.gen_noise = True                # march jitter drawn inside the step (torch.rand_like of custom_functions.py:83)
@@ -191,6 +192,14 @@ class FusedStep:
         if self.n_cls:
             self.zeros[4:6].zero_()
         self.d_depth.zero_()
+        if self.dev_sampling is not None:    # BaseDataset.__getitem__ (datasets/base.py:94-183) on the device: indices + target gather
+            sm = self.dev_sampling
+            ck(L.ncn_sample_ray_batch(sm["strategy"], ptr(sm["seed"]), R, sm["n_poses"], sm["H"], sm["W"], sm["patch"], ptr(self.b_img),
+                                      ptr(self.b_pix), st), "sample_ray_batch")
+            ck(L.ncn_gather_pixels(ptr(sm["images"]), ptr(self.b_img), ptr(self.b_pix), R, sm["H"] * sm["W"], 3, ptr(self.target), st), "gather_rgb")
+            if sm["labels"] is not None:
+                ck(L.ncn_gather_pixels(ptr(sm["labels"]), ptr(self.b_img), ptr(self.b_pix), R, sm["H"] * sm["W"], 2, ptr(self.sem_target), st),
+                   "gather_labels")
         if self.pix_inputs:                  # NeRFSystem.forward gather + get_rays (train_nerf.py:167-182) as the step's first node
             tr = self.tr
             ck(L.ncn_rays_from_pixels(ptr(tr.poses), ptr(tr.directions), ptr(self.b_img), ptr(self.b_pix), R, ptr(self.rays_o),
@@ -469,6 +478,40 @@ class FusedStep:
         if on != self.pix_inputs:
             self.pix_inputs = on
             self.graph = None                 # the captured sequence and the target pointer change
+
+    STRATEGIES = {"all_images_triang_patch": 0, "same_image_triang_patch": 1, "all_images_triang": 2, "same_image_triang": 3}
+
+    def use_device_sampling(self, images, height, width, strategy="all_images_triang_patch", patch_size=8, sem_labels=None, seed=0):
+        """Draw every batch on the device (BaseDataset.__getitem__, datasets/base.py:94-183):
+        images (P, H*W, 3) f32 resident in HBM (the reference keeps `rays` there too, train_nerf.py:239-240), optional
+        sem_labels (P, H*W) i64.  Indices, target gather and ray generation become the first nodes of the step graph;
+        ``step()`` then needs no input.  Also sets the triangle topology the strategy implies (losses.py:294-313)."""
+        images = images.to(self.dev, torch.float32).contiguous()
+        P = images.shape[0]
+        if images.shape != (P, height * width, 3):
+            raise RuntimeError("use_device_sampling: images must be (P, H*W, 3)")
+        if sem_labels is not None:
+            if not self.n_cls:
+                raise RuntimeError("use_device_sampling: sem_labels given but the model has no semantic head")
+            sem_labels = sem_labels.to(self.dev, torch.int64).contiguous()
+        self.use_pixel_batches(True)
+        self.dev_sampling = dict(images=images, labels=sem_labels, H=int(height), W=int(width), n_poses=P, patch=int(patch_size),
+                                 strategy=self.STRATEGIES[strategy], seed=torch.full((1,), int(seed), dtype=torch.int64, device=self.dev))
+        self.set_triangles(self.batch_triangles(self.R, strategy, patch_size))
+        self.graph = None
+
+    @staticmethod
+    def batch_triangles(n_rays, strategy, patch_size=8):
+        """(3, M) ray indices (x1, x2, x3) of every triangle of a batch: losses.py:294-299 for the triangle strategies,
+        :301-313 with the local offsets of datasets/base.py:51-58 (x1 = (i,j), x2 = (i-1,j), x3 = (i,j-1), i,j >= 1) for patches."""
+        if strategy in ("all_images_triang", "same_image_triang"):
+            t = torch.arange(n_rays // 3 * 3).view(-1, 3)
+            return t.t().contiguous()
+        p = patch_size
+        loc = torch.arange(p * p).view(p, p)
+        offs = torch.stack([loc[1:, 1:].reshape(-1), loc[:-1, 1:].reshape(-1), loc[1:, :-1].reshape(-1)])       # (3, (p-1)^2)
+        base = (torch.arange(n_rays // (p * p)) * p * p).view(1, -1, 1)
+        return (base + offs.view(3, 1, -1)).reshape(3, -1).contiguous()
 
     @staticmethod
     def pack_pixel_batch(img_idx, pix_idx, rgb, pin=True):

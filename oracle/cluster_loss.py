@@ -87,3 +87,31 @@ def cluster_terms(normals, labels):
     dot = sum(1.0 - (x * ck).sum(-1).mean() for x, ck in zip(cl, c)) / 3.0
     l1 = sum((x - ck).abs().sum(-1).mean() for x, ck in zip(cl, c)) / 3.0
     return ort, dot, l1
+
+
+def normals_from_depth_image(depth, ray_dirs_cc, poses):
+    """datasets/hypersim_src/utils.py:544-611 (_extract_normals_from_depth_batch), restated: P = dirs * depth in the camera
+    frame; n(y,x) = normalize(cross(P(y-1,x) - P(y,x), P(y,x-1) - P(y,x))) (F.normalize eps 1e-12); rotate by poses[:, :3, :3];
+    zero on the one-pixel border (ZeroPad2d) and where the pixel's own depth is 0 / NaN / Inf (:604-606)."""
+    B, H, W = depth.shape
+    P = ray_dirs_cc.view(1, H, W, 3) * depth.view(B, H, W, 1)
+    P1, P2, P3 = P[:, 1:-1, 1:-1], P[:, :-2, 1:-1], P[:, 1:-1, :-2]
+    n = torch.cross(P2 - P1, P3 - P1, dim=-1)
+    n = n / n.norm(dim=-1, keepdim=True).clamp_min(1e-12)
+    n = torch.einsum("bij,bhwj->bhwi", poses[:, :3, :3], n)
+    out = torch.zeros(B, H, W, 3, dtype=depth.dtype)
+    out[:, 1:-1, 1:-1] = n
+    bad = (depth == 0.0) | torch.isnan(depth) | torch.isinf(depth)
+    out[bad] = 0.0
+    return out
+
+
+def rotation_from_centroids(centrs_new, R_offset):
+    """train_nerf.py:505-517 restated: columns +-c_k matched to the columns of R_offset by largest dot product, projected to SO(3)
+    with scipy's Rotation.from_matrix (the reference's choice)."""
+    from scipy.spatial.transform import Rotation
+    c = centrs_new.double().T
+    both = torch.cat([c, -1.0 * c], dim=1)
+    sim = (R_offset.double().unsqueeze(1) * both.unsqueeze(-1)).sum(0)
+    rot = both[:, torch.argmax(sim, dim=0)]
+    return torch.from_numpy(Rotation.from_matrix(rot.numpy()).as_matrix())

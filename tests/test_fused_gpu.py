@@ -279,3 +279,71 @@ def test_fused_grid_update_matches_module_path_statistically():
     assert abs(pop(ba) - pop(bb)) <= 0.02 * max(pop(ba), 1.0)
     assert abs(float(ga.clamp(min=0).mean()) - float(gb.clamp(min=0).mean())) <= 0.05 * float(ga.clamp(min=0).mean())
     assert float((gb != g0).float().mean()) > 0.2                            # the update touched a large part of the grid
+
+
+@pytest.mark.parametrize("strategy", ["all_images_triang_patch", "same_image_triang_patch", "all_images_triang", "same_image_triang"])
+def test_device_batch_sampling(strategy):
+    """ncn_sample_ray_batch + ncn_gather_pixels against the index arithmetic of BaseDataset.__getitem__ (datasets/base.py:94-183):
+    ranges, patch / triangle structure (incl. the corner-INDEX quirk), one image for the same_image strategies, uniform draws,
+    the seed advancing, gathered targets; ragged batch tail; then a fused step fed by nothing but the device sampler."""
+    import ncn_b200  # noqa: F401
+    from ncn_b200 import _lib, synth
+    from ncn_b200._lib import check, ptr, stream
+    from ncn_b200.fused import FusedStep
+    L = _lib.lib()
+    H, W, P, p = 48, 64, 7, 8
+    R = 64 * 300 + 5                                   # ragged: 5 rays beyond the last whole patch / 2 beyond the last triangle
+    sid = FusedStep.STRATEGIES[strategy]
+    seed = torch.full((1,), 11, dtype=torch.int64, device="cuda")
+    img = torch.empty(R, dtype=torch.int64, device="cuda"); pix = torch.empty(R, dtype=torch.int64, device="cuda")
+    check(L.ncn_sample_ray_batch(sid, ptr(seed), R, P, H, W, p, ptr(img), ptr(pix), stream()))
+    assert int(seed) == 12
+    group = p * p if sid <= 1 else 3
+    n_used = R // group * group
+    assert int(img[n_used:].abs().sum()) == 0 and int(pix[n_used:].abs().sum()) == 0
+    im, px = img[:n_used].view(-1, group), pix[:n_used].view(-1, group)
+    assert int(im.min()) >= 0 and int(im.max()) < P and bool((im == im[:, :1]).all())
+    assert int(px.min()) >= 0 and int(px.max()) < H * W
+    if sid & 1:
+        assert bool((im == im[0, 0]).all())
+    else:
+        cnt = torch.bincount(im[:, 0], minlength=P).float()
+        assert float(cnt.min()) > 0.5 * float(cnt.mean())
+    if sid <= 1:
+        dy, dx = torch.meshgrid(torch.arange(p, device="cuda"), torch.arange(p, device="cuda"), indexing="ij")
+        assert torch.equal(px - px[:, :1], (dy * W + dx).reshape(1, -1).expand_as(px))
+        assert int(px[:, 0].max()) < (H - p + 1) * (W - p + 1)            # corner INDEX, not pixel id (base.py:164-166)
+        assert int(px[:, 0].max()) > 0.9 * (H - p + 1) * (W - p + 1)
+    else:
+        x1, x2, x3 = px[:, 0], px[:, 1], px[:, 2]
+        assert torch.equal(x2, x1 - W) and torch.equal(x3, x1 - 1)
+        y, x = x1 // W, x1 % W
+        assert int(y.min()) >= 1 and int(y.max()) <= H - 2 and int(x.min()) >= 1 and int(x.max()) <= W - 2
+        assert int(y.max()) == H - 2 and int(x.max()) == W - 2 and int(y.min()) == 1 and int(x.min()) == 1
+    img2 = torch.empty_like(img); pix2 = torch.empty_like(pix)
+    check(L.ncn_sample_ray_batch(sid, ptr(seed), R, P, H, W, p, ptr(img2), ptr(pix2), stream()))
+    assert not torch.equal(pix, pix2)
+    g = torch.Generator(device="cuda").manual_seed(0)
+    images = torch.rand(P, H * W, 3, device="cuda", generator=g)
+    out = torch.empty(R, 3, device="cuda")
+    check(L.ncn_gather_pixels(ptr(images), ptr(img), ptr(pix), R, H * W, 3, ptr(out), stream()))
+    assert torch.equal(out, images[img, pix])
+    labels = torch.randint(0, 4, (P, H * W), device="cuda", generator=g)
+    lab = torch.empty(R, dtype=torch.int64, device="cuda")
+    check(L.ncn_gather_pixels(ptr(labels), ptr(img), ptr(pix), R, H * W, 2, ptr(lab), stream()))
+    assert torch.equal(lab, labels[img, pix])
+    # a fused step whose only input is the device sampler
+    tr, *_ = _setup(R=1536, seed=4)
+    poses = torch.from_numpy(synth.camera_poses(50, 0)).cuda(); dirs = torch.from_numpy(synth.pixel_directions("hypersim")).cuda()
+    tr.set_cameras(poses, dirs)
+    fs = tr.fused_step(use_graph=True)
+    imgs = torch.rand(50, 768 * 1024, 3, device="cuda", generator=g)
+    fs.use_device_sampling(imgs, 768, 1024, strategy=strategy, patch_size=8, seed=3)
+    assert fs.M == (1536 // 64 * 49 if sid <= 1 else 512)
+    fs.step(); torch.cuda.synchronize()
+    first = fs.b_pix.clone()
+    assert torch.equal(fs.target, imgs[fs.b_img, fs.b_pix])
+    fs.step(); torch.cuda.synchronize()
+    assert not torch.equal(first, fs.b_pix) and int(fs.dev_sampling["seed"]) >= 5
+    d, n = fs.stats_host()
+    assert np.isfinite(d["total"]) and n > 1536

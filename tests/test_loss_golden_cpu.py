@@ -55,3 +55,35 @@ def test_kmeans_standin_recovers_planted_frame():
     cos = np.abs(axes @ q)            # each selected centroid aligns with one planted axis
     assert (cos.max(1) > np.cos(np.deg2rad(1.5))).all(), cos
     assert sorted(cos.argmax(1).tolist()) == [0, 1, 2]
+
+
+def test_normals_image_oracle_matches_reference_golden():
+    """oracle.cluster_loss.normals_from_depth_image vs the reference's own _extract_normals_from_depth_batch
+    (tests/golden/normals_image_a.npz, generator oracle/gen_golden_normals_image.py): border, invalid depth codes, NaN
+    propagation from invalid neighbours, rotation to the world frame."""
+    import os
+    import numpy as np
+    import torch
+    from oracle import cluster_loss as cl
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "normals_image_a.npz"))
+    out = cl.normals_from_depth_image(torch.from_numpy(g["depth"]), torch.from_numpy(g["dirs"]), torch.from_numpy(g["poses"])).numpy()
+    ref = g["normals"]
+    fin = np.isfinite(ref).all(-1)
+    assert (~fin).sum() == 4 and not np.isfinite(out[~fin]).all(-1).any()
+    np.testing.assert_allclose(out[fin], ref[fin], rtol=0, atol=2e-6)
+    zero = (ref[fin] == 0).all(-1)
+    assert zero.sum() > 300 and (out[fin][zero] == 0).all()
+
+
+def test_rotation_from_centroids_oracle():
+    """train_nerf.py:505-517 restated: a noisy, sign-flipped, permuted copy of a rotation's columns is mapped back onto it"""
+    import numpy as np
+    import torch
+    from oracle import cluster_loss as cl
+    from scipy.spatial.transform import Rotation
+    R = torch.from_numpy(Rotation.from_euler("ZYX", [25.0, -10.0, 5.0], degrees=True).as_matrix())
+    rows = torch.stack([-R[:, 2], R[:, 0], -R[:, 1]]) + 0.01 * torch.randn(3, 3, dtype=torch.float64)     # centroids as rows
+    rot = cl.rotation_from_centroids(rows.float(), R)
+    assert abs(float(torch.det(rot)) - 1.0) < 1e-9
+    ang = np.rad2deg(np.arccos(np.clip((np.trace((rot.T @ R).numpy()) - 1) / 2, -1, 1)))
+    assert ang < 1.5, ang

@@ -144,3 +144,48 @@ def test_cluster_tail_equals_the_four_calls(ncn):
     torch.testing.assert_close(a[3], bb[3], rtol=1e-6, atol=1e-7, equal_nan=True)
     torch.testing.assert_close(a[4], bb[4], rtol=1e-6, atol=1e-9)
     torch.testing.assert_close(a[5], bb[5], rtol=1e-4, atol=1e-7)      # float atomics: order differs
+
+
+def test_normals_image_kernel_matches_reference_golden(ncn):
+    """ncn_normals_from_depth_image vs the reference's _extract_normals_from_depth_batch (golden fixture), with (B,4,4) and
+    (B,3,4) poses; then a full 768x1024 image against the oracle restatement"""
+    import os
+    from ncn_b200 import clustering
+    from oracle import cluster_loss as cl
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "normals_image_a.npz"))
+    depth, dirs, poses = (torch.from_numpy(g[k]).cuda() for k in ("depth", "dirs", "poses"))
+    ref = g["normals"]
+    fin = np.isfinite(ref).all(-1)
+    for p in (poses, poses[:, :3].contiguous()):
+        out = clustering.normals_from_depth_image(depth, dirs, p).cpu().numpy()
+        assert not np.isfinite(out[~fin]).all(-1).any()
+        np.testing.assert_allclose(out[fin], ref[fin], rtol=0, atol=2e-6)
+        zero = (ref[fin] == 0).all(-1)
+        assert (out[fin][zero] == 0).all()
+    gen = torch.Generator().manual_seed(0)
+    H, W = 768, 1024
+    d = 1.0 + torch.rand(2, H, W, generator=gen); d[0, 100:200, 300:400] = 0.0
+    ys, xs = torch.meshgrid(torch.arange(H, dtype=torch.float32), torch.arange(W, dtype=torch.float32), indexing="ij")
+    dr = torch.stack([(xs - W / 2) / 886.81, (ys - H / 2) / 886.81, torch.ones_like(xs)], -1).reshape(-1, 3)
+    q, _ = torch.linalg.qr(torch.randn(2, 3, 3, generator=gen))
+    ps = torch.eye(4).repeat(2, 1, 1); ps[:, :3, :3] = q
+    want = cl.normals_from_depth_image(d, dr, ps)
+    got = clustering.normals_from_depth_image(d.cuda(), dr.cuda(), ps.cuda()).cpu()
+    torch.testing.assert_close(got, want, rtol=0, atol=5e-5)       # random depth: near-degenerate triangles amplify rounding
+    assert float(got[0, 100:200, 300:400].abs().max()) == 0.0
+
+
+def test_rotation_from_normals_recovers_planted_frame(ncn):
+    """validation_epoch_end (train_nerf.py:491-517): K = 30, 30 iterations on planted Manhattan normals; the recovered rotation
+    matches the planted frame within 1.5 degrees, and equals the oracle's read-out of the kernel's own centroids"""
+    from ncn_b200 import clustering, synth
+    from oracle import cluster_loss as cl
+    x, q = synth.manhattan_normals(32768, seed=1)
+    R = torch.from_numpy(q)
+    xt = torch.from_numpy(x).cuda()
+    rot = clustering.rotation_from_normals(xt, R, K=30, niter=30, t_similar=0.99)
+    assert abs(float(torch.det(rot)) - 1.0) < 1e-9
+    ang = np.rad2deg(np.arccos(np.clip((np.trace((rot.T @ R.double()).numpy()) - 1) / 2, -1, 1)))
+    assert ang < 1.5, ang
+    _, _, centrs = clustering.normals_clustering(xt, K=30, niter=30, t_similar=0.99)
+    torch.testing.assert_close(rot, cl.rotation_from_centroids(centrs.cpu(), R), rtol=0, atol=1e-12)
