@@ -70,3 +70,50 @@ def test_unchanged_reference_files_bind_to_the_shims():
                "raymarching_test", "composite_train_fw", "composite_train_bw", "composite_train_multi_fw", "composite_train_multi_bw",
                "composite_test_fw", "composite_test_multi_fw", "distortion_loss_fw", "distortion_loss_bw"}      # binding.cpp:330-350
     assert binding <= set(out["vren_names"])
+
+
+CKPT_PROBE = r'''
+import io, contextlib, json, os, sys, tempfile, warnings
+warnings.filterwarnings("ignore")
+sys.path.insert(0, %(root)r)
+import torch
+import ncn_b200
+from ncn_b200.ngp import NGPMT
+sys.path.insert(0, %(ref)r)
+import utils as ref_utils                      # the reference's checkpoint helpers (utils.py:4-39), unmodified
+kw = dict(scale=0.5, grid_size=32, rgb_act="Sigmoid", pred_sem=True, pred_norm=True, n_sem_cls=3, log2_T=14)
+with contextlib.redirect_stdout(io.StringIO()):
+    a, b = NGPMT(**kw), NGPMT(**kw)
+with torch.no_grad():
+    for p in a.parameters():
+        p.copy_(torch.randn_like(p))
+    a.density_grid.uniform_(); a.density_bitfield.random_(0, 255)
+# what pytorch-lightning writes: {'state_dict': {'model.<key>': tensor, ... other modules ...}}
+sd = {"model." + k: v.clone() for k, v in a.state_dict().items()}
+sd["val_lpips.net.weight"] = torch.zeros(3); sd["directions"] = torch.zeros(4, 3); sd["poses"] = torch.zeros(2, 3, 4)
+path = os.path.join(tempfile.mkdtemp(), "last.ckpt")
+torch.save({"state_dict": sd, "epoch": 3}, path)
+ref_utils.load_ckpt(b, path)
+same = all(torch.equal(x, y) for x, y in zip(a.state_dict().values(), b.state_dict().values()))
+slim = ref_utils.slim_ckpt(path)
+c = NGPMT(**kw)
+torch.save({"state_dict": slim}, path)
+ref_utils.load_ckpt(c, path, prefixes_to_ignore=["density_grid", "grid_coords"])
+same_params = all(torch.equal(x, y) for x, y in zip(a.parameters(), c.parameters()))
+print("PROBE" + json.dumps({"same": same, "same_params_after_slim": same_params, "keys": sorted(a.state_dict().keys()),
+                            "slim_dropped": sorted(set(sd) - set(slim)), "bitfield_kept": bool(torch.equal(a.density_bitfield, c.density_bitfield))}))
+'''
+
+
+@pytest.mark.skipif(not os.path.isfile(os.path.join(REF, "utils.py")), reason="reference tree not present on this machine")
+def test_reference_checkpoint_helpers_round_trip_our_model():
+    """SURVEY section 8 row f4 (checkpoint key compatibility): a Lightning-style checkpoint of our NGPMT goes through the
+    reference's own load_ckpt / slim_ckpt (utils.py:4-39) and restores parameters and occupancy state key for key."""
+    r = subprocess.run([sys.executable, "-c", CKPT_PROBE % dict(root=ROOT, ref=REF)], capture_output=True, text=True, cwd="/tmp", timeout=600)
+    assert r.returncode == 0, r.stderr[-3000:]
+    out = json.loads([l for l in r.stdout.splitlines() if l.startswith("PROBE")][0][5:])
+    assert out["same"] and out["same_params_after_slim"] and out["bitfield_kept"]
+    assert out["keys"] == sorted(["center", "xyz_min", "xyz_max", "half_size", "density_bitfield", "density_grid", "grid_coords",
+                                  "xyz_encoder.params", "sigma_net.params", "dir_encoder.params", "rgb_net.params", "sem_net.params",
+                                  "norm_net.params"])
+    assert out["slim_dropped"] == sorted(["directions", "model.density_grid", "model.grid_coords", "poses", "val_lpips.net.weight"])
