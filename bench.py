@@ -265,6 +265,9 @@ def run_ours(args):
     for i in range(max(args.warmup, 3)):
         step_resident(i)
 
+    if tr.peer is not None and tr.peer.error() != 0:
+        raise RuntimeError("peer-memory exchange: a cross-GPU wait timed out during warm-up (ncn_peer_error)")
+
     # ---- timed region 1: inputs resident in HBM (CUDA-graph replay of the fused step)
     clocks = ClockSampler(local); clocks.start()
     ms = timed(step_resident, args.steps)

@@ -550,7 +550,7 @@ const char* ncn_comm_last_error(void);
  *            (world x 192 bytes, rank order).  world == 1 needs neither.
  *   step   : asynchronous on `stream`, graph-capturable; groups / lr_bc_dev / skip_dev / grad_div_dev as in
  *            ncn_adam_step_groups; sumsq_out_dev (optional) receives the squared norm of the averaged gradient.
- *            Every rank must call it the same number of times.  Cross-GPU waits are bounded (4 s) and set the error word
+ *            Every rank must call it the same number of times.  Cross-GPU waits are bounded (20 s) and set the error word
  *            (ncn_peer_error) instead of hanging. */
 typedef struct ncn_peer ncn_peer;
 int ncn_peer_create(ncn_peer** out, int rank, int world, int64_t n_params);

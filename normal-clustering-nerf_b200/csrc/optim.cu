@@ -267,7 +267,7 @@ extern "C" int ncn_clip_coef(const float* sumsq_dev, float max_norm, float* coef
 //       of the parameters the forward reads), the whole local gradient buffer is zeroed for the next backward.
 // Per rank and step: (W-1)/W * 4 B/param in over NVLink, (W-1)/W * 2 B/param out - vs 2 * (W-1)/W * 4 B each way for a ring
 // all-reduce - no NCCL call, so the whole step stays ONE CUDA graph.  Cross-GPU ordering uses epoch flags in each rank's
-// sync block (release/acquire at system scope); every wait has a wall-clock bound and raises `error` instead of hanging.
+// sync block (release/acquire at system scope); every wait has a wall-clock bound (20 s) and raises `error` instead of hanging.
 namespace ncn {
 
 constexpr int kPeerMax = 8;
@@ -298,13 +298,14 @@ __device__ __forceinline__ unsigned long long peer_now_ns() {
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
   return t;
 }
-// one thread: wait until every rank's flag of `phase` reached `epoch` (bounded: 4 s)
+// one thread: wait until every rank's flag of `phase` reached `epoch` (bounded: 20 s - ranks enter a step within microseconds of
+// each other in steady state; the bound only has to survive start-up skew and must never turn a dead peer into a hung GPU)
 __device__ __forceinline__ void peer_wait(PeerSync* me, int phase, int world, unsigned int epoch) {
   const unsigned long long t0 = peer_now_ns();
   for (int q = 0; q < world; ++q) {
     while ((int)(ld_acquire_sys(&me->flag[phase][q]) - epoch) < 0) {
       __nanosleep(64);
-      if (peer_now_ns() - t0 > 4000000000ull) { atomicExch(&me->error, 1u + (unsigned)phase); return; }
+      if (peer_now_ns() - t0 > 20000000000ull) { atomicExch(&me->error, 1u + (unsigned)phase); return; }
     }
   }
 }

@@ -599,6 +599,9 @@ class FusedStep:
 
     def _capture(self, multi):
         # warm-up on a side stream (sets function attributes, touches every buffer), then capture
+        if self.peer is not None and self.tr.world_size > 1:
+            import torch.distributed as dist
+            dist.barrier()                        # the peer step waits for every rank on the device: enter it together
         self.opt.grad.zero_()
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
