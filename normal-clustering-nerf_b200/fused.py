@@ -11,6 +11,10 @@ FlatAdam), but expressed as one linear sequence of libncn kernels on pre-allocat
   composite fw -> photometric+opacity loss (+gradient) -> normals-from-depth -> k-means -> triple selection ->
   cluster loss (+gradient) -> normals bw -> composite bw -> rgb MLP bw -> dh -> sigma MLP bw -> grid bw ->
   [NCCL all-reduce] -> sum-of-squares -> clip coefficient -> fused Adam (x2 groups)
+  (multi-rank default: the bracket and everything after it = ncn_peer_step, the sharded exchange over NVLink peer memory)
+
+Optional nodes: the batch itself (use_device_sampling: indices + target gather) and ray generation (use_pixel_batches) in
+front; the semantic / normal heads (ncn_field_heads_fwd, ncn_semantic_ce_loss, semantic-head backward) when the model has them.
 
 No torch op, no autograd graph, no allocation and no host synchronisation happen inside the step, so it is
 captured once into a CUDA graph and replayed (the reference's step has >= 6 host syncs).
