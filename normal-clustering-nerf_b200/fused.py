@@ -129,6 +129,10 @@ class FusedStep:
         # multi-rank: the same overlap with three graphs on two streams and an EAGER all-reduce in between
         #   opt stream : [all-reduce(prev grads) -> graph(adam)]      main stream: graph(march) -> join -> graph(field)
         self.defer_multi = use_graph and self.nccl
+        # developer A/B knob (NCN_SUMSQ_TAIL=1): take ||g||^2 at the TAIL of the step that produced the gradient (L2-hot) instead of
+        # in front of the next step's Adam.  Measured: 0.556 vs 0.553 ms/step, e2e 0.581 vs 0.569 - no gain (the optimizer branch
+        # is not what bounds the head of the graph once it co-runs with the march), so the default stays the head placement.
+        self.sumsq_tail = self.defer and self.peer is None and os.environ.get("NCN_SUMSQ_TAIL", "0") == "1"
         self.opt_stream = torch.cuda.Stream(device=dev)
         self.ev_fork2, self.ev_join2 = torch.cuda.Event(), torch.cuda.Event()
         self.coef = torch.ones(1, **f32)
@@ -326,6 +330,23 @@ class FusedStep:
                                      C.byref(self.adam_groups), opt.betas[0], opt.betas[1], opt.eps, ptr(self.grad_div), ptr(self.flag),
                                      ptr(sumsq), ptr(self.dev_sched[sched_off:sched_off + 3]), st), "adam")
 
+    def _sumsq(self):
+        """||g||^2 (+ non-finite flag) of the gradient that is complete on the current stream"""
+        opt = self.opt
+        sumsq = self.zeros[2:3]
+        sumsq.zero_()
+        self.flag.zero_()
+        check(self.L.ncn_grad_sumsq(ptr(opt.grad), opt.grad.numel(), ptr(self.grad_div), ptr(sumsq), ptr(self.flag),
+                                    torch.cuda.current_stream().cuda_stream), "sumsq")
+
+    def _adam_only(self, sched_off=0):
+        """clip + Adam of both parameter groups from an already computed ||g||^2 / skip flag (sumsq_tail mode)"""
+        opt = self.opt
+        check(self.L.ncn_adam_step_groups(ptr(opt.flat), ptr(opt.grad), ptr(opt.m), ptr(opt.v), ptr(self.flat16), opt.flat.numel(),
+                                          C.byref(self.adam_groups), opt.betas[0], opt.betas[1], opt.eps, ptr(self.grad_div), ptr(self.flag),
+                                          ptr(self.zeros[2:3]), ptr(self.dev_sched[sched_off:sched_off + 3]),
+                                          torch.cuda.current_stream().cuda_stream), "adam")
+
     def _run_deferred(self, multi):
         """One replay = [apply the PREVIOUS step's update] || [jitter + AABB + march of THIS step] -> field/backward.
         The optimizer pass (dense, HBM bound) and the march (serial, latency bound) do not depend on each other, so they
@@ -338,11 +359,16 @@ class FusedStep:
         with torch.cuda.stream(opt_stream):
             if multi:
                 self.tr.comm.allreduce_sum_(self.opt.grad)
-            self._optimizer(sched_off=6)
+            if self.sumsq_tail:
+                self._adam_only(sched_off=6)      # norm + skip flag were left by the previous replay's tail (or by step() / flush())
+            else:
+                self._optimizer(sched_off=6)
             self.ev_join2.record(opt_stream)
         self._run_march()
         main.wait_event(self.ev_join2)
         self._run_field()
+        if self.sumsq_tail:
+            self._sumsq()
 
     # ------------------------------------------------------------------ public
     def set_triangles(self, tri):
@@ -422,7 +448,8 @@ class FusedStep:
             if self.graph is None:
                 self._capture(multi)
             if not self.pending:
-                self.flag_init.fill_(1)          # nothing to apply yet: the optimizer branch of this replay is a no-op
+                # nothing to apply yet: the optimizer branch of this replay is a no-op
+                (self.flag if self.sumsq_tail else self.flag_init).fill_(1)
             self.graph[0].replay()
             if not self.pending:
                 self.flag_init.zero_()
@@ -461,7 +488,10 @@ class FusedStep:
         if (self.defer or self.defer_multi) and self.pending:
             if self.nccl:
                 self.tr.comm.allreduce_sum_(self.opt.grad)
-            self._optimizer(sched_off=0)          # slot 0 still holds the last step's schedule
+            if self.sumsq_tail and self.defer:
+                self._adam_only(sched_off=0)      # the replay's tail already took the norm of this gradient
+            else:
+                self._optimizer(sched_off=0)      # slot 0 still holds the last step's schedule
             self.pending = False
 
     def use_pixel_batches(self, on=True):
@@ -603,6 +633,7 @@ class FusedStep:
 
     def _capture(self, multi):
         # warm-up on a side stream (sets function attributes, touches every buffer), then capture
+        self.flush()                              # a gradient still waiting for its update must not be dropped by the re-capture
         if self.peer is not None and self.tr.world_size > 1:
             import torch.distributed as dist
             dist.barrier()                        # the peer step waits for every rank on the device: enter it together
