@@ -3,10 +3,12 @@
 
     timeout 300 python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 tools/check_peer.py
 
-Two trainers per rank with identical initial state, one per exchange; each rank feeds BOTH the same rank-specific batches for
-a few fused steps.  Checks: (1) the peer path's fp16 parameters are bit-identical on every rank and no wait timed out;
-(2) they match the NCCL path's to fp16 rounding (the W gradient terms are summed in a different order); (3) the fp32 master
-inside each rank's own slice matches the replicated master.  Prints per-step time of both exchanges (graph replay)."""
+Three trainers per rank with identical initial state - peer exchange, NCCL exchange, NCCL exchange again - fed the same
+rank-specific batch for 6 fused steps.  Checks: (1) kernel level: ncn_peer_step on explicit random gradients reproduces
+all-reduce -> ncn_grad_sumsq -> ncn_adam_step_groups (norm, owned fp32 slice, fp16 copy, zeroed gradient); (2) the peer path's
+fp16 parameters are bit-identical on every rank and no bounded wait fired; (3) its difference to the NCCL path is within the
+run-to-run difference of the NCCL path itself (the backward accumulates with floating-point atomics); (4) gather_master_params
+rebuilds an identical fp32 master everywhere.  Also prints ms per step of each exchange (100 graph replays)."""
 import json
 import os
 import sys
