@@ -117,7 +117,11 @@ class NeRFMTLoss(nn.Module):
             pred["norm_depth"] = normals
         if self.sem_w > 0 and "semantics" in target:
             # losses.py:240-242, 569-573: void class 0 -> -1 (ignored); mean over the labelled rays; NaN (none labelled) -> 0
-            ce = torch.nn.functional.cross_entropy(pred["sem"][:gt_l].float(), target["semantics"] - 1, ignore_index=-1)
+            # (sum / count instead of reduction="mean": an all-void batch gives 0 with ZERO gradient, like the reference's
+            # replacement of the NaN term by a fresh tensor - the mean form would back-propagate 0 * NaN)
+            lab = target["semantics"] - 1
+            ce_sum = torch.nn.functional.cross_entropy(pred["sem"][:gt_l].float(), lab, ignore_index=-1, reduction="sum")
+            ce = ce_sum / (lab >= 0).sum().clamp_min(1)
             loss_d["sem"] = _valid(self.sem_w * ce)
         loss_d["total"] = sum(v for v in loss_d.values())
         return loss_d

@@ -87,3 +87,30 @@ def test_rotation_from_centroids_oracle():
     assert abs(float(torch.det(rot)) - 1.0) < 1e-9
     ang = np.rad2deg(np.arccos(np.clip((np.trace((rot.T @ R).numpy()) - 1) / 2, -1, 1)))
     assert ang < 1.5, ang
+
+
+def test_semantic_loss_module_path_matches_reference_golden():
+    """ncn_b200.losses.NeRFMTLoss with the semantic term (CPU tensors: the clustering weights are 0, so no kernel is involved)
+    against the reference's own losses.py run on the same inputs (tests/golden/sem_loss_a.npz, oracle/gen_golden_sem.py):
+    'sem', 'rgb', 'opacity', 'total' and the gradients reaching the rendered logits / colours; all-void batch -> term dropped."""
+    import os
+    import numpy as np
+    import torch
+    import ncn_b200  # noqa: F401
+    from ncn_b200.losses import NeRFMTLoss
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "sem_loss_a.npz"))
+    hp = dict(loss_opacity_w=float(g["opacity_w"]), loss_sem_w=float(g["sem_w"]), pred_sem=True, pred_norm_nn=True, pred_norm_depth=False,
+              ray_sampling_strategy="all_images")
+    for case in ("a", "b", "void"):
+        sem = torch.from_numpy(g[f"{case}_sem"]).requires_grad_(True)
+        rgb = torch.from_numpy(g[f"{case}_rgb"]).requires_grad_(True)
+        pred = {"rgb": rgb, "depth": torch.zeros(len(rgb)), "opacity": torch.from_numpy(g[f"{case}_opacity"]), "sem": sem}
+        target = {"rgb": torch.from_numpy(g[f"{case}_target_rgb"]), "semantics": torch.from_numpy(g[f"{case}_labels"])}
+        loss_d = NeRFMTLoss(hp)(pred, target, global_step=3000)
+        loss_d["total"].backward()
+        for k in ("sem", "rgb", "opacity", "total"):
+            np.testing.assert_allclose(float(loss_d[k]), float(g[f"{case}_loss_{k}"]), rtol=1e-6, atol=1e-9)
+        gs = sem.grad if sem.grad is not None else torch.zeros_like(sem)
+        assert torch.isfinite(gs).all()                       # all-void batch: zero gradient, not 0 * NaN
+        np.testing.assert_allclose(gs.numpy(), g[f"{case}_grad_sem"], rtol=1e-5, atol=1e-9)
+        np.testing.assert_allclose(rgb.grad.numpy(), g[f"{case}_grad_rgb"], rtol=1e-5, atol=1e-9)

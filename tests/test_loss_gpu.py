@@ -194,3 +194,38 @@ def test_rotation_from_normals_recovers_planted_frame(ncn):
     assert ang < 1.5, ang
     _, _, centrs = clustering.normals_clustering(xt, K=30, niter=30, t_similar=0.99)
     torch.testing.assert_close(rot, cl.rotation_from_centroids(centrs.cpu(), R), rtol=0, atol=1e-12)
+
+
+def test_semantic_and_photometric_kernels_match_reference_sem_golden(ncn):
+    """ncn_photometric_loss + ncn_semantic_ce_loss on a C = 3 + 3 + n_cls rendered row against the reference's own losses.py with
+    the semantic head enabled (tests/golden/sem_loss_a.npz): the three loss values and the gradient on every channel - colour
+    and logits as the reference computes them, the norm_nn channels exactly zero (the reference puts no loss on them);
+    all-void batch: term dropped, zero gradient."""
+    import ctypes as C
+    import os
+    from ncn_b200 import _lib
+    from ncn_b200._lib import ptr, stream, check
+    L = _lib.lib()
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "sem_loss_a.npz"))
+    sem_w, op_w = float(g["sem_w"]), float(g["opacity_w"])
+    bg = (C.c_float * 3)(0.0, 0.0, 0.0)                 # the golden rgb is the final colour: no background term to add
+    for case in ("a", "b", "void"):
+        rgb = torch.from_numpy(g[f"{case}_rgb"]).cuda(); sem = torch.from_numpy(g[f"{case}_sem"]).cuda()
+        R, n_cls = sem.shape
+        Ct = 6 + n_cls
+        rend = torch.cat([rgb, torch.randn(R, 3, device="cuda"), sem], 1).contiguous()
+        opacity = torch.from_numpy(g[f"{case}_opacity"]).cuda(); target = torch.from_numpy(g[f"{case}_target_rgb"]).cuda()
+        labels = torch.from_numpy(g[f"{case}_labels"]).cuda()
+        sums = torch.zeros(2, device="cuda"); ce = torch.zeros(2, device="cuda")
+        d_rend = torch.full((R, Ct), 5.0, device="cuda"); d_op = torch.empty(R, device="cuda")
+        check(L.ncn_photometric_loss(ptr(rend), ptr(opacity), ptr(target), R, Ct, bg, op_w, 1.0, None, ptr(sums), ptr(d_rend), ptr(d_op), stream()))
+        check(L.ncn_semantic_ce_loss(ptr(rend), Ct, 6, n_cls, ptr(labels), R, sem_w, ptr(ce), ptr(d_rend), stream()))
+        np.testing.assert_allclose(float(sums[0]) / (3 * R), float(g[f"{case}_loss_rgb"]), rtol=1e-5)
+        np.testing.assert_allclose(op_w * float(sums[1]) / R, float(g[f"{case}_loss_opacity"]), rtol=1e-5)
+        n_valid = int((labels > 0).sum())
+        assert int(ce[1]) == n_valid
+        loss_sem = sem_w * float(ce[0]) / n_valid if n_valid else 0.0
+        np.testing.assert_allclose(loss_sem, float(g[f"{case}_loss_sem"]), rtol=1e-5, atol=1e-9)
+        torch.testing.assert_close(d_rend[:, :3].cpu(), torch.from_numpy(g[f"{case}_grad_rgb"]), rtol=1e-4, atol=1e-9)
+        torch.testing.assert_close(d_rend[:, 6:].cpu(), torch.from_numpy(g[f"{case}_grad_sem"]), rtol=1e-4, atol=1e-9)
+        assert float(d_rend[:, 3:6].abs().max()) == 0.0
