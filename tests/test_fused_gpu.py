@@ -219,6 +219,30 @@ def test_pixel_batch_step_equals_ray_step():
     assert fs.target.data_ptr() == fs.inp[2].data_ptr() and fs.graph is None
 
 
+def test_rays_from_pixels_matches_reference_golden():
+    """ncn_rays_from_pixels against the reference's own get_ray_directions + get_rays (datasets/ray_utils.py:8-71) used as
+    NeRFSystem.forward does (tests/golden/get_rays_a.npz, generator oracle/gen_golden_rays.py); the synthetic camera table of
+    ncn_b200.synth follows the same pixel-centre convention."""
+    import os
+    import ncn_b200  # noqa: F401
+    from ncn_b200 import _lib, synth
+    from ncn_b200._lib import check, ptr, stream
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "get_rays_a.npz"))
+    poses = torch.from_numpy(g["poses"]).cuda().contiguous(); dirs = torch.from_numpy(g["directions"]).cuda().contiguous()
+    img = torch.from_numpy(g["img_idx"]).cuda(); pix = torch.from_numpy(g["pix_idx"]).cuda()
+    n = img.shape[0]
+    ro = torch.empty(n, 3, device="cuda"); rd = torch.empty(n, 3, device="cuda")
+    check(_lib.lib().ncn_rays_from_pixels(ptr(poses), ptr(dirs), ptr(img), ptr(pix), n, ptr(ro), ptr(rd), stream()))
+    assert torch.equal(ro.cpu(), torch.from_numpy(g["rays_o"]))
+    torch.testing.assert_close(rd.cpu(), torch.from_numpy(g["rays_d"]), rtol=1e-6, atol=2e-7)
+    # synth.pixel_directions: same (u - cx + 0.5) / fx convention, normalised
+    k = synth.CAMERAS["hypersim"]
+    d = synth.pixel_directions("hypersim").reshape(k["H"], k["W"], 3)
+    v, u = 100, 200
+    want = np.array([(u - k["cx"] + 0.5) / k["fx"], (v - k["cy"] + 0.5) / k["fy"], 1.0])
+    np.testing.assert_allclose(d[v, u], want / np.linalg.norm(want), rtol=1e-6)
+
+
 def test_grid_update_sampling_kernels():
     """ncn_grid_sample_cells / ncn_grid_scatter_density (models/ngp_mt.py:254-271, 345-357): index ranges, the second half
     hits occupied cells only and uniformly, every point lies inside its cell, the seed advances, the scatter writes exp(h0)."""

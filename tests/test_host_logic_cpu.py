@@ -40,3 +40,17 @@ def test_pixel_record_layout():
     assert torch.equal(rec[16 * R:].view(torch.float32).view(R, 3), rgb)
     rec32 = FusedStep.pack_pixel_batch(img.int(), pix.int(), rgb.double(), pin=False)       # other dtypes are converted, not reinterpreted
     assert torch.equal(rec32, rec)
+
+
+def test_get_rays_golden_is_self_consistent():
+    """tests/golden/get_rays_a.npz (the reference's own get_ray_directions + get_rays): rays_d = R d, rays_o = t, pixel-centre
+    directions - the contract ncn_rays_from_pixels and ncn_b200.synth.pixel_directions implement (GPU side: test_fused_gpu.py)"""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "get_rays_a.npz"))
+    c2w = g["poses"][g["img_idx"]]
+    np.testing.assert_allclose(np.einsum("nij,nj->ni", c2w[:, :, :3], g["directions"][g["pix_idx"]]), g["rays_d"], rtol=1e-6, atol=1e-7)
+    assert np.array_equal(c2w[:, :, 3], g["rays_o"])
+    K, H, W = g["K"], int(g["H"]), int(g["W"])
+    v, u = 7, 11
+    want = np.array([(u - K[0, 2] + 0.5) / K[0, 0], (v - K[1, 2] + 0.5) / K[1, 1], 1.0])
+    np.testing.assert_allclose(g["directions"].reshape(H, W, 3)[v, u], want / np.linalg.norm(want), rtol=1e-6)
