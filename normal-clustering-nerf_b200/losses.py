@@ -100,8 +100,8 @@ class NeRFMTLoss(nn.Module):
         unsup_start = gt_l if self.random_tr_poses else 0
         depth_u = pred["depth"][unsup_start:]
         x123 = None
-        if self.pred_norm_depth:
-            x123 = triangle_indices(depth_u.shape[0], self.ray_sampling_strategy, target, depth_u.device)
+        if self.ray_sampling_strategy in ("all_images_triang", "same_image_triang", "all_images_triang_patch", "same_image_triang_patch"):
+            x123 = triangle_indices(depth_u.shape[0], self.ray_sampling_strategy, target, depth_u.device)      # losses.py:317-331
         step = kwargs.get("global_step", 0)
         if self.reg_depth_w > 0 and step > self.can_sched_start and x123 is not None:
             r = (depth_u[x123["x1"]] - depth_u[x123["x2"]]) ** 2 + (depth_u[x123["x1"]] - depth_u[x123["x3"]]) ** 2

@@ -46,5 +46,24 @@ if __name__ == "__main__":
                     f"{case}_loss_total": float(loss_d["total"]),
                     f"{case}_grad_sem": (sem.grad if sem.grad is not None else torch.zeros_like(sem)).numpy(), f"{case}_grad_rgb": rgb.grad.numpy()})
         print(case, {k: float(v) for k, v in loss_d.items()}, "labelled", int((labels > 0).sum()))
+    # depth supervision + RegNeRF-style depth smoothness (losses.py:371-385, 411-417) on a triangle batch: off in the shipped
+    # experiments, carried by the module path
+    hp2 = dict(loss_opacity_w=1e-3, loss_depth_w=0.1, loss_reg_depth_w=0.05, loss_norm_can_start=500, pred_sem=False, pred_norm_nn=False,
+               pred_norm_depth=False, ray_sampling_strategy="all_images_triang", random_tr_poses=False)
+    torch.manual_seed(3)
+    R = 3 * 300
+    depth = (1.0 + torch.rand(R)).requires_grad_(True)
+    rgb = torch.rand(R, 3, requires_grad=True)
+    opacity = torch.rand(R).clamp(0.05, 0.99)
+    d_gt = 1.0 + torch.rand(R); d_gt[::7] = 0.0                       # 0 = no label
+    pred = {"rgb": rgb, "depth": depth, "opacity": opacity, "rays_o": torch.randn(R, 3), "rays_d": torch.randn(R, 3), "deltas": torch.zeros(1),
+            "ts": torch.zeros(1), "rays_a": torch.zeros(1, 3, dtype=torch.int64)}
+    target = {"rgb": torch.rand(R, 3), "depth": d_gt}
+    loss_d = ref_losses.NeRFMTLoss(hp2)(pred, target, global_step=3000)
+    loss_d["total"].backward()
+    out.update(depth_depth=depth.detach().numpy(), depth_rgb=rgb.detach().numpy(), depth_opacity=opacity.numpy(), depth_target_rgb=target["rgb"].numpy(),
+               depth_target_depth=d_gt.numpy(), depth_loss_depth=float(loss_d["depth"]), depth_loss_reg=float(loss_d["reg_depth"]),
+               depth_loss_total=float(loss_d["total"]), depth_grad_depth=depth.grad.numpy(), depth_w=hp2["loss_depth_w"], reg_w=hp2["loss_reg_depth_w"])
+    print("depth", {k: float(v) for k, v in loss_d.items()})
     out["sem_w"] = hp["loss_sem_w"]; out["opacity_w"] = hp["loss_opacity_w"]
     np.savez_compressed(os.path.join(ROOT, "tests", "golden", "sem_loss_a.npz"), **out)

@@ -114,3 +114,26 @@ def test_semantic_loss_module_path_matches_reference_golden():
         assert torch.isfinite(gs).all()                       # all-void batch: zero gradient, not 0 * NaN
         np.testing.assert_allclose(gs.numpy(), g[f"{case}_grad_sem"], rtol=1e-5, atol=1e-9)
         np.testing.assert_allclose(rgb.grad.numpy(), g[f"{case}_grad_rgb"], rtol=1e-5, atol=1e-9)
+
+
+def test_depth_and_reg_depth_terms_match_reference_golden():
+    """module-path NeRFMTLoss: depth supervision (labels 0 = none) and the RegNeRF-style depth smoothness on a triangle batch
+    (losses.py:371-385, 411-417 - the reference does NOT multiply the latter by its weight; reproduced) against the reference's
+    own losses.py (tests/golden/sem_loss_a.npz, case 'depth')"""
+    import os
+    import numpy as np
+    import torch
+    import ncn_b200  # noqa: F401
+    from ncn_b200.losses import NeRFMTLoss
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "sem_loss_a.npz"))
+    hp = dict(loss_opacity_w=float(g["opacity_w"]), loss_depth_w=float(g["depth_w"]), loss_reg_depth_w=float(g["reg_w"]), loss_norm_can_start=500,
+              pred_norm_depth=False, ray_sampling_strategy="all_images_triang")
+    depth = torch.from_numpy(g["depth_depth"]).requires_grad_(True)
+    pred = {"rgb": torch.from_numpy(g["depth_rgb"]), "depth": depth, "opacity": torch.from_numpy(g["depth_opacity"])}
+    target = {"rgb": torch.from_numpy(g["depth_target_rgb"]), "depth": torch.from_numpy(g["depth_target_depth"])}
+    loss_d = NeRFMTLoss(hp)(pred, target, global_step=3000)
+    loss_d["total"].backward()
+    np.testing.assert_allclose(float(loss_d["depth"]), float(g["depth_loss_depth"]), rtol=1e-6)
+    np.testing.assert_allclose(float(loss_d["reg_depth"]), float(g["depth_loss_reg"]), rtol=1e-6)
+    np.testing.assert_allclose(float(loss_d["total"]), float(g["depth_loss_total"]), rtol=1e-6)
+    np.testing.assert_allclose(depth.grad.numpy(), g["depth_grad_depth"], rtol=1e-5, atol=1e-9)
