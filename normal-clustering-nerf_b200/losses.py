@@ -54,6 +54,32 @@ def triangle_indices(n, strategy, target=None, device="cuda"):
     return {k: p[:, target[f"{k}_offsets_local"]].reshape(-1) for k in ("x1", "x2", "x3")}
 
 
+def canonical_axis_terms(normals, labels, tres):
+    """losses.py:480-498 (optional terms, weights 0 in every shipped experiment; module path only): the three normalised cluster
+    means c_k (negative labels flipped, losses.py:445-447) are compared with the six signed canonical axes; every (cluster, axis)
+    pair closer than 3*tres contributes 1 - c.a and |c - a|_1, averaged over the pairs.  Sync-free masked form of the reference's
+    nonzero() selection.  Returns (loss_can_dot, loss_can_l1, any_pair) - the reference adds the terms only when a pair exists."""
+    lab = labels.long()
+    k = lab.abs()
+    n = normals * torch.sign(lab).to(normals.dtype).unsqueeze(-1)
+    zero = torch.zeros_like(n)
+    c = []
+    for q in (1, 2, 3):
+        m = (k == q)
+        mean = torch.where(m.unsqueeze(-1), n, zero).sum(0, keepdim=True) / m.sum().clamp_min(1)
+        c.append(torch.nn.functional.normalize(mean, p=2.0, dim=-1))
+    c_mat = torch.vstack(c)
+    can_3 = torch.tensor([[1.0, 0.0, 0.0], [-1.0, 0.0, 0.0], [0.0, 1.0, 0.0], [0.0, -1.0, 0.0], [0.0, 0.0, 1.0], [0.0, 0.0, -1.0]],
+                         dtype=n.dtype, device=n.device)
+    sim = (c_mat.unsqueeze(1) * can_3.unsqueeze(0)).sum(-1)                    # (3, 6)
+    cond = (1.0 - sim) < tres * 3.0
+    w = cond.to(n.dtype)
+    cnt = cond.sum().clamp_min(1)
+    can_dot = 1.0 - (sim * w).sum() / cnt
+    can_l1 = ((c_mat.unsqueeze(1) - can_3.unsqueeze(0)).abs().sum(-1) * w).sum() / cnt
+    return can_dot, can_l1, cond.any()
+
+
 class NeRFMTLoss(nn.Module):
     def __init__(self, hparams_dict):
         super().__init__()
@@ -66,6 +92,8 @@ class NeRFMTLoss(nn.Module):
         self.w_ort = g("loss_norm_D_C_ort_dot_w", 0)
         self.w_dot = g("loss_norm_D_C_centr_dot_w", 0)
         self.w_l1 = g("loss_norm_D_C_centr_L1_w", 0)
+        self.w_can_dot = g("loss_norm_D_C_can_dot_w", 0)
+        self.w_can_l1 = g("loss_norm_D_C_can_L1_w", 0)
         self.ray_sampling_strategy = g("ray_sampling_strategy", None)
         self.random_tr_poses = g("random_tr_poses", False)
         self.pred_norm_depth = g("pred_norm_depth", False)
@@ -106,7 +134,8 @@ class NeRFMTLoss(nn.Module):
         if self.reg_depth_w > 0 and step > self.can_sched_start and x123 is not None:
             r = (depth_u[x123["x1"]] - depth_u[x123["x2"]]) ** 2 + (depth_u[x123["x1"]] - depth_u[x123["x3"]]) ** 2
             loss_d["reg_depth"] = _valid(r.mean())
-        if (self.w_ort > 0 or self.w_dot > 0 or self.w_l1 > 0) and (step <= self.can_sched_end or self.can_sched_end == -1):
+        if (self.w_ort > 0 or self.w_dot > 0 or self.w_l1 > 0 or self.w_can_dot > 0 or self.w_can_l1 > 0) and \
+                (step <= self.can_sched_end or self.can_sched_end == -1):
             normals = clustering.normals_from_depth(pred["rays_o"][unsup_start:], pred["rays_d"][unsup_start:], depth_u, x123)
             labels, _, _ = clustering.normals_clustering(normals, K=self.kmeans_k, niter=self.kmeans_niter,
                                                          t_similar=1.0 - self.norm_CAN_tres)
@@ -114,6 +143,11 @@ class NeRFMTLoss(nn.Module):
             loss_d["norm_D_C_ort_dot"] = _valid(self.w_sched(self.w_ort, step) * terms[0])
             loss_d["norm_D_C_centr_dot"] = _valid(self.w_sched(self.w_dot, step) * terms[1])
             loss_d["norm_D_C_centr_L1"] = _valid(self.w_sched(self.w_l1, step) * terms[2])
+            if self.w_can_dot > 0 or self.w_can_l1 > 0:
+                can_dot, can_l1, has = canonical_axis_terms(normals, labels, self.norm_CAN_tres)
+                zero = torch.zeros((), dtype=can_dot.dtype, device=can_dot.device)
+                loss_d["norm_D_C_can_dot"] = torch.where(has, _valid(self.w_sched(self.w_can_dot, step) * can_dot), zero)
+                loss_d["norm_D_C_can_L1"] = torch.where(has, _valid(self.w_sched(self.w_can_l1, step) * can_l1), zero)
             pred["norm_depth"] = normals
         if self.sem_w > 0 and "semantics" in target:
             # losses.py:240-242, 569-573: void class 0 -> -1 (ignored); mean over the labelled rays; NaN (none labelled) -> 0

@@ -137,3 +137,36 @@ def test_depth_and_reg_depth_terms_match_reference_golden():
     np.testing.assert_allclose(float(loss_d["reg_depth"]), float(g["depth_loss_reg"]), rtol=1e-6)
     np.testing.assert_allclose(float(loss_d["total"]), float(g["depth_loss_total"]), rtol=1e-6)
     np.testing.assert_allclose(depth.grad.numpy(), g["depth_grad_depth"], rtol=1e-5, atol=1e-9)
+
+
+def test_canonical_axis_terms_match_reference_golden():
+    """ncn_b200.losses.canonical_axis_terms (the optional terms of losses.py:480-502, sync-free masked form) downstream of the
+    reference's own cluster labels: values, and - together with the three cluster terms of the oracle - the gradient that
+    reaches the rendered depth (tests/golden/cluster_can_a.npz, generator oracle/gen_golden_can.py)"""
+    import os
+    import numpy as np
+    import torch
+    import ncn_b200  # noqa: F401
+    from ncn_b200.losses import canonical_axis_terms
+    from oracle import cluster_loss as cl
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "cluster_can_a.npz"))
+    rays_d = torch.from_numpy(g["rays_d"])
+    depth = torch.from_numpy(g["depth"]).requires_grad_(True)
+    x123 = {k: torch.from_numpy(g["tri"][i]) for i, k in enumerate(("x1", "x2", "x3"))}
+    normals = cl.normals_from_rays(rays_d, rays_d, depth, x123)
+    labels = torch.zeros(normals.shape[0], dtype=torch.int64)
+    labels[torch.from_numpy(g["valid"])] = torch.from_numpy(g["labels"])
+    can_dot, can_l1, has = canonical_axis_terms(normals, labels, float(g["tres"]))
+    assert bool(has)
+    np.testing.assert_allclose(float(g["w_can_dot"]) * float(can_dot), float(g["loss_can_dot"]), rtol=2e-5)
+    np.testing.assert_allclose(float(g["w_can_l1"]) * float(can_l1), float(g["loss_can_l1"]), rtol=2e-5)
+    ort, dot, l1 = cl.cluster_terms(normals, labels)
+    w = float(g["w_clu"])
+    np.testing.assert_allclose([w * float(ort), w * float(dot), w * float(l1)], [float(g["loss_ort"]), float(g["loss_dot"]), float(g["loss_l1"])], rtol=2e-5)
+    (float(g["w_can_dot"]) * can_dot + float(g["w_can_l1"]) * can_l1 + w * (ort + dot + l1)).backward()
+    np.testing.assert_allclose(depth.grad.numpy(), g["grad_depth"], rtol=2e-3, atol=2e-7)
+    # no cluster mean near an axis -> flag off (the reference then adds no term)
+    q, _ = torch.linalg.qr(torch.tensor([[1.0, 2.0, 3.0], [-2.0, 1.0, 0.5], [0.3, -1.0, 2.0]]))
+    n = q[:, [0, 1, 2]].T.repeat_interleave(5, 0)
+    lab = torch.tensor([1] * 5 + [2] * 5 + [3] * 5)
+    assert not bool(canonical_axis_terms(n, lab, 0.01)[2])
