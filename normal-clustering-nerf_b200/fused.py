@@ -46,7 +46,8 @@ class FusedStep:
         self.sem_off = 3 + (3 if m.pred_norm else 0)
         self.Ct = Ct = self.sem_off + self.n_cls
         self.sem_w = float(self.hp.get("loss_sem_w", 0.0)) if m.pred_sem else 0.0
-        for k in ("loss_norm_D_C_can_dot_w", "loss_norm_D_C_can_L1_w", "loss_depth_w", "loss_distortion_w", "loss_reg_depth_w"):
+        for k in ("loss_norm_D_C_can_dot_w", "loss_norm_D_C_can_L1_w", "loss_depth_w", "loss_distortion_w", "loss_reg_depth_w",
+                  "loss_norm_depth_L1_w", "loss_norm_depth_dot_w"):
             if float(self.hp.get(k, 0) or 0) > 0:
                 raise NotImplementedError(f"FusedStep: {k} > 0 is carried by the module path only (0 in every shipped experiment)")
         self.dev = dev = trainer.device

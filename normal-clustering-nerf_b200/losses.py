@@ -54,6 +54,19 @@ def triangle_indices(n, strategy, target=None, device="cuda"):
     return {k: p[:, target[f"{k}_offsets_local"]].reshape(-1) for k in ("x1", "x2", "x3")}
 
 
+def gt_normal_terms(norm_depth, nom_tar):
+    """losses.py:387-409 (optional GT-normal supervision of the depth-derived normals, weights 0 in the shipped experiments; module
+    path only): L1 = mean(sum|n - n_gt|), dot = mean(1 - cos(n, n_gt)) over the triangles whose GT normal is non-zero; sync-free
+    masked means.  Returns (L1, dot, any_valid)."""
+    valid = nom_tar.abs().sum(-1) > 0
+    cnt = valid.sum().clamp_min(1)
+    zero = torch.zeros((), dtype=norm_depth.dtype, device=norm_depth.device)
+    l1 = torch.where(valid, (norm_depth - nom_tar).abs().sum(-1), zero).sum() / cnt
+    cos = torch.nn.functional.cosine_similarity(norm_depth, nom_tar, dim=-1)          # eps 1e-8, as nn.CosineSimilarity
+    dot = torch.where(valid, 1.0 - cos, zero).sum() / cnt
+    return l1, dot, valid.any()
+
+
 def canonical_axis_terms(normals, labels, tres):
     """losses.py:480-498 (optional terms, weights 0 in every shipped experiment; module path only): the three normalised cluster
     means c_k (negative labels flipped, losses.py:445-447) are compared with the six signed canonical axes; every (cluster, axis)
@@ -92,6 +105,9 @@ class NeRFMTLoss(nn.Module):
         self.w_ort = g("loss_norm_D_C_ort_dot_w", 0)
         self.w_dot = g("loss_norm_D_C_centr_dot_w", 0)
         self.w_l1 = g("loss_norm_D_C_centr_L1_w", 0)
+        self.w_nd_l1 = g("loss_norm_depth_L1_w", 0)
+        self.w_nd_dot = g("loss_norm_depth_dot_w", 0)
+        self.norm_GT = "normals_depth" if g("loss_norm_GT_depth", False) else "normals"          # losses.py:193-199
         self.w_can_dot = g("loss_norm_D_C_can_dot_w", 0)
         self.w_can_l1 = g("loss_norm_D_C_can_L1_w", 0)
         self.ray_sampling_strategy = g("ray_sampling_strategy", None)
@@ -134,6 +150,16 @@ class NeRFMTLoss(nn.Module):
         if self.reg_depth_w > 0 and step > self.can_sched_start and x123 is not None:
             r = (depth_u[x123["x1"]] - depth_u[x123["x2"]]) ** 2 + (depth_u[x123["x1"]] - depth_u[x123["x3"]]) ** 2
             loss_d["reg_depth"] = _valid(r.mean())
+        if (self.w_nd_l1 > 0 or self.w_nd_dot > 0) and x123 is not None and self.norm_GT in target:
+            # GT-aligned set (identical to the unsupervised set unless random_tr_poses, losses.py:283-300)
+            x_gt = triangle_indices(gt_l, self.ray_sampling_strategy, target, depth_u.device) if unsup_start else x123
+            n_gt = clustering.normals_from_depth(pred["rays_o"][:gt_l], pred["rays_d"][:gt_l], pred["depth"][:gt_l], x_gt)
+            l1, dot, has = gt_normal_terms(n_gt, target[self.norm_GT][x_gt["x1"]])
+            zero = torch.zeros((), dtype=l1.dtype, device=l1.device)
+            if self.w_nd_l1 > 0:
+                loss_d["norm_D_L1"] = torch.where(has, _valid(self.w_nd_l1 * l1), zero)
+            if self.w_nd_dot > 0:
+                loss_d["norm_D_dot"] = torch.where(has, _valid(self.w_nd_dot * dot), zero)
         if (self.w_ort > 0 or self.w_dot > 0 or self.w_l1 > 0 or self.w_can_dot > 0 or self.w_can_l1 > 0) and \
                 (step <= self.can_sched_end or self.can_sched_end == -1):
             normals = clustering.normals_from_depth(pred["rays_o"][unsup_start:], pred["rays_d"][unsup_start:], depth_u, x123)

@@ -170,3 +170,26 @@ def test_canonical_axis_terms_match_reference_golden():
     n = q[:, [0, 1, 2]].T.repeat_interleave(5, 0)
     lab = torch.tensor([1] * 5 + [2] * 5 + [3] * 5)
     assert not bool(canonical_axis_terms(n, lab, 0.01)[2])
+
+
+def test_gt_normal_terms_match_reference_golden():
+    """ncn_b200.losses.gt_normal_terms (losses.py:387-409, masked sync-free form) on the oracle's depth-derived normals against
+    the reference's own losses.py (tests/golden/gt_normals_a.npz): both values and the gradient reaching the rendered depth"""
+    import os
+    import numpy as np
+    import torch
+    import ncn_b200  # noqa: F401
+    from ncn_b200.losses import gt_normal_terms, triangle_indices
+    from oracle import cluster_loss as cl
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "gt_normals_a.npz"))
+    rays_d = torch.from_numpy(g["rays_d"])
+    depth = torch.from_numpy(g["depth"]).requires_grad_(True)
+    x123 = triangle_indices(depth.shape[0], "all_images_triang", None, "cpu")
+    normals = cl.normals_from_rays(rays_d, rays_d, depth, x123)                 # rays_o := rays_d (rendering.py:227)
+    l1, dot, has = gt_normal_terms(normals, torch.from_numpy(g["normals_gt"])[x123["x1"]])
+    assert bool(has)
+    np.testing.assert_allclose(float(g["w_l1"]) * float(l1), float(g["loss_l1"]), rtol=1e-5)
+    np.testing.assert_allclose(float(g["w_dot"]) * float(dot), float(g["loss_dot"]), rtol=1e-5)
+    (float(g["w_l1"]) * l1 + float(g["w_dot"]) * dot).backward()
+    np.testing.assert_allclose(depth.grad.numpy(), g["grad_depth"], rtol=2e-3, atol=2e-7)
+    assert not bool(gt_normal_terms(normals.detach(), torch.zeros_like(normals))[2])
