@@ -144,28 +144,45 @@ class NGPMT(nn.Module):
         return cells
 
     @torch.no_grad()
-    def mark_invisible_cells(self, K, poses, img_wh, near_distance, chunk=64 ** 3):
-        """density -1 for cells no camera covers (ngp_mt.py:273-337; pinhole K (3,3) variant)."""
+    def mark_invisible_cells(self, K, dev, poses, img_wh, near_distance, chunk=64 ** 3):
+        """density -1 for the cells no camera covers, once before training (ngp_mt.py:273-337; same argument list, including the
+        `dev` the reference's caller passes, train_nerf.py:307-312).  K is either a (3,3) pinhole matrix or the Hypersim tuple
+        (M_ndc_from_cam (4,4), M_uv_from_ndc, shift, scale) of the tilt-shift camera model (ngp_mt.py:290-296, 314-321)."""
         N_cams = poses.shape[0]
         self.count_grid = torch.zeros_like(self.density_grid)
         w2c_R = poses[:, :3, :3].transpose(1, 2)
         w2c_T = -w2c_R @ poses[:, :3, 3:]
+        if isinstance(K, torch.Tensor):
+            K = K.to(dev)
+            project = None
+        elif isinstance(K, tuple):
+            M_ndc_from_cam, M_uv_from_ndc, scene_scale = K[0].to(dev), K[1].to(dev), K[3]
+            project = (M_ndc_from_cam, M_uv_from_ndc, scene_scale)
+        else:
+            raise AssertionError("mark_invisible_cells: K must be a (3,3) tensor or the Hypersim projection tuple")
         cells = self.get_all_cells()
         for c in range(self.cascades):
             indices, coords = cells[c]
+            s = min(2 ** (c - 1), self.scale)
+            half_grid_size = s / self.grid_size
             for i in range(0, len(indices), chunk):
-                xyzs = coords[i:i + chunk] / (self.grid_size - 1) * 2 - 1
-                s = min(2 ** (c - 1), self.scale)
-                half_grid_size = s / self.grid_size
-                xyzs_w = (xyzs * (s - half_grid_size)).T
-                xyzs_c = w2c_R @ xyzs_w + w2c_T
-                uvd = K @ xyzs_c
-                uv = uvd[:, :2] / uvd[:, 2:]
+                sl = slice(i, i + chunk)
+                xyzs_w = ((coords[sl] / (self.grid_size - 1) * 2 - 1) * (s - half_grid_size)).T            # (3, chunk)
+                xyzs_c = w2c_R @ xyzs_w + w2c_T                                                           # (N_cams, 3, chunk)
+                if project is None:
+                    uvd = K @ xyzs_c
+                    uv = uvd[:, :2] / uvd[:, 2:]
+                else:       # back to metric scale, homogeneous clip -> ndc -> uv (depth = the uv matrix's third row)
+                    xyzs_c *= 2 * project[2]
+                    xyzs_h = torch.cat((xyzs_c, torch.ones_like(xyzs_c)[:, :1, :]), 1)
+                    xyz_clip = project[0] @ xyzs_h
+                    uvd = project[1] @ (xyz_clip / xyz_clip[:, 3:])
+                    uv = uvd[:, :2]
                 in_image = (uvd[:, 2] >= 0) & (uv[:, 0] >= 0) & (uv[:, 0] < img_wh[0]) & (uv[:, 1] >= 0) & (uv[:, 1] < img_wh[1])
                 covered = (uvd[:, 2] >= near_distance) & in_image
-                self.count_grid[c, indices[i:i + chunk]] = count = covered.sum(0) / N_cams
+                self.count_grid[c, indices[sl]] = count = covered.sum(0) / N_cams
                 too_near = ((uvd[:, 2] < near_distance) & in_image).any(0)
-                self.density_grid[c, indices[i:i + chunk]] = torch.where((count > 0) & (~too_near), 0., -1.)
+                self.density_grid[c, indices[sl]] = torch.where((count > 0) & (~too_near), 0., -1.)
 
     @torch.no_grad()
     def update_density_grid(self, density_threshold, warmup=False, decay=0.95, erode=False):

@@ -13,6 +13,13 @@ because marching bit-exactness depends on the same FMA contraction.
 The reference's own build system (setup.py) is NOT run.  On a box without
 /root/reference (the GPU box) this script is a no-op: the prebuilt .so is used.
 
+The same route ships the reference's UNCHANGED Python hot-path files (models/{__init__,custom_functions,rendering,ngp_mt}.py,
+losses.py, datasets/hypersim_src/utils.py) into git-ignored ``oracle/_ref/py/`` (`stage_py`), so that the GPU box can run
+the reference's own render() / NGPMT / NeRFMTLoss on top of the drop-in shims (tests/test_reference_on_shims_gpu.py,
+bench.py's cpu_baseline leg).  The files are byte-for-byte copies made at build time, never committed; only the two package
+markers ``datasets/__init__.py`` / ``datasets/hypersim_src/__init__.py`` are written empty (the reference's datasets/__init__.py
+imports every dataset class and with them cv2 / h5py / kornia, none of which the hot path uses).
+
 Usage:  python oracle/build_ref.py [--force] [--ptx]
 """
 import os
@@ -55,6 +62,7 @@ def build(force=False, ptx=False, verbose=True):
         return os.path.exists(target())
     os.makedirs(OUT, exist_ok=True)
     os.makedirs(BUILD, exist_ok=True)
+    stage_py(verbose=False)
     srcs = [os.path.join(SRC, f) for f in CU + CPP]
     newest = max(os.path.getmtime(p) for p in srcs + [COMPAT, __file__])
     if not force and os.path.exists(target()) and os.path.getmtime(target()) >= newest:
@@ -106,6 +114,38 @@ def build(force=False, ptx=False, verbose=True):
     if verbose:
         print(f"[oracle/build_ref] built {target()}")
     return True
+
+
+PY_OUT = os.path.join(OUT, "py")
+PY_FILES = ["models/__init__.py", "models/custom_functions.py", "models/rendering.py", "models/ngp_mt.py", "losses.py",
+            "datasets/hypersim_src/utils.py"]
+PY_MARKERS = ["datasets/__init__.py", "datasets/hypersim_src/__init__.py"]
+
+
+def stage_py(verbose=True):
+    """byte-for-byte copies of the reference's hot-path Python files -> oracle/_ref/py/ (git-ignored, travels with gpurun)"""
+    import shutil
+    if not os.path.isdir(os.path.join(REF, "models")):
+        ok = all(os.path.exists(os.path.join(PY_OUT, f)) for f in PY_FILES)
+        if verbose:
+            print(f"[oracle/build_ref] {REF} not present: staged python files {'found' if ok else 'MISSING'} in {PY_OUT}")
+        return ok
+    for f in PY_FILES:
+        dst = os.path.join(PY_OUT, f)
+        os.makedirs(os.path.dirname(dst), exist_ok=True)
+        src = os.path.join(REF, f)
+        if not os.path.exists(dst) or open(src, "rb").read() != open(dst, "rb").read():
+            shutil.copyfile(src, dst)
+    for f in PY_MARKERS:
+        dst = os.path.join(PY_OUT, f)
+        os.makedirs(os.path.dirname(dst), exist_ok=True)
+        open(dst, "w").close()
+    return True
+
+
+def staged_py():
+    """path of the staged reference python tree, or None"""
+    return PY_OUT if all(os.path.exists(os.path.join(PY_OUT, f)) for f in PY_FILES) else None
 
 
 def load():

@@ -74,7 +74,13 @@ if __name__ == "__main__":
               loss_norm_D_C_centr_L1_w=2e-3, loss_norm_can_start=500, loss_norm_can_grow=2500, loss_norm_can_end=-1,
               ray_sampling_strategy="all_images_triang_patch", random_tr_poses=False, pred_norm_nn=False,
               pred_norm_depth=True)
-    for case, (n_rays, seed) in {"a": (1024, 0), "b": (2048, 3)}.items():
+    # case c = BASELINE.json config 1 (8192 rays -> 6272 normals): above 256*K = 5120 points the k-means trains on a sub-sample and
+    # assigns ALL points afterwards (faiss max_points_per_centroid) - the branch the small cases never reach
+    cases = {"a": (1024, 0), "b": (2048, 3), "c": (8192, 5)}
+    only = [a for a in sys.argv[1:] if a in cases]
+    for case, (n_rays, seed) in cases.items():
+        if only and case not in only:
+            continue
         torch.manual_seed(seed)
         b = synth.patch_batch(n_rays, seed=seed)
         rays_d = torch.from_numpy(b["rays_d"])

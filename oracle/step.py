@@ -9,7 +9,8 @@ the oracles in this package, in plain torch on the host cores:
     photometric + opacity + clustering    oracle/cluster_loss.py        (losses.py:347-361, 419-509)
     Adam                                  torch.optim.Adam-equivalent update (apex FusedAdam semantics)
 
-Used by bench.py as the CPU baseline (`cpu_baseline`, `--impl reference`) and by tests as the end-to-end checker.
+Used by bench.py as the CPU baseline (`cpu_baseline.port`, `--impl reference`) and by tests/test_step_oracle_gpu.py as the
+end-to-end checker of the GPU step (losses and per-group gradient norms on 512 rays).
 """
 import numpy as np
 import torch
@@ -43,8 +44,10 @@ class CpuField:
         return sigmas, rgbs
 
 
-def train_step(field, bitfield, rays_o, rays_d, target_rgb, tri, step=3000, hp=None, opt_state=None, lr=1e-2, noise=None):
-    """one CPU training step on numpy rays; returns (loss dict, n_samples)."""
+def train_step(field, bitfield, rays_o, rays_d, target_rgb, tri, step=3000, hp=None, opt_state=None, lr=1e-2, noise=None, centroids=None):
+    """one CPU training step on numpy rays; returns (loss dict, n_samples).  `centroids` (K,3): skip the k-means stand-in and
+    assign every valid normal to its most similar given centroid (what faiss' index.search does, losses.py:90) - lets a test
+    feed the centroids another engine found, so that everything downstream is compared on equal footing."""
     hp = hp or {}
     R = len(rays_o)
     hits = march.aabb(rays_o, rays_d, [0, 0, 0], [field.scale] * 3, hp.get("near", 0.01))
@@ -62,7 +65,11 @@ def train_step(field, bitfield, rays_o, rays_d, target_rgb, tri, step=3000, hp=N
     x123 = {k: t(tri[i]) for i, k in enumerate(("x1", "x2", "x3"))}
     normals = cluster_loss.normals_from_rays(rd, rd, depth, x123)
     valid = cluster_loss.valid_rows(normals.detach())
-    cent, assign = cluster_loss.spherical_kmeans(normals.detach()[valid].numpy(), 20, 20)
+    if centroids is None:
+        cent, assign = cluster_loss.spherical_kmeans(normals.detach()[valid].numpy(), 20, 20)
+    else:
+        cent = np.ascontiguousarray(centroids, dtype=np.float32)
+        assign = (normals.detach()[valid].numpy() @ cent.T).argmax(1).astype(np.int64)
     labels, _ = cluster_loss.select_clusters(t(assign), t(cent), 1.0 - 0.01)
     ort, dot, l1 = cluster_loss.cluster_terms(normals[valid], labels)
     w = max(0.0, min(2e-3, (step - 500) * (2e-3 / 2500)))
