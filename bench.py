@@ -34,7 +34,11 @@ def parse():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--rays", type=int, default=8192)
-    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-cpu-baseline", "--no-baselines", dest="no_cpu_baseline", action="store_true",
+                    help="skip the baseline legs that run after the timed regions (CPU reference losses.py / CPU port / reference csrc kernels and step on the GPU)")
+    ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4, 5],
+                    help="BASELINE.json config: 2 = the headline RGB+depth step (default), 3 = + semantic and normal heads, "
+                         "4 = full-image evaluation render (tools/eval_render.py), 5 = hash-grid sweep T=2^19..2^22 (tools/sweep_hashgrid.py)")
     ap.add_argument("--breakdown", default=None, help="write a per-call CUDA-event breakdown (json) to this path")
     ap.add_argument("--update-interval", type=int, default=None, help="occupancy-grid update period in steps (default: the reference's 16)")
     ap.add_argument("--fuse-fwd", default="mlp", choices=["none", "mlp", "all"], help="forward fusion of the fused step (A/B)")
@@ -126,6 +130,14 @@ def run_reference(args):
             "dtype": "f32", "data": "synthetic", "config": {"workload": WORKLOAD, "sample": sample, "samples_per_ray": spr},
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    line["config"]["same_config_as_gpu_arm"] = False      # a sub-batch of the 8192-ray step, CPU port of the step
+    try:        # BASELINE.md 3a / BASELINE.json config 1: the reference's OWN losses.py on the same host cores, in the same run
+        from tools import baselines
+        rl = baselines.ref_losses_cpu(reps=5)
+        if rl is not None:
+            line["reference_losses_py"] = {k: rl[k] for k in ("what", "config", "cores", "ms_fwd_bwd", "sub_ms", "rays_per_s", "normals_per_s")}
+    except Exception as e:  # noqa: BLE001
+        line["reference_losses_py"] = {"error": f"{type(e).__name__}: {e}"}
     print(json.dumps(line))
 
 
@@ -140,6 +152,12 @@ ALGO = {  # algorithmic bytes (or flops) per unit, SURVEY.md section 8d / DESIGN
     "ncn_mlp_fwd": ("hbm", "sample", 288.0),
     "ncn_field_mlp_fwd": ("hbm", "sample", 64 + 12 + 128 + 32 + 64 + 256 + 32 + 12 + 4.0),     # feat, dirs in; sig_acts, h, x_rgb, rgb_acts, rgb_out, raws, sigmas out
 }
+
+
+# kernels BASELINE.json's metric names explicitly ("composite/hashgrid GB/s vs HBM peak") + the other step kernels with an
+# algorithmic byte count: reported per launch in the line's "kernels" object
+KERNEL_REPORT = ("ncn_composite_train_fw", "ncn_composite_train_bw", "ncn_grid_fwd", "ncn_grid_bwd", "ncn_field_mlp_fwd",
+                 "ncn_mlp_bwd_src_fused", "ncn_adam_step_groups", "ncn_grad_sumsq")
 
 
 NOTES = {
@@ -179,7 +197,10 @@ def run_ours(args):
     tr.set_cameras(poses, dirs)
     if args.update_interval:
         tr.hp["update_interval"] = args.update_interval
-    tr.global_step = 3008          # steady state: clustering weights on, past the occupancy warm-up
+    # steady state: clustering weights on, past the occupancy warm-up.  The timed region STARTS on a grid-update step (3008 = 16 * 188),
+    # so it always contains ceil(K / 16) occupancy-grid updates whatever --steps is (never fewer than the reference's 1-in-16)
+    W_eff = max(args.warmup, 3)
+    tr.global_step = 3008 - W_eff
     # The occupancy-grid update (1 M-point density query + decay/max + packbits, every 16 steps) runs in full, but
     # with a RANDOM-INIT field it would flood the grid within a few updates and the samples/ray would drift with the
     # number of steps run.  To keep the synthetic room stationary the pre-update grid / bitfield are restored after
@@ -262,8 +283,11 @@ def run_ours(args):
             ms = float(t.item())
         return ms
 
-    for i in range(max(args.warmup, 3)):
+    fs.census = {}                      # count the nodes of the captured graphs (gpu_launches)
+    fs.update_grid(restore=restore)     # untimed: captures the grid-update graph (the warm-up steps below may not hit an update step)
+    for i in range(W_eff):
         step_resident(i)
+    assert tr.global_step == 3008
 
     if tr.peer is not None and tr.peer.error() != 0:
         raise RuntimeError("peer-memory exchange: a cross-GPU wait timed out during warm-up (ncn_peer_error)")
@@ -273,9 +297,12 @@ def run_ours(args):
     ms = timed(step_resident, args.steps)
     clk = clocks.stop()
     value = world * R * args.steps / (ms * 1e-3)
+    census = dict(fs.census)            # node counts of the graphs replayed in region 1 (region 2 re-captures with ray generation in front)
+    n_updates = sum(1 for q in range(args.steps) if (3008 + q) % tr.hp["update_interval"] == 0)
 
     # ---- timed region 2: end to end from pinned host buffers, loss read back every step
     fs.use_pixel_batches(True)
+    tr.global_step = 3008 - 2
     for i in range(2):
         step_e2e(i)
 
@@ -317,7 +344,16 @@ def run_ours(args):
     tr.hp["update_interval"] = saved_interval
     fs.use_graph = not args.no_graph
     fs.serial = False
-    launches = int(round(launches_per_step * args.steps))
+    # launches inside the timed region: from the replayed graphs' own kernel-node census when available (libncn kernels AND the few
+    # torch nodes - jitter, accumulator resets - that are captured with them), else from the eager pass's count of libncn kernels
+    own_per_step = launches_per_step
+    step_nodes = census.get("step")
+    if isinstance(step_nodes, list):
+        launches_per_step = float(step_nodes[0])
+        upd = census.get("grid_update")
+        launches = int(step_nodes[0] * args.steps + (upd[0] * n_updates if isinstance(upd, list) else 0))
+    else:
+        launches = int(round(launches_per_step * args.steps))
     # the dominant KERNEL = the longest single launch (a call name that launches twice per step is compared per launch)
     top = max((k for k in summ if k in ALGO), key=lambda k: summ[k][1] / max(summ[k][0], 1), default=None)
     top_stats = summ.get(top) if top else None
@@ -365,11 +401,47 @@ def run_ours(args):
                     "algorithmic_bytes_per_launch": per_unit * units,
                     "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"}
 
+    # per-kernel achieved bandwidth of the kernels BASELINE.json's metric names (composite, hash grid) and of the other step kernels
+    # with an algorithmic byte count: bytes per launch / CUDA-event time per launch (instrumented eager pass), against the measured peak
+    peaks_k = {}
+    try:
+        peaks_k = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:  # noqa: BLE001
+        pass
+    peak_k = float(peaks_k.get("hbm_gbs", 6650.0))
+    kernels = {}
+    for k in KERNEL_REPORT:
+        if k not in summ or k not in ALGO:
+            continue
+        calls, tot_ms = summ[k]
+        _, unit_of, per_unit = ALGO[k]
+        units = n_samples if unit_of == "sample" else tr.opt.grad.numel()
+        us = 1e3 * tot_ms / calls
+        gbs = per_unit * units / (us * 1e-6) / 1e9
+        kernels[k] = {"us_per_launch": us, "launches_per_step": calls / nprof, "algorithmic_bytes_per_launch": per_unit * units,
+                      "GB/s": gbs, "frac_of_hbm_peak": gbs / peak_k}
     cpu = None
+    gpu_ref = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        # --- baseline legs (after the timed regions; the oracle / reference here is the thing MEASURED AGAINST, never the product)
         v, cms, threads, spr = cpu_steps(512, 4, 1)
-        cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "ms_per_step": cms,
-               "sample": "512-ray sub-batch of the same step (oracle/step.py: C march + torch hash-grid/MLP/composite/loss/Adam), 4 steps after 1 warm-up"}
+        port = {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "ms_per_step": cms,
+                "sample": "512-ray sub-batch of the same step (oracle/step.py: C march + torch hash-grid/MLP/composite/loss/Adam), 4 steps after 1 warm-up"}
+        cpu = port
+        try:
+            from tools import baselines
+            rl = baselines.ref_losses_cpu()
+            if rl is not None:      # the reference's own losses.py on config 1, same host cores, same run
+                cpu = {"value": rl["rays_per_s"], "unit": "rays/s through losses.py (config 1)", "cores": rl["cores"], "kind": "reference",
+                       "sample": rl["config"] + "; median of %d fwd+bwd" % rl["reps"], "ms_fwd_bwd": rl["ms_fwd_bwd"], "sub_ms": rl["sub_ms"],
+                       "what": rl["what"], "port_full_step": port}
+            gpu_ref = {"csrc_kernels_us": baselines.ref_kernels_gpu(R), "step_reference_csrc": baselines.ref_step_gpu(R, 10, 3, "ref"),
+                       "step_reference_on_shims": baselines.ref_step_gpu(R, 10, 3, "shim")}
+            for k in ("step_reference_csrc", "step_reference_on_shims"):
+                if gpu_ref[k]:
+                    gpu_ref[k]["ours_over_it"] = (value / world) / gpu_ref[k]["rays_per_s"]
+        except Exception as e:  # noqa: BLE001  (a baseline leg must never take the product's line down)
+            gpu_ref = {"error": f"{type(e).__name__}: {e}"}
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -378,22 +450,38 @@ def run_ours(args):
                            "rays_per_step_per_gpu": R, "samples_per_step_per_gpu": n_samples,
                            "parallelism": f"dp{world}", "ranks_in_sync": ranks_in_sync,
                            "exchange": None if world == 1 else ("sharded reduce + Adam + fp16 publish over NVLink peer memory (ncn_peer_step)" if tr.peer is not None else "ncclAllReduce(fp32 flat gradient) + replicated Adam"), "path": "fused CUDA-graph step (ncn_b200.fused.FusedStep)" if not args.no_graph else "fused eager step",
-                           "occupancy": "synthetic room (13.6 % of 128^3 cells); grid update every 16 steps runs in full, its result is reverted to keep samples/ray stationary",
+                           "occupancy": "synthetic room (13.6 % of 128^3 cells); grid update every 16 steps runs in full (the timed region starts on an update step: ceil(K/16) updates inside), its result is reverted to keep samples/ray stationary",
                            "init": "random (tcnn-style U(-1e-4,1e-4) table, Xavier MLPs)",
                            "l2": "no explicit flush: per-step working set (fp32 params+grads+Adam m,v = 183 MB, + 22 MB fp16 table) exceeds the 126 MB L2"},
                 "clocks": clk, "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
                                        "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 32,
                                        "readback": "loss sums copied to pinned host memory every step; the host reads step i-1's loss while step i runs"},
-                "gpu_launches": launches, "gpu_launches_per_step": launches_per_step, "roofline": roofline, "cpu_baseline": cpu}
+                "gpu_launches": launches, "gpu_launches_per_step": launches_per_step,
+                "gpu_launch_census": {"graphs [kernel, memcpy, memset, other nodes]": census, "grid_updates_in_region": n_updates,
+                                      "libncn_kernels_per_step": own_per_step},
+                "kernels": kernels, "roofline": roofline, "cpu_baseline": cpu, "gpu_reference": gpu_ref}
         print(json.dumps(line))
     tr.comm.close()
     if world > 1:
         dist.destroy_process_group()
 
 
+def run_tool(args):
+    """configs 4 / 5: the evaluation render and the hash-grid sweep have their own drivers (same launch contract, one JSON line)"""
+    import runpy
+    tool, argv = {4: ("eval_render.py", ["--heads", "sem,norm", "--reps", str(max(3, min(args.steps, 10)))]),
+                  5: ("sweep_hashgrid.py", ["--reps", str(max(3, min(args.steps, 10)))])}[args.config]
+    sys.argv = [os.path.join(ROOT, "tools", tool)] + argv
+    runpy.run_path(sys.argv[0], run_name="__main__")
+
+
 if __name__ == "__main__":
     a = parse()
+    if a.config == 3 and not a.heads:
+        a.heads = "sem,norm"
     if a.impl == "reference":
         run_reference(a)
+    elif a.config in (4, 5):
+        run_tool(a)
     else:
         run_ours(a)

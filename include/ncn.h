@@ -54,6 +54,14 @@ const char* ncn_error_string(int code);
 int ncn_device_info(int* sm_count, int* cc_major, int* cc_minor);
 /* developer aid: slots[slot] = %globaltimer (ns) when `stream` reaches this point (works inside a captured graph) */
 int ncn_debug_stamp(uint64_t* slots, int slot, ncn_stream_t stream);
+/* measurement aid: node census of a captured CUDA graph (cudaGraph_t as void*): counts4_host = [kernel, memcpy, memset, other] */
+int ncn_graph_node_counts(void* cuda_graph, int* counts4_host);
+/* Sample-arena overflow guard of a sync-free step.  The reference allocates its sample arrays exactly after a host sync
+ * (raymarching.cu:302-305: counter -> torch::zeros({total_samples,...})); a step that keeps the count on the device marches into
+ * a fixed `capacity`.  counter (2) i32 as written by ncn_march_train; state (3) i32 = [this step overflowed, number of overflowed
+ * steps so far, largest sample count seen]; when counter[0] > capacity, poison[0] (the first gradient element, may be NULL) is set
+ * to NaN so that the optimizer's non-finite path skips the update everywhere (and zeroes the gradient). */
+int ncn_step_guard(const int32_t* counter, int64_t capacity, int32_t* state, float* poison, ncn_stream_t stream);
 
 /* ------------------------------------------------------------------------- */
 /* (1) ray / volume intersection          replaces vren.ray_aabb_intersect,  */
@@ -550,8 +558,12 @@ const char* ncn_comm_last_error(void);
  *            (world x 192 bytes, rank order).  world == 1 needs neither.
  *   step   : asynchronous on `stream`, graph-capturable; groups / lr_bc_dev / skip_dev / grad_div_dev as in
  *            ncn_adam_step_groups; sumsq_out_dev (optional) receives the squared norm of the averaged gradient.
- *            Every rank must call it the same number of times.  Cross-GPU waits are bounded (20 s) and set the error word
- *            (ncn_peer_error) instead of hanging. */
+ *            Every rank must call it the same number of times.  Cross-GPU waits are bounded (20 s by default,
+ *            ncn_peer_set_timeout) and FATAL for the exchange instead of hanging: the error word is latched, the step that
+ *            timed out and every later one are skipped on this rank (no Adam, nothing published, gradient zeroed), and a
+ *            time-out while waiting for the peers' gradients posts NaN as this rank's partial norm so the live peers skip the
+ *            step too.  ncn_peer_poll reads the word from mapped host memory WITHOUT synchronising (0 = ok, 1 + phase);
+ *            ncn_peer_error is the synchronising read. */
 typedef struct ncn_peer ncn_peer;
 int ncn_peer_create(ncn_peer** out, int rank, int world, int64_t n_params);
 float* ncn_peer_grad(ncn_peer* p);
@@ -563,6 +575,8 @@ int ncn_peer_step(ncn_peer* p, float* param, float* m, float* v, const ncn_adam_
                   float beta2, float eps, const float* grad_div_dev, const int32_t* skip_dev,
                   const float* lr_bc_dev, float* sumsq_out_dev, ncn_stream_t stream);
 int ncn_peer_error(ncn_peer* p, unsigned int* error_host);
+unsigned int ncn_peer_poll(ncn_peer* p);
+int ncn_peer_set_timeout(double seconds);
 int ncn_peer_destroy(ncn_peer* p);
 
 #ifdef __cplusplus

@@ -57,7 +57,8 @@ class Profiler:
                         "ncn_grid_desc_init": 0, "ncn_version": 0, "ncn_set_mlp_bwd_impl": 0, "ncn_set_march_segments": 0, "ncn_debug_stamp": 1, "ncn_set_grid_bwd_merge": 0, "ncn_set_grid_fwd_coherent": 0, "ncn_error_string": 0, "ncn_device_info": 0,
                         "ncn_comm_unique_id": 0, "ncn_comm_init": 0, "ncn_comm_destroy": 0, "ncn_comm_last_error": 0,
                         "ncn_sample_ray_batch": 2, "ncn_peer_create": 0, "ncn_peer_grad": 0, "ncn_peer_p16": 0, "ncn_peer_handles": 0, "ncn_peer_connect": 0,
-                        "ncn_peer_shard": 0, "ncn_peer_step": 2, "ncn_peer_error": 0, "ncn_peer_destroy": 0}
+                        "ncn_peer_shard": 0, "ncn_peer_step": 2, "ncn_peer_error": 0, "ncn_peer_destroy": 0,
+                        "ncn_peer_poll": 0, "ncn_peer_set_timeout": 0, "ncn_graph_node_counts": 0}
 
     @classmethod
     def reset(cls):
@@ -207,6 +208,8 @@ SIGNATURES.update({
     "ncn_adam_step": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_f32, c_f32, c_f32, c_f32, c_f32, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "ncn_adam_step_groups": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, C.POINTER(AdamGroups), c_f32, c_f32, c_f32, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "ncn_debug_stamp": (c_i32, [c_vp, c_i32, c_vp]),
+    "ncn_step_guard": (c_i32, [c_vp, c_i64, c_vp, c_vp, c_vp]),
+    "ncn_graph_node_counts": (c_i32, [c_vp, c_vp]),
     "ncn_grid_sample_cells": (c_i32, [c_vp, c_i32, c_i64, c_f32, c_vp, c_vp, c_vp, c_vp]),
     "ncn_grid_scatter_density": (c_i32, [c_vp, c_i32, c_vp, c_i64, c_vp, c_vp, c_vp]),
     "ncn_field_mlp_fwd": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
@@ -238,5 +241,7 @@ SIGNATURES.update({
     "ncn_peer_shard": (None, [c_i64, c_i32, c_i32, C.POINTER(c_i64), C.POINTER(c_i64)]),
     "ncn_peer_step": (c_i32, [c_vp, c_vp, c_vp, c_vp, C.POINTER(AdamGroups), c_f32, c_f32, c_f32, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "ncn_peer_error": (c_i32, [c_vp, C.POINTER(C.c_uint32)]),
+    "ncn_peer_poll": (C.c_uint32, [c_vp]),
+    "ncn_peer_set_timeout": (c_i32, [C.c_double]),
     "ncn_peer_destroy": (c_i32, [c_vp]),
 })

@@ -283,6 +283,7 @@ struct PeerPtrs {
   const float* grad[kPeerMax];
   __half* p16[kPeerMax];
   PeerSync* sync[kPeerMax];
+  unsigned int* err_host;               // this rank's error word in mapped pinned host memory (polled by the host without a sync)
 };
 
 __device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) {
@@ -300,15 +301,26 @@ __device__ __forceinline__ unsigned long long peer_now_ns() {
 }
 // one thread: wait until every rank's flag of `phase` reached `epoch` (bounded: 20 s - ranks enter a step within microseconds of
 // each other in steady state; the bound only has to survive start-up skew and must never turn a dead peer into a hung GPU)
-__device__ __forceinline__ void peer_wait(PeerSync* me, int phase, int world, unsigned int epoch) {
+// A timed-out wait is FATAL for the exchange: the error word is latched (device + host-mapped copy), the step that hit it and
+// every later step become skipped steps on this rank (no Adam, nothing published, gradient zeroed) and - when the time-out
+// happens in phase 0 - NaN is posted as this rank's partial norm so that the live peers skip the step as well.  The host polls
+// the mapped word on every step and raises (ncn_b200.fused / trainer), instead of training on with half-reduced gradients.
+__device__ unsigned long long g_peer_timeout_ns = 20000000000ull;
+__device__ __forceinline__ void peer_wait(PeerSync* me, int phase, int world, unsigned int epoch, unsigned int* err_host) {
   const unsigned long long t0 = peer_now_ns();
+  const unsigned long long limit = g_peer_timeout_ns;
   for (int q = 0; q < world; ++q) {
     while ((int)(ld_acquire_sys(&me->flag[phase][q]) - epoch) < 0) {
       __nanosleep(64);
-      if (peer_now_ns() - t0 > 20000000000ull) { atomicExch(&me->error, 1u + (unsigned)phase); return; }
+      if (peer_now_ns() - t0 > limit) {
+        atomicExch(&me->error, 1u + (unsigned)phase);
+        if (err_host != nullptr) { *reinterpret_cast<volatile unsigned int*>(err_host) = 1u + (unsigned)phase; __threadfence_system(); }
+        return;
+      }
     }
   }
 }
+__device__ __forceinline__ bool peer_failed(PeerSync* me) { return *reinterpret_cast<volatile unsigned int*>(&me->error) != 0u; }
 
 __global__ void __launch_bounds__(256, 2)
 peer_reduce_kernel(PeerPtrs pp, int rank, int world, int64_t lo4, int64_t hi4, float* my_grad /* == pp.grad[rank] */,
@@ -321,14 +333,14 @@ peer_reduce_kernel(PeerPtrs pp, int rank, int world, int64_t lo4, int64_t hi4, f
       __threadfence_system();
       for (int q = 0; q < world; ++q) st_release_sys(&pp.sync[q]->flag[0][rank], e);
     }
-    peer_wait(me, 0, world, e);
+    peer_wait(me, 0, world, e, pp.err_host);
     s_epoch = e;
   }
   __syncthreads();
   const unsigned int epoch = s_epoch;
   const float gmul = grad_div ? 1.f / *grad_div : 1.f;
   float acc = 0.f;
-  bool bad = false;
+  bool bad = peer_failed(me);                    // a peer never arrived: the sums below may be incomplete -> poison the norm
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i0 = lo4 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < hi4; i0 += 2 * stride) {
     const int64_t i1 = i0 + stride;
@@ -404,7 +416,7 @@ peer_adam_kernel(PeerPtrs pp, int rank, int world, int64_t lo4, int64_t hi4, int
   __shared__ float s_tot;
   if (threadIdx.x == 0) {
     const unsigned int e = *reinterpret_cast<volatile unsigned int*>(&me->epoch) + 1u;
-    peer_wait(me, 1, world, e);                // every rank's partial norm is here AND every rank is done reading my gradient
+    peer_wait(me, 1, world, e, pp.err_host);   // every rank's partial norm is here AND every rank is done reading my gradient
     float tot = 0.f;
     for (int q = 0; q < world; ++q) tot += *reinterpret_cast<volatile float*>(&me->norm[e & 1][q]);
     s_tot = tot; s_epoch = e;
@@ -414,7 +426,8 @@ peer_adam_kernel(PeerPtrs pp, int rank, int world, int64_t lo4, int64_t hi4, int
   const float total = s_tot;
   if (blockIdx.x == 0 && threadIdx.x == 0 && sumsq_out) *sumsq_out = total;
   if (lr_bc != nullptr) { a.lr = lr_bc[0]; a.bc1 = lr_bc[1]; a.bc2 = lr_bc[2]; }
-  const bool do_skip = (skip != nullptr && *skip != 0) || !isfinite(total);
+  // (the error word is read after the block-wide barrier above, i.e. after thread 0's own wait: uniform within the block)
+  const bool do_skip = (skip != nullptr && *skip != 0) || !isfinite(total) || peer_failed(me);
   float gmul = grad_div ? 1.f / *grad_div : 1.f;
   if (a.max_norm > 0.f) { const float c = a.max_norm / (sqrtf(total) + 1e-6f); gmul *= c < 1.f ? c : 1.f; }
   const float inv_bc1 = 1.f / a.bc1, inv_bc2 = 1.f / a.bc2;
@@ -451,7 +464,7 @@ peer_adam_kernel(PeerPtrs pp, int rank, int world, int64_t lo4, int64_t hi4, int
     me->ticket[1] = 0;
     __threadfence_system();
     for (int q = 0; q < world; ++q) st_release_sys(&pp.sync[q]->flag[2][rank], epoch);
-    peer_wait(me, 2, world, epoch);            // every shard of MY fp16 parameter buffer has been written by its owner
+    peer_wait(me, 2, world, epoch, pp.err_host);   // every shard of MY fp16 parameter buffer has been written by its owner
     *reinterpret_cast<volatile unsigned int*>(&me->epoch) = epoch;
     __threadfence();
   }
@@ -468,6 +481,7 @@ struct ncn_peer {
   ncn::PeerPtrs ptrs;
   void* opened[3][ncn::kPeerMax];
   bool connected;
+  unsigned int* err_host;               // cudaHostAllocMapped: written by the kernels on a time-out, read by ncn_peer_poll
 };
 
 extern "C" int ncn_peer_create(ncn_peer** out, int rank, int world, int64_t n_params) {
@@ -482,6 +496,9 @@ extern "C" int ncn_peer_create(ncn_peer** out, int rank, int world, int64_t n_pa
   NCN_CUDA(cudaMemset(p->grad, 0, (size_t)n_params * 4));
   NCN_CUDA(cudaMemset(p->p16, 0, (size_t)n_params * 2));
   NCN_CUDA(cudaMemset(p->sync, 0, sizeof(ncn::PeerSync)));
+  NCN_CUDA(cudaHostAlloc((void**)&p->err_host, sizeof(unsigned int), cudaHostAllocMapped));
+  *p->err_host = 0u;
+  { void* dptr = nullptr; NCN_CUDA(cudaHostGetDevicePointer(&dptr, p->err_host, 0)); p->ptrs.err_host = (unsigned int*)dptr; }
   NCN_CUDA(cudaDeviceSynchronize());
   for (int k = 0; k < 3; ++k) for (int q = 0; q < ncn::kPeerMax; ++q) p->opened[k][q] = nullptr;
   if (world == 1) {
@@ -563,9 +580,23 @@ extern "C" int ncn_peer_error(ncn_peer* p, unsigned int* error_host) {
   return NCN_OK;
 }
 
+// the error word WITHOUT a device synchronisation (host-mapped copy): 0 = ok, 1 + phase of the wait that timed out
+extern "C" unsigned int ncn_peer_poll(ncn_peer* p) {
+  return p && p->err_host ? *reinterpret_cast<volatile unsigned int*>(p->err_host) : 0u;
+}
+
+// bound of every cross-GPU wait in seconds (default 20; applies to all ncn_peer objects of the process)
+extern "C" int ncn_peer_set_timeout(double seconds) {
+  NCN_CHECK_SIZE(seconds > 0.0 && seconds < 3600.0);
+  const unsigned long long ns = (unsigned long long)(seconds * 1e9);
+  NCN_CUDA(cudaMemcpyToSymbol(ncn::g_peer_timeout_ns, &ns, sizeof(ns)));
+  return NCN_OK;
+}
+
 extern "C" int ncn_peer_destroy(ncn_peer* p) {
   if (!p) return NCN_OK;
   cudaDeviceSynchronize();
+  if (p->err_host) cudaFreeHost(p->err_host);
   for (int k = 0; k < 3; ++k) for (int q = 0; q < ncn::kPeerMax; ++q) if (p->opened[k][q]) cudaIpcCloseMemHandle(p->opened[k][q]);
   cudaFree(p->grad); cudaFree(p->p16); cudaFree(p->sync);
   delete p;

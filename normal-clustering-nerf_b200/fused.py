@@ -33,7 +33,7 @@ GSCALE = 131072.0      # 2^17: loss scale carried by the fp16 dL/dy tensors (the
 
 
 class FusedStep:
-    def __init__(self, trainer, capacity_per_ray=64, use_graph=True, fuse_fwd="mlp"):
+    def __init__(self, trainer, capacity_per_ray=None, use_graph=True, fuse_fwd="mlp"):
         self.tr = trainer
         self.model = m = trainer.model
         self.opt = trainer.opt
@@ -52,11 +52,10 @@ class FusedStep:
                 raise NotImplementedError(f"FusedStep: {k} > 0 is carried by the module path only (0 in every shipped experiment)")
         self.dev = dev = trainer.device
         self.R = R = self.hp["batch_size"]
-        self.cap = cap = int(R * capacity_per_ray)
         self.use_graph = use_graph
         self.graph = None
         self.L = _lib.lib()
-        f32 = dict(dtype=torch.float32, device=dev); f16 = dict(dtype=torch.float16, device=dev)
+        f32 = dict(dtype=torch.float32, device=dev)
         E = lambda *s, **k: torch.empty(*s, **k)
         # static inputs: ONE (3,R,3) buffer [rays_o | rays_d | target rgb] so a step needs a single input copy
         self.inp = E(3, R, 3, **f32)
@@ -72,43 +71,34 @@ class FusedStep:
         self.counter = torch.zeros(2, dtype=torch.int32, device=dev)
         ws_bytes = self.L.ncn_march_train_workspace_bytes(R, self.hp["rend_max_samples"])
         self.march_ws = E(ws_bytes, dtype=torch.uint8, device=dev)
-        self.xyzs, self.dirs = torch.zeros(cap, 3, **f32), torch.zeros(cap, 3, **f32)
-        self.deltas, self.ts = torch.zeros(cap, **f32), torch.zeros(cap, **f32)
-        # field
-        self.feat, self.h = E(cap, 32, **f16), E(cap, 16, **f16)
-        cap_t = (cap + 127) // 128 * 128                         # saved activations: whole 128-row tiles (ncn_mlp_acts_bytes)
-        self.sig_acts = E(1, cap_t, 64, **f16)
-        self.x_rgb, self.rgb_out, self.rgb_acts = E(cap, 32, **f16), E(cap, 16, **f16), E(2, cap_t, 64, **f16)
-        self.sigmas, self.raws = E(cap, **f32), E(cap, Ct, **f32)
-        # compositing + loss
+        # sample arena.  The reference sizes its sample arrays exactly after a host sync (raymarching.cu:302-305, worst case
+        # N_rays * max_samples right after the warm-up grid); this step never syncs, so the arena has a fixed capacity:
+        #   capacity_per_ray=None  -> the worst case (max_samples per ray: overflow is impossible) whenever that costs < 30 % of the
+        #                             device memory (12 GB for 8192 rays on a 180 GB B200), else 64 per ray
+        #   an explicit number     -> that many rows per ray.
+        # Whenever capacity < worst case the step is GUARDED: ncn_step_guard turns a step whose march overflowed into a skipped
+        # step on the device (never a silently truncated one) and the host, polling a pinned copy of the guard state without a
+        # sync, regrows the arena and re-captures the graph (single rank; a multi-rank job raises - size it for the worst case).
+        worst = int(self.hp["rend_max_samples"])
+        if capacity_per_ray is None:
+            total_mem = torch.cuda.get_device_properties(dev).total_memory
+            capacity_per_ray = worst if R * worst * self._row_bytes() <= 0.30 * total_mem else 64
+        self.cap_max = R * worst
+        self.guard = torch.zeros(3, dtype=torch.int32, device=dev)           # [overflowed, n overflowed steps, max samples seen]
+        self.guard_host = torch.zeros(3, dtype=torch.int32).pin_memory()
+        self.ovf_seen = 0
         self.total_samples = E(R, dtype=torch.int64, device=dev)
-        self.opacity, self.depth, self.rend, self.ws = E(R, **f32), E(R, **f32), E(R, Ct, **f32), E(cap, **f32)
+        self.opacity, self.depth, self.rend = E(R, **f32), E(R, **f32), E(R, Ct, **f32)
         self.rgb = E(R, 3, **f32)
         self.zeros = torch.zeros(8, **f32)          # [0:2] photometric sums, [2] grad sumsq, [3] non-finite flag (as int bits), [4:6] CE sum, valid rays
         self.d_rend, self.d_opacity, self.d_depth = E(R, Ct, **f32), E(R, **f32), torch.zeros(R, **f32)
         self.losses, self.stats, self.weights = E(3, **f32), E(32, **f32), torch.zeros(3, **f32)
-        self.d_sigmas, self.d_raws = E(cap, **f32), E(cap, Ct, **f32)
-        self.dout_rgb, self.dx_rgb, self.dh, self.dfeat = E(cap, 16, **f16), E(cap, 32, **f16), E(cap, 16, **f16), E(cap, 32, **f16)
-        nb = max(self.L.ncn_mlp_bwd_workspace_bytes(C.byref(m.rgb_net.desc), cap),
-                 self.L.ncn_mlp_bwd_workspace_bytes(C.byref(m.sigma_net.desc), cap))
-        # extra heads on h (ngp_mt.py:217-224).  The reference puts no loss on the rendered norm_nn channels (losses.py only
-        # slices them, :279/:294), so norm_net gets an exactly-zero gradient: its backward is not launched.
-        if m.pred_norm:
-            self.norm_out = E(cap, 16, **f16)
         if m.pred_sem:
-            self.sem_out, self.sem_acts, self.dh_sem = E(cap, 16, **f16), E(2, cap_t, 64, **f16), E(cap, 16, **f16)
-            self.sem_dout = E(cap, 16, **f16) if self.n_cls > 3 else None
             self.sem_target = torch.zeros(R, dtype=torch.int64, device=dev)      # labels in [0, n_cls], 0 = void
-            nb = max(nb, self.L.ncn_mlp_bwd_workspace_bytes(C.byref(m.sem_net.desc), cap))
-        self.mlp_ws = E(nb, dtype=torch.uint8, device=dev)
-        self.mlp_ws2 = E(nb, dtype=torch.uint8, device=dev)      # the colour-head backward runs concurrently on a side stream
         # False: encoder, density trunk, glue, colour head, glue (5 launches); "mlp": encoder + ONE launch for both MLPs; True: ONE
         # launch for everything.  The fused kernels build x_rgb / dx_rgb in the [h | d | 1] column order (ncn_mlp_bwd_src.perm)
         self.fuse_fwd = fuse_fwd
-        self.src_rgb = _lib.MlpBwdSrc(1, ptr(self.d_raws), Ct, 0, 3, None, None, None, 1.0, 1 if fuse_fwd else 0)
-        self.src_sig = _lib.MlpBwdSrc(2, None, 0, 0, 0, ptr(self.dx_rgb), ptr(self.d_sigmas), ptr(self.h), 1.0, 2 if fuse_fwd else 0,
-                                      ptr(self.dh_sem) if m.pred_sem else None)
-        self.src_sem = _lib.MlpBwdSrc(1, ptr(self.d_raws), Ct, self.sem_off, self.n_cls, None, None, None, 1.0, 0) if m.pred_sem else None
+        self._alloc_arena(min(int(R * capacity_per_ray), self.cap_max))
         self.side_stream = torch.cuda.Stream(device=dev)
         self.ev_fork, self.ev_join = torch.cuda.Event(), torch.cuda.Event()
         # fp16 parameter copies (owned by the optimizer, refreshed by its Adam kernel each step)
@@ -154,6 +144,89 @@ class FusedStep:
         self.km_params = _lib.KmeansParams(20, 20, 1234, 256, 1)
         self._offsets()
         self._alloc_tri(None)
+
+    def _row_bytes(self):
+        """bytes of arena per sample row (all per-sample buffers of _alloc_arena)"""
+        m = self.model
+        Ct = self.Ct
+        b = 12 + 12 + 4 + 4                      # xyzs, dirs, deltas, ts
+        b += 64 + 32 + 128 + 64 + 32 + 256       # feat, h, sig_acts, x_rgb, rgb_out, rgb_acts
+        b += 4 + 4 * Ct + 4                      # sigmas, raws, ws
+        b += 4 + 4 * Ct + 32 + 64 + 32 + 64      # d_sigmas, d_raws, dout_rgb, dx_rgb, dh, dfeat
+        b += 2 * (16 + 2 * 64) * 2               # two MLP-backward workspaces
+        if m.pred_norm:
+            b += 32
+        if m.pred_sem:
+            b += 32 + 256 + 32 + 32
+        return b
+
+    def _alloc_arena(self, cap):
+        """every per-sample buffer of the step, for `cap` rows (called once, and again by _regrow)"""
+        m, dev, Ct, R = self.model, self.dev, self.Ct, self.R
+        self.cap = cap = int(cap)
+        f32 = dict(dtype=torch.float32, device=dev); f16 = dict(dtype=torch.float16, device=dev)
+        E = lambda *s, **k: torch.empty(*s, **k)
+        self.xyzs, self.dirs = torch.zeros(cap, 3, **f32), torch.zeros(cap, 3, **f32)
+        self.deltas, self.ts = torch.zeros(cap, **f32), torch.zeros(cap, **f32)
+        # field
+        self.feat, self.h = E(cap, 32, **f16), E(cap, 16, **f16)
+        cap_t = (cap + 127) // 128 * 128                         # saved activations: whole 128-row tiles (ncn_mlp_acts_bytes)
+        self.sig_acts = E(1, cap_t, 64, **f16)
+        self.x_rgb, self.rgb_out, self.rgb_acts = E(cap, 32, **f16), E(cap, 16, **f16), E(2, cap_t, 64, **f16)
+        self.sigmas, self.raws = E(cap, **f32), E(cap, Ct, **f32)
+        self.ws = E(cap, **f32)
+        self.d_sigmas, self.d_raws = E(cap, **f32), E(cap, Ct, **f32)
+        self.dout_rgb, self.dx_rgb, self.dh, self.dfeat = E(cap, 16, **f16), E(cap, 32, **f16), E(cap, 16, **f16), E(cap, 32, **f16)
+        nb = max(self.L.ncn_mlp_bwd_workspace_bytes(C.byref(m.rgb_net.desc), cap),
+                 self.L.ncn_mlp_bwd_workspace_bytes(C.byref(m.sigma_net.desc), cap))
+        # extra heads on h (ngp_mt.py:217-224).  The reference puts no loss on the rendered norm_nn channels (losses.py only
+        # slices them, :279/:294), so norm_net gets an exactly-zero gradient: its backward is not launched.
+        if m.pred_norm:
+            self.norm_out = E(cap, 16, **f16)
+        if m.pred_sem:
+            self.sem_out, self.sem_acts, self.dh_sem = E(cap, 16, **f16), E(2, cap_t, 64, **f16), E(cap, 16, **f16)
+            self.sem_dout = E(cap, 16, **f16) if self.n_cls > 3 else None
+            nb = max(nb, self.L.ncn_mlp_bwd_workspace_bytes(C.byref(m.sem_net.desc), cap))
+        self.mlp_ws = E(nb, dtype=torch.uint8, device=dev)
+        self.mlp_ws2 = E(nb, dtype=torch.uint8, device=dev)      # the colour-head backward runs concurrently on a side stream
+        fuse_fwd = self.fuse_fwd
+        self.src_rgb = _lib.MlpBwdSrc(1, ptr(self.d_raws), Ct, 0, 3, None, None, None, 1.0, 1 if fuse_fwd else 0)
+        self.src_sig = _lib.MlpBwdSrc(2, None, 0, 0, 0, ptr(self.dx_rgb), ptr(self.d_sigmas), ptr(self.h), 1.0, 2 if fuse_fwd else 0,
+                                      ptr(self.dh_sem) if m.pred_sem else None)
+        self.src_sem = _lib.MlpBwdSrc(1, ptr(self.d_raws), Ct, self.sem_off, self.n_cls, None, None, None, 1.0, 0) if m.pred_sem else None
+        self.graph = None
+        self.grid_graph = None
+
+    def _regrow(self, need):
+        """the march produced `need` > capacity samples (those steps were skipped on the device): grow and re-capture"""
+        import warnings
+        if self.tr.world_size > 1:
+            raise RuntimeError(f"FusedStep: the march produced {need} samples for an arena of {self.cap} rows on rank {self.tr.rank}; the "
+                               "overflowed steps were skipped on every rank.  A multi-rank job cannot re-capture on one rank alone: "
+                               "construct it with capacity_per_ray=rend_max_samples (the default when it fits in memory)")
+        new_cap = min(self.cap_max, max(2 * self.cap, (int(need * 1.25) + 1023) // 1024 * 1024))
+        warnings.warn(f"FusedStep: sample arena overflow ({need} samples > capacity {self.cap}); {int(self.guard_host[1])} step(s) were skipped. "
+                      f"Growing the arena to {new_cap} rows and re-capturing the step graph.")
+        self.flush()
+        torch.cuda.synchronize()
+        self._alloc_arena(new_cap)
+
+    def _poll(self):
+        """host-side, sync-free health check before a step: peer-exchange time-outs are fatal, arena overflows regrow"""
+        if self.peer is not None and self.peer.poll():
+            raise RuntimeError(f"peer-memory gradient exchange: a cross-GPU wait timed out (phase {self.peer.poll() - 1}) on rank "
+                               f"{self.tr.rank}; the replicated parameters are no longer trustworthy - restart from a checkpoint")
+        n_ovf = int(self.guard_host[1])
+        if n_ovf > self.ovf_seen:
+            self.ovf_seen = n_ovf
+            if int(self.guard_host[2]) > self.cap:
+                self._regrow(int(self.guard_host[2]))
+
+    @property
+    def overflow_steps(self):
+        """number of steps skipped because the march overflowed the arena (synchronises)"""
+        torch.cuda.synchronize()
+        return int(self.guard[1])
 
     def _offsets(self):
         """slices of the flat parameter / gradient buffers per module (hash table first: FlatAdam order)"""
@@ -315,6 +388,9 @@ class FusedStep:
                                    ptr(self.sig_acts), cap, ptr(self._g32("sigma_net")), ptr(self.dfeat), inv, ptr(self.mlp_ws),
                                    self.mlp_ws.numel(), n_dev, st), "sigma_bwd")
         ck(L.ncn_grid_bwd(C.byref(enc.desc), ptr(self.xyzs), ptr(self.dfeat), cap, ptr(self._g32("xyz_encoder")), inv, self.xform, n_dev, st), "grid_bwd")
+        if cap < self.cap_max:          # overflow is possible: a truncated step must become a skipped step, never a silent one
+            ck(L.ncn_step_guard(n_dev, cap, ptr(self.guard), ptr(self.opt.grad), st), "step_guard")
+            self.guard_host.copy_(self.guard, non_blocking=True)       # pinned: the host polls it without synchronising
 
     def _optimizer(self, sched_off=0):
         """sum of squares -> clip coefficient -> fused Adam (both parameter groups); sched_off selects the schedule slot
@@ -412,6 +488,7 @@ class FusedStep:
         rays_o/rays_d/target_rgb (R,3) each, or `packed` (3,R,3) = [rays_o, rays_d, rgb] (one copy), or nothing when the
         caller filled self.inp in place (e.g. rays_from_pixels)."""
         tr = self.tr
+        self._poll()
         if packed is not None:
             self.inp.copy_(packed)
         elif rays_o is not None:
@@ -423,8 +500,16 @@ class FusedStep:
             self.graph = None                 # noise source is part of the captured sequence
         if noise is not None:
             self.noise.copy_(noise)
-        for mod in self._flat_mods:           # parameters written from outside (load_state_dict, tests): refresh the fp16 working copy
-            if mod.params._version != mod._flat_version:
+        stale = [mod for mod in self._flat_mods if mod.params._version != mod._flat_version]
+        if stale:                             # parameters written from outside (load_state_dict, tests): refresh the fp16 working copy
+            if tr.master_stale:
+                # sharded optimizer: outside this rank's slice the fp32 master is stale - rebuild it from the owners before it
+                # overwrites the (correct) fp16 copy.  Collective: replicated parameters must be written on every rank alike.
+                keep = {id(mod): mod.params.detach().clone() for mod in stale}
+                tr.gather_master_params()
+                for mod in stale:             # the caller's write wins inside the written tensors (same write on every rank)
+                    mod.params.data.copy_(keep[id(mod)])
+            for mod in stale:
                 mod._half.copy_(mod.params.detach())
                 mod._flat_version = mod.params._version
         self._schedule()
@@ -465,25 +550,50 @@ class FusedStep:
             if multi:
                 tr.comm.allreduce_sum_(self.opt.grad)
                 self.graph[1].replay()
+        if self.peer is not None and tr.world_size > 1:
+            tr.master_stale = True
         tr.global_step += 1
+
+    def _new_graph(self):
+        if getattr(self, "census", None) is not None:      # bench.py: keep the cudaGraph_t to count its nodes
+            try:
+                return torch.cuda.CUDAGraph(keep_graph=True)
+            except TypeError:
+                pass
+        return torch.cuda.CUDAGraph()
+
+    def _census(self, name, g):
+        """node counts [kernel, memcpy, memset, other] of a captured graph into self.census[name] (only when self.census is a dict)"""
+        if getattr(self, "census", None) is None or not hasattr(g, "raw_cuda_graph"):
+            return
+        try:
+            raw = g.raw_cuda_graph()
+            c = (C.c_int * 4)()
+            check(self.L.ncn_graph_node_counts(C.c_void_p(int(raw)), c), "graph_node_counts")
+            self.census[name] = list(c)
+            g.instantiate()
+        except Exception as e:  # noqa: BLE001  (beta API: a failed census must not break the step)
+            self.census[name] = f"unavailable: {type(e).__name__}: {e}"
 
     def _capture_multi(self):
         self.opt.grad.zero_()
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
-        keep = (self.opt.flat.clone(), self.opt.m.clone(), self.opt.v.clone(), self.flat16.clone())
+        keep = (self.opt.flat.clone(), self.opt.m.clone(), self.opt.v.clone(), self.flat16.clone(), self.guard.clone())
         with torch.cuda.stream(s):
             self._run()
             self._optimizer()
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
+        self.guard.copy_(keep[4]); self.guard_host.copy_(self.guard)      # the warm-up pass is not a step: undo its guard record
         self.opt.flat.copy_(keep[0]); self.opt.m.copy_(keep[1]); self.opt.v.copy_(keep[2]); self.flat16.copy_(keep[3])
         self.opt.grad.zero_()
         graphs = []
-        for fn in (self._run_march, lambda: self._optimizer(sched_off=6), self._run_field):
-            g = torch.cuda.CUDAGraph()
+        for name, fn in (("march", self._run_march), ("optimizer", lambda: self._optimizer(sched_off=6)), ("field", self._run_field)):
+            g = self._new_graph()
             with torch.cuda.graph(g):
                 fn()
+            self._census(name, g)
             graphs.append(g)
         self.graph = tuple(graphs)
 
@@ -627,11 +737,12 @@ class FusedStep:
                 self._update_grid_impl(thr)
             torch.cuda.current_stream().wait_stream(s)
             torch.cuda.synchronize()
-            g = torch.cuda.CUDAGraph()
+            g = self._new_graph()
             with torch.cuda.graph(g):
                 self._update_grid_impl(thr)
                 if restore is not None:
                     self.model.density_grid.copy_(restore[0]); self.model.density_bitfield.copy_(restore[1])
+            self._census("grid_update", g)
             self.grid_graph = g
         self.grid_graph.replay()
 
@@ -644,31 +755,35 @@ class FusedStep:
         self.opt.grad.zero_()
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
-        keep = (self.opt.flat.clone(), self.opt.m.clone(), self.opt.v.clone(), self.flat16.clone())
+        keep = (self.opt.flat.clone(), self.opt.m.clone(), self.opt.v.clone(), self.flat16.clone(), self.guard.clone())
         with torch.cuda.stream(s):
             self._run()
             self._optimizer()
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
+        self.guard.copy_(keep[4]); self.guard_host.copy_(self.guard)      # the warm-up pass is not a step: undo its guard record
         # undo the warm-up update
         self.opt.flat.copy_(keep[0]); self.opt.m.copy_(keep[1]); self.opt.v.copy_(keep[2]); self.flat16.copy_(keep[3])
         self.opt.grad.zero_()
         if self.defer:
-            g0 = torch.cuda.CUDAGraph()
+            g0 = self._new_graph()
             with torch.cuda.graph(g0):
                 self._run_deferred(multi)
+            self._census("step", g0)
             self.graph = (g0, None)
             return
-        g0 = torch.cuda.CUDAGraph()
+        g0 = self._new_graph()
         with torch.cuda.graph(g0):
             self._run()
             if not multi:
                 self._optimizer()
+        self._census("step", g0)
         g1 = None
         if multi:
-            g1 = torch.cuda.CUDAGraph()
+            g1 = self._new_graph()
             with torch.cuda.graph(g1):
                 self._optimizer()
+            self._census("optimizer", g1)
         self.graph = (g0, g1)
 
     def stats_host(self):

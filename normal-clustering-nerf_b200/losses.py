@@ -13,6 +13,9 @@ the hot path, with the same constructor (a hyper-parameter dict), the same ``for
 Reference quirks that are reproduced: normals use ``pred['rays_o']`` which rendering.py:227 sets to the ray
 DIRECTIONS; the distortion term is evaluated on ``ts`` in place of ``ws`` (losses.py:290); clustering runs from
 step 0 even while its schedule weight is 0; an empty cluster zeroes all three cluster terms.
+One logging-only difference: the reference adds the keys norm_D_C_can_dot / norm_D_C_can_L1 whenever a cluster centre happens to lie
+within 3*tres of a canonical axis (losses.py:491-502, decided by a host-side `.any()`), with value w_sched(0)*loss = 0 in every
+shipped configuration; this sync-free mirror emits those keys only when their weights are non-zero.
 """
 import torch
 from torch import nn

@@ -130,6 +130,10 @@ class PeerLink:
         check(_lib.lib().ncn_peer_step(self.handle, ptr(flat), ptr(m), ptr(v), C.byref(groups), betas[0], betas[1], eps, ptr(grad_div),
                                        ptr(flag), ptr(lr_bc), ptr(sumsq_out), st), "peer_step")
 
+    def poll(self):
+        """error word from mapped host memory, no device synchronisation (0 = ok, 1 + phase of the wait that timed out)"""
+        return int(_lib.lib().ncn_peer_poll(self.handle)) if self.handle is not None else 0
+
     def error(self):
         e = C.c_uint32()
         check(_lib.lib().ncn_peer_error(self.handle, C.byref(e)), "peer_error")
@@ -256,6 +260,11 @@ class NeRFTrainer:
             self.opt = mk(False)
         self.peer = self.opt.peer
         self.opt.adopt_half_copies(self.model)
+        # sharded optimizer on W > 1 ranks: the fp32 master / m / v outside this rank's slice go stale with the first step.
+        # state_dict() (checkpoints) rebuilds them from their owners first - a collective, like the checkpoint itself.
+        self.master_stale = False
+        if self.peer is not None and world_size > 1:
+            self.model.register_state_dict_pre_hook(lambda *a, **k: self.gather_master_params())
         self.global_step = 0
         self.fused = None
         self.render_kwargs = dict(near_distance=hp["rend_near_dist"], max_samples=hp["rend_max_samples"],
@@ -286,6 +295,7 @@ class NeRFTrainer:
         import torch.distributed as dist
         if self.fused is not None:
             self.fused.flush()
+        self.master_stale = False
         L = _lib.lib()
         for q in range(self.world_size):
             lo, hi = C.c_int64(), C.c_int64()
@@ -321,12 +331,13 @@ class NeRFTrainer:
         loss_d = self.loss(results, target, global_step=self.global_step)
         return results, loss_d
 
-    def fused_step(self, capacity_per_ray=64, use_graph=True, fuse_fwd="mlp"):
-        """the sync-free CUDA-graph step (ncn_b200.fused.FusedStep)"""
+    def fused_step(self, capacity_per_ray=None, use_graph=True, fuse_fwd="mlp"):
+        """the sync-free CUDA-graph step (ncn_b200.fused.FusedStep).  It carries its own gradient divisor (its gradients are
+        already un-scaled); FlatAdam's divisor (loss_scale * world_size) stays what the module path's train_step needs, so the
+        two paths can be mixed on one trainer."""
         if self.fused is None:
             from .fused import FusedStep
             self.fused = FusedStep(self, capacity_per_ray=capacity_per_ray, use_graph=use_graph, fuse_fwd=fuse_fwd)
-            self.opt.grad_div.fill_(float(self.world_size))     # fused gradients are already un-scaled
         return self.fused
 
     def train_step_fused(self, rays_o=None, rays_d=None, target_rgb=None, tri=None, update_grid=True, noise=None, packed=None,
@@ -351,6 +362,8 @@ class NeRFTrainer:
         self.train_step_fused(update_grid=update_grid, grid_restore=grid_restore)
 
     def train_step(self, rays_o, rays_d, target, update_grid=True):
+        if self.fused is not None:
+            self.fused.flush()                    # a deferred fused update must land before this path reads the parameters
         if update_grid:
             self.maybe_update_grid()
         results, loss_d = self.forward_loss(rays_o, rays_d, target)
@@ -358,5 +371,7 @@ class NeRFTrainer:
         if self.peer is None:
             self.comm.allreduce_sum_(self.opt.grad)
         self.opt.step(self.lr_now())
+        if self.peer is not None and self.world_size > 1:
+            self.master_stale = True
         self.global_step += 1
         return results, loss_d

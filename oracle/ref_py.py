@@ -75,11 +75,13 @@ def _cpu_faiss():
     return {"faiss": faiss, "faiss.contrib": contrib, "faiss.contrib.torch_utils": tu}
 
 
-def load(faiss="shim", want_models=True):
+def load(faiss="shim", want_models=True, vren="shim"):
     """returns a namespace with .rendering, .ngp_mt, .custom_functions (want_models) and .losses, .hypersim_utils:
     the reference's own modules.  faiss="shim": k-means = libncn's GPU kernel through ncn_b200/shims/faiss (what a user of
-    the drop-in gets); faiss="cpu": numpy stand-in, and `vren` an inert stub unless the shims were requested via want_models."""
-    key = (faiss, want_models)
+    the drop-in gets); faiss="cpu": numpy stand-in, and `vren` an inert stub unless the shims were requested via want_models.
+    vren="ref": the reference's models bind to the reference's OWN csrc kernels (oracle/_ref/vren_ref.so) instead of libncn -
+    the GPU reference baseline of BASELINE.md section 3b (tiny-cuda-nn stays the shim: its source is not available)."""
+    key = (faiss, want_models, vren)
     if key in _CACHE:
         return _CACHE[key]
     py = staged_dir()
@@ -99,6 +101,12 @@ def load(faiss="shim", want_models=True):
         injected.update(_cpu_faiss())
         if not want_models:
             injected["vren"] = _stub("vren")
+    if vren == "ref":
+        import build_ref
+        mod = build_ref.load()
+        if mod is None:
+            return None
+        injected["vren"] = mod
     sys.modules.update(injected)
     path_before = list(sys.path)
     if want_models or faiss == "shim":

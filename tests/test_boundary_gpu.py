@@ -25,7 +25,7 @@ def _ref_aabb_near(vren_ref, rays_o, rays_d, center, half_size, near):
     return hits_t
 
 
-def _camera_sets(scene, n=4096):
+def _camera_sets(scene, near, n=4096):
     """rays with origins inside the box, outside it, on a face, and within `near` of the entry face"""
     from ncn_b200 import synth
     dev = scene["dev"]
@@ -51,7 +51,7 @@ def _camera_sets(scene, n=4096):
     # closer to the entry face than `near`: t1 in (0, near) must be lifted to `near`, t1 == 0 too, t1 > near must not move
     o = torch.zeros(n, 3, device=dev)
     d = torch.zeros(n, 3, device=dev); d[:, 0] = 1.0
-    o[:, 0] = -0.5 - torch.linspace(0.0, 0.03, n, device=dev)             # entry distance 0 .. 0.03 around near = 0.01
+    o[:, 0] = -0.5 - torch.linspace(0.0, 3.0 * max(near, 0.01), n, device=dev)   # entry distance 0 .. 3 near: both sides of the clamp
     o[:, 1:] = (torch.rand(n, 2, device=dev, generator=g) - 0.5) * 0.8
     sets["near_band"] = (o.contiguous(), d.contiguous())
     return sets
@@ -60,7 +60,7 @@ def _camera_sets(scene, n=4096):
 @pytest.mark.parametrize("near", [0.01, 0.05, 0.0])
 def test_aabb_near_clamp_matches_reference_kernel_plus_reference_clamp(ncn, vren_ref, scene, near):
     from ncn_b200.rendering import ray_aabb_near
-    for name, (rays_o, rays_d) in _camera_sets(scene).items():
+    for name, (rays_o, rays_d) in _camera_sets(scene, near).items():
         ours = ray_aabb_near(rays_o, rays_d, scene["center"], scene["half_size"], near)
         ref = _ref_aabb_near(vren_ref, rays_o, rays_d, scene["center"], scene["half_size"], near)
         assert ours.shape == ref.shape == (rays_o.shape[0], 1, 2), name

@@ -86,6 +86,9 @@ def _rel(a, b):
     return float((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30))
 
 
+LOSS_SCALE = 1024.0     # what the AMP GradScaler of the reference's Trainer(precision=16) does; without it fp16 dL/dy underflows
+
+
 def _ref_forward_backward(ref, rm, hp, rays_o, rays_d, target, kwargs, step, seed=123):
     loss_fn = ref.losses.NeRFMTLoss(hp)
     torch.manual_seed(seed)
@@ -94,8 +97,8 @@ def _ref_forward_backward(ref, rm, hp, rays_o, rays_d, target, kwargs, step, see
         loss_d = loss_fn(results, target, global_step=step)
     for p in rm.parameters():
         p.grad = None
-    loss_d["total"].backward()
-    grads = {k: (p.grad.detach().clone() if p.grad is not None else torch.zeros_like(p)) for k, p in rm.named_parameters()}
+    (loss_d["total"] * LOSS_SCALE).backward()
+    grads = {k: (p.grad.detach().clone() / LOSS_SCALE if p.grad is not None else torch.zeros_like(p)) for k, p in rm.named_parameters()}
     return results, loss_d, grads
 
 
@@ -132,8 +135,13 @@ def test_reference_render_and_loss_on_shims_equal_the_mirrors(ref, R, heads):
         torch.testing.assert_close(res_r[k].detach().float(), res_o[k].detach().float(), rtol=1e-5, atol=1e-6, msg=lambda m, k=k: f"{k}: {m}")
     assert torch.equal(res_r["rays_o"], res_r["rays_d"]) and torch.equal(res_o["rays_o"], res_o["rays_d"])      # rendering.py:227
     # losses: the reference's selection / merge / opposite / loss code vs the libncn kernels
-    assert set(loss_r) == set(loss_o), (sorted(loss_r), sorted(loss_o))
-    for k in loss_r:
+    # (the reference also emits norm_D_C_can_dot / norm_D_C_can_L1 whenever a cluster centre happens to lie near a canonical axis,
+    #  losses.py:491-502 - a data-dependent key whose value is w_sched(0) * loss = 0 in every shipped configuration; the sync-free
+    #  mirror emits those keys only when their weights are non-zero)
+    extra = set(loss_r) - set(loss_o)
+    assert extra <= {"norm_D_C_can_dot", "norm_D_C_can_L1"} and all(float(loss_r[k]) == 0.0 for k in extra), extra
+    assert set(loss_o) <= set(loss_r), (sorted(loss_r), sorted(loss_o))
+    for k in loss_o:
         a, b = float(loss_r[k]), float(loss_o[k])
         assert abs(a - b) <= 1e-3 * abs(a) + 1e-8, (k, a, b)
     for k in ("norm_D_C_ort_dot", "norm_D_C_centr_dot", "norm_D_C_centr_L1"):
@@ -188,11 +196,11 @@ def _thr(tr):
     return 0.01 * hp["rend_max_samples"] / 3 ** 0.5 * hp["density_tresh_decay"]
 
 
-@pytest.mark.parametrize("table_std", [0.3, 2.0])
+@pytest.mark.parametrize("table_std", [0.3, 4.0])
 def test_update_density_grid_warmup_reference_vs_mirror(ref, table_std):
     """warm-up branch (ngp_mt.py:341-342, all G^3 cells): same cells, same torch RNG -> same jittered positions -> the mirror's
     fused decay/max + packbits must reproduce the reference's torch.where / mean().item() / packbits.  table_std 0.3 leaves the
-    mean density below the threshold (packbits threshold = the mean), 2.0 above it (threshold = density_threshold)."""
+    mean density below the threshold (packbits threshold = the mean), 4.0 above it (threshold = density_threshold)."""
     tr = _trainer(1024, table_std=table_std)
     rm = _ref_model(ref, tr)
     g = torch.Generator(device="cuda").manual_seed(9)
@@ -202,7 +210,8 @@ def test_update_density_grid_warmup_reference_vs_mirror(ref, table_std):
     for rounds in range(2):
         tr.model.density_grid.copy_(start); rm.density_grid.copy_(start)
         torch.manual_seed(77 + rounds)
-        rm.update_density_grid(thr, warmup=True)
+        with torch.autocast("cuda", dtype=torch.float16):      # Lightning runs training_step under AMP (train_nerf.py precision=16):
+            rm.update_density_grid(thr, warmup=True)          # the reference's TruncExp only returns fp32 under autocast (custom_fwd)
         torch.manual_seed(77 + rounds)
         tr.model.update_density_grid(thr, warmup=True)
         torch.cuda.synchronize()
@@ -280,7 +289,8 @@ def test_update_density_grid_steady_reference_vs_mirror_vs_fused(ref):
     out = {}
     rm.density_grid.copy_(start)
     torch.manual_seed(3)
-    rm.update_density_grid(thr, warmup=False)
+    with torch.autocast("cuda", dtype=torch.float16):
+        rm.update_density_grid(thr, warmup=False)
     out["reference"] = (rm.density_grid.clone(), rm.density_bitfield.clone())
     tr.model.density_grid.copy_(start)
     torch.manual_seed(3)
