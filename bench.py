@@ -146,6 +146,7 @@ ALGO = {  # algorithmic bytes (or flops) per unit, SURVEY.md section 8d / DESIGN
     "ncn_grid_fwd": ("hbm", "sample", 588.0), "ncn_grid_bwd": ("hbm", "sample", 12 + 64 + 1024.0),
     "ncn_adam_step": ("hbm", "param", 34.0), "ncn_adam_step_groups": ("hbm", "param", 34.0), "ncn_grad_sumsq": ("hbm", "param", 4.0),
     "ncn_composite_train_fw": ("hbm", "sample", 28.0), "ncn_composite_train_bw": ("hbm", "sample", 48.0),
+    "ncn_composite_train_fw_photometric": ("hbm", "sample", 28.0),      # + 56 B/ray of loss terms (negligible against 28 B x 33 samples)
     "ncn_march_train_expand": ("hbm", "sample", 36.0),
     # tcgen05 MLP backward, two launches per step (colour head 448 B/sample, density trunk 288 B/sample): average per launch
     "ncn_mlp_bwd_src_fused": ("hbm", "sample", 368.0), "ncn_mlp_bwd": ("hbm", "sample", 368.0),
@@ -156,7 +157,7 @@ ALGO = {  # algorithmic bytes (or flops) per unit, SURVEY.md section 8d / DESIGN
 
 # kernels BASELINE.json's metric names explicitly ("composite/hashgrid GB/s vs HBM peak") + the other step kernels with an
 # algorithmic byte count: reported per launch in the line's "kernels" object
-KERNEL_REPORT = ("ncn_composite_train_fw", "ncn_composite_train_bw", "ncn_grid_fwd", "ncn_grid_bwd", "ncn_field_mlp_fwd",
+KERNEL_REPORT = ("ncn_composite_train_fw", "ncn_composite_train_fw_photometric", "ncn_composite_train_bw", "ncn_grid_fwd", "ncn_grid_bwd", "ncn_field_mlp_fwd",
                  "ncn_mlp_bwd_src_fused", "ncn_adam_step_groups", "ncn_grad_sumsq")
 
 

@@ -182,6 +182,9 @@ int ncn_march_test(const float* rays_o, const float* rays_d, float* hits_t,
 /*     composite_train_bw/_multi_bw, composite_test_fw/_multi_fw              */
 /*     (binding.cpp:134-298, volumerendering.cu:16-585)                       */
 /* ------------------------------------------------------------------------- */
+/* developer A/B knob: lanes per ray of the training compositing kernels (4, 8, 16 [default]: sub-warp kernels for C = 3/6/9;
+ * 32: one warp per ray).  Returns the previous value.  Results are identical for T / ws / total_samples in every mode. */
+int ncn_set_composite_width(int lanes_per_ray);
 /* sigmas (N), raws (N,C), deltas, ts (N) f32, rays_a (R,3) i64.
  * out: total_samples (R) i64, opacity, depth (R), rend (R,C), ws (N); all are
  * fully written for the rays_a rows given (rays with 0 samples get zeros; ws
@@ -193,6 +196,16 @@ int ncn_composite_train_fw(const float* sigmas, const float* raws, const float* 
                            int64_t n_rays, int64_t capacity, int n_channels,
                            int64_t* total_samples, float* opacity, float* depth, float* rend,
                            float* ws, ncn_stream_t stream);
+/* ncn_composite_train_fw + ncn_photometric_loss in ONE launch (C = 3, 6 or 9; NCN_E_UNSUPPORTED otherwise): the lane holding a
+ * ray's final sums also evaluates rgb = rend[:3] + bg (1 - opacity) (models/rendering.py:231-241), the squared error against
+ * target_rgb (losses.py:353) and the opacity entropy term (losses.py:357-361) and writes their gradients; arguments as in the two
+ * separate calls.  sums[0] += sum sq err, sums[1] += sum entropy. */
+int ncn_composite_train_fw_photometric(const float* sigmas, const float* raws, const float* deltas, const float* ts,
+                                       const int64_t* rays_a, float T_threshold, int64_t n_rays, int64_t capacity,
+                                       int n_channels, int64_t* total_samples, float* opacity, float* depth, float* rend,
+                                       float* ws, const float* target_rgb, const float* bg_rgb_host, float opacity_w,
+                                       float grad_scale, float* rgb_out, float* sums, float* dL_drend, float* dL_dopacity,
+                                       ncn_stream_t stream);
 /* out: dL_dsigmas (N), dL_draws (N,C) fully written for the samples the rays_a rows
  * cover.  dL_dopacity / dL_ddepth / dL_drend / dL_dws may each be NULL (= zeros).
  * Either output pointer (not both) may be NULL to skip it: dL_draws depends on dL_drend only, so a caller
@@ -574,8 +587,13 @@ void ncn_peer_shard(int64_t n_params, int rank, int world, int64_t* lo, int64_t*
 int ncn_peer_step(ncn_peer* p, float* param, float* m, float* v, const ncn_adam_groups* groups, float beta1,
                   float beta2, float eps, const float* grad_div_dev, const int32_t* skip_dev,
                   const float* lr_bc_dev, float* sumsq_out_dev, ncn_stream_t stream);
+/* on = 1: ncn_peer_step no longer zeroes the gradient buffer outside its own slice; the caller zeroes the WHOLE buffer after the step
+ * (any stream, any time before the next backward) - takes the 4 B/param memset off the exchange's critical path */
+int ncn_peer_set_external_zero(ncn_peer* p, int on);
 int ncn_peer_error(ncn_peer* p, unsigned int* error_host);
 unsigned int ncn_peer_poll(ncn_peer* p);
+/* developer timeline of the last step (synchronises): 8 x ns = [K1 start, wait-0 over, K1 reduced, K2 start, wait-1 over, Adam+publish done, wait-2 over, -] */
+int ncn_peer_debug_times(ncn_peer* p, unsigned long long* times8_host);
 int ncn_peer_set_timeout(double seconds);
 int ncn_peer_destroy(ncn_peer* p);
 

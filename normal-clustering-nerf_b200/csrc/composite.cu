@@ -335,6 +335,262 @@ composite_train_bw_ct_kernel(const float* __restrict__ dL_dopacity, const float*
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Sub-warp kernels (default): W lanes (W = 4, 8, 16) own a ray, so a warp composites 32/W rays at once.  At the training
+// regime of ~30 samples per ray a whole warp per ray spends most of its issue slots on the 32-step transmittance replay
+// of a mostly empty second chunk (728 warp instructions per ray measured); with W = 8 the replay is 8 steps shared by four
+// rays, the chunk granularity follows the ray lengths, and the ray sums are kept as per-lane partials that are reduced ONCE
+// at the end of the ray instead of five warp reductions per chunk.  The transmittance product is still replayed in the
+// reference's sequential order (T, ws, total_samples bit-exact); the ray sums differ from the reference's sequential sums by
+// fp32 rounding only (tolerance in tests/).
+template <int W>
+__device__ __forceinline__ float subwarp_sum(float v) {
+#pragma unroll
+  for (int o = W / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+template <int W>
+__device__ __forceinline__ float subwarp_scan_incl(float v, int sl) {
+#pragma unroll
+  for (int o = 1; o < W; o <<= 1) {
+    const float t = __shfl_up_sync(0xffffffffu, v, o, W);
+    if (sl >= o) v += t;
+  }
+  return v;
+}
+// W-step replay inside every sub-warp of the warp at once (see replay_transmittance)
+template <int W>
+__device__ __forceinline__ int subwarp_replay(float om, float thr, float& T, float& T_before, int sl) {
+  int stop = -1;
+  T_before = T;
+#pragma unroll
+  for (int j = 0; j < W; ++j) {
+    const float omj = __shfl_sync(0xffffffffu, om, j, W);
+    if (sl == j) T_before = T;
+    T = __fmul_rn(T, omj);
+    if (stop < 0 && T <= thr) stop = j;
+  }
+  return stop;
+}
+
+// Photometric epilogue of the fused form (ncn_composite_train_fw_photometric): the lane that holds a ray's final sums evaluates
+// rgb = rend[:3] + bg (1 - opacity), the squared error against the target colour and the opacity entropy term, and writes
+// dL/drend, dL/dopacity (losses.py:347-361, models/rendering.py:231-241) - the separate loss launch and its dependent
+// round trip through memory leave the step's critical path.  Same arithmetic as photometric_kernel (loss.cu).
+struct PhotoArgs {
+  const float* target;      // (R,3)
+  float bg[3];
+  float opacity_w, gscale, inv3n, invn;
+  float* rgb_out;           // (R,3) or null
+  float* sums;              // [0] += sum sq err, [1] += sum entropy
+  float* d_rend;            // (R,CT) or null
+  float* d_opacity;         // (R) or null
+};
+
+template <int CT, int W, bool PHOTO>
+__global__ void __launch_bounds__(256)
+composite_train_fw_sw_kernel(const float* __restrict__ sigmas, const float* __restrict__ raws,
+                             const float* __restrict__ deltas, const float* __restrict__ ts,
+                             const int64_t* __restrict__ rays_a, float thr, int64_t n_rays, int64_t capacity,
+                             int64_t* __restrict__ total_samples, float* __restrict__ opacity,
+                             float* __restrict__ depth, float* __restrict__ rend, float* __restrict__ ws, PhotoArgs ph) {
+  constexpr int RPW = 32 / W;
+  float ph_se = 0.f, ph_ent = 0.f;
+  const int lane = threadIdx.x & 31, sub = lane / W, sl = lane % W;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t n0 = warp * RPW; n0 < n_rays; n0 += n_warps * RPW) {
+    const int64_t n = n0 + sub;
+    const bool have = n < n_rays;
+    int64_t ray_idx = 0, start = 0, N64 = 0;
+    if (have) { ray_idx = rays_a[3 * n]; start = rays_a[3 * n + 1]; N64 = rays_a[3 * n + 2]; }
+    if (start + N64 > capacity) N64 = capacity > start ? capacity - start : 0;
+    const int N = (int)N64;
+    const int N_max = __reduce_max_sync(0xffffffffu, N);
+    float T = 1.0f, acc_o = 0.f, acc_d = 0.f, acc_r[CT];
+#pragma unroll
+    for (int c = 0; c < CT; ++c) acc_r[c] = 0.f;
+    int samples = N;
+    bool dead = false;
+    float sg = 0.f, dl = 0.f, tt = 0.f, rw[CT];
+    auto fetch = [&](int base, float& o_sg, float& o_dl, float& o_tt, float (&o_rw)[CT]) {
+      const int k = base + sl;
+      o_sg = 0.f; o_dl = 0.f; o_tt = 0.f;
+#pragma unroll
+      for (int c = 0; c < CT; ++c) o_rw[c] = 0.f;
+      if (k < N) {
+        const int64_t s = start + k;
+        o_sg = sigmas[s]; o_dl = deltas[s]; o_tt = ts[s];
+#pragma unroll
+        for (int c = 0; c < CT; ++c) o_rw[c] = raws[s * CT + c];
+      }
+    };
+    fetch(0, sg, dl, tt, rw);
+    for (int base = 0; base < N_max; base += W) {
+      const int k = base + sl;
+      const int64_t s = start + k;
+      float n_sg, n_dl, n_tt, n_rw[CT];
+      fetch(base + W, n_sg, n_dl, n_tt, n_rw);
+      const float a = k < N ? __fsub_rn(1.0f, __expf(__fmul_rn(-sg, dl))) : 0.f;
+      float T_before;
+      const int stop = subwarp_replay<W>(__fsub_rn(1.0f, a), thr, T, T_before, sl);
+      const bool active = (k < N) && !dead && (stop < 0 || sl <= stop);
+      const float w = active ? __fmul_rn(a, T_before) : 0.f;
+      if (k < N) ws[s] = w;
+      acc_o += w;
+      acc_d += w * tt;
+#pragma unroll
+      for (int c = 0; c < CT; ++c) acc_r[c] += w * rw[c];
+      if (!dead && stop >= 0) { samples = base + stop; dead = true; }
+      sg = n_sg; dl = n_dl; tt = n_tt;
+#pragma unroll
+      for (int c = 0; c < CT; ++c) rw[c] = n_rw[c];
+    }
+    acc_o = subwarp_sum<W>(acc_o); acc_d = subwarp_sum<W>(acc_d);
+#pragma unroll
+    for (int c = 0; c < CT; ++c) acc_r[c] = subwarp_sum<W>(acc_r[c]);
+    if (have && sl == 0) {
+      total_samples[ray_idx] = samples; opacity[ray_idx] = acc_o; depth[ray_idx] = acc_d;
+#pragma unroll
+      for (int c = 0; c < CT; ++c) rend[ray_idx * CT + c] = acc_r[c];
+      if (PHOTO) {
+        float go = 0.f;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const float v = acc_r[c] + ph.bg[c] * (1.f - acc_o);
+          if (ph.rgb_out) ph.rgb_out[3 * ray_idx + c] = v;
+          const float e = v - ph.target[3 * ray_idx + c];
+          ph_se += e * e;
+          const float g = 2.f * e * ph.inv3n * ph.gscale;
+          if (ph.d_rend) ph.d_rend[ray_idx * CT + c] = g;
+          go -= ph.bg[c] * g;
+        }
+        if (ph.d_rend) {
+#pragma unroll
+          for (int c = 3; c < CT; ++c) ph.d_rend[ray_idx * CT + c] = 0.f;
+        }
+        if (ph.opacity_w > 0.f) {
+          const float oe = acc_o + 1e-10f;
+          const float lg = logf(oe);
+          ph_ent += -oe * lg;
+          go += ph.opacity_w * (-(lg + 1.f)) * ph.invn * ph.gscale;
+        }
+        if (ph.d_opacity) ph.d_opacity[ray_idx] = go;
+      }
+    }
+  }
+  if (PHOTO) {
+    ph_se = warp_sum(ph_se); ph_ent = warp_sum(ph_ent);
+    __shared__ float s_a[8], s_b[8];
+    const int wid = threadIdx.x >> 5;
+    if (lane == 0) { s_a[wid] = ph_se; s_b[wid] = ph_ent; }
+    __syncthreads();
+    if (wid == 0) {
+      ph_se = lane < 8 ? s_a[lane] : 0.f; ph_ent = lane < 8 ? s_b[lane] : 0.f;
+      ph_se = warp_sum(ph_se); ph_ent = warp_sum(ph_ent);
+      if (lane == 0 && (ph_se != 0.f || ph_ent != 0.f)) { atomicAdd(ph.sums, ph_se); atomicAdd(ph.sums + 1, ph_ent); }
+    }
+  }
+}
+
+template <int CT, int W>
+__global__ void __launch_bounds__(256)
+composite_train_bw_sw_kernel(const float* __restrict__ dL_dopacity, const float* __restrict__ dL_ddepth,
+                             const float* __restrict__ dL_drend, const float* __restrict__ dL_dws,
+                             const float* __restrict__ sigmas, const float* __restrict__ raws,
+                             const float* __restrict__ ws, const float* __restrict__ deltas,
+                             const float* __restrict__ ts, const int64_t* __restrict__ rays_a,
+                             const float* __restrict__ opacity, const float* __restrict__ depth,
+                             const float* __restrict__ rend, float thr, int64_t n_rays, int64_t capacity,
+                             float* __restrict__ dL_dsigmas, float* __restrict__ dL_draws) {
+  constexpr int RPW = 32 / W;
+  const int lane = threadIdx.x & 31, sub = lane / W, sl = lane % W;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t n0 = warp * RPW; n0 < n_rays; n0 += n_warps * RPW) {
+    const int64_t n = n0 + sub;
+    const bool have = n < n_rays;
+    int64_t ray_idx = 0, start = 0, N64 = 0;
+    if (have) { ray_idx = rays_a[3 * n]; start = rays_a[3 * n + 1]; N64 = rays_a[3 * n + 2]; }
+    if (start + N64 > capacity) N64 = capacity > start ? capacity - start : 0;
+    const int N = (int)N64;
+    const int N_max = __reduce_max_sync(0xffffffffu, N);
+    if (N_max == 0) continue;
+    float sg = 0.f, dl = 0.f, tt = 0.f, gwv = 0.f, rw[CT];
+    auto fetch = [&](int base, float& o_sg, float& o_dl, float& o_tt, float& o_gw, float (&o_rw)[CT]) {
+      const int k = base + sl;
+      o_sg = 0.f; o_dl = 0.f; o_tt = 0.f; o_gw = 0.f;
+#pragma unroll
+      for (int c = 0; c < CT; ++c) o_rw[c] = 0.f;
+      if (k < N) {
+        const int64_t s = start + k;
+        o_sg = sigmas[s]; o_dl = deltas[s]; o_tt = ts[s];
+        if (dL_drend) {
+#pragma unroll
+          for (int c = 0; c < CT; ++c) o_rw[c] = raws[s * CT + c];
+        }
+        if (dL_dws) o_gw = dL_dws[s];
+      }
+    };
+    fetch(0, sg, dl, tt, gwv, rw);                         // in flight together with the ray-level loads below
+    float gO = 0.f, gD = 0.f, O = 0.f, D = 0.f, gR[CT];
+#pragma unroll
+    for (int c = 0; c < CT; ++c) gR[c] = 0.f;
+    float part = 0.f;
+    if (have && N > 0) {
+      gO = dL_dopacity ? dL_dopacity[ray_idx] : 0.f;
+      gD = dL_ddepth ? dL_ddepth[ray_idx] : 0.f;
+      O = opacity[ray_idx]; D = depth[ray_idx];
+      if (dL_drend) {
+#pragma unroll
+        for (int c = 0; c < CT; ++c) gR[c] = dL_drend[ray_idx * CT + c];
+        if (sl == 0) {
+#pragma unroll
+          for (int c = 0; c < CT; ++c) part += gR[c] * rend[ray_idx * CT + c];
+        }
+      }
+      if (dL_dws) for (int k = sl; k < N; k += W) part += dL_dws[start + k] * ws[start + k];
+    }
+    const float Q_total = subwarp_sum<W>(part) + gD * D;
+    const float gO_term = gO * (1.0f - O);
+    float T = 1.0f, carry = 0.f;
+    bool dead = false;
+    for (int base = 0; base < N_max; base += W) {
+      const int k = base + sl;
+      const int64_t s = start + k;
+      float n_sg, n_dl, n_tt, n_gw, n_rw[CT];
+      fetch(base + W, n_sg, n_dl, n_tt, n_gw, n_rw);
+      float a = 0.f, g = 0.f;
+      if (k < N) {
+        a = __fsub_rn(1.0f, __expf(__fmul_rn(-sg, dl)));
+#pragma unroll
+        for (int c = 0; c < CT; ++c) g += gR[c] * rw[c];
+      }
+      const float om = __fsub_rn(1.0f, a);
+      float T_before;
+      const int stop = subwarp_replay<W>(om, thr, T, T_before, sl);
+      const bool active = (k < N) && !dead && (stop < 0 || sl <= stop);
+      const float w = active ? __fmul_rn(a, T_before) : 0.f;
+      const float T_after = __fmul_rn(T_before, om);
+      const float lin = gD * tt + g;
+      const float q = active ? (w * lin + gwv * w) : 0.f;
+      const float incl = subwarp_scan_incl<W>(q, sl) + carry;
+      if (k < N) {
+        if (dL_dsigmas) dL_dsigmas[s] = active ? dl * (gO_term + T_after * (lin + gwv) - (Q_total - incl)) : 0.f;
+        if (dL_draws) {
+#pragma unroll
+          for (int c = 0; c < CT; ++c) dL_draws[s * CT + c] = active ? gR[c] * w : 0.f;
+        }
+      }
+      carry = __shfl_sync(0xffffffffu, incl, W - 1, W);
+      if (!dead && stop >= 0) dead = true;
+      sg = n_sg; dl = n_dl; tt = n_tt; gwv = n_gw;
+#pragma unroll
+      for (int c = 0; c < CT; ++c) rw[c] = n_rw[c];
+    }
+  }
+}
+
 // Test-time incremental compositing: one thread per alive ray (S is 1..64 and the layout
 // is (A,S[,C]), so consecutive threads read consecutive rows).
 __global__ void __launch_bounds__(256)
@@ -369,6 +625,14 @@ composite_test_fw_kernel(const float* __restrict__ sigmas, const float* __restri
 
 using namespace ncn;
 
+// lanes per ray of the training compositing kernels: 4 / 8 / 16 = sub-warp kernels (C = 3, 6, 9), 32 = one warp per ray
+static int g_composite_width = 16;
+extern "C" int ncn_set_composite_width(int w) {
+  const int old = g_composite_width;
+  if (w == 4 || w == 8 || w == 16 || w == 32) g_composite_width = w;
+  return old;
+}
+
 extern "C" int ncn_composite_train_fw(const float* sigmas, const float* raws, const float* deltas, const float* ts,
                                       const int64_t* rays_a, float T_threshold, int64_t n_rays, int64_t capacity,
                                       int n_channels, int64_t* total_samples, float* opacity, float* depth,
@@ -382,6 +646,18 @@ extern "C" int ncn_composite_train_fw(const float* sigmas, const float* raws, co
     if (n_channels > 0) NCN_CHECK_PTR(raws);
   }
   const int grid = persistent_grid(n_rays * 32, 256, 8);
+  if (g_composite_width < 32 && (n_channels == 3 || n_channels == 6 || n_channels == 9)) {
+    const int gsw = persistent_grid(n_rays * g_composite_width, 256, 8);
+    const PhotoArgs ph = PhotoArgs();
+#define NCN_CFW(CT, W) composite_train_fw_sw_kernel<CT, W, false><<<gsw, 256, 0, as_stream(stream)>>>(sigmas, raws, deltas, ts, rays_a, T_threshold, \
+                                                                                         n_rays, capacity, total_samples, opacity, depth, rend, ws, ph)
+#define NCN_CFW_W(CT) do { if (g_composite_width == 4) NCN_CFW(CT, 4); else if (g_composite_width == 8) NCN_CFW(CT, 8); else NCN_CFW(CT, 16); } while (0)
+    if (n_channels == 3) NCN_CFW_W(3); else if (n_channels == 6) NCN_CFW_W(6); else NCN_CFW_W(9);
+#undef NCN_CFW_W
+#undef NCN_CFW
+    NCN_LAUNCH_OK();
+    return NCN_OK;
+  }
   if (n_channels == 3) {
     composite_train_fw_ct_kernel<3><<<grid, 256, 0, as_stream(stream)>>>(sigmas, raws, deltas, ts, rays_a, T_threshold, n_rays, capacity,
                                                                          total_samples, opacity, depth, rend, ws);
@@ -401,6 +677,35 @@ extern "C" int ncn_composite_train_fw(const float* sigmas, const float* raws, co
   return NCN_OK;
 }
 
+// compositing forward + the photometric / opacity loss terms and their gradients in ONE launch (C = 3, 6 or 9)
+extern "C" int ncn_composite_train_fw_photometric(const float* sigmas, const float* raws, const float* deltas, const float* ts,
+                                                  const int64_t* rays_a, float T_threshold, int64_t n_rays, int64_t capacity,
+                                                  int n_channels, int64_t* total_samples, float* opacity, float* depth, float* rend,
+                                                  float* ws, const float* target_rgb, const float* bg_rgb_host, float opacity_w,
+                                                  float grad_scale, float* rgb_out, float* sums, float* dL_drend, float* dL_dopacity,
+                                                  ncn_stream_t stream) {
+  NCN_CHECK_SIZE(n_rays >= 0 && capacity >= 0);
+  if (n_channels != 3 && n_channels != 6 && n_channels != 9) return NCN_E_UNSUPPORTED;
+  if (n_rays == 0) return NCN_OK;
+  NCN_CHECK_PTR(rays_a); NCN_CHECK_PTR(total_samples); NCN_CHECK_PTR(opacity); NCN_CHECK_PTR(depth); NCN_CHECK_PTR(rend);
+  NCN_CHECK_PTR(target_rgb); NCN_CHECK_PTR(bg_rgb_host); NCN_CHECK_PTR(sums);
+  if (capacity > 0) { NCN_CHECK_PTR(sigmas); NCN_CHECK_PTR(deltas); NCN_CHECK_PTR(ts); NCN_CHECK_PTR(ws); NCN_CHECK_PTR(raws); }
+  PhotoArgs ph;
+  ph.target = target_rgb; ph.bg[0] = bg_rgb_host[0]; ph.bg[1] = bg_rgb_host[1]; ph.bg[2] = bg_rgb_host[2];
+  ph.opacity_w = opacity_w; ph.gscale = grad_scale; ph.inv3n = 1.0f / (3.0f * (float)n_rays); ph.invn = 1.0f / (float)n_rays;
+  ph.rgb_out = rgb_out; ph.sums = sums; ph.d_rend = dL_drend; ph.d_opacity = dL_dopacity;
+  const int w = g_composite_width < 32 ? g_composite_width : 16;
+  const int gsw = persistent_grid(n_rays * w, 256, 8);
+#define NCN_CFP(CT, W) composite_train_fw_sw_kernel<CT, W, true><<<gsw, 256, 0, as_stream(stream)>>>(sigmas, raws, deltas, ts, rays_a, T_threshold, \
+                                                                                       n_rays, capacity, total_samples, opacity, depth, rend, ws, ph)
+#define NCN_CFP_W(CT) do { if (w == 4) NCN_CFP(CT, 4); else if (w == 8) NCN_CFP(CT, 8); else NCN_CFP(CT, 16); } while (0)
+  if (n_channels == 3) NCN_CFP_W(3); else if (n_channels == 6) NCN_CFP_W(6); else NCN_CFP_W(9);
+#undef NCN_CFP_W
+#undef NCN_CFP
+  NCN_LAUNCH_OK();
+  return NCN_OK;
+}
+
 extern "C" int ncn_composite_train_bw(const float* dL_dopacity, const float* dL_ddepth, const float* dL_drend,
                                       const float* dL_dws, const float* sigmas, const float* raws, const float* ws,
                                       const float* deltas, const float* ts, const int64_t* rays_a,
@@ -415,6 +720,18 @@ extern "C" int ncn_composite_train_bw(const float* dL_dopacity, const float* dL_
   if (n_channels > 0) { NCN_CHECK_PTR(raws); NCN_CHECK_PTR(rend); }
   if (dL_dws) NCN_CHECK_PTR(ws);
   const int grid = persistent_grid(n_rays * 32, 256, 8);
+  if (g_composite_width < 32 && (n_channels == 3 || n_channels == 6 || n_channels == 9)) {
+    const int gsw = persistent_grid(n_rays * g_composite_width, 256, 8);
+#define NCN_CBW(CT, W) composite_train_bw_sw_kernel<CT, W><<<gsw, 256, 0, as_stream(stream)>>>(dL_dopacity, dL_ddepth, dL_drend, dL_dws, sigmas, raws, \
+                                                                                         ws, deltas, ts, rays_a, opacity, depth, rend, T_threshold, \
+                                                                                         n_rays, capacity, dL_dsigmas, dL_draws)
+#define NCN_CBW_W(CT) do { if (g_composite_width == 4) NCN_CBW(CT, 4); else if (g_composite_width == 8) NCN_CBW(CT, 8); else NCN_CBW(CT, 16); } while (0)
+    if (n_channels == 3) NCN_CBW_W(3); else if (n_channels == 6) NCN_CBW_W(6); else NCN_CBW_W(9);
+#undef NCN_CBW_W
+#undef NCN_CBW
+    NCN_LAUNCH_OK();
+    return NCN_OK;
+  }
   if (n_channels == 3) {
     composite_train_bw_ct_kernel<3><<<grid, 256, 0, as_stream(stream)>>>(dL_dopacity, dL_ddepth, dL_drend, dL_dws, sigmas, raws, ws, deltas, ts,
                                                                          rays_a, opacity, depth, rend, T_threshold, n_rays, capacity,

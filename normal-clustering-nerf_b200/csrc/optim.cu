@@ -278,6 +278,10 @@ struct PeerSync {                       // lives in each rank's own device memor
   unsigned int ticket[2];               // local: block tickets of K1 / K2
   unsigned int error;                   // local: a wait timed out
   float partials[kSumsqMaxBlocks];      // local: K1 block partials
+  // local, developer timeline (ns, %globaltimer) of the LAST step, written by one thread per event (ncn_peer_debug_times):
+  // [0] K1 start  [1] K1 all peers' backward done (wait 0 over)  [2] K1 last block finished its reduction
+  // [3] K2 start  [4] K2 norms in / peers done reading (wait 1 over)  [5] K2 last block finished Adam + publish  [6] K2 wait 2 over
+  unsigned long long times[8];
 };
 struct PeerPtrs {
   const float* grad[kPeerMax];
@@ -288,6 +292,13 @@ struct PeerPtrs {
 
 __device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) {
   asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// flag fan-out to W peers: ONE system-scope fence (orders every earlier write of this thread - and, through the preceding block /
+// grid synchronisation, of the kernel - before the flags) followed by W RELAXED stores that are all in flight together.  W
+// st.release stores in a row cost W serialised NVLink round trips (measured: 18 us between the last K1 block finishing and K2
+// starting on 8 GPUs), because every release waits for the previous remote store to be acknowledged.
+__device__ __forceinline__ void st_relaxed_sys(unsigned int* p, unsigned int v) {
+  asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 __device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
   unsigned int v;
@@ -331,9 +342,11 @@ peer_reduce_kernel(PeerPtrs pp, int rank, int world, int64_t lo4, int64_t hi4, f
     const unsigned int e = *reinterpret_cast<volatile unsigned int*>(&me->epoch) + 1u;
     if (blockIdx.x == 0) {                     // "my backward is complete": stream order put this kernel after it
       __threadfence_system();
-      for (int q = 0; q < world; ++q) st_release_sys(&pp.sync[q]->flag[0][rank], e);
+      for (int q = 0; q < world; ++q) st_relaxed_sys(&pp.sync[q]->flag[0][rank], e);
     }
+    if (blockIdx.x == 0) me->times[0] = peer_now_ns();
     peer_wait(me, 0, world, e, pp.err_host);
+    if (blockIdx.x == 0) me->times[1] = peer_now_ns();
     s_epoch = e;
   }
   __syncthreads();
@@ -399,10 +412,11 @@ peer_reduce_kernel(PeerPtrs pp, int rank, int world, int64_t lo4, int64_t hi4, f
 #pragma unroll
     for (int w = 0; w < 8; ++w) tot += s[w];
     me->ticket[0] = 0;
+    me->times[2] = peer_now_ns();
     // every block of this rank has finished reading the peers' gradients: post the partial norm, then the flag
     for (int q = 0; q < world; ++q) *reinterpret_cast<volatile float*>(&pp.sync[q]->norm[epoch & 1][rank]) = tot;
     __threadfence_system();
-    for (int q = 0; q < world; ++q) st_release_sys(&pp.sync[q]->flag[1][rank], epoch);
+    for (int q = 0; q < world; ++q) st_relaxed_sys(&pp.sync[q]->flag[1][rank], epoch);
   }
 }
 
@@ -410,13 +424,15 @@ __global__ void __launch_bounds__(256, 2)
 peer_adam_kernel(PeerPtrs pp, int rank, int world, int64_t lo4, int64_t hi4, int64_t n4, float* __restrict__ param,
                  float* __restrict__ grad, float* __restrict__ m, float* __restrict__ v, AdamArgs a,
                  const float* __restrict__ grad_div, const int32_t* __restrict__ skip, const float* __restrict__ lr_bc,
-                 float* __restrict__ sumsq_out) {
+                 float* __restrict__ sumsq_out, int zero_all) {
   PeerSync* me = pp.sync[rank];
   __shared__ unsigned int s_epoch;
   __shared__ float s_tot;
   if (threadIdx.x == 0) {
     const unsigned int e = *reinterpret_cast<volatile unsigned int*>(&me->epoch) + 1u;
+    if (blockIdx.x == 0) me->times[3] = peer_now_ns();
     peer_wait(me, 1, world, e, pp.err_host);   // every rank's partial norm is here AND every rank is done reading my gradient
+    if (blockIdx.x == 0) me->times[4] = peer_now_ns();
     float tot = 0.f;
     for (int q = 0; q < world; ++q) tot += *reinterpret_cast<volatile float*>(&me->norm[e & 1][q]);
     s_tot = tot; s_epoch = e;
@@ -452,8 +468,10 @@ peer_adam_kernel(PeerPtrs pp, int rank, int world, int64_t lo4, int64_t hi4, int
   }
   // the next backward accumulates into a zeroed buffer; peers are done reading it (barrier above)
   // (the shard itself was zeroed element by element by the thread that consumed it)
-  for (int64_t i = tid; i < n4; i += stride)
-    if (do_skip || i < lo4 || i >= hi4) reinterpret_cast<float4*>(grad)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  // (zero_all == 0: the caller zeroes the buffer itself after this kernel, off the critical path - ncn_peer_set_external_zero)
+  if (zero_all)
+    for (int64_t i = tid; i < n4; i += stride)
+      if (do_skip || i < lo4 || i >= hi4) reinterpret_cast<float4*>(grad)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   __threadfence_system();
   __shared__ bool s_last;
   __syncthreads();
@@ -462,9 +480,11 @@ peer_adam_kernel(PeerPtrs pp, int rank, int world, int64_t lo4, int64_t hi4, int
   if (!s_last) return;
   if (threadIdx.x == 0) {
     me->ticket[1] = 0;
+    me->times[5] = peer_now_ns();
     __threadfence_system();
-    for (int q = 0; q < world; ++q) st_release_sys(&pp.sync[q]->flag[2][rank], epoch);
+    for (int q = 0; q < world; ++q) st_relaxed_sys(&pp.sync[q]->flag[2][rank], epoch);
     peer_wait(me, 2, world, epoch, pp.err_host);   // every shard of MY fp16 parameter buffer has been written by its owner
+    me->times[6] = peer_now_ns();
     *reinterpret_cast<volatile unsigned int*>(&me->epoch) = epoch;
     __threadfence();
   }
@@ -481,6 +501,7 @@ struct ncn_peer {
   ncn::PeerPtrs ptrs;
   void* opened[3][ncn::kPeerMax];
   bool connected;
+  bool external_zero;                   // the caller zeroes the gradient buffer after ncn_peer_step (ncn_peer_set_external_zero)
   unsigned int* err_host;               // cudaHostAllocMapped: written by the kernels on a time-out, read by ncn_peer_poll
 };
 
@@ -488,7 +509,7 @@ extern "C" int ncn_peer_create(ncn_peer** out, int rank, int world, int64_t n_pa
   NCN_CHECK_PTR(out);
   NCN_CHECK_SIZE(world >= 1 && world <= ncn::kPeerMax && rank >= 0 && rank < world && n_params > 0 && (n_params & 3) == 0);
   ncn_peer* p = new ncn_peer();
-  p->rank = rank; p->world = world; p->n = n_params; p->connected = false;
+  p->rank = rank; p->world = world; p->n = n_params; p->connected = false; p->external_zero = false;
   NCN_CUDA(cudaGetDevice(&p->device));
   NCN_CUDA(cudaMalloc(&p->grad, (size_t)n_params * 4));
   NCN_CUDA(cudaMalloc(&p->p16, (size_t)n_params * 2));
@@ -569,7 +590,7 @@ extern "C" int ncn_peer_step(ncn_peer* p, float* param, float* m, float* v, cons
   ncn::peer_reduce_kernel<<<grid, 256, 0, st>>>(p->ptrs, p->rank, p->world, lo4, hi4, p->grad, grad_div_dev);
   NCN_LAUNCH_OK();
   ncn::peer_adam_kernel<<<grid, 256, 0, st>>>(p->ptrs, p->rank, p->world, lo4, hi4, n4, param, p->grad, m, v, a, grad_div_dev,
-                                              skip_dev, lr_bc_dev, sumsq_out_dev);
+                                              skip_dev, lr_bc_dev, sumsq_out_dev, p->external_zero ? 0 : 1);
   NCN_LAUNCH_OK();
   return NCN_OK;
 }
@@ -577,6 +598,22 @@ extern "C" int ncn_peer_step(ncn_peer* p, float* param, float* m, float* v, cons
 extern "C" int ncn_peer_error(ncn_peer* p, unsigned int* error_host) {
   NCN_CHECK_PTR(p); NCN_CHECK_PTR(error_host);
   NCN_CUDA(cudaMemcpy(error_host, &p->sync->error, sizeof(unsigned int), cudaMemcpyDeviceToHost));
+  return NCN_OK;
+}
+
+// on = 1: ncn_peer_step leaves the gradient buffer as it is (its own shard is consumed to zero, the rest still holds this rank's
+// gradient) and the CALLER zeroes the whole buffer after the step, on whatever stream lets it overlap the next forward pass -
+// the 45.8 MB memset then leaves the optimizer's critical path.  The buffer must be zero again before the next backward starts.
+extern "C" int ncn_peer_set_external_zero(ncn_peer* p, int on) {
+  NCN_CHECK_PTR(p);
+  p->external_zero = on != 0;
+  return NCN_OK;
+}
+
+// developer timeline of the last completed step (synchronises): 8 x %globaltimer ns, see PeerSync::times
+extern "C" int ncn_peer_debug_times(ncn_peer* p, unsigned long long* times8_host) {
+  NCN_CHECK_PTR(p); NCN_CHECK_PTR(times8_host);
+  NCN_CUDA(cudaMemcpy(times8_host, p->sync->times, sizeof(unsigned long long) * 8, cudaMemcpyDeviceToHost));
   return NCN_OK;
 }
 

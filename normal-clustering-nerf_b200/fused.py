@@ -98,6 +98,7 @@ class FusedStep:
         # False: encoder, density trunk, glue, colour head, glue (5 launches); "mlp": encoder + ONE launch for both MLPs; True: ONE
         # launch for everything.  The fused kernels build x_rgb / dx_rgb in the [h | d | 1] column order (ncn_mlp_bwd_src.perm)
         self.fuse_fwd = fuse_fwd
+        self.fuse_photo = not os.environ.get("NCN_NO_FUSE_PHOTO")      # env: developer A/B only
         self._alloc_arena(min(int(R * capacity_per_ray), self.cap_max))
         self.side_stream = torch.cuda.Stream(device=dev)
         self.ev_fork, self.ev_join = torch.cuda.Event(), torch.cuda.Event()
@@ -118,6 +119,13 @@ class FusedStep:
         # capturing it inside the step graph dead-locked on 2 GPUs)
         # ... unless the optimizer is the sharded peer-memory one (trainer.peer): its two kernels carry the exchange themselves
         self.peer = trainer.peer
+        # sharded exchange: the 4 B/param gradient memset leaves the optimizer kernel and becomes a node of its own that overlaps the
+        # field forward (it only has to land before the first gradient-writing backward kernel)
+        self.ext_zero = self.peer is not None and not os.environ.get("NCN_PEER_ZERO_IN_KERNEL")      # env: developer A/B only
+        if self.peer is not None:
+            self.peer.set_external_zero(self.ext_zero)
+        self.ev_zero = torch.cuda.Event()
+        self._zero_forked = False            # True while capturing / running the deferred form: _run_field must join ev_zero
         self.nccl = trainer.world_size > 1 and self.peer is None
         self.defer = use_graph and not self.nccl and not os.environ.get("NCN_NO_DEFER")      # env: developer A/B only
         # multi-rank: the same overlap with three graphs on two streams and an EAGER all-reduce in between
@@ -332,11 +340,17 @@ class FusedStep:
         if m.pred_sem and not self.fuse_fwd:   # raws[:, sem_off:] = sem_net(h)  (ngp_mt.py:217-220, rendering.py:207-208)
             ck(L.ncn_mlp_fwd(C.byref(m.sem_net.desc), ptr(self.h), ptr(self._w16("sem_net")), cap, ptr(self.sem_out), ptr(self.sem_acts), n_dev, st), "sem_fwd")
             ck(L.ncn_field_head_out(ptr(self.sem_out), 16, cap, n_dev, ptr(self.raws), Ct, self.sem_off, self.n_cls, st), "sem_head_out")
-        ck(L.ncn_composite_train_fw(ptr(self.sigmas), ptr(self.raws), ptr(self.deltas), ptr(self.ts), ptr(self.rays_a), 1e-4, R, cap, Ct,
-                                    ptr(self.total_samples), ptr(self.opacity), ptr(self.depth), ptr(self.rend), ptr(self.ws), st), "composite_fw")
-        # ---- losses (+ their gradients w.r.t. the rendered quantities; channels without a loss get a zero gradient)
-        ck(L.ncn_photometric_loss(ptr(self.rend), ptr(self.opacity), ptr(self.target), R, Ct, self.bg, float(hp["loss_opacity_w"]), GSCALE,
-                                  ptr(self.rgb), ptr(self.zeros), ptr(self.d_rend), ptr(self.d_opacity), st), "photometric")
+        # ---- compositing + losses (+ their gradients w.r.t. the rendered quantities; channels without a loss get a zero gradient)
+        if self.fuse_photo and Ct in (3, 6, 9):      # ONE launch: the lane that finishes a ray also evaluates its photometric / opacity terms
+            ck(L.ncn_composite_train_fw_photometric(ptr(self.sigmas), ptr(self.raws), ptr(self.deltas), ptr(self.ts), ptr(self.rays_a), 1e-4, R, cap, Ct,
+                                                    ptr(self.total_samples), ptr(self.opacity), ptr(self.depth), ptr(self.rend), ptr(self.ws),
+                                                    ptr(self.target), self.bg, float(hp["loss_opacity_w"]), GSCALE, ptr(self.rgb), ptr(self.zeros),
+                                                    ptr(self.d_rend), ptr(self.d_opacity), st), "composite_fw_photometric")
+        else:
+            ck(L.ncn_composite_train_fw(ptr(self.sigmas), ptr(self.raws), ptr(self.deltas), ptr(self.ts), ptr(self.rays_a), 1e-4, R, cap, Ct,
+                                        ptr(self.total_samples), ptr(self.opacity), ptr(self.depth), ptr(self.rend), ptr(self.ws), st), "composite_fw")
+            ck(L.ncn_photometric_loss(ptr(self.rend), ptr(self.opacity), ptr(self.target), R, Ct, self.bg, float(hp["loss_opacity_w"]), GSCALE,
+                                      ptr(self.rgb), ptr(self.zeros), ptr(self.d_rend), ptr(self.d_opacity), st), "photometric")
         if m.pred_sem and self.sem_w > 0:
             ck(L.ncn_semantic_ce_loss(ptr(self.rend), Ct, self.sem_off, self.n_cls, ptr(self.sem_target), R, self.sem_w * GSCALE,
                                       ptr(self.zeros[4:6]), ptr(self.d_rend), st), "semantic_ce")
@@ -354,6 +368,8 @@ class FusedStep:
             ck(L.ncn_composite_train_bw(None, None, ptr(self.d_rend), None, ptr(self.sigmas), ptr(self.raws), ptr(self.ws),
                                         ptr(self.deltas), ptr(self.ts), ptr(self.rays_a), ptr(self.opacity), ptr(self.depth), ptr(self.rend), 1e-4,
                                         R, cap, Ct, None, ptr(self.d_raws), sst), "composite_bw_raws")
+            if self._zero_forked:
+                side.wait_event(self.ev_zero)     # first gradient writer of this branch: the forked memset must have landed
             ck(L.ncn_mlp_bwd_src_fused(C.byref(rgbn.desc), C.byref(self.src_rgb), ptr(self.x_rgb), ptr(self._w16("rgb_net")), ptr(self.rgb_out),
                                        ptr(self.rgb_acts), cap, ptr(self._g32("rgb_net")), ptr(self.dx_rgb), inv, ptr(self.mlp_ws2),
                                        self.mlp_ws2.numel(), n_dev, sst), "rgb_bwd")
@@ -384,6 +400,8 @@ class FusedStep:
                                     ptr(self.deltas), ptr(self.ts), ptr(self.rays_a), ptr(self.opacity), ptr(self.depth), ptr(self.rend), 1e-4,
                                     R, cap, Ct, ptr(self.d_sigmas), None, st), "composite_bw_sigma")
         main.wait_event(self.ev_join)
+        if self._zero_forked:
+            main.wait_event(self.ev_zero)
         ck(L.ncn_mlp_bwd_src_fused(C.byref(sg.desc), C.byref(self.src_sig), ptr(self.feat), ptr(self._w16("sigma_net")), ptr(self.h),
                                    ptr(self.sig_acts), cap, ptr(self._g32("sigma_net")), ptr(self.dfeat), inv, ptr(self.mlp_ws),
                                    self.mlp_ws.numel(), n_dev, st), "sigma_bwd")
@@ -403,6 +421,8 @@ class FusedStep:
         if self.peer is not None:                # gradient exchange + norm + clip + Adam + fp16 refresh over NVLink peer memory
             self.peer.step(opt.flat, opt.m, opt.v, self.adam_groups, opt.betas, opt.eps, self.grad_div, self.flag,
                            self.dev_sched[sched_off:sched_off + 3], sumsq, st)
+            if self.ext_zero and not self._zero_forked:      # sequential forms (eager step, flush): zero right behind the exchange
+                opt.grad.zero_()
             return
         check(L.ncn_grad_sumsq(ptr(opt.grad), opt.grad.numel(), ptr(self.grad_div), ptr(sumsq), ptr(self.flag), st), "sumsq")
         # both parameter groups (hash table wd 0 / MLPs wd 1e-6) and the clip coefficient in ONE launch
@@ -436,17 +456,23 @@ class FusedStep:
         opt_stream = self.opt_stream
         self.ev_fork2.record(main)
         opt_stream.wait_event(self.ev_fork2)
+        forked = self.ext_zero
         with torch.cuda.stream(opt_stream):
             if multi:
                 self.tr.comm.allreduce_sum_(self.opt.grad)
+            self._zero_forked = forked
             if self.sumsq_tail:
                 self._adam_only(sched_off=6)      # norm + skip flag were left by the previous replay's tail (or by step() / flush())
             else:
                 self._optimizer(sched_off=6)
             self.ev_join2.record(opt_stream)
+            if forked:                            # the parameters are published: the forward may start; the memset runs beside it
+                self.opt.grad.zero_()
+                self.ev_zero.record(opt_stream)
         self._run_march()
         main.wait_event(self.ev_join2)
         self._run_field()
+        self._zero_forked = False
         if self.sumsq_tail:
             self._sumsq()
 

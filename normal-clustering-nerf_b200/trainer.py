@@ -90,6 +90,7 @@ class PeerLink:
         L = _lib.lib()
         self.rank, self.world_size, self.n = rank, world_size, int(n_params)
         self.handle = None
+        self.external_zero = False
         h = C.c_void_p()
         if world_size == 1:
             check(L.ncn_peer_create(C.byref(h), rank, world_size, self.n), "peer_create")
@@ -129,6 +130,11 @@ class PeerLink:
     def step(self, flat, m, v, groups, betas, eps, grad_div, flag, lr_bc, sumsq_out, st):
         check(_lib.lib().ncn_peer_step(self.handle, ptr(flat), ptr(m), ptr(v), C.byref(groups), betas[0], betas[1], eps, ptr(grad_div),
                                        ptr(flag), ptr(lr_bc), ptr(sumsq_out), st), "peer_step")
+
+    def set_external_zero(self, on=True):
+        """the caller zeroes the gradient buffer after every step() itself (off the exchange's critical path)"""
+        check(_lib.lib().ncn_peer_set_external_zero(self.handle, 1 if on else 0), "peer_set_external_zero")
+        self.external_zero = bool(on)
 
     def poll(self):
         """error word from mapped host memory, no device synchronisation (0 = ok, 1 + phase of the wait that timed out)"""
