@@ -462,6 +462,22 @@ size_t ncn_kmeans_workspace_bytes(int64_t n_points_max, int k);
 int ncn_kmeans_spherical(const float* x, int64_t n_points, const ncn_kmeans_params* p,
                          float* centroids, int32_t* assign, int32_t* n_valid,
                          void* workspace, size_t workspace_bytes, ncn_stream_t stream);
+/* the per-triangle half of ncn_cluster_tail on its own (after ncn_cluster_chain): dL/dnormals of w[0] L_ort + w[1] L_dot + w[2] L_L1
+ * (weights read from device memory) and, through the normals, dL/ddepth (atomically accumulated) */
+int ncn_cluster_bw_depth(const float* normals, const int32_t* labels, int64_t n_points, const float* stats,
+                         const float* weights_dev, float* dL_dnormals, const float* origin, const float* dir,
+                         const float* depth, const int64_t* idx1, const int64_t* idx2, const int64_t* idx3,
+                         float* dL_ddepth, ncn_stream_t stream);
+/* ncn_normals_from_depth_fw -> ncn_kmeans_spherical -> ncn_cluster_select -> ncn_cluster_loss_fw as ONE thread-block-cluster
+ * launch (3 <= k <= 32, else NCN_E_UNSUPPORTED): the normals are computed by the cluster's CTAs as a prologue, and the selection
+ * (losses.py:97-166), the cluster statistics and the three loss terms (losses.py:441-478) run as an epilogue while the points and
+ * centroids are still resident in the cluster's shared memory (member counts and fixed-point sums folded over distributed shared
+ * memory).  Same outputs as the four calls: normals (M,3), centroids (k,3), assign (M), n_valid (1), labels (M), sel (3),
+ * losses (3), stats (32); integer outputs identical, the float sums of the loss terms differ by fp32 summation order only. */
+int ncn_cluster_chain(const float* origin, const float* dir, const float* depth, const int64_t* idx1, const int64_t* idx2,
+                      const int64_t* idx3, int64_t n_tri, const ncn_kmeans_params* p, float t_similar, float* normals,
+                      float* centroids, int32_t* assign, int32_t* n_valid, int32_t* labels, int32_t* sel, float* losses,
+                      float* stats, void* workspace, size_t workspace_bytes, ncn_stream_t stream);
 /* Orthogonal-triple selection + merge + opposite labelling (losses.py:97-166).
  * labels (M) i32 in {-3..3} (0 = unused / skipped), sel (3) i32 = (c1,c2,c3). */
 int ncn_cluster_select(const float* centroids, const int32_t* assign, int64_t n_points, int k,

@@ -199,6 +199,9 @@ SIGNATURES.update({
     "ncn_normals_from_depth_bw": (c_i32, [c_vp] * 7 + [c_i64, c_vp, c_vp]),
     "ncn_kmeans_workspace_bytes": (c_sz, [c_i64, c_i32]),
     "ncn_kmeans_spherical": (c_i32, [c_vp, c_i64, C.POINTER(KmeansParams), c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
+    "ncn_cluster_bw_depth": (c_i32, [c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "ncn_cluster_chain": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, C.POINTER(KmeansParams), c_f32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp,
+                                  c_vp, c_sz, c_vp]),
     "ncn_cluster_select": (c_i32, [c_vp, c_vp, c_i64, c_i32, c_f32, c_vp, c_vp, c_vp]),
     "ncn_cluster_loss_fw": (c_i32, [c_vp, c_vp, c_i64, c_vp, c_vp, c_vp]),
     "ncn_cluster_loss_bw": (c_i32, [c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp]),

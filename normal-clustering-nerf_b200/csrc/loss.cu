@@ -147,6 +147,10 @@ __device__ __forceinline__ void warp_accumulate_by_key(int key, bool valid, floa
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+// execution barrier only (no memory ordering: no MEMBAR, used where nothing read afterwards depends on the peers' writes)
+__device__ __forceinline__ void cluster_sync_relaxed() {
+  asm volatile("barrier.cluster.arrive.relaxed.aligned;\n\tbarrier.cluster.wait.aligned;" ::: "memory");
+}
 __device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
 // read an int from the same shared-memory variable of CTA `rank` of the cluster (DSMEM)
 __device__ __forceinline__ int dsmem_ld_int(const int* local_ptr, uint32_t rank) {
@@ -163,6 +167,59 @@ __device__ __forceinline__ float dsmem_ld_float(const float* local_ptr, uint32_t
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(a), "r"(rank));
   asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(ra) : "memory");
   return v;
+}
+
+
+// ---- cluster exchange without barrier.cluster ------------------------------------------------------------------------------
+// barrier.cluster.arrive.release lowers to MEMBAR.ALL.GPU + the hardware cluster barrier + an L1 invalidate (SASS), ~2 us per use
+// on a 16-CTA cluster - two thirds of a Lloyd iteration.  The exchange below needs none of it: every CTA pushes its partial sums
+// into an inbox in every peer's shared memory with st.async, whose completion is counted (bytes) by an mbarrier in the RECEIVER's
+// shared memory; the receiver waits on its own mbarrier and then reads its inbox with ordinary shared-memory loads.  Inboxes and
+// mbarriers are double buffered by round parity (a peer can be at most one round ahead: it cannot finish round r+1 before it has
+// received this CTA's round r+1 contribution, which is sent only after round r's inbox has been consumed).
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+  uint32_t ra;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(addr), "r"(rank));
+  return ra;
+}
+__device__ __forceinline__ void st_async_v4(uint32_t remote_addr, uint4 v, uint32_t remote_mbar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];"
+               ::"r"(remote_addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"(remote_mbar) : "memory");
+}
+__device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t mbar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(mbar), "r"(parity) : "memory");
+}
+constexpr int kKmInboxLanes = 32;       // one 16-byte slot per lane of the exchanging warp
+// one round of the all-to-all: lanes [0, n_lanes) of ONE warp each contribute 16 bytes; returns when all CL contributions of the
+// round have landed in this CTA's inbox[round & 1][source rank][lane]
+template <int CL>
+__device__ __forceinline__ const uint4* km_exchange(uint4* inbox, uint64_t* mbar, int round, uint32_t rank, int lane, int n_lanes, uint4 v) {
+  const int buf = round & 1;
+  const uint32_t mb = smem_u32(mbar + buf);
+  if (lane < n_lanes) {
+    const uint32_t dst = smem_u32(inbox + ((size_t)(buf * CL + (int)rank) * kKmInboxLanes + lane));
+#pragma unroll
+    for (uint32_t r = 0; r < CL; ++r) st_async_v4(mapa_u32(dst, r), v, mapa_u32(mb, r));
+  }
+  if (lane == 0) mbar_arrive_expect_tx(mb, (uint32_t)(CL * n_lanes * 16));
+  mbar_wait(mb, (uint32_t)((round >> 1) & 1));
+  __syncwarp();
+  return inbox + (size_t)buf * CL * kKmInboxLanes;
 }
 
 // ---- tensor-core Lloyd iteration (K <= 32) ---------------------------------------------------------------
@@ -207,11 +264,78 @@ __device__ __forceinline__ void split_empty_clusters(float* __restrict__ s_c, fl
   }
 }
 
+
+// warp arg-min / arg-max over (value, index) pairs with ties to the LOWEST index (the reference's argmin / first-max loops)
+__device__ __forceinline__ void warp_argmin(float& v, int& i) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, v, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, i, o);
+    if (ov < v || (ov == v && oi < i)) { v = ov; i = oi; }
+  }
+}
+
+// Orthogonal-triple selection, merge and opposite labelling (losses.py:97-166) for K <= 32 by ONE warp, one lane per cluster:
+// s_sim = centroids @ centroids^T (K x K), s_size = members per cluster -> s_lab[j] in {-3..3}, (c1, c2, c3)
+__device__ __forceinline__ void select_triple_warp(const float* __restrict__ s_sim, const int* __restrict__ s_size, int K, float t_similar,
+                                                   int* __restrict__ s_lab, int& c1_out, int& c2_out, int& c3_out, int lane) {
+  const int j = lane;
+  const bool on = j < K;
+  // biggest cluster (losses.py:104-107): first maximum
+  float negsz = on ? -(float)s_size[j] : INFINITY; int c1 = j;
+  warp_argmin(negsz, c1);
+  // criteria[i][j] = |sim[i,c1]| + |sim[c1,j]| + |sim[i,j]|; column j: min / argmin over i (losses.py:117-118)
+  float mn = INFINITY; int arg = 0;
+  if (on)
+    for (int i = 0; i < K; ++i) {
+      const float v = fabsf(s_sim[i * K + c1]) + fabsf(s_sim[c1 * K + j]) + fabsf(s_sim[i * K + j]);
+      if (v < mn) { mn = v; arg = i; }
+    }
+  float best = mn; int c2 = j;                                            // losses.py:119-120
+  warp_argmin(best, c2);
+  const int c3 = __shfl_sync(0xffffffffu, arg, c2);
+  int lab = 0;
+  const int cs[3] = {c1, c2, c3};
+#pragma unroll
+  for (int q = 0; q < 3; ++q)                                             // merge similar (losses.py:47-54)
+    if (on && s_sim[cs[q] * K + j] > t_similar) lab = q + 1;
+#pragma unroll
+  for (int q = 0; q < 3; ++q) {                                           // opposite clusters (losses.py:57-72)
+    float v = on ? s_sim[cs[q] * K + j] : INFINITY; int o = j;
+    warp_argmin(v, o);
+    if (-v > t_similar && on && s_sim[o * K + j] > t_similar) lab = -(q + 1);
+  }
+  if (on) s_lab[j] = lab;
+  c1_out = c1; c2_out = c2; c3_out = c3;
+}
+
+__device__ __forceinline__ float sgnf(float v) { return v > 0.f ? 1.f : (v < 0.f ? -1.f : 0.f); }
+constexpr int kStats = 32;
+
+// Optional stages the k-means launch can carry in front of and behind the clustering itself (ncn_cluster_chain): the normals from
+// the rendered depth (datasets/hypersim_src/utils.py:505-541) as a prologue, and - with the points and centroids still resident
+// in the cluster's shared memory - the triple selection (losses.py:97-166) and the cluster statistics / three loss terms
+// (losses.py:441-478) as an epilogue.  All-null = plain k-means.
+struct ChainArgs {
+  const float* origin; const float* dir; const float* depth;          // prologue inputs (origin == nullptr: x is given)
+  const int64_t* i1; const int64_t* i2; const int64_t* i3;
+  float* normals_out;
+  float t_similar;                                                    // epilogue (labels == nullptr: none)
+  int32_t* labels; int32_t* sel; float* losses; float* stats;
+};
+__device__ __forceinline__ long long dsmem_ld_i64(const long long* local_ptr, uint32_t rank) {
+  uint32_t a = (uint32_t)__cvta_generic_to_shared(local_ptr), ra;
+  long long v;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(a), "r"(rank));
+  asm volatile("ld.shared::cluster.s64 %0, [%1];" : "=l"(v) : "r"(ra) : "memory");
+  return v;
+}
+
 template <int CL>
 __global__ void __launch_bounds__(kKmThreads, 1)
-kmeans_kernel(const float* __restrict__ x, int64_t n, ncn_kmeans_params p, float* __restrict__ centroids,
+kmeans_kernel(const float* __restrict__ x_in, int64_t n, ncn_kmeans_params p, float* __restrict__ centroids,
               int32_t* __restrict__ assign, int32_t* __restrict__ n_valid_out, int32_t* __restrict__ valid_idx,
-              int nt_cap) {
+              int nt_cap, const ChainArgs ch) {
   extern __shared__ __align__(16) unsigned char km_smem[];
   float* xs = reinterpret_cast<float*>(km_smem);                 // this CTA's training points [my_n][3]
   __shared__ float s_c[kKmMaxK * 3];
@@ -221,10 +345,41 @@ kmeans_kernel(const float* __restrict__ x, int64_t n, ncn_kmeans_params p, float
   __shared__ float s_fw[(kKmThreads / 32) * 32 * 8];             // tensor-core path: per-warp (32 clusters x 8) partial sums
   __shared__ float s_fpart[2][32 * 8];                           // this CTA's partial sums (double buffered), read by peers
   __shared__ int s_nvalid, s_warp_tot[32], s_base, s_any_empty;
+  __shared__ __align__(8) uint64_t s_mbar[2];                    // completion of the two exchange inboxes (double buffered)
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  if (tid == 0) {
+    mbar_init(smem_u32(&s_mbar[0]), 1); mbar_init(smem_u32(&s_mbar[1]), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
   const int K = p.k;
   const uint32_t rank = cluster_ctarank();
   KM_TRACE(0);
+  // 0) chain prologue: the normals of the rendered depth (one triangle per thread, the cluster's CTAs split them), published
+  //    to global memory (the backward pass and the caller read them) and made visible to the whole cluster by one barrier
+  const float* x = x_in;
+  if (ch.origin != nullptr) {
+    for (int64_t m = tid + (int64_t)rank * kKmThreads; m < n; m += (int64_t)kKmThreads * CL) {
+      const int64_t idx[3] = {ch.i1[m], ch.i2[m], ch.i3[m]};
+      float P[3][3];
+#pragma unroll
+      for (int v = 0; v < 3; ++v) {
+        const float dep = ch.depth[idx[v]];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) P[v][c] = __fadd_rn(ch.origin[3 * idx[v] + c], __fmul_rn(ch.dir[3 * idx[v] + c], dep));
+      }
+      float a[3], b[3];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) { a[c] = P[1][c] - P[0][c]; b[c] = P[2][c] - P[0][c]; }
+      const float cx = a[1] * b[2] - a[2] * b[1];
+      const float cy = a[2] * b[0] - a[0] * b[2];
+      const float cz = a[0] * b[1] - a[1] * b[0];
+      const float nrm = fmaxf(sqrtf(cx * cx + cy * cy + cz * cz), 1e-12f);   // F.normalize eps (same arithmetic as normals_fw_kernel)
+      ch.normals_out[3 * m] = cx / nrm; ch.normals_out[3 * m + 1] = cy / nrm; ch.normals_out[3 * m + 2] = cz / nrm;
+    }
+    __threadfence();
+    cluster_sync_all();
+    x = ch.normals_out;
+  }
   // 1) every CTA compacts the valid rows (stable order) - identical results, CTA 0 publishes them.  Warp w owns a
   //    contiguous slice of rows, walked in chunks of 32 x 32 rows whose validity bits a lane gathers with independent
   //    (pipelined) loads: count, one block-wide exclusive scan of the 8 warp totals, then write.
@@ -257,7 +412,7 @@ kmeans_kernel(const float* __restrict__ x, int64_t n, ncn_kmeans_params p, float
           const bool v = (vm >> b) & 1u;
           const unsigned bal = __ballot_sync(0xffffffffu, v);
           if (v) valid_idx[base + __popc(bal & ((1u << lane) - 1))] = (int32_t)i;
-          else if (i < r_end) assign[i] = -1;
+          else if (i < r_end) { assign[i] = -1; if (ch.labels != nullptr) ch.labels[i] = 0; }
           base += __popc(bal);
         }
       }
@@ -270,6 +425,11 @@ kmeans_kernel(const float* __restrict__ x, int64_t n, ncn_kmeans_params p, float
   if (rank == 0 && tid == 0) *n_valid_out = nv;
   if (nv == 0) {
     if (rank == 0) for (int j = tid; j < K * 3; j += kKmThreads) centroids[j] = 0.f;
+    if (rank == 0 && tid == 0 && ch.labels != nullptr) {      // no valid normal: every cluster is empty -> NaN terms, flag 0
+      ch.sel[0] = ch.sel[1] = ch.sel[2] = 0;
+      for (int q = 0; q < kStats; ++q) ch.stats[q] = 0.f;
+      ch.losses[0] = ch.losses[1] = ch.losses[2] = NAN; ch.stats[24] = ch.stats[25] = ch.stats[26] = NAN;
+    }
     return;                         // uniform across the cluster: nobody reaches a cluster barrier
   }
   __threadfence();
@@ -301,6 +461,9 @@ kmeans_kernel(const float* __restrict__ x, int64_t n, ncn_kmeans_params p, float
   const int g = lane >> 2, t = lane & 3;
   const int n_tiles = (my_n + 15) >> 4;
   __half* hq = reinterpret_cast<__half*>(km_smem + (((size_t)((nt_cap + CL - 1) / CL) * 12 + 15) & ~(size_t)15));
+  // exchange inboxes [2][CL][32 lanes] x 16 B behind the fp16 rows (only ever written by the peers' st.async)
+  uint4* inbox = reinterpret_cast<uint4*>(reinterpret_cast<unsigned char*>(hq) + (size_t)(((nt_cap + CL - 1) / CL + 16) * 16));
+  int xround = 0;                                                // exchange rounds done (uniform across the cluster)
   if (use_tc) {
     // iteration-invariant fp16 point rows: hq[point] = (xh,yh,zh,xl,yl,zl,1,0); all-zero rows pad the last tile
     for (int j = tid; j < n_tiles * 16; j += kKmThreads) {
@@ -315,6 +478,8 @@ kmeans_kernel(const float* __restrict__ x, int64_t n, ncn_kmeans_params p, float
     __syncthreads();
   }
   KM_TRACE(3);
+  float prev_c[3] = {0.f, 0.f, 0.f};                               // warp 0, lane j: centroid j before the current iteration
+  if (wid == 0 && lane < K) { prev_c[0] = s_c[3 * lane]; prev_c[1] = s_c[3 * lane + 1]; prev_c[2] = s_c[3 * lane + 2]; }
   for (int it = 0; it < p.niter; ++it) {
     if (it < 4) KM_TRACE(8 + 8 * it);
     if (use_tc) {
@@ -388,31 +553,34 @@ kmeans_kernel(const float* __restrict__ x, int64_t n, ncn_kmeans_params p, float
         row0[64] = acc[mt][2]; row0[65] = acc[mt][3];            // cluster +8 -> 8 rows * 8 floats further
       }
       __syncthreads();
-      float* fpart = s_fpart[it & 1];
       if (tid < 256) {
         float tot = 0.f;                                          // 256 threads <-> 32 clusters x 8 columns, fixed order
 #pragma unroll
         for (int w = 0; w < kKmThreads / 32; ++w) tot += s_fw[(size_t)w * 256 + tid];
-        fpart[tid] = tot;
+        s_fpart[0][tid] = tot;                                    // this CTA's sums (local scratch)
       }
       if (it < 4) KM_TRACE(10 + 8 * it);
-      cluster_sync_all();
-      if (it < 4) KM_TRACE(11 + 8 * it);
-      if (tid < 256) {
-        float tot = 0.f;
-#pragma unroll
-        for (uint32_t r = 0; r < CL; ++r) tot += dsmem_ld_float(fpart + tid, r);
-        s_fw[tid] = tot;                                          // cluster total of (cluster tid/8, column tid%8)
-      }
-      if (it < 4) KM_TRACE(12 + 8 * it);
       __syncthreads();
-      if (it < 4) KM_TRACE(13 + 8 * it);
-      // centroid update by warp 0 alone (K <= 32: one lane per cluster) - warp-level syncs only
+      // exchange + centroid update by warp 0 alone (one lane per cluster); the other warps wait at the block barrier below
       if (wid == 0) {
+        uint4 mine = make_uint4(0u, 0u, 0u, 0u);
         if (lane < K) {
-          const float* r = s_fw + lane * 8;
-          s_acc[4 * lane] = r[0] + r[3]; s_acc[4 * lane + 1] = r[1] + r[4]; s_acc[4 * lane + 2] = r[2] + r[5]; s_acc[4 * lane + 3] = r[6];
+          const float* r = s_fpart[0] + lane * 8;               // hi + lo halves of (x, y, z), member count
+          mine.x = __float_as_uint(r[0] + r[3]); mine.y = __float_as_uint(r[1] + r[4]); mine.z = __float_as_uint(r[2] + r[5]);
+          mine.w = __float_as_uint(r[6]);
         }
+        const uint4* in = km_exchange<CL>(inbox, s_mbar, xround, rank, lane, K, mine);
+        if (it < 4) KM_TRACE(11 + 8 * it);
+        if (lane < K) {
+          float sx = 0.f, sy = 0.f, sz = 0.f, sc = 0.f;           // fold in rank order: identical in every CTA
+#pragma unroll
+          for (int r = 0; r < CL; ++r) {
+            const uint4 q = in[r * kKmInboxLanes + lane];
+            sx += __uint_as_float(q.x); sy += __uint_as_float(q.y); sz += __uint_as_float(q.z); sc += __uint_as_float(q.w);
+          }
+          s_acc[4 * lane] = sx; s_acc[4 * lane + 1] = sy; s_acc[4 * lane + 2] = sz; s_acc[4 * lane + 3] = sc;
+        }
+        if (it < 4) KM_TRACE(12 + 8 * it);
         __syncwarp();
         bool empty = false;
         if (lane < K) {
@@ -433,9 +601,22 @@ kmeans_kernel(const float* __restrict__ x, int64_t n, ncn_kmeans_params p, float
           const float l = sqrtf(s_c[3 * lane] * s_c[3 * lane] + s_c[3 * lane + 1] * s_c[3 * lane + 1] + s_c[3 * lane + 2] * s_c[3 * lane + 2]);
           if (l > 0.f) { const float il = 1.0f / l; s_c[3 * lane] *= il; s_c[3 * lane + 1] *= il; s_c[3 * lane + 2] *= il; }
         }
+        // exact early exit: centroids bit-identical to the previous iteration's are a fixed point of the (deterministic) Lloyd map -
+        // every further iteration would reproduce them, so the result equals running all niter iterations.  Every CTA holds the
+        // same centroids, so the decision is uniform across the cluster without any extra exchange.
+        __syncwarp();
+        bool same = true;
+        if (lane < K)
+          same = __float_as_uint(s_c[3 * lane]) == __float_as_uint(prev_c[0]) && __float_as_uint(s_c[3 * lane + 1]) == __float_as_uint(prev_c[1]) &&
+                 __float_as_uint(s_c[3 * lane + 2]) == __float_as_uint(prev_c[2]);
+        if (lane < K) { prev_c[0] = s_c[3 * lane]; prev_c[1] = s_c[3 * lane + 1]; prev_c[2] = s_c[3 * lane + 2]; }
+        const bool fixed = __all_sync(0xffffffffu, same);
+        if (lane == 0) s_any_empty = fixed ? 1 : 0;               // (s_any_empty doubles as the block-wide "converged" flag on this path)
       }
       if (it < 4) KM_TRACE(14 + 8 * it);
+      ++xround;
       __syncthreads();
+      if (s_any_empty) break;                                     // (xround counts the exchanges actually done: parities stay consistent)
       continue;
     } else {
     int* wacc = s_wacc + wid * K * 4;
@@ -485,15 +666,159 @@ kmeans_kernel(const float* __restrict__ x, int64_t n, ncn_kmeans_params p, float
     // which every CTA reaches only after it finished reading buffer `it`
   }
   KM_TRACE(4);
-  cluster_sync_all();               // no CTA may exit while a peer can still read its shared memory
+  if (!use_tc) cluster_sync_all();  // pull-based exchange: no CTA may run ahead / exit while a peer can still read its shared memory
   KM_TRACE(5);
   // 5) final assignment of every valid row (kmeans.index.search, losses.py:89), split over the cluster + centroids out
+  __shared__ int s_sz[kKmMaxK];                                   // chain: this CTA's member counts, read by the peers
+  if (ch.labels != nullptr) { for (int j = tid; j < K; j += kKmThreads) s_sz[j] = 0; __syncthreads(); }
   for (int j = tid + (int)rank * kKmThreads; j < nv; j += kKmThreads * CL) {
     const int r = valid_idx[j];
-    assign[r] = best_centroid(x[3 * r], x[3 * r + 1], x[3 * r + 2], s_c, K);
+    const int a = best_centroid(x[3 * r], x[3 * r + 1], x[3 * r + 2], s_c, K);
+    assign[r] = a;
+    if (ch.labels != nullptr) atomicAdd(&s_sz[a], 1);
   }
   if (rank == 0) for (int j = tid; j < K * 3; j += kKmThreads) centroids[j] = s_c[j];
   KM_TRACE(6);
+  if (ch.labels == nullptr) return;
+  // ---- 6) chain epilogue (K <= 32): selection, labels, cluster statistics and the three loss terms, with every CTA working on
+  //         the rows it has just assigned.  Integer / fixed-point partials make the folds order independent; the float partials
+  //         of the second pass are folded in rank order - the result is bit-reproducible run to run.
+  __shared__ float s_sim[32 * 32];
+  __shared__ int s_size[32], s_lab[32], s_cnt3[3];
+  __shared__ long long s_p1[12], s_t1[12];                       // this CTA's / the cluster's fixed-point sums (x, y, z, count) x 3 clusters
+  __shared__ float s_p2[16], s_c3[9], s_mu3[3], s_w2[kKmThreads / 32][16];
+  for (int e = tid; e < K * K; e += kKmThreads) {
+    const int i = e / K, j = e % K;
+    s_sim[e] = s_c[3 * i] * s_c[3 * j] + s_c[3 * i + 1] * s_c[3 * j + 1] + s_c[3 * i + 2] * s_c[3 * j + 2];      // centrs @ centrs.T
+  }
+  if (tid < 12) s_p1[tid] = 0;
+  __syncthreads();
+  if (wid == 0) {                                                 // X1: member counts of all CTAs, then the selection (replicated)
+    uint4 mine = make_uint4(lane < K ? (uint32_t)s_sz[lane] : 0u, 0u, 0u, 0u);
+    const uint4* in = km_exchange<CL>(inbox, s_mbar, xround, rank, lane, K, mine);
+    if (lane < K) {
+      int t = 0;
+#pragma unroll
+      for (int r = 0; r < CL; ++r) t += (int)in[r * kKmInboxLanes + lane].x;
+      s_size[lane] = t;
+    }
+    __syncwarp();
+    int c1, c2, c3;
+    select_triple_warp(s_sim, s_size, K, ch.t_similar, s_lab, c1, c2, c3, lane);
+    if (rank == 0 && lane == 0) { ch.sel[0] = c1; ch.sel[1] = c2; ch.sel[2] = c3; }
+  }
+  ++xround;
+  __syncthreads();
+  // labels + first pass: sign-flipped member sums per selected cluster, 2^-20 fixed point in 64-bit shared-memory atomics
+  for (int j = tid + (int)rank * kKmThreads; j < nv; j += kKmThreads * CL) {
+    const int r = valid_idx[j];
+    const int l = s_lab[assign[r]];
+    ch.labels[r] = l;
+    if (l != 0) {
+      const int k = (l > 0 ? l : -l) - 1;
+      const float sg = l > 0 ? 1.f : -1.f;
+      atomicAdd(reinterpret_cast<unsigned long long*>(&s_p1[4 * k]), (unsigned long long)(long long)__float2int_rn(sg * x[3 * r] * kKmFix));
+      atomicAdd(reinterpret_cast<unsigned long long*>(&s_p1[4 * k + 1]), (unsigned long long)(long long)__float2int_rn(sg * x[3 * r + 1] * kKmFix));
+      atomicAdd(reinterpret_cast<unsigned long long*>(&s_p1[4 * k + 2]), (unsigned long long)(long long)__float2int_rn(sg * x[3 * r + 2] * kKmFix));
+      atomicAdd(reinterpret_cast<unsigned long long*>(&s_p1[4 * k + 3]), 1ull);
+    }
+  }
+  __syncthreads();
+  if (wid == 0) {                                                 // X2: fixed-point first-pass sums of all CTAs (12 x i64 = 6 slots)
+    uint4 mine = make_uint4(0u, 0u, 0u, 0u);
+    if (lane < 6) {
+      const unsigned long long a = (unsigned long long)s_p1[2 * lane], b = (unsigned long long)s_p1[2 * lane + 1];
+      mine = make_uint4((uint32_t)a, (uint32_t)(a >> 32), (uint32_t)b, (uint32_t)(b >> 32));
+    }
+    const uint4* in = km_exchange<CL>(inbox, s_mbar, xround, rank, lane, 6, mine);
+    if (lane < 6) {
+      long long ta = 0, tb = 0;
+#pragma unroll
+      for (int r = 0; r < CL; ++r) {
+        const uint4 q = in[r * kKmInboxLanes + lane];
+        ta += (long long)(((unsigned long long)q.y << 32) | q.x); tb += (long long)(((unsigned long long)q.w << 32) | q.z);
+      }
+      s_t1[2 * lane] = ta; s_t1[2 * lane + 1] = tb;
+    }
+    __syncwarp();
+    if (lane < 3) {
+      const int k = lane;
+      const long long sx = s_t1[4 * k], sy = s_t1[4 * k + 1], sz = s_t1[4 * k + 2], cnt = s_t1[4 * k + 3];
+      s_cnt3[k] = (int)cnt;
+      if (cnt > 0) {                                              // same arithmetic as cluster_loss_fw_body
+        const double inv = 1.0 / ((double)cnt * (double)kKmFix);
+        const float mx = (float)((double)sx * inv), my = (float)((double)sy * inv), mz = (float)((double)sz * inv);
+        const float len = sqrtf(mx * mx + my * my + mz * mz);
+        const float d = fmaxf(len, 1e-12f);
+        s_c3[3 * k] = mx / d; s_c3[3 * k + 1] = my / d; s_c3[3 * k + 2] = mz / d; s_mu3[k] = len;
+      } else { s_c3[3 * k] = s_c3[3 * k + 1] = s_c3[3 * k + 2] = 0.f; s_mu3[k] = 0.f; }
+    }
+  }
+  ++xround;
+  __syncthreads();
+  // second pass: per cluster sum of dots, of L1 distances and of sign(n' - c)
+  float v2[16];
+#pragma unroll
+  for (int q = 0; q < 16; ++q) v2[q] = 0.f;
+  for (int j = tid + (int)rank * kKmThreads; j < nv; j += kKmThreads * CL) {
+    const int r = valid_idx[j];
+    const int l = s_lab[assign[r]];
+    if (l == 0) continue;
+    const int k = (l > 0 ? l : -l) - 1;
+    const float sg = l > 0 ? 1.f : -1.f;
+    const float px = sg * x[3 * r], py = sg * x[3 * r + 1], pz = sg * x[3 * r + 2];
+    const float dx = px - s_c3[3 * k], dy = py - s_c3[3 * k + 1], dz = pz - s_c3[3 * k + 2];
+#pragma unroll
+    for (int q = 0; q < 3; ++q) if (q == k) {
+      v2[q] += px * s_c3[3 * q] + py * s_c3[3 * q + 1] + pz * s_c3[3 * q + 2];
+      v2[3 + q] += fabsf(dx) + fabsf(dy) + fabsf(dz);
+      v2[6 + 3 * q] += sgnf(dx); v2[7 + 3 * q] += sgnf(dy); v2[8 + 3 * q] += sgnf(dz);
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < 15; ++q) { const float t = warp_sum(v2[q]); if (lane == 0) s_w2[wid][q] = t; }
+  __syncthreads();
+  if (tid < 15) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < kKmThreads / 32; ++w) t += s_w2[w][tid];
+    s_p2[tid] = t;
+  }
+  __syncthreads();
+  if (wid == 0) {                                                 // X3: second-pass float partials (15 values = 4 slots), folded in rank order
+    uint4 mine = make_uint4(0u, 0u, 0u, 0u);
+    if (lane < 4) mine = make_uint4(__float_as_uint(s_p2[4 * lane]), __float_as_uint(s_p2[4 * lane + 1]), __float_as_uint(s_p2[4 * lane + 2]),
+                                    __float_as_uint(s_p2[4 * lane + 3]));
+    const uint4* in = km_exchange<CL>(inbox, s_mbar, xround, rank, lane, 4, mine);
+    float tot = 0.f;
+    if (lane < 15) {
+      const uint32_t* w = reinterpret_cast<const uint32_t*>(in);
+#pragma unroll
+      for (int r = 0; r < CL; ++r) tot += __uint_as_float(w[(r * kKmInboxLanes + (lane >> 2)) * 4 + (lane & 3)]);
+    }
+    // lane q holds total q: 0-2 dots, 3-5 L1, 6-14 sign sums
+    const float d0 = __shfl_sync(0xffffffffu, tot, 0), d1 = __shfl_sync(0xffffffffu, tot, 1), d2 = __shfl_sync(0xffffffffu, tot, 2);
+    const float a0 = __shfl_sync(0xffffffffu, tot, 3), a1 = __shfl_sync(0xffffffffu, tot, 4), a2 = __shfl_sync(0xffffffffu, tot, 5);
+    if (rank == 0 && lane >= 6 && lane < 15) { const int k = (lane - 6) / 3, d = (lane - 6) % 3; ch.stats[8 * k + 5 + d] = tot; }
+    if (rank == 0 && lane == 0) {
+      const bool ok = s_cnt3[0] > 0 && s_cnt3[1] > 0 && s_cnt3[2] > 0;
+      float l_ort = NAN, l_dot = NAN, l_l1 = NAN;
+      if (ok) {
+        auto dot3 = [&](int a, int b) { return s_c3[3 * a] * s_c3[3 * b] + s_c3[3 * a + 1] * s_c3[3 * b + 1] + s_c3[3 * a + 2] * s_c3[3 * b + 2]; };
+        l_ort = (fabsf(dot3(0, 1)) + fabsf(dot3(0, 2)) + fabsf(dot3(1, 2))) / 3.0f;
+        l_dot = ((1.f - d0 / s_cnt3[0]) + (1.f - d1 / s_cnt3[1]) + (1.f - d2 / s_cnt3[2])) / 3.0f;
+        l_l1 = (a0 / s_cnt3[0] + a1 / s_cnt3[1] + a2 / s_cnt3[2]) / 3.0f;
+      }
+      ch.losses[0] = l_ort; ch.losses[1] = l_dot; ch.losses[2] = l_l1;
+      for (int k = 0; k < 3; ++k) {
+        ch.stats[8 * k] = (float)s_cnt3[k];
+        ch.stats[8 * k + 1] = s_c3[3 * k]; ch.stats[8 * k + 2] = s_c3[3 * k + 1]; ch.stats[8 * k + 3] = s_c3[3 * k + 2];
+        ch.stats[8 * k + 4] = s_mu3[k];
+      }
+      ch.stats[24] = l_ort; ch.stats[25] = l_dot; ch.stats[26] = l_l1; ch.stats[27] = ok ? 1.f : 0.f;
+    }
+  }
+  cluster_sync_relaxed();                                         // leave together: no CTA exits while pushes into a peer are in flight
 }
 #ifdef NCN_KM_TRACE
 extern "C" int ncn_debug_km_trace(long long* host_dst) {
@@ -502,16 +827,6 @@ extern "C" int ncn_debug_km_trace(long long* host_dst) {
 #endif
 
 // ---------------------------------------------------------------- orthogonal-triple selection (one CTA)
-// warp arg-min / arg-max over (value, index) pairs with ties to the LOWEST index (the reference's argmin / first-max loops)
-__device__ __forceinline__ void warp_argmin(float& v, int& i) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    const float ov = __shfl_xor_sync(0xffffffffu, v, o);
-    const int oi = __shfl_xor_sync(0xffffffffu, i, o);
-    if (ov < v || (ov == v && oi < i)) { v = ov; i = oi; }
-  }
-}
-
 __device__ __forceinline__ void cluster_select_body(const float* __restrict__ centroids, const int32_t* __restrict__ assign, int64_t n, int K,
                                                     float t_similar, int32_t* __restrict__ labels, int32_t* __restrict__ sel) {
   __shared__ int s_size[kKmMaxK];
@@ -531,33 +846,8 @@ __device__ __forceinline__ void cluster_select_body(const float* __restrict__ ce
   if (K <= 32) {
     // one lane per cluster, warp 0 only: the selection is a handful of warp arg-min / arg-max reductions
     if (tid < 32) {
-      const int j = lane;
-      const bool on = j < K;
-      // biggest cluster (losses.py:104-107): first maximum
-      float negsz = on ? -(float)s_size[j] : INFINITY; int c1 = j;
-      warp_argmin(negsz, c1);
-      // criteria[i][j] = |sim[i,c1]| + |sim[c1,j]| + |sim[i,j]|; column j: min / argmin over i (losses.py:117-118)
-      float mn = INFINITY; int arg = 0;
-      if (on)
-        for (int i = 0; i < K; ++i) {
-          const float v = fabsf(s_sim[i * K + c1]) + fabsf(s_sim[c1 * K + j]) + fabsf(s_sim[i * K + j]);
-          if (v < mn) { mn = v; arg = i; }
-        }
-      float best = mn; int c2 = j;                                            // losses.py:119-120
-      warp_argmin(best, c2);
-      const int c3 = __shfl_sync(0xffffffffu, arg, c2);
-      int lab = 0;
-      const int cs[3] = {c1, c2, c3};
-#pragma unroll
-      for (int q = 0; q < 3; ++q)                                             // merge similar (losses.py:47-54)
-        if (on && s_sim[cs[q] * K + j] > t_similar) lab = q + 1;
-#pragma unroll
-      for (int q = 0; q < 3; ++q) {                                           // opposite clusters (losses.py:57-72)
-        float v = on ? s_sim[cs[q] * K + j] : INFINITY; int o = j;
-        warp_argmin(v, o);
-        if (-v > t_similar && on && s_sim[o * K + j] > t_similar) lab = -(q + 1);
-      }
-      if (on) s_lab[j] = lab;
+      int c1, c2, c3;
+      select_triple_warp(s_sim, s_size, K, t_similar, s_lab, c1, c2, c3, lane);
       if (lane == 0) { sel[0] = c1; sel[1] = c2; sel[2] = c3; }
     }
     __syncthreads();
@@ -611,10 +901,6 @@ cluster_select_kernel(const float* __restrict__ centroids, const int32_t* __rest
 // ---------------------------------------------------------------- cluster statistics and loss (one CTA)
 // stats layout (floats): per cluster k in 0..2 at stats[8k..]: [count, cx, cy, cz, |mu|, gl1x, gl1y, gl1z]
 // where gl1 = sum_i sign(n'_i - c_k); stats[24..26] = losses (ort, dot, L1); stats[27] = valid flag
-constexpr int kStats = 32;
-
-__device__ __forceinline__ float sgnf(float v) { return v > 0.f ? 1.f : (v < 0.f ? -1.f : 0.f); }
-
 __device__ __forceinline__ void cluster_loss_fw_body(const float* __restrict__ nrm, const int32_t* __restrict__ labels, int64_t n,
                                                      float* __restrict__ losses, float* __restrict__ stats) {
   __shared__ int s_wacc[32 * 12];
@@ -998,9 +1284,8 @@ extern "C" size_t ncn_kmeans_workspace_bytes(int64_t n_points_max, int k) {
   return n_points_max < 0 ? 0 : (size_t)n_points_max * sizeof(int32_t) + 256;
 }
 
-extern "C" int ncn_kmeans_spherical(const float* x, int64_t n_points, const ncn_kmeans_params* p, float* centroids,
-                                    int32_t* assign, int32_t* n_valid, void* workspace, size_t workspace_bytes,
-                                    ncn_stream_t stream) {
+static int launch_kmeans(const float* x, int64_t n_points, const ncn_kmeans_params* p, float* centroids, int32_t* assign,
+                         int32_t* n_valid, void* workspace, size_t workspace_bytes, const ChainArgs& ch, ncn_stream_t stream) {
   NCN_CHECK_PTR(p); NCN_CHECK_PTR(centroids); NCN_CHECK_PTR(n_valid);
   if (p->k < 1 || p->k > kKmMaxK || p->niter < 0 || p->max_points_per_centroid < 1) return NCN_E_CONFIG;
   NCN_CHECK_SIZE(n_points >= 0 && n_points < ((int64_t)1 << 31));
@@ -1015,18 +1300,19 @@ extern "C" int ncn_kmeans_spherical(const float* x, int64_t n_points, const ncn_
     cluster = kKmCluster;
     if (cudaFuncSetAttribute(kmeans_kernel<kKmClusterMax>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess) {
       cudaLaunchConfig_t q = {};
-      q.gridDim = dim3(kKmClusterMax); q.blockDim = dim3(kKmThreads); q.dynamicSmemBytes = 64 * 1024;
+      q.gridDim = dim3(kKmClusterMax); q.blockDim = dim3(kKmThreads); q.dynamicSmemBytes = 96 * 1024;
       cudaLaunchAttribute qa[1];
       qa[0].id = cudaLaunchAttributeClusterDimension; qa[0].val.clusterDim.x = kKmClusterMax; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
       q.attrs = qa; q.numAttrs = 1;
       int n_clusters = 0;
-      cudaFuncSetAttribute(kmeans_kernel<kKmClusterMax>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+      cudaFuncSetAttribute(kmeans_kernel<kKmClusterMax>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
       if (cudaOccupancyMaxActiveClusters(&n_clusters, kmeans_kernel<kKmClusterMax>, &q) == cudaSuccess && n_clusters >= 1) cluster = kKmClusterMax;
     }
     (void)cudaGetLastError();
   }
   const size_t per_cta = (size_t)(cap + cluster - 1) / cluster;
-  const size_t smem = per_cta * 12 + 16 + (per_cta + 16) * 16 + 16;               // this CTA's points (fp32) + fp16 rows
+  // this CTA's points (fp32) + fp16 rows + the two exchange inboxes (cluster x 32 slots x 16 B each)
+  const size_t smem = per_cta * 12 + 16 + (per_cta + 16) * 16 + 16 + (size_t)2 * cluster * 32 * 16;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(cluster); cfg.blockDim = dim3(kKmThreads); cfg.dynamicSmemBytes = smem; cfg.stream = as_stream(stream);
   cudaLaunchAttribute at[1];
@@ -1034,16 +1320,45 @@ extern "C" int ncn_kmeans_spherical(const float* x, int64_t n_points, const ncn_
   cfg.attrs = at; cfg.numAttrs = 1;
   int32_t* wsp = (int32_t*)workspace;
   const int cap_i = (int)cap;
-  // static (~22 KB) + dynamic shared memory can cross the 48 KB default limit: always opt in
+  // static (~28 KB) + dynamic shared memory can cross the 48 KB default limit: always opt in
   if (cluster == kKmClusterMax) {
     NCN_CUDA(cudaFuncSetAttribute(kmeans_kernel<kKmClusterMax>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    NCN_CUDA(cudaLaunchKernelEx(&cfg, kmeans_kernel<kKmClusterMax>, x, n_points, *p, centroids, assign, n_valid, wsp, cap_i));
+    NCN_CUDA(cudaLaunchKernelEx(&cfg, kmeans_kernel<kKmClusterMax>, x, n_points, *p, centroids, assign, n_valid, wsp, cap_i, ch));
   } else {
     NCN_CUDA(cudaFuncSetAttribute(kmeans_kernel<kKmCluster>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    NCN_CUDA(cudaLaunchKernelEx(&cfg, kmeans_kernel<kKmCluster>, x, n_points, *p, centroids, assign, n_valid, wsp, cap_i));
+    NCN_CUDA(cudaLaunchKernelEx(&cfg, kmeans_kernel<kKmCluster>, x, n_points, *p, centroids, assign, n_valid, wsp, cap_i, ch));
   }
   NCN_LAUNCH_OK();
   return NCN_OK;
+}
+
+extern "C" int ncn_kmeans_spherical(const float* x, int64_t n_points, const ncn_kmeans_params* p, float* centroids,
+                                    int32_t* assign, int32_t* n_valid, void* workspace, size_t workspace_bytes,
+                                    ncn_stream_t stream) {
+  ChainArgs ch = ChainArgs();
+  return launch_kmeans(x, n_points, p, centroids, assign, n_valid, workspace, workspace_bytes, ch, stream);
+}
+
+// normals from the rendered depth -> spherical k-means -> triple selection -> cluster statistics and the three loss terms in ONE
+// cluster launch (K <= 32): = ncn_normals_from_depth_fw + ncn_kmeans_spherical + ncn_cluster_select + ncn_cluster_loss_fw
+extern "C" int ncn_cluster_chain(const float* origin, const float* dir, const float* depth, const int64_t* idx1, const int64_t* idx2,
+                                 const int64_t* idx3, int64_t n_tri, const ncn_kmeans_params* p, float t_similar, float* normals,
+                                 float* centroids, int32_t* assign, int32_t* n_valid, int32_t* labels, int32_t* sel, float* losses,
+                                 float* stats, void* workspace, size_t workspace_bytes, ncn_stream_t stream) {
+  NCN_CHECK_PTR(p);
+  if (p->k < 3 || p->k > 32) return NCN_E_UNSUPPORTED;
+  NCN_CHECK_SIZE(n_tri >= 0);
+  NCN_CHECK_PTR(sel); NCN_CHECK_PTR(losses); NCN_CHECK_PTR(stats);
+  if (n_tri > 0) {
+    NCN_CHECK_PTR(origin); NCN_CHECK_PTR(dir); NCN_CHECK_PTR(depth); NCN_CHECK_PTR(idx1); NCN_CHECK_PTR(idx2); NCN_CHECK_PTR(idx3);
+    NCN_CHECK_PTR(normals); NCN_CHECK_PTR(labels);
+  }
+  ChainArgs ch;
+  ch.origin = origin; ch.dir = dir; ch.depth = depth; ch.i1 = idx1; ch.i2 = idx2; ch.i3 = idx3; ch.normals_out = normals;
+  ch.t_similar = t_similar; ch.labels = labels; ch.sel = sel; ch.losses = losses; ch.stats = stats;
+  if (n_tri == 0) { ch.origin = nullptr; }
+  // (the kernel reads its points from `normals` after the prologue; launch_kmeans only checks that the pointer is set)
+  return launch_kmeans(normals, n_tri, p, centroids, assign, n_valid, workspace, workspace_bytes, ch, stream);
 }
 
 extern "C" int ncn_cluster_select(const float* centroids, const int32_t* assign, int64_t n_points, int k, float t_similar,
@@ -1096,6 +1411,24 @@ extern "C" int ncn_cluster_tail(const float* centroids, const int32_t* assign, i
     cluster_bw_depth_kernel<<<persistent_grid(n_points, 256, 8), 256, 0, as_stream(stream)>>>(normals, labels, n_points, stats, weights_dev,
                                                                                              dL_dnormals, origin, dir, depth, idx1, idx2, idx3,
                                                                                              dL_ddepth);
+  NCN_LAUNCH_OK();
+  return NCN_OK;
+}
+
+// second half of ncn_cluster_tail on its own (after ncn_cluster_chain): dL/dnormals of the three cluster terms and, through the
+// normals, dL/ddepth - one launch over the triangles
+extern "C" int ncn_cluster_bw_depth(const float* normals, const int32_t* labels, int64_t n_points, const float* stats,
+                                    const float* weights_dev, float* dL_dnormals, const float* origin, const float* dir,
+                                    const float* depth, const int64_t* idx1, const int64_t* idx2, const int64_t* idx3,
+                                    float* dL_ddepth, ncn_stream_t stream) {
+  NCN_CHECK_SIZE(n_points >= 0);
+  if (n_points == 0) return NCN_OK;
+  NCN_CHECK_PTR(normals); NCN_CHECK_PTR(labels); NCN_CHECK_PTR(stats); NCN_CHECK_PTR(weights_dev); NCN_CHECK_PTR(dL_dnormals);
+  NCN_CHECK_PTR(origin); NCN_CHECK_PTR(dir); NCN_CHECK_PTR(depth); NCN_CHECK_PTR(idx1); NCN_CHECK_PTR(idx2); NCN_CHECK_PTR(idx3);
+  NCN_CHECK_PTR(dL_ddepth);
+  cluster_bw_depth_kernel<<<persistent_grid(n_points, 256, 8), 256, 0, as_stream(stream)>>>(normals, labels, n_points, stats, weights_dev,
+                                                                                           dL_dnormals, origin, dir, depth, idx1, idx2, idx3,
+                                                                                           dL_ddepth);
   NCN_LAUNCH_OK();
   return NCN_OK;
 }

@@ -99,6 +99,7 @@ class FusedStep:
         # launch for everything.  The fused kernels build x_rgb / dx_rgb in the [h | d | 1] column order (ncn_mlp_bwd_src.perm)
         self.fuse_fwd = fuse_fwd
         self.fuse_photo = not os.environ.get("NCN_NO_FUSE_PHOTO")      # env: developer A/B only
+        self.fuse_chain = not os.environ.get("NCN_NO_FUSE_CHAIN")      # env: developer A/B only
         self._alloc_arena(min(int(R * capacity_per_ray), self.cap_max))
         self.side_stream = torch.cuda.Stream(device=dev)
         self.ev_fork, self.ev_join = torch.cuda.Event(), torch.cuda.Event()
@@ -387,15 +388,24 @@ class FusedStep:
             self.ev_join.record(side)
         if self.M > 0:
             x1, x2, x3 = ptr(self.tri[0]), ptr(self.tri[1]), ptr(self.tri[2])
+            t_sim = 1.0 - float(hp["loss_norm_can_tres"])
             # rays_o := rays_d (rendering.py:227 quirk)
-            ck(L.ncn_normals_from_depth_fw(ptr(self.rays_d), ptr(self.rays_d), ptr(self.depth), x1, x2, x3, self.M, ptr(self.normals), st), "normals_fw")
-            ck(L.ncn_kmeans_spherical(ptr(self.normals), self.M, C.byref(self.km_params), ptr(self.centroids), ptr(self.assign),
-                                      ptr(self.n_valid), ptr(self.km_ws), self.km_ws.numel(), st), "kmeans")
-            # selection + cluster losses (one single-CTA launch), dL/dnormals + dL/ddepth (one multi-CTA launch)
-            ck(L.ncn_cluster_tail(ptr(self.centroids), ptr(self.assign), self.M, 20, 1.0 - float(hp["loss_norm_can_tres"]),
-                                  ptr(self.labels), ptr(self.sel), ptr(self.normals), ptr(self.losses), ptr(self.stats),
-                                  ptr(self.dev_sched[3:6]), ptr(self.dn), ptr(self.rays_d), ptr(self.rays_d), ptr(self.depth),
-                                  x1, x2, x3, ptr(self.d_depth), st), "cluster_tail")
+            if self.fuse_chain:
+                # normals -> k-means -> selection -> cluster statistics + losses in ONE cluster launch, then dL/dnormals + dL/ddepth
+                ck(L.ncn_cluster_chain(ptr(self.rays_d), ptr(self.rays_d), ptr(self.depth), x1, x2, x3, self.M, C.byref(self.km_params), t_sim,
+                                       ptr(self.normals), ptr(self.centroids), ptr(self.assign), ptr(self.n_valid), ptr(self.labels), ptr(self.sel),
+                                       ptr(self.losses), ptr(self.stats), ptr(self.km_ws), self.km_ws.numel(), st), "cluster_chain")
+                ck(L.ncn_cluster_bw_depth(ptr(self.normals), ptr(self.labels), self.M, ptr(self.stats), ptr(self.dev_sched[3:6]), ptr(self.dn),
+                                          ptr(self.rays_d), ptr(self.rays_d), ptr(self.depth), x1, x2, x3, ptr(self.d_depth), st), "cluster_bw_depth")
+            else:
+                ck(L.ncn_normals_from_depth_fw(ptr(self.rays_d), ptr(self.rays_d), ptr(self.depth), x1, x2, x3, self.M, ptr(self.normals), st), "normals_fw")
+                ck(L.ncn_kmeans_spherical(ptr(self.normals), self.M, C.byref(self.km_params), ptr(self.centroids), ptr(self.assign),
+                                          ptr(self.n_valid), ptr(self.km_ws), self.km_ws.numel(), st), "kmeans")
+                # selection + cluster losses (one single-CTA launch), dL/dnormals + dL/ddepth (one multi-CTA launch)
+                ck(L.ncn_cluster_tail(ptr(self.centroids), ptr(self.assign), self.M, 20, t_sim,
+                                      ptr(self.labels), ptr(self.sel), ptr(self.normals), ptr(self.losses), ptr(self.stats),
+                                      ptr(self.dev_sched[3:6]), ptr(self.dn), ptr(self.rays_d), ptr(self.rays_d), ptr(self.depth),
+                                      x1, x2, x3, ptr(self.d_depth), st), "cluster_tail")
         ck(L.ncn_composite_train_bw(ptr(self.d_opacity), ptr(self.d_depth), ptr(self.d_rend), None, ptr(self.sigmas), ptr(self.raws), ptr(self.ws),
                                     ptr(self.deltas), ptr(self.ts), ptr(self.rays_a), ptr(self.opacity), ptr(self.depth), ptr(self.rend), 1e-4,
                                     R, cap, Ct, ptr(self.d_sigmas), None, st), "composite_bw_sigma")

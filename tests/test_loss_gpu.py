@@ -146,6 +146,83 @@ def test_cluster_tail_equals_the_four_calls(ncn):
     torch.testing.assert_close(a[5], bb[5], rtol=1e-4, atol=1e-7)      # float atomics: order differs
 
 
+@pytest.mark.parametrize("n_rays,zero_frac", [(8192, 0.02), (2048, 0.0), (512, 0.3), (64, 1.0)])
+def test_cluster_chain_equals_the_four_calls(ncn, n_rays, zero_frac):
+    """ncn_cluster_chain (normals -> k-means -> selection -> cluster statistics + losses in ONE thread-block-cluster launch) against
+    ncn_normals_from_depth_fw -> ncn_kmeans_spherical -> ncn_cluster_select -> ncn_cluster_loss_fw: every integer output identical
+    (assignments, labels, selected triple, valid count), normals / centroids bit-identical, loss terms to fp32 summation order.
+    8192 rays -> 6272 normals crosses the 256*K sub-sampling branch; zero-depth rays make invalid (all-zero) normals; the last
+    case has no valid normal at all."""
+    import ctypes as C
+    from ncn_b200 import _lib, clustering, synth
+    from ncn_b200.vren import ptr, stream
+    L = _lib.lib()
+    dev = "cuda"
+    b = synth.patch_batch(n_rays, seed=7)
+    rays_d = torch.from_numpy(b["rays_d"]).to(dev)
+    tri = torch.from_numpy(b["tri"]).to(dev)
+    g = torch.Generator(device=dev).manual_seed(1)
+    rays_o = torch.from_numpy(b["rays_o"]).to(dev)
+    t_wall = torch.where(rays_d > 0, (0.4 - rays_o) / rays_d, (-0.4 - rays_o) / rays_d).min(-1)[0]      # a room: Manhattan normals
+    depth = (t_wall + 0.004 * torch.randn(n_rays, device=dev, generator=g)).clamp_min(0.02)
+    if zero_frac >= 1.0:
+        depth.zero_()
+    elif zero_frac > 0:
+        n_patch = n_rays // 64
+        patch = torch.arange(n_patch, device=dev) % max(2, int(round(1 / zero_frac))) == 1      # whole patches at depth 0 -> all-zero normals
+        depth[patch.repeat_interleave(64)] = 0.0
+    depth = depth.contiguous()
+    M = tri.shape[1]
+    p = _lib.KmeansParams(20, 20, 1234, 256, 1)
+    ws = torch.empty(L.ncn_kmeans_workspace_bytes(M, 20), dtype=torch.uint8, device=dev)
+    st = stream()
+    # rays_o := rays_d (rendering.py:227): with depth 0 every vertex of a triangle is its own direction -> not degenerate, so the
+    # invalid rows come from the TRUE origin here (all three vertices coincide at depth 0)
+    org = torch.zeros_like(rays_d) if zero_frac > 0 else rays_d
+
+    def alloc():
+        return dict(normals=torch.empty(M, 3, device=dev), cent=torch.empty(20, 3, device=dev), assign=torch.empty(M, dtype=torch.int32, device=dev),
+                    nv=torch.empty(1, dtype=torch.int32, device=dev), labels=torch.empty(M, dtype=torch.int32, device=dev),
+                    sel=torch.empty(3, dtype=torch.int32, device=dev), losses=torch.empty(3, device=dev), stats=torch.zeros(32, device=dev))
+
+    a = alloc()
+    assert L.ncn_normals_from_depth_fw(ptr(org), ptr(rays_d), ptr(depth), ptr(tri[0]), ptr(tri[1]), ptr(tri[2]), M, ptr(a["normals"]), st) == 0
+    assert L.ncn_kmeans_spherical(ptr(a["normals"]), M, C.byref(p), ptr(a["cent"]), ptr(a["assign"]), ptr(a["nv"]), ptr(ws), ws.numel(), st) == 0
+    assert L.ncn_cluster_select(ptr(a["cent"]), ptr(a["assign"]), M, 20, 0.99, ptr(a["labels"]), ptr(a["sel"]), st) == 0
+    assert L.ncn_cluster_loss_fw(ptr(a["normals"]), ptr(a["labels"]), M, ptr(a["losses"]), ptr(a["stats"]), st) == 0
+    torch.cuda.synchronize()
+    c = alloc()
+    for rep in range(2):                       # twice: the second launch must reproduce the first bit for bit
+        rc = L.ncn_cluster_chain(ptr(org), ptr(rays_d), ptr(depth), ptr(tri[0]), ptr(tri[1]), ptr(tri[2]), M, C.byref(p), 0.99, ptr(c["normals"]),
+                                 ptr(c["cent"]), ptr(c["assign"]), ptr(c["nv"]), ptr(c["labels"]), ptr(c["sel"]), ptr(c["losses"]), ptr(c["stats"]),
+                                 ptr(ws), ws.numel(), st)
+        assert rc == 0
+        torch.cuda.synchronize()
+        if rep == 0:
+            first = {k: v.clone() for k, v in c.items()}
+        else:
+            for k in c:
+                assert torch.equal(torch.nan_to_num(c[k].float(), nan=-7.0), torch.nan_to_num(first[k].float(), nan=-7.0)), k
+    nv = int(a["nv"])
+    assert int(c["nv"]) == nv
+    assert torch.equal(c["normals"], a["normals"])
+    valid = a["assign"] >= 0
+    assert int(valid.sum()) == nv
+    if zero_frac >= 1.0:
+        assert nv == 0 and torch.isnan(c["losses"]).all() and float(c["stats"][27]) == 0.0
+        return
+    if zero_frac > 0:
+        assert 0 < nv < M
+    assert torch.equal(c["cent"], a["cent"])
+    assert torch.equal(c["assign"], a["assign"])
+    assert torch.equal(c["labels"], a["labels"]) and torch.equal(c["sel"], a["sel"])
+    assert (a["labels"] != 0).any() and (a["labels"][~valid] == 0).all()
+    torch.testing.assert_close(c["losses"], a["losses"], rtol=2e-6, atol=1e-7, equal_nan=True)
+    torch.testing.assert_close(c["stats"][:28], a["stats"][:28], rtol=2e-6, atol=1e-6, equal_nan=True)
+    if n_rays >= 2048:
+        assert float(a["stats"][27]) == 1.0 and torch.isfinite(a["losses"]).all()      # the room has three populated clusters
+
+
 def test_normals_image_kernel_matches_reference_golden(ncn):
     """ncn_normals_from_depth_image vs the reference's _extract_normals_from_depth_batch (golden fixture), with (B,4,4) and
     (B,3,4) poses; then a full 768x1024 image against the oracle restatement"""
@@ -229,3 +306,20 @@ def test_semantic_and_photometric_kernels_match_reference_sem_golden(ncn):
         torch.testing.assert_close(d_rend[:, :3].cpu(), torch.from_numpy(g[f"{case}_grad_rgb"]), rtol=1e-4, atol=1e-9)
         torch.testing.assert_close(d_rend[:, 6:].cpu(), torch.from_numpy(g[f"{case}_grad_sem"]), rtol=1e-4, atol=1e-9)
         assert float(d_rend[:, 3:6].abs().max()) == 0.0
+
+
+def test_kmeans_early_exit_is_exact(ncn):
+    """the exact early exit (centroids bit-identical to the previous iteration's = a fixed point of the deterministic Lloyd map): on a
+    cleanly separated planted frame the result of niter = 20 equals niter = 200 bit for bit, and a run that cannot converge
+    (niter = 1 vs 2 on noise) still differs - the exit does not fire spuriously"""
+    from ncn_b200 import clustering, synth
+    x, _ = synth.manhattan_normals(6272, seed=3, noise=0.01, frac_axes=1.0, frac_zero=0.0)
+    xt = torch.from_numpy(x).cuda()
+    c20, a20, _ = clustering.kmeans_spherical(xt, 6, 40)
+    c200, a200, _ = clustering.kmeans_spherical(xt, 6, 400)
+    assert torch.equal(c20, c200) and torch.equal(a20, a200)
+    g = torch.Generator(device="cuda").manual_seed(0)
+    noise = torch.nn.functional.normalize(torch.randn(6272, 3, device="cuda", generator=g), dim=-1)
+    c1, _, _ = clustering.kmeans_spherical(noise, 20, 1)
+    c2, _, _ = clustering.kmeans_spherical(noise, 20, 2)
+    assert not torch.equal(c1, c2)
