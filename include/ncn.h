@@ -385,6 +385,9 @@ int ncn_field_heads_fwd(const void* h_f16, int64_t n, const int32_t* n_dev, floa
  * accumulators, 128-row tiles fed by bulk copies (shapes without an instantiation fall back to 0);
  * 0 = warp-MMA dgrad in registers + split-K wgrad kernels.  Returns the old value. */
 int ncn_set_mlp_bwd_impl(int impl);
+/* implementation of ncn_field_mlp_fwd: 1 = tcgen05 / TMEM accumulators, one 128-sample tile per CTA iteration (default);
+ * 0 = warp-level mma.sync.  Returns the previous value (developer A/B knob; results agree to fp16 rounding of the activations). */
+int ncn_set_field_fwd_impl(int impl);
 /* ncn_march_train* on the constant-step path (cascades == 1, exp_step_factor == 0): 1 (default) = four lanes per ray, each
  * marching a quarter of the candidate sequence (bit-identical output); 0 = one lane per ray; 2 = four lanes with every
  * segment re-marched from its predecessor's landing point (test mode for the repair path).  Returns the old value. */

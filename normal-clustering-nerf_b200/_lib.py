@@ -45,6 +45,7 @@ SIGNATURES = {
     "ncn_distortion_bw": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_vp, c_vp]),
     "ncn_segment_csr_sum": (c_i32, [c_vp, c_vp, c_i64, c_i32, c_vp, c_vp]),
     "ncn_set_composite_width": (c_i32, [c_i32]),
+    "ncn_set_field_fwd_impl": (c_i32, [c_i32]),
 }
 
 
@@ -57,7 +58,7 @@ class Profiler:
     events = []            # (name, start_event, end_event, n_items)
     KERNELS_PER_CALL = {"ncn_march_train": 3, "ncn_march_train_count": 3, "ncn_cluster_tail": 2, "ncn_kmeans_workspace_bytes": 0,
                         "ncn_march_train_workspace_bytes": 0, "ncn_mlp_bwd_workspace_bytes": 0, "ncn_mlp_acts_bytes": 0, "ncn_mlp_n_params": 0,
-                        "ncn_grid_desc_init": 0, "ncn_version": 0, "ncn_set_mlp_bwd_impl": 0, "ncn_set_march_segments": 0, "ncn_set_composite_width": 0, "ncn_debug_stamp": 1, "ncn_set_grid_bwd_merge": 0, "ncn_set_grid_fwd_coherent": 0, "ncn_error_string": 0, "ncn_device_info": 0,
+                        "ncn_grid_desc_init": 0, "ncn_version": 0, "ncn_set_mlp_bwd_impl": 0, "ncn_set_march_segments": 0, "ncn_set_composite_width": 0, "ncn_set_field_fwd_impl": 0, "ncn_debug_stamp": 1, "ncn_set_grid_bwd_merge": 0, "ncn_set_grid_fwd_coherent": 0, "ncn_error_string": 0, "ncn_device_info": 0,
                         "ncn_comm_unique_id": 0, "ncn_comm_init": 0, "ncn_comm_destroy": 0, "ncn_comm_last_error": 0,
                         "ncn_sample_ray_batch": 2, "ncn_peer_create": 0, "ncn_peer_grad": 0, "ncn_peer_p16": 0, "ncn_peer_handles": 0, "ncn_peer_connect": 0,
                         "ncn_peer_shard": 0, "ncn_peer_step": 2, "ncn_peer_error": 0, "ncn_peer_destroy": 0,

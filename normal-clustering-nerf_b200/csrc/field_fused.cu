@@ -362,12 +362,24 @@ extern "C" int ncn_field_fwd(const ncn_grid_desc* desc, const float* x, const fl
 
 // density trunk + colour head in one launch on precomputed hash-grid features (replaces ncn_mlp_fwd(sigma) ->
 // ncn_field_prepare_rgb -> ncn_mlp_fwd(rgb) -> ncn_field_head_out; same outputs as ncn_field_fwd, x_rgb in [h | d | 1] order)
+// implementation of ncn_field_mlp_fwd: 1 = tcgen05 / TMEM (field_tc05.cu, default), 0 = warp MMA (this file); developer A/B knob
+int ncn_field_mlp_fwd_tc05_try(const void* feat_f16, const float* dirs, const void* w_sigma_f16, const void* w_rgb_f16, int64_t n,
+                               const int32_t* n_dev, float* sigmas, float* raws, int c_total, void* h_f16, void* sig_acts_f16,
+                               void* x_rgb_f16, void* rgb_acts_f16, void* rgb_out_f16, cudaStream_t st);
+static int g_field_fwd_impl = 1;
+extern "C" int ncn_set_field_fwd_impl(int impl) { const int old = g_field_fwd_impl; g_field_fwd_impl = impl; return old; }
+
 extern "C" int ncn_field_mlp_fwd(const void* feat_f16, const float* dirs, const void* w_sigma_f16, const void* w_rgb_f16, int64_t n,
                                  const int32_t* n_dev, float* sigmas, float* raws, int c_total, void* h_f16, void* sig_acts_f16,
                                  void* x_rgb_f16, void* rgb_acts_f16, void* rgb_out_f16, ncn_stream_t stream) {
   NCN_CHECK_SIZE(n >= 0 && c_total >= 3);
   if (n == 0) return NCN_OK;
   NCN_CHECK_PTR(feat_f16); NCN_CHECK_PTR(dirs); NCN_CHECK_PTR(w_sigma_f16); NCN_CHECK_PTR(w_rgb_f16); NCN_CHECK_PTR(sigmas); NCN_CHECK_PTR(raws);
+  if (g_field_fwd_impl >= 1) {
+    const int rc = ncn_field_mlp_fwd_tc05_try(feat_f16, dirs, w_sigma_f16, w_rgb_f16, n, n_dev, sigmas, raws, c_total, h_f16, sig_acts_f16,
+                                              x_rgb_f16, rgb_acts_f16, rgb_out_f16, as_stream(stream));
+    if (rc != NCN_E_UNSUPPORTED) return rc;
+  }
   FfGridMeta m = {};
   const int grid = persistent_grid(((n + 15) / 16) * 32, kFfThreads, 6);
   field_fwd_kernel<false><<<grid, kFfThreads, 0, as_stream(stream)>>>(m, nullptr, dirs, nullptr, (const __half*)w_sigma_f16,

@@ -250,3 +250,75 @@ def test_field_heads_fwd_equals_separate_launches(ncn, n, n_cls):
     raws3 = torch.full((n, Ct), -7.0, device="cuda")
     check(L.ncn_field_heads_fwd(ptr(h), n, ptr(n_dev), ptr(raws3), Ct, None, 0, 0, None, None, ptr(ws), 6, n_cls, None, None, st))
     assert torch.equal(raws3[:n // 2, 6:], raws_ref[:n // 2, 6:]) and bool((raws3[n // 2:] == -7.0).all()) and bool((raws3[:, :6] == -7.0).all())
+
+
+@pytest.mark.parametrize("n,n_live", [(1, None), (127, None), (128, None), (129, None), (40000 + 77, None), (20000, 12345), (4096, 0)])
+def test_field_mlp_fwd_tcgen05_vs_warp_mma_vs_oracle(ncn, n, n_live):
+    """ncn_field_mlp_fwd (density trunk -> TruncExp -> [h | d/|d| | 1] -> colour head, ngp_mt.py:157-229): the tcgen05 / TMEM
+    implementation against the warp-MMA one (same fp16 rounding points: every output must agree to fp16 rounding of the hidden
+    states) and against the torch restatement oracle/mlp.py; ragged tiles, a device-side live count below the capacity, saved
+    activations in the tiled panel layout the backward reads, and the inference form (no saved tensors)."""
+    import ctypes as C
+    from ncn_b200 import _lib, tinycudann as tcnn
+    from ncn_b200._lib import check, ptr, stream
+    from oracle import mlp
+    L = _lib.lib()
+    g = torch.Generator(device="cuda").manual_seed(n)
+    sig = tcnn.Network(32, 16, dict(otype="FullyFusedMLP", activation="ReLU", output_activation="None", n_neurons=64, n_hidden_layers=1)).cuda()
+    rgb = tcnn.Network(19, 3, dict(otype="FullyFusedMLP", activation="ReLU", output_activation="Sigmoid", n_neurons=64, n_hidden_layers=2)).cuda()
+    w_sig = (sig.params.detach() * 1.5).half().contiguous(); w_rgb = (rgb.params.detach() * 1.5).half().contiguous()
+    feat = (torch.randn(n, 32, device="cuda", generator=g) * 0.5).half().contiguous()
+    dirs = torch.randn(n, 3, device="cuda", generator=g).contiguous() * 3.0          # not normalised: the kernel normalises
+    n_dev = None if n_live is None else torch.tensor([n_live, 0], dtype=torch.int32, device="cuda")
+    live = n if n_live is None else n_live
+    Ct = 3
+    cap_t = (n + 127) // 128 * 128
+
+    def run(impl, save=True):
+        old = L.ncn_set_field_fwd_impl(impl)
+        try:
+            o = dict(sigmas=torch.full((n,), -7.0, device="cuda"), raws=torch.full((n, Ct), -7.0, device="cuda"),
+                     h=torch.zeros(n, 16, dtype=torch.float16, device="cuda"))
+            if save:
+                o.update(sig_acts=torch.zeros(1, cap_t, 64, dtype=torch.float16, device="cuda"), x_rgb=torch.zeros(n, 32, dtype=torch.float16, device="cuda"),
+                         rgb_acts=torch.zeros(2, cap_t, 64, dtype=torch.float16, device="cuda"), rgb_out=torch.zeros(n, 16, dtype=torch.float16, device="cuda"))
+            check(L.ncn_field_mlp_fwd(ptr(feat), ptr(dirs), ptr(w_sig), ptr(w_rgb), n, ptr(n_dev) if n_dev is not None else None, ptr(o["sigmas"]),
+                                      ptr(o["raws"]), Ct, ptr(o["h"]), ptr(o["sig_acts"]) if save else None, ptr(o["x_rgb"]) if save else None,
+                                      ptr(o["rgb_acts"]) if save else None, ptr(o["rgb_out"]) if save else None, stream()), "field_mlp_fwd")
+            torch.cuda.synchronize()
+            return o
+        finally:
+            L.ncn_set_field_fwd_impl(old)
+
+    tc, wm = run(1), run(0)
+    # rows past the live count are never written
+    for o in (tc, wm):
+        assert (o["sigmas"][live:] == -7.0).all() and (o["raws"][live:] == -7.0).all()
+    if live == 0:
+        return
+    # the hidden states are rounded to fp16 at the same points: tile-by-tile agreement to a few fp16 ulps of the pre-activations
+    torch.testing.assert_close(tc["h"][:live].float(), wm["h"][:live].float(), rtol=2e-3, atol=2e-3)
+    torch.testing.assert_close(tc["sigmas"][:live], wm["sigmas"][:live], rtol=4e-3, atol=1e-6)
+    torch.testing.assert_close(tc["raws"][:live], wm["raws"][:live], rtol=0, atol=2e-3)
+    torch.testing.assert_close(tc["x_rgb"][:live].float(), wm["x_rgb"][:live].float(), rtol=2e-3, atol=2e-3)
+    torch.testing.assert_close(tc["rgb_out"][:live].float(), wm["rgb_out"][:live].float(), rtol=0, atol=2e-3)
+    # saved activations: same tiled panel layout (act_offset), same values to fp16 rounding; compare row-major views of the live rows
+    def rows(a, layers):
+        t = a.view(layers, cap_t // 128, 8, 128, 8).permute(0, 1, 3, 2, 4).reshape(layers, cap_t, 64)      # [tile][f/8][row][8] -> (rows, 64)
+        return t[:, :live].float()
+    torch.testing.assert_close(rows(tc["sig_acts"], 1), rows(wm["sig_acts"], 1), rtol=2e-3, atol=2e-3)
+    torch.testing.assert_close(rows(tc["rgb_acts"], 2), rows(wm["rgb_acts"], 2), rtol=2e-3, atol=3e-3)
+    # against the oracle (tcnn semantics, App. B): h = sigma_net(feat); rgb = rgb_net([d/|d|, h])
+    f32 = feat[:live].float()
+    h_ref = mlp.forward(f32, w_sig.float(), 32, 16, 1, "None")
+    torch.testing.assert_close(tc["h"][:live].float(), h_ref.float(), rtol=1e-2, atol=3e-3)
+    d = dirs[:live] / dirs[:live].norm(dim=1, keepdim=True)
+    rgb_ref = mlp.forward(torch.cat([d, tc["h"][:live].float()], 1), w_rgb.float(), 19, 3, 2, "Sigmoid")
+    torch.testing.assert_close(tc["raws"][:live], rgb_ref.float(), rtol=0, atol=4e-3)
+    torch.testing.assert_close(tc["sigmas"][:live], torch.exp(tc["h"][:live, 0].float()), rtol=1e-5, atol=0)
+    # x_rgb = [h | d | 1...] in the fused column order
+    torch.testing.assert_close(tc["x_rgb"][:live, 16:19].float(), d.half().float(), rtol=0, atol=1e-3)
+    assert (tc["x_rgb"][:live, 19:] == 1).all() and torch.equal(tc["x_rgb"][:live, :16], tc["h"][:live])
+    # inference form: nothing saved, same sigma / rgb
+    inf = run(1, save=False)
+    assert torch.equal(inf["sigmas"][:live], tc["sigmas"][:live]) and torch.equal(inf["raws"][:live], tc["raws"][:live])
