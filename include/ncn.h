@@ -432,7 +432,7 @@ int ncn_normals_from_depth_bw(const float* origin, const float* dir, const float
                               const float* dL_dnormals, int64_t n_tri, float* dL_ddepth,
                               ncn_stream_t stream);
 
-/* Training-batch sampling on the device: the index half of BaseDataset.__getitem__ (datasets/base.py:94-173, max_expand = 0)
+/* Training-batch sampling on the device: the index half of BaseDataset.__getitem__ (datasets/base.py:94-173)
  * and the target gather (:175-183).  strategy 0 = all_images_triang_patch, 1 = same_image_triang_patch (patch_size^2 rays per
  * patch: pix = corner_INDEX + dy*W + dx - the reference adds the offsets to the index into valid_idx['patch_corners'],
  * base.py:164-166, reproduced), 2 = all_images_triang, 3 = same_image_triang (3 rays per triangle: x1, x1 - W, x1 - 1).
@@ -441,6 +441,10 @@ int ncn_normals_from_depth_bw(const float* origin, const float* dir, const float
  * gather_pixels: out[r, :] = table[img_idx[r], pix_idx[r], :] with rows of words_per_pixel 4-byte words (rgb f32 x3, labels ...). */
 int ncn_sample_ray_batch(int strategy, int64_t* seed_dev, int n_rays, int n_poses, int height, int width, int patch_size,
                          int64_t* img_idx, int64_t* pix_idx, ncn_stream_t stream);
+/* the same with the triangle expansion of datasets/base.py:130-141 (`triang_max_expand`): x1 moves max_expand rows down, x2
+ * max_expand rows up, x3 max_expand pixels left, each only when it stays inside the image / its row (triangle strategies) */
+int ncn_sample_ray_batch_ex(int strategy, int64_t* seed_dev, int n_rays, int n_poses, int height, int width, int patch_size,
+                            int max_expand, int64_t* img_idx, int64_t* pix_idx, ncn_stream_t stream);
 int ncn_gather_pixels(const void* table, const int64_t* img_idx, const int64_t* pix_idx, int64_t n, int64_t pixels_per_image,
                       int words_per_pixel, void* out, ncn_stream_t stream);
 
@@ -611,6 +615,10 @@ int ncn_peer_step(ncn_peer* p, float* param, float* m, float* v, const ncn_adam_
 int ncn_peer_set_external_zero(ncn_peer* p, int on);
 int ncn_peer_error(ncn_peer* p, unsigned int* error_host);
 unsigned int ncn_peer_poll(ncn_peer* p);
+/* developer A/B knobs of the reduce kernel: 16-byte loads in flight per peer and thread (1 [default], 2, 4; returns the old value);
+ * peers loaded per batch (2, 4 [default], 8) and CTAs per SM (1, 2 [default]) */
+int ncn_peer_set_loads(int loads_per_peer);
+int ncn_peer_set_shape(int peers_per_batch, int ctas_per_sm);
 /* developer timeline of the last step (synchronises): 8 x ns = [K1 start, wait-0 over, K1 reduced, K2 start, wait-1 over, Adam+publish done, wait-2 over, -] */
 int ncn_peer_debug_times(ncn_peer* p, unsigned long long* times8_host);
 int ncn_peer_set_timeout(double seconds);

@@ -60,9 +60,9 @@ class Profiler:
                         "ncn_march_train_workspace_bytes": 0, "ncn_mlp_bwd_workspace_bytes": 0, "ncn_mlp_acts_bytes": 0, "ncn_mlp_n_params": 0,
                         "ncn_grid_desc_init": 0, "ncn_version": 0, "ncn_set_mlp_bwd_impl": 0, "ncn_set_march_segments": 0, "ncn_set_composite_width": 0, "ncn_set_field_fwd_impl": 0, "ncn_debug_stamp": 1, "ncn_set_grid_bwd_merge": 0, "ncn_set_grid_fwd_coherent": 0, "ncn_error_string": 0, "ncn_device_info": 0,
                         "ncn_comm_unique_id": 0, "ncn_comm_init": 0, "ncn_comm_destroy": 0, "ncn_comm_last_error": 0,
-                        "ncn_sample_ray_batch": 2, "ncn_peer_create": 0, "ncn_peer_grad": 0, "ncn_peer_p16": 0, "ncn_peer_handles": 0, "ncn_peer_connect": 0,
+                        "ncn_sample_ray_batch": 2, "ncn_sample_ray_batch_ex": 2, "ncn_peer_create": 0, "ncn_peer_grad": 0, "ncn_peer_p16": 0, "ncn_peer_handles": 0, "ncn_peer_connect": 0,
                         "ncn_peer_shard": 0, "ncn_peer_step": 2, "ncn_peer_error": 0, "ncn_peer_destroy": 0,
-                        "ncn_peer_poll": 0, "ncn_peer_set_timeout": 0, "ncn_graph_node_counts": 0, "ncn_peer_debug_times": 0, "ncn_peer_set_external_zero": 0}
+                        "ncn_peer_poll": 0, "ncn_peer_set_timeout": 0, "ncn_graph_node_counts": 0, "ncn_peer_debug_times": 0, "ncn_peer_set_external_zero": 0, "ncn_peer_set_loads": 0, "ncn_peer_set_shape": 0}
 
     @classmethod
     def reset(cls):
@@ -209,6 +209,7 @@ SIGNATURES.update({
     "ncn_cluster_tail": (c_i32, [c_vp, c_vp, c_i64, c_i32, c_f32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "ncn_photometric_loss": (c_i32, [c_vp, c_vp, c_vp, c_i64, c_i32, C.POINTER(c_f32), c_f32, c_f32, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "ncn_sample_ray_batch": (c_i32, [c_i32, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp]),
+    "ncn_sample_ray_batch_ex": (c_i32, [c_i32, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp]),
     "ncn_gather_pixels": (c_i32, [c_vp, c_vp, c_vp, c_i64, c_i64, c_i32, c_vp, c_vp]),
     "ncn_normals_from_depth_image": (c_i32, [c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp]),
     "ncn_semantic_ce_loss": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_vp, c_i64, c_f32, c_vp, c_vp, c_vp]),
@@ -249,6 +250,8 @@ SIGNATURES.update({
     "ncn_peer_step": (c_i32, [c_vp, c_vp, c_vp, c_vp, C.POINTER(AdamGroups), c_f32, c_f32, c_f32, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "ncn_peer_error": (c_i32, [c_vp, C.POINTER(C.c_uint32)]),
     "ncn_peer_poll": (C.c_uint32, [c_vp]),
+    "ncn_peer_set_loads": (c_i32, [c_i32]),
+    "ncn_peer_set_shape": (c_i32, [c_i32, c_i32]),
     "ncn_peer_set_external_zero": (c_i32, [c_vp, c_i32]),
     "ncn_peer_debug_times": (c_i32, [c_vp, c_vp]),
     "ncn_peer_set_timeout": (c_i32, [C.c_double]),

@@ -138,12 +138,25 @@ sumsq_kernel(const float* __restrict__ grad, int64_t n, const float* __restrict_
   bool bad = false;
   const int64_t n4 = n >> 2;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+  // four independent 16-byte loads in flight per thread and iteration (the gradient is L2 resident right after the backward:
+  // with one load per iteration the pass ran at 2.2 TB/s, a latency figure); the summation order stays fixed for a given grid
+  float acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (; i + 3 * stride < n4; i += 4 * stride) {
+    const float4 g0 = reinterpret_cast<const float4*>(grad)[i], g1 = reinterpret_cast<const float4*>(grad)[i + stride],
+                 g2 = reinterpret_cast<const float4*>(grad)[i + 2 * stride], g3 = reinterpret_cast<const float4*>(grad)[i + 3 * stride];
+    { const float a = g0.x * gmul, b = g0.y * gmul, c = g0.z * gmul, d = g0.w * gmul; acc += a * a + b * b + c * c + d * d; bad |= !(isfinite(a) && isfinite(b) && isfinite(c) && isfinite(d)); }
+    { const float a = g1.x * gmul, b = g1.y * gmul, c = g1.z * gmul, d = g1.w * gmul; acc1 += a * a + b * b + c * c + d * d; bad |= !(isfinite(a) && isfinite(b) && isfinite(c) && isfinite(d)); }
+    { const float a = g2.x * gmul, b = g2.y * gmul, c = g2.z * gmul, d = g2.w * gmul; acc2 += a * a + b * b + c * c + d * d; bad |= !(isfinite(a) && isfinite(b) && isfinite(c) && isfinite(d)); }
+    { const float a = g3.x * gmul, b = g3.y * gmul, c = g3.z * gmul, d = g3.w * gmul; acc3 += a * a + b * b + c * c + d * d; bad |= !(isfinite(a) && isfinite(b) && isfinite(c) && isfinite(d)); }
+  }
+  for (; i < n4; i += stride) {
     const float4 g = reinterpret_cast<const float4*>(grad)[i];
     const float a = g.x * gmul, b = g.y * gmul, c = g.z * gmul, d = g.w * gmul;
     acc += a * a + b * b + c * c + d * d;
     bad |= !(isfinite(a) && isfinite(b) && isfinite(c) && isfinite(d));
   }
+  acc = (acc + acc1) + (acc2 + acc3);
   const int64_t t = (n4 << 2) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t < n) { const float a = grad[t] * gmul; acc += a * a; bad |= !isfinite(a); }
   acc = warp_sum(acc);
@@ -333,6 +346,7 @@ __device__ __forceinline__ void peer_wait(PeerSync* me, int phase, int world, un
 }
 __device__ __forceinline__ bool peer_failed(PeerSync* me) { return *reinterpret_cast<volatile unsigned int*>(&me->error) != 0u; }
 
+template <int U, int B>
 __global__ void __launch_bounds__(256, 2)
 peer_reduce_kernel(PeerPtrs pp, int rank, int world, int64_t lo4, int64_t hi4, float* my_grad /* == pp.grad[rank] */,
                    const float* __restrict__ grad_div) {
@@ -355,32 +369,35 @@ peer_reduce_kernel(PeerPtrs pp, int rank, int world, int64_t lo4, int64_t hi4, f
   float acc = 0.f;
   bool bad = peer_failed(me);                    // a peer never arrived: the sums below may be incomplete -> poison the norm
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i0 = lo4 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < hi4; i0 += 2 * stride) {
-    const int64_t i1 = i0 + stride;
-    const bool two = i1 < hi4;
-    float4 a[kPeerMax], b[kPeerMax];
+  // U float4 per peer and iteration: W * U independent 16-byte loads in flight per thread (sums in fixed rank order).
+  // Measured on 8 GPUs (profiles/r2_timeline_8gpu_*, same box): 4 loads in flight per thread (U = 1, four peers at a time) pull the
+  // 40 MB in 73-81 us, 8 in 104-106 us, 16 in 103-139 us - more requests in flight congest the fabric / the serving GPUs'
+  // memory systems instead of hiding latency, so the default is the shallowest form.
+  for (int64_t i0 = lo4 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < hi4; i0 += U * stride) {
+    float4 sum[U];
 #pragma unroll
-    for (int q = 0; q < kPeerMax; ++q) {
-      if (q < world) {
-        a[q] = __ldcs(reinterpret_cast<const float4*>(pp.grad[q]) + i0);
-        if (two) b[q] = __ldcs(reinterpret_cast<const float4*>(pp.grad[q]) + i1);
-      }
-    }
-    float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0;
+    for (int u = 0; u < U; ++u) sum[u] = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-    for (int q = 0; q < kPeerMax; ++q) {         // fixed order 0..W-1: the sum does not depend on who computes it or when
-      if (q < world) {
-        s0.x += a[q].x; s0.y += a[q].y; s0.z += a[q].z; s0.w += a[q].w;
-        if (two) { s1.x += b[q].x; s1.y += b[q].y; s1.z += b[q].z; s1.w += b[q].w; }
-      }
+    for (int q0 = 0; q0 < kPeerMax; q0 += B) {          // B peers at a time: B * U loads in flight
+      float4 v[B][U];
+#pragma unroll
+      for (int qq = 0; qq < B; ++qq)
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+          if (q0 + qq < world && i0 + u * stride < hi4) v[qq][u] = __ldcs(reinterpret_cast<const float4*>(pp.grad[q0 + qq]) + i0 + u * stride);
+#pragma unroll
+      for (int qq = 0; qq < B; ++qq)
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+          if (q0 + qq < world && i0 + u * stride < hi4) { sum[u].x += v[qq][u].x; sum[u].y += v[qq][u].y; sum[u].z += v[qq][u].z; sum[u].w += v[qq][u].w; }
     }
-    reinterpret_cast<float4*>(my_grad)[i0] = s0;
-    { const float x = s0.x * gmul, y = s0.y * gmul, z = s0.z * gmul, w = s0.w * gmul;
-      acc += x * x + y * y + z * z + w * w; bad |= !(isfinite(x) && isfinite(y) && isfinite(z) && isfinite(w)); }
-    if (two) {
-      reinterpret_cast<float4*>(my_grad)[i1] = s1;
-      const float x = s1.x * gmul, y = s1.y * gmul, z = s1.z * gmul, w = s1.w * gmul;
-      acc += x * x + y * y + z * z + w * w; bad |= !(isfinite(x) && isfinite(y) && isfinite(z) && isfinite(w));
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (i0 + u * stride < hi4) {
+        reinterpret_cast<float4*>(my_grad)[i0 + u * stride] = sum[u];
+        const float x = sum[u].x * gmul, y = sum[u].y * gmul, z = sum[u].z * gmul, w = sum[u].w * gmul;
+        acc += x * x + y * y + z * z + w * w; bad |= !(isfinite(x) && isfinite(y) && isfinite(z) && isfinite(w));
+      }
     }
   }
   if (bad) acc = __int_as_float(0x7fc00000);
@@ -505,6 +522,16 @@ struct ncn_peer {
   unsigned int* err_host;               // cudaHostAllocMapped: written by the kernels on a time-out, read by ncn_peer_poll
 };
 
+// developer A/B knob: 16-byte loads in flight per peer and thread in the reduce kernel (1, 2 [default] or 4)
+static int g_peer_loads = 1, g_peer_batch = 4, g_peer_ctas = 2;
+extern "C" int ncn_peer_set_loads(int u) { const int old = g_peer_loads; if (u == 1 || u == 2 || u == 4) g_peer_loads = u; return old; }
+// further A/B knobs of the reduce kernel: peers loaded per batch (2, 4 [default], 8; with loads = 1) and CTAs per SM (1 or 2 [default])
+extern "C" int ncn_peer_set_shape(int peers_per_batch, int ctas_per_sm) {
+  if (peers_per_batch == 2 || peers_per_batch == 4 || peers_per_batch == 8) g_peer_batch = peers_per_batch;
+  if (ctas_per_sm == 1 || ctas_per_sm == 2) g_peer_ctas = ctas_per_sm;
+  return NCN_OK;
+}
+
 extern "C" int ncn_peer_create(ncn_peer** out, int rank, int world, int64_t n_params) {
   NCN_CHECK_PTR(out);
   NCN_CHECK_SIZE(world >= 1 && world <= ncn::kPeerMax && rank >= 0 && rank < world && n_params > 0 && (n_params & 3) == 0);
@@ -587,7 +614,15 @@ extern "C" int ncn_peer_step(ncn_peer* p, float* param, float* m, float* v, cons
   int grid = ncn::sm_count() * 2;
   if (grid > ncn::kSumsqMaxBlocks) grid = ncn::kSumsqMaxBlocks;
   cudaStream_t st = ncn::as_stream(stream);
-  ncn::peer_reduce_kernel<<<grid, 256, 0, st>>>(p->ptrs, p->rank, p->world, lo4, hi4, p->grad, grad_div_dev);
+  int grid1 = ncn::sm_count() * g_peer_ctas;
+  if (grid1 > ncn::kSumsqMaxBlocks) grid1 = ncn::kSumsqMaxBlocks;
+#define NCN_K1(U, B) ncn::peer_reduce_kernel<U, B><<<grid1, 256, 0, st>>>(p->ptrs, p->rank, p->world, lo4, hi4, p->grad, grad_div_dev)
+  if (g_peer_loads == 4) NCN_K1(4, 4);
+  else if (g_peer_loads == 2) NCN_K1(2, 4);
+  else if (g_peer_batch == 2) NCN_K1(1, 2);
+  else if (g_peer_batch == 8) NCN_K1(1, 8);
+  else NCN_K1(1, 4);
+#undef NCN_K1
   NCN_LAUNCH_OK();
   ncn::peer_adam_kernel<<<grid, 256, 0, st>>>(p->ptrs, p->rank, p->world, lo4, hi4, n4, param, p->grad, m, v, a, grad_div_dev,
                                               skip_dev, lr_bc_dev, sumsq_out_dev, p->external_zero ? 0 : 1);

@@ -1,11 +1,13 @@
 // Training-batch sampling on the device: the index half of BaseDataset.__getitem__
 // (datasets/base.py:94-173) and its target gather (:175-183) - replaces numpy sampling in DataLoader workers + the H2D copy
 // of the batch by two small kernels, so a step needs NO host input at all once the images live in HBM.
-//   strategies (max_expand = 0):
+//   strategies:
 //     0 all_images_triang_patch   n_patches = R / p^2 patches, image per patch, corner per patch, p x p pixels each
 //     1 same_image_triang_patch   one image for the whole batch
 //     2 all_images_triang         n_tri = R / 3 triangles (x1, x2 = up, x3 = left), image per triangle
 //     3 same_image_triang         one image
+//   max_expand > 0 (triangle strategies, base.py:130-141): x1 moves `expand` rows down when that stays inside the image, x2
+//   `expand` rows up when that stays inside, x3 `expand` pixels left when that stays in its row (python floor division)
 // Reference quirk kept: the patch corner is drawn as an INDEX into valid_idx['patch_corners'] (0 <= c < (H-p+1)(W-p+1)) and
 // that index - not the pixel id it points at - is what the patch offsets are added to (base.py:164-166).
 // Random numbers: counter-based splitmix64 of (seed, item, draw); the seed lives in device memory and is advanced by the
@@ -25,7 +27,7 @@ __device__ __forceinline__ uint64_t smp_hash(uint64_t seed, uint64_t i, uint32_t
 __device__ __forceinline__ int64_t smp_below(uint64_t h, int64_t n) { return (int64_t)(((h >> 32) * (uint64_t)n) >> 32); }
 
 __global__ void __launch_bounds__(256)
-sample_batch_kernel(int strategy, int64_t* __restrict__ seed_dev, int n_rays, int n_poses, int H, int W, int patch,
+sample_batch_kernel(int strategy, int64_t* __restrict__ seed_dev, int n_rays, int n_poses, int H, int W, int patch, int max_expand,
                     int64_t* __restrict__ img_idx, int64_t* __restrict__ pix_idx) {
   const uint64_t seed = (uint64_t)*seed_dev;
   const bool patches = strategy <= 1, same = (strategy & 1) != 0;
@@ -45,8 +47,16 @@ sample_batch_kernel(int strategy, int64_t* __restrict__ seed_dev, int n_rays, in
       const int64_t n_valid = (int64_t)(H - 2) * (W - 2);
       const int64_t t = smp_below(smp_hash(seed, (uint64_t)q, 1), n_valid);
       const int64_t y = 1 + t / (W - 2), x = 1 + t % (W - 2);
-      const int64_t x1 = y * W + x;
-      pix = j == 0 ? x1 : (j == 1 ? x1 - W : x1 - 1);
+      int64_t x1 = y * W + x, x2 = x1 - W, x3 = x1 - 1;
+      if (max_expand > 0) {
+        const int64_t e = max_expand, NP = (int64_t)H * W;
+        if (x1 + e * W < NP) x1 += e * W;
+        if (x2 - e * W >= 0) x2 -= e * W;
+        const int64_t x3n = x3 - e;
+        const int64_t row_n = x3n >= 0 ? x3n / W : -((-x3n + W - 1) / W);      // floor division, as numpy's //
+        if (row_n == x3 / W) x3 = x3n;
+      }
+      pix = j == 0 ? x1 : (j == 1 ? x2 : x3);
     }
     img_idx[r] = img; pix_idx[r] = pix;
   }
@@ -70,15 +80,22 @@ gather_pixels_kernel(const uint32_t* __restrict__ table, const int64_t* __restri
 
 using namespace ncn;
 
+extern "C" int ncn_sample_ray_batch_ex(int strategy, int64_t* seed_dev, int n_rays, int n_poses, int height, int width, int patch_size,
+                                       int max_expand, int64_t* img_idx, int64_t* pix_idx, ncn_stream_t stream);
 extern "C" int ncn_sample_ray_batch(int strategy, int64_t* seed_dev, int n_rays, int n_poses, int height, int width, int patch_size,
                                     int64_t* img_idx, int64_t* pix_idx, ncn_stream_t stream) {
-  NCN_CHECK_SIZE(n_rays >= 0 && n_poses >= 1 && strategy >= 0 && strategy <= 3);
+  return ncn_sample_ray_batch_ex(strategy, seed_dev, n_rays, n_poses, height, width, patch_size, 0, img_idx, pix_idx, stream);
+}
+
+extern "C" int ncn_sample_ray_batch_ex(int strategy, int64_t* seed_dev, int n_rays, int n_poses, int height, int width, int patch_size,
+                                       int max_expand, int64_t* img_idx, int64_t* pix_idx, ncn_stream_t stream) {
+  NCN_CHECK_SIZE(n_rays >= 0 && n_poses >= 1 && strategy >= 0 && strategy <= 3 && max_expand >= 0);
   if (strategy <= 1) NCN_CHECK_SIZE(patch_size >= 2 && height >= patch_size && width >= patch_size);
   else NCN_CHECK_SIZE(height >= 3 && width >= 3);
   if (n_rays == 0) return NCN_OK;
   NCN_CHECK_PTR(seed_dev); NCN_CHECK_PTR(img_idx); NCN_CHECK_PTR(pix_idx);
   sample_batch_kernel<<<(unsigned)ceil_div(n_rays, 256), 256, 0, as_stream(stream)>>>(strategy, seed_dev, n_rays, n_poses, height, width,
-                                                                                     patch_size, img_idx, pix_idx);
+                                                                                     patch_size, max_expand, img_idx, pix_idx);
   NCN_LAUNCH_OK();
   sample_advance_kernel<<<1, 1, 0, as_stream(stream)>>>(seed_dev);
   NCN_LAUNCH_OK();

@@ -288,8 +288,8 @@ class FusedStep:
         self.d_depth.zero_()
         if self.dev_sampling is not None:    # BaseDataset.__getitem__ (datasets/base.py:94-183) on the device: indices + target gather
             sm = self.dev_sampling
-            ck(L.ncn_sample_ray_batch(sm["strategy"], ptr(sm["seed"]), R, sm["n_poses"], sm["H"], sm["W"], sm["patch"], ptr(self.b_img),
-                                      ptr(self.b_pix), st), "sample_ray_batch")
+            ck(L.ncn_sample_ray_batch_ex(sm["strategy"], ptr(sm["seed"]), R, sm["n_poses"], sm["H"], sm["W"], sm["patch"], sm["max_expand"],
+                                         ptr(self.b_img), ptr(self.b_pix), st), "sample_ray_batch")
             ck(L.ncn_gather_pixels(ptr(sm["images"]), ptr(self.b_img), ptr(self.b_pix), R, sm["H"] * sm["W"], 3, ptr(self.target), st), "gather_rgb")
             if sm["labels"] is not None:
                 ck(L.ncn_gather_pixels(ptr(sm["labels"]), ptr(self.b_img), ptr(self.b_pix), R, sm["H"] * sm["W"], 2, ptr(self.sem_target), st),
@@ -665,7 +665,8 @@ class FusedStep:
 
     STRATEGIES = {"all_images_triang_patch": 0, "same_image_triang_patch": 1, "all_images_triang": 2, "same_image_triang": 3}
 
-    def use_device_sampling(self, images, height, width, strategy="all_images_triang_patch", patch_size=8, sem_labels=None, seed=0):
+    def use_device_sampling(self, images, height, width, strategy="all_images_triang_patch", patch_size=8, sem_labels=None, seed=0,
+                            max_expand=0):
         """Draw every batch on the device (BaseDataset.__getitem__, datasets/base.py:94-183):
         images (P, H*W, 3) f32 resident in HBM (the reference keeps `rays` there too, train_nerf.py:239-240), optional
         sem_labels (P, H*W) i64.  Indices, target gather and ray generation become the first nodes of the step graph;
@@ -679,7 +680,11 @@ class FusedStep:
                 raise RuntimeError("use_device_sampling: sem_labels given but the model has no semantic head")
             sem_labels = sem_labels.to(self.dev, torch.int64).contiguous()
         self.use_pixel_batches(True)
+        if self.tr.hp.get("random_tr_poses", False):
+            raise NotImplementedError("use_device_sampling: random_tr_poses (half of the batch from generated poses, datasets/base.py:106-126, "
+                                      "235-263) is carried by the host data path only")
         self.dev_sampling = dict(images=images, labels=sem_labels, H=int(height), W=int(width), n_poses=P, patch=int(patch_size),
+                                 max_expand=int(max_expand),      # triang_max_expand of the triangle strategies (base.py:130-141)
                                  strategy=self.STRATEGIES[strategy], seed=torch.full((1,), int(seed), dtype=torch.int64, device=self.dev))
         self.set_triangles(self.batch_triangles(self.R, strategy, patch_size))
         self.graph = None

@@ -91,6 +91,11 @@ class PeerLink:
         self.rank, self.world_size, self.n = rank, world_size, int(n_params)
         self.handle = None
         self.external_zero = False
+        import os
+        if os.environ.get("NCN_PEER_LOADS"):       # developer A/B only
+            L.ncn_peer_set_loads(int(os.environ["NCN_PEER_LOADS"]))
+        if os.environ.get("NCN_PEER_BATCH") or os.environ.get("NCN_PEER_CTAS"):
+            L.ncn_peer_set_shape(int(os.environ.get("NCN_PEER_BATCH", "4")), int(os.environ.get("NCN_PEER_CTAS", "2")))
         h = C.c_void_p()
         if world_size == 1:
             check(L.ncn_peer_create(C.byref(h), rank, world_size, self.n), "peer_create")

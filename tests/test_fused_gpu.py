@@ -371,3 +371,35 @@ def test_device_batch_sampling(strategy):
     assert not torch.equal(first, fs.b_pix) and int(fs.dev_sampling["seed"]) >= 5
     d, n = fs.stats_host()
     assert np.isfinite(d["total"]) and n > 1536
+
+
+@pytest.mark.parametrize("strategy,expand", [("all_images_triang", 3), ("same_image_triang", 40), ("all_images_triang", 0)])
+def test_device_batch_sampling_triangle_expansion(strategy, expand):
+    """`triang_max_expand` of the triangle strategies (datasets/base.py:130-141): with the same seed the expanded batch must be the
+    reference's arithmetic applied to the unit triangles - x1 + e W if it stays below H W, x2 - e W if it stays >= 0, x3 - e if
+    it stays in its row (numpy floor division)."""
+    import ncn_b200  # noqa: F401
+    from ncn_b200 import _lib
+    from ncn_b200._lib import check, ptr, stream
+    from ncn_b200.fused import FusedStep
+    L = _lib.lib()
+    H, W, P = 48, 64, 5
+    R = 3 * 4000
+    sid = FusedStep.STRATEGIES[strategy]
+    out = {}
+    for e in (0, expand):
+        seed = torch.full((1,), 77, dtype=torch.int64, device="cuda")
+        img = torch.empty(R, dtype=torch.int64, device="cuda"); pix = torch.empty(R, dtype=torch.int64, device="cuda")
+        check(L.ncn_sample_ray_batch_ex(sid, ptr(seed), R, P, H, W, 8, e, ptr(img), ptr(pix), stream()))
+        out[e] = (img.cpu().numpy(), pix.cpu().numpy().reshape(-1, 3))
+    assert np.array_equal(out[0][0], out[expand][0])                       # the images do not depend on the expansion
+    x1, x2, x3 = out[0][1][:, 0], out[0][1][:, 1], out[0][1][:, 2]
+    assert np.array_equal(x2, x1 - W) and np.array_equal(x3, x1 - 1)
+    N = H * W
+    x1n = np.where(x1 + expand * W < N, x1 + expand * W, x1)              # base.py:132-133
+    x2n = np.where(x2 - expand * W >= 0, x2 - expand * W, x2)             # :135-136
+    x3n = np.where((x3 - expand) // W == x3 // W, x3 - expand, x3)        # :138-140
+    got = out[expand][1]
+    assert np.array_equal(got[:, 0], x1n) and np.array_equal(got[:, 1], x2n) and np.array_equal(got[:, 2], x3n)
+    if expand:
+        assert (x1n != x1).any() and (x1n == x1).any() and (x3n != x3).any() and (x3n == x3).any()      # both branches occur
