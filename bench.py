@@ -391,12 +391,16 @@ def run_ours(args):
         achieved = per_unit * units / (avg_ms * 1e-3) / 1e9
         peak = float(peaks.get("hbm_gbs", 6650.0))
         traffic = None
-        try:      # DRAM bytes per launch of this kernel from the committed ncu --set full capture (profiles/)
-            traffic = float(json.load(open(os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")))[top]["bytes_per_launch"])
-        except Exception:  # noqa: BLE001
-            pass
+        traffic_src = None
+        for tf in ("r2_ncu_traffic.json", "r1_ncu_traffic.json"):      # DRAM bytes per launch of this kernel from the committed ncu --set full capture
+            try:
+                traffic = float(json.load(open(os.path.join(ROOT, "profiles", tf)))[top]["bytes_per_launch"])
+                traffic_src = "profiles/" + tf
+                break
+            except Exception:  # noqa: BLE001
+                pass
         roofline = {"kernel": top, "bound": bound, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": traffic, "traffic_source": "profiles/r1_ncu_traffic.json (ncu --set full, dram read+write per launch)" if traffic else None,
+                    "traffic": traffic, "traffic_source": (traffic_src + " (ncu --set full, dram read+write per launch)") if traffic else None,
                     "note": NOTES.get(top), "avg_launch_ms": avg_ms, "launches_timed": calls,
                     "timed_in": "instrumented eager pass of the same step right after the timed region (CUDA events around the launch)",
                     "algorithmic_bytes_per_launch": per_unit * units,

@@ -709,19 +709,35 @@ kmeans_kernel(const float* __restrict__ x_in, int64_t n, ncn_kmeans_params p, fl
   }
   ++xround;
   __syncthreads();
-  // labels + first pass: sign-flipped member sums per selected cluster, 2^-20 fixed point in 64-bit shared-memory atomics
-  for (int j = tid + (int)rank * kKmThreads; j < nv; j += kKmThreads * CL) {
-    const int r = valid_idx[j];
-    const int l = s_lab[assign[r]];
-    ch.labels[r] = l;
-    if (l != 0) {
-      const int k = (l > 0 ? l : -l) - 1;
-      const float sg = l > 0 ? 1.f : -1.f;
-      atomicAdd(reinterpret_cast<unsigned long long*>(&s_p1[4 * k]), (unsigned long long)(long long)__float2int_rn(sg * x[3 * r] * kKmFix));
-      atomicAdd(reinterpret_cast<unsigned long long*>(&s_p1[4 * k + 1]), (unsigned long long)(long long)__float2int_rn(sg * x[3 * r + 1] * kKmFix));
-      atomicAdd(reinterpret_cast<unsigned long long*>(&s_p1[4 * k + 2]), (unsigned long long)(long long)__float2int_rn(sg * x[3 * r + 2] * kKmFix));
-      atomicAdd(reinterpret_cast<unsigned long long*>(&s_p1[4 * k + 3]), 1ull);
+  // labels + first pass: sign-flipped member sums per selected cluster in 2^-20 fixed point - warp-aggregated (redux.sync) into a
+  // warp-private row of integer accumulators, no shared-memory atomics (64-bit shared atomics compile to CAS spin loops)
+  {
+    int* wacc = s_wacc + wid * 12;
+    if (lane < 12) wacc[lane] = 0;
+    __syncwarp();
+    const int j_end = ((nv + kKmThreads * CL - 1) / (kKmThreads * CL)) * (kKmThreads * CL);      // whole warps take part in every round
+    for (int j = tid + (int)rank * kKmThreads; j < j_end; j += kKmThreads * CL) {
+      int l = 0, k = 0;
+      float px = 0.f, py = 0.f, pz = 0.f;
+      if (j < nv) {
+        const int r = valid_idx[j];
+        l = s_lab[assign[r]];
+        ch.labels[r] = l;
+        if (l != 0) {
+          k = (l > 0 ? l : -l) - 1;
+          const float sg = l > 0 ? 1.f : -1.f;
+          px = sg * x[3 * r]; py = sg * x[3 * r + 1]; pz = sg * x[3 * r + 2];
+        }
+      }
+      warp_accumulate_by_key(k, l != 0, px, py, pz, wacc, lane);
     }
+  }
+  __syncthreads();
+  if (tid < 12) {
+    long long t = 0;
+#pragma unroll
+    for (int w = 0; w < kKmThreads / 32; ++w) t += s_wacc[w * 12 + tid];
+    s_p1[tid] = t;
   }
   __syncthreads();
   if (wid == 0) {                                                 // X2: fixed-point first-pass sums of all CTAs (12 x i64 = 6 slots)
@@ -1348,6 +1364,7 @@ extern "C" int ncn_cluster_chain(const float* origin, const float* dir, const fl
   NCN_CHECK_PTR(p);
   if (p->k < 3 || p->k > 32) return NCN_E_UNSUPPORTED;
   NCN_CHECK_SIZE(n_tri >= 0);
+  if (n_tri > 262144) return NCN_E_UNSUPPORTED;      // the epilogue's warp-private 32-bit fixed-point sums cover 2047 rows per warp
   NCN_CHECK_PTR(sel); NCN_CHECK_PTR(losses); NCN_CHECK_PTR(stats);
   if (n_tri > 0) {
     NCN_CHECK_PTR(origin); NCN_CHECK_PTR(dir); NCN_CHECK_PTR(depth); NCN_CHECK_PTR(idx1); NCN_CHECK_PTR(idx2); NCN_CHECK_PTR(idx3);

@@ -81,6 +81,29 @@ __device__ __forceinline__ void dout_fetch(DoutRaw<OUT>& R, int64_t row, int64_t
   }
 }
 
+// L2 prefetch of the rows dout_fetch will read for `row` (no destination registers: fire and forget).  The register-resident
+// prefetch this replaces looked free in the source and cost 2600 clocks per tile in the trace: ptxas recycled the loads'
+// destination registers for the next address computations, so every load waited for the previous one to RETURN (ncu source
+// page: 19 % of the kernel's stall samples on those LDG / LDC instructions, long scoreboard).  Now the rows are pulled into the
+// L2 a tile ahead and fetched at the top of their own tile, one L2 round trip.
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+template <int OUT>
+__device__ __forceinline__ void dout_prefetch(int64_t row, int64_t n, const __half* __restrict__ dout, const __half* __restrict__ out, int out_act,
+                                              const ncn_mlp_bwd_src& src) {
+  if (row >= n) return;
+  if (src.mode == 0) {
+    prefetch_l2(dout + row * OUT);
+  } else if (src.mode == 1) {
+    prefetch_l2(src.d_raws + row * src.c_total + src.c_off);
+  } else {
+    prefetch_l2(reinterpret_cast<const __half*>(src.dx_rgb) + row * 32);
+    prefetch_l2(src.d_sigmas + row);
+    prefetch_l2(reinterpret_cast<const __half*>(src.h) + row * 16);
+    if (src.dx_extra != nullptr) prefetch_l2(reinterpret_cast<const __half*>(src.dx_extra) + row * 16);
+  }
+  if (out_act == NCN_ACT_SIGMOID || out_act == NCN_ACT_EXP) prefetch_l2(out + row * OUT);
+}
+
 template <int OUT>
 __device__ __forceinline__ void dout_finish(const DoutRaw<OUT>& R, bool valid, int out_act, const ncn_mlp_bwd_src& src, uint32_t (&drow)[OUT / 2]) {
 #pragma unroll
@@ -188,7 +211,7 @@ mlp_bwd_tc05_kernel(const __half* __restrict__ x, const __half* __restrict__ w, 
   DoutRaw<OUT> raw;
   if (cur < n_tiles) {
     stage_rows<IN>(x, cur * kTile, n, sets + LY::kPdzl + LY::kPact);
-    dout_fetch<OUT>(raw, cur * kTile + tid, n, dout, out, out_act, src);
+    dout_prefetch<OUT>(cur * kTile + tid, n, dout, out, out_act, src);
   }
   load_w_panel_async(w + 64 * IN + (NH - 1) * 64 * 64, OUT, 64, WBl);
   for (int i = 0; i < NH - 1; ++i) load_w_panel_async(w + 64 * IN + i * 64 * 64, 64, 64, WBh + i * 64 * 64);
@@ -221,6 +244,7 @@ mlp_bwd_tc05_kernel(const __half* __restrict__ x, const __half* __restrict__ w, 
     // (0) this tile's dL/dout row (fetched one tile ago) -> dz_last panel; wait for its staged x rows and activations
     {
       uint32_t drow[OUT / 2];
+      dout_fetch<OUT>(raw, row, n, dout, out, out_act, src);      // L2 hits: prefetched one tile ago
       dout_finish<OUT>(raw, row < n, out_act, src, drow);
 #pragma unroll
       for (int j = 0; j < OUT / 8; ++j)
@@ -266,7 +290,7 @@ mlp_bwd_tc05_kernel(const __half* __restrict__ x, const __half* __restrict__ w, 
     // prefetch the next tile's x rows (cp.async) and dL/dout row (registers)
     if (nxt < n_tiles) {
       stage_rows<IN>(x, nxt * kTile, n, sets + (size_t)(set ^ 1) * LY::kSet + LY::kPdzl + LY::kPact);
-      dout_fetch<OUT>(raw, nxt * kTile + tid, n, dout, out, out_act, src);
+      dout_prefetch<OUT>(nxt * kTile + tid, n, dout, out, out_act, src);
     }
     cp_async_commit();
     NCN_TRACE(4);

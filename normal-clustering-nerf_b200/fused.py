@@ -390,7 +390,7 @@ class FusedStep:
             x1, x2, x3 = ptr(self.tri[0]), ptr(self.tri[1]), ptr(self.tri[2])
             t_sim = 1.0 - float(hp["loss_norm_can_tres"])
             # rays_o := rays_d (rendering.py:227 quirk)
-            if self.fuse_chain:
+            if self.fuse_chain and self.M <= 262144 and self.km_params.k <= 32:
                 # normals -> k-means -> selection -> cluster statistics + losses in ONE cluster launch, then dL/dnormals + dL/ddepth
                 ck(L.ncn_cluster_chain(ptr(self.rays_d), ptr(self.rays_d), ptr(self.depth), x1, x2, x3, self.M, C.byref(self.km_params), t_sim,
                                        ptr(self.normals), ptr(self.centroids), ptr(self.assign), ptr(self.n_valid), ptr(self.labels), ptr(self.sel),

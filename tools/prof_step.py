@@ -24,7 +24,12 @@ fs = tr.fused_step(use_graph=False)
 fs.set_triangles(torch.from_numpy(b["tri"]).to(dev))
 if "sem" in heads:
     fs.sem_target.copy_(torch.randint(0, 4, (R,), device=dev))
-for i in range(int(sys.argv[1]) if len(sys.argv) > 1 else 3):
+n_steps = int(sys.argv[1]) if len(sys.argv) > 1 else 3
+for i in range(n_steps):
+    if i == n_steps - 1:          # ncu --nvtx --nvtx-include "prof/" captures only the last (warm) step
+        torch.cuda.synchronize()
+        torch.cuda.nvtx.range_push("prof")
     tr.train_step_fused(ro, rd, rgb, update_grid=False)
 torch.cuda.synchronize()
+torch.cuda.nvtx.range_pop()
 print("ok", fs.stats_host())

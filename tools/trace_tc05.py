@@ -37,4 +37,4 @@ for b in (0, 1, 5):
         r = t[b, it]
         if r[0] == 0:
             break
-        print("  tile", it, " ".join(f"{int(v - base) if v else -1:7d}" for v in r[:13]))
+        print("  tile", it, " ".join(f"{int(v - base) if v else -1:7d}" for v in r[:15]))
