@@ -281,6 +281,12 @@ int ncn_grid_bwd(const ncn_grid_desc* desc_host, const float* x, const void* dL_
 int ncn_grid_bwd_levels(const ncn_grid_desc* desc_host, const float* x, const void* dL_dy_f16, int64_t n, float* grad_table,
                         float grad_scale, const float* xform_host, const int32_t* n_dev, int level_begin, int level_end,
                         int ctas_per_sm, ncn_stream_t stream);
+/* ncn_grid_bwd into an fp16 gradient table (entries x __half2, F = 2 only; ACCUMULATED, caller zeroes): the accumulation
+ * type tiny-cuda-nn itself uses for F > 1 (grid.h, `grad_t`): run sums are still formed in fp32 registers, the reductions are
+ * packed red.global.add.noftz.f16x2 / .v2.f16x2 (4 / 8 bytes instead of 8 / 16).  The caller's loss scale must keep the sums
+ * inside fp16 range.  A selectable mode, measured by tools/sweep_hashgrid.py; the training step uses the fp32 table. */
+int ncn_grid_bwd_f16(const ncn_grid_desc* desc_host, const float* x, const void* dL_dy_f16, int64_t n, void* grad_table_f16,
+                     float grad_scale, const float* xform_host, const int32_t* n_dev, ncn_stream_t stream);
 /* 1 (default): ncn_grid_bwd merges same-entry contributions of consecutive samples inside a warp before the
  * scatter; 0: one reduction per corner.  Returns the old value. */
 int ncn_set_grid_bwd_merge(int on);
@@ -388,6 +394,12 @@ int ncn_set_mlp_bwd_impl(int impl);
 /* implementation of ncn_field_mlp_fwd: 1 = tcgen05 / TMEM accumulators, one 128-sample tile per CTA iteration (default);
  * 0 = warp-level mma.sync.  Returns the previous value (developer A/B knob; results agree to fp16 rounding of the activations). */
 int ncn_set_field_fwd_impl(int impl);
+/* Programmatic dependent launch along the training step's serial kernel chain (encoder -> field MLPs -> compositing -> cluster
+ * chain -> ... -> table backward): 1 (default) = each of those kernels is launched with
+ * cudaLaunchAttributeProgrammaticStreamSerialization, sets up (weights, barriers, TMEM, first loads of tensors that older kernels
+ * produced) while its stream predecessor drains and executes griddepcontrol.wait before it touches the predecessor's output;
+ * 0 = plain stream order.  Results are identical.  Returns the previous value. */
+int ncn_set_pdl(int on);
 /* ncn_march_train* on the constant-step path (cascades == 1, exp_step_factor == 0): 1 (default) = four lanes per ray, each
  * marching a quarter of the candidate sequence (bit-identical output); 0 = one lane per ray; 2 = four lanes with every
  * segment re-marched from its predecessor's landing point (test mode for the repair path).  Returns the old value. */

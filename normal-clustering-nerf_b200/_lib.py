@@ -46,6 +46,7 @@ SIGNATURES = {
     "ncn_segment_csr_sum": (c_i32, [c_vp, c_vp, c_i64, c_i32, c_vp, c_vp]),
     "ncn_set_composite_width": (c_i32, [c_i32]),
     "ncn_set_field_fwd_impl": (c_i32, [c_i32]),
+    "ncn_set_pdl": (c_i32, [c_i32]),
 }
 
 
@@ -58,7 +59,7 @@ class Profiler:
     events = []            # (name, start_event, end_event, n_items)
     KERNELS_PER_CALL = {"ncn_march_train": 3, "ncn_march_train_count": 3, "ncn_cluster_tail": 2, "ncn_kmeans_workspace_bytes": 0,
                         "ncn_march_train_workspace_bytes": 0, "ncn_mlp_bwd_workspace_bytes": 0, "ncn_mlp_acts_bytes": 0, "ncn_mlp_n_params": 0,
-                        "ncn_grid_desc_init": 0, "ncn_version": 0, "ncn_set_mlp_bwd_impl": 0, "ncn_set_march_segments": 0, "ncn_set_composite_width": 0, "ncn_set_field_fwd_impl": 0, "ncn_debug_stamp": 1, "ncn_set_grid_bwd_merge": 0, "ncn_set_grid_fwd_coherent": 0, "ncn_error_string": 0, "ncn_device_info": 0,
+                        "ncn_grid_desc_init": 0, "ncn_version": 0, "ncn_set_mlp_bwd_impl": 0, "ncn_set_march_segments": 0, "ncn_set_composite_width": 0, "ncn_set_field_fwd_impl": 0, "ncn_set_pdl": 0, "ncn_debug_stamp": 1, "ncn_set_grid_bwd_merge": 0, "ncn_set_grid_fwd_coherent": 0, "ncn_error_string": 0, "ncn_device_info": 0,
                         "ncn_comm_unique_id": 0, "ncn_comm_init": 0, "ncn_comm_destroy": 0, "ncn_comm_last_error": 0,
                         "ncn_sample_ray_batch": 2, "ncn_sample_ray_batch_ex": 2, "ncn_peer_create": 0, "ncn_peer_grad": 0, "ncn_peer_p16": 0, "ncn_peer_handles": 0, "ncn_peer_connect": 0,
                         "ncn_peer_shard": 0, "ncn_peer_step": 2, "ncn_peer_error": 0, "ncn_peer_destroy": 0,
@@ -126,6 +127,8 @@ def lib():
             fn.restype = res
             fn.argtypes = args
         _lib = _Proxy(h)
+        if os.environ.get("NCN_PDL", "1") == "0":        # developer A/B knob
+            h.ncn_set_pdl(0)
     return _lib
 
 
@@ -179,6 +182,7 @@ SIGNATURES.update({
     "ncn_grid_desc_init": (c_i64, [C.POINTER(GridDesc)]),
     "ncn_grid_fwd": (c_i32, [C.POINTER(GridDesc), c_vp, c_vp, c_i64, c_vp, C.POINTER(c_f32), c_vp, c_vp]),
     "ncn_grid_bwd": (c_i32, [C.POINTER(GridDesc), c_vp, c_vp, c_i64, c_vp, c_f32, C.POINTER(c_f32), c_vp, c_vp]),
+    "ncn_grid_bwd_f16": (c_i32, [C.POINTER(GridDesc), c_vp, c_vp, c_i64, c_vp, c_f32, C.POINTER(c_f32), c_vp, c_vp]),
     "ncn_grid_bwd_levels": (c_i32, [C.POINTER(GridDesc), c_vp, c_vp, c_i64, c_vp, c_f32, C.POINTER(c_f32), c_vp, c_i32, c_i32, c_i32, c_vp]),
     "ncn_grid_bwd_input": (c_i32, [C.POINTER(GridDesc), c_vp, c_vp, c_vp, c_i64, c_vp, c_vp]),
     "ncn_grid_bwd_bwd_input": (c_i32, [C.POINTER(GridDesc), c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp]),

@@ -19,7 +19,13 @@ int sm_count() {
   return n;
 }
 
+static std::atomic<int> g_pdl{1};
+int pdl_enabled() { return g_pdl.load(std::memory_order_relaxed); }
+
 }  // namespace ncn
+
+// programmatic dependent launch between the kernels of the training step's serial chain (1 = on, default); returns the old value
+extern "C" int ncn_set_pdl(int on) { return ncn::g_pdl.exchange(on ? 1 : 0); }
 
 extern "C" int ncn_version(void) { return NCN_VERSION; }
 

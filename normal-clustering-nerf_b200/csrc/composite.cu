@@ -395,6 +395,7 @@ composite_train_fw_sw_kernel(const float* __restrict__ sigmas, const float* __re
                              int64_t* __restrict__ total_samples, float* __restrict__ opacity,
                              float* __restrict__ depth, float* __restrict__ rend, float* __restrict__ ws, PhotoArgs ph) {
   constexpr int RPW = 32 / W;
+  pdl_wait(); pdl_trigger();
   float ph_se = 0.f, ph_ent = 0.f;
   const int lane = threadIdx.x & 31, sub = lane / W, sl = lane % W;
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -504,6 +505,7 @@ composite_train_bw_sw_kernel(const float* __restrict__ dL_dopacity, const float*
                              const float* __restrict__ rend, float thr, int64_t n_rays, int64_t capacity,
                              float* __restrict__ dL_dsigmas, float* __restrict__ dL_draws) {
   constexpr int RPW = 32 / W;
+  pdl_wait(); pdl_trigger();
   const int lane = threadIdx.x & 31, sub = lane / W, sl = lane % W;
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -696,8 +698,8 @@ extern "C" int ncn_composite_train_fw_photometric(const float* sigmas, const flo
   ph.rgb_out = rgb_out; ph.sums = sums; ph.d_rend = dL_drend; ph.d_opacity = dL_dopacity;
   const int w = g_composite_width < 32 ? g_composite_width : 16;
   const int gsw = persistent_grid(n_rays * w, 256, 8);
-#define NCN_CFP(CT, W) composite_train_fw_sw_kernel<CT, W, true><<<gsw, 256, 0, as_stream(stream)>>>(sigmas, raws, deltas, ts, rays_a, T_threshold, \
-                                                                                       n_rays, capacity, total_samples, opacity, depth, rend, ws, ph)
+#define NCN_CFP(CT, W) NCN_CUDA(launch_pdl(composite_train_fw_sw_kernel<CT, W, true>, dim3(gsw), dim3(256), 0, as_stream(stream), sigmas, raws, deltas, ts, \
+                                          rays_a, T_threshold, n_rays, capacity, total_samples, opacity, depth, rend, ws, ph))
 #define NCN_CFP_W(CT) do { if (w == 4) NCN_CFP(CT, 4); else if (w == 8) NCN_CFP(CT, 8); else NCN_CFP(CT, 16); } while (0)
   if (n_channels == 3) NCN_CFP_W(3); else if (n_channels == 6) NCN_CFP_W(6); else NCN_CFP_W(9);
 #undef NCN_CFP_W
@@ -722,9 +724,9 @@ extern "C" int ncn_composite_train_bw(const float* dL_dopacity, const float* dL_
   const int grid = persistent_grid(n_rays * 32, 256, 8);
   if (g_composite_width < 32 && (n_channels == 3 || n_channels == 6 || n_channels == 9)) {
     const int gsw = persistent_grid(n_rays * g_composite_width, 256, 8);
-#define NCN_CBW(CT, W) composite_train_bw_sw_kernel<CT, W><<<gsw, 256, 0, as_stream(stream)>>>(dL_dopacity, dL_ddepth, dL_drend, dL_dws, sigmas, raws, \
-                                                                                         ws, deltas, ts, rays_a, opacity, depth, rend, T_threshold, \
-                                                                                         n_rays, capacity, dL_dsigmas, dL_draws)
+#define NCN_CBW(CT, W) NCN_CUDA(launch_pdl(composite_train_bw_sw_kernel<CT, W>, dim3(gsw), dim3(256), 0, as_stream(stream), dL_dopacity, dL_ddepth, dL_drend, \
+                                          dL_dws, sigmas, raws, ws, deltas, ts, rays_a, opacity, depth, rend, T_threshold, n_rays, capacity,        \
+                                          dL_dsigmas, dL_draws))
 #define NCN_CBW_W(CT) do { if (g_composite_width == 4) NCN_CBW(CT, 4); else if (g_composite_width == 8) NCN_CBW(CT, 8); else NCN_CBW(CT, 16); } while (0)
     if (n_channels == 3) NCN_CBW_W(3); else if (n_channels == 6) NCN_CBW_W(6); else NCN_CBW_W(9);
 #undef NCN_CBW_W

@@ -121,12 +121,14 @@ field_mlp_fwd_tc05_kernel(const __half* __restrict__ feat, const float* __restri
     fence_proxy_async();
   }
   int64_t cur = blockIdx.x;
-  if (cur < n_tiles) stage_rows<32>(feat, cur * kTile, n, PX0);
+  // the weights were written by the optimizer at the head of the step: staged before the wait on the predecessor (the encoder)
   load_wk_panel_async(w_sigma, 64, 32, WS0);
   load_wk_panel_async(w_sigma + 64 * 32, 16, 64, WS1);
   load_wk_panel_perm(w_rgb, 64, 32, WR0);
   load_wk_panel_async(w_rgb + 64 * 32, 64, 64, WR1);
   load_wk_panel_async(w_rgb + 64 * 32 + 64 * 64, 16, 64, WR2);
+  pdl_wait(); pdl_trigger();
+  if (cur < n_tiles) stage_rows<32>(feat, cur * kTile, n, PX0);
   cp_async_commit();
   __syncwarp();
   if (wid == 0) tmem_alloc<LY::kTmemCols>(tmem_slot);
@@ -359,9 +361,8 @@ int ncn_field_mlp_fwd_tc05_try(const void* feat_f16, const float* dirs, const vo
   int64_t grid = (int64_t)sm_count() * 2;
   if (grid > tiles) grid = tiles;
   if (grid < 1) grid = 1;
-  k<<<(int)grid, kTcThreads, LY::kBytes, st>>>((const __half*)feat_f16, dirs, (const __half*)w_sigma_f16, (const __half*)w_rgb_f16, n, n_dev,
-                                               sigmas, raws, c_total, (__half*)h_f16, (__half*)sig_acts_f16, (__half*)x_rgb_f16,
-                                               (__half*)rgb_acts_f16, (__half*)rgb_out_f16);
-  NCN_LAUNCH_OK();
+  NCN_CUDA(launch_pdl(k, dim3((unsigned)grid), dim3(kTcThreads), LY::kBytes, st, (const __half*)feat_f16, dirs, (const __half*)w_sigma_f16,
+                      (const __half*)w_rgb_f16, n, n_dev, sigmas, raws, c_total, (__half*)h_f16, (__half*)sig_acts_f16, (__half*)x_rgb_f16,
+                      (__half*)rgb_acts_f16, (__half*)rgb_out_f16));
   return NCN_OK;
 }

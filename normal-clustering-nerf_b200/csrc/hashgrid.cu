@@ -43,6 +43,14 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
+__device__ __forceinline__ void red_add_h2(__half2* addr, __half2 v) {
+  asm volatile("red.global.add.noftz.f16x2 [%0], %1;" ::"l"(addr), "r"(*reinterpret_cast<const uint32_t*>(&v)) : "memory");
+}
+__device__ __forceinline__ void red_add_v2_h2(__half2* addr, __half2 a, __half2 b) {
+  asm volatile("red.global.add.noftz.v2.f16x2 [%0], {%1, %2};" ::"l"(addr), "r"(*reinterpret_cast<const uint32_t*>(&a)),
+               "r"(*reinterpret_cast<const uint32_t*>(&b)) : "memory");
+}
+
 struct Cell8 {
   uint32_t idx[8];
   float w[3];       // fractional position
@@ -156,6 +164,7 @@ grid_fwd_coherent_kernel(const __grid_constant__ GridMeta meta, const float* __r
   for (int i = threadIdx.x; i < (int)(sizeof(GridMeta) / 4); i += blockDim.x)
     reinterpret_cast<uint32_t*>(&sm)[i] = reinterpret_cast<const uint32_t*>(&meta)[i];
   __syncthreads();
+  pdl_wait(); pdl_trigger();
   int64_t n = n_cap;
   if (n_dev != nullptr) { const int64_t nd = *n_dev; if (nd < n) n = nd; }
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -238,38 +247,68 @@ grid_bwd_kernel(const __grid_constant__ GridMeta meta, const float* __restrict__
 // are not coherent at this level (fine / hashed levels) detect that with one ballot and take the direct path.
 // segmented sums of the 8 corner contributions over runs of lanes in the same cell; runs are cut at W-lane windows so
 // the prefix scan needs log2(W) steps.  `heads` already contains the window starts.
-template <int W>
-__device__ __forceinline__ void merge_corners(const Cell8& c, bool valid, float g0, float g1, unsigned heads, int lane, float2* __restrict__ gl) {
+// the contributions (ax, ay) to entry i0 and (bx, by) to entry i1 of one level, i0 / i1 = the two x-neighbours of a cell.
+// For an even cell x the two entries are neighbours in the dense layout AND in the hashed one (x enters the hash with
+// multiplier 1, so x ^ h and (x+1) ^ h differ in bit 0 only): one 16-byte reduction instead of two 8-byte ones.
+// HALF: the gradient buffer holds __half2 entries (what tiny-cuda-nn accumulates into for F = 2): 4 / 8 byte packed reductions.
+template <bool HALF>
+__device__ __forceinline__ void emit_pair(void* __restrict__ gl, uint32_t i0, uint32_t i1, float ax, float ay, float bx, float by) {
+  const bool z0 = ax == 0.f && ay == 0.f, z1 = bx == 0.f && by == 0.f;
+  if (z0 && z1) return;
+  if ((i0 ^ i1) == 1u) {
+    const uint32_t lo = i0 & ~1u;
+    const bool sw = (i0 & 1u) != 0;                             // hashed: the pair may come out swapped
+    if (HALF) {
+      const __half2 h0 = __floats2half2_rn(sw ? bx : ax, sw ? by : ay), h1 = __floats2half2_rn(sw ? ax : bx, sw ? ay : by);
+      red_add_v2_h2(reinterpret_cast<__half2*>(gl) + lo, h0, h1);
+    } else {
+      red_add_v4(reinterpret_cast<float*>(reinterpret_cast<float2*>(gl) + lo), sw ? bx : ax, sw ? by : ay, sw ? ax : bx, sw ? ay : by);
+    }
+  } else if (HALF) {
+    if (!z0) red_add_h2(reinterpret_cast<__half2*>(gl) + i0, __floats2half2_rn(ax, ay));
+    if (!z1) red_add_h2(reinterpret_cast<__half2*>(gl) + i1, __floats2half2_rn(bx, by));
+  } else {
+    if (!z0) atomicAdd(reinterpret_cast<float2*>(gl) + i0, make_float2(ax, ay));
+    if (!z1) atomicAdd(reinterpret_cast<float2*>(gl) + i1, make_float2(bx, by));
+  }
+}
+
+template <int W, bool HALF>
+__device__ __forceinline__ void merge_corners(const Cell8& c, bool valid, float g0, float g1, unsigned heads, int lane, void* __restrict__ gl) {
   const bool head = (heads >> lane) & 1u;
   const unsigned later = lane < 31 ? (heads >> (lane + 1)) : 0u;
   const int end = later ? lane + __ffs(later) - 1 : 31;          // last lane of this lane's run (inside the window)
   const int wl = lane & (W - 1);
 #pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    const float wk = valid ? corner_w(c.w, k) : 0.f;
-    float vx = wk * g0, vy = wk * g1;
+  for (int k = 0; k < 8; k += 2) {
+    float s[2][2];
 #pragma unroll
-    for (int o = 1; o < W; o <<= 1) {                            // inclusive prefix sums inside the window
-      const float tx = __shfl_up_sync(0xffffffffu, vx, o), ty = __shfl_up_sync(0xffffffffu, vy, o);
-      if (wl >= o) { vx += tx; vy += ty; }
+    for (int q = 0; q < 2; ++q) {
+      const float wk = valid ? corner_w(c.w, k + q) : 0.f;
+      float vx = wk * g0, vy = wk * g1;
+#pragma unroll
+      for (int o = 1; o < W; o <<= 1) {                          // inclusive prefix sums inside the window
+        const float tx = __shfl_up_sync(0xffffffffu, vx, o), ty = __shfl_up_sync(0xffffffffu, vy, o);
+        if (wl >= o) { vx += tx; vy += ty; }
+      }
+      const float ex = __shfl_sync(0xffffffffu, vx, end), ey = __shfl_sync(0xffffffffu, vy, end);
+      const float bx = __shfl_up_sync(0xffffffffu, vx, 1), by = __shfl_up_sync(0xffffffffu, vy, 1);
+      s[q][0] = ex - (wl > 0 ? bx : 0.f); s[q][1] = ey - (wl > 0 ? by : 0.f);
     }
-    const float ex = __shfl_sync(0xffffffffu, vx, end), ey = __shfl_sync(0xffffffffu, vy, end);
-    const float bx = __shfl_up_sync(0xffffffffu, vx, 1), by = __shfl_up_sync(0xffffffffu, vy, 1);
-    if (head && valid) {
-      const float sx = ex - (wl > 0 ? bx : 0.f), sy = ey - (wl > 0 ? by : 0.f);
-      if (sx != 0.f || sy != 0.f) atomicAdd(gl + c.idx[k], make_float2(sx, sy));
-    }
+    if (head && valid) emit_pair<HALF>(gl, c.idx[k], c.idx[k + 1], s[0][0], s[0][1], s[1][0], s[1][1]);
   }
 }
 
-__global__ void __launch_bounds__(256)
+template <bool HALF>
+__global__ void __launch_bounds__(256, 5)
 grid_bwd_merge_kernel(const __grid_constant__ GridMeta meta, const float* __restrict__ x, const __half* __restrict__ dy,
-                      int64_t n_cap, const int32_t* __restrict__ n_dev, GridXform xf, float grad_scale, float* __restrict__ grad,
+                      int64_t n_cap, const int32_t* __restrict__ n_dev, GridXform xf, float grad_scale, void* __restrict__ grad,
                       int level_begin, int level_end) {
   __shared__ GridMeta sm;
   for (int i = threadIdx.x; i < (int)(sizeof(GridMeta) / 4); i += blockDim.x)
     reinterpret_cast<uint32_t*>(&sm)[i] = reinterpret_cast<const uint32_t*>(&meta)[i];
   __syncthreads();
+  pdl_wait(); pdl_trigger();
   const int L = sm.n_levels;
   int64_t n = n_cap;
   if (n_dev != nullptr) { const int64_t nd = *n_dev; if (nd < n) n = nd; }
@@ -278,9 +317,16 @@ grid_bwd_merge_kernel(const __grid_constant__ GridMeta meta, const float* __rest
   const int64_t n_items = ((n + 31) >> 5) * LR;
   const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  for (int64_t item = warp0; item < n_items; item += n_warps) {
+  int64_t trip = 0;
+  const bool rotate = (n_warps % LR) == 0;
+  for (int64_t item = warp0; item < n_items; item += n_warps, ++trip) {
     const int64_t chunk = item / LR;
-    const int l = level_begin + (int)(item - chunk * LR);
+    // rotate the level with the trip count: with a warp count that is a multiple of LR a warp would stay on ONE level for all
+    // of its items, and CTAs of coarse (merging) levels and of fine (direct) levels would run for different times (the LR
+    // items of a chunk then share one trip count, so the rotation permutes them; other warp counts rotate by themselves)
+    int lr = (int)(item - chunk * LR) + (rotate ? (int)(trip % LR) : 0);
+    if (lr >= LR) lr -= LR;
+    const int l = level_begin + lr;
     const int64_t s = (chunk << 5) + lane;
     const bool valid = s < n;
     float g0 = 0.f, g1 = 0.f;
@@ -298,37 +344,27 @@ grid_bwd_merge_kernel(const __grid_constant__ GridMeta meta, const float* __rest
       for (int k = 0; k < 8; ++k) c.idx[k] = 0xFFFFFFFFu;
       c.w[0] = c.w[1] = c.w[2] = 0.f;
     }
-    float2* gl = reinterpret_cast<float2*>(grad) + sm.offset[l];
+    void* gl = HALF ? static_cast<void*>(reinterpret_cast<__half2*>(grad) + sm.offset[l])
+                    : static_cast<void*>(reinterpret_cast<float2*>(grad) + sm.offset[l]);
     // runs of consecutive samples in the SAME cell share all 8 table entries (exact: compared on the integer cell)
     const uint32_t pa = __shfl_up_sync(0xffffffffu, cell[0], 1), pb = __shfl_up_sync(0xffffffffu, cell[1], 1);
     const unsigned heads0 = __ballot_sync(0xffffffffu, lane == 0 || cell[0] != pa || cell[1] != pb || !valid);
     const int nh = __popc(heads0);
     if (nh > 20) {                                              // incoherent at this level (fine / hashed): direct path
       if (live) {
-        // corners k and k+1 differ in x only.  For an even cell x the two entries are neighbours in the dense layout AND
-        // in the hashed one (x enters the hash with multiplier 1, so x ^ h and (x+1) ^ h differ in bit 0 only): one
-        // 16-byte reduction instead of two 8-byte ones
 #pragma unroll
         for (int k = 0; k < 8; k += 2) {
           const float w0 = corner_w(c.w, k), w1 = corner_w(c.w, k + 1);
-          const uint32_t i0 = c.idx[k], i1 = c.idx[k + 1];
-          if ((i0 ^ i1) == 1u) {
-            const uint32_t lo = i0 & ~1u;
-            const bool sw = (i0 & 1u) != 0;                     // hashed: the pair may come out swapped
-            red_add_v4(reinterpret_cast<float*>(gl + lo), (sw ? w1 : w0) * g0, (sw ? w1 : w0) * g1, (sw ? w0 : w1) * g0, (sw ? w0 : w1) * g1);
-          } else {
-            atomicAdd(gl + i0, make_float2(w0 * g0, w0 * g1));
-            atomicAdd(gl + i1, make_float2(w1 * g0, w1 * g1));
-          }
+          emit_pair<HALF>(gl, c.idx[k], c.idx[k + 1], w0 * g0, w0 * g1, w1 * g0, w1 * g1);
         }
       }
       continue;
     }
     // window = about twice the average run: short scans where runs are short, whole-warp sums on the coarse levels
-    if (nh <= 2) merge_corners<32>(c, valid, g0, g1, heads0 | 0x00000001u, lane, gl);
-    else if (nh <= 4) merge_corners<16>(c, valid, g0, g1, heads0 | 0x00010001u, lane, gl);
-    else if (nh <= 10) merge_corners<8>(c, valid, g0, g1, heads0 | 0x01010101u, lane, gl);
-    else merge_corners<4>(c, valid, g0, g1, heads0 | 0x11111111u, lane, gl);
+    if (nh <= 2) merge_corners<32, HALF>(c, valid, g0, g1, heads0 | 0x00000001u, lane, gl);
+    else if (nh <= 4) merge_corners<16, HALF>(c, valid, g0, g1, heads0 | 0x00010001u, lane, gl);
+    else if (nh <= 10) merge_corners<8, HALF>(c, valid, g0, g1, heads0 | 0x01010101u, lane, gl);
+    else merge_corners<4, HALF>(c, valid, g0, g1, heads0 | 0x11111111u, lane, gl);
   }
 }
 
@@ -471,10 +507,10 @@ extern "C" int ncn_grid_fwd(const ncn_grid_desc* desc, const float* x, const voi
   NCN_CHECK_PTR(x); NCN_CHECK_PTR(table); NCN_CHECK_PTR(out);
   if (((uintptr_t)table | (uintptr_t)out) & 3) return NCN_E_ALIGN;
   if (desc->n_features == 2 && m.n_levels == 16 && g_grid_fwd_coherent) {
-    const int64_t chunks = (n + 31) / 32;
-    int64_t cg = (int64_t)sm_count() * 8;
-    if (cg > chunks) cg = chunks;
-    grid_fwd_coherent_kernel<<<(int)cg, 256, 0, as_stream(stream)>>>(m, x, (const __half*)table, n, n_dev, make_xform(xform_host), (__half*)out);
+    static int resident = 0;
+    const int cg = resident_grid(grid_fwd_coherent_kernel, 256, 0, &resident, (n + 31) / 32);
+    NCN_CUDA(launch_pdl(grid_fwd_coherent_kernel, dim3(cg), dim3(256), 0, as_stream(stream), m, x, (const __half*)table, n, n_dev,
+                        make_xform(xform_host), (__half*)out));
     NCN_LAUNCH_OK();
     return NCN_OK;
   }
@@ -488,27 +524,40 @@ extern "C" int ncn_grid_fwd(const ncn_grid_desc* desc, const float* x, const voi
 // level_begin/level_end restrict the launch to a range of levels (their gradient regions are contiguous in the table), so a
 // data-parallel caller can all-reduce the first range while the second is still being computed; ctas_per_sm < 8 leaves
 // room on the SMs for the collective's kernels
-static int grid_bwd_impl(const ncn_grid_desc* desc, const float* x, const void* dy, int64_t n, float* grad, float grad_scale,
-                         const float* xform_host, const int32_t* n_dev, int level_begin, int level_end, int ctas_per_sm,
-                         ncn_stream_t stream) {
+static int grid_bwd_impl(const ncn_grid_desc* desc, const float* x, const void* dy, int64_t n, void* grad, bool half_grad,
+                         float grad_scale, const float* xform_host, const int32_t* n_dev, int level_begin, int level_end,
+                         int ctas_per_sm, ncn_stream_t stream) {
   GridMeta m; int rc = to_meta(desc, &m); if (rc) return rc;
   NCN_CHECK_SIZE(n >= 0);
   if (level_begin < 0 || level_end > m.n_levels || level_begin >= level_end || ctas_per_sm < 1 || ctas_per_sm > 8) return NCN_E_CONFIG;
+  if (half_grad && desc->n_features != 2) return NCN_E_UNSUPPORTED;
   if (n == 0) return NCN_OK;
   NCN_CHECK_PTR(x); NCN_CHECK_PTR(dy); NCN_CHECK_PTR(grad);
   if ((uintptr_t)grad & 7) return NCN_E_ALIGN;
   const bool whole = level_begin == 0 && level_end == m.n_levels;
+  const int64_t need = ceil_div(n * (level_end - level_begin), (int64_t)256);
+  if (half_grad) {                                                                                  // 8-byte paired fp16 reductions
+    static int resident = 0;
+    int grid = resident_grid(grid_bwd_merge_kernel<true>, 256, 0, &resident, need);
+    if (ctas_per_sm < 8 && grid > sm_count() * ctas_per_sm) grid = sm_count() * ctas_per_sm;
+    NCN_CUDA(launch_pdl(grid_bwd_merge_kernel<true>, dim3(grid), dim3(256), 0, as_stream(stream), m, x, (const __half*)dy, n, n_dev,
+                        make_xform(xform_host), grad_scale, grad, level_begin, level_end));
+    NCN_LAUNCH_OK();
+    return NCN_OK;
+  }
   if (desc->n_features == 2 && (g_grid_bwd_merge || !whole) && ((uintptr_t)grad & 15) == 0) {      // 16-byte paired reductions
-    const int grid = persistent_grid(n * (level_end - level_begin), 256, ctas_per_sm);
-    grid_bwd_merge_kernel<<<grid, 256, 0, as_stream(stream)>>>(m, x, (const __half*)dy, n, n_dev, make_xform(xform_host), grad_scale, grad,
-                                                               level_begin, level_end);
+    static int resident = 0;
+    int grid = resident_grid(grid_bwd_merge_kernel<false>, 256, 0, &resident, need);
+    if (ctas_per_sm < 8 && grid > sm_count() * ctas_per_sm) grid = sm_count() * ctas_per_sm;
+    NCN_CUDA(launch_pdl(grid_bwd_merge_kernel<false>, dim3(grid), dim3(256), 0, as_stream(stream), m, x, (const __half*)dy, n, n_dev,
+                        make_xform(xform_host), grad_scale, grad, level_begin, level_end));
     NCN_LAUNCH_OK();
     return NCN_OK;
   }
   if (!whole) return NCN_E_UNSUPPORTED;
   const int grid = persistent_grid(n * m.n_levels, 256, 8);
   NCN_GRID_DISPATCH(desc->n_features, (grid_bwd_kernel<kF><<<grid, 256, 0, as_stream(stream)>>>(
-      m, x, (const __half*)dy, n, n_dev, make_xform(xform_host), grad_scale, grad)));
+      m, x, (const __half*)dy, n, n_dev, make_xform(xform_host), grad_scale, (float*)grad)));
   NCN_LAUNCH_OK();
   return NCN_OK;
 }
@@ -516,14 +565,20 @@ static int grid_bwd_impl(const ncn_grid_desc* desc, const float* x, const void* 
 extern "C" int ncn_grid_bwd(const ncn_grid_desc* desc, const float* x, const void* dy, int64_t n, float* grad,
                             float grad_scale, const float* xform_host, const int32_t* n_dev, ncn_stream_t stream) {
   if (!desc) return NCN_E_NULL;
-  return grid_bwd_impl(desc, x, dy, n, grad, grad_scale, xform_host, n_dev, 0, desc->n_levels, 8, stream);
+  return grid_bwd_impl(desc, x, dy, n, grad, false, grad_scale, xform_host, n_dev, 0, desc->n_levels, 8, stream);
 }
 
 extern "C" int ncn_grid_bwd_levels(const ncn_grid_desc* desc, const float* x, const void* dy, int64_t n, float* grad,
                                    float grad_scale, const float* xform_host, const int32_t* n_dev, int level_begin, int level_end,
                                    int ctas_per_sm, ncn_stream_t stream) {
   if (!desc) return NCN_E_NULL;
-  return grid_bwd_impl(desc, x, dy, n, grad, grad_scale, xform_host, n_dev, level_begin, level_end, ctas_per_sm, stream);
+  return grid_bwd_impl(desc, x, dy, n, grad, false, grad_scale, xform_host, n_dev, level_begin, level_end, ctas_per_sm, stream);
+}
+
+extern "C" int ncn_grid_bwd_f16(const ncn_grid_desc* desc, const float* x, const void* dy, int64_t n, void* grad_f16,
+                                float grad_scale, const float* xform_host, const int32_t* n_dev, ncn_stream_t stream) {
+  if (!desc) return NCN_E_NULL;
+  return grid_bwd_impl(desc, x, dy, n, grad_f16, true, grad_scale, xform_host, n_dev, 0, desc->n_levels, 8, stream);
 }
 
 extern "C" int ncn_grid_bwd_input(const ncn_grid_desc* desc, const float* x, const void* table, const void* dy,

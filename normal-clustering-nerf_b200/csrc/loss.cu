@@ -353,6 +353,7 @@ kmeans_kernel(const float* __restrict__ x_in, int64_t n, ncn_kmeans_params p, fl
   }
   const int K = p.k;
   const uint32_t rank = cluster_ctarank();
+  pdl_wait(); pdl_trigger();
   KM_TRACE(0);
   // 0) chain prologue: the normals of the rendered depth (one triangle per thread, the cluster's CTAs split them), published
   //    to global memory (the backward pass and the caller read them) and made visible to the whole cluster by one barrier
@@ -1124,6 +1125,7 @@ cluster_bw_depth_kernel(const float* __restrict__ nrm, const int32_t* __restrict
                         const float* __restrict__ w, float* __restrict__ dn, const float* __restrict__ origin,
                         const float* __restrict__ dir, const float* __restrict__ depth, const int64_t* __restrict__ i1,
                         const int64_t* __restrict__ i2, const int64_t* __restrict__ i3, float* __restrict__ ddepth) {
+  pdl_wait(); pdl_trigger();
   const int64_t first = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (int64_t)gridDim.x * blockDim.x;
   cluster_loss_bw_body(nrm, labels, n, stats, w, dn, first, stride);
   normals_bw_body(origin, dir, depth, i1, i2, i3, dn, n, ddepth, first, stride);
@@ -1331,9 +1333,10 @@ static int launch_kmeans(const float* x, int64_t n_points, const ncn_kmeans_para
   const size_t smem = per_cta * 12 + 16 + (per_cta + 16) * 16 + 16 + (size_t)2 * cluster * 32 * 16;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(cluster); cfg.blockDim = dim3(kKmThreads); cfg.dynamicSmemBytes = smem; cfg.stream = as_stream(stream);
-  cudaLaunchAttribute at[1];
+  cudaLaunchAttribute at[2];
   at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = cluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-  cfg.attrs = at; cfg.numAttrs = 1;
+  at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = pdl_enabled() ? 2 : 1;
   int32_t* wsp = (int32_t*)workspace;
   const int cap_i = (int)cap;
   // static (~28 KB) + dynamic shared memory can cross the 48 KB default limit: always opt in
@@ -1443,10 +1446,8 @@ extern "C" int ncn_cluster_bw_depth(const float* normals, const int32_t* labels,
   NCN_CHECK_PTR(normals); NCN_CHECK_PTR(labels); NCN_CHECK_PTR(stats); NCN_CHECK_PTR(weights_dev); NCN_CHECK_PTR(dL_dnormals);
   NCN_CHECK_PTR(origin); NCN_CHECK_PTR(dir); NCN_CHECK_PTR(depth); NCN_CHECK_PTR(idx1); NCN_CHECK_PTR(idx2); NCN_CHECK_PTR(idx3);
   NCN_CHECK_PTR(dL_ddepth);
-  cluster_bw_depth_kernel<<<persistent_grid(n_points, 256, 8), 256, 0, as_stream(stream)>>>(normals, labels, n_points, stats, weights_dev,
-                                                                                           dL_dnormals, origin, dir, depth, idx1, idx2, idx3,
-                                                                                           dL_ddepth);
-  NCN_LAUNCH_OK();
+  NCN_CUDA(launch_pdl(cluster_bw_depth_kernel, dim3(persistent_grid(n_points, 256, 8)), dim3(256), 0, as_stream(stream), normals, labels, n_points,
+                      stats, weights_dev, dL_dnormals, origin, dir, depth, idx1, idx2, idx3, dL_ddepth));
   return NCN_OK;
 }
 

@@ -209,14 +209,15 @@ mlp_bwd_tc05_kernel(const __half* __restrict__ x, const __half* __restrict__ w, 
     first_next = 0;
   }
   DoutRaw<OUT> raw;
-  if (cur < n_tiles) {
-    stage_rows<IN>(x, cur * kTile, n, sets + LY::kPdzl + LY::kPact);
-    dout_prefetch<OUT>(cur * kTile + tid, n, dout, out, out_act, src);
-  }
+  // saved activations, inputs and weights come from the forward pass / the optimizer: requested before the wait on the stream
+  // predecessor (the kernel that produces the dL/dout sources), so they are in flight while that kernel drains
+  if (cur < n_tiles) stage_rows<IN>(x, cur * kTile, n, sets + LY::kPdzl + LY::kPact);
   load_w_panel_async(w + 64 * IN + (NH - 1) * 64 * 64, OUT, 64, WBl);
   for (int i = 0; i < NH - 1; ++i) load_w_panel_async(w + 64 * IN + i * 64 * 64, 64, 64, WBh + i * 64 * 64);
   if (dx) { if (perm_in) load_w_panel_perm(w, 64, IN, WB0); else load_w_panel_async(w, 64, IN, WB0); }
   cp_async_commit();
+  pdl_wait(); pdl_trigger();
+  if (cur < n_tiles) dout_prefetch<OUT>(cur * kTile + tid, n, dout, out, out_act, src);
   (void)first_next; (void)tile_counter; (void)s_tile;
   // tiles are handed out statically (tile = blockIdx.x + i * gridDim.x): every tile costs the same, and the atomic scheduler put
   // a global round trip (and a memset node per launch) on the thread that issues the MMAs
@@ -465,9 +466,8 @@ static int launch_tc05(const void* x, const void* w, const void* out, const void
   if (occ < 1) occ = 1;
   int64_t grid = (int64_t)sm_count() * occ;
   if (grid > tiles) grid = tiles;
-  k<<<(int)grid, kTcThreads, LY::kBytes, st>>>((const __half*)x, (const __half*)w, (const __half*)out, (const __half*)acts,
-                                               (const __half*)dout, n, n_dev, out_act, grad_scale, grad_w, (__half*)dx, tile_counter, src);
-  NCN_LAUNCH_OK();
+  NCN_CUDA(launch_pdl(k, dim3((unsigned)grid), dim3(kTcThreads), LY::kBytes, st, (const __half*)x, (const __half*)w, (const __half*)out,
+                      (const __half*)acts, (const __half*)dout, n, n_dev, out_act, grad_scale, grad_w, (__half*)dx, tile_counter, src));
   return NCN_OK;
 }
 

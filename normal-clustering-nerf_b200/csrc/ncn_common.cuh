@@ -42,6 +42,41 @@ static inline int persistent_grid(int64_t n, int threads, int blocks_per_sm) {
   return (int)(need < cap ? need : cap);
 }
 
+// CTAs of `kernel` that are co-resident on the device (register / shared-memory limited), for grid-stride kernels whose CTAs
+// all carry the same share of the work: a grid larger than this runs a second, partly filled wave (1184 CTAs at 5 per SM were
+// 1.6 waves: ncu showed 15 % of the elapsed cycles with idle SMs).  `cached` is a per-call-site static.
+template <typename K>
+static inline int resident_grid(K kernel, int threads, size_t smem, int* cached, int64_t need_blocks) {
+  if (*cached == 0) {
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+    *cached = per_sm * sm_count();
+  }
+  if (need_blocks < 1) need_blocks = 1;
+  return (int)(need_blocks < (int64_t)*cached ? need_blocks : (int64_t)*cached);
+}
+
+// Programmatic dependent launch (sm_90+).  A kernel launched through launch_pdl() may be scheduled while its stream predecessor
+// is still running; it must execute pdl_wait() before it touches anything an earlier kernel wrote (or overwrites anything an
+// earlier kernel reads) - the wait returns when the predecessor grid has completed and flushed.  pdl_trigger() lets the NEXT
+// kernel of the stream be scheduled; every kernel here triggers only AFTER its own wait, so at most one dependent is ever
+// resident beside a running kernel and completion stays transitive along the stream.  Both are no-ops in a kernel that was
+// launched without the attribute (ncn_set_pdl(0), or a predecessor that is not a kernel).
+int pdl_enabled();
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -255,7 +255,8 @@ extern "C" int ncn_grad_sumsq(const float* grad, int64_t n, const float* grad_di
   if (n == 0) return NCN_OK;
   NCN_CHECK_PTR(grad); NCN_CHECK_PTR(out);
   if ((uintptr_t)grad & 15) return NCN_E_ALIGN;
-  int grid = persistent_grid((n + 3) / 4, 256, 8);
+  static int resident = 0;
+  int grid = resident_grid(sumsq_kernel, 256, 0, &resident, ceil_div((n + 3) / 4, (int64_t)256));
   if (grid > kSumsqMaxBlocks) grid = kSumsqMaxBlocks;
   sumsq_kernel<<<grid, 256, 0, as_stream(stream)>>>(grad, n, grad_div_dev, out, flag);
   NCN_LAUNCH_OK();

@@ -178,6 +178,46 @@ def test_grid_backward_level_ranges_sum_to_the_whole(ncn):
     assert (ga - gb).abs().max() <= 1e-5 * ga.abs().max()
 
 
+@pytest.mark.parametrize("coherent", [True, False])
+def test_grid_backward_fp16_gradient_mode(ncn, coherent):
+    """ncn_grid_bwd_f16 (packed fp16 reductions into a __half2 table, tiny-cuda-nn's own accumulation type for F = 2) against
+    the fp32 table of ncn_grid_bwd on the same inputs: ray-ordered samples (merge paths) and random ones (direct path).
+    Tolerance: fp16 rounding of every accumulated term - entries agree to 2^-10 relative of the level's largest entry
+    plus the accumulated rounding of the most-hit coarse entries (1 %)."""
+    import ctypes as C
+    from ncn_b200 import _lib
+    from ncn_b200._lib import check, ptr, stream
+    enc, cfg = _enc(19, std=0.1)
+    L = _lib.lib()
+    g = torch.Generator(device="cuda").manual_seed(7)
+    n = 40000
+    if coherent:                                  # 1250 rays x 32 samples, 1.7e-3 apart: long runs on the coarse levels
+        o = torch.rand(n // 32, 1, 3, device="cuda", generator=g) * 0.8 + 0.1
+        d = torch.randn(n // 32, 1, 3, device="cuda", generator=g); d = d / d.norm(dim=-1, keepdim=True)
+        t = torch.arange(32, device="cuda").view(1, 32, 1) * 1.7e-3
+        x = (o + t * d).clamp(0, 1).reshape(n, 3).contiguous()
+    else:
+        x = torch.rand(n, 3, device="cuda", generator=g)
+    dy = torch.randn(n, 32, device="cuda", generator=g).half()
+    dy[::7] = 0                                   # terminated samples carry exact zeros
+    g32 = torch.zeros_like(enc.params)
+    g16 = torch.zeros(enc.params.numel(), dtype=torch.float16, device="cuda")
+    check(L.ncn_grid_bwd(C.byref(enc.desc), ptr(x), ptr(dy), n, ptr(g32), 1.0, None, None, stream()))
+    check(L.ncn_grid_bwd_f16(C.byref(enc.desc), ptr(x), ptr(dy), n, ptr(g16), 1.0, None, None, stream()))
+    assert torch.isfinite(g16).all()
+    assert (g32 != 0).sum() > 1000
+    assert ((g16 != 0) & (g32 == 0)).sum() == 0                     # nothing lands outside the entries the fp32 pass touched
+    for l in range(16):
+        a, b = int(enc.desc.level_offset[l]) * 2, int(enc.desc.level_offset[l + 1]) * 2
+        ref, got = g32[a:b], g16[a:b].float()
+        assert (got - ref).abs().max() <= 1e-2 * ref.abs().max() + 1e-6, l
+        assert (got - ref).norm() <= 4e-3 * ref.norm() + 1e-6, l
+    # F != 2 is refused, not silently converted
+    from ncn_b200 import tinycudann as tcnn
+    enc4 = tcnn.Encoding(3, dict(cfg, n_features_per_level=4)).cuda()
+    assert L.ncn_grid_bwd_f16(C.byref(enc4.desc), ptr(x), ptr(dy), 10, ptr(g16), 1.0, None, None, stream()) != 0
+
+
 NETS = [(32, 16, 1, "None"), (19, 3, 2, "Sigmoid"), (16, 3, 2, "None"), (16, 40, 2, "None"), (1, 1, 1, "Sigmoid")]
 
 

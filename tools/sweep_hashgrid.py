@@ -4,7 +4,8 @@ Samples = the occupancy march of `--rays` rays drawn from the 640x480 synthetic 
 (ray-coherent sample order, as in training).  Per T: forward (ncn_grid_fwd) and parameter backward (ncn_grid_bwd) launch
 time by CUDA events, with the L2 flushed between launches (a 256 MB write) so the table is read from where it lives after
 the optimizer pass, and achieved GB/s of the ALGORITHMIC bytes (fwd 12 + 512 + 64 = 588 B/sample,
-bwd 12 + 64 + 1024 B/sample with fp32 gradients) against the measured HBM peak.
+bwd 12 + 64 + 1024 B/sample with fp32 gradients) against the measured HBM peak.  `bwd_f16` = ncn_grid_bwd_f16, the selectable
+fp16-gradient mode (12 + 64 + 512 B/sample; its GB/s is quoted on ITS bytes, its speed-up over fp32 is the ratio of the times).
 
     python tools/sweep_hashgrid.py [--rays 65536] [--out profiles/r1_hashgrid_sweep.json]
     python -m torch.distributed.run --nproc-per-node 8 --master-addr 127.0.0.1 tools/sweep_hashgrid.py   (replicas: aggregate samples/s)
@@ -69,6 +70,7 @@ def main():
         feat = torch.empty(n, 32, dtype=torch.float16, device=dev)
         dfeat = (torch.randn(n, 32, device=dev) * 1e-2).to(torch.float16)
         grad = torch.zeros(enc.params.numel(), dtype=torch.float32, device=dev)
+        grad16 = torch.zeros(enc.params.numel(), dtype=torch.float16, device=dev)
         st = stream()
 
         def fwd():
@@ -76,6 +78,9 @@ def main():
 
         def bwd():
             check(L.ncn_grid_bwd(C.byref(enc.desc), ptr(x01), ptr(dfeat), n, ptr(grad), 1.0, None, None, st), "grid_bwd")
+
+        def bwd_f16():
+            check(L.ncn_grid_bwd_f16(C.byref(enc.desc), ptr(x01), ptr(dfeat), n, ptr(grad16), 1.0, None, None, st), "grid_bwd_f16")
 
         def timed(fn, cold):
             tot = 0.0
@@ -91,7 +96,7 @@ def main():
             return tot / a.reps
 
         row = {"log2_T": log2_T, "params": enc.params.numel(), "table_fp16_MiB": enc.params.numel() * 2 / 2 ** 20, "samples": n}
-        for name, fn, per in (("fwd", fwd, 588), ("bwd", bwd, 1100)):
+        for name, fn, per in (("fwd", fwd, 588), ("bwd", bwd, 1100), ("bwd_f16", bwd_f16, 588)):
             for cold in (True, False):
                 ms = timed(fn, cold)
                 t = torch.tensor([ms], device=dev)
@@ -104,10 +109,10 @@ def main():
                 row[k + "_frac_hbm_peak"] = row[k + "_GBps_algorithmic"] / peak
                 row[k + "_Msamples_per_s_all_gpus"] = world * n / (ms * 1e-3) / 1e6
         rows.append(row)
-        del enc, table, grad
+        del enc, table, grad, grad16
     res = {"config": "hash-grid sweep L=16 F=2, T=2^19..2^22, ScanNet-shaped 640x480 camera, ray-coherent samples of the synthetic room",
            "n_gpus": world, "rays": a.rays, "hbm_peak_GBps": peak,
-           "algorithmic_bytes_per_sample": {"fwd": 588, "bwd": 1100}, "rows": rows}
+           "algorithmic_bytes_per_sample": {"fwd": 588, "bwd": 1100, "bwd_f16": 588}, "rows": rows}
     if rank == 0:
         print(json.dumps(res))
         if a.out:
