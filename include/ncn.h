@@ -287,6 +287,8 @@ int ncn_grid_bwd_levels(const ncn_grid_desc* desc_host, const float* x, const vo
  * inside fp16 range.  A selectable mode, measured by tools/sweep_hashgrid.py; the training step uses the fp32 table. */
 int ncn_grid_bwd_f16(const ncn_grid_desc* desc_host, const float* x, const void* dL_dy_f16, int64_t n, void* grad_table_f16,
                      float grad_scale, const float* xform_host, const int32_t* n_dev, ncn_stream_t stream);
+/* developer A/B knob of the F = 2 table backward: CTAs per SM its kernel is compiled for, 5 (default) or 6; returns the old value */
+int ncn_set_grid_bwd_occupancy(int ctas_per_sm);
 /* 1 (default): ncn_grid_bwd merges same-entry contributions of consecutive samples inside a warp before the
  * scatter; 0: one reduction per corner.  Returns the old value. */
 int ncn_set_grid_bwd_merge(int on);
@@ -625,12 +627,26 @@ int ncn_peer_step(ncn_peer* p, float* param, float* m, float* v, const ncn_adam_
 /* on = 1: ncn_peer_step no longer zeroes the gradient buffer outside its own slice; the caller zeroes the WHOLE buffer after the step
  * (any stream, any time before the next backward) - takes the 4 B/param memset off the exchange's critical path */
 int ncn_peer_set_external_zero(ncn_peer* p, int on);
+/* Overlap of the exchange with the tail of the backward pass.  set_cut(cut): [cut, n) of the flat vector is the EARLY range - the
+ * part of the gradient the backward completes first (the caller orders its launches accordingly: here the fine hash-grid levels
+ * and the MLPs, then the coarse levels); every rank then owns the r-th 1/W slice of [0, cut) AND of [cut, n)
+ * (ncn_peer_segments: {lo, hi, lo_early, hi_early} of rank q).  ncn_peer_early, launched on any stream once the early range of
+ * THIS rank's gradient is complete, reduces this rank's early slice out of every peer's buffer behind its own flag phase while
+ * the rest of the backward is still running everywhere; ncn_peer_step then only pulls the late slice.  With a cut set, every
+ * ncn_peer_step must be preceded by exactly one ncn_peer_early since the previous step (or by none at all while the gradient
+ * is still zero), on every rank.  cut == n (default): no early range, ncn_peer_early is refused. */
+int ncn_peer_set_cut(ncn_peer* p, int64_t cut);
+int ncn_peer_segments(ncn_peer* p, int rank_q, int64_t* seg4_out);
+void ncn_peer_segments_of(int64_t n_params, int64_t cut, int rank, int world, int64_t* seg4_out);   /* host arithmetic only */
+int ncn_peer_early(ncn_peer* p, const float* grad_div_dev, ncn_stream_t stream);
+int ncn_peer_debug_times_early(ncn_peer* p, unsigned long long* times4_host);
 int ncn_peer_error(ncn_peer* p, unsigned int* error_host);
 unsigned int ncn_peer_poll(ncn_peer* p);
 /* developer A/B knobs of the reduce kernel: 16-byte loads in flight per peer and thread (1 [default], 2, 4; returns the old value);
  * peers loaded per batch (2, 4 [default], 8) and CTAs per SM (1, 2 [default]) */
 int ncn_peer_set_loads(int loads_per_peer);
 int ncn_peer_set_shape(int peers_per_batch, int ctas_per_sm);
+int ncn_peer_set_early_loads(int loads_per_peer);      /* the same knob for ncn_peer_early; 0 (default) = by world size (4 / 2 / 1 for <= 2 / <= 4 / 8 ranks) */
 /* developer timeline of the last step (synchronises): 8 x ns = [K1 start, wait-0 over, K1 reduced, K2 start, wait-1 over, Adam+publish done, wait-2 over, -] */
 int ncn_peer_debug_times(ncn_peer* p, unsigned long long* times8_host);
 int ncn_peer_set_timeout(double seconds);

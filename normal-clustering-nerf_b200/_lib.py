@@ -47,6 +47,7 @@ SIGNATURES = {
     "ncn_set_composite_width": (c_i32, [c_i32]),
     "ncn_set_field_fwd_impl": (c_i32, [c_i32]),
     "ncn_set_pdl": (c_i32, [c_i32]),
+    "ncn_set_grid_bwd_occupancy": (c_i32, [c_i32]),
 }
 
 
@@ -59,11 +60,12 @@ class Profiler:
     events = []            # (name, start_event, end_event, n_items)
     KERNELS_PER_CALL = {"ncn_march_train": 3, "ncn_march_train_count": 3, "ncn_cluster_tail": 2, "ncn_kmeans_workspace_bytes": 0,
                         "ncn_march_train_workspace_bytes": 0, "ncn_mlp_bwd_workspace_bytes": 0, "ncn_mlp_acts_bytes": 0, "ncn_mlp_n_params": 0,
-                        "ncn_grid_desc_init": 0, "ncn_version": 0, "ncn_set_mlp_bwd_impl": 0, "ncn_set_march_segments": 0, "ncn_set_composite_width": 0, "ncn_set_field_fwd_impl": 0, "ncn_set_pdl": 0, "ncn_debug_stamp": 1, "ncn_set_grid_bwd_merge": 0, "ncn_set_grid_fwd_coherent": 0, "ncn_error_string": 0, "ncn_device_info": 0,
+                        "ncn_grid_desc_init": 0, "ncn_version": 0, "ncn_set_mlp_bwd_impl": 0, "ncn_set_march_segments": 0, "ncn_set_composite_width": 0, "ncn_set_field_fwd_impl": 0, "ncn_set_pdl": 0, "ncn_set_grid_bwd_occupancy": 0, "ncn_debug_stamp": 1, "ncn_set_grid_bwd_merge": 0, "ncn_set_grid_fwd_coherent": 0, "ncn_error_string": 0, "ncn_device_info": 0,
                         "ncn_comm_unique_id": 0, "ncn_comm_init": 0, "ncn_comm_destroy": 0, "ncn_comm_last_error": 0,
                         "ncn_sample_ray_batch": 2, "ncn_sample_ray_batch_ex": 2, "ncn_peer_create": 0, "ncn_peer_grad": 0, "ncn_peer_p16": 0, "ncn_peer_handles": 0, "ncn_peer_connect": 0,
                         "ncn_peer_shard": 0, "ncn_peer_step": 2, "ncn_peer_error": 0, "ncn_peer_destroy": 0,
-                        "ncn_peer_poll": 0, "ncn_peer_set_timeout": 0, "ncn_graph_node_counts": 0, "ncn_peer_debug_times": 0, "ncn_peer_set_external_zero": 0, "ncn_peer_set_loads": 0, "ncn_peer_set_shape": 0}
+                        "ncn_peer_poll": 0, "ncn_peer_set_timeout": 0, "ncn_graph_node_counts": 0, "ncn_peer_debug_times": 0, "ncn_peer_set_external_zero": 0, "ncn_peer_set_loads": 0, "ncn_peer_set_shape": 0,
+                        "ncn_peer_set_cut": 0, "ncn_peer_set_early_loads": 0, "ncn_peer_segments": 0, "ncn_peer_segments_of": 0, "ncn_peer_debug_times_early": 0}
 
     @classmethod
     def reset(cls):
@@ -127,8 +129,10 @@ def lib():
             fn.restype = res
             fn.argtypes = args
         _lib = _Proxy(h)
-        if os.environ.get("NCN_PDL", "1") == "0":        # developer A/B knob
+        if os.environ.get("NCN_PDL", "1") == "0":        # developer A/B knobs
             h.ncn_set_pdl(0)
+        if os.environ.get("NCN_GRID_BWD_OCC"):
+            h.ncn_set_grid_bwd_occupancy(int(os.environ["NCN_GRID_BWD_OCC"]))
     return _lib
 
 
@@ -250,6 +254,12 @@ SIGNATURES.update({
     "ncn_peer_p16": (c_vp, [c_vp]),
     "ncn_peer_handles": (c_i32, [c_vp, c_vp]),
     "ncn_peer_connect": (c_i32, [c_vp, c_vp]),
+    "ncn_peer_set_cut": (c_i32, [c_vp, c_i64]),
+    "ncn_peer_set_early_loads": (c_i32, [c_i32]),
+    "ncn_peer_segments": (c_i32, [c_vp, c_i32, C.POINTER(c_i64)]),
+    "ncn_peer_segments_of": (None, [c_i64, c_i64, c_i32, c_i32, C.POINTER(c_i64)]),
+    "ncn_peer_early": (c_i32, [c_vp, c_vp, c_vp]),
+    "ncn_peer_debug_times_early": (c_i32, [c_vp, C.POINTER(C.c_ulonglong)]),
     "ncn_peer_shard": (None, [c_i64, c_i32, c_i32, C.POINTER(c_i64), C.POINTER(c_i64)]),
     "ncn_peer_step": (c_i32, [c_vp, c_vp, c_vp, c_vp, C.POINTER(AdamGroups), c_f32, c_f32, c_f32, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "ncn_peer_error": (c_i32, [c_vp, C.POINTER(C.c_uint32)]),

@@ -242,8 +242,8 @@ grid_bwd_kernel(const __grid_constant__ GridMeta meta, const float* __restrict__
 // Samples arrive in ray order, 1.7e-3 apart, so at the coarse levels dozens of consecutive samples fall in the same
 // cell and would issue dozens of same-address reductions (which the L2 atomic unit serialises).  Here a warp takes 32
 // CONSECUTIVE samples of ONE level; lanes in the same grid cell as their left neighbour form a run (found once per
-// sample, not per corner), each corner's contributions are summed over the run with a windowed warp prefix scan whose
-// depth follows the average run length, and only the head lane issues the red.global.add.v2.f32.  Warps whose samples
+// sample, not per corner), each corner's contributions are summed over the run with a windowed segmented warp scan whose
+// depth follows the average run length, and only the run's last lane issues the reduction.  Warps whose samples
 // are not coherent at this level (fine / hashed levels) detect that with one ballot and take the direct path.
 // segmented sums of the 8 corner contributions over runs of lanes in the same cell; runs are cut at W-lane windows so
 // the prefix scan needs log2(W) steps.  `heads` already contains the window starts.
@@ -275,10 +275,13 @@ __device__ __forceinline__ void emit_pair(void* __restrict__ gl, uint32_t i0, ui
 
 template <int W, bool HALF>
 __device__ __forceinline__ void merge_corners(const Cell8& c, bool valid, float g0, float g1, unsigned heads, int lane, void* __restrict__ gl) {
-  const bool head = (heads >> lane) & 1u;
-  const unsigned later = lane < 31 ? (heads >> (lane + 1)) : 0u;
-  const int end = later ? lane + __ffs(later) - 1 : 31;          // last lane of this lane's run (inside the window)
-  const int wl = lane & (W - 1);
+  // segment = run of lanes in one cell, cut at W-lane windows (`heads` has the window starts set).  Segmented Hillis-Steele
+  // scan: at distance o a lane adds its left neighbour's partial sum only if that neighbour belongs to the same segment, so the
+  // LAST lane of a segment ends up with the segment's sum and issues the reduction itself (same cell = same 8 entries) - no
+  // prefix differences, no broadcast back to the head: 2 log2(W) shuffles per corner instead of 2 log2(W) + 4
+  const int start = 31 - __clz(heads & (0xffffffffu >> (31 - lane)));   // bit 0 of `heads` is always set
+  const int dist = lane - start;
+  const bool tail = lane == 31 || ((heads >> (lane + 1)) & 1u);
 #pragma unroll
   for (int k = 0; k < 8; k += 2) {
     float s[2][2];
@@ -287,20 +290,18 @@ __device__ __forceinline__ void merge_corners(const Cell8& c, bool valid, float 
       const float wk = valid ? corner_w(c.w, k + q) : 0.f;
       float vx = wk * g0, vy = wk * g1;
 #pragma unroll
-      for (int o = 1; o < W; o <<= 1) {                          // inclusive prefix sums inside the window
+      for (int o = 1; o < W; o <<= 1) {
         const float tx = __shfl_up_sync(0xffffffffu, vx, o), ty = __shfl_up_sync(0xffffffffu, vy, o);
-        if (wl >= o) { vx += tx; vy += ty; }
+        if (dist >= o) { vx += tx; vy += ty; }
       }
-      const float ex = __shfl_sync(0xffffffffu, vx, end), ey = __shfl_sync(0xffffffffu, vy, end);
-      const float bx = __shfl_up_sync(0xffffffffu, vx, 1), by = __shfl_up_sync(0xffffffffu, vy, 1);
-      s[q][0] = ex - (wl > 0 ? bx : 0.f); s[q][1] = ey - (wl > 0 ? by : 0.f);
+      s[q][0] = vx; s[q][1] = vy;
     }
-    if (head && valid) emit_pair<HALF>(gl, c.idx[k], c.idx[k + 1], s[0][0], s[0][1], s[1][0], s[1][1]);
+    if (tail && valid) emit_pair<HALF>(gl, c.idx[k], c.idx[k + 1], s[0][0], s[0][1], s[1][0], s[1][1]);
   }
 }
 
-template <bool HALF>
-__global__ void __launch_bounds__(256, 5)
+template <bool HALF, int OCC>
+__global__ void __launch_bounds__(256, OCC)
 grid_bwd_merge_kernel(const __grid_constant__ GridMeta meta, const float* __restrict__ x, const __half* __restrict__ dy,
                       int64_t n_cap, const int32_t* __restrict__ n_dev, GridXform xf, float grad_scale, void* __restrict__ grad,
                       int level_begin, int level_end) {
@@ -524,6 +525,13 @@ extern "C" int ncn_grid_fwd(const ncn_grid_desc* desc, const float* x, const voi
 // level_begin/level_end restrict the launch to a range of levels (their gradient regions are contiguous in the table), so a
 // data-parallel caller can all-reduce the first range while the second is still being computed; ctas_per_sm < 8 leaves
 // room on the SMs for the collective's kernels
+static int g_grid_bwd_occ = 5;   // developer A/B knob: CTAs per SM the merge kernel is compiled for (5 or 6)
+extern "C" int ncn_set_grid_bwd_occupancy(int ctas_per_sm) {
+  const int old = g_grid_bwd_occ;
+  if (ctas_per_sm == 5 || ctas_per_sm == 6) g_grid_bwd_occ = ctas_per_sm;
+  return old;
+}
+
 static int grid_bwd_impl(const ncn_grid_desc* desc, const float* x, const void* dy, int64_t n, void* grad, bool half_grad,
                          float grad_scale, const float* xform_host, const int32_t* n_dev, int level_begin, int level_end,
                          int ctas_per_sm, ncn_stream_t stream) {
@@ -536,22 +544,20 @@ static int grid_bwd_impl(const ncn_grid_desc* desc, const float* x, const void* 
   if ((uintptr_t)grad & 7) return NCN_E_ALIGN;
   const bool whole = level_begin == 0 && level_end == m.n_levels;
   const int64_t need = ceil_div(n * (level_end - level_begin), (int64_t)256);
-  if (half_grad) {                                                                                  // 8-byte paired fp16 reductions
-    static int resident = 0;
-    int grid = resident_grid(grid_bwd_merge_kernel<true>, 256, 0, &resident, need);
-    if (ctas_per_sm < 8 && grid > sm_count() * ctas_per_sm) grid = sm_count() * ctas_per_sm;
-    NCN_CUDA(launch_pdl(grid_bwd_merge_kernel<true>, dim3(grid), dim3(256), 0, as_stream(stream), m, x, (const __half*)dy, n, n_dev,
-                        make_xform(xform_host), grad_scale, grad, level_begin, level_end));
-    NCN_LAUNCH_OK();
-    return NCN_OK;
-  }
-  if (desc->n_features == 2 && (g_grid_bwd_merge || !whole) && ((uintptr_t)grad & 15) == 0) {      // 16-byte paired reductions
-    static int resident = 0;
-    int grid = resident_grid(grid_bwd_merge_kernel<false>, 256, 0, &resident, need);
-    if (ctas_per_sm < 8 && grid > sm_count() * ctas_per_sm) grid = sm_count() * ctas_per_sm;
-    NCN_CUDA(launch_pdl(grid_bwd_merge_kernel<false>, dim3(grid), dim3(256), 0, as_stream(stream), m, x, (const __half*)dy, n, n_dev,
-                        make_xform(xform_host), grad_scale, grad, level_begin, level_end));
-    NCN_LAUNCH_OK();
+  if (half_grad || (desc->n_features == 2 && (g_grid_bwd_merge || !whole) && ((uintptr_t)grad & 15) == 0)) {
+    // fp32 table: 16-byte paired reductions; fp16 table: 8-byte ones.  CTAs per SM: 5 (46 registers) or 6 (40, 12 B spilled)
+    static int resident[2][2] = {{0, 0}, {0, 0}};
+    const int o6 = g_grid_bwd_occ == 6 ? 1 : 0;
+#define NCN_GBM(H, O)                                                                                                              \
+  do {                                                                                                                             \
+    int grid = resident_grid(grid_bwd_merge_kernel<H, O>, 256, 0, &resident[H ? 1 : 0][o6], need);                                 \
+    if (ctas_per_sm < 8 && grid > sm_count() * ctas_per_sm) grid = sm_count() * ctas_per_sm;                                       \
+    NCN_CUDA(launch_pdl(grid_bwd_merge_kernel<H, O>, dim3(grid), dim3(256), 0, as_stream(stream), m, x, (const __half*)dy, n, n_dev, \
+                        make_xform(xform_host), grad_scale, grad, level_begin, level_end));                                        \
+  } while (0)
+    if (half_grad) { if (o6) NCN_GBM(true, 6); else NCN_GBM(true, 5); }
+    else { if (o6) NCN_GBM(false, 6); else NCN_GBM(false, 5); }
+#undef NCN_GBM
     return NCN_OK;
   }
   if (!whole) return NCN_E_UNSUPPORTED;

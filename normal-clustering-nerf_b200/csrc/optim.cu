@@ -286,16 +286,18 @@ namespace ncn {
 
 constexpr int kPeerMax = 8;
 struct PeerSync {                       // lives in each rank's own device memory, written by peers
-  unsigned int flag[3][kPeerMax];       // [phase][source rank] = last epoch that rank signalled
+  unsigned int flag[4][kPeerMax];       // [phase][source rank] = last epoch that rank signalled (phase 3: early range complete)
   float norm[2][kPeerMax];              // [epoch & 1][source rank] partial squared norms (NaN = non-finite gradient there)
   unsigned int epoch;                   // local: completed steps
   unsigned int ticket[2];               // local: block tickets of K1 / K2
   unsigned int error;                   // local: a wait timed out
   float partials[kSumsqMaxBlocks];      // local: K1 block partials
+  float partials0[kSumsqMaxBlocks];     // local: block partials of the early reduction (ncn_peer_early), folded in and cleared by K1
   // local, developer timeline (ns, %globaltimer) of the LAST step, written by one thread per event (ncn_peer_debug_times):
   // [0] K1 start  [1] K1 all peers' backward done (wait 0 over)  [2] K1 last block finished its reduction
   // [3] K2 start  [4] K2 norms in / peers done reading (wait 1 over)  [5] K2 last block finished Adam + publish  [6] K2 wait 2 over
   unsigned long long times[8];
+  unsigned long long times0[4];         // early reduction: [0] start  [1] every peer's early range complete  [2] a block finished
 };
 struct PeerPtrs {
   const float* grad[kPeerMax];
@@ -350,18 +352,23 @@ __device__ __forceinline__ bool peer_failed(PeerSync* me) { return *reinterpret_
 template <int U, int B>
 __global__ void __launch_bounds__(256, 2)
 peer_reduce_kernel(PeerPtrs pp, int rank, int world, int64_t lo4, int64_t hi4, float* my_grad /* == pp.grad[rank] */,
-                   const float* __restrict__ grad_div) {
+                   const float* __restrict__ grad_div, int early) {
+  // early = 1 (ncn_peer_early): the same reduction over the EARLY range of this rank's shard, behind its own flag phase (3):
+  // "the early range of my gradient is complete" - the rest of the backward is still running on every rank.  The block
+  // partials of the norm are parked in partials0; the final launch (early = 0) folds them in, in a fixed order.
   PeerSync* me = pp.sync[rank];
+  const int phase = early ? 3 : 0;
+  unsigned long long* tm = early ? me->times0 : me->times;
   __shared__ unsigned int s_epoch;
   if (threadIdx.x == 0) {
     const unsigned int e = *reinterpret_cast<volatile unsigned int*>(&me->epoch) + 1u;
-    if (blockIdx.x == 0) {                     // "my backward is complete": stream order put this kernel after it
+    if (blockIdx.x == 0) {                     // "my backward [its early range] is complete": stream order put this kernel after it
       __threadfence_system();
-      for (int q = 0; q < world; ++q) st_relaxed_sys(&pp.sync[q]->flag[0][rank], e);
+      for (int q = 0; q < world; ++q) st_relaxed_sys(&pp.sync[q]->flag[phase][rank], e);
     }
-    if (blockIdx.x == 0) me->times[0] = peer_now_ns();
-    peer_wait(me, 0, world, e, pp.err_host);
-    if (blockIdx.x == 0) me->times[1] = peer_now_ns();
+    if (blockIdx.x == 0) tm[0] = peer_now_ns();
+    peer_wait(me, phase, world, e, pp.err_host);
+    if (blockIdx.x == 0) tm[1] = peer_now_ns();
     s_epoch = e;
   }
   __syncthreads();
@@ -412,16 +419,22 @@ peer_reduce_kernel(PeerPtrs pp, int rank, int world, int64_t lo4, int64_t hi4, f
     acc = lane < 8 ? s[lane] : 0.f;
     acc = warp_sum(acc);
     if (lane == 0) {
-      me->partials[blockIdx.x] = acc;
-      __threadfence();
-      s_last = atomicAdd(&me->ticket[0], 1u) == gridDim.x - 1;
+      if (early) { me->partials0[blockIdx.x] = acc; tm[2] = peer_now_ns(); s_last = false; }
+      else {
+        me->partials[blockIdx.x] = acc;
+        __threadfence();
+        s_last = atomicAdd(&me->ticket[0], 1u) == gridDim.x - 1;
+      }
     }
   }
   __syncthreads();
   if (!s_last) return;
   __threadfence();
-  float tot = 0.f;                               // fixed order (see sumsq_kernel)
-  for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x) tot += __ldcg(&me->partials[b]);
+  float tot = 0.f;                               // fixed order (see sumsq_kernel); the early launch used the same grid
+  for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x) {
+    tot += __ldcg(&me->partials[b]) + __ldcg(&me->partials0[b]);
+    me->partials0[b] = 0.f;
+  }
   tot = warp_sum(tot);
   if (lane == 0) s[wid] = tot;
   __syncthreads();
@@ -439,7 +452,7 @@ peer_reduce_kernel(PeerPtrs pp, int rank, int world, int64_t lo4, int64_t hi4, f
 }
 
 __global__ void __launch_bounds__(256, 2)
-peer_adam_kernel(PeerPtrs pp, int rank, int world, int64_t lo4, int64_t hi4, int64_t n4, float* __restrict__ param,
+peer_adam_kernel(PeerPtrs pp, int rank, int world, int64_t lo4, int64_t hi4, int64_t lo4e, int64_t hi4e, int64_t n4, float* __restrict__ param,
                  float* __restrict__ grad, float* __restrict__ m, float* __restrict__ v, AdamArgs a,
                  const float* __restrict__ grad_div, const int32_t* __restrict__ skip, const float* __restrict__ lr_bc,
                  float* __restrict__ sumsq_out, int zero_all) {
@@ -468,7 +481,10 @@ peer_adam_kernel(PeerPtrs pp, int rank, int world, int64_t lo4, int64_t hi4, int
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (!do_skip) {
-    for (int64_t i = lo4 + tid; i < hi4; i += stride) {
+    // this rank's shard = [lo4, hi4) of the late range followed by [lo4e, hi4e) of the early range (empty without a cut)
+    const int64_t len_l = hi4 - lo4, len_all = len_l + (hi4e - lo4e);
+    for (int64_t j = tid; j < len_all; j += stride) {
+      const int64_t i = j < len_l ? lo4 + j : lo4e + (j - len_l);
       float4 g = reinterpret_cast<const float4*>(grad)[i];
       float4 p = __ldcs(reinterpret_cast<const float4*>(param) + i), mm = __ldcs(reinterpret_cast<const float4*>(m) + i),
              vv = __ldcs(reinterpret_cast<const float4*>(v) + i);
@@ -489,7 +505,7 @@ peer_adam_kernel(PeerPtrs pp, int rank, int world, int64_t lo4, int64_t hi4, int
   // (zero_all == 0: the caller zeroes the buffer itself after this kernel, off the critical path - ncn_peer_set_external_zero)
   if (zero_all)
     for (int64_t i = tid; i < n4; i += stride)
-      if (do_skip || i < lo4 || i >= hi4) reinterpret_cast<float4*>(grad)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (do_skip || !((i >= lo4 && i < hi4) || (i >= lo4e && i < hi4e))) reinterpret_cast<float4*>(grad)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   __threadfence_system();
   __shared__ bool s_last;
   __syncthreads();
@@ -513,6 +529,7 @@ peer_adam_kernel(PeerPtrs pp, int rank, int world, int64_t lo4, int64_t hi4, int
 struct ncn_peer {
   int rank, world, device;
   int64_t n;
+  int64_t cut;                          // [cut, n) = the early range (ncn_peer_set_cut); cut == n: none
   float* grad;
   void* p16;
   ncn::PeerSync* sync;
@@ -524,7 +541,8 @@ struct ncn_peer {
 };
 
 // developer A/B knob: 16-byte loads in flight per peer and thread in the reduce kernel (1, 2 [default] or 4)
-static int g_peer_loads = 1, g_peer_batch = 4, g_peer_ctas = 2;
+static int g_peer_loads = 1, g_peer_batch = 4, g_peer_ctas = 2, g_peer_early_loads = 0;
+extern "C" int ncn_peer_set_early_loads(int u) { const int old = g_peer_early_loads; if (u == 0 || u == 1 || u == 2 || u == 4) g_peer_early_loads = u; return old; }
 extern "C" int ncn_peer_set_loads(int u) { const int old = g_peer_loads; if (u == 1 || u == 2 || u == 4) g_peer_loads = u; return old; }
 // further A/B knobs of the reduce kernel: peers loaded per batch (2, 4 [default], 8; with loads = 1) and CTAs per SM (1 or 2 [default])
 extern "C" int ncn_peer_set_shape(int peers_per_batch, int ctas_per_sm) {
@@ -537,7 +555,7 @@ extern "C" int ncn_peer_create(ncn_peer** out, int rank, int world, int64_t n_pa
   NCN_CHECK_PTR(out);
   NCN_CHECK_SIZE(world >= 1 && world <= ncn::kPeerMax && rank >= 0 && rank < world && n_params > 0 && (n_params & 3) == 0);
   ncn_peer* p = new ncn_peer();
-  p->rank = rank; p->world = world; p->n = n_params; p->connected = false; p->external_zero = false;
+  p->rank = rank; p->world = world; p->n = n_params; p->cut = n_params; p->connected = false; p->external_zero = false;
   NCN_CUDA(cudaGetDevice(&p->device));
   NCN_CUDA(cudaMalloc(&p->grad, (size_t)n_params * 4));
   NCN_CUDA(cudaMalloc(&p->p16, (size_t)n_params * 2));
@@ -594,6 +612,57 @@ extern "C" void ncn_peer_shard(int64_t n_params, int rank, int world, int64_t* l
   if (hi) *hi = (n4 * (rank + 1) / world) << 2;
 }
 
+// rank q's shard as two segments: [seg[0], seg[1]) of the late range [0, cut) and [seg[2], seg[3]) of the early range [cut, n)
+static void peer_segments(int64_t n, int64_t cut, int q, int world, int64_t seg[4]) {
+  const int64_t c4 = cut >> 2, n4 = n >> 2;
+  seg[0] = (c4 * q / world) << 2; seg[1] = (c4 * (q + 1) / world) << 2;
+  seg[2] = (c4 + (n4 - c4) * q / world) << 2; seg[3] = (c4 + (n4 - c4) * (q + 1) / world) << 2;
+}
+// the same arithmetic without a peer object (host only)
+extern "C" void ncn_peer_segments_of(int64_t n_params, int64_t cut, int rank, int world, int64_t* seg4_out) {
+  if (seg4_out) peer_segments(n_params, cut, rank, world, seg4_out);
+}
+extern "C" int ncn_peer_segments(ncn_peer* p, int rank_q, int64_t* seg4_out) {
+  NCN_CHECK_PTR(p); NCN_CHECK_PTR(seg4_out);
+  NCN_CHECK_SIZE(rank_q >= 0 && rank_q < p->world);
+  peer_segments(p->n, p->cut, rank_q, p->world, seg4_out);
+  return NCN_OK;
+}
+extern "C" int ncn_peer_set_cut(ncn_peer* p, int64_t cut) {
+  NCN_CHECK_PTR(p);
+  NCN_CHECK_SIZE(cut >= 0 && cut <= p->n && (cut & 3) == 0);
+  p->cut = cut;
+  return NCN_OK;
+}
+
+static int peer_launch_reduce(ncn_peer* p, int64_t lo4, int64_t hi4, const float* grad_div_dev, int early, cudaStream_t st) {
+  // the early launch co-runs with the rest of the table backward: ONE CTA per SM (52 registers x 256 threads fit beside four of that
+  // kernel's CTAs; the pull is NVLink bound, its time did not depend on the CTA count - profiles/r2_timeline_8gpu_*)
+  int grid1 = ncn::sm_count() * (early ? 1 : g_peer_ctas);
+  if (grid1 > ncn::kSumsqMaxBlocks) grid1 = ncn::kSumsqMaxBlocks;
+#define NCN_K1(U, B) ncn::peer_reduce_kernel<U, B><<<grid1, 256, 0, st>>>(p->ptrs, p->rank, p->world, lo4, hi4, p->grad, grad_div_dev, early)
+  // the early launch has half the threads of the final one and shares its SMs: keep about 8 loads in flight per thread on small worlds
+  int loads = g_peer_loads;
+  if (early && g_peer_early_loads > 0) loads = g_peer_early_loads;
+  else if (early) loads = p->world <= 2 ? 4 : (p->world <= 4 ? 2 : 1);
+  if (loads == 4) NCN_K1(4, 4);
+  else if (loads == 2) NCN_K1(2, 4);
+  else if (g_peer_batch == 2) NCN_K1(1, 2);
+  else if (g_peer_batch == 8) NCN_K1(1, 8);
+  else NCN_K1(1, 4);
+#undef NCN_K1
+  NCN_LAUNCH_OK();
+  return NCN_OK;
+}
+
+extern "C" int ncn_peer_early(ncn_peer* p, const float* grad_div_dev, ncn_stream_t stream) {
+  NCN_CHECK_PTR(p);
+  if (!p->connected || p->cut >= p->n) return NCN_E_CONFIG;
+  int64_t seg[4];
+  peer_segments(p->n, p->cut, p->rank, p->world, seg);
+  return peer_launch_reduce(p, seg[2] >> 2, seg[3] >> 2, grad_div_dev, 1, ncn::as_stream(stream));
+}
+
 extern "C" int ncn_peer_step(ncn_peer* p, float* param, float* m, float* v, const ncn_adam_groups* groups, float beta1,
                              float beta2, float eps, const float* grad_div_dev, const int32_t* skip_dev,
                              const float* lr_bc_dev, float* sumsq_out_dev, ncn_stream_t stream) {
@@ -609,24 +678,15 @@ extern "C" int ncn_peer_step(ncn_peer* p, float* param, float* m, float* v, cons
     a.start[q] = on ? groups->start[q] : p->n; a.wd[q] = on ? groups->weight_decay[q] : 0.f;
     if (on && (groups->start[q] & 3)) return NCN_E_ALIGN;
   }
-  int64_t lo, hi;
-  ncn_peer_shard(p->n, p->rank, p->world, &lo, &hi);
-  const int64_t lo4 = lo >> 2, hi4 = hi >> 2, n4 = p->n >> 2;
+  int64_t seg[4];
+  peer_segments(p->n, p->cut, p->rank, p->world, seg);
+  const int64_t n4 = p->n >> 2;
   int grid = ncn::sm_count() * 2;
   if (grid > ncn::kSumsqMaxBlocks) grid = ncn::kSumsqMaxBlocks;
   cudaStream_t st = ncn::as_stream(stream);
-  int grid1 = ncn::sm_count() * g_peer_ctas;
-  if (grid1 > ncn::kSumsqMaxBlocks) grid1 = ncn::kSumsqMaxBlocks;
-#define NCN_K1(U, B) ncn::peer_reduce_kernel<U, B><<<grid1, 256, 0, st>>>(p->ptrs, p->rank, p->world, lo4, hi4, p->grad, grad_div_dev)
-  if (g_peer_loads == 4) NCN_K1(4, 4);
-  else if (g_peer_loads == 2) NCN_K1(2, 4);
-  else if (g_peer_batch == 2) NCN_K1(1, 2);
-  else if (g_peer_batch == 8) NCN_K1(1, 8);
-  else NCN_K1(1, 4);
-#undef NCN_K1
-  NCN_LAUNCH_OK();
-  ncn::peer_adam_kernel<<<grid, 256, 0, st>>>(p->ptrs, p->rank, p->world, lo4, hi4, n4, param, p->grad, m, v, a, grad_div_dev,
-                                              skip_dev, lr_bc_dev, sumsq_out_dev, p->external_zero ? 0 : 1);
+  { const int rc = peer_launch_reduce(p, seg[0] >> 2, seg[1] >> 2, grad_div_dev, 0, st); if (rc) return rc; }
+  ncn::peer_adam_kernel<<<grid, 256, 0, st>>>(p->ptrs, p->rank, p->world, seg[0] >> 2, seg[1] >> 2, seg[2] >> 2, seg[3] >> 2, n4, param, p->grad,
+                                              m, v, a, grad_div_dev, skip_dev, lr_bc_dev, sumsq_out_dev, p->external_zero ? 0 : 1);
   NCN_LAUNCH_OK();
   return NCN_OK;
 }
@@ -650,6 +710,12 @@ extern "C" int ncn_peer_set_external_zero(ncn_peer* p, int on) {
 extern "C" int ncn_peer_debug_times(ncn_peer* p, unsigned long long* times8_host) {
   NCN_CHECK_PTR(p); NCN_CHECK_PTR(times8_host);
   NCN_CUDA(cudaMemcpy(times8_host, p->sync->times, sizeof(unsigned long long) * 8, cudaMemcpyDeviceToHost));
+  return NCN_OK;
+}
+
+extern "C" int ncn_peer_debug_times_early(ncn_peer* p, unsigned long long* times4_host) {
+  NCN_CHECK_PTR(p); NCN_CHECK_PTR(times4_host);
+  NCN_CUDA(cudaMemcpy(times4_host, p->sync->times0, sizeof(unsigned long long) * 4, cudaMemcpyDeviceToHost));
   return NCN_OK;
 }
 

@@ -127,6 +127,11 @@ class FusedStep:
             self.peer.set_external_zero(self.ext_zero)
         self.ev_zero = torch.cuda.Event()
         self._zero_forked = False            # True while capturing / running the deferred form: _run_field must join ev_zero
+        # sharded exchange on > 1 rank: the table backward runs as two launches, fine levels first; the fine levels' gradient
+        # (and the MLPs', complete before it) is the exchange's EARLY range, pulled over NVLink by ncn_peer_early on the side
+        # stream while the coarse levels are still being computed (set up in _setup_peer_early once the offsets are known)
+        self.peer_early = None
+        self.ev_fork3, self.ev_join3 = torch.cuda.Event(), torch.cuda.Event()
         self.nccl = trainer.world_size > 1 and self.peer is None
         self.defer = use_graph and not self.nccl and not os.environ.get("NCN_NO_DEFER")      # env: developer A/B only
         # multi-rank: the same overlap with three graphs on two streams and an EAGER all-reduce in between
@@ -415,10 +420,45 @@ class FusedStep:
         ck(L.ncn_mlp_bwd_src_fused(C.byref(sg.desc), C.byref(self.src_sig), ptr(self.feat), ptr(self._w16("sigma_net")), ptr(self.h),
                                    ptr(self.sig_acts), cap, ptr(self._g32("sigma_net")), ptr(self.dfeat), inv, ptr(self.mlp_ws),
                                    self.mlp_ws.numel(), n_dev, st), "sigma_bwd")
-        ck(L.ncn_grid_bwd(C.byref(enc.desc), ptr(self.xyzs), ptr(self.dfeat), cap, ptr(self._g32("xyz_encoder")), inv, self.xform, n_dev, st), "grid_bwd")
+        if self.peer_early is None:
+            self._setup_peer_early()
+        lc = self.peer_early
+        if lc and not getattr(self, "serial", False):
+            ck(L.ncn_grid_bwd_levels(C.byref(enc.desc), ptr(self.xyzs), ptr(self.dfeat), cap, ptr(self._g32("xyz_encoder")), inv, self.xform, n_dev,
+                                     lc, int(enc.desc.n_levels), 8, st), "grid_bwd_fine")
+            self.ev_fork3.record(main)
+            self.side_stream.wait_event(self.ev_fork3)
+            with torch.cuda.stream(self.side_stream):
+                self.peer.early(self.grad_div, self.side_stream.cuda_stream)
+                self.ev_join3.record(self.side_stream)
+            # one CTA slot per SM less than the kernel could fill: the exchange's CTAs must become resident beside it
+            ck(L.ncn_grid_bwd_levels(C.byref(enc.desc), ptr(self.xyzs), ptr(self.dfeat), cap, ptr(self._g32("xyz_encoder")), inv, self.xform, n_dev,
+                                     0, lc, int(os.environ.get("NCN_PEER_EARLY_COARSE_CTAS", "4")), st), "grid_bwd_coarse")
+            main.wait_event(self.ev_join3)
+        else:
+            ck(L.ncn_grid_bwd(C.byref(enc.desc), ptr(self.xyzs), ptr(self.dfeat), cap, ptr(self._g32("xyz_encoder")), inv, self.xform, n_dev, st), "grid_bwd")
+            if lc:                               # instrumented (serial) pass: same exchange, no overlap
+                self.peer.early(self.grad_div, st)
         if cap < self.cap_max:          # overflow is possible: a truncated step must become a skipped step, never a silent one
             ck(L.ncn_step_guard(n_dev, cap, ptr(self.guard), ptr(self.opt.grad), st), "step_guard")
             self.guard_host.copy_(self.guard, non_blocking=True)       # pinned: the host polls it without synchronising
+
+    def _setup_peer_early(self):
+        """decide once whether the exchange gets an early range: > 1 rank on the peer-memory exchange, the hash table is the FIRST
+        tensor of the flat vector (so that [cut, n) = fine levels + every MLP is one contiguous range), NCN_PEER_EARLY=1 (opt-in:
+        see DESIGN.md section 6 for what it measured)"""
+        self.peer_early = 0
+        tr = self.tr
+        force = os.environ.get("NCN_PEER_EARLY_FORCE") == "1"      # developer: the one-rank form (local reads), to look at the co-scheduling
+        if self.peer is None or (tr.world_size < 2 and not force) or os.environ.get("NCN_PEER_EARLY", "0") != "1":
+            return
+        enc = self.model.xyz_encoder
+        o, n = self.off["xyz_encoder"]
+        lc = int(os.environ.get("NCN_PEER_EARLY_LEVEL", "8"))
+        if o != 0 or int(enc.desc.n_features) != 2 or not (0 < lc < int(enc.desc.n_levels)):
+            return
+        self.peer.set_cut(int(enc.desc.level_offset[lc]) * 2)
+        self.peer_early = lc
 
     def _optimizer(self, sched_off=0):
         """sum of squares -> clip coefficient -> fused Adam (both parameter groups); sched_off selects the schedule slot

@@ -94,6 +94,8 @@ class PeerLink:
         import os
         if os.environ.get("NCN_PEER_LOADS"):       # developer A/B only
             L.ncn_peer_set_loads(int(os.environ["NCN_PEER_LOADS"]))
+        if os.environ.get("NCN_PEER_EARLY_LOADS"):
+            L.ncn_peer_set_early_loads(int(os.environ["NCN_PEER_EARLY_LOADS"]))
         if os.environ.get("NCN_PEER_BATCH") or os.environ.get("NCN_PEER_CTAS"):
             L.ncn_peer_set_shape(int(os.environ.get("NCN_PEER_BATCH", "4")), int(os.environ.get("NCN_PEER_CTAS", "2")))
         h = C.c_void_p()
@@ -128,9 +130,24 @@ class PeerLink:
             agree(L.ncn_peer_connect(h, raw) == 0, "cudaIpcOpenMemHandle")
         self.grad = torch.as_tensor(_DeviceMemory(L.ncn_peer_grad(h), self.n, "<f4", self), device=device)
         self.p16 = torch.as_tensor(_DeviceMemory(L.ncn_peer_p16(h), self.n, "<f2", self), device=device)
-        lo, hi = C.c_int64(), C.c_int64()
-        L.ncn_peer_shard(self.n, rank, world_size, C.byref(lo), C.byref(hi))
-        self.shard = (lo.value, hi.value)
+        self.cut = self.n
+        self.shard = self.segments(rank)[0]
+
+    def segments(self, q):
+        """rank q's shard of the flat vector: [(lo, hi) of the late range, (lo, hi) of the early range (empty without a cut)]"""
+        seg = (C.c_int64 * 4)()
+        check(_lib.lib().ncn_peer_segments(self.handle, int(q), seg), "peer_segments")
+        return [(seg[0], seg[1]), (seg[2], seg[3])]
+
+    def set_cut(self, cut):
+        """[cut, n) becomes the early range (include/ncn.h ncn_peer_set_cut); same value on every rank"""
+        check(_lib.lib().ncn_peer_set_cut(self.handle, int(cut)), "peer_set_cut")
+        self.cut = int(cut)
+        self.shard = self.segments(self.rank)[0]
+
+    def early(self, grad_div, st):
+        """reduce this rank's slice of the early range now (its gradient is complete on stream `st`)"""
+        check(_lib.lib().ncn_peer_early(self.handle, ptr(grad_div), st), "peer_early")
 
     def step(self, flat, m, v, groups, betas, eps, grad_div, flag, lr_bc, sumsq_out, st):
         check(_lib.lib().ncn_peer_step(self.handle, ptr(flat), ptr(m), ptr(v), C.byref(groups), betas[0], betas[1], eps, ptr(grad_div),
@@ -309,10 +326,10 @@ class NeRFTrainer:
         self.master_stale = False
         L = _lib.lib()
         for q in range(self.world_size):
-            lo, hi = C.c_int64(), C.c_int64()
-            L.ncn_peer_shard(self.opt.flat.numel(), q, self.world_size, C.byref(lo), C.byref(hi))
-            for buf in (self.opt.flat, self.opt.m, self.opt.v):
-                dist.broadcast(buf[lo.value:hi.value], q)
+            for lo, hi in self.peer.segments(q):
+                if hi > lo:
+                    for buf in (self.opt.flat, self.opt.m, self.opt.v):
+                        dist.broadcast(buf[lo:hi], q)
 
     # dataset tensors that NeRFSystem keeps on the device (train_nerf.py:239-240)
     def set_cameras(self, poses, directions):

@@ -108,3 +108,30 @@ def test_peer_shards_partition_the_parameter_vector():
                 prev = hi.value
                 sizes.append(hi.value - lo.value)
             assert prev == n and max(sizes) - min(sizes) <= 4
+
+
+def test_peer_segments_partition_both_ranges():
+    """ncn_peer_segments_of (host arithmetic of the exchange with an early range, ncn_peer_set_cut): for every cut the W late
+    slices tile [0, cut) and the W early slices tile [cut, n), in rank order, on float4 boundaries, each balanced to within one
+    float4; cut == n reproduces ncn_peer_shard with an empty early range"""
+    import ctypes as C
+    import ncn_b200  # noqa: F401
+    from ncn_b200 import _lib
+    L = _lib.lib()
+    for n in (64, 11468464):
+        for cut in (0, 4, n // 2 // 4 * 4, 3090032 if n > 3090032 else n - 4, n):
+            for world in (1, 2, 3, 8):
+                pl, pe, sl, se = 0, cut, [], []
+                for r in range(world):
+                    seg = (C.c_int64 * 4)()
+                    L.ncn_peer_segments_of(n, cut, r, world, seg)
+                    assert seg[0] == pl and seg[2] == pe and all(v % 4 == 0 for v in seg)
+                    assert seg[1] >= seg[0] and seg[3] >= seg[2]
+                    pl, pe = seg[1], seg[3]
+                    sl.append(seg[1] - seg[0]); se.append(seg[3] - seg[2])
+                    if cut == n:
+                        lo, hi = C.c_int64(), C.c_int64()
+                        L.ncn_peer_shard(n, r, world, C.byref(lo), C.byref(hi))
+                        assert (seg[0], seg[1]) == (lo.value, hi.value) and seg[2] == seg[3] == n
+                assert pl == cut and pe == n
+                assert max(sl) - min(sl) <= 4 and max(se) - min(se) <= 4

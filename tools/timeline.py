@@ -28,7 +28,7 @@ if world > 1:
     dist.init_process_group("nccl", device_id=dev)
 torch.manual_seed(rank)
 R = 8192
-tr = NeRFTrainer(dict(batch_size=R), device=dev, rank=rank, world_size=world)
+tr = NeRFTrainer(dict(batch_size=R), device=dev, rank=rank, world_size=world, shard_optimizer=True if os.environ.get("NCN_TIMELINE_SHARD") == "1" else None)
 grid = synth.density_grid_from_occupancy(synth.room_occupancy(128, 0.5, seed=0))
 tr.model.density_grid.copy_(torch.from_numpy(grid).to(dev))
 vren.packbits(tr.model.density_grid, 5.9, tr.model.density_bitfield)
@@ -62,7 +62,7 @@ if tr.peer is not None:      # the peer step is issued through trainer.PeerLink 
     T.check = check_and_stamp
 fs = tr.fused_step(use_graph=True)
 fs.set_triangles(torch.from_numpy(b["tri"]).to(dev))
-acc, peer_acc = None, None
+acc, peer_acc, early_acc = None, None, None
 n_rep = 0
 for i in range(24):
     ro, rd, rgb = batches[i % NB]
@@ -78,6 +78,11 @@ for i in range(24):
             orig_check(L.ncn_peer_debug_times(tr.peer.handle, buf), "peer_debug_times")
             p = (np.array(list(buf)[:7], dtype=np.float64) - t0) / 1e3
             peer_acc = p if peer_acc is None else peer_acc + p
+            if getattr(fs, "peer_early", 0):
+                b4 = (C.c_ulonglong * 4)()
+                orig_check(L.ncn_peer_debug_times_early(tr.peer.handle, b4), "peer_debug_times_early")
+                q = (np.array(list(b4)[:3], dtype=np.float64) - t0) / 1e3
+                early_acc = q if early_acc is None else early_acc + q
         n_rep += 1
 fs.flush()
 t = acc / n_rep
@@ -98,6 +103,11 @@ if peer_acc is not None:
     res["peer_split_us"] = {"K1 wait for peers' backward": float(p[1] - p[0]), "K1 reduce 7/8 of the shard over NVLink": float(p[2] - p[1]),
                             "K1 end -> K2 start": float(p[3] - p[2]), "K2 wait for norms": float(p[4] - p[3]),
                             "K2 Adam + publish": float(p[5] - p[4]), "K2 wait for all publishes": float(p[6] - p[5]), "total": float(p[6] - p[0])}
+if early_acc is not None:
+    q = early_acc / n_rep
+    res["peer_early_us (same time base; this replay's backward)"] = {"start": float(q[0]), "every peer's early range complete": float(q[1]), "a block finished its pull": float(q[2])}
+    res["peer_split_us"]["EARLY: wait for peers' fine levels"] = float(q[1] - q[0])
+    res["peer_split_us"]["EARLY: pull of the early range (one block's end)"] = float(q[2] - q[1])
 if world > 1:
     every = [None] * world
     dist.all_gather_object(every, res)
