@@ -119,9 +119,45 @@ def _time_gpu(fn, reps=20, warmup=3):
     return _median(ts)
 
 
+def _time_graph(fn, calls=10, replays=5):
+    """device time per call with the host out of the picture: `calls` invocations captured into one CUDA graph, the replay timed
+    with events.  None when the function cannot be captured (host synchronisation / host-side sizing inside it)."""
+    import torch
+    try:
+        fn(); torch.cuda.synchronize()
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.stream(s):
+            with torch.cuda.graph(g, stream=s):
+                for _ in range(calls):
+                    fn()
+        torch.cuda.current_stream().wait_stream(s)
+        g.replay(); torch.cuda.synchronize()
+        ts = []
+        for _ in range(replays):
+            e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+            e0.record(); g.replay(); e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1) * 1e3 / calls)
+        del g
+        return _median(ts)
+    except Exception:  # noqa: BLE001
+        try:
+            torch.cuda.synchronize()
+        except Exception:  # noqa: BLE001
+            pass
+        return None
+
+
 def ref_kernels_gpu(n_rays=8192, reps=20):
     """us per call of each of the 15 vren functions (binding.cpp:330-350): reference csrc (vren_ref) vs libncn (ncn_b200.vren), same
-    inputs, CUDA events around the python-level call (both sides pay their own output allocations, as the reference's callers do)."""
+    inputs.  `ours_us` / `ref_us`: CUDA events around ONE python-level call on an idle GPU (both sides pay their own output
+    allocations and their own host-side call path - ctypes here, pybind there: the calls of a few microseconds of device work are
+    host bound on both sides).  `ours_device_us`: the libncn call captured 10x into a CUDA graph and replayed = its device time
+    alone (null where the call sizes its outputs on the host).  The reference's functions launch on the legacy default stream
+    (`<<<blocks, threads>>>` without a stream argument), which a stream capture does not record, so there is no such figure for
+    them - a graph of them contains only their output allocations."""
     import numpy as np
     import torch
     import ncn_b200  # noqa: F401
@@ -155,6 +191,7 @@ def ref_kernels_gpu(n_rays=8192, reps=20):
     def both(name, f_ours, f_ref, work=None):
         t_o = _time_gpu(f_ours, reps); t_r = _time_gpu(f_ref, reps)
         out[name] = {"ours_us": t_o, "ref_us": t_r, "speedup": t_r / t_o}
+        out[name]["ours_device_us"] = _time_graph(f_ours)
         if work:
             out[name]["work"] = work
 
