@@ -403,3 +403,31 @@ def test_device_batch_sampling_triangle_expansion(strategy, expand):
     assert np.array_equal(got[:, 0], x1n) and np.array_equal(got[:, 1], x2n) and np.array_equal(got[:, 2], x3n)
     if expand:
         assert (x1n != x1).any() and (x1n == x1).any() and (x3n != x3).any() and (x3n == x3).any()      # both branches occur
+
+
+def test_programmatic_dependent_launch_changes_no_result():
+    """ncn_set_pdl(0/1): the forward of one eager fused step (everything up to the losses is deterministic: no atomics) is
+    bit-identical with and without programmatic dependent launch, and so is a CUDA-graph replay of it"""
+    from ncn_b200 import _lib
+    L = _lib.lib()
+    outs = {}
+    old = L.ncn_set_pdl(1)
+    try:
+        for mode in ((1, False), (0, False), (1, True), (0, True)):
+            L.ncn_set_pdl(mode[0])
+            tr, rays_o, rays_d, tri, rgb, target = _setup(R=1024, seed=3)
+            fs = tr.fused_step(use_graph=mode[1]); fs.set_triangles(tri)
+            noise = torch.rand(1024, device="cuda", generator=torch.Generator(device="cuda").manual_seed(9))
+            fs.step(rays_o, rays_d, rgb, noise=noise)
+            fs.flush()
+            torch.cuda.synchronize()
+            n_live = int(fs.counter[0])
+            outs[mode] = (fs.rend.clone(), fs.depth.clone(), fs.opacity.clone(), fs.losses.clone(), fs.d_sigmas[:n_live].clone(), n_live)
+    finally:
+        L.ncn_set_pdl(old)
+    ref = outs[(0, False)]
+    assert ref[5] > 1024 and torch.isfinite(ref[3]).all()
+    for mode, got in outs.items():
+        for a, b in zip(ref[:5], got[:5]):
+            assert torch.equal(a, b), mode
+        assert got[5] == ref[5]

@@ -203,3 +203,94 @@ def test_fused_step_with_sharded_optimizer_single_rank():
     moved = float((tr2.opt.flat - p_start).norm() / p_start.norm())
     assert moved > 5 * rel, (moved, rel)
     assert torch.equal(tr2.opt.flat16, tr2.opt.flat.to(torch.float16))
+
+
+@pytest.mark.parametrize("cut_frac", [0.0, 0.37, 1.0])
+def test_peer_step_with_early_range_single_rank(ncn, cut_frac):
+    """ncn_peer_set_cut + ncn_peer_early + ncn_peer_step at world_size 1 against ncn_grad_sumsq + ncn_adam_step_groups: the
+    early kernel reduces [cut, n) (a self-copy at one rank) and parks its share of the norm, the step's reduce kernel handles
+    [0, cut) and folds the parked partials in - together the same norm, the same update, a zeroed gradient.  cut = n is the
+    plain step and refuses ncn_peer_early; cut = 0 makes everything early."""
+    import ctypes as C
+    from ncn_b200 import _lib
+    from ncn_b200._lib import check, ptr, stream
+    from ncn_b200.trainer import PeerLink
+    L = _lib.lib()
+    n = (1 << 20) + 4 * 33
+    cut = int(n * cut_frac) // 4 * 4
+    dev = torch.device("cuda", torch.cuda.current_device())
+    g = torch.Generator(device="cuda").manual_seed(3)
+    link = PeerLink(0, 1, n, dev)
+    link.set_cut(cut)
+    assert link.segments(0) == [(0, cut), (cut, n)] and link.shard == (0, cut)
+    p0 = torch.randn(n, device="cuda", generator=g) * 0.1
+    groups = _lib.AdamGroups(); groups.n_groups = 2; groups.start[0] = 0; groups.start[1] = n - 4096
+    groups.weight_decay[0] = 0.0; groups.weight_decay[1] = 1e-6; groups.max_norm = 0.05
+    div = torch.tensor([2.0], device="cuda")
+    state = {k: [p0.clone(), torch.zeros(n, device="cuda"), torch.zeros(n, device="cuda")] for k in ("peer", "ref")}
+    p16_ref = torch.zeros(n, dtype=torch.float16, device="cuda")
+    flag = torch.zeros(1, dtype=torch.int32, device="cuda")
+    for step in range(1, 4):
+        grad = torch.randn(n, device="cuda", generator=g) * (10.0 ** -step)
+        lr_bc = torch.tensor([1e-2, 1 - 0.9 ** step, 1 - 0.999 ** step], device="cuda")
+        link.grad.copy_(grad)
+        sumsq_p = torch.zeros(1, device="cuda")
+        p, m, v = state["peer"]
+        if cut < n:
+            link.early(div, stream())
+        else:
+            assert L.ncn_peer_early(link.handle, ptr(div), stream()) != 0
+        link.step(p, m, v, groups, (0.9, 0.999), 1e-15, div, flag, lr_bc, sumsq_p, stream())
+        gr = grad.clone(); sumsq = torch.zeros(1, device="cuda")
+        p, m, v = state["ref"]
+        check(L.ncn_grad_sumsq(ptr(gr), n, ptr(div), ptr(sumsq), ptr(flag), stream()))
+        check(L.ncn_adam_step_groups(ptr(p), ptr(gr), ptr(m), ptr(v), ptr(p16_ref), n, C.byref(groups), 0.9, 0.999, 1e-15, ptr(div), ptr(flag),
+                                     ptr(sumsq), ptr(lr_bc), stream()))
+        torch.testing.assert_close(sumsq_p, sumsq, rtol=1e-5, atol=0)
+        # the norm is summed in a different order (parked early partials + final partials): the clip coefficient may differ in its
+        # last ulps, i.e. the lr = 1e-2 update by a few 1e-9
+        for a, b in zip(state["peer"], state["ref"]):
+            torch.testing.assert_close(a, b, rtol=2e-5, atol=1e-8)
+        torch.testing.assert_close(link.p16.float(), p16_ref.float(), rtol=2e-3, atol=1e-7)
+        assert float(link.grad.abs().max()) == 0.0
+    # a non-finite value in the EARLY range must poison the norm through the parked partials and skip the step
+    if 0 < cut < n:
+        before = state["peer"][0].clone()
+        bad = torch.zeros(n, device="cuda"); bad[n - 5] = float("inf")
+        link.grad.copy_(bad)
+        link.early(div, stream())
+        link.step(*state["peer"], groups, (0.9, 0.999), 1e-15, div, flag, lr_bc, sumsq_p, stream())
+        torch.cuda.synchronize()
+        assert torch.equal(state["peer"][0], before) and float(link.grad.abs().max()) == 0.0 and not torch.isfinite(sumsq_p).all()
+    assert link.error() == 0
+    link.close()
+
+
+def test_fused_step_early_range_single_rank(monkeypatch):
+    """FusedStep with the exchange's early range switched on (the one-rank form, NCN_PEER_EARLY_FORCE): the table backward runs as
+    two launches with ncn_peer_early between them on the side stream; trains like the plain sharded step"""
+    from test_fused_gpu import _setup
+    from ncn_b200.trainer import NeRFTrainer
+    tr, rays_o, rays_d, tri, rgb, target = _setup(R=1024, seed=1)
+    monkeypatch.setenv("NCN_PEER_EARLY", "1"); monkeypatch.setenv("NCN_PEER_EARLY_FORCE", "1")
+    torch.manual_seed(1)
+    tr2 = NeRFTrainer(dict(batch_size=1024), device="cuda", shard_optimizer=True)
+    tr2.model.density_grid.copy_(tr.model.density_grid); tr2.model.density_bitfield.copy_(tr.model.density_bitfield)
+    tr2.opt.flat.copy_(tr.opt.flat); tr2.opt.flat16.copy_(tr.opt.flat16); tr2.global_step = tr.global_step
+    noise = torch.rand(1024, device="cuda")
+    fs = tr.fused_step(use_graph=True); fs.set_triangles(tri)
+    fs2 = tr2.fused_step(use_graph=True); fs2.set_triangles(tri)
+    p_start = tr2.opt.flat.clone()
+    for i in range(4):
+        fs.step(rays_o, rays_d, rgb, noise=noise)
+        fs2.step(rays_o, rays_d, rgb, noise=noise)
+    fs.flush(); fs2.flush()
+    torch.cuda.synchronize()
+    assert fs2.peer_early == 8 and tr2.peer.cut == int(tr2.model.xyz_encoder.desc.level_offset[8]) * 2
+    assert tr2.peer.error() == 0
+    rel = float((tr.opt.flat - tr2.opt.flat).norm() / tr.opt.flat.norm())
+    assert rel < 5e-3, rel
+    moved = float((tr2.opt.flat - p_start).norm() / p_start.norm())
+    assert moved > 5 * rel, (moved, rel)
+    assert torch.equal(tr2.opt.flat16, tr2.opt.flat.to(torch.float16))
+    assert float(tr2.opt.grad.abs().max()) == 0.0
