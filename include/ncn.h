@@ -206,6 +206,15 @@ int ncn_composite_train_fw_photometric(const float* sigmas, const float* raws, c
                                        float* ws, const float* target_rgb, const float* bg_rgb_host, float opacity_w,
                                        float grad_scale, float* rgb_out, float* sums, float* dL_drend, float* dL_dopacity,
                                        ncn_stream_t stream);
+/* the same with a target colour on the first n_gt_rays rays only (--random_tr_poses, losses.py:265-297: the rays of the generated
+ * poses have no ground truth): the squared error is a mean over 3 n_gt_rays values and rays >= n_gt_rays get a zero colour
+ * gradient; the opacity term stays a mean over all n_rays.  target_rgb (n_gt_rays,3); may be NULL when n_gt_rays == 0. */
+int ncn_composite_train_fw_photometric_gt(const float* sigmas, const float* raws, const float* deltas, const float* ts,
+                                          const int64_t* rays_a, float T_threshold, int64_t n_rays, int64_t capacity,
+                                          int n_channels, int64_t* total_samples, float* opacity, float* depth, float* rend,
+                                          float* ws, const float* target_rgb, int64_t n_gt_rays, const float* bg_rgb_host,
+                                          float opacity_w, float grad_scale, float* rgb_out, float* sums, float* dL_drend,
+                                          float* dL_dopacity, ncn_stream_t stream);
 /* out: dL_dsigmas (N), dL_draws (N,C) fully written for the samples the rays_a rows
  * cover.  dL_dopacity / dL_ddepth / dL_drend / dL_dws may each be NULL (= zeros).
  * Either output pointer (not both) may be NULL to skip it: dL_draws depends on dL_drend only, so a caller
@@ -459,6 +468,13 @@ int ncn_sample_ray_batch(int strategy, int64_t* seed_dev, int n_rays, int n_pose
  * max_expand rows up, x3 max_expand pixels left, each only when it stays inside the image / its row (triangle strategies) */
 int ncn_sample_ray_batch_ex(int strategy, int64_t* seed_dev, int n_rays, int n_poses, int height, int width, int patch_size,
                             int max_expand, int64_t* img_idx, int64_t* pix_idx, ncn_stream_t stream);
+/* random_tr_poses (datasets/base.py:106-126, 148-159 `rnd_img_idxs`; train_nerf.py:169-172): fills rows [n_gt_rays, 2 n_gt_rays) of
+ * a batch whose first n_gt_rays rows ncn_sample_ray_batch[_ex] has drawn: pix_idx repeats the first half ("same pixels for random
+ * camera poses"), img_idx = pose_offset + a draw in [0, n_random_poses) per patch / triangle (strategies 0, 2) or one draw for the
+ * whole batch (1, 3).  pose_offset = where the generated poses start in the pose table handed to ncn_rays_from_pixels (the
+ * reference concatenates them behind the training poses' rows, train_nerf.py:170).  Reads seed_dev (does not advance it). */
+int ncn_sample_random_pose_half(int strategy, const int64_t* seed_dev, int n_gt_rays, int n_random_poses, int64_t pose_offset,
+                                int patch_size, int64_t* img_idx, int64_t* pix_idx, ncn_stream_t stream);
 int ncn_gather_pixels(const void* table, const int64_t* img_idx, const int64_t* pix_idx, int64_t n, int64_t pixels_per_image,
                       int words_per_pixel, void* out, ncn_stream_t stream);
 
@@ -534,6 +550,12 @@ int ncn_photometric_loss(const float* rend, const float* opacity, const float* t
                          int64_t n_rays, int n_channels, const float* bg_rgb_host,
                          float opacity_w, float grad_scale, float* rgb_out, float* sums,
                          float* dL_drend, float* dL_dopacity, ncn_stream_t stream);
+
+/* ncn_photometric_loss with a target colour on the first n_gt_rays rays only (see ncn_composite_train_fw_photometric_gt) */
+int ncn_photometric_loss_gt(const float* rend, const float* opacity, const float* target_rgb,
+                            int64_t n_rays, int64_t n_gt_rays, int n_channels, const float* bg_rgb_host,
+                            float opacity_w, float grad_scale, float* rgb_out, float* sums,
+                            float* dL_drend, float* dL_dopacity, ncn_stream_t stream);
 
 /* Semantic cross-entropy on the rendered logits (losses.py:226-242, 569-573: nn.CrossEntropyLoss(ignore_index=-1)
  * applied to (sem_pred, target - 1), mean over the non-void rays): logits = rend[:, c_off : c_off + n_cls] (row stride

@@ -38,6 +38,8 @@ SIGNATURES = {
                                        c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "ncn_composite_train_fw_photometric": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_f32, c_i64, c_i64, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp,
                                                    c_vp, c_vp, c_f32, c_f32, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "ncn_composite_train_fw_photometric_gt": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_f32, c_i64, c_i64, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp,
+                                                      c_vp, c_i64, c_vp, c_f32, c_f32, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "ncn_composite_train_bw": (c_i32, [c_vp] * 13 + [c_f32, c_i64, c_i64, c_i32, c_vp, c_vp, c_vp]),
     "ncn_composite_test_fw": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_f32, c_vp, c_i64, c_i32, c_i32,
                                       c_vp, c_vp, c_vp, c_vp]),
@@ -220,8 +222,10 @@ SIGNATURES.update({
     "ncn_cluster_loss_bw": (c_i32, [c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp]),
     "ncn_cluster_tail": (c_i32, [c_vp, c_vp, c_i64, c_i32, c_f32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "ncn_photometric_loss": (c_i32, [c_vp, c_vp, c_vp, c_i64, c_i32, C.POINTER(c_f32), c_f32, c_f32, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "ncn_photometric_loss_gt": (c_i32, [c_vp, c_vp, c_vp, c_i64, c_i64, c_i32, C.POINTER(c_f32), c_f32, c_f32, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "ncn_sample_ray_batch": (c_i32, [c_i32, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp]),
     "ncn_sample_ray_batch_ex": (c_i32, [c_i32, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp]),
+    "ncn_sample_random_pose_half": (c_i32, [c_i32, c_vp, c_i32, c_i32, c_i64, c_i32, c_vp, c_vp, c_vp]),
     "ncn_gather_pixels": (c_i32, [c_vp, c_vp, c_vp, c_i64, c_i64, c_i32, c_vp, c_vp]),
     "ncn_normals_from_depth_image": (c_i32, [c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp]),
     "ncn_semantic_ce_loss": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_vp, c_i64, c_f32, c_vp, c_vp, c_vp]),

@@ -385,6 +385,7 @@ struct PhotoArgs {
   float* sums;              // [0] += sum sq err, [1] += sum entropy
   float* d_rend;            // (R,CT) or null
   float* d_opacity;         // (R) or null
+  int64_t n_gt;             // rays [0, n_gt) have a target colour; the rest (random_tr_poses, losses.py:271-297) only the opacity term
 };
 
 template <int CT, int W, bool PHOTO>
@@ -460,7 +461,7 @@ composite_train_fw_sw_kernel(const float* __restrict__ sigmas, const float* __re
         for (int c = 0; c < 3; ++c) {
           const float v = acc_r[c] + ph.bg[c] * (1.f - acc_o);
           if (ph.rgb_out) ph.rgb_out[3 * ray_idx + c] = v;
-          const float e = v - ph.target[3 * ray_idx + c];
+          const float e = ray_idx < ph.n_gt ? v - ph.target[3 * ray_idx + c] : 0.f;
           ph_se += e * e;
           const float g = 2.f * e * ph.inv3n * ph.gscale;
           if (ph.d_rend) ph.d_rend[ray_idx * CT + c] = g;
@@ -680,13 +681,14 @@ extern "C" int ncn_composite_train_fw(const float* sigmas, const float* raws, co
 }
 
 // compositing forward + the photometric / opacity loss terms and their gradients in ONE launch (C = 3, 6 or 9)
-extern "C" int ncn_composite_train_fw_photometric(const float* sigmas, const float* raws, const float* deltas, const float* ts,
-                                                  const int64_t* rays_a, float T_threshold, int64_t n_rays, int64_t capacity,
-                                                  int n_channels, int64_t* total_samples, float* opacity, float* depth, float* rend,
-                                                  float* ws, const float* target_rgb, const float* bg_rgb_host, float opacity_w,
-                                                  float grad_scale, float* rgb_out, float* sums, float* dL_drend, float* dL_dopacity,
-                                                  ncn_stream_t stream) {
-  NCN_CHECK_SIZE(n_rays >= 0 && capacity >= 0);
+// n_gt_rays: rays [0, n_gt_rays) carry a target colour (the squared error is a mean over them), every ray the opacity term
+extern "C" int ncn_composite_train_fw_photometric_gt(const float* sigmas, const float* raws, const float* deltas, const float* ts,
+                                                     const int64_t* rays_a, float T_threshold, int64_t n_rays, int64_t capacity,
+                                                     int n_channels, int64_t* total_samples, float* opacity, float* depth, float* rend,
+                                                     float* ws, const float* target_rgb, int64_t n_gt_rays, const float* bg_rgb_host,
+                                                     float opacity_w, float grad_scale, float* rgb_out, float* sums, float* dL_drend,
+                                                     float* dL_dopacity, ncn_stream_t stream) {
+  NCN_CHECK_SIZE(n_rays >= 0 && capacity >= 0 && n_gt_rays >= 0 && n_gt_rays <= n_rays);
   if (n_channels != 3 && n_channels != 6 && n_channels != 9) return NCN_E_UNSUPPORTED;
   if (n_rays == 0) return NCN_OK;
   NCN_CHECK_PTR(rays_a); NCN_CHECK_PTR(total_samples); NCN_CHECK_PTR(opacity); NCN_CHECK_PTR(depth); NCN_CHECK_PTR(rend);
@@ -694,8 +696,8 @@ extern "C" int ncn_composite_train_fw_photometric(const float* sigmas, const flo
   if (capacity > 0) { NCN_CHECK_PTR(sigmas); NCN_CHECK_PTR(deltas); NCN_CHECK_PTR(ts); NCN_CHECK_PTR(ws); NCN_CHECK_PTR(raws); }
   PhotoArgs ph;
   ph.target = target_rgb; ph.bg[0] = bg_rgb_host[0]; ph.bg[1] = bg_rgb_host[1]; ph.bg[2] = bg_rgb_host[2];
-  ph.opacity_w = opacity_w; ph.gscale = grad_scale; ph.inv3n = 1.0f / (3.0f * (float)n_rays); ph.invn = 1.0f / (float)n_rays;
-  ph.rgb_out = rgb_out; ph.sums = sums; ph.d_rend = dL_drend; ph.d_opacity = dL_dopacity;
+  ph.opacity_w = opacity_w; ph.gscale = grad_scale; ph.inv3n = n_gt_rays > 0 ? 1.0f / (3.0f * (float)n_gt_rays) : 0.f; ph.invn = 1.0f / (float)n_rays;
+  ph.rgb_out = rgb_out; ph.sums = sums; ph.d_rend = dL_drend; ph.d_opacity = dL_dopacity; ph.n_gt = n_gt_rays;
   const int w = g_composite_width < 32 ? g_composite_width : 16;
   const int gsw = persistent_grid(n_rays * w, 256, 8);
 #define NCN_CFP(CT, W) NCN_CUDA(launch_pdl(composite_train_fw_sw_kernel<CT, W, true>, dim3(gsw), dim3(256), 0, as_stream(stream), sigmas, raws, deltas, ts, \
@@ -706,6 +708,17 @@ extern "C" int ncn_composite_train_fw_photometric(const float* sigmas, const flo
 #undef NCN_CFP
   NCN_LAUNCH_OK();
   return NCN_OK;
+}
+
+extern "C" int ncn_composite_train_fw_photometric(const float* sigmas, const float* raws, const float* deltas, const float* ts,
+                                                  const int64_t* rays_a, float T_threshold, int64_t n_rays, int64_t capacity,
+                                                  int n_channels, int64_t* total_samples, float* opacity, float* depth, float* rend,
+                                                  float* ws, const float* target_rgb, const float* bg_rgb_host, float opacity_w,
+                                                  float grad_scale, float* rgb_out, float* sums, float* dL_drend, float* dL_dopacity,
+                                                  ncn_stream_t stream) {
+  return ncn_composite_train_fw_photometric_gt(sigmas, raws, deltas, ts, rays_a, T_threshold, n_rays, capacity, n_channels, total_samples,
+                                               opacity, depth, rend, ws, target_rgb, n_rays, bg_rgb_host, opacity_w, grad_scale, rgb_out,
+                                               sums, dL_drend, dL_dopacity, stream);
 }
 
 extern "C" int ncn_composite_train_bw(const float* dL_dopacity, const float* dL_ddepth, const float* dL_drend,

@@ -1137,12 +1137,12 @@ cluster_bw_depth_kernel(const float* __restrict__ nrm, const int32_t* __restrict
 // Gradients are multiplied by `gscale` (loss scale / grad divisor) and written (not accumulated).
 __global__ void __launch_bounds__(256)
 photometric_kernel(const float* __restrict__ rend, const float* __restrict__ opacity, const float* __restrict__ target,
-                   int64_t n_rays, int C, float bg0, float bg1, float bg2, float opacity_w, float gscale,
+                   int64_t n_rays, int64_t n_gt, int C, float bg0, float bg1, float bg2, float opacity_w, float gscale,
                    float* __restrict__ rgb_out, float* __restrict__ sums, float* __restrict__ d_rend,
                    float* __restrict__ d_opacity) {
   float se = 0.f, ent = 0.f;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  const float inv3n = 1.0f / (3.0f * (float)n_rays), invn = 1.0f / (float)n_rays;
+  const float inv3n = n_gt > 0 ? 1.0f / (3.0f * (float)n_gt) : 0.f, invn = 1.0f / (float)n_rays;
   for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_rays; r += stride) {
     const float o = opacity[r];
     const float bg[3] = {bg0, bg1, bg2};
@@ -1151,7 +1151,7 @@ photometric_kernel(const float* __restrict__ rend, const float* __restrict__ opa
     for (int c = 0; c < 3; ++c) {
       const float v = rend[r * C + c] + bg[c] * (1.f - o);
       if (rgb_out) rgb_out[3 * r + c] = v;
-      const float e = v - target[3 * r + c];
+      const float e = r < n_gt ? v - target[3 * r + c] : 0.f;      // rays beyond n_gt have no target colour (random_tr_poses)
       se += e * e;
       const float g = 2.f * e * inv3n * gscale;
       if (d_rend) d_rend[r * C + c] = g;
@@ -1451,18 +1451,26 @@ extern "C" int ncn_cluster_bw_depth(const float* normals, const int32_t* labels,
   return NCN_OK;
 }
 
+extern "C" int ncn_photometric_loss_gt(const float* rend, const float* opacity, const float* target_rgb, int64_t n_rays,
+                                       int64_t n_gt_rays, int n_channels, const float* bg_rgb_host, float opacity_w, float grad_scale,
+                                       float* rgb_out, float* sums, float* dL_drend, float* dL_dopacity, ncn_stream_t stream) {
+  NCN_CHECK_SIZE(n_rays >= 0 && n_channels >= 3 && n_gt_rays >= 0 && n_gt_rays <= n_rays);
+  if (n_rays == 0) return NCN_OK;
+  NCN_CHECK_PTR(rend); NCN_CHECK_PTR(opacity); NCN_CHECK_PTR(bg_rgb_host); NCN_CHECK_PTR(sums);
+  if (n_gt_rays > 0) NCN_CHECK_PTR(target_rgb);
+  photometric_kernel<<<persistent_grid(n_rays, 256, 4), 256, 0, as_stream(stream)>>>(
+      rend, opacity, target_rgb, n_rays, n_gt_rays, n_channels, bg_rgb_host[0], bg_rgb_host[1], bg_rgb_host[2], opacity_w, grad_scale,
+      rgb_out, sums, dL_drend, dL_dopacity);
+  NCN_LAUNCH_OK();
+  return NCN_OK;
+}
+
 extern "C" int ncn_photometric_loss(const float* rend, const float* opacity, const float* target_rgb, int64_t n_rays,
                                     int n_channels, const float* bg_rgb_host, float opacity_w, float grad_scale,
                                     float* rgb_out, float* sums, float* dL_drend, float* dL_dopacity,
                                     ncn_stream_t stream) {
-  NCN_CHECK_SIZE(n_rays >= 0 && n_channels >= 3);
-  if (n_rays == 0) return NCN_OK;
-  NCN_CHECK_PTR(rend); NCN_CHECK_PTR(opacity); NCN_CHECK_PTR(target_rgb); NCN_CHECK_PTR(bg_rgb_host); NCN_CHECK_PTR(sums);
-  photometric_kernel<<<persistent_grid(n_rays, 256, 4), 256, 0, as_stream(stream)>>>(
-      rend, opacity, target_rgb, n_rays, n_channels, bg_rgb_host[0], bg_rgb_host[1], bg_rgb_host[2], opacity_w, grad_scale,
-      rgb_out, sums, dL_drend, dL_dopacity);
-  NCN_LAUNCH_OK();
-  return NCN_OK;
+  return ncn_photometric_loss_gt(rend, opacity, target_rgb, n_rays, n_rays, n_channels, bg_rgb_host, opacity_w, grad_scale, rgb_out, sums,
+                                 dL_drend, dL_dopacity, stream);
 }
 
 extern "C" int ncn_semantic_ce_loss(const float* rend, int c_total, int c_off, int n_cls, const int64_t* labels, int64_t n_rays,

@@ -6,6 +6,7 @@
 //     1 same_image_triang_patch   one image for the whole batch
 //     2 all_images_triang         n_tri = R / 3 triangles (x1, x2 = up, x3 = left), image per triangle
 //     3 same_image_triang         one image
+//   random_tr_poses: ncn_sample_random_pose_half appends the same pixels seen from generated poses (second half of the batch)
 //   max_expand > 0 (triangle strategies, base.py:130-141): x1 moves `expand` rows down when that stays inside the image, x2
 //   `expand` rows up when that stays inside, x3 `expand` pixels left when that stays in its row (python floor division)
 // Reference quirk kept: the patch corner is drawn as an INDEX into valid_idx['patch_corners'] (0 <= c < (H-p+1)(W-p+1)) and
@@ -64,6 +65,23 @@ sample_batch_kernel(int strategy, int64_t* __restrict__ seed_dev, int n_rays, in
 
 __global__ void sample_advance_kernel(int64_t* seed_dev) { *seed_dev += 1; }
 
+// random_tr_poses (datasets/base.py:106-126, 148-159; train_nerf.py:169-172): the second half of the batch repeats the pixels of the
+// first half, seen from GENERATED poses - one pose per patch / triangle (all_images_*) or one for the whole batch (same_image_*).
+// Draw index 2 of the counter hash: independent of the image / corner draws (0, 1) of sample_batch_kernel for any seed.
+__global__ void __launch_bounds__(256)
+sample_random_half_kernel(int strategy, const int64_t* __restrict__ seed_dev, int n_gt, int n_random_poses, int64_t pose_offset, int group,
+                          int64_t* __restrict__ img_idx, int64_t* __restrict__ pix_idx) {
+  const uint64_t seed = (uint64_t)*seed_dev;
+  const bool same = (strategy & 1) != 0;
+  const int64_t same_pose = smp_below(smp_hash(seed, 0xFFFFFFFFull, 2), n_random_poses);
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < n_gt; r += gridDim.x * blockDim.x) {
+    const int q = r / group;
+    const int64_t pose = same ? same_pose : smp_below(smp_hash(seed, (uint64_t)q, 2), n_random_poses);
+    img_idx[n_gt + r] = pose_offset + pose;
+    pix_idx[n_gt + r] = pix_idx[r];
+  }
+}
+
 // out[r, :] = table[img[r], pix[r], :]  (rows of `width` 4-byte words: rgb f32 x3, a depth f32, an int32 label ...)
 __global__ void __launch_bounds__(256)
 gather_pixels_kernel(const uint32_t* __restrict__ table, const int64_t* __restrict__ img_idx, const int64_t* __restrict__ pix_idx,
@@ -98,6 +116,19 @@ extern "C" int ncn_sample_ray_batch_ex(int strategy, int64_t* seed_dev, int n_ra
                                                                                      patch_size, max_expand, img_idx, pix_idx);
   NCN_LAUNCH_OK();
   sample_advance_kernel<<<1, 1, 0, as_stream(stream)>>>(seed_dev);
+  NCN_LAUNCH_OK();
+  return NCN_OK;
+}
+
+extern "C" int ncn_sample_random_pose_half(int strategy, const int64_t* seed_dev, int n_gt_rays, int n_random_poses, int64_t pose_offset,
+                                           int patch_size, int64_t* img_idx, int64_t* pix_idx, ncn_stream_t stream) {
+  NCN_CHECK_SIZE(n_gt_rays >= 0 && n_random_poses >= 1 && pose_offset >= 0 && strategy >= 0 && strategy <= 3);
+  if (strategy <= 1) NCN_CHECK_SIZE(patch_size >= 2);
+  if (n_gt_rays == 0) return NCN_OK;
+  NCN_CHECK_PTR(seed_dev); NCN_CHECK_PTR(img_idx); NCN_CHECK_PTR(pix_idx);
+  const int group = strategy <= 1 ? patch_size * patch_size : 3;
+  sample_random_half_kernel<<<(unsigned)ceil_div(n_gt_rays, 256), 256, 0, as_stream(stream)>>>(strategy, seed_dev, n_gt_rays, n_random_poses,
+                                                                                               pose_offset, group, img_idx, pix_idx);
   NCN_LAUNCH_OK();
   return NCN_OK;
 }

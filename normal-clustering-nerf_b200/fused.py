@@ -52,6 +52,14 @@ class FusedStep:
                 raise NotImplementedError(f"FusedStep: {k} > 0 is carried by the module path only (0 in every shipped experiment)")
         self.dev = dev = trainer.device
         self.R = R = self.hp["batch_size"]
+        # --random_tr_poses (datasets/base.py:106-126, train_nerf.py:169-172, losses.py:265-297): the batch is [n_gt rays of training
+        # views WITH a target colour | the same pixels seen from generated poses]; photometric / semantic terms on the first half,
+        # the opacity term on every ray, the normal-clustering terms on the second half only
+        self.rtp = bool(self.hp.get("random_tr_poses", False))
+        if self.rtp and R % 2:
+            raise RuntimeError("FusedStep: random_tr_poses needs an even batch_size (two halves of equal length)")
+        self.n_gt = R // 2 if self.rtp else R
+        self.u0 = self.n_gt if self.rtp else 0       # first ray of the set the geometric regularisers see (losses.py:286 unsup_start)
         self.use_graph = use_graph
         self.graph = None
         self.L = _lib.lib()
@@ -293,11 +301,15 @@ class FusedStep:
         self.d_depth.zero_()
         if self.dev_sampling is not None:    # BaseDataset.__getitem__ (datasets/base.py:94-183) on the device: indices + target gather
             sm = self.dev_sampling
-            ck(L.ncn_sample_ray_batch_ex(sm["strategy"], ptr(sm["seed"]), R, sm["n_poses"], sm["H"], sm["W"], sm["patch"], sm["max_expand"],
+            n_gt = self.n_gt                 # random_tr_poses: the drawn half; the other half repeats its pixels from generated poses
+            ck(L.ncn_sample_ray_batch_ex(sm["strategy"], ptr(sm["seed"]), n_gt, sm["n_poses"], sm["H"], sm["W"], sm["patch"], sm["max_expand"],
                                          ptr(self.b_img), ptr(self.b_pix), st), "sample_ray_batch")
-            ck(L.ncn_gather_pixels(ptr(sm["images"]), ptr(self.b_img), ptr(self.b_pix), R, sm["H"] * sm["W"], 3, ptr(self.target), st), "gather_rgb")
+            if self.rtp:
+                ck(L.ncn_sample_random_pose_half(sm["strategy"], ptr(sm["seed"]), n_gt, sm["n_random"], sm["n_poses"], sm["patch"],
+                                                 ptr(self.b_img), ptr(self.b_pix), st), "sample_random_pose_half")
+            ck(L.ncn_gather_pixels(ptr(sm["images"]), ptr(self.b_img), ptr(self.b_pix), n_gt, sm["H"] * sm["W"], 3, ptr(self.target), st), "gather_rgb")
             if sm["labels"] is not None:
-                ck(L.ncn_gather_pixels(ptr(sm["labels"]), ptr(self.b_img), ptr(self.b_pix), R, sm["H"] * sm["W"], 2, ptr(self.sem_target), st),
+                ck(L.ncn_gather_pixels(ptr(sm["labels"]), ptr(self.b_img), ptr(self.b_pix), n_gt, sm["H"] * sm["W"], 2, ptr(self.sem_target), st),
                    "gather_labels")
         if self.pix_inputs:                  # NeRFSystem.forward gather + get_rays (train_nerf.py:167-182) as the step's first node
             tr = self.tr
@@ -348,17 +360,18 @@ class FusedStep:
             ck(L.ncn_field_head_out(ptr(self.sem_out), 16, cap, n_dev, ptr(self.raws), Ct, self.sem_off, self.n_cls, st), "sem_head_out")
         # ---- compositing + losses (+ their gradients w.r.t. the rendered quantities; channels without a loss get a zero gradient)
         if self.fuse_photo and Ct in (3, 6, 9):      # ONE launch: the lane that finishes a ray also evaluates its photometric / opacity terms
-            ck(L.ncn_composite_train_fw_photometric(ptr(self.sigmas), ptr(self.raws), ptr(self.deltas), ptr(self.ts), ptr(self.rays_a), 1e-4, R, cap, Ct,
-                                                    ptr(self.total_samples), ptr(self.opacity), ptr(self.depth), ptr(self.rend), ptr(self.ws),
-                                                    ptr(self.target), self.bg, float(hp["loss_opacity_w"]), GSCALE, ptr(self.rgb), ptr(self.zeros),
-                                                    ptr(self.d_rend), ptr(self.d_opacity), st), "composite_fw_photometric")
+            ck(L.ncn_composite_train_fw_photometric_gt(ptr(self.sigmas), ptr(self.raws), ptr(self.deltas), ptr(self.ts), ptr(self.rays_a), 1e-4, R, cap,
+                                                       Ct, ptr(self.total_samples), ptr(self.opacity), ptr(self.depth), ptr(self.rend), ptr(self.ws),
+                                                       ptr(self.target), self.n_gt, self.bg, float(hp["loss_opacity_w"]), GSCALE, ptr(self.rgb),
+                                                       ptr(self.zeros), ptr(self.d_rend), ptr(self.d_opacity), st), "composite_fw_photometric")
         else:
             ck(L.ncn_composite_train_fw(ptr(self.sigmas), ptr(self.raws), ptr(self.deltas), ptr(self.ts), ptr(self.rays_a), 1e-4, R, cap, Ct,
                                         ptr(self.total_samples), ptr(self.opacity), ptr(self.depth), ptr(self.rend), ptr(self.ws), st), "composite_fw")
-            ck(L.ncn_photometric_loss(ptr(self.rend), ptr(self.opacity), ptr(self.target), R, Ct, self.bg, float(hp["loss_opacity_w"]), GSCALE,
-                                      ptr(self.rgb), ptr(self.zeros), ptr(self.d_rend), ptr(self.d_opacity), st), "photometric")
+            ck(L.ncn_photometric_loss_gt(ptr(self.rend), ptr(self.opacity), ptr(self.target), R, self.n_gt, Ct, self.bg, float(hp["loss_opacity_w"]),
+                                         GSCALE, ptr(self.rgb), ptr(self.zeros), ptr(self.d_rend), ptr(self.d_opacity), st), "photometric")
         if m.pred_sem and self.sem_w > 0:
-            ck(L.ncn_semantic_ce_loss(ptr(self.rend), Ct, self.sem_off, self.n_cls, ptr(self.sem_target), R, self.sem_w * GSCALE,
+            # pred['sem'][:gt_l] (losses.py:277): rays of generated poses keep the zero gradient the photometric pass wrote
+            ck(L.ncn_semantic_ce_loss(ptr(self.rend), Ct, self.sem_off, self.n_cls, ptr(self.sem_target), self.n_gt, self.sem_w * GSCALE,
                                       ptr(self.zeros[4:6]), ptr(self.d_rend), st), "semantic_ce")
         inv = 1.0 / GSCALE
         # Two independent branches from here (forked onto a side stream; inside a CUDA graph they become parallel
@@ -394,23 +407,25 @@ class FusedStep:
         if self.M > 0:
             x1, x2, x3 = ptr(self.tri[0]), ptr(self.tri[1]), ptr(self.tri[2])
             t_sim = 1.0 - float(hp["loss_norm_can_tres"])
-            # rays_o := rays_d (rendering.py:227 quirk)
+            # rays_o := rays_d (rendering.py:227 quirk).  The triangles index the rays from u0 on (all rays, or the generated-pose half)
+            u0 = self.u0
+            rd_u, depth_u, ddepth_u = ptr(self.rays_d[u0:]), ptr(self.depth[u0:]), ptr(self.d_depth[u0:])
             if self.fuse_chain and self.M <= 262144 and self.km_params.k <= 32:
                 # normals -> k-means -> selection -> cluster statistics + losses in ONE cluster launch, then dL/dnormals + dL/ddepth
-                ck(L.ncn_cluster_chain(ptr(self.rays_d), ptr(self.rays_d), ptr(self.depth), x1, x2, x3, self.M, C.byref(self.km_params), t_sim,
+                ck(L.ncn_cluster_chain(rd_u, rd_u, depth_u, x1, x2, x3, self.M, C.byref(self.km_params), t_sim,
                                        ptr(self.normals), ptr(self.centroids), ptr(self.assign), ptr(self.n_valid), ptr(self.labels), ptr(self.sel),
                                        ptr(self.losses), ptr(self.stats), ptr(self.km_ws), self.km_ws.numel(), st), "cluster_chain")
                 ck(L.ncn_cluster_bw_depth(ptr(self.normals), ptr(self.labels), self.M, ptr(self.stats), ptr(self.dev_sched[3:6]), ptr(self.dn),
-                                          ptr(self.rays_d), ptr(self.rays_d), ptr(self.depth), x1, x2, x3, ptr(self.d_depth), st), "cluster_bw_depth")
+                                          rd_u, rd_u, depth_u, x1, x2, x3, ddepth_u, st), "cluster_bw_depth")
             else:
-                ck(L.ncn_normals_from_depth_fw(ptr(self.rays_d), ptr(self.rays_d), ptr(self.depth), x1, x2, x3, self.M, ptr(self.normals), st), "normals_fw")
+                ck(L.ncn_normals_from_depth_fw(rd_u, rd_u, depth_u, x1, x2, x3, self.M, ptr(self.normals), st), "normals_fw")
                 ck(L.ncn_kmeans_spherical(ptr(self.normals), self.M, C.byref(self.km_params), ptr(self.centroids), ptr(self.assign),
                                           ptr(self.n_valid), ptr(self.km_ws), self.km_ws.numel(), st), "kmeans")
                 # selection + cluster losses (one single-CTA launch), dL/dnormals + dL/ddepth (one multi-CTA launch)
                 ck(L.ncn_cluster_tail(ptr(self.centroids), ptr(self.assign), self.M, 20, t_sim,
                                       ptr(self.labels), ptr(self.sel), ptr(self.normals), ptr(self.losses), ptr(self.stats),
-                                      ptr(self.dev_sched[3:6]), ptr(self.dn), ptr(self.rays_d), ptr(self.rays_d), ptr(self.depth),
-                                      x1, x2, x3, ptr(self.d_depth), st), "cluster_tail")
+                                      ptr(self.dev_sched[3:6]), ptr(self.dn), rd_u, rd_u, depth_u,
+                                      x1, x2, x3, ddepth_u, st), "cluster_tail")
         ck(L.ncn_composite_train_bw(ptr(self.d_opacity), ptr(self.d_depth), ptr(self.d_rend), None, ptr(self.sigmas), ptr(self.raws), ptr(self.ws),
                                     ptr(self.deltas), ptr(self.ts), ptr(self.rays_a), ptr(self.opacity), ptr(self.depth), ptr(self.rend), 1e-4,
                                     R, cap, Ct, ptr(self.d_sigmas), None, st), "composite_bw_sigma")
@@ -562,15 +577,19 @@ class FusedStep:
     def step(self, rays_o=None, rays_d=None, target_rgb=None, noise=None, packed=None, sem_target=None):
         """one training step.  Inputs are device tensors copied into the graph's static buffers: either
         rays_o/rays_d/target_rgb (R,3) each, or `packed` (3,R,3) = [rays_o, rays_d, rgb] (one copy), or nothing when the
-        caller filled self.inp in place (e.g. rays_from_pixels)."""
+        caller filled self.inp in place (e.g. rays_from_pixels).  With random_tr_poses the rays are [n_gt training-view rays |
+        n_gt rays of generated poses] and target_rgb / sem_target may be given for the first n_gt = R/2 rays only."""
         tr = self.tr
         self._poll()
         if packed is not None:
             self.inp.copy_(packed)
         elif rays_o is not None:
-            self.rays_o.copy_(rays_o); self.rays_d.copy_(rays_d); self.target.copy_(target_rgb)
+            self.rays_o.copy_(rays_o); self.rays_d.copy_(rays_d)
+            if target_rgb.shape[0] not in (self.n_gt, self.R):
+                raise RuntimeError(f"FusedStep.step: target_rgb has {target_rgb.shape[0]} rows, expected {self.n_gt}")
+            self.target[:target_rgb.shape[0]].copy_(target_rgb)
         if sem_target is not None:
-            self.sem_target.copy_(sem_target)
+            self.sem_target[:sem_target.shape[0]].copy_(sem_target)
         if (noise is None) != self.gen_noise:
             self.gen_noise = noise is None
             self.graph = None                 # noise source is part of the captured sequence
@@ -720,13 +739,22 @@ class FusedStep:
                 raise RuntimeError("use_device_sampling: sem_labels given but the model has no semantic head")
             sem_labels = sem_labels.to(self.dev, torch.int64).contiguous()
         self.use_pixel_batches(True)
-        if self.tr.hp.get("random_tr_poses", False):
-            raise NotImplementedError("use_device_sampling: random_tr_poses (half of the batch from generated poses, datasets/base.py:106-126, "
-                                      "235-263) is carried by the host data path only")
+        n_random = 0
+        if self.rtp:
+            # the generated poses follow the P training poses in the trainer's pose table (trainer.set_cameras(random_poses=...)),
+            # as in the reference's torch.cat((poses, random_poses[rnd_img_idxs])) (train_nerf.py:170)
+            n_random = int(getattr(self.tr, "n_random_poses", 0))
+            if n_random < 1 or int(self.tr.n_train_poses) != P:
+                raise RuntimeError("use_device_sampling: random_tr_poses needs trainer.set_cameras(poses, directions, random_poses=...) with as "
+                                   "many training poses as images")
+            group = patch_size * patch_size if strategy.endswith("patch") else 3
+            if self.n_gt % group:
+                raise RuntimeError(f"use_device_sampling: random_tr_poses needs batch_size / 2 to be a whole number of {group}-ray groups")
         self.dev_sampling = dict(images=images, labels=sem_labels, H=int(height), W=int(width), n_poses=P, patch=int(patch_size),
                                  max_expand=int(max_expand),      # triang_max_expand of the triangle strategies (base.py:130-141)
+                                 n_random=n_random,
                                  strategy=self.STRATEGIES[strategy], seed=torch.full((1,), int(seed), dtype=torch.int64, device=self.dev))
-        self.set_triangles(self.batch_triangles(self.R, strategy, patch_size))
+        self.set_triangles(self.batch_triangles(self.R - self.u0, strategy, patch_size))
         self.graph = None
 
     @staticmethod
@@ -743,8 +771,15 @@ class FusedStep:
         return (base + offs.view(3, 1, -1)).reshape(3, -1).contiguous()
 
     @staticmethod
-    def pack_pixel_batch(img_idx, pix_idx, rgb, pin=True):
-        """host-side record for step_pixels: uint8 (R*28) = [img_idx i64 | pix_idx i64 | rgb f32]"""
+    def pack_pixel_batch(img_idx, pix_idx, rgb, pin=True, rnd_img_idx=None, n_train_poses=None):
+        """host-side record for step_pixels: uint8 (R*28) = [img_idx i64 | pix_idx i64 | rgb f32].
+        random_tr_poses: pass the batch of the training views (n_gt rows) plus rnd_img_idx (n_gt) and n_train_poses; the record
+        then holds R = 2 n_gt rows - the same pixels again with image index n_train_poses + rnd_img_idx (the row of the generated
+        pose in trainer.poses, train_nerf.py:169-172) and zero colours that no loss term reads."""
+        if rnd_img_idx is not None:
+            img_idx = torch.cat([img_idx.to(torch.int64), rnd_img_idx.to(torch.int64) + int(n_train_poses)])
+            pix_idx = torch.cat([pix_idx.to(torch.int64), pix_idx.to(torch.int64)])
+            rgb = torch.cat([rgb.to(torch.float32), torch.zeros_like(rgb, dtype=torch.float32)])
         rec = torch.cat([img_idx.to(torch.int64).contiguous().view(torch.uint8).reshape(-1),
                          pix_idx.to(torch.int64).contiguous().view(torch.uint8).reshape(-1),
                          rgb.to(torch.float32).contiguous().view(torch.uint8).reshape(-1)])
@@ -873,7 +908,7 @@ class FusedStep:
         torch.cuda.synchronize()
         R = self.R
         z = self.zeros.cpu()
-        d = {"rgb": float(z[0]) / (3 * R), "opacity": float(self.hp["loss_opacity_w"]) * float(z[1]) / R}
+        d = {"rgb": float(z[0]) / (3 * self.n_gt), "opacity": float(self.hp["loss_opacity_w"]) * float(z[1]) / R}
         if self.M > 0:
             l = torch.nan_to_num(self.losses.cpu())
             w = self.dev_sched[3:6].cpu() / GSCALE

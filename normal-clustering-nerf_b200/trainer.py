@@ -332,8 +332,17 @@ class NeRFTrainer:
                         dist.broadcast(buf[lo:hi], q)
 
     # dataset tensors that NeRFSystem keeps on the device (train_nerf.py:239-240)
-    def set_cameras(self, poses, directions):
-        self.poses = torch.as_tensor(poses, dtype=torch.float32, device=self.device)
+    def set_cameras(self, poses, directions, random_poses=None):
+        """poses (P,3,4), directions (H*W,3); random_poses (Q,3,4) = the generated poses of --random_tr_poses
+        (ncn_b200.batches.generate_random_poses; NeRFSystem keeps them in a buffer of their own, train_nerf.py:241-242) are
+        appended behind the training poses, so one pose table serves both halves of a batch: image index P + q = generated pose q"""
+        poses = torch.as_tensor(poses, dtype=torch.float32, device=self.device)[:, :3, :]
+        self.n_train_poses, self.n_random_poses = int(poses.shape[0]), 0
+        if random_poses is not None:
+            rp = torch.as_tensor(random_poses, dtype=torch.float32, device=self.device)[:, :3, :]
+            self.n_random_poses = int(rp.shape[0])
+            poses = torch.cat([poses, rp], 0)
+        self.poses = poses.contiguous()
         self.directions = torch.as_tensor(directions, dtype=torch.float32, device=self.device)
 
     def rays_from_batch(self, img_idxs, pix_idxs):

@@ -355,3 +355,61 @@ def test_mark_invisible_cells_reference_vs_mirror(ref, variant):
         assert torch.equal(rm.count_grid, tr.model.count_grid)
         frac = float((rm.density_grid < 0).float().mean())
         assert 0.02 < frac < 0.98, frac                                                   # both outcomes occur
+
+
+# ------------------------------------------------------------------ f4: --random_tr_poses
+def _batch_rtp(R):
+    """[R/2 rays of training views with a target colour | R/2 rays of other (generated) poses], patch topology in both halves"""
+    ro_a, rd_a, tri, rgb, target = _batch(R // 2, seed=0)
+    ro_b, rd_b, _, _, _ = _batch(R // 2, seed=5)
+    return torch.cat([ro_a, ro_b]).contiguous(), torch.cat([rd_a, rd_b]).contiguous(), tri, rgb, target
+
+
+def test_random_tr_poses_reference_vs_mirror_vs_fused(ref):
+    """--random_tr_poses (losses.py:265-297, train_nerf.py:169-172, 338-344): photometric term on the first half of the batch only,
+    opacity on every ray, the normal-clustering terms on the rays of the generated poses only.  The reference's own render +
+    NeRFMTLoss on the shims is the oracle for the module-path mirror and for FusedStep (n_gt / u0 split, ncn_*_gt kernels)."""
+    R = 2048
+    hp = dict(HP, random_tr_poses=True)
+    tr = _trainer(R, hp=dict(random_tr_poses=True))
+    rm = _ref_model(ref, tr)
+    rays_o, rays_d, tri, rgb, target = _batch_rtp(R)
+    assert rgb.shape[0] == R // 2 and int(tri.max()) == R // 2 - 1
+    res_r, loss_r, g_ref = _ref_forward_backward(ref, rm, hp, rays_o, rays_d, target, dict(tr.render_kwargs), tr.global_step)
+    # module-path mirror
+    torch.manual_seed(123)
+    res_o, loss_o = tr.forward_loss(rays_o, rays_d, target)
+    (loss_o["total"] * tr.hp["loss_scale"]).backward()
+    g_our = {k: (p.grad / tr.hp["loss_scale"]).clone() for k, p in tr.model.named_parameters() if p.numel()}
+    tr.opt.grad.zero_()
+    for k in loss_o:
+        a, b = float(loss_r[k]), float(loss_o[k])
+        assert abs(a - b) <= 1e-3 * abs(a) + 1e-8, (k, a, b)
+    for k, gr in g_ref.items():
+        if gr.numel():
+            assert float(gr.norm()) > 0 and _rel(g_our[k], gr) <= 2e-2, (k, _rel(g_our[k], gr))
+    # the split matters: the loss over ALL rays against an R-row target would differ
+    assert res_r["rgb"].shape[0] == R
+    # fused step
+    torch.manual_seed(123)
+    noise = torch.rand(R, device="cuda")
+    fs = tr.fused_step(use_graph=False)
+    assert fs.rtp and fs.n_gt == R // 2 and fs.u0 == R // 2
+    fs.set_triangles(tri)
+    fs.gen_noise = False
+    fs.rays_o.copy_(rays_o); fs.rays_d.copy_(rays_d); fs.target[:R // 2].copy_(rgb); fs.target[R // 2:].fill_(123.0)      # never read
+    fs.noise.copy_(noise)
+    fs._schedule()
+    fs._run()
+    torch.cuda.synchronize()
+    assert int(fs.counter[0]) == int(res_r["rm_samples"]) and torch.equal(fs.rays_a, res_r["rays_a"])
+    torch.testing.assert_close(fs.depth, res_r["depth"].detach(), rtol=1e-4, atol=1e-5)
+    d, n = fs.stats_host()
+    for k in ("rgb", "opacity", "norm_D_C_ort_dot", "norm_D_C_centr_dot", "norm_D_C_centr_L1"):
+        assert abs(d[k] - float(loss_r[k])) <= 2e-3 * abs(float(loss_r[k])) + 1e-7, (k, d[k], float(loss_r[k]))
+    assert float(fs.d_rend[R // 2:].abs().max()) == 0.0 and float(fs.d_rend[:R // 2].abs().max()) > 0      # no colour gradient on the generated half
+    assert float(fs.d_depth[:R // 2].abs().max()) == 0.0 and float(fs.d_depth[R // 2:].abs().max()) > 0    # no cluster gradient on the training half
+    for name in ("rgb_net", "sigma_net", "xyz_encoder"):
+        o, k = fs.off[name]
+        rel = _rel(tr.opt.grad[o:o + k], g_ref[name + ".params"])
+        assert rel <= 3e-2, (name, rel)
