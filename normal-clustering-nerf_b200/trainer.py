@@ -395,7 +395,7 @@ class NeRFTrainer:
         """public end-to-end entry: (image, pixel) indices + target colours on the device -> one fused training step"""
         fs = self.fused_step()
         fs.rays_from_pixels(img_idx, pix_idx)
-        fs.target.copy_(target_rgb)
+        fs.target[:target_rgb.shape[0]].copy_(target_rgb)      # random_tr_poses: colours exist for the first half of the rays only
         self.train_step_fused(update_grid=update_grid, grid_restore=grid_restore)
 
     def train_step(self, rays_o, rays_d, target, update_grid=True):

@@ -368,13 +368,14 @@ def _batch_rtp(R):
 def test_random_tr_poses_reference_vs_mirror_vs_fused(ref):
     """--random_tr_poses (losses.py:265-297, train_nerf.py:169-172, 338-344): photometric term on the first half of the batch only,
     opacity on every ray, the normal-clustering terms on the rays of the generated poses only.  The reference's own render +
-    NeRFMTLoss on the shims is the oracle for the module-path mirror and for FusedStep (n_gt / u0 split, ncn_*_gt kernels)."""
-    R = 2048
+    NeRFMTLoss on the shims is the oracle for the module-path mirror and for FusedStep (n_gt / u0 split, ncn_*_gt kernels).
+    R = 4096: the generated-pose half yields the 1568 normals of the R = 2048 tests above (same k-means regime)."""
+    R = 4096
     hp = dict(HP, random_tr_poses=True)
     tr = _trainer(R, hp=dict(random_tr_poses=True))
     rm = _ref_model(ref, tr)
     rays_o, rays_d, tri, rgb, target = _batch_rtp(R)
-    assert rgb.shape[0] == R // 2 and int(tri.max()) == R // 2 - 1
+    assert rgb.shape[0] == R // 2 and int(tri.max()) < R // 2
     res_r, loss_r, g_ref = _ref_forward_backward(ref, rm, hp, rays_o, rays_d, target, dict(tr.render_kwargs), tr.global_step)
     # module-path mirror
     torch.manual_seed(123)
