@@ -147,6 +147,7 @@ ALGO = {  # algorithmic bytes (or flops) per unit, SURVEY.md section 8d / DESIGN
     "ncn_adam_step": ("hbm", "param", 34.0), "ncn_adam_step_groups": ("hbm", "param", 34.0), "ncn_grad_sumsq": ("hbm", "param", 4.0),
     "ncn_composite_train_fw": ("hbm", "sample", 28.0), "ncn_composite_train_bw": ("hbm", "sample", 48.0),
     "ncn_composite_train_fw_photometric": ("hbm", "sample", 28.0),      # + 56 B/ray of loss terms (negligible against 28 B x 33 samples)
+    "ncn_composite_train_fw_photometric_gt": ("hbm", "sample", 28.0),   # the random_tr_poses form of the same launch
     "ncn_march_train_expand": ("hbm", "sample", 36.0),
     # tcgen05 MLP backward, two launches per step (colour head 448 B/sample, density trunk 288 B/sample): average per launch
     "ncn_mlp_bwd_src_fused": ("hbm", "sample", 368.0), "ncn_mlp_bwd": ("hbm", "sample", 368.0),

@@ -359,16 +359,23 @@ class FusedStep:
             ck(L.ncn_mlp_fwd(C.byref(m.sem_net.desc), ptr(self.h), ptr(self._w16("sem_net")), cap, ptr(self.sem_out), ptr(self.sem_acts), n_dev, st), "sem_fwd")
             ck(L.ncn_field_head_out(ptr(self.sem_out), 16, cap, n_dev, ptr(self.raws), Ct, self.sem_off, self.n_cls, st), "sem_head_out")
         # ---- compositing + losses (+ their gradients w.r.t. the rendered quantities; channels without a loss get a zero gradient)
+        # random_tr_poses: the *_gt entry points (target colours on the first n_gt rays only); otherwise the plain ones (n_gt = R)
         if self.fuse_photo and Ct in (3, 6, 9):      # ONE launch: the lane that finishes a ray also evaluates its photometric / opacity terms
-            ck(L.ncn_composite_train_fw_photometric_gt(ptr(self.sigmas), ptr(self.raws), ptr(self.deltas), ptr(self.ts), ptr(self.rays_a), 1e-4, R, cap,
-                                                       Ct, ptr(self.total_samples), ptr(self.opacity), ptr(self.depth), ptr(self.rend), ptr(self.ws),
-                                                       ptr(self.target), self.n_gt, self.bg, float(hp["loss_opacity_w"]), GSCALE, ptr(self.rgb),
-                                                       ptr(self.zeros), ptr(self.d_rend), ptr(self.d_opacity), st), "composite_fw_photometric")
+            head = (ptr(self.sigmas), ptr(self.raws), ptr(self.deltas), ptr(self.ts), ptr(self.rays_a), 1e-4, R, cap, Ct, ptr(self.total_samples),
+                    ptr(self.opacity), ptr(self.depth), ptr(self.rend), ptr(self.ws), ptr(self.target))
+            tail = (self.bg, float(hp["loss_opacity_w"]), GSCALE, ptr(self.rgb), ptr(self.zeros), ptr(self.d_rend), ptr(self.d_opacity), st)
+            if self.rtp:
+                ck(L.ncn_composite_train_fw_photometric_gt(*head, self.n_gt, *tail), "composite_fw_photometric")
+            else:
+                ck(L.ncn_composite_train_fw_photometric(*head, *tail), "composite_fw_photometric")
         else:
             ck(L.ncn_composite_train_fw(ptr(self.sigmas), ptr(self.raws), ptr(self.deltas), ptr(self.ts), ptr(self.rays_a), 1e-4, R, cap, Ct,
                                         ptr(self.total_samples), ptr(self.opacity), ptr(self.depth), ptr(self.rend), ptr(self.ws), st), "composite_fw")
-            ck(L.ncn_photometric_loss_gt(ptr(self.rend), ptr(self.opacity), ptr(self.target), R, self.n_gt, Ct, self.bg, float(hp["loss_opacity_w"]),
-                                         GSCALE, ptr(self.rgb), ptr(self.zeros), ptr(self.d_rend), ptr(self.d_opacity), st), "photometric")
+            tail = (Ct, self.bg, float(hp["loss_opacity_w"]), GSCALE, ptr(self.rgb), ptr(self.zeros), ptr(self.d_rend), ptr(self.d_opacity), st)
+            if self.rtp:
+                ck(L.ncn_photometric_loss_gt(ptr(self.rend), ptr(self.opacity), ptr(self.target), R, self.n_gt, *tail), "photometric")
+            else:
+                ck(L.ncn_photometric_loss(ptr(self.rend), ptr(self.opacity), ptr(self.target), R, *tail), "photometric")
         if m.pred_sem and self.sem_w > 0:
             # pred['sem'][:gt_l] (losses.py:277): rays of generated poses keep the zero gradient the photometric pass wrote
             ck(L.ncn_semantic_ce_loss(ptr(self.rend), Ct, self.sem_off, self.n_cls, ptr(self.sem_target), self.n_gt, self.sem_w * GSCALE,

@@ -18,7 +18,7 @@ COLS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
 # C-ABI call name (bench.py's ALGO keys) <- kernel name fragment
 CALLS = {"ncn_grid_bwd": "grid_bwd_merge_kernel", "ncn_grid_fwd": "grid_fwd_coherent_kernel", "ncn_field_mlp_fwd": "field_mlp_fwd_tc05_kernel",
          "ncn_mlp_bwd_src_fused": "mlp_bwd_tc05_kernel", "ncn_adam_step_groups": "adam_kernel", "ncn_adam_step": "adam_kernel",
-         "ncn_grad_sumsq": "sumsq_kernel", "ncn_composite_train_fw_photometric": "composite_train_fw_sw_kernel",
+         "ncn_grad_sumsq": "sumsq_kernel", "ncn_composite_train_fw_photometric": "composite_train_fw_sw_kernel", "ncn_composite_train_fw_photometric_gt": "composite_train_fw_sw_kernel",
          "ncn_composite_train_fw": "composite_train_fw_sw_kernel", "ncn_composite_train_bw": "composite_train_bw_sw_kernel",
          "ncn_march_train_expand": "march_train_expand_kernel", "ncn_cluster_chain": "kmeans_kernel"}
 
