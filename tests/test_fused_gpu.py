@@ -407,7 +407,9 @@ def test_device_batch_sampling_triangle_expansion(strategy, expand):
 
 def test_programmatic_dependent_launch_changes_no_result():
     """ncn_set_pdl(0/1): the forward of one eager fused step (everything up to the losses is deterministic: no atomics) is
-    bit-identical with and without programmatic dependent launch, and so is a CUDA-graph replay of it"""
+    bit-identical with and without programmatic dependent launch, and so is a CUDA-graph replay of it.  dL/dsigma sits behind
+    dL/ddepth, which the normals' backward accumulates with fp32 atomics (up to three triangles meet in a ray, in any order), so it
+    is reproducible to rounding only - a missed dependency would show as whole missing contributions, far above that bound."""
     from ncn_b200 import _lib
     L = _lib.lib()
     outs = {}
@@ -428,6 +430,7 @@ def test_programmatic_dependent_launch_changes_no_result():
     ref = outs[(0, False)]
     assert ref[5] > 1024 and torch.isfinite(ref[3]).all()
     for mode, got in outs.items():
-        for a, b in zip(ref[:5], got[:5]):
+        for a, b in zip(ref[:4], got[:4]):
             assert torch.equal(a, b), mode
         assert got[5] == ref[5]
+        torch.testing.assert_close(got[4], ref[4], rtol=1e-5, atol=1e-6 * float(ref[4].abs().max()), msg=lambda m, mode=mode: f"{mode}: {m}")
