@@ -433,4 +433,4 @@ def test_programmatic_dependent_launch_changes_no_result():
         for a, b in zip(ref[:4], got[:4]):
             assert torch.equal(a, b), mode
         assert got[5] == ref[5]
-        torch.testing.assert_close(got[4], ref[4], rtol=1e-5, atol=1e-6 * float(ref[4].abs().max()), msg=lambda m, mode=mode: f"{mode}: {m}")
+        torch.testing.assert_close(got[4], ref[4], rtol=1e-4, atol=1e-5 * float(ref[4].abs().max()), msg=lambda m, mode=mode: f"{mode}: {m}")
