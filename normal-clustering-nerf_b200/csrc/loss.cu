@@ -102,7 +102,10 @@ normals_bw_kernel(const float* __restrict__ origin, const float* __restrict__ di
 // integer reduction (redux.sync; fixed point 2^20 => order independent => bit-reproducible), publishes its K x 4
 // partial sums in its own shared memory, and after one barrier.cluster every CTA folds all 8 partials through
 // distributed shared memory and updates the (replicated) centroids.  No atomics, no host round trip.
-constexpr int kKmThreads = 512;     // 16 warps: with a 16-CTA cluster a warp owns 1-2 sixteen-point tiles per Lloyd iteration
+#ifndef NCN_KM_THREADS
+#define NCN_KM_THREADS 512           // 16 warps: with a 16-CTA cluster a warp owns 1-2 sixteen-point tiles per Lloyd iteration
+#endif                               // (-DNCN_KM_THREADS=640: 20 warps = one tile per warp at 5120 training points; A/B build)
+constexpr int kKmThreads = NCN_KM_THREADS;
 constexpr int kKmCluster = 8;        // portable cluster size (fallback)
 constexpr int kKmClusterMax = 16;    // non-portable size tried first: half the tiles per CTA and Lloyd iteration
 constexpr int kKmMaxK = 64;
@@ -339,10 +342,13 @@ kmeans_kernel(const float* __restrict__ x_in, int64_t n, ncn_kmeans_params p, fl
   extern __shared__ __align__(16) unsigned char km_smem[];
   float* xs = reinterpret_cast<float*>(km_smem);                 // this CTA's training points [my_n][3]
   __shared__ float s_c[kKmMaxK * 3];
-  __shared__ int s_wacc[(kKmThreads / 32) * kKmMaxK * 4];        // per-warp private accumulators
+  // per-warp private accumulators (integer Lloyd path, epilogue) and the tensor-core path's per-warp (32 clusters x 8) partial
+  // sums are never live at the same time (block barriers in between): one array
+  constexpr int kWaccInts = (kKmThreads / 32) * kKmMaxK * 4, kFwFloats = (kKmThreads / 32) * 32 * 8;
+  __shared__ __align__(16) int s_wacc[kWaccInts > kFwFloats ? kWaccInts : kFwFloats];
   __shared__ int s_part[2][kKmMaxK * 4];                         // this CTA's partial sums (double buffered), read by peers
   __shared__ float s_acc[kKmMaxK * 4];
-  __shared__ float s_fw[(kKmThreads / 32) * 32 * 8];             // tensor-core path: per-warp (32 clusters x 8) partial sums
+  float* s_fw = reinterpret_cast<float*>(s_wacc);
   __shared__ float s_fpart[2][32 * 8];                           // this CTA's partial sums (double buffered), read by peers
   __shared__ int s_nvalid, s_warp_tot[32], s_base, s_any_empty;
   __shared__ __align__(8) uint64_t s_mbar[2];                    // completion of the two exchange inboxes (double buffered)
