@@ -116,3 +116,63 @@ def sample_batch_indices(strategy, batch_size, n_poses, height, width, patch_siz
         x3 = np.where((x3 - e) // W == x3 // W, x3 - e, x3)
     out["pix_idxs"] = np.stack([x1, x2, x3], axis=1).reshape(-1)
     return out
+
+
+class HostBatcher:
+    """What a DataLoader worker of the reference does per step (BaseDataset.__getitem__, datasets/base.py:94-183, training split),
+    in the form the fused step consumes: draw the batch indices (sample_batch_indices), gather the target colours (and labels)
+    from HOST-resident images, and write ONE packed record - [img_idx i64 (R) | pix_idx i64 (R) | rgb f32 (R,3)], 28 bytes per ray,
+    FusedStep.step_pixels / pack_pixel_batch - into a ring of pinned buffers, so the step needs a single host->device copy and the
+    host can prepare record i+1 while the copy of record i is in flight (ring >= 2).
+
+    images (P, H*W, 3) float32 (the reference's `self.rays[..., :3]`); labels: optional (P, H*W) integer map gathered for the
+    training-view rays (e.g. `semantics`).  With random_tr_poses the record holds [training views | the same pixels with image index
+    n_poses + rnd_img_idx] (the generated poses follow the training poses in trainer.set_cameras(random_poses=...))."""
+
+    def __init__(self, images, height, width, strategy, batch_size, patch_size=8, max_expand=0, random_tr_poses=False, n_random_poses=0,
+                 labels=None, ring=4, rng=None, pin=None):
+        self.images = torch.as_tensor(images, dtype=torch.float32)
+        P = self.images.shape[0]
+        if self.images.shape != (P, height * width, 3):
+            raise ValueError("HostBatcher: images must be (P, H*W, 3)")
+        if strategy not in STRATEGIES:
+            raise ValueError(f"HostBatcher: unknown ray_sampling_strategy {strategy!r}")
+        if random_tr_poses and ("triang" not in strategy or n_random_poses < 1):      # asserted by the reference (base.py:98-102)
+            raise ValueError("HostBatcher: random_tr_poses needs a triangle / patch strategy and generated poses")
+        self.labels = None if labels is None else torch.as_tensor(labels)
+        self.args = dict(strategy=strategy, batch_size=int(batch_size), n_poses=P, height=int(height), width=int(width),
+                         patch_size=int(patch_size), max_expand=int(max_expand), random_tr_poses=bool(random_tr_poses),
+                         n_random_poses=int(n_random_poses))
+        self.rng = np.random if rng is None else rng
+        probe = sample_batch_indices(rng=np.random.RandomState(0), **self.args)
+        self.n_gt = len(probe["pix_idxs"])
+        self.n_rays = self.n_gt * (2 if random_tr_poses else 1)          # rows of the record = FusedStep's batch_size
+        pin = torch.cuda.is_available() if pin is None else pin
+        self.ring = [torch.zeros(self.n_rays * 28, dtype=torch.uint8, pin_memory=pin) for _ in range(max(1, int(ring)))]
+        self.pos = 0
+        self.last = None
+
+    def views(self, rec):
+        """(img_idx (R) i64, pix_idx (R) i64, rgb (R,3) f32) views into a record"""
+        R = self.n_rays
+        return rec[:8 * R].view(torch.int64), rec[8 * R:16 * R].view(torch.int64), rec[16 * R:].view(torch.float32).view(R, 3)
+
+    def next(self):
+        """-> (record, labels of the training-view rays or None).  The record is a slot of the ring: it is overwritten `ring` calls
+        later, so at most ring - 1 copies may be in flight."""
+        s = sample_batch_indices(rng=self.rng, **self.args)
+        self.last = s
+        rec = self.ring[self.pos % len(self.ring)]
+        self.pos += 1
+        b_img, b_pix, b_rgb = self.views(rec)
+        n = self.n_gt
+        img = torch.from_numpy(np.ascontiguousarray(np.broadcast_to(s["img_idxs"], (n,)).astype(np.int64)))
+        pix = torch.from_numpy(np.ascontiguousarray(s["pix_idxs"].astype(np.int64)))
+        b_img[:n] = img; b_pix[:n] = pix
+        torch.index_select(self.images.view(-1, 3), 0, img * self.images.shape[1] + pix, out=b_rgb[:n])
+        if self.args["random_tr_poses"]:
+            b_img[n:] = torch.from_numpy(s["rnd_img_idxs"].astype(np.int64)) + self.args["n_poses"]
+            b_pix[n:] = pix
+            b_rgb[n:] = 0.0
+        lab = None if self.labels is None else self.labels[img, pix]
+        return rec, lab

@@ -77,3 +77,39 @@ def test_batch_triangles_of_the_unsupervised_half():
     from ncn_b200.fused import FusedStep
     t = FusedStep.batch_triangles(4096, "all_images_triang_patch", 8)
     assert t.shape == (3, 64 * 49) and int(t.max()) == 4095 and int(t.min()) == 1      # ray 0 (a patch corner) is no triangle vertex
+
+
+def test_host_batcher_records():
+    """HostBatcher = the DataLoader-worker half of a step (BaseDataset.__getitem__): the packed record equals pack_pixel_batch of the
+    reference-pinned index draw, targets are gathered from the images, the ring rotates, random_tr_poses appends the generated half"""
+    import ncn_b200  # noqa: F401
+    from ncn_b200 import batches
+    from ncn_b200.fused import FusedStep
+    H, W, P, Q, B = 24, 32, 5, 37, 768
+    g = torch.Generator().manual_seed(0)
+    images = torch.rand(P, H * W, 3, generator=g)
+    labels = torch.randint(0, 4, (P, H * W), generator=g)
+    for strategy, rtp in (("all_images_triang_patch", False), ("all_images_triang_patch", True), ("same_image_triang", True),
+                          ("all_images", False)):
+        hb = batches.HostBatcher(images, H, W, strategy, B, patch_size=8, random_tr_poses=rtp, n_random_poses=Q, labels=labels, ring=2,
+                                 rng=np.random.RandomState(11), pin=False)
+        want = batches.sample_batch_indices(strategy, B, P, H, W, patch_size=8, random_tr_poses=rtp, n_random_poses=Q,
+                                            rng=np.random.RandomState(11))
+        rec, lab = hb.next()
+        n = len(want["pix_idxs"])
+        assert hb.n_gt == n and hb.n_rays == (2 * n if rtp else n) and rec.numel() == hb.n_rays * 28
+        img = torch.from_numpy(np.broadcast_to(want["img_idxs"], (n,)).astype(np.int64).copy()); pix = torch.from_numpy(want["pix_idxs"].astype(np.int64))
+        ref = FusedStep.pack_pixel_batch(img, pix, images[img, pix], pin=False,
+                                         rnd_img_idx=torch.from_numpy(want["rnd_img_idxs"].astype(np.int64)) if rtp else None, n_train_poses=P)
+        assert torch.equal(rec, ref)
+        assert torch.equal(lab, labels[img, pix])
+        rec2, _ = hb.next()
+        assert rec2.data_ptr() != rec.data_ptr() and not torch.equal(rec2, ref)      # next slot of the ring, a fresh draw
+        rec3, _ = hb.next()
+        assert rec3.data_ptr() == rec.data_ptr()                                     # ring of 2
+    for bad in (dict(strategy="nope"), dict(strategy="all_images", random_tr_poses=True, n_random_poses=3)):
+        try:
+            batches.HostBatcher(images, H, W, batch_size=B, pin=False, **bad)
+            raise AssertionError("expected ValueError")
+        except ValueError:
+            pass
