@@ -167,3 +167,45 @@ def test_graph_step_fed_by_the_device_sampler_with_random_poses():
     d, n_s = fs.stats_host()
     assert all(np.isfinite(v) for v in d.values()) and n_s > R and d["rgb"] > 0 and "norm_D_C_centr_dot" in d
     assert float((tr.opt.flat - p0).abs().max()) > 0                   # the optimizer moved the parameters
+
+
+def test_host_batcher_feeds_step_pixels():
+    """the host data path of random_tr_poses end to end: HostBatcher (reference index draw + target gather + pinned record) ->
+    FusedStep.step_pixels (one H2D copy + one graph replay); the step sees exactly the batch the host drew"""
+    import ncn_b200  # noqa: F401
+    from ncn_b200 import batches, synth, vren
+    from ncn_b200.trainer import NeRFTrainer
+    R, P, Q, H, W = 1024, 6, 40, 768, 1024
+    torch.manual_seed(5)
+    tr = NeRFTrainer(dict(batch_size=R, random_tr_poses=True), device="cuda")
+    grid = synth.density_grid_from_occupancy(synth.room_occupancy(128, 0.5, seed=0))
+    tr.model.density_grid.copy_(torch.from_numpy(grid).cuda())
+    vren.packbits(tr.model.density_grid, 5.9, tr.model.density_bitfield)
+    n = tr.model.xyz_encoder.params.numel()
+    tr.opt.flat[:n].copy_(torch.randn(n, device="cuda", generator=torch.Generator(device="cuda").manual_seed(1)) * 0.3)
+    tr.opt.flat16.copy_(tr.opt.flat)
+    tr.global_step = 3000
+    poses = synth.camera_poses(P, 0)
+    rnd_poses, _ = batches.generate_random_poses(poses, poses[:, :3, 3].min(0), poses[:, :3, 3].max(0), Q, rng=np.random.RandomState(0))
+    tr.set_cameras(torch.from_numpy(poses), torch.from_numpy(synth.pixel_directions("hypersim")).cuda(), random_poses=rnd_poses)
+    images = torch.rand(P, H * W, 3, generator=torch.Generator().manual_seed(0))
+    strategy = "all_images_triang_patch"
+    hb = batches.HostBatcher(images, H, W, strategy, R, patch_size=8, random_tr_poses=True, n_random_poses=Q, ring=3,
+                             rng=np.random.RandomState(3))
+    assert hb.n_rays == R and hb.n_gt == R // 2 and hb.ring[0].is_pinned()
+    fs = tr.fused_step(use_graph=True)
+    fs.use_pixel_batches(True)
+    fs.set_triangles(fs.batch_triangles(R - fs.u0, strategy, 8))
+    for it in range(3):
+        rec, _ = hb.next()
+        fs.step_pixels(rec)
+        torch.cuda.synchronize()
+        img, pix, rgb = hb.views(rec)
+        assert torch.equal(fs.b_img.cpu(), img) and torch.equal(fs.b_pix.cpu(), pix)
+        assert torch.equal(fs.target[:R // 2].cpu(), images[img[:R // 2], pix[:R // 2]])
+        assert int(img[R // 2:].min()) >= P and torch.equal(pix[R // 2:], pix[:R // 2])
+        ro, rd = tr.rays_from_batch(fs.b_img, fs.b_pix)
+        torch.testing.assert_close(fs.rays_o, ro, rtol=0, atol=0)
+        torch.testing.assert_close(fs.rays_d, rd, rtol=1e-6, atol=1e-7)
+    d, n_s = fs.stats_host()
+    assert all(np.isfinite(v) for v in d.values()) and n_s > R and d["rgb"] > 0
